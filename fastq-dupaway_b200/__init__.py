@@ -1,0 +1,347 @@
+"""fastq-dupaway_b200 - Python binding (ctypes) of libfqd_cuda.so, the B200 deduplication engine.
+
+This module is test / benchmark plumbing over the C ABI declared in include/fqd.h; the drop-in product is the
+C++ command line in fastq-dupaway_b200/host (same flags as the reference, src/main.cpp:40-179).  It mirrors the
+reference's in-process seam (HashDupRemover / SeqDupRemover, src/hash_dup_remover.hpp:73-94,
+src/seq_dup_remover.hpp:12-38) on byte buffers so that parity tests read like the reference's own tests.
+
+There is no CPU fallback: if libfqd_cuda.so is missing or no CUDA device is usable, calls raise.
+Import with importlib.import_module("fastq-dupaway_b200") (the directory name is not a Python identifier).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+HERE = Path(__file__).resolve().parent
+CSRC = HERE / "csrc"
+LIB_PATH = CSRC / "libfqd_cuda.so"
+HEADER = HERE.parent / "include" / "fqd.h"
+
+FQD_ABI_VERSION = 1
+FORMAT_FASTQ, FORMAT_FASTA = 0, 1
+MODE_FAST, MODE_SEQ_TIGHT, MODE_SEQ_LOOSE, MODE_SEQ_HAMMING = 0, 1, 2, 3
+MODE_BY_NAME = {"fast": MODE_FAST, "tight": MODE_SEQ_TIGHT, "loose": MODE_SEQ_LOOSE, "tail-hamming": MODE_SEQ_HAMMING}
+
+STATUS = {0: "FQD_OK", 1: "FQD_ERR_INVALID", 2: "FQD_ERR_CUDA", 3: "FQD_ERR_EMPTY", 4: "FQD_ERR_BAD_START",
+          5: "FQD_ERR_LEN_MISMATCH", 6: "FQD_ERR_BAD_BASE", 7: "FQD_ERR_CAPACITY", 8: "FQD_ERR_SEQ_TOO_LONG"}
+
+
+class FqdError(RuntimeError):
+    def __init__(self, code, msg=""):
+        super().__init__(f"{STATUS.get(code, code)}: {msg}")
+        self.code = code
+
+
+class Config(C.Structure):
+    _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("mode", C.c_int32), ("format", C.c_int32),
+                ("paired", C.c_int32), ("unordered", C.c_int32), ("hamming_dist", C.c_uint32),
+                ("max_seq_len", C.c_uint32), ("max_records", C.c_uint64), ("max_chunk_bytes", C.c_uint64),
+                ("max_chunk_records", C.c_uint64)]
+
+
+class Stats(C.Structure):
+    _fields_ = [("total", C.c_uint64), ("dups", C.c_uint64), ("unmatched", C.c_uint64),
+                ("err", C.c_int32), ("err_char", C.c_int32), ("err_record", C.c_uint64)]
+
+
+class ChunkResult(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("consumed", C.c_uint64 * 2), ("first_record", C.c_uint64),
+                ("n_survivors", C.c_uint64), ("rec_start", C.POINTER(C.c_uint32) * 2), ("dup", C.POINTER(C.c_uint8))]
+
+
+class Emission(C.Structure):
+    _fields_ = [("n_out", C.c_uint64), ("off", C.POINTER(C.c_uint64) * 2), ("len", C.POINTER(C.c_uint32) * 2),
+                ("head", C.POINTER(C.c_uint64))]
+
+
+_lib = None
+
+
+def build(verbose: bool = False) -> Path:
+    """Compile libfqd_cuda.so in-tree for sm_100a (nvcc cross-compiles without a GPU)."""
+    res = subprocess.run(["make", "-C", str(CSRC), "all"], capture_output=True, text=True)
+    if verbose or res.returncode:
+        print(res.stdout[-4000:])
+        print(res.stderr[-4000:])
+    if res.returncode:
+        raise RuntimeError("building libfqd_cuda.so failed")
+    return LIB_PATH
+
+
+def load_library():
+    """Load libfqd_cuda.so; raises (never falls back) when it is absent."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists():
+        raise FileNotFoundError(f"{LIB_PATH} is missing - run __graft_entry__.build() / make -C {CSRC}")
+    lib = C.CDLL(str(LIB_PATH))
+    vp, sz, u64 = C.c_void_p, C.c_size_t, C.c_uint64
+    lib.fqd_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    lib.fqd_destroy.argtypes = [vp]
+    lib.fqd_destroy.restype = None
+    lib.fqd_last_error.argtypes = [vp]
+    lib.fqd_last_error.restype = C.c_char_p
+    lib.fqd_host_alloc.argtypes = [C.POINTER(vp), sz]
+    lib.fqd_host_free.argtypes = [vp]
+    lib.fqd_push.argtypes = [vp, vp, sz, vp, sz, C.POINTER(ChunkResult)]
+    lib.fqd_push_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(ChunkResult)]
+    lib.fqd_push_device_async.argtypes = [vp, vp, sz, vp, sz]
+    lib.fqd_sync.argtypes = [vp]
+    lib.fqd_append.argtypes = [vp, C.c_int, vp, sz]
+    lib.fqd_append_device.argtypes = [vp, C.c_int, vp, sz]
+    lib.fqd_finish.argtypes = [vp]
+    lib.fqd_emission.argtypes = [vp, C.POINTER(Emission)]
+    lib.fqd_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.fqd_device_time_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
+    lib.fqd_synth_fastq.argtypes = [C.c_int, vp, u64, u64, C.c_uint32, C.c_int, u64, C.c_uint32, C.c_uint32, C.c_int]
+    lib.fqd_synth_record_bytes.argtypes = [C.c_uint32]
+    lib.fqd_synth_record_bytes.restype = sz
+    lib.fqd_device_alloc.argtypes = [C.c_int, C.POINTER(vp), sz]
+    lib.fqd_device_free.argtypes = [C.c_int, vp]
+    lib.fqd_memcpy_d2h.argtypes = [C.c_int, vp, vp, sz]
+    lib.fqd_memcpy_h2d.argtypes = [C.c_int, vp, vp, sz]
+    _lib = lib
+    return lib
+
+
+def declared_symbols():
+    """Function names declared in include/fqd.h (used by the CPU-side export test)."""
+    import re
+    txt = HEADER.read_text()
+    return sorted(set(re.findall(r"\b(fqd_[a-z0-9_]+)\s*\(", txt)))
+
+
+class DeviceBuffer:
+    """Raw device allocation through the C ABI (no torch needed)."""
+
+    def __init__(self, nbytes: int, device: int = 0):
+        self.lib = load_library()
+        self.device = device
+        self.nbytes = int(nbytes)
+        p = C.c_void_p()
+        rc = self.lib.fqd_device_alloc(device, C.byref(p), max(self.nbytes, 16))
+        if rc:
+            raise FqdError(rc, f"cudaMalloc({nbytes})")
+        self.ptr = p.value
+
+    def upload(self, data: bytes, offset: int = 0):
+        rc = self.lib.fqd_memcpy_h2d(self.device, C.c_void_p(self.ptr + offset), data, len(data))
+        if rc:
+            raise FqdError(rc, "h2d")
+
+    def download(self, nbytes: int | None = None, offset: int = 0) -> bytes:
+        n = self.nbytes - offset if nbytes is None else nbytes
+        buf = C.create_string_buffer(n)
+        rc = self.lib.fqd_memcpy_d2h(self.device, buf, C.c_void_p(self.ptr + offset), n)
+        if rc:
+            raise FqdError(rc, "d2h")
+        return buf.raw
+
+    def free(self):
+        if self.ptr:
+            self.lib.fqd_device_free(self.device, C.c_void_p(self.ptr))
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+class Engine:
+    """One fqd_handle."""
+
+    def __init__(self, mode="fast", fmt=FORMAT_FASTQ, paired=False, unordered=False, hamming_dist=2,
+                 max_seq_len=150, max_records=1 << 20, max_chunk_bytes=64 << 20, max_chunk_records=0, device=0):
+        self.lib = load_library()
+        cfg = Config(FQD_ABI_VERSION, device, MODE_BY_NAME[mode] if isinstance(mode, str) else mode, fmt,
+                     int(paired), int(unordered), hamming_dist, max_seq_len, max_records, max_chunk_bytes,
+                     max_chunk_records)
+        self.cfg = cfg
+        self.h = C.c_void_p()
+        rc = self.lib.fqd_create(C.byref(cfg), C.byref(self.h))
+        if rc:
+            raise FqdError(rc, (self.lib.fqd_last_error(None) or b"").decode())
+
+    def _check(self, rc):
+        if rc:
+            raise FqdError(rc, (self.lib.fqd_last_error(self.h) or b"").decode())
+
+    def close(self):
+        if self.h:
+            self.lib.fqd_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- fast ordered mode
+    def push(self, r1: bytes, r2: bytes | None = None) -> ChunkResult:
+        res = ChunkResult()
+        self._check(self.lib.fqd_push(self.h, r1, len(r1), r2, len(r2) if r2 is not None else 0, C.byref(res)))
+        return res
+
+    def push_device(self, d1, n1, d2=None, n2=0) -> ChunkResult:
+        res = ChunkResult()
+        self._check(self.lib.fqd_push_device(self.h, C.c_void_p(d1), n1, C.c_void_p(d2) if d2 else None, n2, C.byref(res)))
+        return res
+
+    def push_device_async(self, d1, n1, d2=None, n2=0):
+        self._check(self.lib.fqd_push_device_async(self.h, C.c_void_p(d1), n1, C.c_void_p(d2) if d2 else None, n2))
+
+    def sync(self):
+        self._check(self.lib.fqd_sync(self.h))
+
+    # -- whole-input modes
+    def append(self, mate: int, buf: bytes):
+        self._check(self.lib.fqd_append(self.h, mate, buf, len(buf)))
+
+    def append_device(self, mate: int, dptr: int, n: int):
+        self._check(self.lib.fqd_append_device(self.h, mate, C.c_void_p(dptr), n))
+
+    def finish(self):
+        self._check(self.lib.fqd_finish(self.h))
+
+    def emission(self) -> Emission:
+        em = Emission()
+        self._check(self.lib.fqd_emission(self.h, C.byref(em)))
+        return em
+
+    def stats(self) -> Stats:
+        st = Stats()
+        self._check(self.lib.fqd_stats(self.h, C.byref(st)))
+        return st
+
+    def device_time_ms(self):
+        ms, n = C.c_double(0), C.c_uint64(0)
+        self._check(self.lib.fqd_device_time_ms(self.h, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+
+def _np(ptr, n, dtype):
+    if n == 0:
+        return np.zeros(0, dtype=dtype)
+    return np.ctypeslib.as_array(ptr, shape=(int(n),)).astype(dtype, copy=True)
+
+
+def _gather_spans(buf: bytes, starts: np.ndarray, keep: np.ndarray) -> bytes:
+    """Concatenate records [starts[i], starts[i+1]) for which keep[i]; merges adjacent survivors."""
+    mv = memoryview(buf)
+    out = []
+    n = len(keep)
+    i = 0
+    while i < n:
+        if not keep[i]:
+            i += 1
+            continue
+        j = i
+        while j + 1 < n and keep[j + 1]:
+            j += 1
+        out.append(mv[int(starts[i]): int(starts[j + 1])])
+        i = j + 1
+    return b"".join(out)
+
+
+def dedup_fast(b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, chunk_bytes=1 << 20, max_seq_len=150,
+               max_records=None, device=0):
+    """--fast ordered mode on byte buffers, streamed in chunks the way the host reader does it:
+    push a chunk, write the surviving records, carry the incomplete tail into the next chunk
+    (src/bufferedinput.hpp:57-88).  Returns (out1, out2 | None, Stats)."""
+    paired = b2 is not None
+    if max_records is None:
+        max_records = max(1024, (b1.count(b"\n") // 2) + 16)
+    eng = Engine("fast", fmt, paired, False, 2, max_seq_len, max_records, chunk_bytes, 0, device)
+    lead = b"@" if fmt == FORMAT_FASTQ else b">"
+    try:
+        outs = [[], []]
+        bufs = [b1, b2 if paired else b""]
+        pos = [0, 0]
+        n_mates = 2 if paired else 1
+        first = True
+        adj_total = adj_dups = 0
+        st = eng.stats()
+        while True:
+            chunk = [bufs[m][pos[m]: pos[m] + chunk_bytes] for m in range(n_mates)]
+            if any(len(c) == 0 for c in chunk):
+                if first:   # empty input: the reference's first refresh() throws (src/bufferedinput.hpp:82-85)
+                    st = eng.stats()
+                    st.err = 3
+                    return b"", (b"" if paired else None), st
+                break
+            res = eng.push(chunk[0], chunk[1] if paired else None)
+            n = int(res.n_records)
+            st = eng.stats()
+            if n == 0 and st.err == 0:
+                at_end = all(pos[m] + len(chunk[m]) >= len(bufs[m]) for m in range(n_mates))
+                if first and at_end:
+                    st.err = 3
+                    return b"", (b"" if paired else None), st
+                if at_end:
+                    break
+                raise FqdError(7, "a single record does not fit in one chunk")
+            first = False
+            keep = _np(res.dup, n, np.uint8) == 0
+            # A non-record byte where the NEXT record should start aborts the run while the last complete
+            # record is being fetched (src/bufferedinput.hpp:90-103 pre-parses it; src/fastqview.cpp:91-92
+            # checks the lead byte before looking for line ends) - that last record is then never processed.
+            tail_err = None
+            if st.err == 0:
+                for m in range(n_mates):
+                    nxt = pos[m] + int(res.consumed[m])
+                    if nxt < len(bufs[m]) and bufs[m][nxt: nxt + 1] != lead:
+                        tail_err = (m, bufs[m][nxt])
+                        break
+            if tail_err is not None:
+                adj_total -= 1
+                adj_dups -= int(not keep[n - 1])
+                keep[n - 1] = False
+            for m in range(n_mates):
+                starts = _np(res.rec_start[m], n + 1, np.int64) if n else np.zeros(1, np.int64)
+                outs[m].append(_gather_spans(chunk[m], starts, keep))
+                pos[m] += int(res.consumed[m]) if st.err == 0 else 0
+            if tail_err is not None:
+                st.err, st.err_char, st.err_record = 4, tail_err[1], st.total
+                break
+            if st.err:
+                break
+            if all(pos[m] >= len(bufs[m]) for m in range(n_mates)):
+                break
+        if st.err in (0, 4):
+            st.total += adj_total
+            st.dups += adj_dups
+        return b"".join(outs[0]), (b"".join(outs[1]) if paired else None), st
+    finally:
+        eng.close()
+
+
+def dedup_whole(mode: str, b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, dist=2, unordered=False,
+                max_seq_len=150, append_bytes=1 << 22, device=0):
+    """Sequence-based modes and --fast --unordered: whole input on the device, emission order out."""
+    paired = b2 is not None
+    eng = Engine(mode, fmt, paired, unordered, dist, max_seq_len, 0, max(append_bytes, 1 << 16), 0, device)
+    try:
+        for m, b in enumerate([b1, b2] if paired else [b1]):
+            for o in range(0, len(b), append_bytes):
+                eng.append(m, b[o: o + append_bytes])
+        eng.finish()
+        st = eng.stats()
+        em = eng.emission()
+        n = int(em.n_out)
+        outs = []
+        for m, b in enumerate([b1, b2] if paired else [b1]):
+            off = _np(em.off[m], n, np.int64)
+            ln = _np(em.len[m], n, np.int64)
+            mv = memoryview(b)
+            outs.append(b"".join(mv[int(o): int(o + l)] for o, l in zip(off, ln)))
+        return outs[0], (outs[1] if paired else None), st
+    finally:
+        eng.close()

@@ -1,0 +1,107 @@
+// common.cuh - shared device helpers for libfqd_cuda (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fqd {
+
+typedef unsigned long long u64;
+typedef uint32_t u32;
+typedef uint16_t u16;
+typedef uint8_t u8;
+
+// ---------------------------------------------------------------------------------------------------------
+// Packed sequence keys.
+//   One key "mate row" = W 64-bit words; each word holds 20 bases, 3 bits per base, first base in the most
+//   significant position (bits 59..57), so that comparing rows word by word as unsigned integers is the
+//   byte order of sequence+'\n' that FastqView::cmp defines (src/fastqview.cpp:56-67):
+//        code 0 = end of sequence / padding ('\n' sorts below every base)   A=1  C=2  G=3  N=4  T=5
+//   Equality of rows <=> equal length and equal bytes, which is setRecord::operator== on the reference's
+//   base-5 packing (src/hash_dup_remover.cpp:10-14, src/seq_utils.cpp:23-49).
+constexpr int BASES_PER_WORD = 20;
+
+// Per-chunk control block written by the kernels, read back by the host (or by later kernels).
+struct ChunkCtl {
+    u32 ticket;            // dynamic tile ordering for the decoupled look-back
+    u32 n_newlines;        // total '\n' in the chunk (written by the last tile)
+    u32 n_records;         // complete records parsed (<= capacity)
+    u32 consumed;          // bytes covered by those records
+    u64 err_parse;         // min over records of (record << 16 | code << 8 | char); ~0 = none
+    u64 err_base;          // min over records of (record << 32 | pos << 8 | char);  ~0 = none
+    u32 too_long;          // a sequence exceeded the key row
+    u32 pad;
+};
+
+// Persistent per-handle device state.
+struct RunState {
+    u64 n_records;         // records (pairs) inserted so far == next key-store slot
+    u64 n_dups;            // duplicates so far
+    u64 n_survivors;
+    u32 capacity_exceeded; // key store or table overflow
+    u32 chunk_pairs;       // pairs in the chunk being processed (min over mates)
+    u32 chunk_dups;
+    u32 pad;
+};
+
+constexpr u64 NO_ERR = ~0ull;
+enum { PERR_BAD_START = 1, PERR_LEN_MISMATCH = 2 };
+
+// ---------------------------------------------------------------------------------------------------------
+// hashing: multilinear over 32-bit limbs with per-position odd keys, finalised by a 64-bit mixer.
+__device__ __forceinline__ u64 mix64(u64 x) {
+    x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32; x *= 0xD6E8FEB86659FD93ull;
+    x ^= x >> 32;
+    return x;
+}
+__device__ __forceinline__ u64 pos_key(u32 w) {           // odd 64-bit key for word position w
+    u64 z = (u64)(w + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return (z ^ (z >> 31)) | 1ull;
+}
+__device__ __forceinline__ u64 word_hash(u64 word, u64 key) {
+    u32 lo = (u32)word, hi = (u32)(word >> 32);
+    u64 k2 = (key >> 17) | (key << 47) | 1ull;
+    return (u64)lo * key + (u64)hi * k2 + ((u64)lo << 32 ^ (u64)hi);   // mod 2^64
+}
+__device__ __forceinline__ u64 pair_hash(u64 h1, u64 h2) {
+    return mix64(h1 + 0x9E3779B97F4A7C15ull * ((h2 << 31) | (h2 >> 33)));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// mbarrier + bulk async copy (TMA, 1-D): global -> shared, completion on an mbarrier.
+__device__ __forceinline__ u32 smem_u32(const void* p) { return (u32)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(u64* bar, u32 count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(u64* bar, u32 bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
+    u32 ok;
+    do {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+__device__ __forceinline__ u64 ld_volatile_u64(const u64* p) {
+    u64 v;
+    asm volatile("ld.volatile.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_volatile_u64(u64* p, u64 v) {
+    asm volatile("st.volatile.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+}  // namespace fqd

@@ -1,0 +1,452 @@
+// fqd_api.cu - C ABI of libfqd_cuda.so (declared in include/fqd.h).  Host side of the device pipeline:
+// owns the CUDA stream, the key store, the hash table and the per-chunk tables; launches the kernels.
+// There is no CPU fallback anywhere in this file: every data path runs the sm_100a kernels.
+#include <cuda_runtime.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <string>
+#include <vector>
+
+#include "../../include/fqd.h"
+#include "common.cuh"
+#include "hashset.cuh"
+#include "parse_pack.cuh"
+#include "seqmode.cuh"
+#include "synth.cuh"
+
+using namespace fqd;
+
+static thread_local std::string g_create_error;
+
+struct MateChunk {
+    u8* d_raw = nullptr;          // staging for host pushes (max_chunk_bytes + slack)
+    u64* d_tile_state = nullptr;
+    ChunkCtl* d_ctl = nullptr;
+    u32* d_rec_start = nullptr;   // [cap+1]
+    u64* d_hash = nullptr;        // [cap]
+    u32* h_rec_start = nullptr;   // pinned
+    ChunkCtl* h_ctl = nullptr;    // pinned
+    u32 n_tiles_cap = 0;
+};
+
+struct fqd_handle {
+    fqd_config cfg;
+    cudaStream_t stream = nullptr;
+    bool own_stream = true;
+    int sm_count = 148;
+    u32 W = 0, row_words = 0;
+    u64 key_capacity = 0;
+    u64* d_keys = nullptr;
+    u64* d_table = nullptr;
+    u64 n_buckets = 0;
+    u32 bucket_shift = 0;
+    RunState* d_run = nullptr;
+    RunState* h_run = nullptr;    // pinned
+    MateChunk mate[2];
+    u32 cap = 0;                  // records per chunk
+    u8* d_dup = nullptr;
+    u8* h_dup = nullptr;          // pinned
+    fqd_stats_t stats;
+    std::string err;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pending_events;
+    std::vector<cudaEvent_t> event_pool;
+    double device_ms = 0.0;
+    u64 launches = 0;
+    bool pending_async = false;
+    SeqState* seq = nullptr;      // whole-input modes (seqmode.cuh)
+};
+
+#define CUDA_TRY(h, call)                                                                      \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            char b_[512];                                                                      \
+            snprintf(b_, sizeof b_, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+            if (h) (h)->err = b_; else g_create_error = b_;                                    \
+            return FQD_ERR_CUDA;                                                               \
+        }                                                                                      \
+    } while (0)
+
+static int fail(fqd_handle* h, int code, const char* msg) {
+    if (h) h->err = msg; else g_create_error = msg;
+    return code;
+}
+
+extern "C" int fqd_abi_version(void) { return FQD_ABI_VERSION; }
+
+extern "C" const char* fqd_last_error(const fqd_handle* h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+extern "C" int fqd_host_alloc(void** p, size_t bytes) {
+    return cudaHostAlloc(p, bytes, cudaHostAllocDefault) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
+}
+extern "C" int fqd_host_free(void* p) { return cudaFreeHost(p) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA; }
+
+extern "C" int fqd_device_alloc(int device, void** d_ptr, size_t bytes) {
+    if (cudaSetDevice(device) != cudaSuccess) return FQD_ERR_CUDA;
+    return cudaMalloc(d_ptr, bytes) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
+}
+extern "C" int fqd_device_free(int device, void* d_ptr) {
+    if (cudaSetDevice(device) != cudaSuccess) return FQD_ERR_CUDA;
+    return cudaFree(d_ptr) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
+}
+extern "C" int fqd_memcpy_d2h(int device, void* dst, const void* d_src, size_t bytes) {
+    if (cudaSetDevice(device) != cudaSuccess) return FQD_ERR_CUDA;
+    return cudaMemcpy(dst, d_src, bytes, cudaMemcpyDeviceToHost) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
+}
+extern "C" int fqd_memcpy_h2d(int device, void* d_dst, const void* src, size_t bytes) {
+    if (cudaSetDevice(device) != cudaSuccess) return FQD_ERR_CUDA;
+    return cudaMemcpy(d_dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
+}
+
+static u32 words_for(u32 max_seq_len) {
+    u32 w = (max_seq_len + BASES_PER_WORD - 1) / BASES_PER_WORD;
+    if (w < 2) w = 2;
+    return (w + 1u) & ~1u;      // even, so rows are 16-byte aligned
+}
+
+extern "C" void fqd_destroy(fqd_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->cfg.device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    if (h->seq) seq_destroy(h->seq);
+    for (auto& pe : h->pending_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
+    for (auto e : h->event_pool) cudaEventDestroy(e);
+    for (int m = 0; m < 2; ++m) {
+        MateChunk& c = h->mate[m];
+        cudaFree(c.d_raw); cudaFree(c.d_tile_state); cudaFree(c.d_ctl); cudaFree(c.d_rec_start); cudaFree(c.d_hash);
+        if (c.h_rec_start) cudaFreeHost(c.h_rec_start);
+        if (c.h_ctl) cudaFreeHost(c.h_ctl);
+    }
+    cudaFree(h->d_keys); cudaFree(h->d_table); cudaFree(h->d_run); cudaFree(h->d_dup);
+    if (h->h_run) cudaFreeHost(h->h_run);
+    if (h->h_dup) cudaFreeHost(h->h_dup);
+    if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+static int create_impl(const fqd_config* cfg, fqd_handle* h) {
+    h->cfg = *cfg;
+    memset(&h->stats, 0, sizeof h->stats);
+    int ndev = 0;
+    CUDA_TRY(h, cudaGetDeviceCount(&ndev));
+    if (cfg->device < 0 || cfg->device >= ndev) return fail(h, FQD_ERR_CUDA, "no such CUDA device");
+    CUDA_TRY(h, cudaSetDevice(cfg->device));
+    cudaDeviceProp prop;
+    CUDA_TRY(h, cudaGetDeviceProperties(&prop, cfg->device));
+    if (prop.major < 10) return fail(h, FQD_ERR_CUDA, "libfqd_cuda is built for sm_100a (B200) only");
+    h->sm_count = prop.multiProcessorCount;
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+
+    const int mates = cfg->paired ? 2 : 1;
+    h->W = words_for(cfg->max_seq_len ? cfg->max_seq_len : 150);
+    h->row_words = h->W * mates;
+    if (cfg->max_chunk_bytes == 0 || cfg->max_chunk_bytes >= (1ull << 32) - (1ull << 20))
+        return fail(h, FQD_ERR_INVALID, "max_chunk_bytes must be in (0, 4 GiB - 1 MiB)");
+    h->cap = (u32)(cfg->max_chunk_records ? cfg->max_chunk_records : std::max<u64>(cfg->max_chunk_bytes / 64, 1024));
+    const bool whole_input = cfg->mode != FQD_MODE_FAST || cfg->unordered;
+
+    CUDA_TRY(h, cudaMalloc(&h->d_run, sizeof(RunState)));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_run, 0, sizeof(RunState), h->stream));
+    CUDA_TRY(h, cudaHostAlloc(&h->h_run, sizeof(RunState), cudaHostAllocDefault));
+
+    if (!whole_input) {
+        if (cfg->max_records == 0) return fail(h, FQD_ERR_INVALID, "max_records must be > 0");
+        h->key_capacity = cfg->max_records;
+        CUDA_TRY(h, cudaMalloc(&h->d_keys, h->key_capacity * h->row_words * sizeof(u64)));
+        u64 nb = 1024;
+        while (nb * 2 < h->key_capacity) nb <<= 1;        // 4*nb entries >= 2*capacity  (load factor <= 0.5)
+        h->n_buckets = nb;
+        u32 lg = 0; while ((1ull << lg) < nb) ++lg;
+        h->bucket_shift = 64 - lg;
+        CUDA_TRY(h, cudaMalloc(&h->d_table, nb * 4 * sizeof(u64)));
+        CUDA_TRY(h, cudaMemsetAsync(h->d_table, 0xFF, nb * 4 * sizeof(u64), h->stream));
+        for (int m = 0; m < mates; ++m) {
+            MateChunk& c = h->mate[m];
+            c.n_tiles_cap = (u32)((cfg->max_chunk_bytes + PP_TILE - 1) / PP_TILE) + 1;
+            CUDA_TRY(h, cudaMalloc(&c.d_raw, cfg->max_chunk_bytes + 4096));
+            CUDA_TRY(h, cudaMalloc(&c.d_tile_state, (size_t)c.n_tiles_cap * sizeof(u64)));
+            CUDA_TRY(h, cudaMalloc(&c.d_ctl, sizeof(ChunkCtl)));
+            CUDA_TRY(h, cudaMalloc(&c.d_rec_start, ((size_t)h->cap + 1) * sizeof(u32)));
+            CUDA_TRY(h, cudaMalloc(&c.d_hash, (size_t)h->cap * sizeof(u64)));
+            CUDA_TRY(h, cudaHostAlloc(&c.h_rec_start, ((size_t)h->cap + 1) * sizeof(u32), cudaHostAllocDefault));
+            CUDA_TRY(h, cudaHostAlloc(&c.h_ctl, sizeof(ChunkCtl), cudaHostAllocDefault));
+        }
+        CUDA_TRY(h, cudaMalloc(&h->d_dup, (size_t)h->cap + 64));
+        CUDA_TRY(h, cudaHostAlloc(&h->h_dup, (size_t)h->cap + 64, cudaHostAllocDefault));
+    } else {
+        int rc = seq_create(&h->seq, cfg, h->stream, h->sm_count, h->W, &h->err);
+        if (rc) return rc;
+    }
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return FQD_OK;
+}
+
+extern "C" int fqd_create(const fqd_config* cfg, fqd_handle** out) {
+    if (!cfg || !out) return fail(nullptr, FQD_ERR_INVALID, "null argument");
+    if (cfg->abi_version != FQD_ABI_VERSION) return fail(nullptr, FQD_ERR_INVALID, "ABI version mismatch");
+    if (cfg->unordered && (cfg->mode != FQD_MODE_FAST || !cfg->paired))
+        return fail(nullptr, FQD_ERR_INVALID, "--unordered needs --fast and paired input");   // src/main.cpp:158-164
+    fqd_handle* h = new fqd_handle();
+    int rc = create_impl(cfg, h);
+    if (rc) { g_create_error = h->err; fqd_destroy(h); *out = nullptr; return rc; }
+    *out = h;
+    return FQD_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------------
+__global__ void k_init_chunk(ChunkCtl* ctl, u64* tile_state, u32 n_tiles) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        ctl->ticket = 0; ctl->n_newlines = 0; ctl->n_records = 0; ctl->consumed = 0;
+        ctl->err_parse = NO_ERR; ctl->err_base = NO_ERR; ctl->too_long = 0; ctl->pad = 0;
+    }
+    for (; i < n_tiles; i += gridDim.x * blockDim.x) tile_state[i] = 0;
+}
+
+static cudaEvent_t get_event(fqd_handle* h) {
+    if (!h->event_pool.empty()) { cudaEvent_t e = h->event_pool.back(); h->event_pool.pop_back(); return e; }
+    cudaEvent_t e; cudaEventCreate(&e); return e;
+}
+
+// Enqueue parse+pack for one mate of a chunk.
+static int launch_parse(fqd_handle* h, int m, const u8* d_raw, size_t n, u8* d_dup_unused) {
+    (void)d_dup_unused;
+    MateChunk& c = h->mate[m];
+    const u32 n_tiles = (u32)((n + PP_TILE - 1) / PP_TILE);
+    k_init_chunk<<<std::max(1u, std::min(n_tiles / 256 + 1, 1024u)), 256, 0, h->stream>>>(c.d_ctl, c.d_tile_state, n_tiles);
+    h->launches++;
+    if (n_tiles == 0) return FQD_OK;
+    ParseParams p;
+    p.raw = d_raw; p.n = (u32)n; p.n_tiles = n_tiles; p.tile_state = c.d_tile_state; p.ctl = c.d_ctl; p.run = h->d_run;
+    p.rec_start = c.d_rec_start; p.cap = h->cap; p.keys = h->d_keys; p.key_capacity = h->key_capacity;
+    p.row_words = h->row_words; p.mate_off = m * h->W; p.W = h->W; p.hash = c.d_hash; p.seq_len = nullptr; p.word0 = nullptr;
+    p.strict = 1; p.hash_salt = m * 4096u; p.dup = (m == 0) ? h->d_dup : nullptr;
+    if (h->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
+    else k_parse_pack<2><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
+    h->launches++;
+    return FQD_OK;
+}
+
+static int enqueue_fast_chunk(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2) {
+    const bool paired = h->cfg.paired != 0;
+    if (((uintptr_t)d_r1 & 15) || (paired && ((uintptr_t)d_r2 & 15))) return fail(h, FQD_ERR_INVALID, "device buffers must be 16-byte aligned");
+    if (n1 > h->cfg.max_chunk_bytes || n2 > h->cfg.max_chunk_bytes) return fail(h, FQD_ERR_INVALID, "chunk larger than max_chunk_bytes");
+    cudaEvent_t e0 = get_event(h), e1 = get_event(h);
+    CUDA_TRY(h, cudaEventRecord(e0, h->stream));
+    launch_parse(h, 0, (const u8*)d_r1, n1, nullptr);
+    if (paired) launch_parse(h, 1, (const u8*)d_r2, n2, nullptr);
+    InsertParams ip;
+    ip.table = h->d_table; ip.bucket_shift = h->bucket_shift; ip.bucket_mask = h->n_buckets - 1; ip.keys = h->d_keys;
+    ip.row_words = h->row_words; ip.key_capacity = h->key_capacity;
+    ip.hash1 = h->mate[0].d_hash; ip.hash2 = paired ? h->mate[1].d_hash : nullptr;
+    ip.ctl1 = h->mate[0].d_ctl; ip.ctl2 = paired ? h->mate[1].d_ctl : nullptr; ip.run = h->d_run; ip.dup = h->d_dup;
+    k_chunk_begin<<<1, 1, 0, h->stream>>>(ip);
+    k_insert<<<h->sm_count * 8, HS_THREADS, 0, h->stream>>>(ip);
+    k_count_dups<<<h->sm_count * 2, HS_THREADS, 0, h->stream>>>(h->d_dup, h->d_run);
+    k_chunk_end<<<1, 1, 0, h->stream>>>(h->d_run);
+    h->launches += 4;
+    CUDA_TRY(h, cudaEventRecord(e1, h->stream));
+    h->pending_events.emplace_back(e0, e1);
+    CUDA_TRY(h, cudaGetLastError());
+    return FQD_OK;
+}
+
+static int drain_events(fqd_handle* h) {
+    for (auto& pe : h->pending_events) {
+        float ms = 0.f;
+        CUDA_TRY(h, cudaEventElapsedTime(&ms, pe.first, pe.second));
+        h->device_ms += ms;
+        h->event_pool.push_back(pe.first);
+        h->event_pool.push_back(pe.second);
+    }
+    h->pending_events.clear();
+    return FQD_OK;
+}
+
+// Fold the device counters / error words of the chunk that just finished into the host statistics.
+// Order of errors follows the reference's lazy record fetch (src/bufferedinput.hpp:90-103): fetching pair k
+// pre-parses record k+1 of each mate (left first), so a malformed record e aborts before pair e-1 is
+// processed; a bad base in pair j aborts while pair j is being keyed (left mate first).
+static int fold_chunk(fqd_handle* h, u64 first_record, u64* n_ok) {
+    const int mates = h->cfg.paired ? 2 : 1;
+    u64 pairs = h->h_run->chunk_pairs;
+    *n_ok = pairs;
+    if (h->stats.err) { *n_ok = 0; return h->stats.err; }
+    long long best_t = -1; int best_code = 0, best_char = 0; u64 best_rec = 0, best_ok = 0;
+    bool have = false;
+    for (int m = 0; m < mates; ++m) {
+        const ChunkCtl& c = *h->mate[m].h_ctl;
+        if (c.err_parse != NO_ERR) {
+            u64 e = c.err_parse >> 16; int code = (int)((c.err_parse >> 8) & 0xFF); int ch = (int)(c.err_parse & 0xFF);
+            if (e <= pairs) {     // a malformed record right after the last processed pair still aborts it
+                long long t = e == 0 ? (first_record == 0 ? -8 + m : -4 + m) : (long long)(e - 1) * 4 + m;
+                if (!have || t < best_t) {
+                    have = true; best_t = t; best_char = ch; best_rec = first_record + e;
+                    best_code = code == PERR_BAD_START ? FQD_ERR_BAD_START : FQD_ERR_LEN_MISMATCH;
+                    best_ok = e == 0 ? 0 : e - 1;
+                }
+            }
+        }
+        if (c.err_base != NO_ERR) {
+            u64 j = c.err_base >> 32; int ch = (int)(c.err_base & 0xFF);
+            if (j < pairs) {
+                long long t = (long long)j * 4 + 2 + m;
+                if (!have || t < best_t) {
+                    have = true; best_t = t; best_char = ch; best_rec = first_record + j; best_code = FQD_ERR_BAD_BASE; best_ok = j;
+                }
+            }
+        }
+        if (c.too_long == 1 && !have) { have = true; best_t = 1ll << 60; best_code = FQD_ERR_SEQ_TOO_LONG; best_ok = 0; }
+    }
+    if (h->h_run->capacity_exceeded && !have) { have = true; best_code = FQD_ERR_CAPACITY; best_ok = pairs; }
+    if (have) {
+        h->stats.err = best_code; h->stats.err_char = best_char; h->stats.err_record = best_rec;
+        *n_ok = best_ok;
+    }
+    return h->stats.err;
+}
+
+static int finish_fast_chunk(fqd_handle* h, size_t n1, size_t n2, fqd_chunk_result* res) {
+    const int mates = h->cfg.paired ? 2 : 1;
+    for (int m = 0; m < mates; ++m)
+        CUDA_TRY(h, cudaMemcpyAsync(h->mate[m].h_ctl, h->mate[m].d_ctl, sizeof(ChunkCtl), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_run, h->d_run, sizeof(RunState), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    drain_events(h);
+    const u64 pairs = h->h_run->chunk_pairs;
+    const u64 first_record = h->h_run->n_records - pairs;
+    for (int m = 0; m < mates; ++m)
+        CUDA_TRY(h, cudaMemcpyAsync(h->mate[m].h_rec_start, h->mate[m].d_rec_start, (pairs + 1) * sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_dup, h->d_dup, pairs, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    u64 n_ok = pairs;
+    fold_chunk(h, first_record, &n_ok);
+    // statistics count only what the reference would have processed before an error
+    u64 dups_ok = h->h_run->chunk_dups;
+    if (n_ok < pairs) { dups_ok = 0; for (u64 i = 0; i < n_ok; ++i) dups_ok += h->h_dup[i]; }
+    h->stats.total += n_ok;
+    h->stats.dups += dups_ok;
+    if (res) {
+        memset(res, 0, sizeof *res);
+        res->n_records = n_ok;
+        res->first_record = first_record;
+        res->n_survivors = n_ok - dups_ok;
+        res->dup = h->h_dup;
+        const size_t nn[2] = {n1, n2};
+        for (int m = 0; m < mates; ++m) {
+            res->rec_start[m] = h->mate[m].h_rec_start;
+            res->consumed[m] = nn[m] ? h->mate[m].h_rec_start[pairs] : 0;
+        }
+    }
+    return FQD_OK;
+}
+
+extern "C" int fqd_push_device(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2, fqd_chunk_result* res) {
+    if (!h) return FQD_ERR_INVALID;
+    if (h->cfg.mode != FQD_MODE_FAST || h->cfg.unordered) return fail(h, FQD_ERR_INVALID, "fqd_push* is for ordered --fast mode; use fqd_append/fqd_finish");
+    if (h->pending_async) { int rc = fqd_sync(h); if (rc) return rc; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = enqueue_fast_chunk(h, d_r1, n1, h->cfg.paired ? d_r2 : nullptr, h->cfg.paired ? n2 : 0);
+    if (rc) return rc;
+    return finish_fast_chunk(h, n1, n2, res);
+}
+
+extern "C" int fqd_push(fqd_handle* h, const char* r1, size_t n1, const char* r2, size_t n2, fqd_chunk_result* res) {
+    if (!h) return FQD_ERR_INVALID;
+    if (h->cfg.mode != FQD_MODE_FAST || h->cfg.unordered) return fail(h, FQD_ERR_INVALID, "fqd_push* is for ordered --fast mode; use fqd_append/fqd_finish");
+    if (n1 > h->cfg.max_chunk_bytes || n2 > h->cfg.max_chunk_bytes) return fail(h, FQD_ERR_INVALID, "chunk larger than max_chunk_bytes");
+    if (h->pending_async) { int rc = fqd_sync(h); if (rc) return rc; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (n1) CUDA_TRY(h, cudaMemcpyAsync(h->mate[0].d_raw, r1, n1, cudaMemcpyHostToDevice, h->stream));
+    if (h->cfg.paired && n2) CUDA_TRY(h, cudaMemcpyAsync(h->mate[1].d_raw, r2, n2, cudaMemcpyHostToDevice, h->stream));
+    int rc = enqueue_fast_chunk(h, h->mate[0].d_raw, n1, h->cfg.paired ? h->mate[1].d_raw : nullptr, h->cfg.paired ? n2 : 0);
+    if (rc) return rc;
+    return finish_fast_chunk(h, n1, n2, res);
+}
+
+extern "C" int fqd_push_device_async(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2) {
+    if (!h) return FQD_ERR_INVALID;
+    if (h->cfg.mode != FQD_MODE_FAST || h->cfg.unordered) return fail(h, FQD_ERR_INVALID, "fqd_push* is for ordered --fast mode");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    h->pending_async = true;
+    return enqueue_fast_chunk(h, d_r1, n1, h->cfg.paired ? d_r2 : nullptr, h->cfg.paired ? n2 : 0);
+}
+
+extern "C" int fqd_sync(fqd_handle* h) {
+    if (!h) return FQD_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->seq) { CUDA_TRY(h, cudaStreamSynchronize(h->stream)); return drain_events(h); }
+    const int mates = h->cfg.paired ? 2 : 1;
+    for (int m = 0; m < mates; ++m)
+        CUDA_TRY(h, cudaMemcpyAsync(h->mate[m].h_ctl, h->mate[m].d_ctl, sizeof(ChunkCtl), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_run, h->d_run, sizeof(RunState), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    drain_events(h);
+    if (h->pending_async) {
+        // async pushes: totals come from the device counters; data errors are reported for the last chunk only
+        h->pending_async = false;
+        u64 n_ok;
+        h->stats.total = h->h_run->n_records;
+        h->stats.dups = h->h_run->n_dups;
+        fold_chunk(h, h->h_run->n_records - h->h_run->chunk_pairs, &n_ok);
+    }
+    return FQD_OK;
+}
+
+extern "C" int fqd_stats(fqd_handle* h, fqd_stats_t* out) {
+    if (!h || !out) return FQD_ERR_INVALID;
+    if (h->seq) seq_stats(h->seq, &h->stats);
+    *out = h->stats;
+    return FQD_OK;
+}
+
+extern "C" int fqd_device_time_ms(fqd_handle* h, double* ms, uint64_t* launches) {
+    if (!h) return FQD_ERR_INVALID;
+    if (h->seq) { h->device_ms = seq_device_ms(h->seq); h->launches = seq_launches(h->seq); }
+    if (ms) *ms = h->device_ms;
+    if (launches) *launches = h->launches;
+    return FQD_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------------
+// whole-input modes
+extern "C" int fqd_append(fqd_handle* h, int mate, const char* buf, size_t n) {
+    if (!h || !h->seq) return fail(h, FQD_ERR_INVALID, "fqd_append is for sequence / unordered modes");
+    cudaSetDevice(h->cfg.device);
+    return seq_append(h->seq, mate, buf, n, false, &h->err);
+}
+extern "C" int fqd_append_device(fqd_handle* h, int mate, const void* d_buf, size_t n) {
+    if (!h || !h->seq) return fail(h, FQD_ERR_INVALID, "fqd_append_device is for sequence / unordered modes");
+    cudaSetDevice(h->cfg.device);
+    return seq_append(h->seq, mate, d_buf, n, true, &h->err);
+}
+extern "C" int fqd_finish(fqd_handle* h) {
+    if (!h || !h->seq) return fail(h, FQD_ERR_INVALID, "fqd_finish is for sequence / unordered modes");
+    cudaSetDevice(h->cfg.device);
+    int rc = seq_finish(h->seq, &h->err);
+    seq_stats(h->seq, &h->stats);
+    return rc;
+}
+extern "C" int fqd_emission(fqd_handle* h, fqd_emission_t* out) {
+    if (!h || !h->seq || !out) return fail(h, FQD_ERR_INVALID, "fqd_emission is for sequence / unordered modes");
+    return seq_emission(h->seq, out, &h->err);
+}
+
+// -----------------------------------------------------------------------------------------------------------
+extern "C" size_t fqd_synth_record_bytes(uint32_t read_len) { return 22u + 2u * (size_t)read_len; }
+
+extern "C" int fqd_synth_fastq(int device, void* d_out, uint64_t first, uint64_t count, uint32_t read_len, int mate,
+                               uint64_t seed, uint32_t dup_permille, uint32_t n_permille, int variant) {
+    if (cudaSetDevice(device) != cudaSuccess) return FQD_ERR_CUDA;
+    if (count == 0) return FQD_OK;
+    SynthParams p;
+    p.out = (u8*)d_out; p.first = first; p.count = count; p.read_len = read_len; p.mate = mate; p.seed = seed;
+    p.dup_permille = dup_permille; p.n_permille = n_permille; p.variant = variant;
+    u64 blocks = std::min<u64>((count + 7) / 8, 148ull * 64);
+    k_synth_fastq<<<(unsigned)blocks, 256>>>(p);
+    if (cudaGetLastError() != cudaSuccess) return FQD_ERR_CUDA;
+    return cudaDeviceSynchronize() == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
+}

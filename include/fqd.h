@@ -1,0 +1,157 @@
+/*
+ * fqd.h - C ABI of libfqd_cuda.so, the B200 (sm_100a) deduplication engine behind fastq-dupaway's hot paths.
+ *
+ * The reference (fastq-dupaway V1.5.0) has no FFI; its in-process seam is main()'s dispatch onto
+ *   HashDupRemover<T>::filterSE / filterPE(+unordered)   (src/hash_dup_remover.hpp:73-94,105-347)
+ *   SeqDupRemover<T>::filterSE / filterPE                (src/seq_dup_remover.hpp:12-38,54-218)
+ * with T in {FastqView, FastaView, *ViewWithId}.  The host keeps file / gzip I/O (src/file_utils.cpp,
+ * src/bufferedinput.hpp) and hands raw record bytes to this library, which replaces everything those
+ * drivers do per record: record splitting (FastqView::read_new src/fastqview.cpp:89-119), key packing
+ * (SeqUtils::seq2hash src/seq_utils.cpp:35-49), the exact first-occurrence set (src/hash_dup_remover.hpp:
+ * 113-139), the sorters (src/external_sort.hpp, src/paired_external_sort.hpp), the comparators
+ * (src/comparator.cpp:45-91) and the ID-tag merge-join (src/hash_dup_remover.hpp:257-347).
+ *
+ * Conventions: plain pointers and sizes only; every call returns an fqd_status (0 = ok); no exception
+ * crosses the boundary; one handle is driven by one host thread at a time.  "Device" pointers are CUDA
+ * device pointers on the handle's device.  There is NO CPU fallback: without a usable CUDA device
+ * fqd_create fails with FQD_ERR_CUDA.
+ */
+#ifndef FQD_H
+#define FQD_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FQD_ABI_VERSION 1
+
+typedef enum {
+    FQD_OK = 0,
+    FQD_ERR_INVALID = 1,        /* bad argument / call sequence                                          */
+    FQD_ERR_CUDA = 2,           /* CUDA runtime failure (fqd_last_error has the text)                    */
+    FQD_ERR_EMPTY = 3,          /* "Not enough memory to read a single object!"  src/bufferedinput.hpp:82-85 */
+    FQD_ERR_BAD_START = 4,      /* record does not start with '@' / '>'          src/fastqview.cpp:121-126   */
+    FQD_ERR_LEN_MISMATCH = 5,   /* FASTQ: len(seq) != len(qual)                  src/fastqview.cpp:117       */
+    FQD_ERR_BAD_BASE = 6,       /* fast mode: byte outside {A,C,G,T,N}           src/seq_utils.cpp:17-19     */
+    FQD_ERR_CAPACITY = 7,       /* record / key-store / table capacity exceeded                          */
+    FQD_ERR_SEQ_TOO_LONG = 8    /* sequence longer than fqd_config.max_seq_len                           */
+} fqd_status;
+
+typedef enum { FQD_FORMAT_FASTQ = 0, FQD_FORMAT_FASTA = 1 } fqd_format;      /* --format           src/main.cpp:111-120 */
+typedef enum {
+    FQD_MODE_FAST = 0,          /* --fast                      HashDupRemover   src/main.cpp:147-150 */
+    FQD_MODE_SEQ_TIGHT = 1,     /* --compare-seq tight         TightComparator  src/comparator.cpp:45-58 */
+    FQD_MODE_SEQ_LOOSE = 2,     /* --compare-seq loose         LooseComparator  src/comparator.cpp:60-74 */
+    FQD_MODE_SEQ_HAMMING = 3    /* --compare-seq tail-hamming  HammingComparator src/comparator.cpp:76-91 */
+} fqd_mode;
+
+typedef struct {
+    uint32_t abi_version;       /* FQD_ABI_VERSION                                                       */
+    int32_t  device;            /* CUDA device ordinal                                                   */
+    int32_t  mode;              /* fqd_mode                                                              */
+    int32_t  format;            /* fqd_format                                                            */
+    int32_t  paired;            /* 0 single-end, 1 paired-end (-u/-p)                                    */
+    int32_t  unordered;         /* --unordered (FAST + paired only)       src/main.cpp:158-164           */
+    uint32_t hamming_dist;      /* --distance                             src/main.cpp:34                */
+    uint32_t max_seq_len;       /* longest sequence line (bases, without '\n') the key rows must hold    */
+    uint64_t max_records;       /* capacity of the key store: records (pairs) over the whole run         */
+    uint64_t max_chunk_bytes;   /* largest buffer ever passed to one fqd_push* call (per mate), < 4 GiB  */
+    uint64_t max_chunk_records; /* records per chunk the per-chunk tables hold; 0 = max_chunk_bytes/64   */
+} fqd_config;
+
+typedef struct {
+    uint64_t total;             /* records / pairs processed   (-v line, src/hash_dup_remover.hpp:147,254)  */
+    uint64_t dups;              /* duplicates removed                                                     */
+    uint64_t unmatched;         /* --unordered: non-matching entries skipped  src/hash_dup_remover.hpp:345 */
+    int32_t  err;               /* sticky fqd_status of the first data error in input order, or FQD_OK    */
+    int32_t  err_char;          /* offending byte for BAD_START / BAD_BASE                                */
+    uint64_t err_record;        /* global index of the record that raised it                              */
+} fqd_stats_t;
+
+/* Result of one pushed chunk (FAST ordered mode) - host pointers owned by the handle, valid until the next
+ * push on the same handle. */
+typedef struct {
+    uint64_t n_records;         /* complete records (pairs) parsed from this chunk                        */
+    uint64_t consumed[2];       /* bytes of each mate's buffer covered by those records (carry the rest)  */
+    uint64_t first_record;      /* global index of record 0 of this chunk                                 */
+    uint64_t n_survivors;       /* records of this chunk that are WRITTEN                                 */
+    const uint32_t* rec_start[2]; /* n_records+1 offsets into each mate's buffer                          */
+    const uint8_t*  dup;        /* n_records flags: 1 = duplicate (dropped), 0 = written                  */
+} fqd_chunk_result;
+
+typedef struct fqd_handle fqd_handle;
+
+/* Lifecycle. */
+int fqd_create(const fqd_config* cfg, fqd_handle** out);
+void fqd_destroy(fqd_handle* h);
+const char* fqd_last_error(const fqd_handle* h);   /* also valid with h == NULL for fqd_create failures */
+int fqd_abi_version(void);
+
+/* Pinned host staging memory for the reader threads (cudaHostAlloc / cudaFreeHost). */
+int fqd_host_alloc(void** p, size_t bytes);
+int fqd_host_free(void* p);
+
+/*
+ * FAST ordered mode, streaming (replaces the per-record loop of impl_filterSE / impl_filterPE,
+ * src/hash_dup_remover.hpp:126-144,228-251).  Each push holds whole records from the start of the buffer;
+ * an incomplete trailing record is left to the caller (consumed[] says where it begins), exactly as
+ * BufferedInput::refresh carries the partial tail (src/bufferedinput.hpp:66-74).  Paired: the two buffers
+ * advance in lock-step, min(n1, n2) pairs are processed.  Records are numbered in input order across pushes;
+ * the first occurrence of a key in that order is the one written.
+ *   fqd_push        : host buffers (H2D copy inside)          fqd_push_device : buffers already in HBM
+ * r2 / n2 are NULL / 0 for single-end.  res may be NULL (statistics only).
+ */
+int fqd_push(fqd_handle* h, const char* r1, size_t n1, const char* r2, size_t n2, fqd_chunk_result* res);
+int fqd_push_device(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2, fqd_chunk_result* res);
+/* Same as fqd_push_device but returns after enqueueing; nothing is copied to the host.  fqd_sync() waits and
+ * folds the chunk counters into the statistics.  Used for device-resident throughput measurement. */
+int fqd_push_device_async(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2);
+int fqd_sync(fqd_handle* h);
+
+/*
+ * Whole-input modes: sequence-based (sort + comparator scan) and --fast --unordered (tag join).  The caller
+ * appends the raw bytes of the whole input (any number of fqd_append calls per mate; buffers are concatenated
+ * in call order and may cut records anywhere), then fqd_finish runs the sort / scan / join on the device.
+ * fqd_emission returns, in EMISSION order (sorted order for sequence mode, tag order for unordered -
+ * SURVEY.md F2), the byte span of every written record inside the concatenated input of each mate.
+ */
+int fqd_append(fqd_handle* h, int mate, const char* buf, size_t n);
+int fqd_append_device(fqd_handle* h, int mate, const void* d_buf, size_t n);
+int fqd_finish(fqd_handle* h);
+typedef struct {
+    uint64_t n_out;             /* records (pairs) written                                               */
+    const uint64_t* off[2];     /* per mate: byte offset of each written record in the concatenated input */
+    const uint32_t* len[2];     /* per mate: its byte length                                              */
+    const uint64_t* head;       /* sequence mode: for every INPUT-sorted position, unused unless clusters  */
+} fqd_emission_t;
+int fqd_emission(fqd_handle* h, fqd_emission_t* out);
+
+/* Statistics / sticky data error (feeds the -v lines and the reference's error messages). */
+int fqd_stats(fqd_handle* h, fqd_stats_t* out);
+
+/* Device time (ms, CUDA events on the handle's stream) spent in kernels since creation, and kernel launches. */
+int fqd_device_time_ms(fqd_handle* h, double* ms, uint64_t* launches);
+
+/*
+ * Counter-based synthetic FASTQ generator: fills a DEVICE buffer with records
+ * [first, first+count) of the stream (seed, dup_permille, n_permille): "@SYN.%010u <mate>\n" + read_len bases
+ * + "\n+\n" + read_len quals + "\n".  Record size is 22 + 2*read_len bytes (322 for 150 bp).  mate is 1 or 2.
+ * variant: 0 exact duplicates; 1 = loose (some duplicates truncated); 2 = hamming (tail substitutions).
+ */
+int fqd_synth_fastq(int device, void* d_out, uint64_t first, uint64_t count, uint32_t read_len, int mate,
+                    uint64_t seed, uint32_t dup_permille, uint32_t n_permille, int variant);
+size_t fqd_synth_record_bytes(uint32_t read_len);
+
+/* Raw device memory helpers so that bindings need no CUDA runtime of their own. */
+int fqd_device_alloc(int device, void** d_ptr, size_t bytes);
+int fqd_device_free(int device, void* d_ptr);
+int fqd_memcpy_d2h(int device, void* dst, const void* d_src, size_t bytes);
+int fqd_memcpy_h2d(int device, void* d_dst, const void* src, size_t bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FQD_H */
