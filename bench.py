@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py - throughput of the --fast deduplication hot path on B200 (contract in the build prompt).
+
+  python bench.py --gpus N --steps K --warmup W            our arm (CUDA through the C ABI)
+  python bench.py --impl reference --gpus N --steps K ...   the reference's own CPU implementation (oracle/_ref)
+
+A "step" is one whole job: the hash set is emptied, then every read of the workload goes through
+parse+pack -> insert -> count, with the raw FASTQ already resident in HBM (`value`), or pushed from pinned host
+memory through fqd_push with the per-chunk results copied back (`e2e`).  Workload = BASELINE.json configs[1]:
+synthetic 100 M x 150 bp single-end FASTQ, 30 % exact duplicates (32.2 GB, far larger than the 126 MB L2).
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+READ_LEN = 150
+REC_BYTES = 22 + 2 * READ_LEN            # 322
+SEED = 1
+DUP_PERMILLE = 300
+N_PERMILLE = 1
+# algorithmic bytes per read (DESIGN.md "Algorithmic bytes"): K1 parse+pack reads the record once and writes
+# the 64-byte key row, the 8-byte hash, the 4-byte record offset and the 1-byte flag
+K1_BYTES_PER_READ = REC_BYTES + 64 + 8 + 4 + 1
+METRIC = "dedup reads/sec"
+UNIT = "reads/s"
+
+
+def measured_peak_gbs():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured"
+        except Exception:
+            pass
+    return 6650.0, "fallback"
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = threading.Event()
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([t.strip() for t in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm = sorted(int(float(s[1])) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit())
+        mx = [int(float(s[2])) for s in self.samples if len(s) > 2 and s[2].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            for k, nm in enumerate(names):
+                if len(s) > 5 + k and s[5 + k].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def dist_env():
+    return int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+
+
+# ---------------------------------------------------------------------------------------------------------
+def reference_arm(args):
+    """The reference's own CPU implementation of the path (unmodified sources compiled into oracle/_ref, else the
+    oracle port) on the host cores of this box.  The reference is single-threaded: cores = 1."""
+    rank, _, world = dist_env()
+    if rank != 0:
+        return
+    sys.path.insert(0, str(ROOT / "oracle"))
+    oracle = importlib.import_module("oracle")
+    kind = "reference" if oracle.ref_available() else "port"
+    gen = importlib.import_module("bench_synth")
+    budget_s = float(os.environ.get("FQD_REF_BUDGET_S", 150))
+    # calibrate on a small sample, then size the per-step sample so warmup+steps fit the budget
+    tmp = Path(tempfile.mkdtemp(prefix="fqd_ref_", dir="/dev/shm" if Path("/dev/shm").is_dir() else None))
+    try:
+        def run(n_reads):
+            buf = gen.synth_fastq_cpu(0, n_reads, READ_LEN, 1, SEED, DUP_PERMILLE, N_PERMILLE)
+            t0 = time.perf_counter()
+            if kind == "reference":
+                rc, _, _, so, se = oracle.run_ref(tmp / "w", "fast", oracle.FASTQ, buf)
+                assert rc == 0, se
+            else:
+                oracle.fast_se(buf, oracle.FASTQ)
+            return time.perf_counter() - t0
+        t_cal = run(100_000)
+        rate = 100_000 / t_cal
+        n_step = int(max(50_000, min(3_000_000, rate * budget_s / max(1, args.steps + args.warmup))))
+        buf = gen.synth_fastq_cpu(0, n_step, READ_LEN, 1, SEED, DUP_PERMILLE, N_PERMILLE)
+        inp = tmp / "in.fq"
+        inp.write_bytes(buf)
+        times = []
+        for it in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            if kind == "reference":
+                res = subprocess.run([str(oracle.REF_BIN), "-i", str(inp), "-o", str(tmp / "out.fq"), "--fast"],
+                                     cwd=tmp, capture_output=True)
+                assert res.returncode == 0, res.stderr.decode()
+            else:
+                oracle.fast_se(buf, oracle.FASTQ)
+            dt = time.perf_counter() - t0
+            if it >= args.warmup:
+                times.append(dt)
+        total = sum(times)
+        value = n_step * len(times) / total
+        sample = f"first {n_step} reads of the synthetic stream per step, plain FASTQ on tmpfs, --fast, wall clock around the process"
+        line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": 1000.0 * total / len(times), "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+                "config": workload_config(args, n_step),
+                "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+                "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line), flush=True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def workload_config(args, n_reads):
+    return {"workload": "BASELINE configs[1]: synthetic 100Mx150bp single-end FASTQ, 30% exact duplicates, --fast",
+            "reads_per_step": int(n_reads), "read_len": READ_LEN, "record_bytes": REC_BYTES, "dup_fraction": DUP_PERMILLE / 1000,
+            "input": "larger than L2 (no flush needed)", "seed": SEED}
+
+
+# ---------------------------------------------------------------------------------------------------------
+def cpu_baseline(n_sample=3_000_000):
+    sys.path.insert(0, str(ROOT / "oracle"))
+    oracle = importlib.import_module("oracle")
+    gen = importlib.import_module("bench_synth")
+    kind = "reference" if oracle.ref_available() else "port"
+    tmp = Path(tempfile.mkdtemp(prefix="fqd_cpu_", dir="/dev/shm" if Path("/dev/shm").is_dir() else None))
+    try:
+        buf = gen.synth_fastq_cpu(0, n_sample, READ_LEN, 1, SEED, DUP_PERMILLE, N_PERMILLE)
+        inp = tmp / "in.fq"
+        inp.write_bytes(buf)
+        t0 = time.perf_counter()
+        if kind == "reference":
+            res = subprocess.run([str(oracle.REF_BIN), "-i", str(inp), "-o", str(tmp / "out.fq"), "--fast"], cwd=tmp, capture_output=True)
+            assert res.returncode == 0, res.stderr.decode()
+        else:
+            oracle.fast_se(buf, oracle.FASTQ)
+        dt = time.perf_counter() - t0
+        return {"value": n_sample / dt, "unit": UNIT, "cores": 1, "kind": kind,
+                "sample": f"first {n_sample} reads of the same synthetic stream ({n_sample * REC_BYTES / 1e9:.2f} GB plain FASTQ on tmpfs), --fast, one run, wall clock"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def our_arm(args):
+    rank, local_rank, world = dist_env()
+    fqd = importlib.import_module("fastq-dupaway_b200")
+    lib = fqd.load_library()            # raises when the CUDA library is missing: no fallback
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        dist = dist_mod
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    dev = local_rank
+    n_total = int(os.environ.get("FQD_BENCH_READS", 100_000_000))
+    if world > 1:
+        sys.path.insert(0, str(ROOT))
+        mg = importlib.import_module("bench_multi")
+        return mg.run(args, fqd, dist, rank, local_rank, world, n_total)
+
+    chunk_reads = 6_000_000
+    n_chunks = (n_total + chunk_reads - 1) // chunk_reads
+    raw = fqd.DeviceBuffer(n_total * REC_BYTES + 65536, dev)
+    for c in range(n_chunks):
+        first = c * chunk_reads
+        cnt = min(chunk_reads, n_total - first)
+        rc = lib.fqd_synth_fastq(dev, raw.ptr + first * REC_BYTES, first, cnt, READ_LEN, 1, SEED, DUP_PERMILLE, N_PERMILLE, 0)
+        assert rc == 0
+    eng = fqd.Engine("fast", fqd.FORMAT_FASTQ, False, False, 2, READ_LEN, n_total + 1024, chunk_reads * REC_BYTES + 65536,
+                     chunk_reads + 1024, dev)
+
+    def step_device():
+        eng.reset()
+        for c in range(n_chunks):
+            first = c * chunk_reads
+            cnt = min(chunk_reads, n_total - first)
+            eng.push_device_async(raw.ptr + first * REC_BYTES, cnt * REC_BYTES)
+
+    # ---- device-resident throughput (`value`)
+    for _ in range(max(3, args.warmup)):
+        step_device()
+    eng.sync()
+    st = eng.stats()
+    assert st.err == 0 and st.total == n_total, (st.err, st.total)
+    dups = st.dups
+    sampler = ClockSampler(dev)
+    sampler.start()
+    eng.profile_enable(True)
+    _, l0 = eng.device_time_ms()
+    eng.timer_start()
+    for _ in range(args.steps):
+        step_device()
+    ms_total = eng.timer_stop()
+    eng.sync()
+    _, l1 = eng.device_time_ms()
+    prof = eng.profile()
+    eng.profile_enable(False)
+    sampler.stop_flag.set()
+    sampler.join()
+    st = eng.stats()
+    assert st.err == 0 and st.total == n_total and st.dups == dups
+    ms_per_step = ms_total / args.steps
+    value = n_total / (ms_per_step / 1000.0)
+
+    peak, peak_kind = measured_peak_gbs()
+    k1_ms = prof.parse_ms / max(1, prof.parse_launches)
+    reads_per_launch = (prof.parse_bytes / max(1, prof.parse_launches)) / REC_BYTES
+    achieved = reads_per_launch * K1_BYTES_PER_READ / (k1_ms / 1000.0) / 1e9 if k1_ms > 0 else 0.0
+    roofline = {"bound": "hbm", "kernel": "k_parse_pack<4>", "achieved": achieved, "peak": peak, "peak_kind": peak_kind,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+                "alg_bytes_per_read": K1_BYTES_PER_READ, "reads_per_launch": reads_per_launch, "avg_launch_ms": k1_ms,
+                "kernel_share_of_step": prof.parse_ms / ms_total if ms_total else None,
+                "insert_share_of_step": prof.insert_ms / ms_total if ms_total else None,
+                "whole_path_input_GBps": n_total * REC_BYTES / (ms_per_step / 1000.0) / 1e9}
+    tr = ROOT / "profiles" / "traffic.json"
+    if tr.exists():
+        try:
+            roofline["traffic"] = json.loads(tr.read_text()).get("k_parse_pack_bytes_per_launch")
+        except Exception:
+            pass
+
+    # ---- end to end through the C ABI with HOST buffers (`e2e`)
+    e2e = None
+    try:
+        e2e = e2e_run(args, fqd, lib, eng, raw, n_total, chunk_reads, dups)
+    except Exception as ex:   # report, never hide
+        e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)}
+    eng.close()
+    raw.free()
+
+    cpu = cpu_baseline()
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
+            "data": "synthetic", "config": workload_config(args, n_total), "clocks": sampler.summary(),
+            "e2e": e2e, "gpu_launches": int((l1 - l0)), "roofline": roofline, "cpu_baseline": cpu,
+            "duplicates_removed": int(dups), "input_GBps": n_total * REC_BYTES / (ms_per_step / 1000.0) / 1e9}
+    print(json.dumps(line), flush=True)
+
+
+def e2e_run(args, fqd, lib, eng, raw, n_total, chunk_reads, dups_expected):
+    """Same job, inputs in pinned HOST memory, every chunk pushed with fqd_push (H2D inside) and its record
+    offsets + duplicate flags read back (D2H inside)."""
+    import ctypes as C
+    n_e2e = int(os.environ.get("FQD_BENCH_E2E_READS", n_total))
+    chunk = min(chunk_reads, 3_000_000)
+    nbytes = n_e2e * REC_BYTES
+    host = C.c_void_p()
+    rc = lib.fqd_host_alloc(C.byref(host), nbytes)
+    if rc:
+        raise MemoryError(f"pinned host allocation of {nbytes} bytes failed")
+    try:
+        # fill the pinned buffer from the device-resident synthetic data (same bytes as the `value` run)
+        step = 1 << 30
+        for o in range(0, nbytes, step):
+            n = min(step, nbytes - o)
+            assert lib.fqd_memcpy_d2h(eng.cfg.device, C.c_void_p(host.value + o), C.c_void_p(raw.ptr + o), n) == 0
+        n_chunks = (n_e2e + chunk - 1) // chunk
+        d2h = 0
+
+        def one_step():
+            nonlocal d2h
+            eng.reset()
+            surv = 0
+            d2h = 0
+            for c in range(n_chunks):
+                first = c * chunk
+                cnt = min(chunk, n_e2e - first)
+                res = fqd.ChunkResult()
+                rc2 = lib.fqd_push(eng.h, C.c_void_p(host.value + first * REC_BYTES), cnt * REC_BYTES, None, 0, C.byref(res))
+                assert rc2 == 0 and res.n_records == cnt
+                surv += res.n_survivors
+                d2h += (cnt + 1) * 4 + cnt + 64
+            return surv
+        for _ in range(1):
+            one_step()
+        steps = max(1, min(args.steps, 5))
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            surv = one_step()
+        dt = (time.perf_counter() - t0) / steps
+        if n_e2e == n_total:
+            assert n_e2e - surv == dups_expected
+        return {"value": n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h,
+                "reads_per_step": n_e2e, "ms_per_step": dt * 1000.0, "steps": steps,
+                "path": "fqd_push (pinned host FASTQ -> H2D -> kernels -> D2H of record offsets + duplicate flags), wall clock"}
+    finally:
+        lib.fqd_host_free(host)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        our_arm(args)
+
+
+if __name__ == "__main__":
+    main()

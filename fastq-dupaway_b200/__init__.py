@@ -58,6 +58,11 @@ class Emission(C.Structure):
                 ("head", C.POINTER(C.c_uint64))]
 
 
+class Profile(C.Structure):
+    _fields_ = [("parse_ms", C.c_double), ("parse_launches", C.c_uint64), ("parse_bytes", C.c_uint64),
+                ("parse_records", C.c_uint64), ("insert_ms", C.c_double), ("insert_launches", C.c_uint64)]
+
+
 _lib = None
 
 
@@ -92,6 +97,11 @@ def load_library():
     lib.fqd_push_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(ChunkResult)]
     lib.fqd_push_device_async.argtypes = [vp, vp, sz, vp, sz]
     lib.fqd_sync.argtypes = [vp]
+    lib.fqd_reset.argtypes = [vp]
+    lib.fqd_timer_start.argtypes = [vp]
+    lib.fqd_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
+    lib.fqd_profile_enable.argtypes = [vp, C.c_int]
+    lib.fqd_profile_get.argtypes = [vp, C.POINTER(Profile)]
     lib.fqd_append.argtypes = [vp, C.c_int, vp, sz]
     lib.fqd_append_device.argtypes = [vp, C.c_int, vp, sz]
     lib.fqd_finish.argtypes = [vp]
@@ -113,7 +123,7 @@ def declared_symbols():
     """Function names declared in include/fqd.h (used by the CPU-side export test)."""
     import re
     txt = HEADER.read_text()
-    return sorted(set(re.findall(r"\b(fqd_[a-z0-9_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"^(?:int|void|size_t|const char\*)\s+(fqd_[a-z0-9_]+)\s*\(", txt, flags=re.M)))
 
 
 class DeviceBuffer:
@@ -200,6 +210,25 @@ class Engine:
 
     def sync(self):
         self._check(self.lib.fqd_sync(self.h))
+
+    def reset(self):
+        self._check(self.lib.fqd_reset(self.h))
+
+    def timer_start(self):
+        self._check(self.lib.fqd_timer_start(self.h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double(0)
+        self._check(self.lib.fqd_timer_stop(self.h, C.byref(ms)))
+        return ms.value
+
+    def profile_enable(self, on=True):
+        self._check(self.lib.fqd_profile_enable(self.h, int(on)))
+
+    def profile(self) -> Profile:
+        p = Profile()
+        self._check(self.lib.fqd_profile_get(self.h, C.byref(p)))
+        return p
 
     # -- whole-input modes
     def append(self, mate: int, buf: bytes):

@@ -56,6 +56,10 @@ struct fqd_handle {
     double device_ms = 0.0;
     u64 launches = 0;
     bool pending_async = false;
+    cudaEvent_t timer0 = nullptr, timer1 = nullptr;
+    bool profile = false;
+    fqd_profile_t prof;
+    std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_parse, prof_insert;
     SeqState* seq = nullptr;      // whole-input modes (seqmode.cuh)
 };
 
@@ -112,6 +116,9 @@ extern "C" void fqd_destroy(fqd_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->seq) seq_destroy(h->seq);
+    if (h->timer0) { cudaEventDestroy(h->timer0); cudaEventDestroy(h->timer1); }
+    for (auto& pe : h->prof_parse) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
+    for (auto& pe : h->prof_insert) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     for (auto& pe : h->pending_events) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     for (auto e : h->event_pool) cudaEventDestroy(e);
     for (int m = 0; m < 2; ++m) {
@@ -130,6 +137,7 @@ extern "C" void fqd_destroy(fqd_handle* h) {
 static int create_impl(const fqd_config* cfg, fqd_handle* h) {
     h->cfg = *cfg;
     memset(&h->stats, 0, sizeof h->stats);
+    memset(&h->prof, 0, sizeof h->prof);
     int ndev = 0;
     CUDA_TRY(h, cudaGetDeviceCount(&ndev));
     if (cfg->device < 0 || cfg->device >= ndev) return fail(h, FQD_ERR_CUDA, "no such CUDA device");
@@ -224,8 +232,11 @@ static int launch_parse(fqd_handle* h, int m, const u8* d_raw, size_t n, u8* d_d
     p.rec_start = c.d_rec_start; p.cap = h->cap; p.keys = h->d_keys; p.key_capacity = h->key_capacity;
     p.row_words = h->row_words; p.mate_off = m * h->W; p.W = h->W; p.hash = c.d_hash; p.seq_len = nullptr; p.word0 = nullptr;
     p.strict = 1; p.hash_salt = m * 4096u; p.dup = (m == 0) ? h->d_dup : nullptr;
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (h->profile) { pe0 = get_event(h); pe1 = get_event(h); cudaEventRecord(pe0, h->stream); }
     if (h->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
     else k_parse_pack<2><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
+    if (h->profile) { cudaEventRecord(pe1, h->stream); h->prof_parse.emplace_back(pe0, pe1); h->prof.parse_launches++; h->prof.parse_bytes += n; }
     h->launches++;
     return FQD_OK;
 }
@@ -244,7 +255,10 @@ static int enqueue_fast_chunk(fqd_handle* h, const void* d_r1, size_t n1, const 
     ip.hash1 = h->mate[0].d_hash; ip.hash2 = paired ? h->mate[1].d_hash : nullptr;
     ip.ctl1 = h->mate[0].d_ctl; ip.ctl2 = paired ? h->mate[1].d_ctl : nullptr; ip.run = h->d_run; ip.dup = h->d_dup;
     k_chunk_begin<<<1, 1, 0, h->stream>>>(ip);
+    cudaEvent_t ie0 = nullptr, ie1 = nullptr;
+    if (h->profile) { ie0 = get_event(h); ie1 = get_event(h); cudaEventRecord(ie0, h->stream); }
     k_insert<<<h->sm_count * 8, HS_THREADS, 0, h->stream>>>(ip);
+    if (h->profile) { cudaEventRecord(ie1, h->stream); h->prof_insert.emplace_back(ie0, ie1); h->prof.insert_launches++; }
     k_count_dups<<<h->sm_count * 2, HS_THREADS, 0, h->stream>>>(h->d_dup, h->d_run);
     k_chunk_end<<<1, 1, 0, h->stream>>>(h->d_run);
     h->launches += 4;
@@ -255,6 +269,16 @@ static int enqueue_fast_chunk(fqd_handle* h, const void* d_r1, size_t n1, const 
 }
 
 static int drain_events(fqd_handle* h) {
+    for (auto& pe : h->prof_parse) {
+        float ms = 0.f; CUDA_TRY(h, cudaEventElapsedTime(&ms, pe.first, pe.second)); h->prof.parse_ms += ms;
+        h->event_pool.push_back(pe.first); h->event_pool.push_back(pe.second);
+    }
+    h->prof_parse.clear();
+    for (auto& pe : h->prof_insert) {
+        float ms = 0.f; CUDA_TRY(h, cudaEventElapsedTime(&ms, pe.first, pe.second)); h->prof.insert_ms += ms;
+        h->event_pool.push_back(pe.first); h->event_pool.push_back(pe.second);
+    }
+    h->prof_insert.clear();
     for (auto& pe : h->pending_events) {
         float ms = 0.f;
         CUDA_TRY(h, cudaEventElapsedTime(&ms, pe.first, pe.second));
@@ -393,6 +417,55 @@ extern "C" int fqd_sync(fqd_handle* h) {
         h->stats.dups = h->h_run->n_dups;
         fold_chunk(h, h->h_run->n_records - h->h_run->chunk_pairs, &n_ok);
     }
+    return FQD_OK;
+}
+
+extern "C" int fqd_timer_start(fqd_handle* h) {
+    if (!h) return FQD_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->timer0) { CUDA_TRY(h, cudaEventCreate(&h->timer0)); CUDA_TRY(h, cudaEventCreate(&h->timer1)); }
+    CUDA_TRY(h, cudaEventRecord(h->timer0, h->stream));
+    return FQD_OK;
+}
+extern "C" int fqd_timer_stop(fqd_handle* h, double* ms) {
+    if (!h || !h->timer0) return FQD_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaEventRecord(h->timer1, h->stream));
+    CUDA_TRY(h, cudaEventSynchronize(h->timer1));
+    float f = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&f, h->timer0, h->timer1));
+    if (ms) *ms = f;
+    return FQD_OK;
+}
+extern "C" int fqd_profile_enable(fqd_handle* h, int on) {
+    if (!h) return FQD_ERR_INVALID;
+    h->profile = on != 0;
+    if (on) memset(&h->prof, 0, sizeof h->prof);
+    return FQD_OK;
+}
+extern "C" int fqd_profile_get(fqd_handle* h, fqd_profile_t* out) {
+    if (!h || !out) return FQD_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    int rc = drain_events(h);
+    if (rc) return rc;
+    h->prof.parse_records = h->seq ? 0 : h->prof.parse_records;
+    *out = h->prof;
+    return FQD_OK;
+}
+
+extern "C" int fqd_reset(fqd_handle* h) {
+    if (!h) return FQD_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->seq) return seq_reset(h->seq, &h->err);
+    cudaEvent_t e0 = get_event(h), e1 = get_event(h);
+    CUDA_TRY(h, cudaEventRecord(e0, h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_table, 0xFF, h->n_buckets * 4 * sizeof(u64), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_run, 0, sizeof(RunState), h->stream));
+    CUDA_TRY(h, cudaEventRecord(e1, h->stream));
+    h->pending_events.emplace_back(e0, e1);
+    h->launches += 2;
+    memset(&h->stats, 0, sizeof h->stats);
     return FQD_OK;
 }
 

@@ -10,6 +10,7 @@ static int seq_create(SeqState** out, const fqd_config*, cudaStream_t, int, u32,
     *out = nullptr; *err = "sequence / unordered modes are not built yet"; return FQD_ERR_INVALID;
 }
 static void seq_destroy(SeqState*) {}
+static int seq_reset(SeqState*, std::string*) { return FQD_ERR_INVALID; }
 static int seq_append(SeqState*, int, const void*, size_t, bool, std::string*) { return FQD_ERR_INVALID; }
 static int seq_finish(SeqState*, std::string*) { return FQD_ERR_INVALID; }
 static int seq_emission(SeqState*, fqd_emission_t*, std::string*) { return FQD_ERR_INVALID; }

@@ -110,6 +110,8 @@ int fqd_push_device(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2
  * folds the chunk counters into the statistics.  Used for device-resident throughput measurement. */
 int fqd_push_device_async(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2);
 int fqd_sync(fqd_handle* h);
+/* Forget every key seen so far (empty set, counters and sticky error cleared): start a new job on the same handle. */
+int fqd_reset(fqd_handle* h);
 
 /*
  * Whole-input modes: sequence-based (sort + comparator scan) and --fast --unordered (tag join).  The caller
@@ -134,6 +136,18 @@ int fqd_stats(fqd_handle* h, fqd_stats_t* out);
 
 /* Device time (ms, CUDA events on the handle's stream) spent in kernels since creation, and kernel launches. */
 int fqd_device_time_ms(fqd_handle* h, double* ms, uint64_t* launches);
+/* Stopwatch on the handle's stream: start records a CUDA event, stop records another, waits for it and returns
+ * the elapsed device time between the two (everything enqueued on the handle in between). */
+int fqd_timer_start(fqd_handle* h);
+int fqd_timer_stop(fqd_handle* h, double* ms);
+/* Per-kernel-class profile (CUDA events around every launch of the parse+pack kernel and of the insert kernel
+ * while enabled): accumulated milliseconds and launch counts since the last fqd_profile_enable(h, 1). */
+typedef struct {
+    double   parse_ms;   uint64_t parse_launches;   uint64_t parse_bytes;    uint64_t parse_records;
+    double   insert_ms;  uint64_t insert_launches;
+} fqd_profile_t;
+int fqd_profile_enable(fqd_handle* h, int on);
+int fqd_profile_get(fqd_handle* h, fqd_profile_t* out);
 
 /*
  * Counter-based synthetic FASTQ generator: fills a DEVICE buffer with records
