@@ -257,13 +257,15 @@ def our_arm(args):
     # ---- end to end through the C ABI with HOST buffers (`e2e`)
     e2e = None
     try:
+        if os.environ.get("FQD_BENCH_SKIP_E2E"):
+            raise RuntimeError("skipped (FQD_BENCH_SKIP_E2E)")
         e2e = e2e_run(args, fqd, lib, eng, raw, n_total, chunk_reads, dups)
     except Exception as ex:   # report, never hide
         e2e = {"value": None, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0, "error": repr(ex)}
     eng.close()
     raw.free()
 
-    cpu = cpu_baseline()
+    cpu = None if os.environ.get("FQD_BENCH_SKIP_CPU") else cpu_baseline()
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": workload_config(args, n_total), "clocks": sampler.summary(),

@@ -1,0 +1,201 @@
+// io.hpp - host-side byte I/O of the drop-in binary.  Same observable behaviour as the reference's
+// FileUtils (src/file_utils.{hpp,cpp}): ".gz" is decided by the file name alone, independently per file
+// (:42-48,71-92); a missing input prints "Cannot open file <name>" and throws (:110-121 of the header).
+// Different mechanics: zlib directly instead of Boost.Iostreams, and a reader THREAD that fills a small ring
+// of PINNED blocks (fqd_host_alloc) so that inflate / read() overlap the H2D copies and the kernels - the
+// successor of BufferedInput<T>'s single malloc'd block (src/bufferedinput.hpp:28-36,57-88).
+#pragma once
+#include <zlib.h>
+
+#include <condition_variable>
+#include <cstdio>
+#include <cstring>
+#include <deque>
+#include <filesystem>
+#include <iostream>
+#include <mutex>
+#include <stdexcept>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include "../../include/fqd.h"
+
+namespace fqdhost {
+
+inline bool has_gz_ext(const std::string& name) { return std::filesystem::path(name).extension() == ".gz"; }
+
+class InputFile {
+public:
+    explicit InputFile(const std::string& name) : m_name(name), m_gz(has_gz_ext(name)) {
+        m_f = std::fopen(name.c_str(), "rb");
+        if (!m_f) {
+            std::cerr << "Cannot open file " << name << std::endl;
+            throw std::runtime_error("File does not exist or cannot be opened!");
+        }
+        if (m_gz) {
+            std::memset(&m_z, 0, sizeof m_z);
+            if (inflateInit2(&m_z, 15 + 16) != Z_OK) throw std::runtime_error("zlib: inflateInit2 failed");
+            m_in.resize(1 << 20);
+        }
+    }
+    ~InputFile() { if (m_gz) inflateEnd(&m_z); if (m_f) std::fclose(m_f); }
+    // read up to n bytes; returns the number read (< n only at end of input)
+    size_t read(char* dst, size_t n) {
+        if (!m_gz) {
+            size_t got = std::fread(dst, 1, n, m_f);
+            if (got < n) m_eof = true;
+            return got;
+        }
+        size_t got = 0;
+        while (got < n && !m_eof) {
+            if (m_z.avail_in == 0) {
+                m_z.avail_in = (uInt)std::fread(m_in.data(), 1, m_in.size(), m_f);
+                m_z.next_in = (Bytef*)m_in.data();
+                if (m_z.avail_in == 0) { m_eof = true; break; }
+            }
+            m_z.next_out = (Bytef*)dst + got;
+            size_t want = n - got;
+            m_z.avail_out = (uInt)std::min<size_t>(want, 1u << 30);
+            uInt before = m_z.avail_out;
+            int rc = inflate(&m_z, Z_NO_FLUSH);
+            got += before - m_z.avail_out;
+            if (rc == Z_STREAM_END) inflateReset(&m_z);           // multi-member gzip
+            else if (rc != Z_OK && rc != Z_BUF_ERROR) throw std::runtime_error("gzip error");
+        }
+        return got;
+    }
+    bool eof() const { return m_eof; }
+private:
+    std::string m_name;
+    bool m_gz, m_eof = false;
+    FILE* m_f = nullptr;
+    z_stream m_z;
+    std::vector<char> m_in;
+};
+
+// One pinned block: [head room | data].  The consumer copies the (small) unconsumed tail of the previous
+// block into the head room so that every chunk handed to fqd_push is contiguous.
+struct Block {
+    char* base = nullptr;
+    size_t head = 0, cap = 0, len = 0;
+    bool last = false;
+    char* data() const { return base + head; }
+};
+
+class BlockReader {
+public:
+    BlockReader(const std::string& name, size_t block_bytes, int nbuf = 3) : m_file(name), m_block(block_bytes) {
+        for (int i = 0; i < nbuf; ++i) {
+            Block* b = new Block();
+            b->head = block_bytes; b->cap = block_bytes;
+            void* p = nullptr;
+            if (fqd_host_alloc(&p, b->head + b->cap + 64) != FQD_OK) throw std::runtime_error("pinned host allocation failed");
+            b->base = (char*)p;
+            m_all.push_back(b);
+            m_free.push_back(b);
+        }
+        m_thread = std::thread([this] { this->run(); });
+    }
+    ~BlockReader() {
+        { std::lock_guard<std::mutex> g(m_mu); m_stop = true; }
+        m_cv.notify_all();
+        if (m_thread.joinable()) m_thread.join();
+        for (Block* b : m_all) { fqd_host_free(b->base); delete b; }
+    }
+    // next filled block, or nullptr after the last one; rethrows reader errors
+    Block* next() {
+        std::unique_lock<std::mutex> g(m_mu);
+        m_cv.wait(g, [this] { return !m_full.empty() || m_done || m_err; });
+        if (m_err) std::rethrow_exception(m_err);
+        if (m_full.empty()) return nullptr;
+        Block* b = m_full.front(); m_full.pop_front();
+        return b;
+    }
+    void release(Block* b) {
+        { std::lock_guard<std::mutex> g(m_mu); m_free.push_back(b); }
+        m_cv.notify_all();
+    }
+    size_t block_bytes() const { return m_block; }
+private:
+    void run() {
+        try {
+            for (;;) {
+                Block* b;
+                {
+                    std::unique_lock<std::mutex> g(m_mu);
+                    m_cv.wait(g, [this] { return !m_free.empty() || m_stop; });
+                    if (m_stop) return;
+                    b = m_free.front(); m_free.pop_front();
+                }
+                b->len = m_file.read(b->data(), b->cap);
+                b->last = m_file.eof();
+                bool last = b->last;
+                {
+                    std::lock_guard<std::mutex> g(m_mu);
+                    if (b->len > 0 || !last) m_full.push_back(b); else m_free.push_back(b);
+                    if (last) m_done = true;
+                }
+                m_cv.notify_all();
+                if (last) return;
+            }
+        } catch (...) {
+            std::lock_guard<std::mutex> g(m_mu);
+            m_err = std::current_exception();
+            m_done = true;
+            m_cv.notify_all();
+        }
+    }
+    InputFile m_file;
+    size_t m_block;
+    std::vector<Block*> m_all;
+    std::deque<Block*> m_free, m_full;
+    std::mutex m_mu;
+    std::condition_variable m_cv;
+    std::thread m_thread;
+    bool m_stop = false, m_done = false;
+    std::exception_ptr m_err;
+};
+
+// UniversalOutputFile (src/file_utils.cpp:83-92): plain or gzip by extension.
+class OutputFile {
+public:
+    explicit OutputFile(const std::string& name) : m_gz(has_gz_ext(name)) {
+        if (m_gz) {
+            m_g = gzopen(name.c_str(), "wb");
+            if (m_g) gzbuffer(m_g, 1 << 20);
+        } else {
+            m_f = std::fopen(name.c_str(), "wb");
+            if (m_f) std::setvbuf(m_f, nullptr, _IOFBF, 4 << 20);
+        }
+    }
+    ~OutputFile() { close(); }
+    void write(const char* p, size_t n) {
+        if (m_gz) {
+            while (m_g && n) { unsigned w = (unsigned)std::min<size_t>(n, 1u << 30); gzwrite(m_g, p, w); p += w; n -= w; }
+        } else if (m_f) {
+            std::fwrite(p, 1, n, m_f);
+        }
+    }
+    void close() {
+        if (m_g) { gzclose(m_g); m_g = nullptr; }
+        if (m_f) { std::fclose(m_f); m_f = nullptr; }
+    }
+private:
+    bool m_gz;
+    FILE* m_f = nullptr;
+    gzFile m_g = nullptr;
+};
+
+// ClusterFile (src/file_utils.cpp:98-112): "<out>.clusters", head = ID line, member = "--" + ID line.
+class ClusterFile {
+public:
+    void open(const std::string& base) { m_f = std::fopen((base + ".clusters").c_str(), "wb"); }
+    ~ClusterFile() { if (m_f) std::fclose(m_f); }
+    void write_cluster_head(const char* p, size_t n) { if (m_f) std::fwrite(p, 1, n, m_f); }
+    void write_cluster_item(const char* p, size_t n) { if (m_f) { std::fwrite("--", 1, 2, m_f); std::fwrite(p, 1, n, m_f); } }
+private:
+    FILE* m_f = nullptr;
+};
+
+}  // namespace fqdhost
