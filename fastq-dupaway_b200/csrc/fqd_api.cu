@@ -147,6 +147,8 @@ static int create_impl(const fqd_config* cfg, fqd_handle* h) {
     if (prop.major < 10) return fail(h, FQD_ERR_CUDA, "libfqd_cuda is built for sm_100a (B200) only");
     h->sm_count = prop.multiProcessorCount;
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_parse_pack<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_parse_pack<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 
     const int mates = cfg->paired ? 2 : 1;
     h->W = words_for(cfg->max_seq_len ? cfg->max_seq_len : 150);
@@ -234,8 +236,9 @@ static int launch_parse(fqd_handle* h, int m, const u8* d_raw, size_t n, u8* d_d
     p.strict = 1; p.hash_salt = m * 4096u; p.dup = (m == 0) ? h->d_dup : nullptr;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (h->profile) { pe0 = get_event(h); pe1 = get_event(h); cudaEventRecord(pe0, h->stream); }
-    if (h->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
-    else k_parse_pack<2><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
+    const u32 grid = n_tiles;      // one tile per CTA, processed in ticket order
+    if (h->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<grid, PP_THREADS, 0, h->stream>>>(p);
+    else k_parse_pack<2><<<grid, PP_THREADS, 0, h->stream>>>(p);
     if (h->profile) { cudaEventRecord(pe1, h->stream); h->prof_parse.emplace_back(pe0, pe1); h->prof.parse_launches++; h->prof.parse_bytes += n; }
     h->launches++;
     return FQD_OK;

@@ -23,7 +23,7 @@ constexpr u32 PP_TILE = 16384;
 constexpr u32 PP_HALO = 1024;
 constexpr u32 PP_WINDOW = PP_TILE + PP_HALO;
 constexpr u32 PP_NW = PP_WINDOW / 64;          // 64-bit mask words per window
-constexpr u32 PP_QCAP = 512;                   // records packed per round
+constexpr u32 PP_QCAP = 256;                   // records packed per round
 constexpr u32 PP_NONE = 0xFFFFFFFFu;
 
 struct ParseParams {
@@ -153,215 +153,316 @@ __device__ __forceinline__ u32 find_nl(const u64* mask64, u32 pos, const u8* raw
     return PP_NONE;
 }
 
+// Geometry + validation of one record whose first byte is at window-local offset start_l and whose LPR
+// line ends are e[0..LPR) (PP_NONE = not found before the end of the chunk).  Returns the queue entry.
+template <int LPR>
+__device__ __forceinline__ void finish_record(const ParseParams& p, const u8* win, u32 base, u32 R, u32 start_l,
+                                              u32 e0, u32 e1, u32 e2, u32 e3, u32& qoff, u32& qlen) {
+    qoff = PP_NONE; qlen = 0;
+    const u32 elast = (LPR == 4) ? e3 : e1;
+    if (elast == PP_NONE) return;                       // incomplete record: left to the next chunk
+    const u8 lead = (LPR == 4) ? '@' : '>';
+    const u32 c0 = start_l < PP_WINDOW ? win[start_l] : p.raw[(u64)base + start_l];
+    if (c0 != lead) {
+        atomicMin(&p.ctl->err_parse, ((u64)R << 16) | ((u64)PERR_BAD_START << 8) | c0);
+    } else if (LPR == 4 && (e1 - e0) != (e3 - e2)) {
+        atomicMin(&p.ctl->err_parse, ((u64)R << 16) | ((u64)PERR_LEN_MISMATCH << 8));
+    } else {
+        qoff = e0 + 1u;
+        qlen = e1 - e0 - 1u;
+    }
+}
+
+constexpr u32 PP_NLCAP = 1024;     // newline positions compacted per window; denser tiles take the slow path
+constexpr int PP_MIN_CTAS = 5;
+
 template <int LPR>   // lines per record: 4 = FASTQ, 2 = FASTA
-__global__ void __launch_bounds__(PP_THREADS, 4) k_parse_pack(const ParseParams p) {
+__global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const ParseParams p) {
     __shared__ __align__(128) u8 win[PP_WINDOW];
     __shared__ __align__(16) u64 mask64[PP_NW];
+    __shared__ u16 nlpos[PP_NLCAP];
     __shared__ u32 q_off[PP_QCAP];
     __shared__ u32 q_len[PP_QCAP];
     __shared__ u32 warp_sum[PP_THREADS / 32];
-    __shared__ u32 s_tile, s_P, s_total;
+    __shared__ u32 s_tile, s_P, s_total, s_halo;
     __shared__ __align__(8) u64 mbar;
 
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31u, warp = tid >> 5;
+    const u64 slot_base = p.run->n_records;
 
     if (tid == 0) {
-        s_tile = atomicAdd(&p.ctl->ticket, 1u);
-        mbar_init(&mbar, 1);
+        s_tile = atomicAdd(&p.ctl->ticket, 1u);      // tiles are processed in ticket order: every predecessor
+        mbar_init(&mbar, 1);                         // of a tile is already resident (look-back cannot deadlock)
     }
     __syncthreads();
     const u32 tile = s_tile;
-    const u32 base = tile * PP_TILE;
-    const u32 valid = min(PP_WINDOW, p.n - base);
-    if (tid == 0) {
-        u32 bytes = (valid + 15u) & ~15u;
-        mbar_expect_tx(&mbar, bytes);
-        bulk_g2s(win, p.raw + base, bytes, &mbar);
-    }
-    mbar_wait(&mbar, 0);
-
-    // ---- 1. newline bitmask of the window
     {
-        const u32 n_units = (valid + 15u) >> 4;
-        u16* m16 = reinterpret_cast<u16*>(mask64);
-        for (u32 u = tid; u < PP_WINDOW / 16; u += PP_THREADS) {
-            u32 m = 0;
-            if (u < n_units) {
-                uint4 v = reinterpret_cast<const uint4*>(win)[u];
-                m = nl_mask16(v);
-                u32 rem = valid - u * 16u;
-                if (rem < 16u) m &= (1u << rem) - 1u;
-            }
-            m16[u] = (u16)m;
+        const u32 base = tile * PP_TILE;
+        const u32 valid = min(PP_WINDOW, p.n - base);
+        if (tid == 0) {
+            const u32 bytes = (valid + 15u) & ~15u;
+            mbar_expect_tx(&mbar, bytes);
+            bulk_g2s(win, p.raw + base, bytes, &mbar);
         }
-    }
-    __syncthreads();
+        mbar_wait(&mbar, 0);
 
-    // ---- 2. ranks: block scan + decoupled look-back
-    const u64 my_mask = mask64[tid];                 // PP_TILE/64 == PP_THREADS words cover the tile proper
-    const u32 cnt = (u32)__popcll(my_mask);
-    u32 incl = cnt;
+        // ---- 1. newline bitmask of the window
+        {
+            const u32 n_units = (valid + 15u) >> 4;
+            u16* m16 = reinterpret_cast<u16*>(mask64);
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= (u32)d) incl += t;
-    }
-    if (lane == 31) warp_sum[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        u32 ws = lane < PP_THREADS / 32 ? warp_sum[lane] : 0u;
-        u32 wi = ws;
-#pragma unroll
-        for (int d = 1; d < 8; d <<= 1) {
-            u32 t = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-            if (lane >= (u32)d) wi += t;
-        }
-        if (lane < PP_THREADS / 32) warp_sum[lane] = wi - ws;      // exclusive warp offsets
-        const u32 total = __shfl_sync(0xFFFFFFFFu, wi, PP_THREADS / 32 - 1);
-        u32 P = 0;
-        if (tile == 0) {
-            if (lane == 0) st_volatile_u64(p.tile_state, (2ull << 32) | total);
-        } else {
-            if (lane == 0) st_volatile_u64(p.tile_state + tile, (1ull << 32) | total);
-            int look = (int)tile - 1;
-            for (;;) {
-                int idx = look - (int)lane;
-                u64 s = (2ull << 32);
-                if (idx >= 0) {
-                    do { s = ld_volatile_u64(p.tile_state + idx); } while ((s >> 32) == 0);
+            for (u32 it = 0; it < (PP_WINDOW / 16 + PP_THREADS - 1) / PP_THREADS; ++it) {
+                const u32 u = tid + it * PP_THREADS;
+                if (u < PP_WINDOW / 16) {
+                    u32 m = 0;
+                    if (u < n_units) {
+                        uint4 v = reinterpret_cast<const uint4*>(win)[u];
+                        m = nl_mask16(v);
+                        u32 rem = valid - u * 16u;
+                        if (rem < 16u) m &= (1u << rem) - 1u;
+                    }
+                    m16[u] = (u16)m;
                 }
-                u32 is_prefix = __ballot_sync(0xFFFFFFFFu, (s >> 32) == 2);
-                u32 val = (u32)s;
-                if (is_prefix) {
-                    u32 first = (u32)__ffs((int)is_prefix) - 1u;     // closest predecessor holding a prefix
-                    if (lane > first) val = 0;
-                }
+            }
+        }
+        __syncthreads();
+
+        // ---- 2. local ranks: block scan over the tile's mask words (+ the halo words, ranked after them)
+        const u64 my_mask = mask64[tid];               // PP_TILE/64 == PP_THREADS words cover the tile proper
+        const u32 cnt = (u32)__popcll(my_mask);
+        u32 incl = cnt;
 #pragma unroll
-                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, d);
-                P += val;
-                if (is_prefix) break;
-                look -= 32;
-            }
-            if (lane == 0) st_volatile_u64(p.tile_state + tile, (2ull << 32) | (u64)(P + total));
+        for (int d = 1; d < 32; d <<= 1) {
+            u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+            if (lane >= (u32)d) incl += t;
         }
-        if (lane == 0) {
-            s_P = P;
-            s_total = total;
-            if (tile == p.n_tiles - 1) {
-                u32 all = P + total;
-                p.ctl->n_newlines = all;
-                u32 nrec = all / LPR;
-                p.ctl->n_records = nrec < p.cap ? nrec : p.cap;
+        if (lane == 31) warp_sum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            u32 ws = lane < PP_THREADS / 32 ? warp_sum[lane] : 0u;
+            u32 wi = ws;
+#pragma unroll
+            for (int d = 1; d < 8; d <<= 1) {
+                u32 t = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+                if (lane >= (u32)d) wi += t;
+            }
+            if (lane < PP_THREADS / 32) warp_sum[lane] = wi - ws;      // exclusive warp offsets
+            const u32 total = __shfl_sync(0xFFFFFFFFu, wi, PP_THREADS / 32 - 1);
+            // publish this tile's aggregate as early as possible
+            if (lane == 0) {
+                if (tile == 0) st_volatile_u64(p.tile_state, (2ull << 32) | total);
+                else st_volatile_u64(p.tile_state + tile, (1ull << 32) | total);
+                s_total = total;
+            }
+            // halo words (PP_HALO/64 <= 32): ranks continue after the tile's
+            const u64 hm = lane < (PP_NW - PP_THREADS) ? mask64[PP_THREADS + lane] : 0ull;
+            const u32 hc = (u32)__popcll(hm);
+            u32 hi = hc;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                u32 t = __shfl_up_sync(0xFFFFFFFFu, hi, d);
+                if (lane >= (u32)d) hi += t;
+            }
+            const u32 htot = __shfl_sync(0xFFFFFFFFu, hi, 31);
+            if (lane == 0) s_halo = htot;
+            u32 r = total + hi - hc;
+            u64 m = hm;
+            while (m) {
+                u32 b = (u32)__ffsll((long long)m) - 1u;
+                m &= m - 1;
+                if (r < PP_NLCAP) nlpos[r] = (u16)((PP_THREADS + lane) * 64u + b);
+                ++r;
             }
         }
-    }
-    __syncthreads();
-    const u32 P = s_P;
-    const u32 T = s_total;
-    const u32 ex = P + warp_sum[warp] + (incl - cnt);      // global rank of my first newline
-
-    // records owned by this tile: those whose preceding newline (rank LPR*R-1) lies in the tile proper
-    u32 R_first = (P + LPR) / LPR;
-    const u32 R_last = (P + T) / LPR;
-    if (tile == 0) R_first = 0;
-    const u32 n_owned = R_last >= R_first ? R_last - R_first + 1u : 0u;
-    const u64 slot_base = p.run->n_records;
-    const u8 lead = (LPR == 4) ? '@' : '>';
-
-    for (u32 rbase = 0; rbase < n_owned; rbase += PP_QCAP) {
-        // ---- 3. owners: geometry + validation
+        __syncthreads();
+        const u32 T = s_total;
+        const u32 lex = warp_sum[warp] + (incl - cnt);      // local rank of my first newline
         {
             u64 m = my_mask;
-            u32 k = ex;
-            bool virt = (tile == 0 && tid == 0);      // record 0 starts at offset 0 with no newline before it
-            while (m || virt) {
-                u32 R, start_l;
-                if (virt) { virt = false; R = 0; start_l = 0; }
-                else {
-                    u32 b = (u32)__ffsll((long long)m) - 1u;
-                    m &= m - 1;
-                    u32 kk = k++;
-                    if ((kk + 1u) % LPR) continue;
-                    R = (kk + 1u) / LPR;
-                    start_l = tid * 64u + b + 1u;
-                }
-                const u32 gstart = base + start_l;
-                if (rbase == 0 && R <= p.cap) {
-                    p.rec_start[R] = gstart;
-                    if (p.dup && R < p.cap) p.dup[R] = 0;
-                }
-                const u32 o = R - R_first;
-                if (o < rbase || o >= rbase + PP_QCAP) continue;
-                u32 qoff = PP_NONE, qlen = 0;
-                if (R < p.cap && gstart < p.n) {
-                    u32 e0 = find_nl(mask64, start_l, p.raw, base, p.n);
-                    u32 e1 = e0 == PP_NONE ? PP_NONE : find_nl(mask64, e0 + 1u, p.raw, base, p.n);
-                    u32 e3 = e1;
-                    u32 e2 = e1;
-                    if (LPR == 4) {
-                        e2 = e1 == PP_NONE ? PP_NONE : find_nl(mask64, e1 + 1u, p.raw, base, p.n);
-                        e3 = e2 == PP_NONE ? PP_NONE : find_nl(mask64, e2 + 1u, p.raw, base, p.n);
+            u32 r = lex;
+            while (m) {
+                u32 b = (u32)__ffsll((long long)m) - 1u;
+                m &= m - 1;
+                if (r < PP_NLCAP) nlpos[r] = (u16)(tid * 64u + b);
+                ++r;
+            }
+        }
+        // ---- decoupled look-back (warp 0) for the global rank of the tile's first newline
+        if (warp == 0) {
+            u32 P = 0;
+            if (tile != 0) {
+                // window of 128 predecessors per hop (4 per lane): one L2 round trip must cover more tiles than
+                // the chip starts in that time, otherwise the distance to the nearest published prefix grows
+                int look = (int)tile - 1;
+                for (;;) {
+                    u64 s4[4];
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        int idx = look - (int)lane - 32 * r;
+                        s4[r] = (2ull << 32);
+                        if (idx >= 0) s4[r] = ld_volatile_u64(p.tile_state + idx);
                     }
-                    if (e3 != PP_NONE) {     // complete record
-                        u32 c0 = start_l < PP_WINDOW ? win[start_l] : p.raw[(u64)base + start_l];
-                        if (c0 != lead) {
-                            atomicMin(&p.ctl->err_parse, ((u64)R << 16) | ((u64)PERR_BAD_START << 8) | c0);
-                        } else if (LPR == 4 && (e1 - e0) != (e3 - e2)) {
-                            atomicMin(&p.ctl->err_parse, ((u64)R << 16) | ((u64)PERR_LEN_MISMATCH << 8));
-                        } else {
-                            qoff = e0 + 1u;
-                            qlen = e1 - e0 - 1u;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        int idx = look - (int)lane - 32 * r;
+                        while ((s4[r] >> 32) == 0) s4[r] = ld_volatile_u64(p.tile_state + idx);
+                    }
+                    bool found = false;
+#pragma unroll
+                    for (int r = 0; r < 4; ++r) {
+                        if (!found) {
+                            u32 is_prefix = __ballot_sync(0xFFFFFFFFu, (s4[r] >> 32) == 2);
+                            u32 val = (u32)s4[r];
+                            if (is_prefix) {
+                                u32 first = (u32)__ffs((int)is_prefix) - 1u;     // closest predecessor holding a prefix
+                                if (lane > first) val = 0;
+                                found = true;
+                            }
+#pragma unroll
+                            for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, d);
+                            P += val;
                         }
                     }
+                    if (found) break;
+                    look -= 128;
                 }
-                q_off[o - rbase] = qoff;
-                q_len[o - rbase] = qlen;
+                if (lane == 0) st_volatile_u64(p.tile_state + tile, (2ull << 32) | (u64)(P + T));
+            }
+            if (lane == 0) {
+                s_P = P;
+                if (tile == p.n_tiles - 1) {
+                    u32 all = P + T;
+                    p.ctl->n_newlines = all;
+                    u32 nrec = all / LPR;
+                    p.ctl->n_records = nrec < p.cap ? nrec : p.cap;
+                }
             }
         }
         __syncthreads();
+        const u32 P = s_P;
+        const u32 WN = T + s_halo;                          // newlines in the whole window
+        const bool dense = WN <= PP_NLCAP;
 
-        // ---- 4. pack: 8 lanes per record
-        {
+        // records owned by this tile: those whose preceding newline (rank LPR*R-1) lies in the tile proper
+        u32 R_first = (P + LPR) / LPR;
+        const u32 R_last = (P + T) / LPR;
+        if (tile == 0) R_first = 0;
+        const u32 n_owned = R_last >= R_first ? R_last - R_first + 1u : 0u;
+
+        for (u32 rbase = 0; rbase < n_owned; rbase += PP_QCAP) {
             const u32 n_round = min(PP_QCAP, n_owned - rbase);
-            const u32 g8 = tid >> 3, l8 = tid & 7u;
-            const u32 gmask = 0xFFu << (lane & 24u);
-            for (u32 q = g8; q < n_round; q += PP_THREADS / 8) {
-                const u32 off = q_off[q];
-                if (off == PP_NONE) continue;
-                const u32 nb = q_len[q];
-                const u32 R = R_first + rbase + q;
-                const u64 slot = slot_base + R;
-                if (slot >= p.key_capacity) { if (l8 == 0) p.ctl->too_long = 2; continue; }
-                if (nb > p.W * BASES_PER_WORD) { if (l8 == 0) p.ctl->too_long = 1; continue; }
-                u64* row = p.keys + slot * p.row_words + p.mate_off;
-                u64 hsum = 0;
-                u32 bad = 0, badw = 0;
-                for (u32 w = l8; w < p.W; w += 8) {
-                    u32 done = w * BASES_PER_WORD;
-                    u32 nvalid = nb > done ? min(nb - done, (u32)BASES_PER_WORD) : 0u;
-                    PackOut po = pack_word(win, p.raw, base, p.n, off + done, nvalid);
-                    row[w] = po.word;
-                    hsum += word_hash(po.word, pos_key(p.hash_salt + w));
-                    if (po.bad && !bad) { bad = po.bad; badw = w; }
+            // ---- 3. owners: geometry + validation
+            if (dense) {
+                // one thread per record: the record's line ends are consecutive entries of nlpos
+                for (u32 o = tid; o < n_round; o += PP_THREADS) {
+                    const u32 R = R_first + rbase + o;
+                    const int j0 = (int)(LPR * R) - 1 - (int)P;          // local rank of the newline before the record
+                    const u32 start_l = j0 < 0 ? 0u : (u32)nlpos[j0] + 1u;
+                    const u32 gstart = base + start_l;
+                    u32 qoff = PP_NONE, qlen = 0;
+                    if (R <= p.cap) {
+                        p.rec_start[R] = gstart;
+                        if (p.dup && R < p.cap) p.dup[R] = 0;
+                    }
+                    if (R < p.cap && gstart < p.n) {
+                        u32 e[4];
+#pragma unroll
+                        for (int k = 0; k < LPR; ++k) {
+                            const u32 j = (u32)(j0 + 1 + k);
+                            if (j < WN) e[k] = nlpos[j];
+                            else {
+                                const u32 from = k == 0 ? start_l : (e[k - 1] == PP_NONE ? PP_NONE : e[k - 1] + 1u);
+                                e[k] = from == PP_NONE ? PP_NONE : find_nl(mask64, max(from, PP_WINDOW), p.raw, base, p.n);
+                            }
+                        }
+                        finish_record<LPR>(p, win, base, R, start_l, e[0], e[1], LPR == 4 ? e[2] : e[1], LPR == 4 ? e[3] : e[1], qoff, qlen);
+                    }
+                    q_off[o] = qoff;
+                    q_len[o] = qlen;
                 }
-                hsum += __shfl_xor_sync(gmask, hsum, 1);
-                hsum += __shfl_xor_sync(gmask, hsum, 2);
-                hsum += __shfl_xor_sync(gmask, hsum, 4);
-                if (l8 == 0) {
-                    p.hash[R] = mix64(hsum);
-                    if (p.seq_len) p.seq_len[R] = nb;
-                }
-                if (p.word0 && l8 == 0) p.word0[R] = row[0];
-                if (bad && p.strict) {
-                    u32 pos = badw * BASES_PER_WORD + ((bad >> 8) & 0xFFu);
-                    atomicMin(&p.ctl->err_base, ((u64)R << 32) | ((u64)pos << 8) | (bad & 0xFFu));
-                } else if (bad) {
-                    p.ctl->pad = 1;   // non-ACGTN byte seen in a mode that accepts any byte
+            } else {
+                // very dense tile (tiny records): every thread walks its own newline bits
+                u64 m = my_mask;
+                u32 k = P + lex;
+                bool virt = (tile == 0 && tid == 0);      // record 0 starts at offset 0 with no newline before it
+                while (m || virt) {
+                    u32 R, start_l;
+                    if (virt) { virt = false; R = 0; start_l = 0; }
+                    else {
+                        u32 b = (u32)__ffsll((long long)m) - 1u;
+                        m &= m - 1;
+                        u32 kk = k++;
+                        if ((kk + 1u) % LPR) continue;
+                        R = (kk + 1u) / LPR;
+                        start_l = tid * 64u + b + 1u;
+                    }
+                    const u32 gstart = base + start_l;
+                    if (rbase == 0 && R <= p.cap) {
+                        p.rec_start[R] = gstart;
+                        if (p.dup && R < p.cap) p.dup[R] = 0;
+                    }
+                    const u32 o = R - R_first;
+                    if (o < rbase || o >= rbase + PP_QCAP) continue;
+                    u32 qoff = PP_NONE, qlen = 0;
+                    if (R < p.cap && gstart < p.n) {
+                        u32 e0 = find_nl(mask64, start_l, p.raw, base, p.n);
+                        u32 e1 = e0 == PP_NONE ? PP_NONE : find_nl(mask64, e0 + 1u, p.raw, base, p.n);
+                        u32 e3 = e1, e2 = e1;
+                        if (LPR == 4) {
+                            e2 = e1 == PP_NONE ? PP_NONE : find_nl(mask64, e1 + 1u, p.raw, base, p.n);
+                            e3 = e2 == PP_NONE ? PP_NONE : find_nl(mask64, e2 + 1u, p.raw, base, p.n);
+                        }
+                        finish_record<LPR>(p, win, base, R, start_l, e0, e1, e2, e3, qoff, qlen);
+                    }
+                    q_off[o - rbase] = qoff;
+                    q_len[o - rbase] = qlen;
                 }
             }
+            __syncthreads();
+
+            // ---- 4. pack: 8 lanes per record
+            {
+                const u32 g8 = tid >> 3, l8 = tid & 7u;
+                const u32 gmask = 0xFFu << (lane & 24u);
+                for (u32 q = g8; q < n_round; q += PP_THREADS / 8) {
+                    const u32 off = q_off[q];
+                    if (off == PP_NONE) continue;
+                    const u32 nb = q_len[q];
+                    const u32 R = R_first + rbase + q;
+                    const u64 slot = slot_base + R;
+                    if (slot >= p.key_capacity) { if (l8 == 0) p.ctl->too_long = 2; continue; }
+                    if (nb > p.W * BASES_PER_WORD) { if (l8 == 0) p.ctl->too_long = 1; continue; }
+                    u64* row = p.keys + slot * p.row_words + p.mate_off;
+                    u64 hsum = 0, w0 = 0;
+                    u32 bad = 0, badw = 0;
+                    for (u32 w = l8; w < p.W; w += 8) {
+                        u32 done = w * BASES_PER_WORD;
+                        u32 nvalid = nb > done ? min(nb - done, (u32)BASES_PER_WORD) : 0u;
+                        PackOut po = pack_word(win, p.raw, base, p.n, off + done, nvalid);
+                        row[w] = po.word;
+                        if (w == 0) w0 = po.word;
+                        hsum += word_hash(po.word, pos_key(p.hash_salt + w));
+                        if (po.bad && !bad) { bad = po.bad; badw = w; }
+                    }
+                    hsum += __shfl_xor_sync(gmask, hsum, 1);
+                    hsum += __shfl_xor_sync(gmask, hsum, 2);
+                    hsum += __shfl_xor_sync(gmask, hsum, 4);
+                    if (l8 == 0) {
+                        p.hash[R] = mix64(hsum);
+                        if (p.seq_len) p.seq_len[R] = nb;
+                        if (p.word0) p.word0[R] = w0;
+                    }
+                    if (bad && p.strict) {
+                        u32 pos = badw * BASES_PER_WORD + ((bad >> 8) & 0xFFu);
+                        atomicMin(&p.ctl->err_base, ((u64)R << 32) | ((u64)pos << 8) | (bad & 0xFFu));
+                    } else if (bad) {
+                        p.ctl->pad = 1;   // non-ACGTN byte seen in a mode that accepts any byte
+                    }
+                }
+            }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
