@@ -45,7 +45,8 @@ class Config(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("total", C.c_uint64), ("dups", C.c_uint64), ("unmatched", C.c_uint64),
-                ("err", C.c_int32), ("err_char", C.c_int32), ("err_record", C.c_uint64)]
+                ("err", C.c_int32), ("err_char", C.c_int32), ("err_record", C.c_uint64),
+                ("err_mate", C.c_int32), ("reserved", C.c_int32)]
 
 
 class ChunkResult(C.Structure):

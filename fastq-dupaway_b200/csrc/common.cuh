@@ -54,16 +54,19 @@ __device__ __forceinline__ u64 mix64(u64 x) {
     x ^= x >> 32;
     return x;
 }
-__device__ __forceinline__ u64 pos_key(u32 w) {           // odd 64-bit key for word position w
+// Two odd 32-bit keys for word position w (salted per mate).  A key row hashes to
+//     sum_w  lo32(word_w) * keyA(w) + hi32(word_w) * keyB(w)      (mod 2^64, two IMAD.WIDE per word)
+// stored raw by K1 and finalised with mix64 by whoever consumes it.  The hash only places keys in the table and
+// provides the 24-bit tag; equality is always decided on the full key rows.
+__host__ __device__ __forceinline__ uint2 pos_keys(u32 w) {
     u64 z = (u64)(w + 1) * 0x9E3779B97F4A7C15ull;
     z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
     z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
-    return (z ^ (z >> 31)) | 1ull;
+    z ^= z >> 31;
+    return make_uint2((u32)z | 1u, (u32)(z >> 32) | 1u);
 }
-__device__ __forceinline__ u64 word_hash(u64 word, u64 key) {
-    u32 lo = (u32)word, hi = (u32)(word >> 32);
-    u64 k2 = (key >> 17) | (key << 47) | 1ull;
-    return (u64)lo * key + (u64)hi * k2 + ((u64)lo << 32 ^ (u64)hi);   // mod 2^64
+__device__ __forceinline__ u64 word_hash(u64 word, uint2 k) {
+    return (u64)(u32)word * k.x + (u64)(u32)(word >> 32) * k.y;
 }
 __device__ __forceinline__ u64 pair_hash(u64 h1, u64 h2) {
     return mix64(h1 + 0x9E3779B97F4A7C15ull * ((h2 << 31) | (h2 >> 33)));

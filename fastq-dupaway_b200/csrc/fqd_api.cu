@@ -302,7 +302,7 @@ static int fold_chunk(fqd_handle* h, u64 first_record, u64* n_ok) {
     u64 pairs = h->h_run->chunk_pairs;
     *n_ok = pairs;
     if (h->stats.err) { *n_ok = 0; return h->stats.err; }
-    long long best_t = -1; int best_code = 0, best_char = 0; u64 best_rec = 0, best_ok = 0;
+    long long best_t = -1; int best_code = 0, best_char = 0, best_mate = 0; u64 best_rec = 0, best_ok = 0;
     bool have = false;
     for (int m = 0; m < mates; ++m) {
         const ChunkCtl& c = *h->mate[m].h_ctl;
@@ -311,7 +311,7 @@ static int fold_chunk(fqd_handle* h, u64 first_record, u64* n_ok) {
             if (e <= pairs) {     // a malformed record right after the last processed pair still aborts it
                 long long t = e == 0 ? (first_record == 0 ? -8 + m : -4 + m) : (long long)(e - 1) * 4 + m;
                 if (!have || t < best_t) {
-                    have = true; best_t = t; best_char = ch; best_rec = first_record + e;
+                    have = true; best_t = t; best_char = ch; best_rec = first_record + e; best_mate = m;
                     best_code = code == PERR_BAD_START ? FQD_ERR_BAD_START : FQD_ERR_LEN_MISMATCH;
                     best_ok = e == 0 ? 0 : e - 1;
                 }
@@ -322,7 +322,7 @@ static int fold_chunk(fqd_handle* h, u64 first_record, u64* n_ok) {
             if (j < pairs) {
                 long long t = (long long)j * 4 + 2 + m;
                 if (!have || t < best_t) {
-                    have = true; best_t = t; best_char = ch; best_rec = first_record + j; best_code = FQD_ERR_BAD_BASE; best_ok = j;
+                    have = true; best_t = t; best_char = ch; best_rec = first_record + j; best_code = FQD_ERR_BAD_BASE; best_ok = j; best_mate = m;
                 }
             }
         }
@@ -330,7 +330,7 @@ static int fold_chunk(fqd_handle* h, u64 first_record, u64* n_ok) {
     }
     if (h->h_run->capacity_exceeded && !have) { have = true; best_code = FQD_ERR_CAPACITY; best_ok = pairs; }
     if (have) {
-        h->stats.err = best_code; h->stats.err_char = best_char; h->stats.err_record = best_rec;
+        h->stats.err = best_code; h->stats.err_char = best_char; h->stats.err_record = best_rec; h->stats.err_mate = best_mate;
         *n_ok = best_ok;
     }
     return h->stats.err;

@@ -62,8 +62,8 @@ __global__ void __launch_bounds__(HS_THREADS) k_insert(const InsertParams p) {
     const u64 slot_base = p.run->n_records;
     const u32 stride = gridDim.x * blockDim.x;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
-        u64 h = p.hash1[i];
-        if (p.hash2) h = pair_hash(h, p.hash2[i]);
+        u64 h = p.hash1[i];                       // raw multilinear sums from K1
+        h = p.hash2 ? pair_hash(h, p.hash2[i]) : mix64(h);
         const u64 slot = slot_base + i;
         const u64 tag = (h >> 8) & 0xFFFFFFull;
         const u64 mine = (tag << 40) | slot;

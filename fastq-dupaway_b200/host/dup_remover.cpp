@@ -1,0 +1,295 @@
+// dup_remover.cpp - the two drivers of the drop-in binary on top of the C ABI (include/fqd.h).
+#include "dup_remover.hpp"
+
+#include <sys/stat.h>
+
+#include <algorithm>
+#include <cstring>
+#include <iostream>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+#include "../../include/fqd.h"
+#include "io.hpp"
+
+namespace fqdhost {
+namespace {
+
+struct EngineDeleter { void operator()(fqd_handle* h) const { fqd_destroy(h); } };
+using EnginePtr = std::unique_ptr<fqd_handle, EngineDeleter>;
+
+struct Restart : std::exception { int what_code; explicit Restart(int c) : what_code(c) {} };
+
+[[noreturn]] void throw_engine_error(fqd_handle* h, int rc) {
+    std::string msg = "CUDA engine failure";
+    const char* e = fqd_last_error(h);
+    if (e && *e) msg += std::string(": ") + e;
+    msg += " (status " + std::to_string(rc) + ")";
+    throw std::runtime_error(msg);
+}
+
+// The reference's messages for data errors (src/seq_utils.cpp:17-19, src/fastqview.cpp:121-138,
+// src/fastaview.cpp:95-100, src/bufferedinput.hpp:82-85).
+[[noreturn]] void throw_data_error(const fqd_stats_t& st, bool fasta, const char* rec = nullptr, size_t rec_len = 0) {
+    switch (st.err) {
+    case FQD_ERR_BAD_BASE:
+        std::cerr << "Error: unknown character in DNA sequence: " << (char)st.err_char << '\n';
+        throw std::runtime_error("Supported sequence character set: {A, N, C, G, T}!");
+    case FQD_ERR_BAD_START:
+        std::cerr << "Invalid record start character: " << (char)st.err_char << std::endl;
+        throw std::runtime_error(fasta ? "Fasta record should start with > symbol!" : "Fastq record should start with @ symbol!");
+    case FQD_ERR_LEN_MISMATCH: {
+        if (rec) {   // "Found sequence <seq> of length <n> and quality string <qual> of length <m>"
+            const char* end = rec + rec_len;
+            const char* l[5] = {rec, nullptr, nullptr, nullptr, nullptr};
+            for (int i = 1; i < 5; ++i) {
+                const char* nl = l[i - 1] ? (const char*)memchr(l[i - 1], '\n', end - l[i - 1]) : nullptr;
+                l[i] = nl ? nl + 1 : nullptr;
+            }
+            if (l[4]) {
+                std::cerr << "Found sequence ";
+                std::cerr.write(l[1], l[2] - l[1] - 1);
+                std::cerr << " of length " << (l[2] - l[1]) << " and quality string ";
+                std::cerr.write(l[3], l[4] - l[3] - 1);
+                std::cerr << " of length " << (l[4] - l[3]) << std::endl;
+            }
+        }
+        throw std::runtime_error("Sequence and Quality fields of Fastq record should have the same length!");
+    }
+    case FQD_ERR_EMPTY:
+        throw std::runtime_error("Not enough memory to read a single object!");
+    default:
+        throw std::runtime_error("Data error " + std::to_string(st.err));
+    }
+}
+
+size_t file_size_or_zero(const std::string& name) {
+    struct stat sb;
+    return stat(name.c_str(), &sb) == 0 ? (size_t)sb.st_size : 0;
+}
+
+// Longest sequence line and mean record size of a sample (first bytes of the first block).
+void sample_geometry(const char* p, size_t n, int lpr, size_t& max_seq, double& avg_rec) {
+    max_seq = 0; avg_rec = 0;
+    size_t line = 0, recs = 0, last_rec_end = 0;
+    const char* cur = p; const char* end = p + n;
+    while (cur < end) {
+        const char* nl = (const char*)memchr(cur, '\n', end - cur);
+        if (!nl) break;
+        if ((int)(line % lpr) == 1) max_seq = std::max<size_t>(max_seq, nl - cur);
+        ++line;
+        if ((int)(line % lpr) == 0) { ++recs; last_rec_end = nl + 1 - p; }
+        cur = nl + 1;
+    }
+    if (recs) avg_rec = (double)last_rec_end / recs; else { avg_rec = 64; max_seq = std::max<size_t>(max_seq, n); }
+}
+
+struct MateStream {
+    std::unique_ptr<BlockReader> reader;
+    Block* cur = nullptr;      // block that holds [ptr, ptr+len)
+    Block* peeked = nullptr;   // next block, fetched early to look at its first byte
+    char* ptr = nullptr;
+    size_t len = 0;
+    bool no_more = false;      // reader exhausted
+    Block* fetch() {
+        if (peeked) { Block* b = peeked; peeked = nullptr; return b; }
+        if (no_more) return nullptr;
+        Block* b = reader->next();
+        if (!b) no_more = true;
+        return b;
+    }
+    // append the next block behind the unconsumed tail (tail is copied into the block's head room)
+    bool refill() {
+        Block* b = fetch();
+        if (!b) return false;
+        if (len > b->head) throw std::runtime_error("Not enough memory to read a single object!");
+        char* dst = b->data() - len;
+        if (len) memcpy(dst, ptr, len);
+        if (cur) reader->release(cur);
+        cur = b; ptr = dst; len += b->len;
+        return true;
+    }
+    // first byte that follows [ptr, ptr+len) in the file, or -1 at end of input
+    int peek_next_byte() {
+        if (!peeked) {
+            if (no_more) return -1;
+            peeked = reader->next();
+            if (!peeked) { no_more = true; return -1; }
+        }
+        return peeked->len ? (unsigned char)peeked->data()[0] : -1;
+    }
+};
+
+void write_survivors(OutputFile& out, const char* base, const uint32_t* rec_start, const uint8_t* dup, size_t n) {
+    size_t i = 0;
+    while (i < n) {
+        if (dup[i]) { ++i; continue; }
+        size_t j = i;
+        while (j + 1 < n && !dup[j + 1]) ++j;
+        out.write(base + rec_start[i], rec_start[j + 1] - rec_start[i]);
+        i = j + 1;
+    }
+}
+
+}  // namespace
+
+// -------------------------------------------------------------------------------------------------------------
+// HashDupRemover: --fast, input order preserved (src/hash_dup_remover.hpp:105-148,194-255)
+void HashDupRemover::filterSE(const std::string& infile, const std::string& outfile) {
+    const std::string in[1] = {infile}, out[1] = {outfile};
+    run_ordered(in, out, 1);
+}
+
+void HashDupRemover::filterPE(const std::string& infile1, const std::string& infile2,
+                              const std::string& outfile1, const std::string& outfile2, bool unordered) {
+    const std::string in[2] = {infile1, infile2}, out[2] = {outfile1, outfile2};
+    if (unordered) run_whole_input(FQD_MODE_FAST, m_fasta, true, 0, 2, in, out, false, m_verbose, m_memlimit, m_device);
+    else run_ordered(in, out, 2);
+}
+
+void HashDupRemover::run_ordered(const std::string* in, const std::string* out, int mates) {
+    const int lpr = m_fasta ? 2 : 4;
+    const char lead = m_fasta ? '>' : '@';
+    // pinned staging: 3 blocks (head room + data) per input file inside the -m budget
+    size_t block = (size_t)m_memlimit / (size_t)(mates * 3 * 2);
+    block = std::min<size_t>(std::max<size_t>(block, 4u << 20), 256u << 20) & ~(size_t)4095;
+    double growth = 1.0;
+    unsigned seq_growth = 0;
+
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        // outputs are created first, like the reference (an unreadable input leaves empty outputs behind)
+        std::vector<std::unique_ptr<OutputFile>> outs;
+        for (int m = 0; m < mates; ++m) outs.emplace_back(new OutputFile(out[m]));
+        MateStream ms[2];
+        for (int m = 0; m < mates; ++m) ms[m].reader.reset(new BlockReader(in[m], block));
+        for (int m = 0; m < mates; ++m)
+            if (!ms[m].refill()) throw std::runtime_error("Not enough memory to read a single object!");   // empty file
+        for (int m = 0; m < mates; ++m)       // the very first record is validated by set_file()'s refresh (src/bufferedinput.hpp:76-86)
+            if (ms[m].len && ms[m].ptr[0] != lead) {
+                fqd_stats_t st; memset(&st, 0, sizeof st); st.err = FQD_ERR_BAD_START; st.err_char = (unsigned char)ms[m].ptr[0];
+                throw_data_error(st, m_fasta);
+            }
+
+        size_t max_seq = 0; double avg_rec = 0; uint64_t est_records = 0;
+        for (int m = 0; m < mates; ++m) {
+            size_t ms_ = 0; double ar = 0;
+            sample_geometry(ms[m].ptr, std::min<size_t>(ms[m].len, 8u << 20), lpr, ms_, ar);
+            max_seq = std::max(max_seq, ms_);
+            size_t fsz = file_size_or_zero(in[m]);
+            double expand = has_gz_ext(in[m]) ? 8.0 : 1.0;
+            uint64_t est = (uint64_t)((double)fsz * expand / std::max(ar, 8.0) * 1.02) + (1u << 16);
+            est_records = m == 0 ? est : std::min(est_records, est);
+            avg_rec = std::max(avg_rec, ar);
+        }
+        fqd_config cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.abi_version = FQD_ABI_VERSION; cfg.device = m_device; cfg.mode = FQD_MODE_FAST;
+        cfg.format = m_fasta ? FQD_FORMAT_FASTA : FQD_FORMAT_FASTQ; cfg.paired = mates == 2;
+        cfg.max_seq_len = (uint32_t)((std::max<size_t>(max_seq, 20) + 19) / 20 * 20) << seq_growth;
+        cfg.max_records = (uint64_t)((double)est_records * growth);
+        cfg.max_chunk_bytes = 2 * block + 4096;
+        cfg.max_chunk_records = 0;
+        fqd_handle* hraw = nullptr;
+        int rc = fqd_create(&cfg, &hraw);
+        if (rc) throw_engine_error(nullptr, rc);
+        EnginePtr eng(hraw);
+
+        bool restart = false;
+        uint64_t total = 0, dups = 0;
+        for (;;) {
+            // make sure every mate has something new to parse; a mate whose tail is already large waits
+            for (int m = 0; m < mates; ++m)
+                if (ms[m].len < block / 2) ms[m].refill();
+            fqd_chunk_result res;
+            rc = fqd_push(eng.get(), ms[0].ptr, ms[0].len, mates == 2 ? ms[1].ptr : nullptr, mates == 2 ? ms[1].len : 0, &res);
+            if (rc) throw_engine_error(eng.get(), rc);
+            fqd_stats_t st;
+            fqd_stats(eng.get(), &st);
+            if (st.err == FQD_ERR_SEQ_TOO_LONG) { ++seq_growth; restart = true; break; }
+            if (st.err == FQD_ERR_CAPACITY) { growth *= 2.0; restart = true; break; }
+            size_t n = (size_t)res.n_records;
+            uint64_t chunk_dups = n - res.n_survivors;
+            // A record that does not start with '@'/'>' aborts the run while the record BEFORE it is fetched
+            // (src/bufferedinput.hpp:90-103 pre-parses it; src/fastqview.cpp:91-92 checks the first byte before
+            // anything else), so that last record is not written.  Inside the chunk the engine reports it; at the
+            // chunk's end the byte comes from the carried tail or from the next block.
+            int tail_err_mate = -1, tail_char = 0;
+            if (st.err == 0 && n > 0) {
+                for (int m = 0; m < mates && tail_err_mate < 0; ++m) {
+                    int nb = res.consumed[m] < ms[m].len ? (unsigned char)ms[m].ptr[res.consumed[m]] : ms[m].peek_next_byte();
+                    if (nb >= 0 && nb != lead) { tail_err_mate = m; tail_char = nb; }
+                }
+            }
+            if (tail_err_mate >= 0) {
+                const uint8_t last_dup = res.dup[n - 1];
+                n -= 1;
+                chunk_dups -= last_dup;
+            }
+            for (int m = 0; m < mates; ++m) write_survivors(*outs[m], ms[m].ptr, res.rec_start[m], res.dup, n);
+            total += n; dups += chunk_dups;
+            if (tail_err_mate >= 0) {
+                st.err = FQD_ERR_BAD_START; st.err_char = tail_char;
+                for (auto& o : outs) o->close();
+                throw_data_error(st, m_fasta);
+            }
+            if (st.err) {
+                for (auto& o : outs) o->close();
+                const int em = st.err_mate;
+                size_t e = (size_t)(st.err_record - res.first_record);
+                const char* rec = nullptr; size_t rl = 0;
+                if (st.err == FQD_ERR_LEN_MISMATCH) { rec = ms[em].ptr + res.rec_start[em][e]; rl = ms[em].len - res.rec_start[em][e]; }
+                throw_data_error(st, m_fasta, rec, rl);
+            }
+            for (int m = 0; m < mates; ++m) { ms[m].ptr += res.consumed[m]; ms[m].len -= res.consumed[m]; }
+            if (res.n_records == 0) {
+                // nothing complete in what we have: read more, or stop at the end of a file
+                bool progressed = false;
+                for (int m = 0; m < mates; ++m) {
+                    bool has_rec = false;   // does this mate still hold a complete record?  (cheap upper bound: lpr newlines)
+                    size_t cnt = 0; const char* c = ms[m].ptr; const char* e2 = c + ms[m].len;
+                    while (cnt < (size_t)lpr && c < e2) { const char* nl = (const char*)memchr(c, '\n', e2 - c); if (!nl) break; ++cnt; c = nl + 1; }
+                    has_rec = cnt == (size_t)lpr;
+                    if (!has_rec) progressed |= ms[m].refill();
+                }
+                if (!progressed) break;      // a file is exhausted: stop at the shorter one (src/hash_dup_remover.hpp:228-230)
+            }
+        }
+        if (restart) continue;
+        if (total == 0) {
+            fqd_stats_t st; memset(&st, 0, sizeof st); st.err = FQD_ERR_EMPTY;
+            throw_data_error(st, m_fasta);
+        }
+        for (auto& o : outs) o->close();
+        if (m_verbose) {
+            if (mates == 1) std::cout << total << " reads processed, out of which " << dups << " duplicates were removed.\n";
+            else std::cout << total << " read pairs processed, out of which " << dups << " duplicates were removed.\n";
+        }
+        return;
+    }
+    throw std::runtime_error("input exceeds the device capacity of the fast-mode key store");
+}
+
+// -------------------------------------------------------------------------------------------------------------
+// SeqDupRemover: sort + comparator scan, output in sorted order (src/seq_dup_remover.hpp:40-109,111-218)
+void SeqDupRemover::filterSE(const std::string& infile, const std::string& outfile) {
+    const std::string in[1] = {infile}, out[1] = {outfile};
+    int mode = m_ctype == CT_LOOSE ? FQD_MODE_SEQ_LOOSE : m_ctype == CT_HAMMING ? FQD_MODE_SEQ_HAMMING : FQD_MODE_SEQ_TIGHT;
+    run_whole_input(mode, m_fasta, false, m_dist, 1, in, out, m_write_clusters, m_verbose, m_memlimit, m_device);
+}
+
+void SeqDupRemover::filterPE(const std::string& infile1, const std::string& infile2,
+                             const std::string& outfile1, const std::string& outfile2) {
+    const std::string in[2] = {infile1, infile2}, out[2] = {outfile1, outfile2};
+    int mode = m_ctype == CT_LOOSE ? FQD_MODE_SEQ_LOOSE : m_ctype == CT_HAMMING ? FQD_MODE_SEQ_HAMMING : FQD_MODE_SEQ_TIGHT;
+    run_whole_input(mode, m_fasta, false, m_dist, 2, in, out, m_write_clusters, m_verbose, m_memlimit, m_device);
+}
+
+void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int mates, const std::string* in,
+                     const std::string* out, bool write_clusters, bool verbose, ssize_t memlimit, int device) {
+    (void)mode; (void)fasta; (void)unordered; (void)dist; (void)mates; (void)in; (void)out; (void)write_clusters; (void)verbose;
+    (void)memlimit; (void)device;
+    throw std::runtime_error("sequence-based and --unordered modes are not available in this build yet");
+}
+
+}  // namespace fqdhost

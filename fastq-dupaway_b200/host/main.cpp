@@ -1,0 +1,32 @@
+// main.cpp - the drop-in `fastq-dupaway` binary: argument handling and dispatch as in the reference
+// (src/main.cpp:181-262), with the two drivers backed by the B200 engine (libfqd_cuda.so).
+#include <iostream>
+
+#include "dup_remover.hpp"
+#include "options.hpp"
+
+using namespace fqdhost;
+
+int main(int argc, char** argv) {
+    Options opts;
+    if (!parse_args(argc, argv, opts)) return 1;
+    try {
+        if (!opts.hash) {
+            SeqDupRemover remover(opts.memLimit, opts.ctype, opts.hammdist, opts.fasta, opts.write_clusters, opts.verbose, opts.device);
+            if (opts.paired) remover.filterPE(opts.input_1, opts.input_2, opts.output_1, opts.output_2);
+            else remover.filterSE(opts.input_1, opts.output_1);
+        } else {
+            HashDupRemover remover(opts.memLimit, opts.fasta, opts.verbose, opts.device);
+            if (opts.paired) remover.filterPE(opts.input_1, opts.input_2, opts.output_1, opts.output_2, opts.unordered);
+            else remover.filterSE(opts.input_1, opts.output_1);
+        }
+    } catch (const std::exception& exc) {
+        std::cerr << "An error occured during fastq-dupaway execution:\n";
+        std::cerr << exc.what() << '\n';
+        return 1;
+    } catch (...) {
+        std::cerr << "Unknown error occured during fastq-dupaway execution!\n";
+        return 1;
+    }
+    return 0;
+}

@@ -69,6 +69,8 @@ typedef struct {
     int32_t  err;               /* sticky fqd_status of the first data error in input order, or FQD_OK    */
     int32_t  err_char;          /* offending byte for BAD_START / BAD_BASE                                */
     uint64_t err_record;        /* global index of the record that raised it                              */
+    int32_t  err_mate;          /* 0 / 1: which input file the offending record belongs to                */
+    int32_t  reserved;
 } fqd_stats_t;
 
 /* Result of one pushed chunk (FAST ordered mode) - host pointers owned by the handle, valid until the next
