@@ -27,7 +27,7 @@ MODE_FAST, MODE_SEQ_TIGHT, MODE_SEQ_LOOSE, MODE_SEQ_HAMMING = 0, 1, 2, 3
 MODE_BY_NAME = {"fast": MODE_FAST, "tight": MODE_SEQ_TIGHT, "loose": MODE_SEQ_LOOSE, "tail-hamming": MODE_SEQ_HAMMING}
 
 STATUS = {0: "FQD_OK", 1: "FQD_ERR_INVALID", 2: "FQD_ERR_CUDA", 3: "FQD_ERR_EMPTY", 4: "FQD_ERR_BAD_START",
-          5: "FQD_ERR_LEN_MISMATCH", 6: "FQD_ERR_BAD_BASE", 7: "FQD_ERR_CAPACITY", 8: "FQD_ERR_SEQ_TOO_LONG"}
+          5: "FQD_ERR_LEN_MISMATCH", 6: "FQD_ERR_BAD_BASE", 7: "FQD_ERR_CAPACITY", 8: "FQD_ERR_SEQ_TOO_LONG", 9: "FQD_ERR_UNSUPPORTED_BYTE"}
 
 
 class FqdError(RuntimeError):
@@ -354,16 +354,20 @@ def dedup_fast(b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, chunk_bytes
 
 
 def dedup_whole(mode: str, b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, dist=2, unordered=False,
-                max_seq_len=150, append_bytes=1 << 22, device=0):
+                max_seq_len=150, append_bytes=1 << 22, seg_bytes=1 << 24, max_records=None, device=0):
     """Sequence-based modes and --fast --unordered: whole input on the device, emission order out."""
     paired = b2 is not None
-    eng = Engine(mode, fmt, paired, unordered, dist, max_seq_len, 0, max(append_bytes, 1 << 16), 0, device)
+    if max_records is None:
+        max_records = max(1024, max(b1.count(b"\n"), b2.count(b"\n") if paired else 0) // 2 + 16)
+    eng = Engine(mode, fmt, paired, unordered, dist, max_seq_len, max_records, seg_bytes, 0, device)
     try:
         for m, b in enumerate([b1, b2] if paired else [b1]):
             for o in range(0, len(b), append_bytes):
                 eng.append(m, b[o: o + append_bytes])
         eng.finish()
         st = eng.stats()
+        if st.err:
+            return b"", (b"" if paired else None), st
         em = eng.emission()
         n = int(em.n_out)
         outs = []

@@ -207,15 +207,6 @@ extern "C" int fqd_create(const fqd_config* cfg, fqd_handle** out) {
 }
 
 // -----------------------------------------------------------------------------------------------------------
-__global__ void k_init_chunk(ChunkCtl* ctl, u64* tile_state, u32 n_tiles) {
-    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) {
-        ctl->ticket = 0; ctl->n_newlines = 0; ctl->n_records = 0; ctl->consumed = 0;
-        ctl->err_parse = NO_ERR; ctl->err_base = NO_ERR; ctl->too_long = 0; ctl->pad = 0;
-    }
-    for (; i < n_tiles; i += gridDim.x * blockDim.x) tile_state[i] = 0;
-}
-
 static cudaEvent_t get_event(fqd_handle* h) {
     if (!h->event_pool.empty()) { cudaEvent_t e = h->event_pool.back(); h->event_pool.pop_back(); return e; }
     cudaEvent_t e; cudaEventCreate(&e); return e;

@@ -499,4 +499,14 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     }
 }
 
+__global__ void k_init_chunk(ChunkCtl* ctl, u64* tile_state, u32 n_tiles) {
+    u32 i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) {
+        ctl->ticket = 0; ctl->n_newlines = 0; ctl->n_records = 0; ctl->consumed = 0;
+        ctl->err_parse = NO_ERR; ctl->err_base = NO_ERR; ctl->too_long = 0; ctl->pad = 0;
+    }
+    for (; i < n_tiles; i += gridDim.x * blockDim.x) tile_state[i] = 0;
+}
+
+
 }  // namespace fqd

@@ -1,0 +1,241 @@
+// sortlib.cuh - device primitives for the whole-input modes: single-pass exclusive scan, stable LSD radix sort
+// of (64-bit key, 32-bit payload[, 32-bit payload]) and the multi-word "sort by rounds" driver that replaces
+// the reference's std::sort + k-way heap merge on disk (src/external_sort.hpp:88-207,
+// src/paired_external_sort.hpp:112-257).  Order = unsigned lexicographic order of a key row (word 0 first),
+// ties broken by the smaller record index (stable), which is the documented tie-break.
+#pragma once
+#include "common.cuh"
+
+namespace fqd {
+
+// ---------------------------------------------------------------------------------------------------------
+// exclusive scan of u32 (decoupled look-back, one pass).  state[] must hold ceil(n / SCAN_TILE) zeroed words.
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;
+constexpr u32 SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_exclusive(const u32* __restrict__ in, u32* __restrict__ out, u64 n,
+                                                                  u64* state, u32* ticket, u64* total_out) {
+    __shared__ u32 warp_sum[SCAN_THREADS / 32];
+    __shared__ u32 s_tile;
+    __shared__ u64 s_prefix;
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    if (tid == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const u32 tile = s_tile;
+    const u64 base = (u64)tile * SCAN_TILE + (u64)tid * SCAN_ITEMS;
+    u32 v[SCAN_ITEMS];
+    u32 sum = 0;
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        v[i] = (base + i < n) ? in[base + i] : 0u;
+        sum += v[i];
+    }
+    u32 incl = sum;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (u32)d) incl += t;
+    }
+    if (lane == 31) warp_sum[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        u32 ws = lane < SCAN_THREADS / 32 ? warp_sum[lane] : 0u;
+        u32 wi = ws;
+#pragma unroll
+        for (int d = 1; d < 8; d <<= 1) {
+            u32 t = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= (u32)d) wi += t;
+        }
+        if (lane < SCAN_THREADS / 32) warp_sum[lane] = wi - ws;
+        const u64 total = __shfl_sync(0xFFFFFFFFu, wi, SCAN_THREADS / 32 - 1);
+        // state word: flag (2 bits) << 62 | value (62 bits)
+        u64 P = 0;
+        if (tile == 0) {
+            if (lane == 0) st_volatile_u64(state, (2ull << 62) | total);
+        } else {
+            if (lane == 0) st_volatile_u64(state + tile, (1ull << 62) | total);
+            long long look = (long long)tile - 1;
+            for (;;) {
+                long long idx = look - lane;
+                u64 s = (2ull << 62);
+                if (idx >= 0) { do { s = ld_volatile_u64(state + idx); } while ((s >> 62) == 0); }
+                u32 is_prefix = __ballot_sync(0xFFFFFFFFu, (s >> 62) == 2);
+                u64 val = s & ((1ull << 62) - 1);
+                if (is_prefix) {
+                    u32 first = (u32)__ffs((int)is_prefix) - 1u;
+                    if (lane > first) val = 0;
+                }
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, d);
+                P += val;
+                if (is_prefix) break;
+                look -= 32;
+            }
+            if (lane == 0) st_volatile_u64(state + tile, (2ull << 62) | (P + total));
+        }
+        if (lane == 0) {
+            s_prefix = P;
+            if (total_out && (u64)(tile + 1) * SCAN_TILE >= n) *total_out = P + total;
+        }
+    }
+    __syncthreads();
+    u32 run = (u32)s_prefix + warp_sum[warp] + (incl - sum);
+#pragma unroll
+    for (int i = 0; i < SCAN_ITEMS; ++i) {
+        if (base + i < n) out[base + i] = run;
+        run += v[i];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// LSD radix sort, 8-bit digits, stable.  Items = (key64, a32[, b32]); one pass = histogram, scan, scatter.
+constexpr int RS_THREADS = 256;
+constexpr int RS_ITEMS = 16;
+constexpr u32 RS_TILE = RS_THREADS * RS_ITEMS;
+
+__global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const u64* __restrict__ keys, u64 n, u32 shift, u32* __restrict__ hist, u32 nblocks) {
+    __shared__ u32 h[256];
+    const u32 tid = threadIdx.x;
+    h[tid] = 0;
+    __syncthreads();
+    const u64 base = (u64)blockIdx.x * RS_TILE;
+#pragma unroll 4
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        u64 g = base + (u64)i * RS_THREADS + tid;
+        if (g < n) atomicAdd(&h[(keys[g] >> shift) & 0xFFu], 1u);
+    }
+    __syncthreads();
+    hist[(u64)tid * nblocks + blockIdx.x] = h[tid];      // bin-major: a plain exclusive scan yields global bases
+}
+
+template <bool HAS_B>
+__global__ void __launch_bounds__(RS_THREADS) k_radix_scatter(const u64* __restrict__ keys, const u32* __restrict__ a, const u32* __restrict__ b,
+                                                               u64* __restrict__ keys_out, u32* __restrict__ a_out, u32* __restrict__ b_out,
+                                                               u64 n, u32 shift, const u32* __restrict__ base_scanned, u32 nblocks) {
+    __shared__ u32 whist[RS_THREADS / 32][256];
+    __shared__ u32 gbase[256];
+    const u32 tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    for (u32 i = tid; i < (RS_THREADS / 32) * 256; i += RS_THREADS) (&whist[0][0])[i] = 0;
+    gbase[tid] = base_scanned[(u64)tid * nblocks + blockIdx.x];
+    __syncthreads();
+    // blocked arrangement keeps the input order: warp w owns items [w*512, (w+1)*512) of the tile, step s lane l
+    const u64 wbase = (u64)blockIdx.x * RS_TILE + (u64)warp * (32 * RS_ITEMS);
+    u64 k[RS_ITEMS];
+    u16 rank[RS_ITEMS];
+#pragma unroll
+    for (int s = 0; s < RS_ITEMS; ++s) {
+        const u64 g = wbase + (u64)s * 32 + lane;
+        const bool ok = g < n;
+        k[s] = ok ? keys[g] : ~0ull;
+        const u32 d = ok ? (u32)((k[s] >> shift) & 0xFFu) : 256u;      // 256 = out of range: no peer among real digits
+        const u32 peers = __match_any_sync(0xFFFFFFFFu, d);
+        const u32 before = __popc(peers & ((1u << lane) - 1u));
+        u32 old = 0;
+        if (ok && before == 0) {                     // leader of its digit in this step
+            old = whist[warp][d];
+            whist[warp][d] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xFFFFFFFFu, old, __ffs((int)peers) - 1);
+        rank[s] = (u16)(old + before);
+        __syncwarp();                                // the next step's leaders read this step's counter updates
+    }
+    __syncthreads();
+    {   // exclusive scan of each digit's counts across the warps (thread = digit)
+        u32 run = gbase[tid];
+#pragma unroll
+        for (int w = 0; w < RS_THREADS / 32; ++w) {
+            u32 c = whist[w][tid];
+            whist[w][tid] = run;
+            run += c;
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int s = 0; s < RS_ITEMS; ++s) {
+        const u64 g = wbase + (u64)s * 32 + lane;
+        if (g < n) {
+            const u32 d = (u32)((k[s] >> shift) & 0xFFu);
+            const u64 pos = (u64)whist[warp][d] + rank[s];
+            keys_out[pos] = k[s];
+            a_out[pos] = a[g];
+            if (HAS_B) b_out[pos] = b[g];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// small helper kernels of the multi-word sort
+__global__ void k_iota_u32(u32* p, u64 n) {
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = (u32)i;
+}
+__global__ void k_memset_u32(u32* p, u64 n, u32 v) {
+    u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) p[i] = v;
+}
+// key[i] = word `w` of the row of record idx[i]  (rows: base + idx * stride)
+__global__ void k_gather_word(const u64* __restrict__ rows, u32 stride, u32 w, const u32* __restrict__ idx, u64 n, u64* __restrict__ key) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) key[i] = rows[(u64)idx[i] * stride + w];
+}
+// After sorting the active items by (segment, word): flags of the refined segmentation.
+//   head[i] = 1 when item i starts a new (segment, word) group
+__global__ void k_mark_heads(const u64* __restrict__ key, const u32* __restrict__ seg, u64 n, u32* __restrict__ head) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step)
+        head[i] = (i == 0 || key[i] != key[i - 1] || (seg && seg[i] != seg[i - 1])) ? 1u : 0u;
+}
+// seg_id[i] = (inclusive scan of head)[i] - 1 is produced by the exclusive scan + head; group sizes via atomics.
+__global__ void k_group_ids(const u32* __restrict__ head, const u32* __restrict__ head_excl, u64 n, u32* __restrict__ gid, u32* __restrict__ gsize) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        u32 g = head_excl[i] + head[i] - 1u;
+        gid[i] = g;
+        atomicAdd(&gsize[g], 1u);
+    }
+}
+// A group still needs refinement when it has more than one member and its members' rows differ somewhere in the
+// words that have not been used yet (identical rows are already in index order thanks to stability).
+__global__ void k_mark_unresolved(const u64* __restrict__ rows, u32 stride, u32 w_next, u32 n_words, const u32* __restrict__ idx,
+                                  const u32* __restrict__ gid, u64 n, u32* __restrict__ gdiff) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        if (i == 0 || gid[i] != gid[i - 1]) continue;
+        const u64* a = rows + (u64)idx[i] * stride;
+        const u64* b = rows + (u64)idx[i - 1] * stride;
+        u64 diff = 0;
+        for (u32 w = w_next; w < n_words; ++w) diff |= a[w] ^ b[w];
+        if (diff) gdiff[gid[i]] = 1u;
+    }
+}
+__global__ void k_active_flags(const u32* __restrict__ gid, const u32* __restrict__ gsize, const u32* __restrict__ gdiff, u64 n, u32* __restrict__ flag) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        u32 g = gid[i];
+        flag[i] = (gsize[g] > 1u && gdiff[g]) ? 1u : 0u;
+    }
+}
+// compaction of the active items: (position in perm, record index, group id)
+__global__ void k_compact_active(const u32* __restrict__ flag, const u32* __restrict__ excl, const u32* __restrict__ pos_in, const u32* __restrict__ idx,
+                                 const u32* __restrict__ gid, u64 n, u32* __restrict__ pos_out, u32* __restrict__ idx_out, u32* __restrict__ gid_out) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        if (flag[i]) {
+            u32 o = excl[i];
+            pos_out[o] = pos_in ? pos_in[i] : (u32)i;
+            idx_out[o] = idx[i];
+            gid_out[o] = gid[i];
+        }
+    }
+}
+__global__ void k_scatter_perm(const u32* __restrict__ pos, const u32* __restrict__ idx, u64 n, u32* __restrict__ perm) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) perm[pos[i]] = idx[i];
+}
+__global__ void k_u32_to_u64key(const u32* __restrict__ in, u64 n, u64* __restrict__ out) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) out[i] = in[i];
+}
+
+}  // namespace fqd

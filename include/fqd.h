@@ -37,7 +37,9 @@ typedef enum {
     FQD_ERR_LEN_MISMATCH = 5,   /* FASTQ: len(seq) != len(qual)                  src/fastqview.cpp:117       */
     FQD_ERR_BAD_BASE = 6,       /* fast mode: byte outside {A,C,G,T,N}           src/seq_utils.cpp:17-19     */
     FQD_ERR_CAPACITY = 7,       /* record / key-store / table capacity exceeded                          */
-    FQD_ERR_SEQ_TOO_LONG = 8    /* sequence longer than fqd_config.max_seq_len                           */
+    FQD_ERR_SEQ_TOO_LONG = 8,   /* sequence longer than fqd_config.max_seq_len                           */
+    FQD_ERR_UNSUPPORTED_BYTE = 9 /* sequence mode: a sequence byte outside {A,C,G,T,N}; the packed-key path does
+                                    not order arbitrary bytes yet (the reference accepts any byte there)   */
 } fqd_status;
 
 typedef enum { FQD_FORMAT_FASTQ = 0, FQD_FORMAT_FASTA = 1 } fqd_format;      /* --format           src/main.cpp:111-120 */
