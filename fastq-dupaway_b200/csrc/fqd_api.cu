@@ -224,7 +224,7 @@ static int launch_parse(fqd_handle* h, int m, const u8* d_raw, size_t n, u8* d_d
     p.raw = d_raw; p.n = (u32)n; p.n_tiles = n_tiles; p.tile_state = c.d_tile_state; p.ctl = c.d_ctl; p.run = h->d_run;
     p.rec_start = c.d_rec_start; p.cap = h->cap; p.keys = h->d_keys; p.key_capacity = h->key_capacity;
     p.row_words = h->row_words; p.mate_off = m * h->W; p.W = h->W; p.hash = c.d_hash; p.seq_len = nullptr; p.word0 = nullptr;
-    p.strict = 1; p.hash_salt = m * 4096u; p.dup = (m == 0) ? h->d_dup : nullptr;
+    p.strict = 1; p.hash_salt = m * 4096u; p.bad_rec = nullptr; p.dup = (m == 0) ? h->d_dup : nullptr;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (h->profile) { pe0 = get_event(h); pe1 = get_event(h); cudaEventRecord(pe0, h->stream); }
     const u32 grid = n_tiles;      // one tile per CTA, processed in ticket order

@@ -49,6 +49,8 @@ struct ParseParams {
     u32* seq_len;           // optional [cap]: sequence length in bases (chunk-local index)
     u64* word0;             // optional [cap]: first key word (radix-sort key), chunk-local index
     u8* dup;                // optional [cap]: duplicate flags, cleared here for every record of the chunk
+    u32* bad_rec;           // optional [cap], initialised to ~0: (position << 8 | byte) of the first byte outside
+                            // {A,C,G,T,N} of each record
     u32 strict;             // 1: bytes outside {A,C,G,T,N} are an error (fast mode, src/seq_utils.cpp:17-19)
     u32 hash_salt;          // distinguishes mates in the position keys
 };
@@ -486,6 +488,7 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                     if (p.word0) p.word0[R] = w0;
                 }
                 if (bad) {
+                    if (p.bad_rec) atomicMin(&p.bad_rec[R], ((badw * BASES_PER_WORD + ((bad >> 8) & 0xFFu)) << 8) | (bad & 0xFFu));
                     if (p.strict) {
                         u32 pos = badw * BASES_PER_WORD + ((bad >> 8) & 0xFFu);
                         atomicMin(&p.ctl->err_base, ((u64)R << 32) | ((u64)pos << 8) | (bad & 0xFFu));

@@ -165,6 +165,162 @@ __global__ void k_emit(const u32* keep, const u32* excl, const u32* perm, u64 n,
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// --fast --unordered
+// ID tag of a record (FastqViewWithId::read_new, src/fastqview.cpp:190-204; Fasta twin src/fastaview.cpp:153-167):
+// after the first '.' of the ID line (anywhere in it, description and '\n' included), else after the lead
+// character; up to the first ' ' at/after the tag start, else to the end of the line INCLUDING the '\n'.
+// Tag order = strncmp + shorter-first (src/fastqview.cpp:168-178): the bytes are packed big-endian, 8 per word,
+// zero padded, so that unsigned word-by-word comparison is that order.
+__global__ void k_extract_tags(const u8* raw, const u32* rec_start, const ChunkCtl* ctl, u32 TW, u64* tags, ChunkCtl* ctl_out) {
+    const u32 n = ctl->n_records;
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += step) {
+        const u8* p = raw + rec_start[r];
+        const u32 rec_len = rec_start[r + 1] - rec_start[r];
+        u32 idlen = 0, dot = 0xFFFFFFFFu;
+        for (u32 i = 0; i < rec_len; ++i) {
+            const u8 c = p[i];
+            if (c == '.' && dot == 0xFFFFFFFFu) dot = i;
+            if (c == '\n') { idlen = i + 1; break; }
+        }
+        const u32 t0 = dot != 0xFFFFFFFFu ? dot + 1 : 1u;
+        u32 t1 = idlen;
+        for (u32 i = t0; i < idlen; ++i) if (p[i] == ' ') { t1 = i; break; }
+        const u32 tl = t1 > t0 ? t1 - t0 : 0u;
+        if (tl > TW * 8u) ctl_out->too_long = 3;
+        u64* out = tags + r * TW;
+        for (u32 w = 0; w < TW; ++w) {
+            u64 v = 0;
+            for (u32 b = 0; b < 8; ++b) {
+                const u32 k = w * 8 + b;
+                v = (v << 8) | (k < tl ? (u64)p[t0 + k] : 0ull);
+            }
+            out[w] = v;
+        }
+    }
+}
+
+__device__ __forceinline__ int cmp_rows(const u64* a, const u64* b, u32 nw) {
+    for (u32 w = 0; w < nw; ++w) {
+        if (a[w] < b[w]) return -1;
+        if (a[w] > b[w]) return 1;
+    }
+    return 0;
+}
+// first position in the tag-sorted list (perm over rows `tags`) whose tag is >= key (upper = false) or > key
+__device__ __forceinline__ u32 tag_bound(const u64* tags, const u32* perm, u32 n, u32 TW, const u64* key, bool upper) {
+    u32 lo = 0, hi = n;
+    while (lo < hi) {
+        const u32 mid = lo + ((hi - lo) >> 1);
+        const int c = cmp_rows(tags + (u64)perm[mid] * TW, key, TW);
+        if (c < 0 || (upper && c == 0)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+struct JoinParams {
+    const u64* tagsL; const u32* permL; u32 n;
+    const u64* tagsR; const u32* permR; u32 m;
+    u32 TW;
+    u32* matchL;        // [n] partner position in R's sorted list or ~0
+    u32* matchR;        // [m] partner position in L's sorted list or ~0 (pre-filled)
+};
+struct JoinStop { u32 is, js, limit_i, limit_j, final_equal, use_a; };
+
+// The two-pointer walk of impl_filterPE_unordered (src/hash_dup_remover.hpp:279-315) pairs the k-th record of a
+// tag in L with the k-th record of the same tag in R.
+__global__ void k_join_match(const JoinParams p) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
+        const u64* key = p.tagsL + (u64)p.permL[i] * p.TW;
+        const u32 g0 = tag_bound(p.tagsL, p.permL, p.n, p.TW, key, false);
+        const u32 rank = (u32)i - g0;
+        const u32 lb = tag_bound(p.tagsR, p.permR, p.m, p.TW, key, false);
+        const u32 ub = tag_bound(p.tagsR, p.permR, p.m, p.TW, key, true);
+        u32 partner = 0xFFFFFFFFu;
+        if (rank < ub - lb) { partner = lb + rank; p.matchR[partner] = (u32)i; }
+        p.matchL[i] = partner;
+    }
+}
+// Where the walk stops: the loop ends as soon as either side has fetched its LAST record; exactly
+// one more comparison is made there.  enter_j(i) = R position when the walk first stands on L[i].
+__device__ __forceinline__ u32 join_enter(const u64* tagsA, const u32* permA, u32 na, const u64* tagsB, const u32* permB, u32 nb, u32 TW, u32 i) {
+    if (i == 0) return 0;
+    const u64* key = tagsA + (u64)permA[i - 1] * TW;
+    const u32 g0 = tag_bound(tagsA, permA, na, TW, key, false);
+    const u32 rank = (i - 1) - g0;
+    const u32 lb = tag_bound(tagsB, permB, nb, TW, key, false);
+    const u32 ub = tag_bound(tagsB, permB, nb, TW, key, true);
+    return lb + min(rank + 1u, ub - lb);
+}
+__global__ void k_join_stop(const JoinParams p, JoinStop* out) {
+    const u32 ja = join_enter(p.tagsL, p.permL, p.n, p.tagsR, p.permR, p.m, p.TW, p.n - 1);
+    JoinStop s;
+    if (ja < p.m - 1) { s.use_a = 1; s.is = p.n - 1; s.js = ja; }
+    else { s.use_a = 0; s.js = p.m - 1; s.is = join_enter(p.tagsR, p.permR, p.m, p.tagsL, p.permL, p.n, p.TW, p.m - 1); }
+    s.limit_i = s.is; s.limit_j = s.js;
+    s.final_equal = 0;
+    if (s.is < p.n && s.js < p.m)
+        s.final_equal = cmp_rows(p.tagsL + (u64)p.permL[s.is] * p.TW, p.tagsR + (u64)p.permR[s.js] * p.TW, p.TW) == 0 ? 1u : 0u;
+    *out = s;
+}
+__global__ void k_join_flags(const JoinParams p, const JoinStop* st, u32* emit, u32* unL, u32* unR) {
+    const JoinStop s = *st;
+    u64 step = (u64)gridDim.x * blockDim.x;
+    const u64 tot = (u64)max(p.n, p.m);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < tot; i += step) {
+        if (i < p.n) {
+            const u32 pr = p.matchL[i];
+            // pairs visited before the stop state, plus the stop state itself when its tags are equal
+            const bool before = pr != 0xFFFFFFFFu && i < s.limit_i && pr < s.limit_j;
+            const bool last = i == s.is && s.final_equal;
+            emit[i] = (before || last) ? 1u : 0u;
+            unL[i] = (i < s.limit_i && pr == 0xFFFFFFFFu) ? 1u : 0u;
+        }
+        if (i < p.m) unR[i] = (i < s.limit_j && p.matchR[i] == 0xFFFFFFFFu) ? 1u : 0u;
+    }
+}
+// pair key store for the emitted pairs, in emission order
+__global__ void k_build_pairs(const JoinParams p, const JoinStop* st, const u32* emit, const u32* excl, const u64* rows, u32 stride, u32 W,
+                              const u64* hashL, const u64* hashR, const u32* badL, const u32* badR,
+                              u64* pair_rows, u64* h1, u64* h2, u32* idxL, u32* idxR, u64* first_bad) {
+    const JoinStop s = *st;
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
+        if (!emit[i]) continue;
+        const u32 e = excl[i];
+        const u32 pr = (i == s.is && s.final_equal) ? s.js : p.matchL[i];
+        const u32 gl = p.permL[i], gr = p.permR[pr];
+        idxL[e] = gl; idxR[e] = gr;
+        const u64* a = rows + (u64)gl * stride;
+        const u64* b = rows + (u64)gr * stride + W;
+        u64* o = pair_rows + (u64)e * 2 * W;
+        for (u32 w = 0; w < W; ++w) { o[w] = a[w]; o[W + w] = b[w]; }
+        h1[e] = hashL[gl]; h2[e] = hashR[gr];
+        // setRecordPair keys the left mate first (src/hash_dup_remover.cpp:16-24): its bad byte is reported first
+        const u32 bl = badL[gl], br = badR[gr];
+        if (bl != 0xFFFFFFFFu) atomicMin(first_bad, ((u64)e << 8) | (bl & 0xFFu));
+        else if (br != 0xFFFFFFFFu) atomicMin(first_bad, ((u64)e << 8) | (br & 0xFFu));
+    }
+}
+__global__ void k_keep_from_dup(const u8* dup, u64 n, u64 limit, u32* keep) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) keep[i] = (i < limit && !dup[i]) ? 1u : 0u;
+}
+__global__ void k_emit_pairs(const u32* keep, const u32* excl, u64 n, const u32* idxL, const u32* idxR, const u64* off0, const u32* len0,
+                             const u64* off1, const u32* len1, u64* o_off0, u32* o_len0, u64* o_off1, u32* o_len1) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        if (!keep[i]) continue;
+        const u32 o = excl[i];
+        o_off0[o] = off0[idxL[i]]; o_len0[o] = len0[idxL[i]];
+        o_off1[o] = off1[idxR[i]]; o_len1[o] = len1[idxR[i]];
+    }
+}
+__global__ void k_set_chunk_pairs(RunState* run, u32 n) { run->n_records = 0; run->chunk_pairs = n; run->chunk_dups = 0; }
+
 // ---------------------------------------------------------------------------------------------------------
 struct SeqSegment { u8* d = nullptr; size_t cap = 0, fill = 0; u64 logical_base = 0; };
 
@@ -175,6 +331,9 @@ struct SeqMate {
     u64* d_rec_off = nullptr;
     u32* d_rec_len = nullptr;
     u32* d_seq_len = nullptr;
+    u64* d_hash = nullptr;        // unordered: raw key hash per record
+    u32* d_bad = nullptr;         // unordered: first byte outside {A,C,G,T,N} per record (~0 = none)
+    u64* d_tags = nullptr;        // unordered: TW words per record
     bool finished = false;
 };
 
@@ -182,7 +341,7 @@ struct SeqState {
     fqd_config cfg;
     cudaStream_t stream = nullptr;
     int sm = 148;
-    u32 W = 0, mates = 1, row_words = 0;
+    u32 W = 0, mates = 1, row_words = 0, TW = 4;
     u64 capacity = 0;
     size_t seg_bytes = 0;
     u32 chunk_cap = 0;
@@ -213,6 +372,12 @@ static int seq_alloc_tables(SeqState* s, std::string* err) {
         SEQ_TRY(cudaMalloc(&mt.d_rec_off, s->capacity * sizeof(u64)));
         SEQ_TRY(cudaMalloc(&mt.d_rec_len, s->capacity * sizeof(u32)));
         SEQ_TRY(cudaMalloc(&mt.d_seq_len, s->capacity * sizeof(u32)));
+        if (s->cfg.unordered) {
+            SEQ_TRY(cudaMalloc(&mt.d_hash, s->capacity * sizeof(u64)));
+            SEQ_TRY(cudaMalloc(&mt.d_bad, s->capacity * sizeof(u32)));
+            SEQ_TRY(cudaMemsetAsync(mt.d_bad, 0xFF, s->capacity * sizeof(u32), s->stream));
+            SEQ_TRY(cudaMalloc(&mt.d_tags, s->capacity * s->TW * sizeof(u64)));
+        }
     }
     s->tiles_cap = (u32)((s->seg_bytes + PP_TILE - 1) / PP_TILE) + 1;
     SEQ_TRY(cudaMalloc(&s->d_tile_state, (size_t)s->tiles_cap * sizeof(u64)));
@@ -228,6 +393,7 @@ static int seq_create(SeqState** out, const fqd_config* cfg, cudaStream_t stream
     s->cfg = *cfg; s->stream = stream; s->sm = sm; s->W = W;
     s->mates = cfg->paired ? 2 : 1;
     s->row_words = W * s->mates;
+    s->TW = (cfg->max_tag_len ? cfg->max_tag_len : 32) / 8 + ((cfg->max_tag_len ? cfg->max_tag_len : 32) % 8 ? 1 : 0);
     memset(&s->stats, 0, sizeof s->stats);
     if (cfg->max_records == 0) { *err = "max_records must be > 0"; delete s; return FQD_ERR_INVALID; }
     s->capacity = cfg->max_records;
@@ -252,6 +418,7 @@ static void seq_destroy(SeqState* s) {
     for (int m = 0; m < 2; ++m) {
         for (auto& sg : s->mate[m].segs) cudaFree(sg.d);
         cudaFree(s->mate[m].d_run); cudaFree(s->mate[m].d_rec_off); cudaFree(s->mate[m].d_rec_len); cudaFree(s->mate[m].d_seq_len);
+        cudaFree(s->mate[m].d_hash); cudaFree(s->mate[m].d_bad); cudaFree(s->mate[m].d_tags);
     }
     cudaFree(s->d_keys); cudaFree(s->d_tile_state); cudaFree(s->d_ctl); cudaFree(s->d_rec_start); cudaFree(s->d_hash);
     if (s->h_ctl) cudaFreeHost(s->h_ctl);
@@ -266,6 +433,7 @@ static int seq_reset(SeqState* s, std::string* err) {
         s->mate[m].segs.clear();
         s->mate[m].n_records = 0; s->mate[m].finished = false;
         SEQ_TRY(cudaMemsetAsync(s->mate[m].d_run, 0, sizeof(RunState), s->stream));
+        if (s->mate[m].d_bad) SEQ_TRY(cudaMemsetAsync(s->mate[m].d_bad, 0xFF, s->capacity * sizeof(u32), s->stream));
     }
     s->n = s->n_out = 0; s->finished = false; s->ms = 0;
     memset(&s->stats, 0, sizeof s->stats);
@@ -291,9 +459,14 @@ static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
     p.raw = sg.d; p.n = (u32)sg.fill; p.n_tiles = n_tiles; p.tile_state = s->d_tile_state; p.ctl = s->d_ctl; p.run = mt.d_run;
     p.rec_start = s->d_rec_start; p.cap = (u32)std::min<u64>(s->chunk_cap, room); p.keys = s->d_keys; p.key_capacity = s->capacity;
     p.row_words = s->row_words; p.mate_off = m * s->W; p.W = s->W; p.hash = s->d_hash; p.seq_len = mt.d_seq_len + mt.n_records;
-    p.word0 = nullptr; p.dup = nullptr; p.strict = 0; p.hash_salt = m * 4096u;
+    p.word0 = nullptr; p.dup = nullptr; p.strict = 0; p.hash_salt = m * 4096u; p.bad_rec = nullptr;
+    if (s->cfg.unordered) { p.hash = mt.d_hash + mt.n_records; p.bad_rec = mt.d_bad + mt.n_records; }
     if (s->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<n_tiles, PP_THREADS, 0, s->stream>>>(p);
     else k_parse_pack<2><<<n_tiles, PP_THREADS, 0, s->stream>>>(p);
+    if (s->cfg.unordered) {
+        k_extract_tags<<<s->sm * 8, 128, 0, s->stream>>>(sg.d, s->d_rec_start, s->d_ctl, s->TW, mt.d_tags + mt.n_records * s->TW, s->d_ctl);
+        s->launches++;
+    }
     k_finish_segment<<<s->sm * 4, 256, 0, s->stream>>>(s->d_ctl, s->d_rec_start, sg.logical_base, mt.d_rec_off + mt.n_records,
                                                        mt.d_rec_len + mt.n_records, mt.d_run, s->d_ctl);
     k_advance_run<<<1, 1, 0, s->stream>>>(mt.d_run);
@@ -310,7 +483,8 @@ static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
     }
     if (c.too_long == 1) seq_set_error(s, FQD_ERR_SEQ_TOO_LONG, 0, first, m);
     if (c.too_long == 2) seq_set_error(s, FQD_ERR_CAPACITY, 0, first, m);
-    if (c.pad) seq_set_error(s, FQD_ERR_UNSUPPORTED_BYTE, 0, first, m);
+    if (c.too_long == 3) seq_set_error(s, FQD_ERR_TAG_TOO_LONG, 0, first, m);
+    if (c.pad && !s->cfg.unordered) seq_set_error(s, FQD_ERR_UNSUPPORTED_BYTE, 0, first, m);
     mt.n_records += c.n_records;
     const size_t consumed = c.consumed, tail = sg.fill - consumed;
     if (c.n_records == 0 && !final && sg.fill >= sg.cap) {
@@ -588,9 +762,95 @@ static int seq_finish(SeqState* s, std::string* err) {
 }
 
 static int seq_finish_unordered(SeqState* s, std::string* err) {
-    (void)s;
-    *err = "--unordered is not built yet";
-    return FQD_ERR_INVALID;
+    const u64 n = s->mate[0].n_records, m = s->mate[1].n_records;
+    int rc;
+    u32 *permL, *permR;
+    if ((rc = seq_dalloc(s, &permL, n, err)) || (rc = seq_dalloc(s, &permR, m, err))) return rc;
+    // ExternalSorter<*ViewWithId> on each file (src/hash_dup_remover.hpp:163-173), stable on the input index
+    if ((rc = sort_rows(s, s->mate[0].d_tags, s->TW, 0, s->TW, 64, n, permL, err))) return rc;
+    if ((rc = sort_rows(s, s->mate[1].d_tags, s->TW, 0, s->TW, 64, m, permR, err))) return rc;
+
+    const u64 big = std::max(n, m);
+    u32 *matchL, *matchR, *emit, *unL, *unR, *excl;
+    JoinStop* d_stop;
+    if ((rc = seq_dalloc(s, &matchL, n, err)) || (rc = seq_dalloc(s, &matchR, m, err)) || (rc = seq_dalloc(s, &emit, n, err)) ||
+        (rc = seq_dalloc(s, &unL, n, err)) || (rc = seq_dalloc(s, &unR, m, err)) || (rc = seq_dalloc(s, &excl, big, err)) ||
+        (rc = seq_dalloc(s, &d_stop, 1, err))) return rc;
+    SEQ_TRY(cudaMemsetAsync(matchR, 0xFF, m * sizeof(u32), s->stream));
+    JoinParams jp;
+    jp.tagsL = s->mate[0].d_tags; jp.permL = permL; jp.n = (u32)n; jp.tagsR = s->mate[1].d_tags; jp.permR = permR; jp.m = (u32)m;
+    jp.TW = s->TW; jp.matchL = matchL; jp.matchR = matchR;
+    k_join_match<<<seq_grid(s, n), 256, 0, s->stream>>>(jp);
+    k_join_stop<<<1, 1, 0, s->stream>>>(jp, d_stop);
+    k_join_flags<<<seq_grid(s, big), 256, 0, s->stream>>>(jp, d_stop, emit, unL, unR);
+    s->launches += 3;
+    SortScratch sc;
+    if ((rc = seq_dalloc(s, &sc.scan_state, (big + SCAN_TILE - 1) / SCAN_TILE + 16, err)) || (rc = seq_dalloc(s, &sc.ticket, 4, err)) ||
+        (rc = seq_dalloc(s, &sc.d_total, 2, err))) return rc;
+    u64 uL = 0, uR = 0, E = 0;
+    if ((rc = device_scan(s, sc, unL, excl, n, &uL, err))) return rc;
+    if ((rc = device_scan(s, sc, unR, excl, m, &uR, err))) return rc;
+    if ((rc = device_scan(s, sc, emit, excl, n, &E, err))) return rc;
+    JoinStop hs;
+    SEQ_TRY(cudaMemcpy(&hs, d_stop, sizeof hs, cudaMemcpyDeviceToHost));
+    s->stats.unmatched = uL + uR + (hs.final_equal ? 0 : 1);
+    s->stats.total = E;
+    s->n = E;
+    s->n_out = 0;
+    if (E == 0) { s->stats.dups = 0; return FQD_OK; }
+
+    // exact first-occurrence set over the pair keys, in emission order (src/hash_dup_remover.hpp:291-306)
+    const u32 W = s->W;
+    u64 *pair_rows, *h1, *h2, *first_bad, *table;
+    u32 *idxL, *idxR, *keep;
+    u8* dup;
+    RunState* run;
+    u64 nb = 1024;
+    while (nb * 2 < E) nb <<= 1;
+    u32 lg = 0; while ((1ull << lg) < nb) ++lg;
+    if ((rc = seq_dalloc(s, &pair_rows, E * 2 * W, err)) || (rc = seq_dalloc(s, &h1, E, err)) || (rc = seq_dalloc(s, &h2, E, err)) ||
+        (rc = seq_dalloc(s, &first_bad, 1, err)) || (rc = seq_dalloc(s, &table, nb * 4, err)) || (rc = seq_dalloc(s, &idxL, E, err)) ||
+        (rc = seq_dalloc(s, &idxR, E, err)) || (rc = seq_dalloc(s, &keep, E, err)) || (rc = seq_dalloc(s, &dup, E + 64, err)) ||
+        (rc = seq_dalloc(s, &run, 1, err))) return rc;
+    SEQ_TRY(cudaMemsetAsync(first_bad, 0xFF, sizeof(u64), s->stream));
+    SEQ_TRY(cudaMemsetAsync(table, 0xFF, nb * 4 * sizeof(u64), s->stream));
+    SEQ_TRY(cudaMemsetAsync(dup, 0, E + 64, s->stream));
+    k_build_pairs<<<seq_grid(s, n), 256, 0, s->stream>>>(jp, d_stop, emit, excl, s->d_keys, s->row_words, W, s->mate[0].d_hash, s->mate[1].d_hash,
+                                                         s->mate[0].d_bad, s->mate[1].d_bad, pair_rows, h1, h2, idxL, idxR, first_bad);
+    k_set_chunk_pairs<<<1, 1, 0, s->stream>>>(run, (u32)E);
+    InsertParams ip;
+    ip.table = table; ip.bucket_shift = 64 - lg; ip.bucket_mask = nb - 1; ip.keys = pair_rows; ip.row_words = 2 * W; ip.key_capacity = E;
+    ip.hash1 = h1; ip.hash2 = h2; ip.ctl1 = nullptr; ip.ctl2 = nullptr; ip.run = run; ip.dup = dup;
+    k_insert<<<s->sm * 8, HS_THREADS, 0, s->stream>>>(ip);
+    s->launches += 3;
+    u64 hbad = 0;
+    SEQ_TRY(cudaMemcpy(&hbad, first_bad, sizeof hbad, cudaMemcpyDeviceToHost));
+    u64 limit = E;
+    if (hbad != ~0ull) {      // a matched pair holds a byte outside {A,C,G,T,N}: the run aborts when it is keyed
+        limit = hbad >> 8;
+        seq_set_error(s, FQD_ERR_BAD_BASE, (int)(hbad & 0xFF), limit, 0);
+    }
+    k_keep_from_dup<<<seq_grid(s, E), 256, 0, s->stream>>>(dup, E, limit, keep);
+    u64 n_out = 0;
+    if ((rc = device_scan(s, sc, keep, excl, E, &n_out, err))) return rc;
+    s->n_out = n_out;
+    s->stats.total = limit;
+    s->stats.dups = limit - n_out;
+    u64* o_off[2]; u32* o_len[2];
+    for (u32 k = 0; k < 2; ++k)
+        if ((rc = seq_dalloc(s, &o_off[k], n_out, err)) || (rc = seq_dalloc(s, &o_len[k], n_out, err))) return rc;
+    k_emit_pairs<<<seq_grid(s, E), 256, 0, s->stream>>>(keep, excl, E, idxL, idxR, s->mate[0].d_rec_off, s->mate[0].d_rec_len,
+                                                        s->mate[1].d_rec_off, s->mate[1].d_rec_len, o_off[0], o_len[0], o_off[1], o_len[1]);
+    s->launches += 2;
+    for (u32 k = 0; k < 2; ++k) {
+        s->h_off[k].resize(n_out); s->h_len[k].resize(n_out);
+        if (n_out) {
+            SEQ_TRY(cudaMemcpyAsync(s->h_off[k].data(), o_off[k], n_out * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+            SEQ_TRY(cudaMemcpyAsync(s->h_len[k].data(), o_len[k], n_out * sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
+        }
+    }
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    return FQD_OK;
 }
 
 static int seq_emission(SeqState* s, fqd_emission_t* out, std::string* err) {

@@ -190,6 +190,7 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
         cfg.max_records = (uint64_t)((double)est_records * growth);
         cfg.max_chunk_bytes = 2 * block + 4096;
         cfg.max_chunk_records = 0;
+        cfg.max_tag_len = 0;
         fqd_handle* hraw = nullptr;
         int rc = fqd_create(&cfg, &hraw);
         if (rc) throw_engine_error(nullptr, rc);

@@ -38,6 +38,7 @@ typedef enum {
     FQD_ERR_BAD_BASE = 6,       /* fast mode: byte outside {A,C,G,T,N}           src/seq_utils.cpp:17-19     */
     FQD_ERR_CAPACITY = 7,       /* record / key-store / table capacity exceeded                          */
     FQD_ERR_SEQ_TOO_LONG = 8,   /* sequence longer than fqd_config.max_seq_len                           */
+    FQD_ERR_TAG_TOO_LONG = 10,  /* --unordered: an ID tag is longer than fqd_config.max_tag_len          */
     FQD_ERR_UNSUPPORTED_BYTE = 9 /* sequence mode: a sequence byte outside {A,C,G,T,N}; the packed-key path does
                                     not order arbitrary bytes yet (the reference accepts any byte there)   */
 } fqd_status;
@@ -62,6 +63,8 @@ typedef struct {
     uint64_t max_records;       /* capacity of the key store: records (pairs) over the whole run         */
     uint64_t max_chunk_bytes;   /* largest buffer ever passed to one fqd_push* call (per mate), < 4 GiB  */
     uint64_t max_chunk_records; /* records per chunk the per-chunk tables hold; 0 = max_chunk_bytes/64   */
+    uint32_t max_tag_len;       /* --unordered: longest ID tag in bytes the tag keys must hold; 0 = 32    */
+    uint32_t reserved;
 } fqd_config;
 
 typedef struct {

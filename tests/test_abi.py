@@ -18,7 +18,7 @@ def test_abi_version(fqd):
 def test_struct_layouts_match_header(fqd):
     # sizes as the C compiler lays them out (checked against a tiny C program would need a compiler run;
     # the header uses only fixed-width fields in natural alignment, so ctypes' layout is the C layout)
-    assert ctypes.sizeof(fqd.Config) == 56
+    assert ctypes.sizeof(fqd.Config) == 64
     assert ctypes.sizeof(fqd.Stats) == 48
     assert ctypes.sizeof(fqd.ChunkResult) == 64
 
