@@ -107,6 +107,7 @@ def load_library():
     lib.fqd_append_device.argtypes = [vp, C.c_int, vp, sz]
     lib.fqd_finish.argtypes = [vp]
     lib.fqd_emission.argtypes = [vp, C.POINTER(Emission)]
+    lib.fqd_emit.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(C.c_int)]
     lib.fqd_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.fqd_device_time_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
     lib.fqd_synth_fastq.argtypes = [C.c_int, vp, u64, u64, C.c_uint32, C.c_int, u64, C.c_uint32, C.c_uint32, C.c_int]
@@ -247,6 +248,18 @@ class Engine:
         self._check(self.lib.fqd_emission(self.h, C.byref(em)))
         return em
 
+    def emit_all(self, mate: int, cap: int = 1 << 22) -> bytes:
+        """Output bytes of one mate, gathered on the device (fqd_emit) in emission order."""
+        buf = C.create_string_buffer(cap)
+        out = []
+        while True:
+            n, done = C.c_size_t(0), C.c_int(0)
+            self._check(self.lib.fqd_emit(self.h, mate, buf, cap, C.byref(n), C.byref(done)))
+            out.append(buf.raw[: n.value])
+            if done.value:
+                break
+        return b"".join(out)
+
     def stats(self) -> Stats:
         st = Stats()
         self._check(self.lib.fqd_stats(self.h, C.byref(st)))
@@ -355,7 +368,8 @@ def dedup_fast(b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, chunk_bytes
 
 
 def dedup_whole(mode: str, b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, dist=2, unordered=False,
-                max_seq_len=150, append_bytes=1 << 22, seg_bytes=1 << 24, max_records=None, device=0, max_tag_len=0):
+                max_seq_len=150, append_bytes=1 << 22, seg_bytes=1 << 24, max_records=None, device=0, max_tag_len=0,
+                device_gather=True, emit_cap=1 << 16):
     """Sequence-based modes and --fast --unordered: whole input on the device, emission order out."""
     paired = b2 is not None
     if max_records is None:
@@ -367,7 +381,7 @@ def dedup_whole(mode: str, b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ,
                 eng.append(m, b[o: o + append_bytes])
         eng.finish()
         st = eng.stats()
-        if st.err:
+        if st.err and st.err != 6:
             return b"", (b"" if paired else None), st
         em = eng.emission()
         n = int(em.n_out)
@@ -377,6 +391,10 @@ def dedup_whole(mode: str, b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ,
             ln = _np(em.len[m], n, np.int64)
             mv = memoryview(b)
             outs.append(b"".join(mv[int(o): int(o + l)] for o, l in zip(off, ln)))
+            if device_gather:      # the device-side gather must produce the same bytes
+                got = eng.emit_all(m, emit_cap)
+                if got != outs[-1]:
+                    raise AssertionError("fqd_emit bytes differ from the (offset, length) emission list")
         return outs[0], (outs[1] if paired else None), st
     finally:
         eng.close()

@@ -357,6 +357,15 @@ struct SeqState {
     bool finished = false;
     std::vector<u64> h_off[2];
     std::vector<u32> h_len[2];
+    u64* d_o_off[2] = {nullptr, nullptr};      // device copies of the emission (off, len) lists
+    u32* d_o_len[2] = {nullptr, nullptr};
+    u64 emit_cursor[2] = {0, 0};
+    u64* d_seg_base[2] = {nullptr, nullptr};   // per mate: logical base of every segment (+ sentinel)
+    u8** d_seg_ptr[2] = {nullptr, nullptr};
+    u32 n_segs[2] = {0, 0};
+    u8* d_stage = nullptr; size_t stage_cap = 0;
+    u32* d_dst = nullptr; size_t dst_cap = 0;
+    u64* em_scan_state = nullptr; u32* em_ticket = nullptr; u64* em_total = nullptr;
     std::vector<void*> scratch;      // freed at destroy / reset
     u64 launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -436,6 +445,9 @@ static int seq_reset(SeqState* s, std::string* err) {
         if (s->mate[m].d_bad) SEQ_TRY(cudaMemsetAsync(s->mate[m].d_bad, 0xFF, s->capacity * sizeof(u32), s->stream));
     }
     s->n = s->n_out = 0; s->finished = false; s->ms = 0;
+    s->emit_cursor[0] = s->emit_cursor[1] = 0;
+    for (int m = 0; m < 2; ++m) { s->d_o_off[m] = nullptr; s->d_o_len[m] = nullptr; s->d_seg_base[m] = nullptr; s->d_seg_ptr[m] = nullptr; }
+    s->d_stage = nullptr; s->stage_cap = 0; s->d_dst = nullptr; s->dst_cap = 0; s->em_scan_state = nullptr;
     memset(&s->stats, 0, sizeof s->stats);
     return FQD_OK;
 }
@@ -717,6 +729,7 @@ static int seq_finish_sequence_mode(SeqState* s, std::string* err) {
                                                   o_off[0], o_len[0], o_off[1], o_len[1], o_idx);
     s->launches++;
     for (u32 m = 0; m < s->mates; ++m) {
+        s->d_o_off[m] = o_off[m]; s->d_o_len[m] = o_len[m];
         s->h_off[m].resize(n_out); s->h_len[m].resize(n_out);
         if (n_out) {
             SEQ_TRY(cudaMemcpyAsync(s->h_off[m].data(), o_off[m], n_out * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
@@ -843,6 +856,7 @@ static int seq_finish_unordered(SeqState* s, std::string* err) {
                                                         s->mate[1].d_rec_off, s->mate[1].d_rec_len, o_off[0], o_len[0], o_off[1], o_len[1]);
     s->launches += 2;
     for (u32 k = 0; k < 2; ++k) {
+        s->d_o_off[k] = o_off[k]; s->d_o_len[k] = o_len[k];
         s->h_off[k].resize(n_out); s->h_len[k].resize(n_out);
         if (n_out) {
             SEQ_TRY(cudaMemcpyAsync(s->h_off[k].data(), o_off[k], n_out * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
@@ -850,6 +864,67 @@ static int seq_finish_unordered(SeqState* s, std::string* err) {
         }
     }
     SEQ_TRY(cudaStreamSynchronize(s->stream));
+    return FQD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// device-side output gather (one warp per record)
+__global__ void k_gather_records(const u64* off, const u32* len, const u32* dst, u64 count, const u64* seg_base, u8* const* seg_ptr,
+                                 u32 n_segs, u8* out) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 r = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < count; r += warps) {
+        const u64 o = off[r];
+        u32 lo = 0, hi = n_segs;             // last segment whose logical base is <= o
+        while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (seg_base[mid] <= o) lo = mid; else hi = mid; }
+        const u8* src = seg_ptr[lo] + (o - seg_base[lo]);
+        u8* d = out + dst[r];
+        const u32 n = len[r];
+        for (u32 i = lane; i < n; i += 32) d[i] = src[i];
+    }
+}
+
+static int seq_emit(SeqState* s, int m, void* dst, size_t cap, size_t* n_bytes, int* done, std::string* err) {
+    if (!s->finished) { *err = "fqd_emit before fqd_finish"; return FQD_ERR_INVALID; }
+    if (m < 0 || (u32)m >= s->mates) { *err = "bad mate index"; return FQD_ERR_INVALID; }
+    *n_bytes = 0; *done = 0;
+    if (s->stats.err && s->stats.err != FQD_ERR_BAD_BASE) { *done = 1; return FQD_OK; }
+    if (!s->d_seg_base[m]) {         // first call for this mate: upload its segment table
+        SeqMate& mt = s->mate[m];
+        std::vector<u64> base; std::vector<u8*> ptr;
+        for (auto& sg : mt.segs) { base.push_back(sg.logical_base); ptr.push_back(sg.d); }
+        s->n_segs[m] = (u32)base.size();
+        int rc;
+        if ((rc = seq_dalloc(s, &s->d_seg_base[m], base.size(), err)) || (rc = seq_dalloc(s, &s->d_seg_ptr[m], ptr.size(), err))) return rc;
+        SEQ_TRY(cudaMemcpy(s->d_seg_base[m], base.data(), base.size() * sizeof(u64), cudaMemcpyHostToDevice));
+        SEQ_TRY(cudaMemcpy(s->d_seg_ptr[m], ptr.data(), ptr.size() * sizeof(u8*), cudaMemcpyHostToDevice));
+    }
+    const u64 k0 = s->emit_cursor[m];
+    if (k0 >= s->n_out) { *done = 1; return FQD_OK; }
+    // as many whole records as fit into cap (and into 2^31 bytes, the u32 offset range of one batch)
+    const size_t lim = std::min<size_t>(cap, (size_t)1 << 31);
+    u64 k1 = k0; size_t bytes = 0;
+    while (k1 < s->n_out && bytes + s->h_len[m][k1] <= lim) { bytes += s->h_len[m][k1]; ++k1; }
+    if (k1 == k0) { *err = "fqd_emit: cap is smaller than one record"; return FQD_ERR_INVALID; }
+    const u64 cnt = k1 - k0;
+    int rc;
+    if (s->stage_cap < bytes) { if ((rc = seq_dalloc(s, &s->d_stage, bytes + 256, err))) return rc; s->stage_cap = bytes; }
+    if (s->dst_cap < cnt) {
+        if ((rc = seq_dalloc(s, &s->d_dst, cnt, err))) return rc;
+        s->dst_cap = cnt;
+        if ((rc = seq_dalloc(s, &s->em_scan_state, (cnt + SCAN_TILE - 1) / SCAN_TILE + 16, err)) || (rc = seq_dalloc(s, &s->em_ticket, 4, err)) ||
+            (rc = seq_dalloc(s, &s->em_total, 2, err))) return rc;
+    }
+    SortScratch sc; sc.scan_state = s->em_scan_state; sc.ticket = s->em_ticket; sc.d_total = s->em_total;
+    if ((rc = device_scan(s, sc, s->d_o_len[m] + k0, s->d_dst, cnt, nullptr, err))) return rc;
+    k_gather_records<<<seq_grid(s, cnt * 32), 256, 0, s->stream>>>(s->d_o_off[m] + k0, s->d_o_len[m] + k0, s->d_dst, cnt, s->d_seg_base[m],
+                                                                   s->d_seg_ptr[m], s->n_segs[m], s->d_stage);
+    s->launches++;
+    SEQ_TRY(cudaMemcpyAsync(dst, s->d_stage, bytes, cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    s->emit_cursor[m] = k1;
+    *n_bytes = bytes;
+    *done = k1 >= s->n_out ? 1 : 0;
     return FQD_OK;
 }
 

@@ -288,9 +288,97 @@ void SeqDupRemover::filterPE(const std::string& infile1, const std::string& infi
 
 void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int mates, const std::string* in,
                      const std::string* out, bool write_clusters, bool verbose, ssize_t memlimit, int device) {
-    (void)mode; (void)fasta; (void)unordered; (void)dist; (void)mates; (void)in; (void)out; (void)write_clusters; (void)verbose;
-    (void)memlimit; (void)device;
-    throw std::runtime_error("sequence-based and --unordered modes are not available in this build yet");
+    if (write_clusters)
+        throw std::runtime_error("--write-clusters is not available in the B200 build yet");
+    const int lpr = fasta ? 2 : 4;
+    size_t block = (size_t)memlimit / (size_t)(mates * 3 * 2);
+    block = std::min<size_t>(std::max<size_t>(block, 4u << 20), 256u << 20) & ~(size_t)4095;
+    double growth = 1.0;
+    unsigned seq_growth = 0, tag_growth = 0;
+
+    for (int attempt = 0; attempt < 10; ++attempt) {
+        std::vector<std::unique_ptr<BlockReader>> readers;
+        for (int m = 0; m < mates; ++m) readers.emplace_back(new BlockReader(in[m], block));
+        // geometry of the first block of every file sizes the key rows and the record tables
+        std::vector<Block*> first(mates, nullptr);
+        size_t max_seq = 0; uint64_t est_records = 0;
+        for (int m = 0; m < mates; ++m) {
+            first[m] = readers[m]->next();
+            if (!first[m] || first[m]->len == 0) throw std::runtime_error("Not enough memory to read a single object!");
+            size_t ms_ = 0; double ar = 0;
+            sample_geometry(first[m]->data(), std::min<size_t>(first[m]->len, 8u << 20), lpr, ms_, ar);
+            max_seq = std::max(max_seq, ms_);
+            double expand = has_gz_ext(in[m]) ? 8.0 : 1.0;
+            uint64_t est = (uint64_t)((double)file_size_or_zero(in[m]) * expand / std::max(ar, 8.0) * 1.02) + (1u << 16);
+            est_records = std::max(est_records, est);
+        }
+        fqd_config cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.abi_version = FQD_ABI_VERSION; cfg.device = device; cfg.mode = mode;
+        cfg.format = fasta ? FQD_FORMAT_FASTA : FQD_FORMAT_FASTQ; cfg.paired = mates == 2; cfg.unordered = unordered;
+        cfg.hamming_dist = dist;
+        cfg.max_seq_len = (uint32_t)((std::max<size_t>(max_seq, 20) + 19) / 20 * 20) << seq_growth;
+        cfg.max_records = (uint64_t)((double)est_records * growth);
+        cfg.max_chunk_bytes = 1ull << 30;              // device segments of 1 GiB
+        cfg.max_tag_len = 32u << tag_growth;
+        fqd_handle* hraw = nullptr;
+        int rc = fqd_create(&cfg, &hraw);
+        if (rc) throw_engine_error(nullptr, rc);
+        EnginePtr eng(hraw);
+
+        // ship every block to the device (the sort/join needs the whole input; nothing is kept on the host)
+        for (int m = 0; m < mates; ++m) {
+            Block* b = first[m];
+            while (b) {
+                rc = fqd_append(eng.get(), m, b->data(), b->len);
+                if (rc) throw_engine_error(eng.get(), rc);
+                readers[m]->release(b);
+                b = readers[m]->next();
+            }
+        }
+        rc = fqd_finish(eng.get());
+        if (rc) throw_engine_error(eng.get(), rc);
+        fqd_stats_t st;
+        fqd_stats(eng.get(), &st);
+        if (st.err == FQD_ERR_SEQ_TOO_LONG) { ++seq_growth; continue; }
+        if (st.err == FQD_ERR_CAPACITY) { growth *= 2.0; continue; }
+        if (st.err == FQD_ERR_TAG_TOO_LONG) { ++tag_growth; continue; }
+        if (st.err == FQD_ERR_UNSUPPORTED_BYTE)
+            throw std::runtime_error("sequence-based mode of the B200 build supports the alphabet {A, C, G, T, N} only");
+        // parse errors surface while the inputs are being sorted, before any output file exists
+        // (src/seq_dup_remover.hpp:44-50, src/hash_dup_remover.hpp:160-174)
+        if (st.err && st.err != FQD_ERR_BAD_BASE) throw_data_error(st, fasta);
+
+        std::vector<std::unique_ptr<OutputFile>> outs;
+        for (int m = 0; m < mates; ++m) outs.emplace_back(new OutputFile(out[m]));
+        const size_t cap = 64u << 20;
+        void* stage = nullptr;
+        if (fqd_host_alloc(&stage, cap) != FQD_OK) throw std::runtime_error("pinned host allocation failed");
+        struct Free { void* p; ~Free() { fqd_host_free(p); } } guard{stage};
+        for (int m = 0; m < mates; ++m) {
+            for (;;) {
+                size_t nb = 0; int done = 0;
+                rc = fqd_emit(eng.get(), m, stage, cap, &nb, &done);
+                if (rc) throw_engine_error(eng.get(), rc);
+                outs[m]->write((const char*)stage, nb);
+                if (done) break;
+            }
+        }
+        for (auto& o : outs) o->close();
+        if (st.err == FQD_ERR_BAD_BASE) throw_data_error(st, fasta);     // --unordered: raised while pairs are keyed
+        if (verbose) {
+            if (unordered) {
+                std::cout << st.total << " valid read pairs processed, out of which " << st.dups << " duplicates were removed.\n";
+                std::cout << st.unmatched << " Non-matching entries from both files were skipped.\n";
+            } else if (mates == 1) {
+                std::cout << st.total << " reads processed, out of which " << st.dups << " duplicates were removed.\n";
+            } else {
+                std::cout << st.total << " read pairs processed, out of which " << st.dups << " duplicates were removed.\n";
+            }
+        }
+        return;
+    }
+    throw std::runtime_error("input exceeds the device capacity");
 }
 
 }  // namespace fqdhost

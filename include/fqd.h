@@ -137,6 +137,12 @@ typedef struct {
     const uint64_t* head;       /* sequence mode: for every INPUT-sorted position, unused unless clusters  */
 } fqd_emission_t;
 int fqd_emission(fqd_handle* h, fqd_emission_t* out);
+/* Streams the OUTPUT BYTES of one mate in emission order: the device gathers the written records out of the raw
+ * input it still holds, so the host never needs the input again.  Each call fills dst with whole records
+ * (up to cap bytes, cap >= the longest record), sets *n_bytes, and sets *done when the mate's output is complete.
+ * (Replaces the `output_file.write(obj.start(), obj.size())` calls of src/seq_dup_remover.hpp:74,88,163-186 and
+ * src/hash_dup_remover.hpp:295-298.) */
+int fqd_emit(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, int* done);
 
 /* Statistics / sticky data error (feeds the -v lines and the reference's error messages). */
 int fqd_stats(fqd_handle* h, fqd_stats_t* out);
