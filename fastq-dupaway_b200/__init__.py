@@ -109,6 +109,13 @@ def load_library():
     lib.fqd_emission.argtypes = [vp, C.POINTER(Emission)]
     lib.fqd_emit.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(C.c_int)]
     lib.fqd_stats.argtypes = [vp, C.POINTER(Stats)]
+    lib.fqd_set_stream.argtypes = [vp, vp]
+    lib.fqd_shard_row_bytes.argtypes = [vp]
+    lib.fqd_shard_row_bytes.restype = sz
+    lib.fqd_shard_pack.argtypes = [vp, vp, sz, C.c_uint32, vp, C.POINTER(u64), C.POINTER(u64)]
+    lib.fqd_shard_insert.argtypes = [vp, vp, u64, C.c_uint32, vp]
+    lib.fqd_shard_apply.argtypes = [vp, vp, C.POINTER(u64)]
+    lib.fqd_shard_read_flags.argtypes = [vp, vp, sz]
     lib.fqd_device_time_ms.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(u64)]
     lib.fqd_synth_fastq.argtypes = [C.c_int, vp, u64, u64, C.c_uint32, C.c_int, u64, C.c_uint32, C.c_uint32, C.c_int]
     lib.fqd_synth_record_bytes.argtypes = [C.c_uint32]

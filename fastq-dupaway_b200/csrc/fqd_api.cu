@@ -15,6 +15,7 @@
 #include "hashset.cuh"
 #include "parse_pack.cuh"
 #include "seqmode.cuh"
+#include "shard.cuh"
 #include "synth.cuh"
 
 using namespace fqd;
@@ -61,6 +62,16 @@ struct fqd_handle {
     fqd_profile_t prof;
     std::vector<std::pair<cudaEvent_t, cudaEvent_t>> prof_parse, prof_insert;
     SeqState* seq = nullptr;      // whole-input modes (seqmode.cuh)
+    // multi-GPU --fast mode (shard.cuh)
+    SeqState* shard_ctx = nullptr;   // stream / scratch bookkeeping for the sort primitives
+    SortScratch shard_sc;
+    u64* d_stage_keys = nullptr;     // [cap * row_words] packed keys of the chunk being exchanged
+    RunState* d_stage_run = nullptr; // zero: K1 writes the chunk's rows at slot 0
+    u64* d_final_hash = nullptr;     // [cap]
+    u32* d_counts = nullptr;         // [n_shards + 1]
+    u64* d_recv_hash = nullptr;      // [cap_recv]
+    u64 recv_cap = 0;
+    u64 shard_last_n = 0;
 };
 
 #define CUDA_TRY(h, call)                                                                      \
@@ -116,6 +127,10 @@ extern "C" void fqd_destroy(fqd_handle* h) {
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
     if (h->seq) seq_destroy(h->seq);
+    if (h->shard_ctx) {
+        seq_free_results(h->shard_ctx); delete h->shard_ctx;
+        cudaFree(h->d_stage_keys); cudaFree(h->d_stage_run); cudaFree(h->d_final_hash); cudaFree(h->d_counts); cudaFree(h->d_recv_hash);
+    }
     if (h->timer0) { cudaEventDestroy(h->timer0); cudaEventDestroy(h->timer1); }
     for (auto& pe : h->prof_parse) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
     for (auto& pe : h->prof_insert) { cudaEventDestroy(pe.first); cudaEventDestroy(pe.second); }
@@ -248,6 +263,7 @@ static int enqueue_fast_chunk(fqd_handle* h, const void* d_r1, size_t n1, const 
     ip.row_words = h->row_words; ip.key_capacity = h->key_capacity;
     ip.hash1 = h->mate[0].d_hash; ip.hash2 = paired ? h->mate[1].d_hash : nullptr;
     ip.ctl1 = h->mate[0].d_ctl; ip.ctl2 = paired ? h->mate[1].d_ctl : nullptr; ip.run = h->d_run; ip.dup = h->d_dup;
+    ip.hash_mul = 1; ip.hash_final = 0;
     k_chunk_begin<<<1, 1, 0, h->stream>>>(ip);
     cudaEvent_t ie0 = nullptr, ie1 = nullptr;
     if (h->profile) { ie0 = get_event(h); ie1 = get_event(h); cudaEventRecord(ie0, h->stream); }
@@ -460,6 +476,139 @@ extern "C" int fqd_reset(fqd_handle* h) {
     h->pending_events.emplace_back(e0, e1);
     h->launches += 2;
     memset(&h->stats, 0, sizeof h->stats);
+    return FQD_OK;
+}
+
+// -----------------------------------------------------------------------------------------------------------
+// multi-GPU --fast mode
+extern "C" int fqd_set_stream(fqd_handle* h, void* cuda_stream) {
+    if (!h) return FQD_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->own_stream && h->stream) cudaStreamDestroy(h->stream);
+    h->stream = (cudaStream_t)cuda_stream;
+    h->own_stream = false;
+    if (h->seq) h->seq->stream = h->stream;
+    if (h->shard_ctx) h->shard_ctx->stream = h->stream;
+    return FQD_OK;
+}
+extern "C" size_t fqd_shard_row_bytes(fqd_handle* h) { return h ? ((size_t)h->row_words + 1) * sizeof(u64) : 0; }
+
+static int shard_init(fqd_handle* h) {
+    if (h->shard_ctx) return FQD_OK;
+    if (h->cfg.mode != FQD_MODE_FAST || h->cfg.unordered || h->cfg.paired) return fail(h, FQD_ERR_INVALID, "sharded path: single-end --fast only");
+    h->shard_ctx = new SeqState();
+    h->shard_ctx->stream = h->stream; h->shard_ctx->sm = h->sm_count;
+    int rc = sort_scratch_alloc(h->shard_ctx, h->shard_sc, h->cap, &h->err);
+    if (rc) return rc;
+    CUDA_TRY(h, cudaMalloc(&h->d_stage_keys, (size_t)h->cap * h->row_words * sizeof(u64)));
+    CUDA_TRY(h, cudaMalloc(&h->d_stage_run, sizeof(RunState)));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_stage_run, 0, sizeof(RunState), h->stream));
+    CUDA_TRY(h, cudaMalloc(&h->d_final_hash, (size_t)h->cap * sizeof(u64)));
+    CUDA_TRY(h, cudaMalloc(&h->d_counts, 64 * sizeof(u32)));
+    h->recv_cap = (u64)h->cap * 2;
+    CUDA_TRY(h, cudaMalloc(&h->d_recv_hash, h->recv_cap * sizeof(u64)));
+    cudaFree(h->d_dup); cudaFreeHost(h->h_dup);
+    CUDA_TRY(h, cudaMalloc(&h->d_dup, h->recv_cap + 64));
+    CUDA_TRY(h, cudaHostAlloc(&h->h_dup, h->recv_cap + 64, cudaHostAllocDefault));
+    return FQD_OK;
+}
+
+extern "C" int fqd_shard_pack(fqd_handle* h, const void* d_raw, size_t n, uint32_t n_shards, void* d_send, uint64_t* counts, uint64_t* n_records) {
+    if (!h || !counts || n_shards == 0 || n_shards > 32) return FQD_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    int rc = shard_init(h);
+    if (rc) return rc;
+    if (n > h->cfg.max_chunk_bytes) return fail(h, FQD_ERR_INVALID, "chunk larger than max_chunk_bytes");
+    MateChunk& c = h->mate[0];
+    const u32 n_tiles = (u32)((n + PP_TILE - 1) / PP_TILE);
+    k_init_chunk<<<std::max(1u, std::min(n_tiles / 256 + 1, 1024u)), 256, 0, h->stream>>>(c.d_ctl, c.d_tile_state, n_tiles);
+    ParseParams p;
+    p.raw = (const u8*)d_raw; p.n = (u32)n; p.n_tiles = n_tiles; p.tile_state = c.d_tile_state; p.ctl = c.d_ctl; p.run = h->d_stage_run;
+    p.rec_start = c.d_rec_start; p.cap = h->cap; p.keys = h->d_stage_keys; p.key_capacity = h->cap;
+    p.row_words = h->row_words; p.mate_off = 0; p.W = h->W; p.hash = c.d_hash; p.seq_len = nullptr; p.word0 = nullptr;
+    p.strict = 1; p.hash_salt = 0; p.dup = nullptr; p.bad_rec = nullptr;
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (h->profile) { pe0 = get_event(h); pe1 = get_event(h); cudaEventRecord(pe0, h->stream); }
+    if (n_tiles) {
+        if (h->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
+        else k_parse_pack<2><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
+    }
+    if (h->profile) { cudaEventRecord(pe1, h->stream); h->prof_parse.emplace_back(pe0, pe1); h->prof.parse_launches++; h->prof.parse_bytes += n; }
+    // owner of every key, one stable radix pass groups the records by owner
+    SortScratch& sc = h->shard_sc;
+    const unsigned g = (unsigned)h->sm_count * 8;
+    k_shard_owner<<<g, 256, 0, h->stream>>>(c.d_hash, c.d_ctl, n_shards, sc.keyA, h->d_final_hash, sc.aA);
+    CUDA_TRY(h, cudaMemcpyAsync(c.h_ctl, c.d_ctl, sizeof(ChunkCtl), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const u64 nrec = c.h_ctl->n_records;
+    h->shard_ctx->stream = h->stream;
+    rc = radix_sort(h->shard_ctx, sc, nrec, 0, 8, false, &h->err);
+    if (rc) return rc;
+    k_shard_counts<<<1, 64, 0, h->stream>>>(sc.keyA, c.d_ctl, n_shards, h->d_counts);
+    k_shard_gather<<<g, 256, 0, h->stream>>>(h->d_stage_keys, h->row_words, h->d_final_hash, sc.aA, c.d_ctl, (u64*)d_send);
+    u32 hc[64];
+    CUDA_TRY(h, cudaMemcpyAsync(hc, h->d_counts, (n_shards + 1) * sizeof(u32), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    for (u32 k = 0; k < n_shards; ++k) counts[k] = hc[k + 1] - hc[k];
+    if (n_records) *n_records = nrec;
+    h->shard_last_n = nrec;
+    h->launches += 5 + h->shard_ctx->launches; h->shard_ctx->launches = 0;
+    u64 n_ok;
+    h->h_run->chunk_pairs = (u32)nrec; h->h_run->capacity_exceeded = 0;
+    fold_chunk(h, h->stats.total, &n_ok);
+    CUDA_TRY(h, cudaGetLastError());
+    return FQD_OK;
+}
+
+extern "C" int fqd_shard_insert(fqd_handle* h, const void* d_recv, uint64_t n_recv, uint32_t n_shards, void* d_flags) {
+    if (!h || !h->shard_ctx) return FQD_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (n_recv > h->recv_cap) return fail(h, FQD_ERR_CAPACITY, "more rows received than the shard buffers hold");
+    const unsigned g = (unsigned)h->sm_count * 8;
+    CUDA_TRY(h, cudaMemsetAsync(d_flags, 0, n_recv, h->stream));
+    k_shard_set_pairs<<<1, 1, 0, h->stream>>>(h->d_run, (u32)n_recv, h->key_capacity);
+    k_shard_append<<<g, 256, 0, h->stream>>>((const u64*)d_recv, (u32)n_recv, h->row_words, h->d_keys, h->d_run, h->key_capacity, h->d_recv_hash);
+    InsertParams ip;
+    ip.table = h->d_table; ip.bucket_shift = h->bucket_shift; ip.bucket_mask = h->n_buckets - 1; ip.keys = h->d_keys;
+    ip.row_words = h->row_words; ip.key_capacity = h->key_capacity; ip.hash1 = h->d_recv_hash; ip.hash2 = nullptr;
+    ip.ctl1 = nullptr; ip.ctl2 = nullptr; ip.run = h->d_run; ip.dup = (u8*)d_flags; ip.hash_mul = n_shards; ip.hash_final = 1;
+    cudaEvent_t ie0 = nullptr, ie1 = nullptr;
+    if (h->profile) { ie0 = get_event(h); ie1 = get_event(h); cudaEventRecord(ie0, h->stream); }
+    k_insert<<<g, HS_THREADS, 0, h->stream>>>(ip);
+    if (h->profile) { cudaEventRecord(ie1, h->stream); h->prof_insert.emplace_back(ie0, ie1); h->prof.insert_launches++; }
+    k_chunk_end<<<1, 1, 0, h->stream>>>(h->d_run);
+    h->launches += 4;
+    CUDA_TRY(h, cudaGetLastError());
+    return FQD_OK;
+}
+
+extern "C" int fqd_shard_apply(fqd_handle* h, const void* d_flags_back, uint64_t* chunk_dups) {
+    if (!h || !h->shard_ctx) return FQD_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    MateChunk& c = h->mate[0];
+    const unsigned g = (unsigned)h->sm_count * 4;
+    k_shard_flags_back<<<g, 256, 0, h->stream>>>((const u8*)d_flags_back, h->shard_sc.aA, c.d_ctl, h->d_dup);
+    // count this chunk's duplicates with the same reduction the single-GPU path uses
+    k_shard_set_pairs<<<1, 1, 0, h->stream>>>(h->d_stage_run, (u32)h->shard_last_n, ~0ull);
+    k_count_dups<<<h->sm_count * 2, HS_THREADS, 0, h->stream>>>(h->d_dup, h->d_stage_run);
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_run, h->d_stage_run, sizeof(RunState), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    h->launches += 3;
+    const u64 d = h->h_run->chunk_dups;
+    h->stats.total += h->shard_last_n;
+    h->stats.dups += d;
+    if (chunk_dups) *chunk_dups = d;
+    // K1 of the next chunk must again see slot base 0
+    CUDA_TRY(h, cudaMemsetAsync(h->d_stage_run, 0, sizeof(RunState), h->stream));
+    return FQD_OK;
+}
+
+extern "C" int fqd_shard_read_flags(fqd_handle* h, void* dst, size_t n) {
+    if (!h || !h->shard_ctx || n > h->shard_last_n) return FQD_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaMemcpyAsync(dst, h->d_dup, n, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     return FQD_OK;
 }
 

@@ -32,6 +32,9 @@ struct InsertParams {
     const ChunkCtl* ctl2;   // paired else nullptr
     RunState* run;
     u8* dup;                // [cap] chunk-local flags, zero-initialised
+    u64 hash_mul;           // 1, or the number of shards: a shard owns the hash range [k/N,(k+1)/N) and spreads its
+                            // keys over its own table with the low 64 bits of hash * N
+    u32 hash_final;         // 1: hash1 already holds the finalised 64-bit hash (sharded path)
 };
 
 __device__ __forceinline__ bool rows_equal(const u64* a, const u64* b, u32 words) {
@@ -63,7 +66,8 @@ __global__ void __launch_bounds__(HS_THREADS) k_insert(const InsertParams p) {
     const u32 stride = gridDim.x * blockDim.x;
     for (u32 i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
         u64 h = p.hash1[i];                       // raw multilinear sums from K1
-        h = p.hash2 ? pair_hash(h, p.hash2[i]) : mix64(h);
+        if (!p.hash_final) h = p.hash2 ? pair_hash(h, p.hash2[i]) : mix64(h);
+        h *= p.hash_mul;
         const u64 slot = slot_base + i;
         const u64 tag = (h >> 8) & 0xFFFFFFull;
         const u64 mine = (tag << 40) | slot;

@@ -833,7 +833,7 @@ static int seq_finish_unordered(SeqState* s, std::string* err) {
     k_set_chunk_pairs<<<1, 1, 0, s->stream>>>(run, (u32)E);
     InsertParams ip;
     ip.table = table; ip.bucket_shift = 64 - lg; ip.bucket_mask = nb - 1; ip.keys = pair_rows; ip.row_words = 2 * W; ip.key_capacity = E;
-    ip.hash1 = h1; ip.hash2 = h2; ip.ctl1 = nullptr; ip.ctl2 = nullptr; ip.run = run; ip.dup = dup;
+    ip.hash1 = h1; ip.hash2 = h2; ip.ctl1 = nullptr; ip.ctl2 = nullptr; ip.run = run; ip.dup = dup; ip.hash_mul = 1; ip.hash_final = 0;
     k_insert<<<s->sm * 8, HS_THREADS, 0, s->stream>>>(ip);
     s->launches += 3;
     u64 hbad = 0;

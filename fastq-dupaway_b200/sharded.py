@@ -1,0 +1,85 @@
+"""Multi-GPU --fast mode: hash-range sharding of the key space across the ranks of one box.
+
+One process per GPU.  Per chunk every rank
+  1. splits + packs its own slice of the input and groups the packed keys by owning rank   (fqd_shard_pack)
+  2. exchanges the key rows with ONE all-to-all (torch.distributed: NCCL over NVLink / NVSwitch)
+  3. inserts the rows it received - they arrive ordered by global input position - into its set (fqd_shard_insert)
+  4. returns one duplicate flag per row with a second, byte-sized all-to-all
+  5. stores the flags against its own records                                                (fqd_shard_apply)
+The exchange plumbing below is independent of the device code (`ops` is any object with pack / insert / apply), which
+is how tests/test_sharded_cpu.py exercises it with two gloo ranks on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+
+class GpuShardOps:
+    """pack / insert / apply on one GPU through the C ABI; buffers are torch tensors on that GPU."""
+
+    def __init__(self, pkg, engine, world, device, max_rows):
+        import torch
+        self.torch = torch
+        self.pkg, self.eng, self.world = pkg, engine, world
+        self.lib = pkg.load_library()
+        self.dev = torch.device("cuda", device)
+        self.row_bytes = int(self.lib.fqd_shard_row_bytes(engine.h))
+        self.send = torch.empty((max_rows, self.row_bytes), dtype=torch.uint8, device=self.dev)
+        self.flags = torch.empty(2 * max_rows, dtype=torch.uint8, device=self.dev)
+        rc = self.lib.fqd_set_stream(engine.h, C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream))
+        assert rc == 0
+
+    def pack(self, raw_ptr, nbytes):
+        counts = (C.c_uint64 * self.world)()
+        nrec = C.c_uint64(0)
+        rc = self.lib.fqd_shard_pack(self.eng.h, C.c_void_p(raw_ptr), nbytes, self.world, C.c_void_p(self.send.data_ptr()), counts, C.byref(nrec))
+        self.eng._check(rc)
+        return self.send[: nrec.value], [int(c) for c in counts]
+
+    def insert(self, recv_rows):
+        n = int(recv_rows.shape[0])
+        rc = self.lib.fqd_shard_insert(self.eng.h, C.c_void_p(recv_rows.data_ptr()), n, self.world, C.c_void_p(self.flags.data_ptr()))
+        self.eng._check(rc)
+        return self.flags[:n]
+
+    def apply(self, flags_back):
+        d = C.c_uint64(0)
+        rc = self.lib.fqd_shard_apply(self.eng.h, C.c_void_p(flags_back.data_ptr()), C.byref(d))
+        self.eng._check(rc)
+        return int(d.value)
+
+
+def exchange_chunk(ops, dist, world, raw_ptr, nbytes, via_cpu=False):
+    """One chunk through pack -> all-to-all -> insert -> all-to-all -> apply.  Returns this rank's duplicate count."""
+    import torch
+    send_rows, counts = ops.pack(raw_ptr, nbytes)
+    dev = send_rows.device
+    row_bytes = int(send_rows.shape[1])
+    # how many rows will every peer send me?
+    cdev = torch.device("cpu") if via_cpu else dev
+    c_out = torch.tensor(counts, dtype=torch.int64, device=cdev)
+    c_in = torch.empty(world, dtype=torch.int64, device=cdev)
+    dist.all_to_all_single(c_in, c_out)
+    recv_counts = [int(x) for x in c_in.tolist()]
+    n_recv = sum(recv_counts)
+    # rows: one all-to-all
+    s = send_rows.reshape(-1)
+    if via_cpu:
+        s_h = s.cpu()
+        r_h = torch.empty(n_recv * row_bytes, dtype=torch.uint8)
+        dist.all_to_all_single(r_h, s_h, [c * row_bytes for c in recv_counts], [c * row_bytes for c in counts])
+        recv = r_h.to(dev)
+    else:
+        recv = torch.empty(n_recv * row_bytes, dtype=torch.uint8, device=dev)
+        dist.all_to_all_single(recv, s, [c * row_bytes for c in recv_counts], [c * row_bytes for c in counts])
+    flags = ops.insert(recv.reshape(n_recv, row_bytes))
+    # flags back: one byte per row, reverse direction
+    if via_cpu:
+        f_h = flags.cpu()
+        b_h = torch.empty(sum(counts), dtype=torch.uint8)
+        dist.all_to_all_single(b_h, f_h, counts, recv_counts)
+        back = b_h.to(dev)
+    else:
+        back = torch.empty(sum(counts), dtype=torch.uint8, device=dev)
+        dist.all_to_all_single(back, flags, counts, recv_counts)
+    return ops.apply(back), sum(counts)

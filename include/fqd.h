@@ -144,6 +144,27 @@ int fqd_emission(fqd_handle* h, fqd_emission_t* out);
  * src/hash_dup_remover.hpp:295-298.) */
 int fqd_emit(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, int* done);
 
+/*
+ * Multi-GPU --fast mode (one handle per GPU / process).  The all-to-all exchanges themselves are
+ * done by the caller (torch.distributed / NCCL) on the stream given to fqd_set_stream, between these calls:
+ *   fqd_shard_pack     split + pack one chunk of THIS rank's input and group the packed keys by owning shard;
+ *                      d_send receives n_records rows of fqd_shard_row_bytes() bytes, counts[k] (host) rows for shard k
+ *   -- all-to-all of the rows --
+ *   fqd_shard_insert   insert n_recv received rows (already ordered by global input position: shard 0's rows first)
+ *                      into this rank's set; d_flags receives one byte per row, 1 = duplicate
+ *   -- all-to-all of the flags back --
+ *   fqd_shard_apply    flags, in the order the rows were sent, are stored against this rank's records; the chunk's
+ *                      duplicate count is added to the statistics
+ * Chunks must be fed in global input order: chunk c of rank r holds the records that follow chunk c of rank r-1.
+ */
+int fqd_set_stream(fqd_handle* h, void* cuda_stream);
+size_t fqd_shard_row_bytes(fqd_handle* h);
+int fqd_shard_pack(fqd_handle* h, const void* d_raw, size_t n, uint32_t n_shards, void* d_send, uint64_t* counts, uint64_t* n_records);
+int fqd_shard_insert(fqd_handle* h, const void* d_recv, uint64_t n_recv, uint32_t n_shards, void* d_flags);
+int fqd_shard_apply(fqd_handle* h, const void* d_flags_back, uint64_t* chunk_dups);
+/* duplicate flags (one byte per record, record order) of the chunk last given to fqd_shard_apply, copied to the host */
+int fqd_shard_read_flags(fqd_handle* h, void* dst, size_t n);
+
 /* Statistics / sticky data error (feeds the -v lines and the reference's error messages). */
 int fqd_stats(fqd_handle* h, fqd_stats_t* out);
 
