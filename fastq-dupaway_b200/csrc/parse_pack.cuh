@@ -142,6 +142,13 @@ __device__ __noinline__ void fetch24_slow(const u8* win, const u8* raw, u32 base
     }
 }
 
+// slow path of the packer: the 24 source bytes are not all inside the staged window
+__device__ __noinline__ PackOut pack_word_slow(const u8* win, const u8* raw, u32 base, u32 n, u32 pos, u32 nvalid) {
+    u32 x[6];
+    fetch24_slow(win, raw, base, n, pos, x);
+    return pack20(x, pos & 3u, nvalid);
+}
+
 __device__ __forceinline__ u32 find_nl(const u64* mask64, u32 pos, const u8* raw, u32 base, u32 n) {
     if (pos < PP_WINDOW) {
         u32 w = pos >> 6;
@@ -161,29 +168,133 @@ __device__ __forceinline__ u32 find_nl(const u64* mask64, u32 pos, const u8* raw
     return PP_NONE;
 }
 
-// Validation of one record whose first byte is at window-local offset start_l and whose line ends are e0..e3
-// (PP_NONE = not found before the end of the chunk).  Produces the queue entry:
-//   qoff = window-local offset of the sequence (PP_NONE: nothing to pack), qlen = bases | fast-path flag << 31
+// ---- named barriers: warp 0 resolves the tile's newline rank (decoupled look-back) while warps 1..7 already split
+// and pack the records; BAR_POS = compacted newline positions complete, BAR_P = look-back result available,
+// BAR_WORK = warps 1..7 only
+template <int ID, int N> __device__ __forceinline__ void bar_sync_c() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+template <int ID, int N> __device__ __forceinline__ void bar_arrive_c() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
+enum { BAR_POS = 1, BAR_P = 2, BAR_WORK = 3 };
+constexpr u32 PP_PACKERS = PP_THREADS - 32;        // threads of warps 1..7
+constexpr u32 PP_GROUP = 4;                        // lanes that pack one record (two key words each per 8 words)
+enum { RS_NONE = 0, RS_OK = 1, RS_BAD_START = 2, RS_LEN_MISMATCH = 3, RS_TOO_LONG = 4 };
+
+// Geometry + validation of one record whose first byte is at window-local offset start_l and whose line ends are
+// e0..e3 (PP_NONE = not found before the end of the chunk).  Nothing here depends on the record's index, so it can
+// run before the look-back has delivered it.  Returns RS_* | first byte << 8;
+//   qoff = window-local offset of the sequence, qlen = bases | fast-path flag << 31   (RS_OK only)
 template <int LPR>
-__device__ __forceinline__ void finish_record(const ParseParams& p, const u8* win, u32 base, u64 slot, u32 R, u32 start_l,
-                                              u32 e0, u32 e1, u32 e2, u32 e3, u32& qoff, u32& qlen) {
+__device__ __forceinline__ u32 classify_record(const ParseParams& p, const u8* win, u32 base, u32 start_l,
+                                               u32 e0, u32 e1, u32 e2, u32 e3, u32& qoff, u32& qlen) {
     qoff = PP_NONE; qlen = 0;
     const u32 elast = (LPR == 4) ? e3 : e1;
-    if (elast == PP_NONE) return;                       // incomplete record: left to the next chunk
+    if (elast == PP_NONE) return RS_NONE;               // incomplete record: left to the next chunk
     const u8 lead = (LPR == 4) ? '@' : '>';
     const u32 c0 = start_l < PP_WINDOW ? win[start_l] : p.raw[(u64)base + start_l];
-    if (c0 != lead) {
-        atomicMin(&p.ctl->err_parse, ((u64)R << 16) | ((u64)PERR_BAD_START << 8) | c0);
-    } else if (LPR == 4 && (e1 - e0) != (e3 - e2)) {
-        atomicMin(&p.ctl->err_parse, ((u64)R << 16) | ((u64)PERR_LEN_MISMATCH << 8));
+    if (c0 != lead) return RS_BAD_START | (c0 << 8);
+    if (LPR == 4 && (e1 - e0) != (e3 - e2)) return RS_LEN_MISMATCH;
+    const u32 nb = e1 - e0 - 1u;
+    if (nb > p.W * BASES_PER_WORD) return RS_TOO_LONG;
+    qoff = e0 + 1u;
+    // fast path: every word of the row can be fetched from the staged window
+    const u32 fast = (qoff + p.W * BASES_PER_WORD + 4u <= PP_WINDOW) ? 0x80000000u : 0u;
+    qlen = nb | fast;
+    return RS_OK;
+}
+
+// What the owner thread of record R does once R is known (src/fastqview.cpp:121-138 error precedence).
+__device__ __forceinline__ void commit_record(const ParseParams& p, u64 slot_base, u32 R, u32 gstart, u32 status) {
+    if (R <= p.cap) {
+        p.rec_start[R] = gstart;
+        if (p.dup && R < p.cap) p.dup[R] = 0;
+    }
+    if (R >= p.cap) return;
+    const u32 rs = status & 0xFFu;
+    if (rs == RS_BAD_START) atomicMin(&p.ctl->err_parse, ((u64)R << 16) | ((u64)PERR_BAD_START << 8) | (status >> 8));
+    else if (rs == RS_LEN_MISMATCH) atomicMin(&p.ctl->err_parse, ((u64)R << 16) | ((u64)PERR_LEN_MISMATCH << 8));
+    else if (rs == RS_OK || rs == RS_TOO_LONG) {
+        if (slot_base + R >= p.key_capacity) p.ctl->too_long = 2;
+        else if (rs == RS_TOO_LONG) p.ctl->too_long = 1;
+    }
+}
+
+// One 20-base key word of the sequence at window-local offset off (nb bases).  The last, partial word of a
+// sequence is built from the LAST 20 bases of the sequence and shifted, so that no byte beyond the sequence is ever
+// looked at (no masking of the validity check); only sequences shorter than 20 bases take the masked path.
+//   bad: 0, or 0x80000000 | position in the sequence << 8 | offending byte
+__device__ __forceinline__ u64 pack_word(const u8* win, const ParseParams& p, u32 base, u32 off, u32 ql, u32 w, u32& bad) {
+    const u32 nb = ql & 0x7FFFFFFFu;
+    const u32 done = w * BASES_PER_WORD;
+    bad = 0;
+    if (nb <= done) return 0ull;
+    u32 nvalid = min(nb - done, (u32)BASES_PER_WORD);
+    u32 first = done, shift = 0;
+    if (nvalid < BASES_PER_WORD && nb >= BASES_PER_WORD) {
+        first = nb - BASES_PER_WORD;
+        shift = 3u * (BASES_PER_WORD - nvalid);
+        nvalid = BASES_PER_WORD;
+    }
+    const u32 pos = off + first;
+    PackOut po;
+    if (ql >> 31) {          // staged in shared memory
+        const u32* w32 = reinterpret_cast<const u32*>(win) + (pos >> 2);
+        u32 x[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) x[i] = w32[i];
+        po = pack20(x, pos & 3u, nvalid);
     } else {
-        const u32 nb = e1 - e0 - 1u;
-        if (slot >= p.key_capacity) { p.ctl->too_long = 2; return; }
-        if (nb > p.W * BASES_PER_WORD) { p.ctl->too_long = 1; return; }
-        qoff = e0 + 1u;
-        // fast path: every word of the row can be fetched from the staged window
-        const u32 fast = (qoff + p.W * BASES_PER_WORD + 4u <= PP_WINDOW) ? 0x80000000u : 0u;
-        qlen = nb | fast;
+        po = pack_word_slow(win, p.raw, base, p.n, pos, nvalid);
+    }
+    if (po.bad) bad = 0x80000000u | ((first + ((po.bad >> 8) & 0xFFu)) << 8) | (po.bad & 0xFFu);
+    return (po.word << shift) & 0x0FFFFFFFFFFFFFFFull;
+}
+
+// Which newline of the tile ends a record?  c = (rank of the tile's first newline) mod LPR decides it.  The exact
+// value comes from the look-back; this is a guess from the first bytes of up to 32 lines ('@' ... '+' for FASTQ,
+// '>' for FASTA) that lets the packers start before the look-back returns.  It is verified against the exact
+// value before anything is written; an ambiguous window returns PP_NONE (no speculation).
+template <int LPR>
+__device__ __forceinline__ u32 guess_phase(const u8* win, const u16* nlpos, u32 WN, u32 valid, u32 lane) {
+    bool ok = lane < WN;
+    u32 ch = 0;
+    if (ok) {
+        const u32 st = (u32)nlpos[lane] + 1u;
+        ok = st < valid;
+        if (ok) ch = win[st];
+    }
+    const u32 V = __ballot_sync(0xFFFFFFFFu, ok);
+    const u32 A = __ballot_sync(0xFFFFFFFFu, ok && ch == (LPR == 4 ? '@' : '>'));
+    const u32 B = __ballot_sync(0xFFFFFFFFu, ok && ch == '+');
+    u32 found = PP_NONE, n_ok = 0;
+#pragma unroll
+    for (u32 c = 0; c < (u32)LPR; ++c) {
+        bool good;
+        if (LPR == 4) {
+            const u32 m0 = 0x11111111u << (3u - c);                 // lines that must start a record
+            const u32 m2 = 0x11111111u << ((5u - c) & 3u);          // lines that must be the '+' line
+            good = (V & m0) != 0 && (V & m0 & ~A) == 0 && (V & m2 & ~B) == 0;
+        } else {
+            const u32 m0 = c == 0 ? 0xAAAAAAAAu : 0x55555555u;
+            good = (V & m0) != 0 && (V & m0 & ~A) == 0 && (V & ~m0 & A) == 0;
+        }
+        if (good) { found = c; ++n_ok; }
+    }
+    return n_ok == 1 ? found : PP_NONE;
+}
+
+// Per-record results of a pack group: PP_GROUP lanes reduce the key hash; lane 0 writes the per-record tables.
+__device__ __forceinline__ void commit_group(const ParseParams& p, u32 R, u32 nb, u32 l4, u32 gmask, u64 hsum, u64 w0, u32 bad) {
+    hsum += __shfl_xor_sync(gmask, hsum, 1);
+    hsum += __shfl_xor_sync(gmask, hsum, 2);
+    if (l4 == 0) {
+        p.hash[R] = hsum;
+        if (p.seq_len) p.seq_len[R] = nb;
+        if (p.word0) p.word0[R] = w0;
+    }
+    if (bad) {
+        const u32 v = bad & 0x7FFFFFFFu;               // position in the sequence << 8 | byte
+        if (p.bad_rec) atomicMin(&p.bad_rec[R], v);
+        if (p.strict) atomicMin(&p.ctl->err_base, ((u64)R << 32) | v);
+        else p.ctl->pad = 1;                           // non-ACGTN byte seen in a mode that accepts any byte
     }
 }
 
@@ -196,7 +307,7 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     __shared__ u32 q_len[PP_QCAP];
     __shared__ uint2 s_hkey[PP_HKEYS];
     __shared__ u32 warp_sum[PP_THREADS / 32];
-    __shared__ u32 s_tile, s_P, s_total, s_halo;
+    __shared__ u32 s_tile, s_P, s_halo;
     __shared__ __align__(8) u64 mbar;
 
     const u32 tid = threadIdx.x;
@@ -258,39 +369,55 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     u32 incl = cnt;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        u32 t = __shfl_up_sync(0xFFFFFFFFu, incl, d);
-        if (lane >= (u32)d) incl += t;
+        u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if (lane >= (u32)d) incl += x;
     }
     if (lane == 31) warp_sum[warp] = incl;
     __syncthreads();
-    if (warp == 0) {
-        u32 ws = lane < PP_THREADS / 32 ? warp_sum[lane] : 0u;
+    u32 T, lex;                                     // newlines in the tile proper; local rank of my first newline
+    {
+        const u32 ws = lane < PP_THREADS / 32 ? warp_sum[lane] : 0u;
         u32 wi = ws;
 #pragma unroll
-        for (int d = 1; d < 8; d <<= 1) {
-            u32 t = __shfl_up_sync(0xFFFFFFFFu, wi, d);
-            if (lane >= (u32)d) wi += t;
+        for (int d = 1; d < PP_THREADS / 32; d <<= 1) {
+            u32 x = __shfl_up_sync(0xFFFFFFFFu, wi, d);
+            if (lane >= (u32)d) wi += x;
         }
-        if (lane < PP_THREADS / 32) warp_sum[lane] = wi - ws;      // exclusive warp offsets
-        const u32 total = __shfl_sync(0xFFFFFFFFu, wi, PP_THREADS / 32 - 1);
-        // publish this tile's aggregate as early as possible
-        if (lane == 0) {
-            if (tile == 0) st_volatile_u64(p.tile_state, (2ull << 32) | total);
-            else st_volatile_u64(p.tile_state + tile, (1ull << 32) | total);
-            s_total = total;
+        T = __shfl_sync(0xFFFFFFFFu, wi, PP_THREADS / 32 - 1);
+        lex = __shfl_sync(0xFFFFFFFFu, wi - ws, warp) + (incl - cnt);
+    }
+    // publish this tile's aggregate as early as possible
+    if (tid == 0) st_volatile_u64(p.tile_state + tile, ((tile == 0 ? 2ull : 1ull) << 32) | T);
+    {
+        u32 r = lex;
+        u32 lo = (u32)my_mask, hi = (u32)(my_mask >> 32);
+        while (lo) {
+            const u32 b = (u32)__ffs((int)lo) - 1u;
+            lo &= lo - 1;
+            if (r < PP_NLCAP) nlpos[r] = (u16)(tid * 64u + b);
+            ++r;
         }
+        while (hi) {
+            const u32 b = (u32)__ffs((int)hi) - 1u;
+            hi &= hi - 1;
+            if (r < PP_NLCAP) nlpos[r] = (u16)(tid * 64u + 32u + b);
+            ++r;
+        }
+    }
+    bool compact;                                  // the compacted positions hold every newline of the window
+    if (warp == 0) {
         // halo words (PP_HALO/64 <= 32): ranks continue after the tile's
         const u64 hm = lane < (PP_NW - PP_THREADS) ? mask64[PP_THREADS + lane] : 0ull;
         const u32 hc = (u32)__popcll(hm);
         u32 hi = hc;
 #pragma unroll
         for (int d = 1; d < 32; d <<= 1) {
-            u32 t = __shfl_up_sync(0xFFFFFFFFu, hi, d);
-            if (lane >= (u32)d) hi += t;
+            u32 x = __shfl_up_sync(0xFFFFFFFFu, hi, d);
+            if (lane >= (u32)d) hi += x;
         }
         const u32 htot = __shfl_sync(0xFFFFFFFFu, hi, 31);
         if (lane == 0) s_halo = htot;
-        u32 r = total + hi - hc;
+        u32 r = T + hi - hc;
         u64 m = hm;
         while (m) {
             u32 b = (u32)__ffsll((long long)m) - 1u;
@@ -298,22 +425,11 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
             if (r < PP_NLCAP) nlpos[r] = (u16)((PP_THREADS + lane) * 64u + b);
             ++r;
         }
-    }
-    __syncthreads();
-    const u32 T = s_total;
-    const u32 lex = warp_sum[warp] + (incl - cnt);      // local rank of my first newline
-    {
-        u64 m = my_mask;
-        u32 r = lex;
-        while (m) {
-            u32 b = (u32)__ffsll((long long)m) - 1u;
-            m &= m - 1;
-            if (r < PP_NLCAP) nlpos[r] = (u16)(tid * 64u + b);
-            ++r;
-        }
-    }
-    // ---- decoupled look-back (warp 0) for the global rank of the tile's first newline
-    if (warp == 0) {
+        compact = T + htot <= PP_NLCAP;
+        __syncwarp();
+        bar_arrive_c<BAR_POS, PP_THREADS>();
+
+        // ---- decoupled look-back for the global rank of the tile's first newline; warps 1..7 do not wait for it
         u32 P = 0;
         if (tile != 0) {
             // window of 128 predecessors per hop (4 per lane): one L2 round trip must cover more tiles than
@@ -322,30 +438,28 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
             for (;;) {
                 u64 s4[4];
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    int idx = look - (int)lane - 32 * r;
-                    s4[r] = (2ull << 32);
-                    if (idx >= 0) s4[r] = ld_volatile_u64(p.tile_state + idx);
+                for (int r4 = 0; r4 < 4; ++r4) {
+                    int idx = look - (int)lane - 32 * r4;
+                    s4[r4] = (2ull << 32);
+                    if (idx >= 0) s4[r4] = ld_volatile_u64(p.tile_state + idx);
                 }
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
-                    int idx = look - (int)lane - 32 * r;
-                    while ((s4[r] >> 32) == 0) s4[r] = ld_volatile_u64(p.tile_state + idx);
+                for (int r4 = 0; r4 < 4; ++r4) {
+                    int idx = look - (int)lane - 32 * r4;
+                    while ((s4[r4] >> 32) == 0) s4[r4] = ld_volatile_u64(p.tile_state + idx);
                 }
                 bool found = false;
 #pragma unroll
-                for (int r = 0; r < 4; ++r) {
+                for (int r4 = 0; r4 < 4; ++r4) {
                     if (!found) {
-                        u32 is_prefix = __ballot_sync(0xFFFFFFFFu, (s4[r] >> 32) == 2);
-                        u32 val = (u32)s4[r];
+                        u32 is_prefix = __ballot_sync(0xFFFFFFFFu, (s4[r4] >> 32) == 2);
+                        u32 val = (u32)s4[r4];
                         if (is_prefix) {
                             u32 first = (u32)__ffs((int)is_prefix) - 1u;     // closest predecessor holding a prefix
                             if (lane > first) val = 0;
                             found = true;
                         }
-#pragma unroll
-                        for (int d = 16; d > 0; d >>= 1) val += __shfl_xor_sync(0xFFFFFFFFu, val, d);
-                        P += val;
+                        P += __reduce_add_sync(0xFFFFFFFFu, val);
                     }
                 }
                 if (found) break;
@@ -362,34 +476,44 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                 p.ctl->n_records = nrec < p.cap ? nrec : p.cap;
             }
         }
+        __syncwarp();
+        if (compact) { bar_arrive_c<BAR_P, PP_THREADS>(); return; }
+        bar_sync_c<BAR_P, PP_THREADS>();                // very dense tile: warp 0 helps to split and pack it
+    } else {
+        bar_sync_c<BAR_POS, PP_THREADS>();
+        compact = T + s_halo <= PP_NLCAP;
+        if (!compact) bar_sync_c<BAR_P, PP_THREADS>();  // very dense tile: everybody waits for the look-back
     }
-    __syncthreads();
-    const u32 P = s_P;
     const u32 WN = T + s_halo;                          // newlines in the whole window
-    const bool dense = WN <= PP_NLCAP;
+    const u32 l4 = tid & (PP_GROUP - 1u);
+    const u32 gmask = 0xFu << (lane & 28u);
+    const u32 Rrel_first = tile == 0 ? 0u : 1u;         // owned records, counted from floor(P / LPR)
 
-    // records owned by this tile: those whose preceding newline (rank LPR*R-1) lies in the tile proper
-    u32 R_first = (P + LPR) / LPR;
-    const u32 R_last = (P + T) / LPR;
-    if (tile == 0) R_first = 0;
-    const u32 n_owned = R_last >= R_first ? R_last - R_first + 1u : 0u;
-
-    for (u32 rbase = 0; rbase < n_owned; rbase += PP_QCAP) {
-        const u32 n_round = min(PP_QCAP, n_owned - rbase);
-        // ---- 3. owners: geometry + validation
-        if (dense) {
-            // one thread per record: the record's line ends are consecutive entries of nlpos
-            for (u32 o = tid; o < n_round; o += PP_THREADS) {
-                const u32 R = R_first + rbase + o;
-                const int j0 = (int)(LPR * R) - 1 - (int)P;          // local rank of the newline before the record
+    if (compact) {
+        // ================= normal tile: warps 1..7.  One thread per record: its line ends are consecutive entries
+        // of nlpos; everything but the record's index follows from c = P mod LPR.
+        const u32 wtid = tid - 32u;
+        const u32 g = wtid / PP_GROUP;
+        u32 P = 0, c = tile == 0 ? 0u : guess_phase<LPR>(win, nlpos, WN, valid, lane);
+        bool p_known = false;
+        if (c == PP_NONE || p.W > 8u) {
+            bar_sync_c<BAR_P, PP_THREADS>();
+            P = s_P; p_known = true; c = P % LPR;
+        }
+        u32 rbase = 0;
+        for (;;) {
+            const u32 Rrel_last = (c + T) / LPR;
+            const u32 n_owned = Rrel_last >= Rrel_first ? Rrel_last - Rrel_first + 1u : 0u;
+            const u32 n_round = rbase < n_owned ? min(PP_PACKERS / PP_GROUP, n_owned - rbase) : 0u;
+            // ---- owners: geometry + validation
+            u32 status = RS_NONE, gstart = 0;
+            if (wtid < n_round) {
+                const u32 Rrel = Rrel_first + rbase + wtid;
+                const int j0 = (int)(LPR * Rrel) - 1 - (int)c;            // local rank of the newline before the record
                 const u32 start_l = j0 < 0 ? 0u : (u32)nlpos[j0] + 1u;
-                const u32 gstart = base + start_l;
+                gstart = base + start_l;
                 u32 qoff = PP_NONE, qlen = 0;
-                if (R <= p.cap) {
-                    p.rec_start[R] = gstart;
-                    if (p.dup && R < p.cap) p.dup[R] = 0;
-                }
-                if (R < p.cap && gstart < p.n) {
+                if (gstart < p.n) {
                     u32 e[4];
 #pragma unroll
                     for (int k = 0; k < LPR; ++k) {
@@ -401,14 +525,79 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                             e[k] = from == PP_NONE ? PP_NONE : find_nl(mask64, max(from, PP_WINDOW), p.raw, base, p.n);
                         }
                     }
-                    finish_record<LPR>(p, win, base, slot_base + R, R, start_l, e[0], e[1], LPR == 4 ? e[2] : e[1],
-                                       LPR == 4 ? e[3] : e[1], qoff, qlen);
+                    status = classify_record<LPR>(p, win, base, start_l, e[0], e[1], LPR == 4 ? e[2] : e[1],
+                                                  LPR == 4 ? e[3] : e[1], qoff, qlen);
                 }
-                q_off[o] = qoff;
-                q_len[o] = qlen;
+                q_off[wtid] = qoff;
+                q_len[wtid] = qlen;
             }
-        } else {
-            // very dense tile (tiny records): every thread walks its own newline bits
+            bar_sync_c<BAR_WORK, PP_PACKERS>();
+            // ---- pack (rows of up to 8 words: into registers, before the record index is known)
+            const bool active = g < n_round && q_off[g] != PP_NONE;
+            u32 off = 0, ql = 0, bad = 0;
+            u64 wa = 0, wb = 0, hsum = 0;
+            if (active) {
+                off = q_off[g]; ql = q_len[g];
+                if (p.W <= 8u) {
+                    const u32 w = 2u * l4;
+                    if (w < p.W) {
+                        u32 bad_b;
+                        wa = pack_word(win, p, base, off, ql, w, bad);
+                        wb = pack_word(win, p, base, off, ql, w + 1u, bad_b);
+                        if (!bad) bad = bad_b;
+                        hsum = word_hash(wa, s_hkey[w]) + word_hash(wb, s_hkey[w + 1u]);
+                    }
+                }
+            }
+            if (!p_known) {
+                bar_sync_c<BAR_P, PP_THREADS>();
+                P = s_P; p_known = true;
+                if (P % LPR != c) { c = P % LPR; continue; }       // wrong guess: split this round again
+            }
+            // ---- commit
+            const u32 R0 = P / LPR + Rrel_first + rbase;
+            if (wtid < n_round) commit_record(p, slot_base, R0 + wtid, gstart, status);
+            if (active) {
+                const u32 R = R0 + g;
+                if (R < p.cap && slot_base + R < p.key_capacity) {
+                    u64* row = p.keys + (slot_base + R) * p.row_words + p.mate_off;
+                    u64 w0 = wa;
+                    if (p.W <= 8u) {
+                        if (2u * l4 < p.W) *reinterpret_cast<ulonglong2*>(row + 2u * l4) = make_ulonglong2(wa, wb);
+                    } else {
+                        for (u32 w = 2u * l4; w < p.W; w += 2u * PP_GROUP) {
+                            u32 bad_a, bad_b;
+                            const u64 xa = pack_word(win, p, base, off, ql, w, bad_a);
+                            const u64 xb = pack_word(win, p, base, off, ql, w + 1u, bad_b);
+                            *reinterpret_cast<ulonglong2*>(row + w) = make_ulonglong2(xa, xb);
+                            if (w == 0) w0 = xa;
+                            if (!bad) bad = bad_a ? bad_a : bad_b;
+                            const uint2 ka = w < PP_HKEYS ? s_hkey[w] : pos_keys(p.hash_salt + w);
+                            const uint2 kb = w + 1u < PP_HKEYS ? s_hkey[w + 1u] : pos_keys(p.hash_salt + w + 1u);
+                            hsum += word_hash(xa, ka) + word_hash(xb, kb);
+                        }
+                    }
+                    commit_group(p, R, ql & 0x7FFFFFFFu, l4, gmask, hsum, w0, bad);
+                }
+            }
+            rbase += PP_PACKERS / PP_GROUP;
+            if (rbase >= n_owned) break;
+            bar_sync_c<BAR_WORK, PP_PACKERS>();          // the queue is rewritten by the next round
+        }
+        return;
+    }
+
+    // ================= very dense tile (tiny records; all 8 warps, after the look-back): every thread walks its
+    // own newline bits
+    {
+        const u32 P = s_P;
+        u32 R_first = (P + LPR) / LPR;
+        const u32 R_last = (P + T) / LPR;
+        if (tile == 0) R_first = 0;
+        const u32 n_owned = R_last >= R_first ? R_last - R_first + 1u : 0u;
+        const u32 g = tid / PP_GROUP;
+        for (u32 rbase = 0; rbase < n_owned; rbase += PP_QCAP) {
+            const u32 n_round = min(PP_QCAP, n_owned - rbase);
             u64 m = my_mask;
             u32 k = P + lex;
             bool virt = (tile == 0 && tid == 0);      // record 0 starts at offset 0 with no newline before it
@@ -424,14 +613,10 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                     start_l = tid * 64u + b + 1u;
                 }
                 const u32 gstart = base + start_l;
-                if (rbase == 0 && R <= p.cap) {
-                    p.rec_start[R] = gstart;
-                    if (p.dup && R < p.cap) p.dup[R] = 0;
-                }
                 const u32 o = R - R_first;
                 if (o < rbase || o >= rbase + PP_QCAP) continue;
-                u32 qoff = PP_NONE, qlen = 0;
-                if (R < p.cap && gstart < p.n) {
+                u32 qoff = PP_NONE, qlen = 0, status = RS_NONE;
+                if (gstart < p.n) {
                     u32 e0 = find_nl(mask64, start_l, p.raw, base, p.n);
                     u32 e1 = e0 == PP_NONE ? PP_NONE : find_nl(mask64, e0 + 1u, p.raw, base, p.n);
                     u32 e3 = e1, e2 = e1;
@@ -439,66 +624,37 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                         e2 = e1 == PP_NONE ? PP_NONE : find_nl(mask64, e1 + 1u, p.raw, base, p.n);
                         e3 = e2 == PP_NONE ? PP_NONE : find_nl(mask64, e2 + 1u, p.raw, base, p.n);
                     }
-                    finish_record<LPR>(p, win, base, slot_base + R, R, start_l, e0, e1, e2, e3, qoff, qlen);
+                    status = classify_record<LPR>(p, win, base, start_l, e0, e1, e2, e3, qoff, qlen);
                 }
+                commit_record(p, slot_base, R, gstart, status);
                 q_off[o - rbase] = qoff;
                 q_len[o - rbase] = qlen;
             }
-        }
-        __syncthreads();
-
-        // ---- 4. pack: 8 lanes per record
-        {
-            const u32 g8 = tid >> 3, l8 = tid & 7u;
-            const u32 gmask = 0xFFu << (lane & 24u);
-            for (u32 q = g8; q < n_round; q += PP_THREADS / 8) {
+            __syncthreads();
+            for (u32 q = g; q < n_round; q += PP_THREADS / PP_GROUP) {
                 const u32 off = q_off[q];
                 if (off == PP_NONE) continue;
                 const u32 ql = q_len[q];
-                const u32 nb = ql & 0x7FFFFFFFu;
                 const u32 R = R_first + rbase + q;
+                if (R >= p.cap || slot_base + R >= p.key_capacity) continue;
                 u64* row = p.keys + (slot_base + R) * p.row_words + p.mate_off;
                 u64 hsum = 0, w0 = 0;
-                u32 bad = 0, badw = 0;
-                for (u32 w = l8; w < p.W; w += 8) {
-                    const u32 done = w * BASES_PER_WORD;
-                    const u32 pos = off + done;
-                    const u32 nvalid = nb > done ? min(nb - done, (u32)BASES_PER_WORD) : 0u;
-                    u32 x[6];
-                    if (ql >> 31) {          // staged in shared memory
-                        const u32* w32 = reinterpret_cast<const u32*>(win) + (pos >> 2);
-#pragma unroll
-                        for (int i = 0; i < 6; ++i) x[i] = w32[i];
-                    } else {
-                        fetch24_slow(win, p.raw, base, p.n, pos, x);
-                    }
-                    const PackOut po = pack20(x, pos & 3u, nvalid);
-                    row[w] = po.word;
-                    if (w == 0) w0 = po.word;
-                    const uint2 hk = w < PP_HKEYS ? s_hkey[w] : pos_keys(p.hash_salt + w);
-                    hsum += word_hash(po.word, hk);
-                    if (po.bad && !bad) { bad = po.bad; badw = w; }
+                u32 bad = 0;
+                for (u32 w = 2u * l4; w < p.W; w += 2u * PP_GROUP) {
+                    u32 bad_a, bad_b;
+                    const u64 xa = pack_word(win, p, base, off, ql, w, bad_a);
+                    const u64 xb = pack_word(win, p, base, off, ql, w + 1u, bad_b);
+                    *reinterpret_cast<ulonglong2*>(row + w) = make_ulonglong2(xa, xb);
+                    if (w == 0) w0 = xa;
+                    if (!bad) bad = bad_a ? bad_a : bad_b;
+                    const uint2 ka = w < PP_HKEYS ? s_hkey[w] : pos_keys(p.hash_salt + w);
+                    const uint2 kb = w + 1u < PP_HKEYS ? s_hkey[w + 1u] : pos_keys(p.hash_salt + w + 1u);
+                    hsum += word_hash(xa, ka) + word_hash(xb, kb);
                 }
-                hsum += __shfl_xor_sync(gmask, hsum, 1);
-                hsum += __shfl_xor_sync(gmask, hsum, 2);
-                hsum += __shfl_xor_sync(gmask, hsum, 4);
-                if (l8 == 0) {
-                    p.hash[R] = hsum;
-                    if (p.seq_len) p.seq_len[R] = nb;
-                    if (p.word0) p.word0[R] = w0;
-                }
-                if (bad) {
-                    if (p.bad_rec) atomicMin(&p.bad_rec[R], ((badw * BASES_PER_WORD + ((bad >> 8) & 0xFFu)) << 8) | (bad & 0xFFu));
-                    if (p.strict) {
-                        u32 pos = badw * BASES_PER_WORD + ((bad >> 8) & 0xFFu);
-                        atomicMin(&p.ctl->err_base, ((u64)R << 32) | ((u64)pos << 8) | (bad & 0xFFu));
-                    } else {
-                        p.ctl->pad = 1;   // non-ACGTN byte seen in a mode that accepts any byte
-                    }
-                }
+                commit_group(p, R, ql & 0x7FFFFFFFu, l4, gmask, hsum, w0, bad);
             }
+            __syncthreads();
         }
-        __syncthreads();
     }
 }
 
