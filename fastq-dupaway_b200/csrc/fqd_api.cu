@@ -162,6 +162,7 @@ static int create_impl(const fqd_config* cfg, fqd_handle* h) {
     if (prop.major < 10) return fail(h, FQD_ERR_CUDA, "libfqd_cuda is built for sm_100a (B200) only");
     h->sm_count = prop.multiProcessorCount;
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CUDA_TRY(h, pp_init_tables());
     CUDA_TRY(h, cudaFuncSetAttribute(k_parse_pack<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CUDA_TRY(h, cudaFuncSetAttribute(k_parse_pack<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 

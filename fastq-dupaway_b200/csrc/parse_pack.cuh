@@ -298,6 +298,15 @@ __device__ __forceinline__ void commit_group(const ParseParams& p, u32 R, u32 nb
     }
 }
 
+// pos_keys(mate * 4096 + w) for w < PP_HKEYS, both mates (filled once by pp_init_tables)
+__constant__ uint2 c_hkeys[2 * PP_HKEYS];
+static inline cudaError_t pp_init_tables() {
+    uint2 h[2 * PP_HKEYS];
+    for (u32 m = 0; m < 2; ++m)
+        for (u32 w = 0; w < PP_HKEYS; ++w) h[m * PP_HKEYS + w] = pos_keys(m * 4096u + w);
+    return cudaMemcpyToSymbol(c_hkeys, h, sizeof(h));
+}
+
 template <int LPR>   // lines per record: 4 = FASTQ, 2 = FASTA
 __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const ParseParams p) {
     __shared__ __align__(128) u8 win[PP_WINDOW];
@@ -307,7 +316,8 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     __shared__ u32 q_len[PP_QCAP];
     __shared__ uint2 s_hkey[PP_HKEYS];
     __shared__ u32 warp_sum[PP_THREADS / 32];
-    __shared__ u32 s_tile, s_P, s_halo;
+    __shared__ u32 s_tile, s_P, s_halo, s_c;
+    __shared__ volatile u32 s_Pready;
     __shared__ __align__(8) u64 mbar;
 
     const u32 tid = threadIdx.x;
@@ -317,8 +327,9 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     if (tid == 0) {
         s_tile = atomicAdd(&p.ctl->ticket, 1u);      // tiles are processed in ticket order: every predecessor
         mbar_init(&mbar, 1);                         // of a tile is already resident (look-back cannot deadlock)
+        s_Pready = 0;
     }
-    if (tid < PP_HKEYS) s_hkey[tid] = pos_keys(p.hash_salt + tid);
+    if (tid < PP_HKEYS) s_hkey[tid] = c_hkeys[((p.hash_salt >> 12) & 1u) * PP_HKEYS + tid];
     __syncthreads();
     const u32 tile = s_tile;
     const u32 base = tile * PP_TILE;
@@ -388,20 +399,23 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     }
     // publish this tile's aggregate as early as possible
     if (tid == 0) st_volatile_u64(p.tile_state + tile, ((tile == 0 ? 2ull : 1ull) << 32) | T);
-    {
-        u32 r = lex;
-        u32 lo = (u32)my_mask, hi = (u32)(my_mask >> 32);
-        while (lo) {
-            const u32 b = (u32)__ffs((int)lo) - 1u;
-            lo &= lo - 1;
-            if (r < PP_NLCAP) nlpos[r] = (u16)(tid * 64u + b);
-            ++r;
-        }
-        while (hi) {
-            const u32 b = (u32)__ffs((int)hi) - 1u;
-            hi &= hi - 1;
-            if (r < PP_NLCAP) nlpos[r] = (u16)(tid * 64u + 32u + b);
-            ++r;
+    if (cnt) {
+        // straight-line for the first two newlines of my 64 bytes (a FASTQ line pair "...\n+\n" at most), loop for more
+        u64 m = my_mask;
+        const u32 b0 = (u32)__ffsll((long long)m) - 1u;
+        if (lex < PP_NLCAP) nlpos[lex] = (u16)(tid * 64u + b0);
+        m &= m - 1;
+        if (m) {
+            const u32 b1 = (u32)__ffsll((long long)m) - 1u;
+            if (lex + 1u < PP_NLCAP) nlpos[lex + 1u] = (u16)(tid * 64u + b1);
+            m &= m - 1;
+            u32 r = lex + 2u;
+            while (m) {
+                const u32 b = (u32)__ffsll((long long)m) - 1u;
+                m &= m - 1;
+                if (r < PP_NLCAP) nlpos[r] = (u16)(tid * 64u + b);
+                ++r;
+            }
         }
     }
     bool compact;                                  // the compacted positions hold every newline of the window
@@ -469,6 +483,8 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
         }
         if (lane == 0) {
             s_P = P;
+            __threadfence_block();
+            s_Pready = 1;
             if (tile == p.n_tiles - 1) {
                 u32 all = P + T;
                 p.ctl->n_newlines = all;
@@ -494,17 +510,25 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
         // of nlpos; everything but the record's index follows from c = P mod LPR.
         const u32 wtid = tid - 32u;
         const u32 g = wtid / PP_GROUP;
-        u32 P = 0, c = tile == 0 ? 0u : guess_phase<LPR>(win, nlpos, WN, valid, lane);
+        // Only the warps that hold owner threads need c before the first barrier; the others read it afterwards.
+        // Without a usable guess the owners poll for the look-back result (BAR_P itself is always passed at the
+        // same point, after the pack stage, by every packer).
+        u32 P = 0, c = 0;
         bool p_known = false;
-        if (c == PP_NONE || p.W > 8u) {
-            bar_sync_c<BAR_P, PP_THREADS>();
-            P = s_P; p_known = true; c = P % LPR;
+        const bool owner_warp = wtid < ((PP_PACKERS / PP_GROUP + 31u) & ~31u);
+        if (owner_warp && tile != 0) {
+            c = guess_phase<LPR>(win, nlpos, WN, valid, lane);
+            if (c == PP_NONE) {
+                while (!s_Pready) { }
+                c = s_P % LPR;
+            }
         }
+        if (wtid == 0) s_c = c;
         u32 rbase = 0;
         for (;;) {
-            const u32 Rrel_last = (c + T) / LPR;
-            const u32 n_owned = Rrel_last >= Rrel_first ? Rrel_last - Rrel_first + 1u : 0u;
-            const u32 n_round = rbase < n_owned ? min(PP_PACKERS / PP_GROUP, n_owned - rbase) : 0u;
+            u32 Rrel_last = (c + T) / LPR;
+            u32 n_owned = Rrel_last >= Rrel_first ? Rrel_last - Rrel_first + 1u : 0u;
+            u32 n_round = rbase < n_owned ? min(PP_PACKERS / PP_GROUP, n_owned - rbase) : 0u;
             // ---- owners: geometry + validation
             u32 status = RS_NONE, gstart = 0;
             if (wtid < n_round) {
@@ -532,6 +556,12 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                 q_len[wtid] = qlen;
             }
             bar_sync_c<BAR_WORK, PP_PACKERS>();
+            if (!p_known && !owner_warp) {
+                c = s_c;
+                Rrel_last = (c + T) / LPR;
+                n_owned = Rrel_last >= Rrel_first ? Rrel_last - Rrel_first + 1u : 0u;
+                n_round = rbase < n_owned ? min(PP_PACKERS / PP_GROUP, n_owned - rbase) : 0u;
+            }
             // ---- pack (rows of up to 8 words: into registers, before the record index is known)
             const bool active = g < n_round && q_off[g] != PP_NONE;
             u32 off = 0, ql = 0, bad = 0;
