@@ -1,0 +1,145 @@
+#!/usr/bin/env python
+"""bench_seq.py - throughput of the whole-input modes on one B200 (BASELINE.json configs[2] and configs[3]).
+
+  python bench_seq.py --mode tight|loose|tail-hamming|unordered [--pairs N] [--steps K] [--cpu]
+
+Workload: synthetic 2x150 bp paired-end FASTQ (644 B per pair), 30 % duplicates, the SURVEY section 8d variants
+(loose: 10 % of the duplicates truncated; tail-hamming: 10 % of the duplicates with <= 2 tail substitutions;
+unordered: the same pairs with R2 read in a different order).  A step = one whole job: every chunk is appended
+(parse + pack into HBM segments), then fqd_finish runs sort + scan (or tag sort + join + pair set).  The synthetic
+chunks are generated on the device outside the timed regions; device time is the sum of the CUDA-event intervals
+around the appends and the finish.  Prints one JSON line per mode; profiles/ keeps the committed results.
+"""
+from __future__ import annotations
+
+import argparse
+import importlib
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+READ_LEN = 150
+REC = 22 + 2 * READ_LEN
+SEED = 2
+DUP_PERMILLE = 300
+N_PERMILLE = 1
+VARIANT = {"tight": 0, "loose": 1, "tail-hamming": 2, "unordered": 0}
+# algorithmic bytes per pair: both records read once + 2 x 64 B key rows written (K1),
+# (8 B word + 4 B index) read twice and written once per 8-bit radix pass over the first key word (8 passes), the
+# two key rows of a pair and of its predecessor read by the scan, 4 B of survivor list
+ALG_BYTES_PER_PAIR = 2 * REC + 2 * 64 + 8 * 36 + 2 * 128 + 4
+
+
+def run_mode(fqd, lib, mode, n_pairs, steps, dev=0):
+    unordered = mode == "unordered"
+    emode = "fast" if unordered else mode
+    chunk_pairs = 1_500_000
+    n_chunks = (n_pairs + chunk_pairs - 1) // chunk_pairs
+    stage = [fqd.DeviceBuffer(chunk_pairs * REC + 65536, dev) for _ in range(2)]
+    eng = fqd.Engine(emode, fqd.FORMAT_FASTQ, True, unordered, 2, READ_LEN, n_pairs + 1024, 1 << 30, 0, dev, 16)
+    times = []
+    stats = None
+    order = list(range(n_chunks))
+    for it in range(steps + 1):
+        if it:
+            eng.reset()
+        t_ms = 0.0
+        for c in order:
+            first = c * chunk_pairs
+            cnt = min(chunk_pairs, n_pairs - first)
+            # unordered: R2 arrives chunk-reversed (its tag sort has to undo that; pairs are matched by tag)
+            c2 = (n_chunks - 1 - c) if unordered else c
+            first2 = c2 * chunk_pairs
+            cnt2 = min(chunk_pairs, n_pairs - first2)
+            assert lib.fqd_synth_fastq(dev, stage[0].ptr, first, cnt, READ_LEN, 1, SEED, DUP_PERMILLE, N_PERMILLE, VARIANT[mode]) == 0
+            assert lib.fqd_synth_fastq(dev, stage[1].ptr, first2, cnt2, READ_LEN, 2, SEED, DUP_PERMILLE, N_PERMILLE, VARIANT[mode]) == 0
+            eng.timer_start()
+            eng.append_device(0, stage[0].ptr, cnt * REC)
+            eng.append_device(1, stage[1].ptr, cnt2 * REC)
+            t_ms += eng.timer_stop()
+        eng.timer_start()
+        eng.finish()
+        t_ms += eng.timer_stop()
+        st = eng.stats()
+        assert st.err == 0, (st.err, st.err_record)
+        if it:
+            times.append(t_ms)
+        stats = st
+    em = eng.emission()
+    n_out = int(em.n_out)
+    _, launches = eng.device_time_ms()
+    eng.close()
+    for s in stage:
+        s.free()
+    ms = sum(times) / len(times)
+    peak = 6538.6
+    pk = ROOT / "MEASURED_PEAKS.json"
+    if pk.exists():
+        peak = float(json.loads(pk.read_text())["hbm_gbs"])
+    line = {"metric": "dedup read pairs/sec", "mode": mode, "value": n_pairs / (ms / 1e3), "unit": "pairs/s",
+            "reads_per_s": 2 * n_pairs / (ms / 1e3), "n_gpus": 1, "steps": steps, "ms_per_step": ms,
+            "config": {"workload": f"synthetic {n_pairs} x 2x150bp paired-end FASTQ, 30% duplicates, "
+                                   + ("--fast --unordered (R2 chunk-reversed)" if unordered else f"--compare-seq {mode}"),
+                       "pairs": n_pairs, "record_bytes": REC, "seed": SEED},
+            "pairs_total": int(stats.total), "duplicates_removed": int(stats.dups), "unmatched": int(stats.unmatched),
+            "pairs_out": n_out, "input_GBps": n_pairs * 2 * REC / (ms / 1e3) / 1e9,
+            "alg_GBps": n_pairs * ALG_BYTES_PER_PAIR / (ms / 1e3) / 1e9, "alg_bytes_per_pair": ALG_BYTES_PER_PAIR,
+            "frac_of_measured_peak": n_pairs * ALG_BYTES_PER_PAIR / (ms / 1e3) / 1e9 / peak}
+    return line
+
+
+def cpu_reference(mode, n_pairs):
+    """The unmodified reference (oracle/_ref) on the same synthetic stream, one core, tmpfs."""
+    sys.path.insert(0, str(ROOT / "oracle"))
+    oracle = importlib.import_module("oracle")
+    if not oracle.ref_available():
+        return None
+    gen = importlib.import_module("bench_synth")
+    if VARIANT[mode] != 0:
+        return None          # the CPU twin of the generator only knows variant 0
+    tmp = Path(tempfile.mkdtemp(prefix="fqd_cpu_", dir="/dev/shm" if Path("/dev/shm").is_dir() else None))
+    try:
+        (tmp / "r1.fq").write_bytes(gen.synth_fastq_cpu(0, n_pairs, READ_LEN, 1, SEED, DUP_PERMILLE, N_PERMILLE))
+        (tmp / "r2.fq").write_bytes(gen.synth_fastq_cpu(0, n_pairs, READ_LEN, 2, SEED, DUP_PERMILLE, N_PERMILLE))
+        cmd = [str(oracle.REF_BIN), "-i", "r1.fq", "-u", "r2.fq", "-o", "o1.fq", "-p", "o2.fq", "-m", "10240"]
+        if mode == "unordered":
+            cmd += ["--fast", "--unordered"]
+        else:
+            cmd += ["--compare-seq", mode]
+        t0 = time.perf_counter()
+        res = subprocess.run(cmd, cwd=tmp, capture_output=True)
+        dt = time.perf_counter() - t0
+        assert res.returncode == 0, res.stderr.decode()
+        return {"value": n_pairs / dt, "unit": "pairs/s", "cores": 1, "kind": "reference",
+                "sample": f"{n_pairs} pairs of the same synthetic stream, plain FASTQ on tmpfs, -m 10240, wall clock"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--mode", default="all")
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("FQD_BENCH_PAIRS", 20_000_000)))
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--cpu", action="store_true", help="also time the reference binary on a 1 M-pair sample")
+    args = ap.parse_args()
+    fqd = importlib.import_module("fastq-dupaway_b200")
+    lib = fqd.load_library()
+    modes = ["tight", "loose", "tail-hamming", "unordered"] if args.mode == "all" else [args.mode]
+    for m in modes:
+        line = run_mode(fqd, lib, m, args.pairs, args.steps)
+        if args.cpu:
+            line["cpu_baseline"] = cpu_reference(m, 1_000_000)
+        print(json.dumps(line), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -7,6 +7,9 @@
 // sortlib.cuh sorts record indices by packed key rows (stable on the input index), and the scans below decide
 // which records are written.  Nothing spills to disk; nothing is computed on the host.
 #pragma once
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
 #include <algorithm>
 #include <string>
 #include <vector>
@@ -366,11 +369,28 @@ struct SeqState {
     u8* d_stage = nullptr; size_t stage_cap = 0;
     u32* d_dst = nullptr; size_t dst_cap = 0;
     u64* em_scan_state = nullptr; u32* em_ticket = nullptr; u64* em_total = nullptr;
+    bool lists_on_host = false;      // h_off / h_len filled (only fqd_emission needs them)
+    u32* h_lenwin = nullptr;         // pinned window of record lengths for fqd_emit's batch cuts
     std::vector<void*> scratch;      // freed at destroy / reset
     u64 launches = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     double ms = 0.0;
 };
+
+// Transient device memory (input segments, sort / scan / emission scratch) comes from the device's stream-ordered
+// memory pool: cudaMalloc costs ~0.1 ms per MiB on a busy B200 (170 ms of a 400 ms job at 20 M pairs), pool
+// blocks are reused by the next job of the same handle without any driver call.
+static int seq_pool_init(SeqState* s, std::string* err) {
+    cudaMemPool_t pool;
+    SEQ_TRY(cudaDeviceGetDefaultMemPool(&pool, s->cfg.device));
+    uint64_t keep = ~0ull;
+    SEQ_TRY(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+    return FQD_OK;
+}
+static void seq_pool_trim(SeqState* s) {
+    cudaMemPool_t pool;
+    if (cudaDeviceGetDefaultMemPool(&pool, s->cfg.device) == cudaSuccess) { cudaStreamSynchronize(s->stream); cudaMemPoolTrimTo(pool, 0); }
+}
 
 static int seq_alloc_tables(SeqState* s, std::string* err) {
     SEQ_TRY(cudaMalloc(&s->d_keys, s->capacity * s->row_words * sizeof(u64)));
@@ -409,23 +429,27 @@ static int seq_create(SeqState** out, const fqd_config* cfg, cudaStream_t stream
     s->seg_bytes = (size_t)cfg->max_chunk_bytes;
     s->chunk_cap = (u32)std::min<u64>(cfg->max_chunk_records ? cfg->max_chunk_records : std::max<u64>(s->seg_bytes / 16, 1024), s->capacity);
     cudaEventCreate(&s->ev0); cudaEventCreate(&s->ev1);
-    int rc = seq_alloc_tables(s, err);
+    int rc = seq_pool_init(s, err);
+    if (!rc) rc = seq_alloc_tables(s, err);
     if (rc) { *out = s; return rc; }
     *out = s;
     return FQD_OK;
 }
 
 static void seq_free_results(SeqState* s) {
-    for (void* p : s->scratch) cudaFree(p);
+    for (void* p : s->scratch) cudaFreeAsync(p, s->stream);
     s->scratch.clear();
     for (int m = 0; m < 2; ++m) { s->h_off[m].clear(); s->h_len[m].clear(); }
+    s->lists_on_host = false;
 }
 
 static void seq_destroy(SeqState* s) {
     if (!s) return;
     seq_free_results(s);
+    for (int m = 0; m < 2; ++m) for (auto& sg : s->mate[m].segs) cudaFreeAsync(sg.d, s->stream);
+    seq_pool_trim(s);
+    if (s->h_lenwin) cudaFreeHost(s->h_lenwin);
     for (int m = 0; m < 2; ++m) {
-        for (auto& sg : s->mate[m].segs) cudaFree(sg.d);
         cudaFree(s->mate[m].d_run); cudaFree(s->mate[m].d_rec_off); cudaFree(s->mate[m].d_rec_len); cudaFree(s->mate[m].d_seq_len);
         cudaFree(s->mate[m].d_hash); cudaFree(s->mate[m].d_bad); cudaFree(s->mate[m].d_tags);
     }
@@ -438,7 +462,7 @@ static void seq_destroy(SeqState* s) {
 static int seq_reset(SeqState* s, std::string* err) {
     seq_free_results(s);
     for (u32 m = 0; m < s->mates; ++m) {
-        for (auto& sg : s->mate[m].segs) cudaFree(sg.d);
+        for (auto& sg : s->mate[m].segs) cudaFreeAsync(sg.d, s->stream);
         s->mate[m].segs.clear();
         s->mate[m].n_records = 0; s->mate[m].finished = false;
         SEQ_TRY(cudaMemsetAsync(s->mate[m].d_run, 0, sizeof(RunState), s->stream));
@@ -451,6 +475,19 @@ static int seq_reset(SeqState* s, std::string* err) {
     memset(&s->stats, 0, sizeof s->stats);
     return FQD_OK;
 }
+
+// FQD_TRACE=1: wall-clock checkpoints on stderr (each one synchronises the stream; for finding host-side stalls)
+struct SeqTrace {
+    bool on; std::chrono::steady_clock::time_point t0;
+    SeqTrace() : on(getenv("FQD_TRACE") != nullptr), t0(std::chrono::steady_clock::now()) {}
+    void mark(cudaStream_t st, const char* what) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fqd trace] %-28s %9.3f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
+    }
+};
 
 static void seq_set_error(SeqState* s, int code, int ch, u64 rec, int mate) {
     if (s->stats.err) return;
@@ -506,7 +543,7 @@ static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
     if (!final) {
         SeqSegment nx;
         nx.cap = s->seg_bytes;
-        SEQ_TRY(cudaMalloc(&nx.d, nx.cap + 4096));
+        SEQ_TRY(cudaMallocAsync(&nx.d, nx.cap + 4096, s->stream));
         nx.logical_base = sg.logical_base + consumed;
         if (tail) SEQ_TRY(cudaMemcpyAsync(nx.d, sg.d + consumed, tail, cudaMemcpyDeviceToDevice, s->stream));
         nx.fill = tail;
@@ -534,7 +571,7 @@ static int seq_append(SeqState* s, int m, const void* buf, size_t n, bool is_dev
     while (n) {
         if (mt.segs.empty()) {
             SeqSegment sg; sg.cap = s->seg_bytes;
-            SEQ_TRY(cudaMalloc(&sg.d, sg.cap + 4096));
+            SEQ_TRY(cudaMallocAsync(&sg.d, sg.cap + 4096, s->stream));
             mt.segs.push_back(sg);
         }
         SeqSegment& sg = mt.segs.back();
@@ -566,7 +603,7 @@ struct SortScratch {
 template <class T>
 static int seq_dalloc(SeqState* s, T** p, size_t count, std::string* err) {
     void* q = nullptr;
-    SEQ_TRY(cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T)));
+    SEQ_TRY(cudaMallocAsync(&q, std::max<size_t>(count, 1) * sizeof(T), s->stream));
     s->scratch.push_back(q);
     *p = (T*)q;
     return FQD_OK;
@@ -634,6 +671,7 @@ static int radix_sort(SeqState* s, SortScratch& sc, u64 n, u32 bit_lo, u32 bit_h
 // per word), ties by index.  perm receives the sorted indices.
 static int sort_rows(SeqState* s, const u64* rows, u32 stride, u32 w_begin, u32 n_words, u32 word_bits, u64 n, u32* perm, std::string* err) {
     SortScratch sc;
+    SeqTrace tr;
     int rc = sort_scratch_alloc(s, sc, n, err);
     if (rc) return rc;
     u32 *head, *excl, *gid, *gsize, *gdiff, *flag, *posA, *posB;
@@ -641,6 +679,7 @@ static int sort_rows(SeqState* s, const u64* rows, u32 stride, u32 w_begin, u32 
         (rc = seq_dalloc(s, &gsize, n, err)) || (rc = seq_dalloc(s, &gdiff, n, err)) || (rc = seq_dalloc(s, &flag, n, err)) ||
         (rc = seq_dalloc(s, &posA, n, err)) || (rc = seq_dalloc(s, &posB, n, err))) return rc;
     const u32 hi_bit = (word_bits + 7) / 8 * 8;
+    tr.mark(s->stream, "  sort: scratch alloc");
 
     // round 0: all records by their first word
     k_iota_u32<<<seq_grid(s, n), 256, 0, s->stream>>>(sc.aA, n);
@@ -648,6 +687,7 @@ static int sort_rows(SeqState* s, const u64* rows, u32 stride, u32 w_begin, u32 
     s->launches += 2;
     if ((rc = radix_sort(s, sc, n, 0, hi_bit, false, err))) return rc;
     SEQ_TRY(cudaMemcpyAsync(perm, sc.aA, n * sizeof(u32), cudaMemcpyDeviceToDevice, s->stream));
+    tr.mark(s->stream, "  sort: round 0");
 
     u64 n_act = n;                  // items in keyA/aA (sorted by the words used so far), bA = group of each
     const u32* pos_in = nullptr;    // their positions in perm (nullptr = identity)
@@ -686,6 +726,7 @@ static int sort_rows(SeqState* s, const u64* rows, u32 stride, u32 w_begin, u32 
         s->launches += 3;
         seg_in = sc.bA;
     }
+    tr.mark(s->stream, "  sort: refine rounds");
     SEQ_TRY(cudaGetLastError());
     return FQD_OK;
 }
@@ -695,8 +736,10 @@ static int seq_finish_sequence_mode(SeqState* s, std::string* err) {
     const u64 n = s->n;
     int rc;
     u32* perm;
+    SeqTrace tr;
     if ((rc = seq_dalloc(s, &perm, n, err))) return rc;
     if ((rc = sort_rows(s, s->d_keys, s->row_words, 0, s->row_words, 60, n, perm, err))) return rc;
+    tr.mark(s->stream, "sort_rows");
 
     u32 *keep, *excl, *brk = nullptr;
     if ((rc = seq_dalloc(s, &keep, n, err)) || (rc = seq_dalloc(s, &excl, n, err))) return rc;
@@ -719,6 +762,7 @@ static int seq_finish_sequence_mode(SeqState* s, std::string* err) {
         (rc = seq_dalloc(s, &sc.d_total, 2, err))) return rc;
     u64 n_out = 0;
     if ((rc = device_scan(s, sc, keep, excl, n, &n_out, err))) return rc;
+    tr.mark(s->stream, "scan + survivor count");
     s->n_out = n_out;
     u64 *o_off[2] = {nullptr, nullptr}; u32 *o_len[2] = {nullptr, nullptr}; u32* o_idx;
     if ((rc = seq_dalloc(s, &o_idx, n_out, err))) return rc;
@@ -728,15 +772,9 @@ static int seq_finish_sequence_mode(SeqState* s, std::string* err) {
                                                   s->mates == 2 ? s->mate[1].d_rec_off : nullptr, s->mates == 2 ? s->mate[1].d_rec_len : nullptr,
                                                   o_off[0], o_len[0], o_off[1], o_len[1], o_idx);
     s->launches++;
-    for (u32 m = 0; m < s->mates; ++m) {
-        s->d_o_off[m] = o_off[m]; s->d_o_len[m] = o_len[m];
-        s->h_off[m].resize(n_out); s->h_len[m].resize(n_out);
-        if (n_out) {
-            SEQ_TRY(cudaMemcpyAsync(s->h_off[m].data(), o_off[m], n_out * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
-            SEQ_TRY(cudaMemcpyAsync(s->h_len[m].data(), o_len[m], n_out * sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
-        }
-    }
+    for (u32 m = 0; m < s->mates; ++m) { s->d_o_off[m] = o_off[m]; s->d_o_len[m] = o_len[m]; }
     SEQ_TRY(cudaStreamSynchronize(s->stream));
+    tr.mark(s->stream, "emit lists");
     s->stats.total = n;
     s->stats.dups = n - n_out;
     return FQD_OK;
@@ -747,6 +785,7 @@ static int seq_finish_unordered(SeqState* s, std::string* err);
 static int seq_finish(SeqState* s, std::string* err) {
     if (s->finished) { *err = "fqd_finish called twice"; return FQD_ERR_INVALID; }
     s->finished = true;
+    SeqTrace tr;
     for (u32 m = 0; m < s->mates; ++m) {
         SeqMate& mt = s->mate[m];
         if (mt.segs.empty()) { seq_set_error(s, FQD_ERR_EMPTY, 0, 0, m); continue; }
@@ -760,6 +799,7 @@ static int seq_finish(SeqState* s, std::string* err) {
         int rc = seq_parse_segment(s, m, true, err);
         if (rc) return rc;
     }
+    tr.mark(s->stream, "finish: last segments");
     if (s->stats.err) return FQD_OK;            // data error: reported through fqd_stats, like the fast mode
     u64 n = s->mate[0].n_records;
     if (s->mates == 2 && !s->cfg.unordered) n = std::min(n, s->mate[1].n_records);      // stops at the shorter file
@@ -855,15 +895,23 @@ static int seq_finish_unordered(SeqState* s, std::string* err) {
     k_emit_pairs<<<seq_grid(s, E), 256, 0, s->stream>>>(keep, excl, E, idxL, idxR, s->mate[0].d_rec_off, s->mate[0].d_rec_len,
                                                         s->mate[1].d_rec_off, s->mate[1].d_rec_len, o_off[0], o_len[0], o_off[1], o_len[1]);
     s->launches += 2;
-    for (u32 k = 0; k < 2; ++k) {
-        s->d_o_off[k] = o_off[k]; s->d_o_len[k] = o_len[k];
-        s->h_off[k].resize(n_out); s->h_len[k].resize(n_out);
-        if (n_out) {
-            SEQ_TRY(cudaMemcpyAsync(s->h_off[k].data(), o_off[k], n_out * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
-            SEQ_TRY(cudaMemcpyAsync(s->h_len[k].data(), o_len[k], n_out * sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
+    for (u32 k = 0; k < 2; ++k) { s->d_o_off[k] = o_off[k]; s->d_o_len[k] = o_len[k]; }
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    return FQD_OK;
+}
+
+// The (offset, length) emission lists on the host: only fqd_emission() needs them (the CLI gathers on the device).
+static int seq_lists_to_host(SeqState* s, std::string* err) {
+    if (s->lists_on_host) return FQD_OK;
+    for (u32 m = 0; m < s->mates; ++m) {
+        s->h_off[m].resize(s->n_out); s->h_len[m].resize(s->n_out);
+        if (s->n_out && s->d_o_off[m]) {
+            SEQ_TRY(cudaMemcpyAsync(s->h_off[m].data(), s->d_o_off[m], s->n_out * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+            SEQ_TRY(cudaMemcpyAsync(s->h_len[m].data(), s->d_o_len[m], s->n_out * sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
         }
     }
     SEQ_TRY(cudaStreamSynchronize(s->stream));
+    s->lists_on_host = true;
     return FQD_OK;
 }
 
@@ -903,8 +951,13 @@ static int seq_emit(SeqState* s, int m, void* dst, size_t cap, size_t* n_bytes, 
     if (k0 >= s->n_out) { *done = 1; return FQD_OK; }
     // as many whole records as fit into cap (and into 2^31 bytes, the u32 offset range of one batch)
     const size_t lim = std::min<size_t>(cap, (size_t)1 << 31);
+    constexpr u64 LENWIN = 1u << 20;          // record lengths are fetched window by window into pinned memory
+    if (!s->h_lenwin) SEQ_TRY(cudaHostAlloc(&s->h_lenwin, LENWIN * sizeof(u32), cudaHostAllocDefault));
+    const u64 nwin = std::min<u64>(LENWIN, s->n_out - k0);
+    SEQ_TRY(cudaMemcpyAsync(s->h_lenwin, s->d_o_len[m] + k0, nwin * sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
     u64 k1 = k0; size_t bytes = 0;
-    while (k1 < s->n_out && bytes + s->h_len[m][k1] <= lim) { bytes += s->h_len[m][k1]; ++k1; }
+    while (k1 < k0 + nwin && bytes + s->h_lenwin[k1 - k0] <= lim) { bytes += s->h_lenwin[k1 - k0]; ++k1; }
     if (k1 == k0) { *err = "fqd_emit: cap is smaller than one record"; return FQD_ERR_INVALID; }
     const u64 cnt = k1 - k0;
     int rc;
@@ -931,6 +984,8 @@ static int seq_emit(SeqState* s, int m, void* dst, size_t cap, size_t* n_bytes, 
 static int seq_emission(SeqState* s, fqd_emission_t* out, std::string* err) {
     if (!s->finished) { *err = "fqd_emission before fqd_finish"; return FQD_ERR_INVALID; }
     memset(out, 0, sizeof *out);
+    int rc = seq_lists_to_host(s, err);
+    if (rc) return rc;
     out->n_out = s->n_out;
     for (u32 m = 0; m < s->mates; ++m) { out->off[m] = (const uint64_t*)s->h_off[m].data(); out->len[m] = s->h_len[m].data(); }
     return FQD_OK;
