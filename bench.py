@@ -250,7 +250,9 @@ def our_arm(args):
     tr = ROOT / "profiles" / "traffic.json"
     if tr.exists():
         try:
-            roofline["traffic"] = json.loads(tr.read_text()).get("k_parse_pack_bytes_per_launch")
+            # DRAM bytes per read of K1 from the committed ncu capture, scaled to this run's reads per launch
+            roofline["traffic"] = json.loads(tr.read_text())["k_parse_pack_bytes_per_read"] * reads_per_launch
+            roofline["traffic_source"] = "profiles/traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum per read x reads per launch)"
         except Exception:
             pass
 
