@@ -106,6 +106,15 @@ def load_library():
     lib.fqd_append.argtypes = [vp, C.c_int, vp, sz]
     lib.fqd_append_device.argtypes = [vp, C.c_int, vp, sz]
     lib.fqd_finish.argtypes = [vp]
+    lib.fqd_finish_scan.argtypes = [vp]
+    lib.fqd_finish_emit.argtypes = [vp]
+    lib.fqd_boundary_bytes.argtypes = [vp]
+    lib.fqd_boundary_bytes.restype = sz
+    lib.fqd_boundary_get.argtypes = [vp, vp]
+    lib.fqd_boundary_fix.argtypes = [vp, vp]
+    lib.fqd_partition_sample.argtypes = [vp, C.c_uint32, C.POINTER(u64), C.POINTER(u64)]
+    lib.fqd_partition_plan.argtypes = [vp, C.POINTER(u64), C.c_uint32, C.POINTER(u64), C.POINTER(u64)]
+    lib.fqd_partition_gather.argtypes = [vp, C.c_int, vp]
     lib.fqd_emission.argtypes = [vp, C.POINTER(Emission)]
     lib.fqd_emit.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(C.c_int)]
     lib.fqd_stats.argtypes = [vp, C.POINTER(Stats)]
@@ -249,6 +258,43 @@ class Engine:
 
     def finish(self):
         self._check(self.lib.fqd_finish(self.h))
+
+    # -- staged finish + repartition by key range (multi-GPU sequence mode, see sharded_seq.py)
+    def finish_scan(self):
+        self._check(self.lib.fqd_finish_scan(self.h))
+
+    def finish_emit(self):
+        self._check(self.lib.fqd_finish_emit(self.h))
+
+    def boundary_get(self) -> bytes:
+        n = int(self.lib.fqd_boundary_bytes(self.h))
+        buf = C.create_string_buffer(n)
+        self._check(self.lib.fqd_boundary_get(self.h, buf))
+        return buf.raw
+
+    def boundary_fix(self, prev: bytes):
+        assert len(prev) == int(self.lib.fqd_boundary_bytes(self.h))
+        self._check(self.lib.fqd_boundary_fix(self.h, prev))
+
+    def partition_sample(self, n_samples: int):
+        """-> (numpy uint64 array [n_samples, 2] of (word 0, word 1) key pairs, records in this slice)"""
+        out = (C.c_uint64 * (2 * n_samples))()
+        n = C.c_uint64(0)
+        self._check(self.lib.fqd_partition_sample(self.h, n_samples, out, C.byref(n)))
+        return np.frombuffer(out, dtype=np.uint64).reshape(n_samples, 2).copy(), int(n.value)
+
+    def partition_plan(self, splitters, n_ranges: int):
+        """splitters: uint64 array [n_ranges - 1, 2] -> (records per owner, bytes[mate][owner])"""
+        mates = 2 if self.cfg.paired else 1
+        sp = np.ascontiguousarray(splitters, dtype=np.uint64).reshape(-1)
+        arr = (C.c_uint64 * max(1, sp.size))(*[int(x) for x in sp])
+        counts = (C.c_uint64 * n_ranges)()
+        nbytes = (C.c_uint64 * (mates * n_ranges))()
+        self._check(self.lib.fqd_partition_plan(self.h, arr, n_ranges, counts, nbytes))
+        return [int(c) for c in counts], [[int(nbytes[m * n_ranges + o]) for o in range(n_ranges)] for m in range(mates)]
+
+    def partition_gather(self, mate: int, dptr: int):
+        self._check(self.lib.fqd_partition_gather(self.h, mate, C.c_void_p(dptr)))
 
     def emission(self) -> Emission:
         em = Emission()

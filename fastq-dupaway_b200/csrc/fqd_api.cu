@@ -647,6 +647,48 @@ extern "C" int fqd_finish(fqd_handle* h) {
     seq_stats(h->seq, &h->stats);
     return rc;
 }
+extern "C" int fqd_finish_scan(fqd_handle* h) {
+    if (!h || !h->seq) return fail(h, FQD_ERR_INVALID, "fqd_finish_scan is for sequence-based modes");
+    cudaSetDevice(h->cfg.device);
+    int rc = seq_finish_scan(h->seq, &h->err);
+    seq_stats(h->seq, &h->stats);
+    return rc;
+}
+extern "C" int fqd_finish_emit(fqd_handle* h) {
+    if (!h || !h->seq) return fail(h, FQD_ERR_INVALID, "fqd_finish_emit is for sequence-based modes");
+    cudaSetDevice(h->cfg.device);
+    int rc = seq_finish_emit(h->seq, &h->err);
+    seq_stats(h->seq, &h->stats);
+    return rc;
+}
+extern "C" size_t fqd_boundary_bytes(fqd_handle* h) { return h && h->seq ? boundary_words(h->seq->row_words) * sizeof(u64) : 0; }
+extern "C" int fqd_boundary_get(fqd_handle* h, void* state) {
+    if (!h || !h->seq || !state) return fail(h, FQD_ERR_INVALID, "fqd_boundary_get is for sequence-based modes");
+    cudaSetDevice(h->cfg.device);
+    return seq_boundary_get(h->seq, (u64*)state, &h->err);
+}
+extern "C" int fqd_boundary_fix(fqd_handle* h, const void* prev_state) {
+    if (!h || !h->seq || !prev_state) return fail(h, FQD_ERR_INVALID, "fqd_boundary_fix is for sequence-based modes");
+    cudaSetDevice(h->cfg.device);
+    return seq_boundary_fix(h->seq, (const u64*)prev_state, &h->err);
+}
+extern "C" int fqd_partition_sample(fqd_handle* h, uint32_t n_samples, uint64_t* samples, uint64_t* n_records) {
+    if (!h || !h->seq || !samples || !n_records) return fail(h, FQD_ERR_INVALID, "fqd_partition_sample is for sequence-based modes");
+    cudaSetDevice(h->cfg.device);
+    int rc = seq_partition_sample(h->seq, n_samples, (u64*)samples, (u64*)n_records, &h->err);
+    seq_stats(h->seq, &h->stats);
+    return rc;
+}
+extern "C" int fqd_partition_plan(fqd_handle* h, const uint64_t* splitters, uint32_t n_ranges, uint64_t* counts, uint64_t* bytes) {
+    if (!h || !h->seq || !counts || !bytes || (n_ranges > 1 && !splitters)) return fail(h, FQD_ERR_INVALID, "fqd_partition_plan: bad arguments");
+    cudaSetDevice(h->cfg.device);
+    return seq_partition_plan(h->seq, (const u64*)splitters, n_ranges, (u64*)counts, (u64*)bytes, &h->err);
+}
+extern "C" int fqd_partition_gather(fqd_handle* h, int mate, void* d_out) {
+    if (!h || !h->seq) return fail(h, FQD_ERR_INVALID, "fqd_partition_gather is for sequence-based modes");
+    cudaSetDevice(h->cfg.device);
+    return seq_partition_gather(h->seq, mate, d_out, &h->err);
+}
 extern "C" int fqd_emit(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, int* done) {
     if (!h || !h->seq || !dst || !n_bytes || !done) return fail(h, FQD_ERR_INVALID, "fqd_emit is for sequence / unordered modes");
     cudaSetDevice(h->cfg.device);

@@ -65,7 +65,14 @@ struct ScanParams {
     const u32* perm; u64 n; u32 dist;
     u32* keep;                            // [n] in sorted order: 1 = written
     u32* brk;                             // hamming: definite cluster breaks
+    u32* tail_head;                       // hamming: record that is the cluster head after the last sorted record
+                                          // (0xFFFFFFFF: the head handed in by the previous key range)
 };
+
+// Boundary state between two key ranges of a sorted stream that is split across GPUs (multi-GPU sequence mode).
+// Layout in 64-bit words, rw = row words:  [0,rw) last sorted row   [rw] its lengths (mate 1 | mate 2 << 32)
+//   [rw+1, 2rw+1) row of the cluster head after the last record   [2rw+1] its lengths   [2rw+2] 1 = valid
+__host__ __device__ inline u32 boundary_words(u32 rw) { return 2u * rw + 4u; }
 
 // TightComparator (src/comparator.cpp:45-58) against the previous record of the sorted stream
 __global__ void k_scan_tight(const ScanParams p) {
@@ -128,7 +135,8 @@ __global__ void k_ham_segments(const ScanParams p) {
         if (!p.brk[i]) continue;
         p.keep[i] = 1;
         u32 head = p.perm[i];
-        for (u64 j = i + 1; j < p.n && !p.brk[j]; ++j) {
+        u64 j = i + 1;
+        for (; j < p.n && !p.brk[j]; ++j) {
             const u32 c = p.perm[j];
             const u64* a = p.rows + (u64)c * p.stride;
             const u64* q = p.rows + (u64)head * p.stride;
@@ -138,6 +146,123 @@ __global__ void k_ham_segments(const ScanParams p) {
             p.keep[j] = dup ? 0u : 1u;
             if (!dup) head = c;
         }
+        if (j == p.n && p.tail_head) *p.tail_head = head;      // cluster head at the end of this key range
+    }
+}
+
+// ---- the first sorted records of a key range, re-evaluated against the boundary state of the range before it
+__global__ void k_fix_first_tight(const ScanParams p, const u64* prev) {
+    if (p.n == 0 || !prev[2 * p.stride + 2]) return;
+    p.keep[0] = rows_equal_range(p.rows + (u64)p.perm[0] * p.stride, prev, 0, p.W * p.mates) ? 0u : 1u;
+}
+__global__ void k_fix_first_loose(const ScanParams p, const u64* prev) {
+    if (p.n == 0 || !prev[2 * p.stride + 2]) return;
+    const u32 c = p.perm[0];
+    const u64* a = p.rows + (u64)c * p.stride;
+    const u64 pl = prev[p.stride];
+    const u32 lc1 = p.len0[c], lh1 = (u32)pl;
+    bool dup = prefix_equal(a, prev, min(lc1, lh1));
+    if (dup && p.mates == 2) {
+        const u32 lc2 = p.len1[c], lh2 = (u32)(pl >> 32);
+        dup = prefix_equal(a + p.W, prev + p.W, min(lc2, lh2));
+        if (dup) dup = ((lh1 <= lc1) && (lh2 <= lc2)) || ((lh1 > lc1) && (lh2 > lc2));
+    }
+    p.keep[0] = dup ? 0u : 1u;
+}
+// tail-hamming: is the first record a definite break against the last record of the previous range?  If not, the
+// first segment belongs to the previous range's last cluster: scan it again, starting from that cluster's head.
+__global__ void k_fix_first_ham(const ScanParams p, const u64* prev) {
+    if (p.n == 0 || !prev[2 * p.stride + 2]) return;
+    const u32 c0 = p.perm[0];
+    const u64* a0 = p.rows + (u64)c0 * p.stride;
+    const u64 pl = prev[p.stride];
+    bool same = p.len0[c0] == (u32)pl && hamming_words(a0, prev, p.W) <= 2u * p.dist;
+    if (same && p.mates == 2) same = p.len1[c0] == (u32)(pl >> 32) && hamming_words(a0 + p.W, prev + p.W, p.W) <= 2u * p.dist;
+    if (!same) { p.brk[0] = 1; return; }
+    p.brk[0] = 0;
+    const u64* hq = prev + p.stride + 1;          // head of the previous range's last cluster
+    u32 head = 0xFFFFFFFFu;
+    u64 j = 0;
+    for (; j < p.n && (j == 0 || !p.brk[j]); ++j) {
+        const u32 c = p.perm[j];
+        const u64* a = p.rows + (u64)c * p.stride;
+        bool dup = hamming_words(a, hq, p.W) <= p.dist;
+        if (dup && p.mates == 2) dup = hamming_words(a + p.W, hq + p.W, p.W) <= p.dist;
+        p.keep[j] = dup ? 0u : 1u;
+        if (!dup) { head = c; hq = a; }
+    }
+    if (j == p.n) *p.tail_head = head;
+}
+// boundary state after the last sorted record of this range (prev: the state this range started from, or nullptr)
+__global__ void k_tail_state(const ScanParams p, const u64* prev, int hamming, u64* out) {
+    const u32 rw = p.stride;
+    const u32 t = threadIdx.x;
+    const u32 last = p.perm[p.n - 1];
+    u32 head = last;
+    bool ext = false;
+    if (hamming) { head = *p.tail_head; ext = head == 0xFFFFFFFFu; }
+    for (u32 w = t; w < rw; w += blockDim.x) {
+        out[w] = p.rows[(u64)last * rw + w];
+        out[rw + 1 + w] = ext ? prev[rw + 1 + w] : p.rows[(u64)head * rw + w];
+    }
+    if (t == 0) {
+        out[rw] = (u64)p.len0[last] | (p.len1 ? (u64)p.len1[last] << 32 : 0ull);
+        out[2 * rw + 1] = ext ? prev[2 * rw + 1] : ((u64)p.len0[head] | (p.len1 ? (u64)p.len1[head] << 32 : 0ull));
+        out[2 * rw + 2] = 1; out[2 * rw + 3] = 0;
+    }
+}
+
+// ---- repartition of the input records by key range (multi-GPU sequence mode)
+// owner of record i = number of splitters <= (word 0, word 1) of its row
+__global__ void k_range_owner(const u64* rows, u32 stride, u64 n, const u64* splitters, u32 n_split, u64* owner_key, u32* idx) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        const u64 w0 = rows[i * stride], w1 = rows[i * stride + 1];
+        u32 lo = 0, hi = n_split;            // first splitter > key
+        while (lo < hi) {
+            const u32 mid = (lo + hi) >> 1;
+            const u64 s0 = splitters[2 * mid], s1 = splitters[2 * mid + 1];
+            if (s0 < w0 || (s0 == w0 && s1 <= w1)) lo = mid + 1; else hi = mid;
+        }
+        owner_key[i] = lo;
+        idx[i] = (u32)i;
+    }
+}
+__global__ void k_range_starts(const u64* sorted_owner, u64 n, u32 n_shards, u64* starts) {
+    const u32 o = threadIdx.x;
+    if (o > n_shards) return;
+    u64 lo = 0, hi = n;                      // first position with owner >= o
+    while (lo < hi) { u64 mid = (lo + hi) >> 1; if (sorted_owner[mid] < o) lo = mid + 1; else hi = mid; }
+    starts[o] = lo;
+}
+__global__ void k_gather_u32(const u32* src, const u32* perm, u64 n, u32* out) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) out[i] = src[perm[i]];
+}
+__global__ void k_pick_u64(const u64* src, const u64* pos, u32 n, u64 total_pos, u64 total, u64* out) {
+    const u32 t = threadIdx.x;
+    if (t < n) out[t] = pos[t] >= total_pos ? total : src[pos[t]];
+}
+__global__ void k_sample_rows(const u64* rows, u32 stride, u64 n, u32 n_samples, u64* out) {
+    const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_samples) return;
+    const u64 i = (u64)(((unsigned __int128)j * n) / n_samples);
+    out[2 * j] = rows[i * stride]; out[2 * j + 1] = rows[i * stride + 1];
+}
+// records in `perm` order, packed back to back at dst[r] (segmented input, one warp per record)
+__global__ void k_gather_records_perm(const u64* rec_off, const u32* rec_len, const u32* perm, const u64* dst, u64 count,
+                                      const u64* seg_base, u8* const* seg_ptr, u32 n_segs, u8* out) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 r = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < count; r += warps) {
+        const u32 g = perm[r];
+        const u64 o = rec_off[g];
+        u32 lo = 0, hi = n_segs;             // last segment whose logical base is <= o
+        while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (seg_base[mid] <= o) lo = mid; else hi = mid; }
+        const u8* src = seg_ptr[lo] + (o - seg_base[lo]);
+        u8* d = out + dst[r];
+        const u32 n = rec_len[g];
+        for (u32 i = lane; i < n; i += 32) d[i] = src[i];
     }
 }
 
@@ -369,6 +494,14 @@ struct SeqState {
     u8* d_stage = nullptr; size_t stage_cap = 0;
     u32* d_dst = nullptr; size_t dst_cap = 0;
     u64* em_scan_state = nullptr; u32* em_ticket = nullptr; u64* em_total = nullptr;
+    // stages of fqd_finish (the multi-GPU driver runs them one by one, with the boundary exchange in between)
+    bool parsed = false, scanned = false;
+    u32 *d_perm = nullptr, *d_keep = nullptr, *d_brk = nullptr, *d_tail_head = nullptr;
+    u64 *d_bound_prev = nullptr, *d_bound_out = nullptr;
+    bool has_prev = false;
+    // repartition by key range
+    u32* d_part_perm = nullptr; u64* d_part_starts = nullptr; u64* d_part_off[2] = {nullptr, nullptr};
+    u32 part_G = 0; u64 part_n = 0;
     bool lists_on_host = false;      // h_off / h_len filled (only fqd_emission needs them)
     u32* h_lenwin = nullptr;         // pinned window of record lengths for fqd_emit's batch cuts
     std::vector<void*> scratch;      // freed at destroy / reset
@@ -469,6 +602,9 @@ static int seq_reset(SeqState* s, std::string* err) {
         if (s->mate[m].d_bad) SEQ_TRY(cudaMemsetAsync(s->mate[m].d_bad, 0xFF, s->capacity * sizeof(u32), s->stream));
     }
     s->n = s->n_out = 0; s->finished = false; s->ms = 0;
+    s->parsed = s->scanned = s->has_prev = false;
+    s->d_perm = s->d_keep = s->d_brk = s->d_tail_head = nullptr; s->d_bound_prev = s->d_bound_out = nullptr;
+    s->d_part_perm = nullptr; s->d_part_starts = nullptr; s->d_part_off[0] = s->d_part_off[1] = nullptr; s->part_G = 0; s->part_n = 0;
     s->emit_cursor[0] = s->emit_cursor[1] = 0;
     for (int m = 0; m < 2; ++m) { s->d_o_off[m] = nullptr; s->d_o_len[m] = nullptr; s->d_seg_base[m] = nullptr; s->d_seg_ptr[m] = nullptr; }
     s->d_stage = nullptr; s->stage_cap = 0; s->d_dst = nullptr; s->dst_cap = 0; s->em_scan_state = nullptr;
@@ -732,37 +868,80 @@ static int sort_rows(SeqState* s, const u64* rows, u32 stride, u32 w_begin, u32 
 }
 
 // ---------------------------------------------------------------------------------------------------------
-static int seq_finish_sequence_mode(SeqState* s, std::string* err) {
-    const u64 n = s->n;
-    int rc;
-    u32* perm;
-    SeqTrace tr;
-    if ((rc = seq_dalloc(s, &perm, n, err))) return rc;
-    if ((rc = sort_rows(s, s->d_keys, s->row_words, 0, s->row_words, 60, n, perm, err))) return rc;
-    tr.mark(s->stream, "sort_rows");
-
-    u32 *keep, *excl, *brk = nullptr;
-    if ((rc = seq_dalloc(s, &keep, n, err)) || (rc = seq_dalloc(s, &excl, n, err))) return rc;
+static ScanParams seq_scan_params(SeqState* s) {
     ScanParams sp;
     sp.rows = s->d_keys; sp.stride = s->row_words; sp.W = s->W; sp.mates = s->mates;
     sp.len0 = s->mate[0].d_seq_len; sp.len1 = s->mates == 2 ? s->mate[1].d_seq_len : nullptr;
-    sp.perm = perm; sp.n = n; sp.dist = s->cfg.hamming_dist; sp.keep = keep; sp.brk = nullptr;
+    sp.perm = s->d_perm; sp.n = s->n; sp.dist = s->cfg.hamming_dist; sp.keep = s->d_keep; sp.brk = s->d_brk;
+    sp.tail_head = s->d_tail_head;
+    return sp;
+}
+
+// stage 1 of fqd_finish: sort + comparator scan -> keep flags in sorted order (as if nothing preceded this input)
+static int seq_scan_stage(SeqState* s, std::string* err) {
+    const u64 n = s->n;
+    int rc;
+    SeqTrace tr;
+    if ((rc = seq_dalloc(s, &s->d_perm, n, err))) return rc;
+    if ((rc = sort_rows(s, s->d_keys, s->row_words, 0, s->row_words, 60, n, s->d_perm, err))) return rc;
+    tr.mark(s->stream, "sort_rows");
+    if ((rc = seq_dalloc(s, &s->d_keep, n, err)) || (rc = seq_dalloc(s, &s->d_tail_head, 1, err)) ||
+        (rc = seq_dalloc(s, &s->d_bound_prev, boundary_words(s->row_words), err)) ||
+        (rc = seq_dalloc(s, &s->d_bound_out, boundary_words(s->row_words), err))) return rc;
+    SEQ_TRY(cudaMemsetAsync(s->d_bound_prev, 0, boundary_words(s->row_words) * sizeof(u64), s->stream));
+    if (s->cfg.mode == FQD_MODE_SEQ_HAMMING && (rc = seq_dalloc(s, &s->d_brk, n, err))) return rc;
+    const ScanParams sp = seq_scan_params(s);
     if (s->cfg.mode == FQD_MODE_SEQ_TIGHT) k_scan_tight<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
     else if (s->cfg.mode == FQD_MODE_SEQ_LOOSE) k_scan_loose<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
     else {
-        if ((rc = seq_dalloc(s, &brk, n, err))) return rc;
-        sp.brk = brk;
         k_ham_breaks<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
         k_ham_segments<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
         s->launches++;
     }
     s->launches++;
+    s->scanned = true;
+    tr.mark(s->stream, "scan");
+    return FQD_OK;
+}
+
+// The boundary state after this input's last sorted record (host buffer of boundary_words(row_words) words).
+static int seq_boundary_get(SeqState* s, u64* out, std::string* err) {
+    if (!s->scanned) { *err = "boundary state before the scan stage"; return FQD_ERR_INVALID; }
+    const ScanParams sp = seq_scan_params(s);
+    k_tail_state<<<1, 64, 0, s->stream>>>(sp, s->d_bound_prev, s->cfg.mode == FQD_MODE_SEQ_HAMMING ? 1 : 0, s->d_bound_out);
+    s->launches++;
+    SEQ_TRY(cudaMemcpyAsync(out, s->d_bound_out, boundary_words(s->row_words) * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    return FQD_OK;
+}
+// Re-evaluate the first sorted records against the boundary state of the key range that precedes this input.
+static int seq_boundary_fix(SeqState* s, const u64* prev, std::string* err) {
+    if (!s->scanned || s->finished) { *err = "boundary fix outside the scan stage"; return FQD_ERR_INVALID; }
+    SEQ_TRY(cudaMemcpyAsync(s->d_bound_prev, prev, boundary_words(s->row_words) * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
+    const ScanParams sp = seq_scan_params(s);
+    if (s->cfg.mode == FQD_MODE_SEQ_TIGHT) k_fix_first_tight<<<1, 1, 0, s->stream>>>(sp, s->d_bound_prev);
+    else if (s->cfg.mode == FQD_MODE_SEQ_LOOSE) k_fix_first_loose<<<1, 1, 0, s->stream>>>(sp, s->d_bound_prev);
+    else k_fix_first_ham<<<1, 1, 0, s->stream>>>(sp, s->d_bound_prev);
+    s->launches++;
+    SEQ_TRY(cudaStreamSynchronize(s->stream));       // prev is the caller's buffer
+    s->has_prev = true;
+    return FQD_OK;
+}
+
+// stage 2 of fqd_finish: survivors -> emission lists
+static int seq_emit_stage(SeqState* s, std::string* err) {
+    const u64 n = s->n;
+    int rc;
+    SeqTrace tr;
+    u32* excl;
+    if ((rc = seq_dalloc(s, &excl, n, err))) return rc;
+    u32 *keep = s->d_keep, *perm = s->d_perm;
     SortScratch sc;      // only the scan scratch is used here
     if ((rc = seq_dalloc(s, &sc.scan_state, (n + SCAN_TILE - 1) / SCAN_TILE + 16, err)) || (rc = seq_dalloc(s, &sc.ticket, 4, err)) ||
         (rc = seq_dalloc(s, &sc.d_total, 2, err))) return rc;
     u64 n_out = 0;
     if ((rc = device_scan(s, sc, keep, excl, n, &n_out, err))) return rc;
-    tr.mark(s->stream, "scan + survivor count");
+    tr.mark(s->stream, "survivor count");
     s->n_out = n_out;
     u64 *o_off[2] = {nullptr, nullptr}; u32 *o_len[2] = {nullptr, nullptr}; u32* o_idx;
     if ((rc = seq_dalloc(s, &o_idx, n_out, err))) return rc;
@@ -782,9 +961,10 @@ static int seq_finish_sequence_mode(SeqState* s, std::string* err) {
 
 static int seq_finish_unordered(SeqState* s, std::string* err);
 
-static int seq_finish(SeqState* s, std::string* err) {
-    if (s->finished) { *err = "fqd_finish called twice"; return FQD_ERR_INVALID; }
-    s->finished = true;
+// everything appended so far is parsed; s->n = records (pairs) that take part
+static int seq_parse_rest(SeqState* s, std::string* err) {
+    if (s->parsed) return FQD_OK;
+    s->parsed = true;
     SeqTrace tr;
     for (u32 m = 0; m < s->mates; ++m) {
         SeqMate& mt = s->mate[m];
@@ -805,9 +985,50 @@ static int seq_finish(SeqState* s, std::string* err) {
     if (s->mates == 2 && !s->cfg.unordered) n = std::min(n, s->mate[1].n_records);      // stops at the shorter file
     if (n == 0 || (s->mates == 2 && s->mate[1].n_records == 0)) { seq_set_error(s, FQD_ERR_EMPTY, 0, 0, 0); return FQD_OK; }
     s->n = n;
+    return FQD_OK;
+}
+
+// fqd_finish_scan / fqd_finish_emit: the two halves of fqd_finish for sequence-based modes
+static int seq_finish_scan(SeqState* s, std::string* err) {
+    if (s->finished || s->scanned) { *err = "fqd_finish_scan called twice"; return FQD_ERR_INVALID; }
+    if (s->cfg.unordered) { *err = "staged finish is for sequence-based modes"; return FQD_ERR_INVALID; }
+    int rc = seq_parse_rest(s, err);
+    if (rc || s->stats.err) return rc;
     SEQ_TRY(cudaEventRecord(s->ev0, s->stream));
-    int rc = s->cfg.unordered ? seq_finish_unordered(s, err) : seq_finish_sequence_mode(s, err);
+    if ((rc = seq_scan_stage(s, err))) return rc;
+    SEQ_TRY(cudaEventRecord(s->ev1, s->stream));
+    SEQ_TRY(cudaEventSynchronize(s->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, s->ev0, s->ev1); s->ms += ms;
+    return FQD_OK;
+}
+static int seq_finish_emit(SeqState* s, std::string* err) {
+    if (s->finished) { *err = "fqd_finish called twice"; return FQD_ERR_INVALID; }
+    s->finished = true;
+    if (s->stats.err) return FQD_OK;
+    if (!s->scanned) { *err = "fqd_finish_emit before fqd_finish_scan"; return FQD_ERR_INVALID; }
+    SEQ_TRY(cudaEventRecord(s->ev0, s->stream));
+    int rc = seq_emit_stage(s, err);
     if (rc) return rc;
+    SEQ_TRY(cudaEventRecord(s->ev1, s->stream));
+    SEQ_TRY(cudaEventSynchronize(s->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, s->ev0, s->ev1); s->ms += ms;
+    return FQD_OK;
+}
+
+static int seq_finish_unordered(SeqState* s, std::string* err);
+
+static int seq_finish(SeqState* s, std::string* err) {
+    if (s->finished) { *err = "fqd_finish called twice"; return FQD_ERR_INVALID; }
+    if (!s->cfg.unordered) {
+        int rc = s->scanned ? FQD_OK : seq_finish_scan(s, err);
+        if (rc) return rc;
+        return seq_finish_emit(s, err);
+    }
+    s->finished = true;
+    int rc = seq_parse_rest(s, err);
+    if (rc || s->stats.err) return rc;
+    SEQ_TRY(cudaEventRecord(s->ev0, s->stream));
+    if ((rc = seq_finish_unordered(s, err))) return rc;
     SEQ_TRY(cudaEventRecord(s->ev1, s->stream));
     SEQ_TRY(cudaEventSynchronize(s->ev1));
     float ms = 0; cudaEventElapsedTime(&ms, s->ev0, s->ev1); s->ms += ms;
@@ -932,21 +1153,108 @@ __global__ void k_gather_records(const u64* off, const u32* len, const u32* dst,
     }
 }
 
+// per mate: where every input segment lives (logical base -> device pointer), for the record gathers
+static int seq_upload_segtab(SeqState* s, int m, std::string* err) {
+    if (s->d_seg_base[m]) return FQD_OK;
+    SeqMate& mt = s->mate[m];
+    std::vector<u64> base; std::vector<u8*> ptr;
+    for (auto& sg : mt.segs) { base.push_back(sg.logical_base); ptr.push_back(sg.d); }
+    s->n_segs[m] = (u32)base.size();
+    int rc;
+    if ((rc = seq_dalloc(s, &s->d_seg_base[m], base.size(), err)) || (rc = seq_dalloc(s, &s->d_seg_ptr[m], ptr.size(), err))) return rc;
+    SEQ_TRY(cudaMemcpyAsync(s->d_seg_base[m], base.data(), base.size() * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
+    SEQ_TRY(cudaMemcpyAsync(s->d_seg_ptr[m], ptr.data(), ptr.size() * sizeof(u8*), cudaMemcpyHostToDevice, s->stream));
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    return FQD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Repartition by key range (multi-GPU sequence mode): every rank parses its slice of the input,
+// the ranks agree on G-1 splitters over (word 0, word 1) of the key rows, every record goes to the rank that owns
+// its key range - as raw bytes, grouped by owner, input order kept - and that rank deduplicates what it received
+// with the ordinary single-GPU engine.  Rows with equal leading words share an owner, so exact duplicates never
+// straddle two ranks; prefix and Hamming neighbours can, which the boundary state above takes care of.
+static int seq_partition_sample(SeqState* s, u32 n_samples, u64* out, u64* n_records, std::string* err) {
+    int rc = seq_parse_rest(s, err);
+    if (rc) return rc;
+    *n_records = s->stats.err ? 0 : s->n;
+    if (s->stats.err == FQD_ERR_EMPTY) { s->stats.err = 0; s->n = 0; }      // an empty slice is fine here
+    if (s->stats.err || s->n == 0 || n_samples == 0) { for (u32 i = 0; i < 2 * n_samples; ++i) out[i] = ~0ull; return FQD_OK; }
+    u64* d_out;
+    if ((rc = seq_dalloc(s, &d_out, 2ull * n_samples, err))) return rc;
+    k_sample_rows<<<(n_samples + 255) / 256, 256, 0, s->stream>>>(s->d_keys, s->row_words, s->n, n_samples, d_out);
+    s->launches++;
+    SEQ_TRY(cudaMemcpyAsync(out, d_out, 2ull * n_samples * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    return FQD_OK;
+}
+
+// splitters: (G-1) x 2 words, ascending.  counts[G]: records per owner; bytes[mates * G]: raw bytes per mate and owner
+static int seq_partition_plan(SeqState* s, const u64* splitters, u32 G, u64* counts, u64* bytes, std::string* err) {
+    if (!s->parsed) { *err = "fqd_partition_plan before fqd_partition_sample"; return FQD_ERR_INVALID; }
+    if (G == 0 || G > 64) { *err = "bad number of key ranges"; return FQD_ERR_INVALID; }
+    const u64 n = s->n;
+    s->part_G = G; s->part_n = n;
+    for (u32 o = 0; o < G; ++o) { counts[o] = 0; for (u32 m = 0; m < s->mates; ++m) bytes[m * G + o] = 0; }
+    if (n == 0) return FQD_OK;
+    int rc;
+    SortScratch sc;
+    if ((rc = sort_scratch_alloc(s, sc, n, err))) return rc;
+    u64* d_split;
+    if ((rc = seq_dalloc(s, &d_split, 2ull * std::max(G, 2u), err)) || (rc = seq_dalloc(s, &s->d_part_starts, G + 1, err)) ||
+        (rc = seq_dalloc(s, &s->d_part_perm, n, err))) return rc;
+    if (G > 1) SEQ_TRY(cudaMemcpyAsync(d_split, splitters, 2ull * (G - 1) * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
+    k_range_owner<<<seq_grid(s, n), 256, 0, s->stream>>>(s->d_keys, s->row_words, n, d_split, G - 1, sc.keyA, sc.aA);
+    if ((rc = radix_sort(s, sc, n, 0, 8, false, err))) return rc;
+    k_range_starts<<<1, 128, 0, s->stream>>>(sc.keyA, n, G, s->d_part_starts);
+    SEQ_TRY(cudaMemcpyAsync(s->d_part_perm, sc.aA, n * sizeof(u32), cudaMemcpyDeviceToDevice, s->stream));
+    s->launches += 2;
+    std::vector<u64> h_starts(G + 1), h_pick(G + 1);
+    SEQ_TRY(cudaMemcpyAsync(h_starts.data(), s->d_part_starts, (G + 1) * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    // byte offset of every record in the owner-grouped stream of each mate
+    u32* lens;
+    u64* d_pick;
+    if ((rc = seq_dalloc(s, &lens, n, err)) || (rc = seq_dalloc(s, &d_pick, G + 1, err))) return rc;
+    for (u32 m = 0; m < s->mates; ++m) {
+        if ((rc = seq_dalloc(s, &s->d_part_off[m], n + 1, err))) return rc;
+        k_gather_u32<<<seq_grid(s, n), 256, 0, s->stream>>>(s->mate[m].d_rec_len, s->d_part_perm, n, lens);
+        const u64 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+        SEQ_TRY(cudaMemsetAsync(sc.scan_state, 0, tiles * sizeof(u64), s->stream));
+        SEQ_TRY(cudaMemsetAsync(sc.ticket, 0, sizeof(u32), s->stream));
+        k_scan_exclusive_t<u64><<<(unsigned)tiles, SCAN_THREADS, 0, s->stream>>>(lens, s->d_part_off[m], n, sc.scan_state, sc.ticket, sc.d_total);
+        SEQ_TRY(cudaMemcpyAsync(s->d_part_off[m] + n, sc.d_total, sizeof(u64), cudaMemcpyDeviceToDevice, s->stream));
+        k_pick_u64<<<1, 128, 0, s->stream>>>(s->d_part_off[m], s->d_part_starts, G + 1, n + 1, 0, d_pick);
+        s->launches += 3;
+        SEQ_TRY(cudaMemcpyAsync(h_pick.data(), d_pick, (G + 1) * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+        SEQ_TRY(cudaStreamSynchronize(s->stream));
+        for (u32 o = 0; o < G; ++o) bytes[m * G + o] = h_pick[o + 1] - h_pick[o];
+    }
+    for (u32 o = 0; o < G; ++o) counts[o] = h_starts[o + 1] - h_starts[o];
+    SEQ_TRY(cudaGetLastError());
+    return FQD_OK;
+}
+
+// the records of one mate, grouped by owner (input order inside a group), written back to back into d_out
+static int seq_partition_gather(SeqState* s, int m, void* d_out, std::string* err) {
+    if (!s->d_part_perm && s->part_n) { *err = "fqd_partition_gather before fqd_partition_plan"; return FQD_ERR_INVALID; }
+    if (m < 0 || (u32)m >= s->mates) { *err = "bad mate index"; return FQD_ERR_INVALID; }
+    if (s->part_n == 0) return FQD_OK;
+    int rc = seq_upload_segtab(s, m, err);
+    if (rc) return rc;
+    k_gather_records_perm<<<seq_grid(s, s->part_n * 32), 256, 0, s->stream>>>(s->mate[m].d_rec_off, s->mate[m].d_rec_len, s->d_part_perm,
+                                                                             s->d_part_off[m], s->part_n, s->d_seg_base[m], s->d_seg_ptr[m],
+                                                                             s->n_segs[m], (u8*)d_out);
+    s->launches++;
+    SEQ_TRY(cudaGetLastError());
+    return FQD_OK;
+}
+
 static int seq_emit(SeqState* s, int m, void* dst, size_t cap, size_t* n_bytes, int* done, std::string* err) {
     if (!s->finished) { *err = "fqd_emit before fqd_finish"; return FQD_ERR_INVALID; }
     if (m < 0 || (u32)m >= s->mates) { *err = "bad mate index"; return FQD_ERR_INVALID; }
     *n_bytes = 0; *done = 0;
     if (s->stats.err && s->stats.err != FQD_ERR_BAD_BASE) { *done = 1; return FQD_OK; }
-    if (!s->d_seg_base[m]) {         // first call for this mate: upload its segment table
-        SeqMate& mt = s->mate[m];
-        std::vector<u64> base; std::vector<u8*> ptr;
-        for (auto& sg : mt.segs) { base.push_back(sg.logical_base); ptr.push_back(sg.d); }
-        s->n_segs[m] = (u32)base.size();
-        int rc;
-        if ((rc = seq_dalloc(s, &s->d_seg_base[m], base.size(), err)) || (rc = seq_dalloc(s, &s->d_seg_ptr[m], ptr.size(), err))) return rc;
-        SEQ_TRY(cudaMemcpy(s->d_seg_base[m], base.data(), base.size() * sizeof(u64), cudaMemcpyHostToDevice));
-        SEQ_TRY(cudaMemcpy(s->d_seg_ptr[m], ptr.data(), ptr.size() * sizeof(u8*), cudaMemcpyHostToDevice));
-    }
+    { int rc0 = seq_upload_segtab(s, m, err); if (rc0) return rc0; }
     const u64 k0 = s->emit_cursor[m];
     if (k0 >= s->n_out) { *done = 1; return FQD_OK; }
     // as many whole records as fit into cap (and into 2^31 bytes, the u32 offset range of one batch)

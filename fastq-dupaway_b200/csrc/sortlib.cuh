@@ -14,8 +14,9 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr u32 SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
 
-__global__ void __launch_bounds__(SCAN_THREADS) k_scan_exclusive(const u32* __restrict__ in, u32* __restrict__ out, u64 n,
-                                                                  u64* state, u32* ticket, u64* total_out) {
+template <class OUT>      // u32 (the caller knows the total fits) or u64
+__global__ void __launch_bounds__(SCAN_THREADS) k_scan_exclusive_t(const u32* __restrict__ in, OUT* __restrict__ out, u64 n,
+                                                                    u64* state, u32* ticket, u64* total_out) {
     __shared__ u32 warp_sum[SCAN_THREADS / 32];
     __shared__ u32 s_tile;
     __shared__ u64 s_prefix;
@@ -80,13 +81,14 @@ __global__ void __launch_bounds__(SCAN_THREADS) k_scan_exclusive(const u32* __re
         }
     }
     __syncthreads();
-    u32 run = (u32)s_prefix + warp_sum[warp] + (incl - sum);
+    OUT run = (OUT)s_prefix + (OUT)(warp_sum[warp] + (incl - sum));
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
         if (base + i < n) out[base + i] = run;
         run += v[i];
     }
 }
+#define k_scan_exclusive k_scan_exclusive_t<u32>
 
 // ---------------------------------------------------------------------------------------------------------
 // LSD radix sort, 8-bit digits, stable.  Items = (key64, a32[, b32]); one pass = histogram, scan, scatter.

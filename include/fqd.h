@@ -145,6 +145,33 @@ int fqd_emission(fqd_handle* h, fqd_emission_t* out);
 int fqd_emit(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, int* done);
 
 /*
+ * Multi-GPU sequence-based mode (one process per GPU, SURVEY.md 8e: sampled splitters + all-to-all).  The reference has
+ * no counterpart (it is single-threaded; its only "sharding" is the chunk + k-way merge of src/external_sort.hpp:88-207).
+ * Every rank appends ITS contiguous slice of the input to an "origin" handle, then
+ *   fqd_partition_sample   parses what was appended and returns n_samples evenly spaced (word 0, word 1) key pairs
+ *                          (2 x n_samples words; all-ones when the slice is empty) and the slice's record count;
+ *   the ranks all-gather the samples, sort them and agree on n_ranges - 1 ascending splitters;
+ *   fqd_partition_plan     owner of a record = number of splitters <= its (word 0, word 1); returns the record count
+ *                          per owner and, per mate and owner, the raw bytes that go there (bytes[mate * n_ranges + o]);
+ *   fqd_partition_gather   writes the raw records of one mate to a device buffer, grouped by owner, input order kept;
+ *   one all-to-all per mate moves the bytes; the receiver appends what it got, in rank order, to a second, ordinary
+ *   handle of the same mode (fqd_append_device) - the records of one key range, still in global input order.
+ * Exact duplicates share their leading key words and therefore their owner; prefix (loose) and Hamming neighbours may
+ * straddle two ranges.  So the finish is staged: fqd_finish_scan (sort + comparator scan, as if nothing preceded this
+ * range), then rank by rank fqd_boundary_get on range k-1 -> fqd_boundary_fix on range k (re-evaluates the first sorted
+ * records against the last record / last cluster head of the range before), then fqd_finish_emit.  The output of the
+ * job is the concatenation of the ranges' outputs in range order.  fqd_finish == fqd_finish_scan + fqd_finish_emit.
+ */
+int fqd_partition_sample(fqd_handle* h, uint32_t n_samples, uint64_t* samples, uint64_t* n_records);
+int fqd_partition_plan(fqd_handle* h, const uint64_t* splitters, uint32_t n_ranges, uint64_t* counts, uint64_t* bytes);
+int fqd_partition_gather(fqd_handle* h, int mate, void* d_out);
+int fqd_finish_scan(fqd_handle* h);
+size_t fqd_boundary_bytes(fqd_handle* h);
+int fqd_boundary_get(fqd_handle* h, void* state);
+int fqd_boundary_fix(fqd_handle* h, const void* prev_state);
+int fqd_finish_emit(fqd_handle* h);
+
+/*
  * Multi-GPU --fast mode (one handle per GPU / process).  The all-to-all exchanges themselves are
  * done by the caller (torch.distributed / NCCL) on the stream given to fqd_set_stream, between these calls:
  *   fqd_shard_pack     split + pack one chunk of THIS rank's input and group the packed keys by owning shard;
