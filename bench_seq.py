@@ -96,6 +96,70 @@ def run_mode(fqd, lib, mode, n_pairs, steps, dev=0):
     return line
 
 
+def run_mode_multi(fqd, lib, mode, n_pairs_per_rank, steps):
+    """N > 1 (under torchrun): weak scaling, every rank contributes n_pairs_per_rank pairs of ONE global stream
+    (rank r holds pairs [r * n, (r + 1) * n)); key-range sharding through fastq-dupaway_b200/sharded_seq.py."""
+    import torch
+    import torch.distributed as dist
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    sh = importlib.import_module("fastq-dupaway_b200.sharded_seq")
+    dev = local
+    chunk_pairs = 1_500_000
+    n = n_pairs_per_rank
+    n_chunks = (n + chunk_pairs - 1) // chunk_pairs
+    stage = [fqd.DeviceBuffer(chunk_pairs * REC + 65536, dev) for _ in range(2)]
+    ops = sh.GpuRangeOps(fqd, mode, fqd.FORMAT_FASTQ, True, 2, READ_LEN, n + 1024, int(n * 1.3) + (1 << 20), dev, seg_bytes=1 << 30)
+    times = []
+    res = None
+    for it in range(steps + 1):
+        if it:
+            ops.reset()
+        t_append = 0.0
+        for c in range(n_chunks):
+            first = rank * n + c * chunk_pairs
+            cnt = min(chunk_pairs, n - c * chunk_pairs)
+            for m in range(2):
+                assert lib.fqd_synth_fastq(dev, stage[m].ptr, first, cnt, READ_LEN, m + 1, SEED, DUP_PERMILLE, N_PERMILLE, VARIANT[mode]) == 0
+            ops.origin.timer_start()
+            for m in range(2):
+                ops.append(m, stage[m].ptr, cnt * REC)
+            t_append += ops.origin.timer_stop()          # parse + pack of this rank's slice (same as the N = 1 arm)
+            torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        res = sh.dedup_ranges(ops, dist, rank, world, n_samples=8192)
+        torch.cuda.synchronize(dev)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1) + t_append], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if it:
+            times.append(float(ms.item()))
+    tot = torch.tensor(list(res), dtype=torch.int64, device=f"cuda:{dev}")
+    own = [torch.zeros_like(tot) for _ in range(world)]
+    dist.all_gather(own, tot)
+    if rank == 0:
+        ms = sum(times) / len(times)
+        total = world * n
+        owned = [int(t[0].item()) for t in own]
+        line = {"metric": "dedup read pairs/sec", "mode": mode, "value": total / (ms / 1e3), "unit": "pairs/s",
+                "reads_per_s": 2 * total / (ms / 1e3), "n_gpus": world, "steps": steps, "ms_per_step": ms, "scaling": "weak",
+                "config": {"workload": f"synthetic {total} x 2x150bp paired-end FASTQ, 30% duplicates, --compare-seq {mode}",
+                           "pairs_per_gpu": n, "parallelism": f"key-range x{world}", "record_bytes": REC, "seed": SEED,
+                           "timed": "appends (parse + pack of the slice) + sample + splitters + plan + gather + all-to-all of raw records + parse + sort + scan + "
+                                    "boundary chain + emission lists (slices already appended and resident)"},
+                "pairs_total": total, "duplicates_removed": int(sum(int(t[2].item()) for t in own)),
+                "pairs_out": int(sum(int(t[1].item()) for t in own)), "owned_per_rank": owned,
+                "imbalance": max(owned) / (sum(owned) / world), "input_GBps": total * 2 * REC / (ms / 1e3) / 1e9,
+                "alltoall_bytes_per_gpu": n * 2 * REC}
+        print(json.dumps(line), flush=True)
+    ops.close()
+    for s_ in stage:
+        s_.free()
+
+
 def cpu_reference(mode, n_pairs):
     """The unmodified reference (oracle/_ref) on the same synthetic stream, one core, tmpfs."""
     sys.path.insert(0, str(ROOT / "oracle"))
@@ -133,6 +197,18 @@ def main():
     args = ap.parse_args()
     fqd = importlib.import_module("fastq-dupaway_b200")
     lib = fqd.load_library()
+    if int(os.environ.get("WORLD_SIZE", 1)) > 1:
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        modes = ["tight", "loose", "tail-hamming"] if args.mode == "all" else [args.mode]
+        for m in modes:
+            run_mode_multi(fqd, lib, m, args.pairs, args.steps)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     modes = ["tight", "loose", "tail-hamming", "unordered"] if args.mode == "all" else [args.mode]
     for m in modes:
         line = run_mode(fqd, lib, m, args.pairs, args.steps)

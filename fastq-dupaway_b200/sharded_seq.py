@@ -62,12 +62,16 @@ class GpuRangeOps:
 
     # -- owner side
     def receive(self, mate, recv):
+        self.torch.cuda.synchronize(self.dev)          # the all-to-all that fills recv runs on torch's stream
         if recv.numel():
             self.range.append_device(mate, recv.data_ptr(), int(recv.numel()))
             self.torch.cuda.synchronize(self.dev)
 
     def scan(self):
         self.range.finish_scan()
+        st = self.range.stats()
+        if st.err:
+            raise self.pkg.FqdError(st.err, f"key range engine: data error at record {st.err_record}")
 
     def boundary_bytes(self):
         return int(self.range.lib.fqd_boundary_bytes(self.range.h))
