@@ -20,7 +20,7 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
     dev = local_rank
     torch.cuda.set_device(dev)
     REC = b.REC_BYTES
-    chunk_reads = int(os.environ.get("FQD_BENCH_CHUNK_READS", 4_000_000))
+    chunk_reads = int(os.environ.get("FQD_BENCH_CHUNK_READS", 10_000_000))     # < 4 GiB per chunk (u32 offsets); fewer, larger chunks amortise the per-chunk collectives
     n_chunks = (n_per_rank + chunk_reads - 1) // chunk_reads
     raw = fqd.DeviceBuffer(n_per_rank * REC + 65536, dev)
     # chunk c of rank r = global reads [(c*world + r) * chunk_reads, ...): chunks are fed in global input order
