@@ -117,6 +117,7 @@ def load_library():
     lib.fqd_partition_gather.argtypes = [vp, C.c_int, vp]
     lib.fqd_emission.argtypes = [vp, C.POINTER(Emission)]
     lib.fqd_emit.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(C.c_int)]
+    lib.fqd_emit_clusters.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(C.c_int)]
     lib.fqd_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.fqd_set_stream.argtypes = [vp, vp]
     lib.fqd_shard_row_bytes.argtypes = [vp]
@@ -308,6 +309,18 @@ class Engine:
         while True:
             n, done = C.c_size_t(0), C.c_int(0)
             self._check(self.lib.fqd_emit(self.h, mate, buf, cap, C.byref(n), C.byref(done)))
+            out.append(buf.raw[: n.value])
+            if done.value:
+                break
+        return b"".join(out)
+
+    def emit_clusters_all(self, mate: int, cap: int = 1 << 20) -> bytes:
+        """Text of `<out>.clusters` for one mate (--write-clusters), gathered on the device."""
+        buf = C.create_string_buffer(cap)
+        out = []
+        while True:
+            n, done = C.c_size_t(0), C.c_int(0)
+            self._check(self.lib.fqd_emit_clusters(self.h, mate, buf, cap, C.byref(n), C.byref(done)))
             out.append(buf.raw[: n.value])
             if done.value:
                 break

@@ -694,6 +694,11 @@ extern "C" int fqd_emit(fqd_handle* h, int mate, void* dst, size_t cap, size_t* 
     cudaSetDevice(h->cfg.device);
     return seq_emit(h->seq, mate, dst, cap, n_bytes, done, &h->err);
 }
+extern "C" int fqd_emit_clusters(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, int* done) {
+    if (!h || !h->seq || !dst || !n_bytes || !done) return fail(h, FQD_ERR_INVALID, "fqd_emit_clusters is for sequence-based modes");
+    cudaSetDevice(h->cfg.device);
+    return seq_emit_clusters(h->seq, mate, dst, cap, n_bytes, done, &h->err);
+}
 extern "C" int fqd_emission(fqd_handle* h, fqd_emission_t* out) {
     if (!h || !h->seq || !out) return fail(h, FQD_ERR_INVALID, "fqd_emission is for sequence / unordered modes");
     return seq_emission(h->seq, out, &h->err);

@@ -502,6 +502,8 @@ struct SeqState {
     // repartition by key range
     u32* d_part_perm = nullptr; u64* d_part_starts = nullptr; u64* d_part_off[2] = {nullptr, nullptr};
     u32 part_G = 0; u64 part_n = 0;
+    u32* d_cl_len[2] = {nullptr, nullptr};     // --write-clusters: line length per sorted position
+    u64 cl_cursor[2] = {0, 0};
     bool lists_on_host = false;      // h_off / h_len filled (only fqd_emission needs them)
     u32* h_lenwin = nullptr;         // pinned window of record lengths for fqd_emit's batch cuts
     std::vector<void*> scratch;      // freed at destroy / reset
@@ -603,6 +605,7 @@ static int seq_reset(SeqState* s, std::string* err) {
     }
     s->n = s->n_out = 0; s->finished = false; s->ms = 0;
     s->parsed = s->scanned = s->has_prev = false;
+    s->d_cl_len[0] = s->d_cl_len[1] = nullptr; s->cl_cursor[0] = s->cl_cursor[1] = 0;
     s->d_perm = s->d_keep = s->d_brk = s->d_tail_head = nullptr; s->d_bound_prev = s->d_bound_out = nullptr;
     s->d_part_perm = nullptr; s->d_part_starts = nullptr; s->d_part_off[0] = s->d_part_off[1] = nullptr; s->part_G = 0; s->part_n = 0;
     s->emit_cursor[0] = s->emit_cursor[1] = 0;
@@ -1153,6 +1156,45 @@ __global__ void k_gather_records(const u64* off, const u32* len, const u32* dst,
     }
 }
 
+// ---- --write-clusters (src/seq_dup_remover.hpp:60-62,75-76,89-101 and the paired twin; src/file_utils.cpp:98-112):
+// one line per record in sorted order - the ID line of a written record (cluster head), "--" + ID line of a removed one
+__device__ __forceinline__ const u8* seg_locate(u64 o, const u64* seg_base, u8* const* seg_ptr, u32 n_segs) {
+    u32 lo = 0, hi = n_segs;             // last segment whose logical base is <= o
+    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (seg_base[mid] <= o) lo = mid; else hi = mid; }
+    return seg_ptr[lo] + (o - seg_base[lo]);
+}
+__global__ void k_cluster_lens(const u32* perm, const u32* keep, const u64* rec_off, const u32* rec_len, u64 n,
+                               const u64* seg_base, u8* const* seg_ptr, u32 n_segs, u32* out_len) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 i = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < n; i += warps) {
+        const u32 g = perm[i];
+        const u8* src = seg_locate(rec_off[g], seg_base, seg_ptr, n_segs);
+        const u32 len = rec_len[g];
+        u32 idlen = len;
+        for (u32 j0 = 0; j0 < len; j0 += 32) {
+            const u32 j = j0 + lane;
+            const u32 hit = __ballot_sync(0xFFFFFFFFu, j < len && src[j] == '\n');
+            if (hit) { idlen = j0 + (u32)__ffs((int)hit); break; }
+        }
+        if (lane == 0) out_len[i] = idlen + (keep[i] ? 0u : 2u);
+    }
+}
+__global__ void k_gather_clusters(const u32* perm, const u32* keep, const u64* rec_off, const u32* cl_len, const u32* dst, u64 k0, u64 count,
+                                  const u64* seg_base, u8* const* seg_ptr, u32 n_segs, u8* out) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
+    for (u64 r = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < count; r += warps) {
+        const u64 i = k0 + r;
+        const u8* src = seg_locate(rec_off[perm[i]], seg_base, seg_ptr, n_segs);
+        const u32 pre = keep[i] ? 0u : 2u;
+        const u32 n = cl_len[i] - pre;
+        u8* d = out + dst[r];
+        if (lane < pre) d[lane] = '-';
+        for (u32 j = lane; j < n; j += 32) d[pre + j] = src[j];
+    }
+}
+
 // per mate: where every input segment lives (logical base -> device pointer), for the record gathers
 static int seq_upload_segtab(SeqState* s, int m, std::string* err) {
     if (s->d_seg_base[m]) return FQD_OK;
@@ -1286,6 +1328,54 @@ static int seq_emit(SeqState* s, int m, void* dst, size_t cap, size_t* n_bytes, 
     s->emit_cursor[m] = k1;
     *n_bytes = bytes;
     *done = k1 >= s->n_out ? 1 : 0;
+    return FQD_OK;
+}
+
+// Streams the <out>.clusters text of one mate (sequence-based modes), like seq_emit streams the records.
+static int seq_emit_clusters(SeqState* s, int m, void* dst, size_t cap, size_t* n_bytes, int* done, std::string* err) {
+    if (!s->finished) { *err = "fqd_emit_clusters before fqd_finish"; return FQD_ERR_INVALID; }
+    if (s->cfg.unordered || s->cfg.mode == FQD_MODE_FAST) { *err = "cluster files exist in sequence-based modes only"; return FQD_ERR_INVALID; }
+    if (m < 0 || (u32)m >= s->mates) { *err = "bad mate index"; return FQD_ERR_INVALID; }
+    *n_bytes = 0; *done = 0;
+    if (s->stats.err || s->n == 0) { *done = 1; return FQD_OK; }
+    int rc = seq_upload_segtab(s, m, err);
+    if (rc) return rc;
+    const u64 n = s->n;
+    if (!s->d_cl_len[m]) {
+        if ((rc = seq_dalloc(s, &s->d_cl_len[m], n, err))) return rc;
+        k_cluster_lens<<<seq_grid(s, n * 32), 256, 0, s->stream>>>(s->d_perm, s->d_keep, s->mate[m].d_rec_off, s->mate[m].d_rec_len, n,
+                                                                   s->d_seg_base[m], s->d_seg_ptr[m], s->n_segs[m], s->d_cl_len[m]);
+        s->launches++;
+    }
+    const u64 k0 = s->cl_cursor[m];
+    if (k0 >= n) { *done = 1; return FQD_OK; }
+    const size_t lim = std::min<size_t>(cap, (size_t)1 << 31);
+    constexpr u64 LENWIN = 1u << 20;
+    if (!s->h_lenwin) SEQ_TRY(cudaHostAlloc(&s->h_lenwin, LENWIN * sizeof(u32), cudaHostAllocDefault));
+    const u64 nwin = std::min<u64>(LENWIN, n - k0);
+    SEQ_TRY(cudaMemcpyAsync(s->h_lenwin, s->d_cl_len[m] + k0, nwin * sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    u64 k1 = k0; size_t bytes = 0;
+    while (k1 < k0 + nwin && bytes + s->h_lenwin[k1 - k0] <= lim) { bytes += s->h_lenwin[k1 - k0]; ++k1; }
+    if (k1 == k0) { *err = "fqd_emit_clusters: cap is smaller than one line"; return FQD_ERR_INVALID; }
+    const u64 cnt = k1 - k0;
+    if (s->stage_cap < bytes) { if ((rc = seq_dalloc(s, &s->d_stage, bytes + 256, err))) return rc; s->stage_cap = bytes; }
+    if (s->dst_cap < cnt) {
+        if ((rc = seq_dalloc(s, &s->d_dst, cnt, err))) return rc;
+        s->dst_cap = cnt;
+        if ((rc = seq_dalloc(s, &s->em_scan_state, (cnt + SCAN_TILE - 1) / SCAN_TILE + 16, err)) || (rc = seq_dalloc(s, &s->em_ticket, 4, err)) ||
+            (rc = seq_dalloc(s, &s->em_total, 2, err))) return rc;
+    }
+    SortScratch sc; sc.scan_state = s->em_scan_state; sc.ticket = s->em_ticket; sc.d_total = s->em_total;
+    if ((rc = device_scan(s, sc, s->d_cl_len[m] + k0, s->d_dst, cnt, nullptr, err))) return rc;
+    k_gather_clusters<<<seq_grid(s, cnt * 32), 256, 0, s->stream>>>(s->d_perm, s->d_keep, s->mate[m].d_rec_off, s->d_cl_len[m], s->d_dst, k0, cnt,
+                                                                    s->d_seg_base[m], s->d_seg_ptr[m], s->n_segs[m], s->d_stage);
+    s->launches++;
+    SEQ_TRY(cudaMemcpyAsync(dst, s->d_stage, bytes, cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    s->cl_cursor[m] = k1;
+    *n_bytes = bytes;
+    *done = k1 >= n ? 1 : 0;
     return FQD_OK;
 }
 

@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstring>
 #include <iostream>
+#include <fstream>
 #include <memory>
 #include <stdexcept>
 #include <vector>
@@ -288,8 +289,6 @@ void SeqDupRemover::filterPE(const std::string& infile1, const std::string& infi
 
 void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int mates, const std::string* in,
                      const std::string* out, bool write_clusters, bool verbose, ssize_t memlimit, int device) {
-    if (write_clusters)
-        throw std::runtime_error("--write-clusters is not available in the B200 build yet");
     const int lpr = fasta ? 2 : 4;
     size_t block = (size_t)memlimit / (size_t)(mates * 3 * 2);
     block = std::min<size_t>(std::max<size_t>(block, 4u << 20), 256u << 20) & ~(size_t)4095;
@@ -365,6 +364,19 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
             }
         }
         for (auto& o : outs) o->close();
+        if (write_clusters) {
+            // ClusterFile (src/file_utils.cpp:98-112): plain text <outfile>.clusters next to every output file
+            for (int m = 0; m < mates; ++m) {
+                std::ofstream cf(out[m] + ".clusters", std::ios::binary);
+                for (;;) {
+                    size_t nb = 0; int done = 0;
+                    rc = fqd_emit_clusters(eng.get(), m, stage, cap, &nb, &done);
+                    if (rc) throw_engine_error(eng.get(), rc);
+                    cf.write((const char*)stage, (std::streamsize)nb);
+                    if (done) break;
+                }
+            }
+        }
         if (st.err == FQD_ERR_BAD_BASE) throw_data_error(st, fasta);     // --unordered: raised while pairs are keyed
         if (verbose) {
             if (unordered) {

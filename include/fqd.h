@@ -143,6 +143,10 @@ int fqd_emission(fqd_handle* h, fqd_emission_t* out);
  * (Replaces the `output_file.write(obj.start(), obj.size())` calls of src/seq_dup_remover.hpp:74,88,163-186 and
  * src/hash_dup_remover.hpp:295-298.) */
 int fqd_emit(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, int* done);
+/* --write-clusters (sequence-based modes): streams the text of `<out>.clusters` for one mate the same way - one line
+ * per input record in sorted order, the ID line of a written record (cluster head) or "--" + the ID line of a removed
+ * one (src/seq_dup_remover.hpp:60-62,75-76,89-101,142-146,165-169,187-208; src/file_utils.cpp:98-112). */
+int fqd_emit_clusters(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, int* done);
 
 /*
  * Multi-GPU sequence-based mode (one process per GPU, SURVEY.md 8e: sampled splitters + all-to-all).  The reference has

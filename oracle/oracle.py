@@ -156,6 +156,25 @@ def run_oracle(mode: str, fmt: int, b1: bytes, b2: bytes | None = None, dist: in
     return o1, o2, st
 
 
+def cluster_text(mode: str, fmt: int, b1: bytes, b2: bytes | None = None, dist: int = 2):
+    """Text of `<out>.clusters` per mate (--write-clusters): one line per record in sorted order, the ID line of a
+    written record or "--" + the ID line of a removed one (src/seq_dup_remover.hpp:60-62,75-76,89-101;
+    src/file_utils.cpp:98-112)."""
+    kept, st, order, _head = seq_mode(b1, b2, fmt, MODE_BY_NAME[mode], dist, want_clusters=True)
+    written = set(int(i) for i in kept)
+    outs = []
+    for b in ([b1] if b2 is None else [b1, b2]):
+        t, _ = split(b, fmt)
+        mv = memoryview(b)
+        parts = []
+        for i in order:
+            i = int(i)
+            idline = bytes(mv[int(t[i, 0]): int(t[i, 0] + t[i, 1])])
+            parts.append(idline if i in written else b"--" + idline)
+        outs.append(b"".join(parts))
+    return outs, st
+
+
 # ------------------------------------------------------------------------------------------------------
 # The compiled, unmodified reference (oracle/_ref) driven through its CLI.
 

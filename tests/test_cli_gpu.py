@@ -171,3 +171,21 @@ def test_error_messages_and_exit_codes(tmp_path):
                         "Sequence and Quality fields of Fastq record should have the same length!\n")
     r = run("-i", tmp_path / "missing.fq", "-o", tmp_path / "x.out", "--fast")
     assert r.returncode == 1 and r.stderr == f"Cannot open file {tmp_path / 'missing.fq'}\n" + banner + "File does not exist or cannot be opened!\n"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["tight", "loose"])
+def test_write_clusters_through_files(tmp_path, oracle, mode):
+    """--write-clusters: <out>.clusters next to every output file (src/file_utils.cpp:98-112)."""
+    s1, s2 = synth.make_pair(5000, seed=81, read_len=50, var_len=True, prefix_frac=0.3, dup_frac=0.5)
+    b1, b2 = synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2)
+    (tmp_path / "r1.fq").write_bytes(b1)
+    (tmp_path / "r2.fq").write_bytes(b2)
+    res = run("-i", tmp_path / "r1.fq", "-u", tmp_path / "r2.fq", "-o", tmp_path / "o1.fq", "-p", tmp_path / "o2.fq",
+              "--compare-seq", mode, "--write-clusters")
+    assert res.returncode == 0, res.stderr
+    texts, _ = oracle.cluster_text(mode, oracle.FASTQ, b1, b2)
+    e1, e2, _ = oracle.run_oracle(mode, oracle.FASTQ, b1, b2)
+    assert (tmp_path / "o1.fq").read_bytes() == e1 and (tmp_path / "o2.fq").read_bytes() == e2
+    assert (tmp_path / "o1.fq.clusters").read_bytes() == texts[0]
+    assert (tmp_path / "o2.fq.clusters").read_bytes() == texts[1]

@@ -140,6 +140,26 @@ def test_ref_stable_seq_modes(oracle, tmp_path, mode, dist, paired):
     assert _parse_counts(so)[:2] == [st.total, st.dups]
 
 
+@pytest.mark.parametrize("mode,dist", [("tight", 2), ("loose", 2), ("tail-hamming", 2)])
+@pytest.mark.parametrize("paired", [False, True])
+def test_ref_stable_cluster_files(oracle, tmp_path, mode, dist, paired):
+    """--write-clusters: the oracle's cluster text against the files the stable-sort build of the reference writes."""
+    _need_ref(oracle, stable=True)
+    kw = dict(read_len=30, var_len=True, min_len=0, n_frac=0.05, prefix_frac=0.3, sub_frac=0.3, dup_frac=0.5)
+    if paired:
+        s1, s2 = synth.make_pair(800, seed=21, **kw)
+        b1, b2 = synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2)
+    else:
+        b1, b2 = synth.to_fastq(synth.make_reads(1000, seed=22, **kw)), None
+    rc, r1, r2, so, se = oracle.run_ref(tmp_path, mode, oracle.FASTQ, b1, b2, dist=dist, stable=True, mem_mb=10240,
+                                        extra=["--write-clusters"])
+    assert rc == 0, se
+    texts, st = oracle.cluster_text(mode, oracle.FASTQ, b1, b2, dist=dist)
+    assert (tmp_path / "out_1.fq.clusters").read_bytes() == texts[0]
+    if paired:
+        assert (tmp_path / "out_2.fq.clusters").read_bytes() == texts[1]
+
+
 def _seq_column(buf, fmt_fastq=True):
     lines = buf.split(b"\n")
     step = 4 if fmt_fastq else 2

@@ -101,3 +101,29 @@ def test_error_paths(fqd, oracle):
     # bytes outside A/C/G/T/N are legal for the reference in this mode; this build reports them explicitly
     _, _, st = fqd.dedup_whole("tight", b"@a\nACGT\n+\nFFFF\n@b\nacgt\n+\nFFFF\n", None, fqd.FORMAT_FASTQ)
     assert st.err == 9
+
+
+@pytest.mark.parametrize("mode,dist", [("tight", 2), ("loose", 2), ("tail-hamming", 2)])
+@pytest.mark.parametrize("paired", [False, True])
+def test_cluster_files(fqd, oracle, mode, dist, paired):
+    """--write-clusters: fqd_emit_clusters against the oracle's cluster text (pinned to the reference in test_oracle.py);
+    small emission buffer, several input segments."""
+    kw = dict(read_len=40, var_len=True, min_len=0, n_frac=0.05, prefix_frac=0.3, sub_frac=0.3, dup_frac=0.5)
+    if paired:
+        s1, s2 = synth.make_pair(3000, seed=71, **kw)
+        bufs = [synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2)]
+    else:
+        bufs = [synth.to_fastq(synth.make_reads(4000, seed=72, **kw), id_fmt="@SYN.{i} some description {mate}")]
+    texts, est = oracle.cluster_text(mode, oracle.FASTQ, bufs[0], bufs[1] if paired else None, dist=dist)
+    eng = fqd.Engine(mode, fqd.FORMAT_FASTQ, paired, False, dist, 40, 5000, 1 << 17, 0, 0)
+    try:
+        for m, b in enumerate(bufs):
+            for o in range(0, len(b), 70_000):
+                eng.append(m, b[o: o + 70_000])
+        eng.finish()
+        st = eng.stats()
+        assert st.err == 0 and (st.total, st.dups) == (est.total, est.dups)
+        for m in range(len(bufs)):
+            assert eng.emit_clusters_all(m, cap=3000) == texts[m]
+    finally:
+        eng.close()
