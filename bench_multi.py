@@ -96,6 +96,8 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
                              "collectives_per_chunk": 3},
                 "duplicates_removed": int(tot[0].item()), "input_GBps": n_total * REC / (ms_per_step / 1000.0) / 1e9}
         print(json.dumps(line), flush=True)
+    if rank == 0 and sharded.TRACE:
+        print("[fqd trace] per-phase wall clock, ms over all steps:", json.dumps({k: round(v, 2) for k, v in sharded.TRACE.items()}), file=sys.stderr)
     eng.close()
     raw.free()
     dist.barrier()

@@ -40,7 +40,7 @@ class Config(C.Structure):
     _fields_ = [("abi_version", C.c_uint32), ("device", C.c_int32), ("mode", C.c_int32), ("format", C.c_int32),
                 ("paired", C.c_int32), ("unordered", C.c_int32), ("hamming_dist", C.c_uint32),
                 ("max_seq_len", C.c_uint32), ("max_records", C.c_uint64), ("max_chunk_bytes", C.c_uint64),
-                ("max_chunk_records", C.c_uint64), ("max_tag_len", C.c_uint32), ("reserved", C.c_uint32)]
+                ("max_chunk_records", C.c_uint64), ("max_tag_len", C.c_uint32), ("byte_keys", C.c_uint32)]
 
 
 class Stats(C.Structure):
@@ -188,11 +188,11 @@ class Engine:
 
     def __init__(self, mode="fast", fmt=FORMAT_FASTQ, paired=False, unordered=False, hamming_dist=2,
                  max_seq_len=150, max_records=1 << 20, max_chunk_bytes=64 << 20, max_chunk_records=0, device=0,
-                 max_tag_len=0):
+                 max_tag_len=0, byte_keys=0):
         self.lib = load_library()
         cfg = Config(FQD_ABI_VERSION, device, MODE_BY_NAME[mode] if isinstance(mode, str) else mode, fmt,
                      int(paired), int(unordered), hamming_dist, max_seq_len, max_records, max_chunk_bytes,
-                     max_chunk_records, max_tag_len, 0)
+                     max_chunk_records, max_tag_len, int(byte_keys))
         self.cfg = cfg
         self.h = C.c_void_p()
         rc = self.lib.fqd_create(C.byref(cfg), C.byref(self.h))
@@ -435,12 +435,12 @@ def dedup_fast(b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, chunk_bytes
 
 def dedup_whole(mode: str, b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, dist=2, unordered=False,
                 max_seq_len=150, append_bytes=1 << 22, seg_bytes=1 << 24, max_records=None, device=0, max_tag_len=0,
-                device_gather=True, emit_cap=1 << 16):
+                device_gather=True, emit_cap=1 << 16, byte_keys=0):
     """Sequence-based modes and --fast --unordered: whole input on the device, emission order out."""
     paired = b2 is not None
     if max_records is None:
         max_records = max(1024, max(b1.count(b"\n"), b2.count(b"\n") if paired else 0) // 2 + 16)
-    eng = Engine(mode, fmt, paired, unordered, dist, max_seq_len, max_records, seg_bytes, 0, device, max_tag_len)
+    eng = Engine(mode, fmt, paired, unordered, dist, max_seq_len, max_records, seg_bytes, 0, device, max_tag_len, byte_keys)
     try:
         for m, b in enumerate([b1, b2] if paired else [b1]):
             for o in range(0, len(b), append_bytes):

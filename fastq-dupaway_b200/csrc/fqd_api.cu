@@ -116,8 +116,8 @@ extern "C" int fqd_memcpy_h2d(int device, void* d_dst, const void* src, size_t b
     return cudaMemcpy(d_dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
 }
 
-static u32 words_for(u32 max_seq_len) {
-    u32 w = (max_seq_len + BASES_PER_WORD - 1) / BASES_PER_WORD;
+static u32 words_for(u32 max_seq_len, bool byte_keys = false) {
+    u32 w = byte_keys ? (max_seq_len + 1 + 7) / 8 : (max_seq_len + BASES_PER_WORD - 1) / BASES_PER_WORD;
     if (w < 2) w = 2;
     return (w + 1u) & ~1u;      // even, so rows are 16-byte aligned
 }
@@ -167,7 +167,9 @@ static int create_impl(const fqd_config* cfg, fqd_handle* h) {
     CUDA_TRY(h, cudaFuncSetAttribute(k_parse_pack<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 
     const int mates = cfg->paired ? 2 : 1;
-    h->W = words_for(cfg->max_seq_len ? cfg->max_seq_len : 150);
+    if (cfg->byte_keys && (cfg->mode == FQD_MODE_FAST || cfg->unordered))
+        return fail(h, FQD_ERR_INVALID, "byte_keys is for sequence-based modes (--fast accepts {A,C,G,T,N} only, src/seq_utils.cpp:3-21)");
+    h->W = words_for(cfg->max_seq_len ? cfg->max_seq_len : 150, cfg->byte_keys != 0);
     h->row_words = h->W * mates;
     if (cfg->max_chunk_bytes == 0 || cfg->max_chunk_bytes >= (1ull << 32) - (1ull << 20))
         return fail(h, FQD_ERR_INVALID, "max_chunk_bytes must be in (0, 4 GiB - 1 MiB)");
@@ -240,7 +242,7 @@ static int launch_parse(fqd_handle* h, int m, const u8* d_raw, size_t n, u8* d_d
     p.raw = d_raw; p.n = (u32)n; p.n_tiles = n_tiles; p.tile_state = c.d_tile_state; p.ctl = c.d_ctl; p.run = h->d_run;
     p.rec_start = c.d_rec_start; p.cap = h->cap; p.keys = h->d_keys; p.key_capacity = h->key_capacity;
     p.row_words = h->row_words; p.mate_off = m * h->W; p.W = h->W; p.hash = c.d_hash; p.seq_len = nullptr; p.word0 = nullptr;
-    p.strict = 1; p.hash_salt = m * 4096u; p.bad_rec = nullptr; p.dup = (m == 0) ? h->d_dup : nullptr;
+    p.strict = 1; p.hash_salt = m * 4096u; p.bad_rec = nullptr; p.dup = (m == 0) ? h->d_dup : nullptr; p.byte_keys = 0;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (h->profile) { pe0 = get_event(h); pe1 = get_event(h); cudaEventRecord(pe0, h->stream); }
     const u32 grid = n_tiles;      // one tile per CTA, processed in ticket order
@@ -528,7 +530,7 @@ extern "C" int fqd_shard_pack(fqd_handle* h, const void* d_raw, size_t n, uint32
     p.raw = (const u8*)d_raw; p.n = (u32)n; p.n_tiles = n_tiles; p.tile_state = c.d_tile_state; p.ctl = c.d_ctl; p.run = h->d_stage_run;
     p.rec_start = c.d_rec_start; p.cap = h->cap; p.keys = h->d_stage_keys; p.key_capacity = h->cap;
     p.row_words = h->row_words; p.mate_off = 0; p.W = h->W; p.hash = c.d_hash; p.seq_len = nullptr; p.word0 = nullptr;
-    p.strict = 1; p.hash_salt = 0; p.dup = nullptr; p.bad_rec = nullptr;
+    p.strict = 1; p.hash_salt = 0; p.dup = nullptr; p.bad_rec = nullptr; p.byte_keys = 0;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (h->profile) { pe0 = get_event(h); pe1 = get_event(h); cudaEventRecord(pe0, h->stream); }
     if (n_tiles) {

@@ -53,6 +53,8 @@ struct ParseParams {
                             // {A,C,G,T,N} of each record
     u32 strict;             // 1: bytes outside {A,C,G,T,N} are an error (fast mode, src/seq_utils.cpp:17-19)
     u32 hash_salt;          // distinguishes mates in the position keys
+    u32 byte_keys;          // 1: rows hold the raw bytes of sequence + '\n', 8 per word, first byte in the top bits
+                            //    (sequence-based modes on inputs with bytes outside {A,C,G,T,N}); 0: 3-bit codes, 20 per word
 };
 
 // ---- newline detection: 16 input bytes -> 16-bit mask of '\n' positions (bit j <-> byte j)
@@ -193,10 +195,11 @@ __device__ __forceinline__ u32 classify_record(const ParseParams& p, const u8* w
     if (c0 != lead) return RS_BAD_START | (c0 << 8);
     if (LPR == 4 && (e1 - e0) != (e3 - e2)) return RS_LEN_MISMATCH;
     const u32 nb = e1 - e0 - 1u;
-    if (nb > p.W * BASES_PER_WORD) return RS_TOO_LONG;
+    const u32 room = p.byte_keys ? p.W * 8u - 1u : p.W * BASES_PER_WORD;      // byte keys include the '\n'
+    if (nb > room) return RS_TOO_LONG;
     qoff = e0 + 1u;
     // fast path: every word of the row can be fetched from the staged window
-    const u32 fast = (qoff + p.W * BASES_PER_WORD + 4u <= PP_WINDOW) ? 0x80000000u : 0u;
+    const u32 fast = (qoff + room + 8u <= PP_WINDOW) ? 0x80000000u : 0u;
     qlen = nb | fast;
     return RS_OK;
 }
@@ -221,10 +224,40 @@ __device__ __forceinline__ void commit_record(const ParseParams& p, u64 slot_bas
 // sequence is built from the LAST 20 bases of the sequence and shifted, so that no byte beyond the sequence is ever
 // looked at (no masking of the validity check); only sequences shorter than 20 bases take the masked path.
 //   bad: 0, or 0x80000000 | position in the sequence << 8 | offending byte
+// byte keys: word w = bytes [8w, 8w + 8) of sequence + '\n' (the '\n' is the one in the file), zero padded.  Unsigned
+// word order is then the byte order FastqView::cmp defines for ANY byte (src/fastqview.cpp:56-67).
+__device__ __forceinline__ u64 pack_word_bytes(const u8* win, const ParseParams& p, u32 base, u32 off, u32 ql, u32 w) {
+    const u32 nb = (ql & 0x7FFFFFFFu) + 1u;           // symbols incl. the terminator
+    const u32 first = w * 8u;
+    if (nb <= first) return 0ull;
+    const u32 pos = off + first;
+    u32 x[3];
+    if (ql >> 31) {
+        const u32* w32 = reinterpret_cast<const u32*>(win) + (pos >> 2);
+        x[0] = w32[0]; x[1] = w32[1]; x[2] = w32[2];
+    } else {
+        u32 y[6];
+        fetch24_slow(win, p.raw, base, p.n, pos, y);
+        x[0] = y[0]; x[1] = y[1]; x[2] = y[2];
+    }
+    const u32 sel = 0x0123u + (pos & 3u) * 0x1111u;   // align + byte-reverse
+    const u32 hi = __byte_perm(x[0], x[1], sel), lo = __byte_perm(x[1], x[2], sel);
+    u64 word = ((u64)hi << 32) | lo;
+    const u32 valid = nb - first;
+    const u64 vmask = valid < 8u ? ~0ull << (8u * (8u - valid)) : ~0ull;
+    word &= vmask;
+    // a byte below the line feed (0x0A) breaks "a prefix sorts before its extensions": tell the host side, the loose
+    // scan then runs the reference's literal loop (no byte >= 0x80 is flagged: ~word clears those)
+    const u64 t = (word | 0x8080808080808080ull) - 0x0A0A0A0A0A0A0A0Aull;
+    if (~t & ~word & 0x8080808080808080ull & vmask) p.ctl->pad = 2;
+    return word;
+}
+
 __device__ __forceinline__ u64 pack_word(const u8* win, const ParseParams& p, u32 base, u32 off, u32 ql, u32 w, u32& bad) {
     const u32 nb = ql & 0x7FFFFFFFu;
     const u32 done = w * BASES_PER_WORD;
     bad = 0;
+    if (p.byte_keys) return pack_word_bytes(win, p, base, off, ql, w);
     if (nb <= done) return 0ull;
     u32 nvalid = min(nb - done, (u32)BASES_PER_WORD);
     u32 first = done, shift = 0;

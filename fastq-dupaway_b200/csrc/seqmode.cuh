@@ -40,20 +40,27 @@ __device__ __forceinline__ bool rows_equal_range(const u64* a, const u64* b, u32
     for (u32 w = w0; w < w1; ++w) diff |= a[w] ^ b[w];
     return diff == 0;
 }
-// first nb bases equal?
-__device__ __forceinline__ bool prefix_equal(const u64* a, const u64* b, u32 nb) {
-    const u32 full = nb / BASES_PER_WORD, rem = nb % BASES_PER_WORD;
+// Rows hold `bits` bits per symbol: 3 (codes of {A,C,G,T,N}, 20 per word) or 8 (raw bytes, 8 per word).
+// first nb symbols equal?
+__device__ __forceinline__ bool prefix_equal(const u64* a, const u64* b, u32 nb, u32 bits) {
+    const u32 per = bits == 8u ? 8u : (u32)BASES_PER_WORD;
+    const u32 full = nb / per, rem = nb % per;
     u64 diff = 0;
     for (u32 w = 0; w < full; ++w) diff |= a[w] ^ b[w];
-    if (rem) diff |= (a[full] ^ b[full]) & (~0ull << (3u * (BASES_PER_WORD - rem)));
+    if (rem) diff |= (a[full] ^ b[full]) & (~0ull << (bits * (per - rem)));
     return diff == 0;
 }
-// number of differing bases (SeqUtils::hammingDistance, src/seq_utils.cpp:65-72, on equal-length sequences)
-__device__ __forceinline__ u32 hamming_words(const u64* a, const u64* b, u32 W) {
+// number of differing symbols (SeqUtils::hammingDistance, src/seq_utils.cpp:65-72, on equal-length sequences)
+__device__ __forceinline__ u32 hamming_words(const u64* a, const u64* b, u32 W, u32 bits) {
     u32 d = 0;
     for (u32 w = 0; w < W; ++w) {
         u64 x = a[w] ^ b[w];
-        x = (x | (x >> 1) | (x >> 2)) & 0x0249249249249249ull;
+        if (bits == 8u) {
+            x |= x >> 4; x |= x >> 2; x |= x >> 1;
+            x &= 0x0101010101010101ull;
+        } else {
+            x = (x | (x >> 1) | (x >> 2)) & 0x0249249249249249ull;
+        }
         d += (u32)__popcll(x);
     }
     return d;
@@ -63,6 +70,7 @@ struct ScanParams {
     const u64* rows; u32 stride; u32 W; u32 mates;
     const u32* len0; const u32* len1;     // sequence lengths (bases) per record and mate
     const u32* perm; u64 n; u32 dist;
+    u32 bits;                             // bits per symbol of the key rows (3 or 8)
     u32* keep;                            // [n] in sorted order: 1 = written
     u32* brk;                             // hamming: definite cluster breaks
     u32* tail_head;                       // hamming: record that is the cluster head after the last sorted record
@@ -100,15 +108,39 @@ __global__ void k_scan_loose(const ScanParams p) {
             const u64* a = p.rows + (u64)c * p.stride;
             const u64* b = p.rows + (u64)h * p.stride;
             const u32 lc1 = p.len0[c], lh1 = p.len0[h];
-            bool dup = prefix_equal(a, b, min(lc1, lh1));
+            bool dup = prefix_equal(a, b, min(lc1, lh1), p.bits);
             if (dup && p.mates == 2) {
                 const u32 lc2 = p.len1[c], lh2 = p.len1[h];
-                dup = prefix_equal(a + p.W, b + p.W, min(lc2, lh2));
+                dup = prefix_equal(a + p.W, b + p.W, min(lc2, lh2), p.bits);
                 if (dup) dup = ((lh1 <= lc1) && (lh2 <= lc2)) || ((lh1 > lc1) && (lh2 > lc2));
             }
             k = dup ? 0u : 1u;
         }
         p.keep[i] = k;
+    }
+}
+// The literal loop of SeqDupRemover::impl_filterSE/PE with the LooseComparator (src/seq_dup_remover.hpp:78-101,173-208,
+// src/comparator.cpp:60-74), one thread.  Only used when a sequence holds a byte below the line feed: such a byte sorts
+// an extension BEFORE its prefix, and the head of a cluster is then no longer the previous record.
+__global__ void k_scan_loose_literal(const ScanParams p) {
+    if (p.n == 0) return;
+    u32 h = p.perm[0];
+    p.keep[0] = 1;
+    for (u64 i = 1; i < p.n; ++i) {
+        const u32 c = p.perm[i];
+        const u64* a = p.rows + (u64)c * p.stride;
+        const u64* b = p.rows + (u64)h * p.stride;
+        const u32 lc1 = p.len0[c], lh1 = p.len0[h];
+        u32 lc2 = 0, lh2 = 0;
+        bool dup = prefix_equal(a, b, min(lc1, lh1), p.bits);
+        if (dup && p.mates == 2) {
+            lc2 = p.len1[c]; lh2 = p.len1[h];
+            dup = prefix_equal(a + p.W, b + p.W, min(lc2, lh2), p.bits);
+            if (dup) dup = ((lh1 <= lc1) && (lh2 <= lc2)) || ((lh1 > lc1) && (lh2 > lc2));
+        }
+        p.keep[i] = dup ? 0u : 1u;
+        if (!dup) h = c;
+        else if (lh1 <= lc1 && (p.mates == 1 || lh2 <= lc2)) h = c;      // keep the longest as the reference
     }
 }
 // HammingComparator (src/comparator.cpp:76-91) compares against the cluster HEAD, a sequential greedy scan.
@@ -122,8 +154,8 @@ __global__ void k_ham_breaks(const ScanParams p) {
             const u32 c = p.perm[i], h = p.perm[i - 1];
             const u64* a = p.rows + (u64)c * p.stride;
             const u64* q = p.rows + (u64)h * p.stride;
-            bool same = p.len0[c] == p.len0[h] && hamming_words(a, q, p.W) <= 2u * p.dist;
-            if (same && p.mates == 2) same = p.len1[c] == p.len1[h] && hamming_words(a + p.W, q + p.W, p.W) <= 2u * p.dist;
+            bool same = p.len0[c] == p.len0[h] && hamming_words(a, q, p.W, p.bits) <= 2u * p.dist;
+            if (same && p.mates == 2) same = p.len1[c] == p.len1[h] && hamming_words(a + p.W, q + p.W, p.W, p.bits) <= 2u * p.dist;
             b = same ? 0u : 1u;
         }
         p.brk[i] = b;
@@ -141,8 +173,8 @@ __global__ void k_ham_segments(const ScanParams p) {
             const u64* a = p.rows + (u64)c * p.stride;
             const u64* q = p.rows + (u64)head * p.stride;
             // lengths are equal inside a segment (a length change is a break)
-            bool dup = hamming_words(a, q, p.W) <= p.dist;
-            if (dup && p.mates == 2) dup = hamming_words(a + p.W, q + p.W, p.W) <= p.dist;
+            bool dup = hamming_words(a, q, p.W, p.bits) <= p.dist;
+            if (dup && p.mates == 2) dup = hamming_words(a + p.W, q + p.W, p.W, p.bits) <= p.dist;
             p.keep[j] = dup ? 0u : 1u;
             if (!dup) head = c;
         }
@@ -161,10 +193,10 @@ __global__ void k_fix_first_loose(const ScanParams p, const u64* prev) {
     const u64* a = p.rows + (u64)c * p.stride;
     const u64 pl = prev[p.stride];
     const u32 lc1 = p.len0[c], lh1 = (u32)pl;
-    bool dup = prefix_equal(a, prev, min(lc1, lh1));
+    bool dup = prefix_equal(a, prev, min(lc1, lh1), p.bits);
     if (dup && p.mates == 2) {
         const u32 lc2 = p.len1[c], lh2 = (u32)(pl >> 32);
-        dup = prefix_equal(a + p.W, prev + p.W, min(lc2, lh2));
+        dup = prefix_equal(a + p.W, prev + p.W, min(lc2, lh2), p.bits);
         if (dup) dup = ((lh1 <= lc1) && (lh2 <= lc2)) || ((lh1 > lc1) && (lh2 > lc2));
     }
     p.keep[0] = dup ? 0u : 1u;
@@ -176,8 +208,8 @@ __global__ void k_fix_first_ham(const ScanParams p, const u64* prev) {
     const u32 c0 = p.perm[0];
     const u64* a0 = p.rows + (u64)c0 * p.stride;
     const u64 pl = prev[p.stride];
-    bool same = p.len0[c0] == (u32)pl && hamming_words(a0, prev, p.W) <= 2u * p.dist;
-    if (same && p.mates == 2) same = p.len1[c0] == (u32)(pl >> 32) && hamming_words(a0 + p.W, prev + p.W, p.W) <= 2u * p.dist;
+    bool same = p.len0[c0] == (u32)pl && hamming_words(a0, prev, p.W, p.bits) <= 2u * p.dist;
+    if (same && p.mates == 2) same = p.len1[c0] == (u32)(pl >> 32) && hamming_words(a0 + p.W, prev + p.W, p.W, p.bits) <= 2u * p.dist;
     if (!same) { p.brk[0] = 1; return; }
     p.brk[0] = 0;
     const u64* hq = prev + p.stride + 1;          // head of the previous range's last cluster
@@ -186,8 +218,8 @@ __global__ void k_fix_first_ham(const ScanParams p, const u64* prev) {
     for (; j < p.n && (j == 0 || !p.brk[j]); ++j) {
         const u32 c = p.perm[j];
         const u64* a = p.rows + (u64)c * p.stride;
-        bool dup = hamming_words(a, hq, p.W) <= p.dist;
-        if (dup && p.mates == 2) dup = hamming_words(a + p.W, hq + p.W, p.W) <= p.dist;
+        bool dup = hamming_words(a, hq, p.W, p.bits) <= p.dist;
+        if (dup && p.mates == 2) dup = hamming_words(a + p.W, hq + p.W, p.W, p.bits) <= p.dist;
         p.keep[j] = dup ? 0u : 1u;
         if (!dup) { head = c; hq = a; }
     }
@@ -504,6 +536,7 @@ struct SeqState {
     u32 part_G = 0; u64 part_n = 0;
     u32* d_cl_len[2] = {nullptr, nullptr};     // --write-clusters: line length per sorted position
     u64 cl_cursor[2] = {0, 0};
+    bool low_bytes = false;          // byte keys: a sequence holds a byte below '\n' (see k_scan_loose_literal)
     bool lists_on_host = false;      // h_off / h_len filled (only fqd_emission needs them)
     u32* h_lenwin = nullptr;         // pinned window of record lengths for fqd_emit's batch cuts
     std::vector<void*> scratch;      // freed at destroy / reset
@@ -604,7 +637,7 @@ static int seq_reset(SeqState* s, std::string* err) {
         if (s->mate[m].d_bad) SEQ_TRY(cudaMemsetAsync(s->mate[m].d_bad, 0xFF, s->capacity * sizeof(u32), s->stream));
     }
     s->n = s->n_out = 0; s->finished = false; s->ms = 0;
-    s->parsed = s->scanned = s->has_prev = false;
+    s->parsed = s->scanned = s->has_prev = false; s->low_bytes = false;
     s->d_cl_len[0] = s->d_cl_len[1] = nullptr; s->cl_cursor[0] = s->cl_cursor[1] = 0;
     s->d_perm = s->d_keep = s->d_brk = s->d_tail_head = nullptr; s->d_bound_prev = s->d_bound_out = nullptr;
     s->d_part_perm = nullptr; s->d_part_starts = nullptr; s->d_part_off[0] = s->d_part_off[1] = nullptr; s->part_G = 0; s->part_n = 0;
@@ -648,6 +681,7 @@ static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
     p.rec_start = s->d_rec_start; p.cap = (u32)std::min<u64>(s->chunk_cap, room); p.keys = s->d_keys; p.key_capacity = s->capacity;
     p.row_words = s->row_words; p.mate_off = m * s->W; p.W = s->W; p.hash = s->d_hash; p.seq_len = mt.d_seq_len + mt.n_records;
     p.word0 = nullptr; p.dup = nullptr; p.strict = 0; p.hash_salt = m * 4096u; p.bad_rec = nullptr;
+    p.byte_keys = s->cfg.byte_keys ? 1u : 0u;
     if (s->cfg.unordered) { p.hash = mt.d_hash + mt.n_records; p.bad_rec = mt.d_bad + mt.n_records; }
     if (s->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<n_tiles, PP_THREADS, 0, s->stream>>>(p);
     else k_parse_pack<2><<<n_tiles, PP_THREADS, 0, s->stream>>>(p);
@@ -672,7 +706,8 @@ static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
     if (c.too_long == 1) seq_set_error(s, FQD_ERR_SEQ_TOO_LONG, 0, first, m);
     if (c.too_long == 2) seq_set_error(s, FQD_ERR_CAPACITY, 0, first, m);
     if (c.too_long == 3) seq_set_error(s, FQD_ERR_TAG_TOO_LONG, 0, first, m);
-    if (c.pad && !s->cfg.unordered) seq_set_error(s, FQD_ERR_UNSUPPORTED_BYTE, 0, first, m);
+    if (c.pad == 2 && s->cfg.byte_keys) s->low_bytes = true;
+    else if (c.pad && !s->cfg.unordered) seq_set_error(s, FQD_ERR_UNSUPPORTED_BYTE, 0, first, m);
     mt.n_records += c.n_records;
     const size_t consumed = c.consumed, tail = sg.fill - consumed;
     if (c.n_records == 0 && !final && sg.fill >= sg.cap) {
@@ -876,6 +911,7 @@ static ScanParams seq_scan_params(SeqState* s) {
     sp.rows = s->d_keys; sp.stride = s->row_words; sp.W = s->W; sp.mates = s->mates;
     sp.len0 = s->mate[0].d_seq_len; sp.len1 = s->mates == 2 ? s->mate[1].d_seq_len : nullptr;
     sp.perm = s->d_perm; sp.n = s->n; sp.dist = s->cfg.hamming_dist; sp.keep = s->d_keep; sp.brk = s->d_brk;
+    sp.bits = s->cfg.byte_keys ? 8u : 3u;
     sp.tail_head = s->d_tail_head;
     return sp;
 }
@@ -886,7 +922,7 @@ static int seq_scan_stage(SeqState* s, std::string* err) {
     int rc;
     SeqTrace tr;
     if ((rc = seq_dalloc(s, &s->d_perm, n, err))) return rc;
-    if ((rc = sort_rows(s, s->d_keys, s->row_words, 0, s->row_words, 60, n, s->d_perm, err))) return rc;
+    if ((rc = sort_rows(s, s->d_keys, s->row_words, 0, s->row_words, s->cfg.byte_keys ? 64 : 60, n, s->d_perm, err))) return rc;
     tr.mark(s->stream, "sort_rows");
     if ((rc = seq_dalloc(s, &s->d_keep, n, err)) || (rc = seq_dalloc(s, &s->d_tail_head, 1, err)) ||
         (rc = seq_dalloc(s, &s->d_bound_prev, boundary_words(s->row_words), err)) ||
@@ -895,6 +931,7 @@ static int seq_scan_stage(SeqState* s, std::string* err) {
     if (s->cfg.mode == FQD_MODE_SEQ_HAMMING && (rc = seq_dalloc(s, &s->d_brk, n, err))) return rc;
     const ScanParams sp = seq_scan_params(s);
     if (s->cfg.mode == FQD_MODE_SEQ_TIGHT) k_scan_tight<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
+    else if (s->cfg.mode == FQD_MODE_SEQ_LOOSE && s->low_bytes) k_scan_loose_literal<<<1, 1, 0, s->stream>>>(sp);
     else if (s->cfg.mode == FQD_MODE_SEQ_LOOSE) k_scan_loose<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
     else {
         k_ham_breaks<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
@@ -910,6 +947,10 @@ static int seq_scan_stage(SeqState* s, std::string* err) {
 // The boundary state after this input's last sorted record (host buffer of boundary_words(row_words) words).
 static int seq_boundary_get(SeqState* s, u64* out, std::string* err) {
     if (!s->scanned) { *err = "boundary state before the scan stage"; return FQD_ERR_INVALID; }
+    if (s->low_bytes && s->cfg.mode == FQD_MODE_SEQ_LOOSE) {
+        *err = "loose mode on sequences with bytes below the line feed cannot be split into key ranges";
+        return FQD_ERR_INVALID;
+    }
     const ScanParams sp = seq_scan_params(s);
     k_tail_state<<<1, 64, 0, s->stream>>>(sp, s->d_bound_prev, s->cfg.mode == FQD_MODE_SEQ_HAMMING ? 1 : 0, s->d_bound_out);
     s->launches++;

@@ -294,6 +294,7 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
     block = std::min<size_t>(std::max<size_t>(block, 4u << 20), 256u << 20) & ~(size_t)4095;
     double growth = 1.0;
     unsigned seq_growth = 0, tag_growth = 0;
+    bool byte_keys = false;         // sequence-based modes order ANY byte (src/fastqview.cpp:56-67): raw-byte key rows
 
     for (int attempt = 0; attempt < 10; ++attempt) {
         std::vector<std::unique_ptr<BlockReader>> readers;
@@ -320,6 +321,7 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
         cfg.max_records = (uint64_t)((double)est_records * growth);
         cfg.max_chunk_bytes = 1ull << 30;              // device segments of 1 GiB
         cfg.max_tag_len = 32u << tag_growth;
+        cfg.byte_keys = byte_keys ? 1u : 0u;
         fqd_handle* hraw = nullptr;
         int rc = fqd_create(&cfg, &hraw);
         if (rc) throw_engine_error(nullptr, rc);
@@ -342,8 +344,7 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
         if (st.err == FQD_ERR_SEQ_TOO_LONG) { ++seq_growth; continue; }
         if (st.err == FQD_ERR_CAPACITY) { growth *= 2.0; continue; }
         if (st.err == FQD_ERR_TAG_TOO_LONG) { ++tag_growth; continue; }
-        if (st.err == FQD_ERR_UNSUPPORTED_BYTE)
-            throw std::runtime_error("sequence-based mode of the B200 build supports the alphabet {A, C, G, T, N} only");
+        if (st.err == FQD_ERR_UNSUPPORTED_BYTE && !byte_keys) { byte_keys = true; continue; }
         // parse errors surface while the inputs are being sorted, before any output file exists
         // (src/seq_dup_remover.hpp:44-50, src/hash_dup_remover.hpp:160-174)
         if (st.err && st.err != FQD_ERR_BAD_BASE) throw_data_error(st, fasta);

@@ -49,10 +49,29 @@ class GpuShardOps:
         return int(d.value)
 
 
+TRACE = {}
+
+
+def _mark(name, t0):
+    """FQD_TRACE=1: wall-clock per phase of exchange_chunk (each mark synchronises the device)."""
+    import os
+    import time
+    import torch
+    if not os.environ.get("FQD_TRACE"):
+        return t0
+    torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    TRACE[name] = TRACE.get(name, 0.0) + (t1 - t0) * 1e3
+    return t1
+
+
 def exchange_chunk(ops, dist, world, raw_ptr, nbytes, via_cpu=False):
     """One chunk through pack -> all-to-all -> insert -> all-to-all -> apply.  Returns this rank's duplicate count."""
+    import time
     import torch
+    t = time.perf_counter()
     send_rows, counts = ops.pack(raw_ptr, nbytes)
+    t = _mark("pack (K1 + owner sort + row gather)", t)
     dev = send_rows.device
     row_bytes = int(send_rows.shape[1])
     # how many rows will every peer send me?
@@ -62,6 +81,7 @@ def exchange_chunk(ops, dist, world, raw_ptr, nbytes, via_cpu=False):
     dist.all_to_all_single(c_in, c_out)
     recv_counts = [int(x) for x in c_in.tolist()]
     n_recv = sum(recv_counts)
+    t = _mark("counts all-to-all", t)
     # rows: one all-to-all
     s = send_rows.reshape(-1)
     if via_cpu:
@@ -72,7 +92,9 @@ def exchange_chunk(ops, dist, world, raw_ptr, nbytes, via_cpu=False):
     else:
         recv = torch.empty(n_recv * row_bytes, dtype=torch.uint8, device=dev)
         dist.all_to_all_single(recv, s, [c * row_bytes for c in recv_counts], [c * row_bytes for c in counts])
+    t = _mark("rows all-to-all", t)
     flags = ops.insert(recv.reshape(n_recv, row_bytes))
+    t = _mark("insert (append + K2)", t)
     # flags back: one byte per row, reverse direction
     if via_cpu:
         f_h = flags.cpu()
@@ -82,4 +104,7 @@ def exchange_chunk(ops, dist, world, raw_ptr, nbytes, via_cpu=False):
     else:
         back = torch.empty(sum(counts), dtype=torch.uint8, device=dev)
         dist.all_to_all_single(back, flags, counts, recv_counts)
-    return ops.apply(back), sum(counts)
+    t = _mark("flags all-to-all", t)
+    r = ops.apply(back), sum(counts)
+    _mark("apply", t)
+    return r

@@ -64,7 +64,9 @@ typedef struct {
     uint64_t max_chunk_bytes;   /* largest buffer ever passed to one fqd_push* call (per mate), < 4 GiB  */
     uint64_t max_chunk_records; /* records per chunk the per-chunk tables hold; 0 = max_chunk_bytes/64   */
     uint32_t max_tag_len;       /* --unordered: longest ID tag in bytes the tag keys must hold; 0 = 32    */
-    uint32_t reserved;
+    uint32_t byte_keys;         /* sequence-based modes: 1 = key rows hold the raw bytes of sequence + '\n' (8 bits per
+                                   symbol, any byte is legal, src/fastqview.cpp:56-67 orders arbitrary bytes) instead of
+                                   3-bit codes of {A,C,G,T,N}; the host sets it after FQD_ERR_UNSUPPORTED_BYTE         */
 } fqd_config;
 
 typedef struct {

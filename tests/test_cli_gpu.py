@@ -189,3 +189,16 @@ def test_write_clusters_through_files(tmp_path, oracle, mode):
     assert (tmp_path / "o1.fq").read_bytes() == e1 and (tmp_path / "o2.fq").read_bytes() == e2
     assert (tmp_path / "o1.fq.clusters").read_bytes() == texts[0]
     assert (tmp_path / "o2.fq.clusters").read_bytes() == texts[1]
+
+
+@pytest.mark.gpu
+def test_arbitrary_bytes_through_files(tmp_path, oracle):
+    """Lower case / IUPAC symbols in sequence-based mode: accepted and ordered like the reference does (any byte)."""
+    seqs = synth.make_reads(20000, seed=95, read_len=80, var_len=True, prefix_frac=0.2, sub_frac=0.2, dup_frac=0.4, alphabet=b"ACGTNacgtnRYKM")
+    buf = synth.to_fastq(seqs)
+    (tmp_path / "in.fq").write_bytes(buf)
+    res = run("-i", tmp_path / "in.fq", "-o", tmp_path / "out.fq", "--compare-seq", "tail-hamming", "-v")
+    assert res.returncode == 0, res.stderr
+    exp, _, est = oracle.run_oracle("tail-hamming", oracle.FASTQ, buf)
+    assert (tmp_path / "out.fq").read_bytes() == exp
+    assert res.stdout == f"{est.total} reads processed, out of which {est.dups} duplicates were removed.\n"

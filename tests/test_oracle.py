@@ -142,6 +142,25 @@ def test_ref_stable_seq_modes(oracle, tmp_path, mode, dist, paired):
 
 @pytest.mark.parametrize("mode,dist", [("tight", 2), ("loose", 2), ("tail-hamming", 2)])
 @pytest.mark.parametrize("paired", [False, True])
+def test_ref_stable_arbitrary_bytes(oracle, tmp_path, mode, dist, paired):
+    """Sequence-based modes accept and order ANY byte (src/fastqview.cpp:56-67): lower case, IUPAC codes,
+    gaps, a tab (sorts below the line feed).  Full bytes against the stable-sort build of the reference."""
+    _need_ref(oracle, stable=True)
+    kw = dict(read_len=30, var_len=True, min_len=1, prefix_frac=0.3, sub_frac=0.3, dup_frac=0.5, alphabet=b"ACGTNacgtnRYKM*-.\t")
+    if paired:
+        s1, s2 = synth.make_pair(1200, seed=31, **kw)
+        b1, b2 = synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2)
+    else:
+        b1, b2 = synth.to_fastq(synth.make_reads(1500, seed=32, **kw)), None
+    rc, r1, r2, so, se = oracle.run_ref(tmp_path, mode, oracle.FASTQ, b1, b2, dist=dist, stable=True, mem_mb=10240)
+    o1, o2, st = oracle.run_oracle(mode, oracle.FASTQ, b1, b2, dist=dist)
+    assert rc == 0, se
+    assert o1 == r1 and o2 == r2
+    assert _parse_counts(so)[:2] == [st.total, st.dups]
+
+
+@pytest.mark.parametrize("mode,dist", [("tight", 2), ("loose", 2), ("tail-hamming", 2)])
+@pytest.mark.parametrize("paired", [False, True])
 def test_ref_stable_cluster_files(oracle, tmp_path, mode, dist, paired):
     """--write-clusters: the oracle's cluster text against the files the stable-sort build of the reference writes."""
     _need_ref(oracle, stable=True)

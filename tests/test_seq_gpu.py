@@ -127,3 +127,29 @@ def test_cluster_files(fqd, oracle, mode, dist, paired):
             assert eng.emit_clusters_all(m, cap=3000) == texts[m]
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("mode,dist", [("tight", 2), ("loose", 2), ("tail-hamming", 1), ("tail-hamming", 3)])
+@pytest.mark.parametrize("paired", [False, True])
+def test_arbitrary_bytes_with_byte_keys(fqd, oracle, mode, dist, paired):
+    """Any byte is a legal sequence symbol in sequence-based modes (src/fastqview.cpp:56-67): with 3-bit rows the engine
+    reports FQD_ERR_UNSUPPORTED_BYTE (the host then restarts with cfg.byte_keys), with byte rows it matches the oracle."""
+    kw = dict(read_len=45, var_len=True, min_len=0, prefix_frac=0.3, sub_frac=0.3, dup_frac=0.5, alphabet=b"ACGTNacgtnRYKM*-.\t")
+    if paired:
+        s1, s2 = synth.make_pair(4000, seed=91, **kw)
+        b1, b2 = synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2)
+    else:
+        b1, b2 = synth.to_fastq(synth.make_reads(6000, seed=92, **kw)), None
+    _, _, st = fqd.dedup_whole(mode, b1, b2, fqd.FORMAT_FASTQ, dist=dist, max_seq_len=45, seg_bytes=1 << 17)
+    assert st.err == 9        # FQD_ERR_UNSUPPORTED_BYTE
+    _check(fqd, oracle, mode, b1, b2, fqd.FORMAT_FASTQ, dist=dist, max_seq_len=45, seg_bytes=1 << 17, append_bytes=60_000, byte_keys=1)
+
+
+def test_byte_keys_on_plain_bases_match_code_keys(fqd, oracle):
+    """Same input, both row formats: identical output (the order of {\\n,A,C,G,N,T} is the byte order)."""
+    seqs = synth.make_reads(5000, seed=93, read_len=70, var_len=True, n_frac=0.1, prefix_frac=0.3, sub_frac=0.3, dup_frac=0.5)
+    buf = synth.to_fastq(seqs)
+    for mode in ("tight", "loose", "tail-hamming"):
+        a, _, sa = fqd.dedup_whole(mode, buf, None, fqd.FORMAT_FASTQ, max_seq_len=70, byte_keys=0)
+        b, _, sb = fqd.dedup_whole(mode, buf, None, fqd.FORMAT_FASTQ, max_seq_len=70, byte_keys=1)
+        assert a == b and (sa.total, sa.dups) == (sb.total, sb.dups)
