@@ -115,6 +115,8 @@ def dedup_ranges(ops, dist, rank, world, n_samples=4096, tensor_device=None, via
     # 3. plan
     counts, nbytes = ops.plan(splitters, world)
     mates = len(nbytes)
+    if sum(counts) != n_local:
+        raise RuntimeError(f"rank {rank}: partition plan covers {sum(counts)} of {n_local} records")
     # 4. exchange
     c_out = torch.tensor([counts] + nbytes, dtype=torch.int64, device=dev).reshape(-1)
     c_in = torch.empty_like(c_out)

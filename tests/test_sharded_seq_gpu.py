@@ -37,7 +37,11 @@ def _worker(rank, world, port, mode, dval, fmt_name, slices, result_dir):
             ops.append(m, d.ptr, len(b))
             torch.cuda.synchronize()
             d.free()
+    n_local_expected = mine[0].count(b"\n") // (4 if fmt_name == "fastq" else 2)
+    st0 = None
     owned, kept, dups = sh.dedup_ranges(ops, dist, rank, world, n_samples=256, via_cpu=True)
+    st0 = ops.origin.stats()
+    assert ops.origin.partition_sample(1)[1] == n_local_expected, (rank, ops.origin.partition_sample(1)[1], n_local_expected, st0.err)
     for m in range(len(mine)):
         (Path(result_dir) / f"out_{rank}_{m}.bin").write_bytes(ops.output(m) if owned else b"")
     (Path(result_dir) / f"cnt_{rank}.txt").write_text(f"{owned} {kept} {dups}")
