@@ -123,6 +123,7 @@ def load_library():
     lib.fqd_shard_row_bytes.argtypes = [vp]
     lib.fqd_shard_row_bytes.restype = sz
     lib.fqd_shard_pack.argtypes = [vp, vp, sz, C.c_uint32, vp, C.POINTER(u64), C.POINTER(u64)]
+    lib.fqd_shard_pack_pe.argtypes = [vp, vp, sz, vp, sz, C.c_uint32, vp, C.POINTER(u64), C.POINTER(u64)]
     lib.fqd_shard_insert.argtypes = [vp, vp, u64, C.c_uint32, vp]
     lib.fqd_shard_apply.argtypes = [vp, vp, C.POINTER(u64)]
     lib.fqd_shard_read_flags.argtypes = [vp, vp, sz]

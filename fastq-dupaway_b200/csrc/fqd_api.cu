@@ -499,7 +499,7 @@ extern "C" size_t fqd_shard_row_bytes(fqd_handle* h) { return h ? ((size_t)h->ro
 
 static int shard_init(fqd_handle* h) {
     if (h->shard_ctx) return FQD_OK;
-    if (h->cfg.mode != FQD_MODE_FAST || h->cfg.unordered || h->cfg.paired) return fail(h, FQD_ERR_INVALID, "sharded path: single-end --fast only");
+    if (h->cfg.mode != FQD_MODE_FAST || h->cfg.unordered) return fail(h, FQD_ERR_INVALID, "sharded path: ordered --fast only");
     h->shard_ctx = new SeqState();
     h->shard_ctx->stream = h->stream; h->shard_ctx->sm = h->sm_count;
     int rc = sort_scratch_alloc(h->shard_ctx, h->shard_sc, h->cap, &h->err);
@@ -517,34 +517,47 @@ static int shard_init(fqd_handle* h) {
     return FQD_OK;
 }
 
-extern "C" int fqd_shard_pack(fqd_handle* h, const void* d_raw, size_t n, uint32_t n_shards, void* d_send, uint64_t* counts, uint64_t* n_records) {
+// single-end: d_raw2 == nullptr.  paired-end: both chunks must hold the same records (cut at the same record index).
+static int shard_pack_impl(fqd_handle* h, const void* d_raw, size_t n, const void* d_raw2, size_t n2, uint32_t n_shards, void* d_send,
+                           uint64_t* counts, uint64_t* n_records) {
     if (!h || !counts || n_shards == 0 || n_shards > 32) return FQD_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = shard_init(h);
     if (rc) return rc;
-    if (n > h->cfg.max_chunk_bytes) return fail(h, FQD_ERR_INVALID, "chunk larger than max_chunk_bytes");
-    MateChunk& c = h->mate[0];
-    const u32 n_tiles = (u32)((n + PP_TILE - 1) / PP_TILE);
-    k_init_chunk<<<std::max(1u, std::min(n_tiles / 256 + 1, 1024u)), 256, 0, h->stream>>>(c.d_ctl, c.d_tile_state, n_tiles);
-    ParseParams p;
-    p.raw = (const u8*)d_raw; p.n = (u32)n; p.n_tiles = n_tiles; p.tile_state = c.d_tile_state; p.ctl = c.d_ctl; p.run = h->d_stage_run;
-    p.rec_start = c.d_rec_start; p.cap = h->cap; p.keys = h->d_stage_keys; p.key_capacity = h->cap;
-    p.row_words = h->row_words; p.mate_off = 0; p.W = h->W; p.hash = c.d_hash; p.seq_len = nullptr; p.word0 = nullptr;
-    p.strict = 1; p.hash_salt = 0; p.dup = nullptr; p.bad_rec = nullptr; p.byte_keys = 0;
+    const int mates = h->cfg.paired ? 2 : 1;
+    if ((mates == 2) != (d_raw2 != nullptr)) return fail(h, FQD_ERR_INVALID, "paired handle needs both chunks, single-end handle one");
+    if (n > h->cfg.max_chunk_bytes || n2 > h->cfg.max_chunk_bytes) return fail(h, FQD_ERR_INVALID, "chunk larger than max_chunk_bytes");
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (h->profile) { pe0 = get_event(h); pe1 = get_event(h); cudaEventRecord(pe0, h->stream); }
-    if (n_tiles) {
-        if (h->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
-        else k_parse_pack<2><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
+    for (int m = 0; m < mates; ++m) {
+        MateChunk& c = h->mate[m];
+        const u8* raw = (const u8*)(m ? d_raw2 : d_raw);
+        const size_t nb = m ? n2 : n;
+        const u32 n_tiles = (u32)((nb + PP_TILE - 1) / PP_TILE);
+        k_init_chunk<<<std::max(1u, std::min(n_tiles / 256 + 1, 1024u)), 256, 0, h->stream>>>(c.d_ctl, c.d_tile_state, n_tiles);
+        ParseParams p;
+        p.raw = raw; p.n = (u32)nb; p.n_tiles = n_tiles; p.tile_state = c.d_tile_state; p.ctl = c.d_ctl; p.run = h->d_stage_run;
+        p.rec_start = c.d_rec_start; p.cap = h->cap; p.keys = h->d_stage_keys; p.key_capacity = h->cap;
+        p.row_words = h->row_words; p.mate_off = m * h->W; p.W = h->W; p.hash = c.d_hash; p.seq_len = nullptr; p.word0 = nullptr;
+        p.strict = 1; p.hash_salt = m * 4096u; p.dup = nullptr; p.bad_rec = nullptr; p.byte_keys = 0;
+        if (n_tiles) {
+            if (h->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
+            else k_parse_pack<2><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
+        }
+        if (h->profile) { h->prof.parse_launches++; h->prof.parse_bytes += nb; }
     }
-    if (h->profile) { cudaEventRecord(pe1, h->stream); h->prof_parse.emplace_back(pe0, pe1); h->prof.parse_launches++; h->prof.parse_bytes += n; }
+    if (h->profile) { cudaEventRecord(pe1, h->stream); h->prof_parse.emplace_back(pe0, pe1); }
     // owner of every key, one stable radix pass groups the records by owner
+    MateChunk& c = h->mate[0];
     SortScratch& sc = h->shard_sc;
     const unsigned g = (unsigned)h->sm_count * 8;
-    k_shard_owner<<<g, 256, 0, h->stream>>>(c.d_hash, c.d_ctl, n_shards, sc.keyA, h->d_final_hash, sc.aA);
-    CUDA_TRY(h, cudaMemcpyAsync(c.h_ctl, c.d_ctl, sizeof(ChunkCtl), cudaMemcpyDeviceToHost, h->stream));
+    k_shard_owner<<<g, 256, 0, h->stream>>>(c.d_hash, mates == 2 ? h->mate[1].d_hash : nullptr, c.d_ctl, n_shards, sc.keyA, h->d_final_hash, sc.aA);
+    for (int m = 0; m < mates; ++m)
+        CUDA_TRY(h, cudaMemcpyAsync(h->mate[m].h_ctl, h->mate[m].d_ctl, sizeof(ChunkCtl), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     const u64 nrec = c.h_ctl->n_records;
+    if (mates == 2 && h->mate[1].h_ctl->n_records != nrec)
+        return fail(h, FQD_ERR_INVALID, "sharded paired input: the two chunks hold different numbers of records");
     h->shard_ctx->stream = h->stream;
     rc = radix_sort(h->shard_ctx, sc, nrec, 0, 8, false, &h->err);
     if (rc) return rc;
@@ -556,12 +569,20 @@ extern "C" int fqd_shard_pack(fqd_handle* h, const void* d_raw, size_t n, uint32
     for (u32 k = 0; k < n_shards; ++k) counts[k] = hc[k + 1] - hc[k];
     if (n_records) *n_records = nrec;
     h->shard_last_n = nrec;
-    h->launches += 5 + h->shard_ctx->launches; h->shard_ctx->launches = 0;
+    h->launches += 3 + 2 * mates + h->shard_ctx->launches; h->shard_ctx->launches = 0;
     u64 n_ok;
     h->h_run->chunk_pairs = (u32)nrec; h->h_run->capacity_exceeded = 0;
     fold_chunk(h, h->stats.total, &n_ok);
     CUDA_TRY(h, cudaGetLastError());
     return FQD_OK;
+}
+extern "C" int fqd_shard_pack(fqd_handle* h, const void* d_raw, size_t n, uint32_t n_shards, void* d_send, uint64_t* counts, uint64_t* n_records) {
+    return shard_pack_impl(h, d_raw, n, nullptr, 0, n_shards, d_send, counts, n_records);
+}
+extern "C" int fqd_shard_pack_pe(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2, uint32_t n_shards, void* d_send,
+                                 uint64_t* counts, uint64_t* n_records) {
+    if (!d_r2) return fail(h, FQD_ERR_INVALID, "fqd_shard_pack_pe needs both mates");
+    return shard_pack_impl(h, d_r1, n1, d_r2, n2, n_shards, d_send, counts, n_records);
 }
 
 extern "C" int fqd_shard_insert(fqd_handle* h, const void* d_recv, uint64_t n_recv, uint32_t n_shards, void* d_flags) {

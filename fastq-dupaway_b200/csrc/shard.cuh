@@ -12,12 +12,12 @@
 namespace fqd {
 
 // owner of every record of the chunk + finalised hash
-__global__ void k_shard_owner(const u64* __restrict__ raw_hash, const ChunkCtl* ctl, u32 n_shards, u64* __restrict__ owner_key,
-                              u64* __restrict__ final_hash, u32* __restrict__ idx) {
+__global__ void k_shard_owner(const u64* __restrict__ raw_hash, const u64* __restrict__ raw_hash2, const ChunkCtl* ctl, u32 n_shards,
+                              u64* __restrict__ owner_key, u64* __restrict__ final_hash, u32* __restrict__ idx) {
     const u32 n = ctl->n_records;
     u64 step = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-        const u64 h = mix64(raw_hash[i]);
+        const u64 h = raw_hash2 ? pair_hash(raw_hash[i], raw_hash2[i]) : mix64(raw_hash[i]);     // pair key = both mates
         final_hash[i] = h;
         owner_key[i] = __umul64hi(h, (u64)n_shards);
         idx[i] = (u32)i;

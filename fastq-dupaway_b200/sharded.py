@@ -29,10 +29,14 @@ class GpuShardOps:
         rc = self.lib.fqd_set_stream(engine.h, C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream))
         assert rc == 0
 
-    def pack(self, raw_ptr, nbytes):
+    def pack(self, raw_ptr, nbytes, raw2_ptr=None, nbytes2=0):
         counts = (C.c_uint64 * self.world)()
         nrec = C.c_uint64(0)
-        rc = self.lib.fqd_shard_pack(self.eng.h, C.c_void_p(raw_ptr), nbytes, self.world, C.c_void_p(self.send.data_ptr()), counts, C.byref(nrec))
+        if raw2_ptr is None:
+            rc = self.lib.fqd_shard_pack(self.eng.h, C.c_void_p(raw_ptr), nbytes, self.world, C.c_void_p(self.send.data_ptr()), counts, C.byref(nrec))
+        else:
+            rc = self.lib.fqd_shard_pack_pe(self.eng.h, C.c_void_p(raw_ptr), nbytes, C.c_void_p(raw2_ptr), nbytes2, self.world,
+                                            C.c_void_p(self.send.data_ptr()), counts, C.byref(nrec))
         self.eng._check(rc)
         return self.send[: nrec.value], [int(c) for c in counts]
 
@@ -65,12 +69,12 @@ def _mark(name, t0):
     return t1
 
 
-def exchange_chunk(ops, dist, world, raw_ptr, nbytes, via_cpu=False):
+def exchange_chunk(ops, dist, world, raw_ptr, nbytes, via_cpu=False, raw2_ptr=None, nbytes2=0):
     """One chunk through pack -> all-to-all -> insert -> all-to-all -> apply.  Returns this rank's duplicate count."""
     import time
     import torch
     t = time.perf_counter()
-    send_rows, counts = ops.pack(raw_ptr, nbytes)
+    send_rows, counts = ops.pack(raw_ptr, nbytes) if raw2_ptr is None else ops.pack(raw_ptr, nbytes, raw2_ptr, nbytes2)
     t = _mark("pack (K1 + owner sort + row gather)", t)
     dev = send_rows.device
     row_bytes = int(send_rows.shape[1])

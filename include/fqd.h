@@ -193,6 +193,10 @@ int fqd_finish_emit(fqd_handle* h);
 int fqd_set_stream(fqd_handle* h, void* cuda_stream);
 size_t fqd_shard_row_bytes(fqd_handle* h);
 int fqd_shard_pack(fqd_handle* h, const void* d_raw, size_t n, uint32_t n_shards, void* d_send, uint64_t* counts, uint64_t* n_records);
+/* paired-end handle: the two chunks hold the same records (cut at the same record index); the rows carry both mates'
+ * keys and are owned by the hash of the pair (setRecordPair, src/hash_dup_remover.hpp:30-41,55-68) */
+int fqd_shard_pack_pe(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2, uint32_t n_shards, void* d_send,
+                      uint64_t* counts, uint64_t* n_records);
 int fqd_shard_insert(fqd_handle* h, const void* d_recv, uint64_t n_recv, uint32_t n_shards, void* d_flags);
 int fqd_shard_apply(fqd_handle* h, const void* d_flags_back, uint64_t* chunk_dups);
 /* duplicate flags (one byte per record, record order) of the chunk last given to fqd_shard_apply, copied to the host */

@@ -27,14 +27,22 @@ def _worker(rank, world, port, chunks, result_dir):
     sharded = importlib.import_module("fastq-dupaway_b200.sharded")
     torch.cuda.set_device(0)
     mine = chunks[rank]
-    maxb = max(len(c) for c in mine) + 4096
-    eng = fqd.Engine("fast", fqd.FORMAT_FASTQ, False, False, 2, 100, 200000, maxb, 50000, 0)
+    maxb = max(len(c) for c in mine) + 4096 if not isinstance(mine[0], tuple) else 0
+    paired = isinstance(mine[0], tuple)
+    if paired:
+        maxb = max(max(len(a), len(b)) for a, b in mine) + 4096
+    eng = fqd.Engine("fast", fqd.FORMAT_FASTQ, paired, False, 2, 100, 200000, maxb, 50000, 0)
     ops = sharded.GpuShardOps(fqd, eng, world, 0, 50000)
     buf = fqd.DeviceBuffer(maxb, 0)
+    buf2 = fqd.DeviceBuffer(maxb, 0) if paired else None
     flags = []
     for c in mine:
-        buf.upload(c)
-        d, n = sharded.exchange_chunk(ops, dist, world, buf.ptr, len(c), via_cpu=True)
+        if paired:
+            buf.upload(c[0]); buf2.upload(c[1])
+            d, n = sharded.exchange_chunk(ops, dist, world, buf.ptr, len(c[0]), via_cpu=True, raw2_ptr=buf2.ptr, nbytes2=len(c[1]))
+        else:
+            buf.upload(c)
+            d, n = sharded.exchange_chunk(ops, dist, world, buf.ptr, len(c), via_cpu=True)
         res = np.frombuffer(C_string(eng, n), dtype=np.uint8).copy()
         assert int(res.sum()) == d
         flags.append(res)
@@ -68,6 +76,29 @@ def test_two_ranks_one_gpu(tmp_path, oracle):
     exp = np.ones(len(recs), dtype=np.uint8)
     exp[keep_idx.astype(np.int64)] = 0
     got = np.zeros(len(recs), dtype=np.uint8)
+    for r in range(world):
+        f = np.load(tmp_path / f"flags_{r}.npy")
+        for c in range(n_chunks):
+            lo = (c * world + r) * per_chunk
+            got[lo: lo + per_chunk] = f[c * per_chunk: (c + 1) * per_chunk]
+    assert np.array_equal(got, exp)
+
+
+def test_two_ranks_one_gpu_paired(tmp_path, oracle):
+    """Paired-end: the exchanged rows carry both mates' keys, ownership follows the hash of the pair."""
+    world, n_chunks, per_chunk = 2, 3, 3000
+    s1, s2 = synth.make_pair(world * n_chunks * per_chunk, seed=52, read_len=80, var_len=True, n_frac=0.02, dup_frac=0.4)
+    r1 = [synth.to_fastq([s], ids=[b"@g.%d 1" % i]) for i, s in enumerate(s1)]
+    r2 = [synth.to_fastq([s], ids=[b"@g.%d 2" % i]) for i, s in enumerate(s2)]
+    def cut(recs, c, r):
+        return b"".join(recs[(c * world + r) * per_chunk: (c * world + r + 1) * per_chunk])
+    chunks = [[(cut(r1, c, r), cut(r2, c, r)) for c in range(n_chunks)] for r in range(world)]
+    port = 29700 + (os.getpid() % 2000)
+    mp.spawn(_worker, args=(world, port, chunks, str(tmp_path)), nprocs=world, join=True)
+    keep_idx, est = oracle.fast_pe(b"".join(r1), b"".join(r2), oracle.FASTQ)
+    exp = np.ones(len(r1), dtype=np.uint8)
+    exp[keep_idx.astype(np.int64)] = 0
+    got = np.zeros(len(r1), dtype=np.uint8)
     for r in range(world):
         f = np.load(tmp_path / f"flags_{r}.npy")
         for c in range(n_chunks):
