@@ -180,7 +180,8 @@ def our_arm(args):
     fqd = importlib.import_module("fastq-dupaway_b200")
     lib = fqd.load_library()            # raises when the CUDA library is missing: no fallback
     dist = None
-    if world > 1:
+    force_sharded = bool(os.environ.get("FQD_BENCH_FORCE_SHARDED")) and "RANK" in os.environ      # profiling aid: N = 1 through the sharded path
+    if world > 1 or force_sharded:
         import torch
         import torch.distributed as dist_mod
         dist = dist_mod
@@ -188,7 +189,7 @@ def our_arm(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = local_rank
     n_total = int(os.environ.get("FQD_BENCH_READS", 100_000_000))
-    if world > 1:
+    if world > 1 or force_sharded:
         sys.path.insert(0, str(ROOT))
         mg = importlib.import_module("bench_multi")
         return mg.run(args, fqd, dist, rank, local_rank, world, n_total)

@@ -114,6 +114,8 @@ def run_mode_multi(fqd, lib, mode, n_pairs_per_rank, steps):
     for it in range(steps + 1):
         if it:
             ops.reset()
+        if it == 1:
+            sh.TRACE.clear()          # FQD_TRACE: the warm-up job (pool growth, NCCL set-up) is not representative
         t_append = 0.0
         for c in range(n_chunks):
             first = rank * n + c * chunk_pairs
@@ -155,6 +157,9 @@ def run_mode_multi(fqd, lib, mode, n_pairs_per_rank, steps):
                 "imbalance": max(owned) / (sum(owned) / world), "input_GBps": total * 2 * REC / (ms / 1e3) / 1e9,
                 "alltoall_bytes_per_gpu": n * 2 * REC}
         print(json.dumps(line), flush=True)
+        if sh.TRACE:
+            print("[fqd trace] ms over all steps:", json.dumps({k: round(v, 1) for k, v in sh.TRACE.items()}), file=sys.stderr)
+            sh.TRACE.clear()
     ops.close()
     for s_ in stage:
         s_.free()

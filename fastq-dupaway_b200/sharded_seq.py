@@ -98,6 +98,23 @@ class GpuRangeOps:
         self.range.close()
 
 
+TRACE = {}
+
+
+def _mark(name, t0):
+    """FQD_TRACE=1: wall clock per phase of dedup_ranges (each mark synchronises the device)."""
+    import os
+    import time
+    if not os.environ.get("FQD_TRACE"):
+        return t0
+    import torch
+    if torch.cuda.is_available():
+        torch.cuda.synchronize()
+    t1 = time.perf_counter()
+    TRACE[name] = TRACE.get(name, 0.0) + (t1 - t0) * 1e3
+    return t1
+
+
 def dedup_ranges(ops, dist, rank, world, n_samples=4096, tensor_device=None, via_cpu=False):
     """Steps 1-7 above for what has been appended to ops' origin engine.  Returns (records this rank owns,
     records it writes, duplicates it removed) - `ops.output(mate)` then yields this rank's part of the output."""
@@ -105,15 +122,20 @@ def dedup_ranges(ops, dist, rank, world, n_samples=4096, tensor_device=None, via
     dev = tensor_device if tensor_device is not None else getattr(ops, "dev", torch.device("cpu"))
     if via_cpu:                       # gloo ranks sharing one GPU (tests): collectives on host tensors
         dev = torch.device("cpu")
+    import time
+    t = time.perf_counter()
     samples, n_local = ops.sample(n_samples)
+    t = _mark("sample (parse rest + samples)", t)
     # 2. splitters
     mine = torch.from_numpy(samples.astype(np.int64)).to(dev)
     allsmp = [torch.empty_like(mine) for _ in range(world)]
     dist.all_gather(allsmp, mine)
     gathered = np.concatenate([t.cpu().numpy().astype(np.uint64) for t in allsmp], axis=0)
     splitters = choose_splitters(gathered, world)
+    t = _mark("splitters (all-gather + sort)", t)
     # 3. plan
     counts, nbytes = ops.plan(splitters, world)
+    t = _mark("plan (owner + partition + offsets)", t)
     mates = len(nbytes)
     if sum(counts) != n_local:
         raise RuntimeError(f"rank {rank}: partition plan covers {sum(counts)} of {n_local} records")
@@ -123,8 +145,10 @@ def dedup_ranges(ops, dist, rank, world, n_samples=4096, tensor_device=None, via
     dist.all_to_all_single(c_in, c_out.reshape(1 + mates, world).t().contiguous().reshape(-1))
     c_in = c_in.reshape(world, 1 + mates).t().contiguous()         # [1 + mates][source]
     n_owned = int(c_in[0].sum().item())
+    t = _mark("counts all-to-all", t)
     for m in range(mates):
         send = ops.gather(m, sum(nbytes[m]))
+        t = _mark("gather records", t)
         recv_sizes = [int(x) for x in c_in[1 + m].tolist()]
         if via_cpu:
             r_h = torch.empty(sum(recv_sizes), dtype=torch.uint8)
@@ -133,11 +157,14 @@ def dedup_ranges(ops, dist, rank, world, n_samples=4096, tensor_device=None, via
         else:
             recv = torch.empty(sum(recv_sizes), dtype=torch.uint8, device=send.device)
             dist.all_to_all_single(recv, send, recv_sizes, nbytes[m])
+        t = _mark("records all-to-all", t)
         ops.receive(m, recv)
+        t = _mark("receive (append + parse of full segments)", t)
     # 5. local sort + scan
     have = n_owned > 0
     if have:
         ops.scan()
+    t = _mark("scan stage (parse rest + sort + scan)", t)
     # 6. boundary chain: the state after range k-1 goes to range k; an empty range passes on what it received
     nb = ops.boundary_bytes()
     state = torch.zeros(nb, dtype=torch.uint8, device=dev)          # all-zero = "nothing before" (valid flag 0)
@@ -151,6 +178,7 @@ def dedup_ranges(ops, dist, rank, world, n_samples=4096, tensor_device=None, via
             if any(prev):
                 ops.boundary_fix(prev)
         # rank k now holds, in `state`, what precedes it; if it has records it will overwrite it with its own tail
+    t = _mark("boundary chain", t)
     # 7. emission
     if have:
         st = ops.emit()
