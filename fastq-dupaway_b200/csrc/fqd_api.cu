@@ -113,7 +113,10 @@ extern "C" int fqd_memcpy_d2h(int device, void* dst, const void* d_src, size_t b
 }
 extern "C" int fqd_memcpy_h2d(int device, void* d_dst, const void* src, size_t bytes) {
     if (cudaSetDevice(device) != cudaSuccess) return FQD_ERR_CUDA;
-    return cudaMemcpy(d_dst, src, bytes, cudaMemcpyHostToDevice) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
+    // cudaMemcpy from pageable memory may return once the data sits in the staging buffer, before the DMA to the
+    // device has finished; it is ordered only against the default stream, and the handles use non-blocking streams.
+    if (cudaMemcpy(d_dst, src, bytes, cudaMemcpyHostToDevice) != cudaSuccess) return FQD_ERR_CUDA;
+    return cudaDeviceSynchronize() == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
 }
 
 static u32 words_for(u32 max_seq_len, bool byte_keys = false) {

@@ -281,20 +281,48 @@ __global__ void k_sample_rows(const u64* rows, u32 stride, u64 n, u32 n_samples,
     const u64 i = (u64)(((unsigned __int128)j * n) / n_samples);
     out[2 * j] = rows[i * stride]; out[2 * j + 1] = rows[i * stride + 1];
 }
-// records in `perm` order, packed back to back at dst[r] (segmented input, one warp per record)
+// ---- record gathers.  A warp takes 32 records at a time: every lane fetches the geometry of ONE record (coalesced
+// table reads, the segment search in parallel), then the warp copies the 32 records one after the other with the
+// geometry broadcast by shuffles.  (One record per warp-iteration left the copy waiting ~2 us for four dependent
+// loads per 322 bytes: 0.8 TB/s; source and destination are byte-aligned only, so the copy itself moves bytes.)
+__device__ __forceinline__ const u8* seg_locate(u64 o, const u64* seg_base, u8* const* seg_ptr, u32 n_segs) {
+    u32 lo = 0, hi = n_segs;             // last segment whose logical base is <= o
+    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (seg_base[mid] <= o) lo = mid; else hi = mid; }
+    return seg_ptr[lo] + (o - seg_base[lo]);
+}
+// copy `n` bytes src -> dst (+ `pre` dashes in front) for the up-to-32 records held one per lane
+__device__ __forceinline__ void warp_copy_records(const u8* my_src, u8* my_dst, u32 my_n, u32 my_pre, u32 n_valid, u32 lane) {
+    for (u32 j = 0; j < n_valid; ++j) {
+        const u8* src = reinterpret_cast<const u8*>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(my_src), j));
+        u8* d = reinterpret_cast<u8*>(__shfl_sync(0xFFFFFFFFu, reinterpret_cast<unsigned long long>(my_dst), j));
+        const u32 n = __shfl_sync(0xFFFFFFFFu, my_n, j);
+        const u32 pre = __shfl_sync(0xFFFFFFFFu, my_pre, j);
+        if (lane < pre) d[lane] = '-';
+        d += pre;
+        u32 i = lane;
+        for (; i + 96u < n; i += 128u) {          // four independent loads in flight per lane
+            const u8 a = src[i], b = src[i + 32u], c = src[i + 64u], e = src[i + 96u];
+            d[i] = a; d[i + 32u] = b; d[i + 64u] = c; d[i + 96u] = e;
+        }
+        for (; i < n; i += 32u) d[i] = src[i];
+    }
+}
+
+// records in `perm` order, packed back to back at dst[r] (segmented input)
 __global__ void k_gather_records_perm(const u64* rec_off, const u32* rec_len, const u32* perm, const u64* dst, u64 count,
                                       const u64* seg_base, u8* const* seg_ptr, u32 n_segs, u8* out) {
     const u32 lane = threadIdx.x & 31u;
     const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
-    for (u64 r = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < count; r += warps) {
-        const u32 g = perm[r];
-        const u64 o = rec_off[g];
-        u32 lo = 0, hi = n_segs;             // last segment whose logical base is <= o
-        while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (seg_base[mid] <= o) lo = mid; else hi = mid; }
-        const u8* src = seg_ptr[lo] + (o - seg_base[lo]);
-        u8* d = out + dst[r];
-        const u32 n = rec_len[g];
-        for (u32 i = lane; i < n; i += 32) d[i] = src[i];
+    for (u64 r0 = (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; r0 < count; r0 += warps * 32u) {
+        const u64 r = r0 + lane;
+        const u8* src = nullptr; u8* d = nullptr; u32 n = 0;
+        if (r < count) {
+            const u32 g = perm[r];
+            src = seg_locate(rec_off[g], seg_base, seg_ptr, n_segs);
+            d = out + dst[r];
+            n = rec_len[g];
+        }
+        warp_copy_records(src, d, n, 0u, (u32)min((u64)32, count - r0), lane);
     }
 }
 
@@ -1186,24 +1214,20 @@ __global__ void k_gather_records(const u64* off, const u32* len, const u32* dst,
                                  u32 n_segs, u8* out) {
     const u32 lane = threadIdx.x & 31u;
     const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
-    for (u64 r = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < count; r += warps) {
-        const u64 o = off[r];
-        u32 lo = 0, hi = n_segs;             // last segment whose logical base is <= o
-        while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (seg_base[mid] <= o) lo = mid; else hi = mid; }
-        const u8* src = seg_ptr[lo] + (o - seg_base[lo]);
-        u8* d = out + dst[r];
-        const u32 n = len[r];
-        for (u32 i = lane; i < n; i += 32) d[i] = src[i];
+    for (u64 r0 = (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; r0 < count; r0 += warps * 32u) {
+        const u64 r = r0 + lane;
+        const u8* src = nullptr; u8* d = nullptr; u32 n = 0;
+        if (r < count) {
+            src = seg_locate(off[r], seg_base, seg_ptr, n_segs);
+            d = out + dst[r];
+            n = len[r];
+        }
+        warp_copy_records(src, d, n, 0u, (u32)min((u64)32, count - r0), lane);
     }
 }
 
 // ---- --write-clusters (src/seq_dup_remover.hpp:60-62,75-76,89-101 and the paired twin; src/file_utils.cpp:98-112):
 // one line per record in sorted order - the ID line of a written record (cluster head), "--" + ID line of a removed one
-__device__ __forceinline__ const u8* seg_locate(u64 o, const u64* seg_base, u8* const* seg_ptr, u32 n_segs) {
-    u32 lo = 0, hi = n_segs;             // last segment whose logical base is <= o
-    while (hi - lo > 1) { u32 mid = (lo + hi) >> 1; if (seg_base[mid] <= o) lo = mid; else hi = mid; }
-    return seg_ptr[lo] + (o - seg_base[lo]);
-}
 __global__ void k_cluster_lens(const u32* perm, const u32* keep, const u64* rec_off, const u32* rec_len, u64 n,
                                const u64* seg_base, u8* const* seg_ptr, u32 n_segs, u32* out_len) {
     const u32 lane = threadIdx.x & 31u;
@@ -1225,14 +1249,17 @@ __global__ void k_gather_clusters(const u32* perm, const u32* keep, const u64* r
                                   const u64* seg_base, u8* const* seg_ptr, u32 n_segs, u8* out) {
     const u32 lane = threadIdx.x & 31u;
     const u64 warps = ((u64)gridDim.x * blockDim.x) >> 5;
-    for (u64 r = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5; r < count; r += warps) {
-        const u64 i = k0 + r;
-        const u8* src = seg_locate(rec_off[perm[i]], seg_base, seg_ptr, n_segs);
-        const u32 pre = keep[i] ? 0u : 2u;
-        const u32 n = cl_len[i] - pre;
-        u8* d = out + dst[r];
-        if (lane < pre) d[lane] = '-';
-        for (u32 j = lane; j < n; j += 32) d[pre + j] = src[j];
+    for (u64 r0 = (((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 32u; r0 < count; r0 += warps * 32u) {
+        const u64 r = r0 + lane;
+        const u8* src = nullptr; u8* d = nullptr; u32 n = 0, pre = 0;
+        if (r < count) {
+            const u64 i = k0 + r;
+            src = seg_locate(rec_off[perm[i]], seg_base, seg_ptr, n_segs);
+            pre = keep[i] ? 0u : 2u;
+            n = cl_len[i] - pre;
+            d = out + dst[r];
+        }
+        warp_copy_records(src, d, n, pre, (u32)min((u64)32, count - r0), lane);
     }
 }
 
@@ -1324,7 +1351,7 @@ static int seq_partition_gather(SeqState* s, int m, void* d_out, std::string* er
     if (s->part_n == 0) return FQD_OK;
     int rc = seq_upload_segtab(s, m, err);
     if (rc) return rc;
-    k_gather_records_perm<<<seq_grid(s, s->part_n * 32), 256, 0, s->stream>>>(s->mate[m].d_rec_off, s->mate[m].d_rec_len, s->d_part_perm,
+    k_gather_records_perm<<<seq_grid(s, s->part_n), 256, 0, s->stream>>>(s->mate[m].d_rec_off, s->mate[m].d_rec_len, s->d_part_perm,
                                                                              s->d_part_off[m], s->part_n, s->d_seg_base[m], s->d_seg_ptr[m],
                                                                              s->n_segs[m], (u8*)d_out);
     s->launches++;
@@ -1361,7 +1388,7 @@ static int seq_emit(SeqState* s, int m, void* dst, size_t cap, size_t* n_bytes, 
     }
     SortScratch sc; sc.scan_state = s->em_scan_state; sc.ticket = s->em_ticket; sc.d_total = s->em_total;
     if ((rc = device_scan(s, sc, s->d_o_len[m] + k0, s->d_dst, cnt, nullptr, err))) return rc;
-    k_gather_records<<<seq_grid(s, cnt * 32), 256, 0, s->stream>>>(s->d_o_off[m] + k0, s->d_o_len[m] + k0, s->d_dst, cnt, s->d_seg_base[m],
+    k_gather_records<<<seq_grid(s, cnt), 256, 0, s->stream>>>(s->d_o_off[m] + k0, s->d_o_len[m] + k0, s->d_dst, cnt, s->d_seg_base[m],
                                                                    s->d_seg_ptr[m], s->n_segs[m], s->d_stage);
     s->launches++;
     SEQ_TRY(cudaMemcpyAsync(dst, s->d_stage, bytes, cudaMemcpyDeviceToHost, s->stream));
@@ -1409,7 +1436,7 @@ static int seq_emit_clusters(SeqState* s, int m, void* dst, size_t cap, size_t* 
     }
     SortScratch sc; sc.scan_state = s->em_scan_state; sc.ticket = s->em_ticket; sc.d_total = s->em_total;
     if ((rc = device_scan(s, sc, s->d_cl_len[m] + k0, s->d_dst, cnt, nullptr, err))) return rc;
-    k_gather_clusters<<<seq_grid(s, cnt * 32), 256, 0, s->stream>>>(s->d_perm, s->d_keep, s->mate[m].d_rec_off, s->d_cl_len[m], s->d_dst, k0, cnt,
+    k_gather_clusters<<<seq_grid(s, cnt), 256, 0, s->stream>>>(s->d_perm, s->d_keep, s->mate[m].d_rec_off, s->d_cl_len[m], s->d_dst, k0, cnt,
                                                                     s->d_seg_base[m], s->d_seg_ptr[m], s->n_segs[m], s->d_stage);
     s->launches++;
     SEQ_TRY(cudaMemcpyAsync(dst, s->d_stage, bytes, cudaMemcpyDeviceToHost, s->stream));

@@ -41,7 +41,9 @@ def _worker(rank, world, port, mode, dval, fmt_name, slices, result_dir):
     st0 = None
     owned, kept, dups = sh.dedup_ranges(ops, dist, rank, world, n_samples=256, via_cpu=True)
     st0 = ops.origin.stats()
-    assert ops.origin.partition_sample(1)[1] == n_local_expected, (rank, ops.origin.partition_sample(1)[1], n_local_expected, st0.err)
+    assert ops.origin.partition_sample(1)[1] == n_local_expected, (
+        "origin parse", rank, ops.origin.partition_sample(1)[1], n_local_expected, st0.err, st0.err_record, st0.err_char, st0.err_mate,
+        [len(b) for b in mine])
     for m in range(len(mine)):
         (Path(result_dir) / f"out_{rank}_{m}.bin").write_bytes(ops.output(m) if owned else b"")
     (Path(result_dir) / f"cnt_{rank}.txt").write_text(f"{owned} {kept} {dups}")
