@@ -5,10 +5,10 @@
 
 Workload: synthetic 2x150 bp paired-end FASTQ (644 B per pair), 30 % duplicates, the SURVEY section 8d variants
 (loose: 10 % of the duplicates truncated; tail-hamming: 10 % of the duplicates with <= 2 tail substitutions;
-unordered: the same pairs with R2 read in a different order).  A step = one whole job: every chunk is appended
-(parse + pack into HBM segments), then fqd_finish runs sort + scan (or tag sort + join + pair set).  The synthetic
-chunks are generated on the device outside the timed regions; device time is the sum of the CUDA-event intervals
-around the appends and the finish.  Prints one JSON line per mode; profiles/ keeps the committed results.
+unordered: the same pairs with R2 read in a different order).  A step = one whole job: the engine adopts the
+input that is resident in HBM (fqd_adopt_device: parse + pack in place), then fqd_finish runs sort + scan (or tag
+sort + join + pair set).  The synthetic input is generated on the device outside the timed region; device time is
+the CUDA-event interval around adopt + finish.  Prints one JSON line per mode; profiles/ keeps the committed results.
 """
 from __future__ import annotations
 
@@ -43,31 +43,31 @@ def run_mode(fqd, lib, mode, n_pairs, steps, dev=0):
     emode = "fast" if unordered else mode
     chunk_pairs = 1_500_000
     n_chunks = (n_pairs + chunk_pairs - 1) // chunk_pairs
-    stage = [fqd.DeviceBuffer(chunk_pairs * REC + 65536, dev) for _ in range(2)]
+    # the whole input of both mates is generated into HBM once (outside the timed region); the engine adopts the
+    # buffers (fqd_adopt_device: parsed in place, no copy)
+    raw = [fqd.DeviceBuffer(n_pairs * REC + 65536, dev) for _ in range(2)]
+    off2 = 0
+    for c in range(n_chunks):
+        first = c * chunk_pairs
+        cnt = min(chunk_pairs, n_pairs - first)
+        assert lib.fqd_synth_fastq(dev, raw[0].ptr + first * REC, first, cnt, READ_LEN, 1, SEED, DUP_PERMILLE, N_PERMILLE, VARIANT[mode]) == 0
+        # unordered: R2 arrives chunk-reversed (its tag sort has to undo that; pairs are matched by tag)
+        c2 = (n_chunks - 1 - c) if unordered else c
+        first2 = c2 * chunk_pairs
+        cnt2 = min(chunk_pairs, n_pairs - first2)
+        assert lib.fqd_synth_fastq(dev, raw[1].ptr + off2, first2, cnt2, READ_LEN, 2, SEED, DUP_PERMILLE, N_PERMILLE, VARIANT[mode]) == 0
+        off2 += cnt2 * REC
     eng = fqd.Engine(emode, fqd.FORMAT_FASTQ, True, unordered, 2, READ_LEN, n_pairs + 1024, 1 << 30, 0, dev, 16)
     times = []
     stats = None
-    order = list(range(n_chunks))
     for it in range(steps + 1):
         if it:
             eng.reset()
-        t_ms = 0.0
-        for c in order:
-            first = c * chunk_pairs
-            cnt = min(chunk_pairs, n_pairs - first)
-            # unordered: R2 arrives chunk-reversed (its tag sort has to undo that; pairs are matched by tag)
-            c2 = (n_chunks - 1 - c) if unordered else c
-            first2 = c2 * chunk_pairs
-            cnt2 = min(chunk_pairs, n_pairs - first2)
-            assert lib.fqd_synth_fastq(dev, stage[0].ptr, first, cnt, READ_LEN, 1, SEED, DUP_PERMILLE, N_PERMILLE, VARIANT[mode]) == 0
-            assert lib.fqd_synth_fastq(dev, stage[1].ptr, first2, cnt2, READ_LEN, 2, SEED, DUP_PERMILLE, N_PERMILLE, VARIANT[mode]) == 0
-            eng.timer_start()
-            eng.append_device(0, stage[0].ptr, cnt * REC)
-            eng.append_device(1, stage[1].ptr, cnt2 * REC)
-            t_ms += eng.timer_stop()
         eng.timer_start()
+        eng.adopt_device(0, raw[0].ptr, n_pairs * REC)
+        eng.adopt_device(1, raw[1].ptr, n_pairs * REC)
         eng.finish()
-        t_ms += eng.timer_stop()
+        t_ms = eng.timer_stop()
         st = eng.stats()
         assert st.err == 0, (st.err, st.err_record)
         if it:
@@ -77,7 +77,7 @@ def run_mode(fqd, lib, mode, n_pairs, steps, dev=0):
     n_out = int(em.n_out)
     _, launches = eng.device_time_ms()
     eng.close()
-    for s in stage:
+    for s in raw:
         s.free()
     ms = sum(times) / len(times)
     peak = 6538.6
@@ -107,8 +107,19 @@ def run_mode_multi(fqd, lib, mode, n_pairs_per_rank, steps):
     chunk_pairs = 1_500_000
     n = n_pairs_per_rank
     n_chunks = (n + chunk_pairs - 1) // chunk_pairs
-    stage = [fqd.DeviceBuffer(chunk_pairs * REC + 65536, dev) for _ in range(2)]
+    # this rank's slice of both mates, generated into HBM once (outside the timed region) and adopted in place
+    raw = [fqd.DeviceBuffer(n * REC + 65536, dev) for _ in range(2)]
+    for c in range(n_chunks):
+        first = c * chunk_pairs
+        cnt = min(chunk_pairs, n - first)
+        for m in range(2):
+            assert lib.fqd_synth_fastq(dev, raw[m].ptr + first * REC, rank * n + first, cnt, READ_LEN, m + 1, SEED, DUP_PERMILLE, N_PERMILLE,
+                                       VARIANT[mode]) == 0
     ops = sh.GpuRangeOps(fqd, mode, fqd.FORMAT_FASTQ, True, 2, READ_LEN, n + 1024, int(n * 1.3) + (1 << 20), dev, seg_bytes=1 << 30)
+    peer = None
+    if not os.environ.get("FQD_NO_PEER"):
+        px = importlib.import_module("fastq-dupaway_b200.peer")
+        peer = [px.PeerExchange(fqd, dist, rank, world, dev, int(n * REC * 1.3) + (64 << 20)) for _ in range(2)]     # one receive buffer per mate
     times = []
     res = None
     for it in range(steps + 1):
@@ -116,22 +127,16 @@ def run_mode_multi(fqd, lib, mode, n_pairs_per_rank, steps):
             ops.reset()
         if it == 1:
             sh.TRACE.clear()          # FQD_TRACE: the warm-up job (pool growth, NCCL set-up) is not representative
-        t_append = 0.0
-        for c in range(n_chunks):
-            first = rank * n + c * chunk_pairs
-            cnt = min(chunk_pairs, n - c * chunk_pairs)
-            for m in range(2):
-                assert lib.fqd_synth_fastq(dev, stage[m].ptr, first, cnt, READ_LEN, m + 1, SEED, DUP_PERMILLE, N_PERMILLE, VARIANT[mode]) == 0
-            ops.origin.timer_start()
-            for m in range(2):
-                ops.append(m, stage[m].ptr, cnt * REC)
-            t_append += ops.origin.timer_stop()          # parse + pack of this rank's slice (same as the N = 1 arm)
-            torch.cuda.synchronize(dev)
+        torch.cuda.synchronize(dev)
+        ops.origin.timer_start()
+        for m in range(2):
+            ops.origin.adopt_device(m, raw[m].ptr, n * REC)
+        t_append = ops.origin.timer_stop()              # parse + pack of this rank's slice (same as the N = 1 arm)
         dist.barrier()
         torch.cuda.synchronize(dev)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        res = sh.dedup_ranges(ops, dist, rank, world, n_samples=8192)
+        res = sh.dedup_ranges(ops, dist, rank, world, n_samples=8192, peer=peer)
         torch.cuda.synchronize(dev)
         e1.record()
         torch.cuda.synchronize(dev)
@@ -150,18 +155,22 @@ def run_mode_multi(fqd, lib, mode, n_pairs_per_rank, steps):
                 "reads_per_s": 2 * total / (ms / 1e3), "n_gpus": world, "steps": steps, "ms_per_step": ms, "scaling": "weak",
                 "config": {"workload": f"synthetic {total} x 2x150bp paired-end FASTQ, 30% duplicates, --compare-seq {mode}",
                            "pairs_per_gpu": n, "parallelism": f"key-range x{world}", "record_bytes": REC, "seed": SEED,
-                           "timed": "appends (parse + pack of the slice) + sample + splitters + plan + gather + all-to-all of raw records + parse + sort + scan + "
+                           "timed": "adopt (parse + pack of the slice in place) + sample + splitters + plan + gather + all-to-all of raw records + parse + sort + scan + "
                                     "boundary chain + emission lists (slices already appended and resident)"},
                 "pairs_total": total, "duplicates_removed": int(sum(int(t[2].item()) for t in own)),
                 "pairs_out": int(sum(int(t[1].item()) for t in own)), "owned_per_rank": owned,
                 "imbalance": max(owned) / (sum(owned) / world), "input_GBps": total * 2 * REC / (ms / 1e3) / 1e9,
-                "alltoall_bytes_per_gpu": n * 2 * REC}
+                "alltoall_bytes_per_gpu": n * 2 * REC,
+                "exchange": "mapped peer memory (CUDA IPC + copy engines)" if peer is not None else "NCCL all_to_all_single"}
         print(json.dumps(line), flush=True)
         if sh.TRACE:
             print("[fqd trace] ms over all steps:", json.dumps({k: round(v, 1) for k, v in sh.TRACE.items()}), file=sys.stderr)
             sh.TRACE.clear()
     ops.close()
-    for s_ in stage:
+    if peer is not None:
+        for px_ in peer:
+            px_.close()
+    for s_ in raw:
         s_.free()
 
 

@@ -105,6 +105,7 @@ def load_library():
     lib.fqd_profile_get.argtypes = [vp, C.POINTER(Profile)]
     lib.fqd_append.argtypes = [vp, C.c_int, vp, sz]
     lib.fqd_append_device.argtypes = [vp, C.c_int, vp, sz]
+    lib.fqd_adopt_device.argtypes = [vp, C.c_int, vp, sz]
     lib.fqd_finish.argtypes = [vp]
     lib.fqd_finish_scan.argtypes = [vp]
     lib.fqd_finish_emit.argtypes = [vp]
@@ -131,6 +132,10 @@ def load_library():
     lib.fqd_synth_fastq.argtypes = [C.c_int, vp, u64, u64, C.c_uint32, C.c_int, u64, C.c_uint32, C.c_uint32, C.c_int]
     lib.fqd_synth_record_bytes.argtypes = [C.c_uint32]
     lib.fqd_synth_record_bytes.restype = sz
+    lib.fqd_ipc_export.argtypes = [C.c_int, vp, vp]
+    lib.fqd_ipc_open.argtypes = [C.c_int, vp, C.POINTER(vp)]
+    lib.fqd_ipc_close.argtypes = [C.c_int, vp]
+    lib.fqd_peer_copy_async.argtypes = [C.c_int, vp, vp, sz, vp]
     lib.fqd_device_alloc.argtypes = [C.c_int, C.POINTER(vp), sz]
     lib.fqd_device_free.argtypes = [C.c_int, vp]
     lib.fqd_memcpy_d2h.argtypes = [C.c_int, vp, vp, sz]
@@ -257,6 +262,10 @@ class Engine:
 
     def append_device(self, mate: int, dptr: int, n: int):
         self._check(self.lib.fqd_append_device(self.h, mate, C.c_void_p(dptr), n))
+
+    def adopt_device(self, mate: int, dptr: int, n: int):
+        """Zero-copy: the whole input of `mate` is the device buffer [dptr, dptr + n) (must outlive the job)."""
+        self._check(self.lib.fqd_adopt_device(self.h, mate, C.c_void_p(dptr), n))
 
     def finish(self):
         self._check(self.lib.fqd_finish(self.h))

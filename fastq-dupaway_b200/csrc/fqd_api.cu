@@ -119,6 +119,30 @@ extern "C" int fqd_memcpy_h2d(int device, void* d_dst, const void* src, size_t b
     return cudaDeviceSynchronize() == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
 }
 
+// ---- peer-memory exchange (multi-GPU, one process per GPU): a rank exports a device buffer, its peers map it and
+// write their part of an all-to-all straight into it over NVLink with the copy engines (cudaMemcpyAsync on mapped
+// peer memory), instead of NCCL's SM-driven send/recv kernels.
+extern "C" int fqd_ipc_export(int device, void* d_ptr, void* handle64) {
+    if (cudaSetDevice(device) != cudaSuccess || !d_ptr || !handle64) return FQD_ERR_INVALID;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    return cudaIpcGetMemHandle((cudaIpcMemHandle_t*)handle64, d_ptr) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
+}
+extern "C" int fqd_ipc_open(int device, const void* handle64, void** d_ptr) {
+    if (cudaSetDevice(device) != cudaSuccess || !d_ptr || !handle64) return FQD_ERR_INVALID;
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle64, sizeof h);
+    return cudaIpcOpenMemHandle(d_ptr, h, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
+}
+extern "C" int fqd_ipc_close(int device, void* d_ptr) {
+    if (cudaSetDevice(device) != cudaSuccess) return FQD_ERR_CUDA;
+    return cudaIpcCloseMemHandle(d_ptr) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
+}
+extern "C" int fqd_peer_copy_async(int device, void* d_dst, const void* d_src, size_t bytes, void* cuda_stream) {
+    if (cudaSetDevice(device) != cudaSuccess) return FQD_ERR_CUDA;
+    if (bytes == 0) return FQD_OK;
+    return cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, (cudaStream_t)cuda_stream) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
+}
+
 static u32 words_for(u32 max_seq_len, bool byte_keys = false) {
     u32 w = byte_keys ? (max_seq_len + 1 + 7) / 8 : (max_seq_len + BASES_PER_WORD - 1) / BASES_PER_WORD;
     if (w < 2) w = 2;
@@ -245,7 +269,7 @@ static int launch_parse(fqd_handle* h, int m, const u8* d_raw, size_t n, u8* d_d
     p.raw = d_raw; p.n = (u32)n; p.n_tiles = n_tiles; p.tile_state = c.d_tile_state; p.ctl = c.d_ctl; p.run = h->d_run;
     p.rec_start = c.d_rec_start; p.cap = h->cap; p.keys = h->d_keys; p.key_capacity = h->key_capacity;
     p.row_words = h->row_words; p.mate_off = m * h->W; p.W = h->W; p.hash = c.d_hash; p.seq_len = nullptr; p.word0 = nullptr;
-    p.strict = 1; p.hash_salt = m * 4096u; p.bad_rec = nullptr; p.dup = (m == 0) ? h->d_dup : nullptr; p.byte_keys = 0;
+    p.strict = 1; p.hash_salt = m * 4096u; p.bad_rec = nullptr; p.dup = (m == 0) ? h->d_dup : nullptr; p.byte_keys = 0; p.skip = 0;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (h->profile) { pe0 = get_event(h); pe1 = get_event(h); cudaEventRecord(pe0, h->stream); }
     const u32 grid = n_tiles;      // one tile per CTA, processed in ticket order
@@ -542,7 +566,7 @@ static int shard_pack_impl(fqd_handle* h, const void* d_raw, size_t n, const voi
         p.raw = raw; p.n = (u32)nb; p.n_tiles = n_tiles; p.tile_state = c.d_tile_state; p.ctl = c.d_ctl; p.run = h->d_stage_run;
         p.rec_start = c.d_rec_start; p.cap = h->cap; p.keys = h->d_stage_keys; p.key_capacity = h->cap;
         p.row_words = h->row_words; p.mate_off = m * h->W; p.W = h->W; p.hash = c.d_hash; p.seq_len = nullptr; p.word0 = nullptr;
-        p.strict = 1; p.hash_salt = m * 4096u; p.dup = nullptr; p.bad_rec = nullptr; p.byte_keys = 0;
+        p.strict = 1; p.hash_salt = m * 4096u; p.dup = nullptr; p.bad_rec = nullptr; p.byte_keys = 0; p.skip = 0;
         if (n_tiles) {
             if (h->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
             else k_parse_pack<2><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
@@ -665,6 +689,13 @@ extern "C" int fqd_append_device(fqd_handle* h, int mate, const void* d_buf, siz
     if (!h || !h->seq) return fail(h, FQD_ERR_INVALID, "fqd_append_device is for sequence / unordered modes");
     cudaSetDevice(h->cfg.device);
     return seq_append(h->seq, mate, d_buf, n, true, &h->err);
+}
+extern "C" int fqd_adopt_device(fqd_handle* h, int mate, const void* d_buf, size_t n) {
+    if (!h || !h->seq) return fail(h, FQD_ERR_INVALID, "fqd_adopt_device is for sequence / unordered modes");
+    cudaSetDevice(h->cfg.device);
+    int rc = seq_adopt(h->seq, mate, d_buf, n, &h->err);
+    seq_stats(h->seq, &h->stats);
+    return rc;
 }
 extern "C" int fqd_finish(fqd_handle* h) {
     if (!h || !h->seq) return fail(h, FQD_ERR_INVALID, "fqd_finish is for sequence / unordered modes");

@@ -53,6 +53,8 @@ struct ParseParams {
                             // {A,C,G,T,N} of each record
     u32 strict;             // 1: bytes outside {A,C,G,T,N} are an error (fast mode, src/seq_utils.cpp:17-19)
     u32 hash_salt;          // distinguishes mates in the position keys
+    u32 skip;               // < 16: the chunk proper starts at raw + skip (raw is aligned down for the bulk copies; the bytes
+                            //       before belong to the record before); record 0 starts there
     u32 byte_keys;          // 1: rows hold the raw bytes of sequence + '\n', 8 per word, first byte in the top bits
                             //    (sequence-based modes on inputs with bytes outside {A,C,G,T,N}); 0: 3-bit codes, 20 per word
 };
@@ -408,7 +410,8 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     __syncthreads();
 
     // ---- 2. local ranks: block scan over the tile's mask words (+ the halo words, ranked after them)
-    const u64 my_mask = mask64[tid];               // PP_TILE/64 == PP_THREADS words cover the tile proper
+    // PP_TILE/64 == PP_THREADS words cover the tile proper; newlines before the chunk's first byte are not ours
+    const u64 my_mask = mask64[tid] & ((tile == 0 && tid == 0) ? (~0ull << p.skip) : ~0ull);
     const u32 cnt = (u32)__popcll(my_mask);
     u32 incl = cnt;
 #pragma unroll
@@ -567,7 +570,7 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
             if (wtid < n_round) {
                 const u32 Rrel = Rrel_first + rbase + wtid;
                 const int j0 = (int)(LPR * Rrel) - 1 - (int)c;            // local rank of the newline before the record
-                const u32 start_l = j0 < 0 ? 0u : (u32)nlpos[j0] + 1u;
+                const u32 start_l = j0 < 0 ? p.skip : (u32)nlpos[j0] + 1u;
                 gstart = base + start_l;
                 u32 qoff = PP_NONE, qlen = 0;
                 if (gstart < p.n) {
@@ -666,7 +669,7 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
             bool virt = (tile == 0 && tid == 0);      // record 0 starts at offset 0 with no newline before it
             while (m || virt) {
                 u32 R, start_l;
-                if (virt) { virt = false; R = 0; start_l = 0; }
+                if (virt) { virt = false; R = 0; start_l = p.skip; }
                 else {
                     u32 b = (u32)__ffsll((long long)m) - 1u;
                     m &= m - 1;

@@ -510,10 +510,13 @@ __global__ void k_emit_pairs(const u32* keep, const u32* excl, u64 n, const u32*
 __global__ void k_set_chunk_pairs(RunState* run, u32 n) { run->n_records = 0; run->chunk_pairs = n; run->chunk_dups = 0; }
 
 // ---------------------------------------------------------------------------------------------------------
-struct SeqSegment { u8* d = nullptr; size_t cap = 0, fill = 0; u64 logical_base = 0; };
+// owned: pool memory holding a copy of the input.  !owned: a view into a caller's buffer (fqd_adopt_device): d is the
+// view's start aligned down to 16 bytes (bulk copies need it), the view proper begins `skip` bytes later.
+struct SeqSegment { u8* d = nullptr; size_t cap = 0, fill = 0; u64 logical_base = 0; bool owned = true; u32 skip = 0; };
 
 struct SeqMate {
     std::vector<SeqSegment> segs;
+    bool adopted = false;            // the input is a caller's buffer, cut into views at record boundaries
     RunState* d_run = nullptr;
     u64 n_records = 0;
     u64* d_rec_off = nullptr;
@@ -642,7 +645,7 @@ static void seq_free_results(SeqState* s) {
 static void seq_destroy(SeqState* s) {
     if (!s) return;
     seq_free_results(s);
-    for (int m = 0; m < 2; ++m) for (auto& sg : s->mate[m].segs) cudaFreeAsync(sg.d, s->stream);
+    for (int m = 0; m < 2; ++m) for (auto& sg : s->mate[m].segs) if (sg.owned) cudaFreeAsync(sg.d, s->stream);
     seq_pool_trim(s);
     if (s->h_lenwin) cudaFreeHost(s->h_lenwin);
     for (int m = 0; m < 2; ++m) {
@@ -658,8 +661,8 @@ static void seq_destroy(SeqState* s) {
 static int seq_reset(SeqState* s, std::string* err) {
     seq_free_results(s);
     for (u32 m = 0; m < s->mates; ++m) {
-        for (auto& sg : s->mate[m].segs) cudaFreeAsync(sg.d, s->stream);
-        s->mate[m].segs.clear();
+        for (auto& sg : s->mate[m].segs) if (sg.owned) cudaFreeAsync(sg.d, s->stream);
+        s->mate[m].segs.clear(); s->mate[m].adopted = false;
         s->mate[m].n_records = 0; s->mate[m].finished = false;
         SEQ_TRY(cudaMemsetAsync(s->mate[m].d_run, 0, sizeof(RunState), s->stream));
         if (s->mate[m].d_bad) SEQ_TRY(cudaMemsetAsync(s->mate[m].d_bad, 0xFF, s->capacity * sizeof(u32), s->stream));
@@ -709,7 +712,7 @@ static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
     p.rec_start = s->d_rec_start; p.cap = (u32)std::min<u64>(s->chunk_cap, room); p.keys = s->d_keys; p.key_capacity = s->capacity;
     p.row_words = s->row_words; p.mate_off = m * s->W; p.W = s->W; p.hash = s->d_hash; p.seq_len = mt.d_seq_len + mt.n_records;
     p.word0 = nullptr; p.dup = nullptr; p.strict = 0; p.hash_salt = m * 4096u; p.bad_rec = nullptr;
-    p.byte_keys = s->cfg.byte_keys ? 1u : 0u;
+    p.byte_keys = s->cfg.byte_keys ? 1u : 0u; p.skip = sg.skip;
     if (s->cfg.unordered) { p.hash = mt.d_hash + mt.n_records; p.bad_rec = mt.d_bad + mt.n_records; }
     if (s->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<n_tiles, PP_THREADS, 0, s->stream>>>(p);
     else k_parse_pack<2><<<n_tiles, PP_THREADS, 0, s->stream>>>(p);
@@ -738,11 +741,13 @@ static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
     else if (c.pad && !s->cfg.unordered) seq_set_error(s, FQD_ERR_UNSUPPORTED_BYTE, 0, first, m);
     mt.n_records += c.n_records;
     const size_t consumed = c.consumed, tail = sg.fill - consumed;
-    if (c.n_records == 0 && !final && sg.fill >= sg.cap) {
+    if (c.n_records == 0 && !final && sg.owned && sg.fill >= sg.cap) {
         *err = "a single record does not fit into one device segment (raise max_chunk_bytes)";
         return FQD_ERR_CAPACITY;
     }
-    if (!final) {
+    if (!final && !sg.owned) {
+        mt.segs.back().fill = consumed;          // the next view (seq_adopt) starts where this one stopped
+    } else if (!final) {
         SeqSegment nx;
         nx.cap = s->seg_bytes;
         SEQ_TRY(cudaMallocAsync(&nx.d, nx.cap + 4096, s->stream));
@@ -765,10 +770,53 @@ static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
     return FQD_OK;
 }
 
+// The whole input of one mate is a device buffer of the caller: no copy, the engine parses it in place through views of
+// at most seg_bytes that are cut at record boundaries.  One call per mate, 16-byte aligned, instead of fqd_append*.
+static int seq_adopt(SeqState* s, int m, const void* d_buf, size_t n, std::string* err) {
+    if (m < 0 || (u32)m >= s->mates) { *err = "bad mate index"; return FQD_ERR_INVALID; }
+    if (s->finished || s->parsed) { *err = "fqd_adopt_device after fqd_finish"; return FQD_ERR_INVALID; }
+    SeqMate& mt = s->mate[m];
+    if (!mt.segs.empty()) { *err = "fqd_adopt_device: the mate already has input"; return FQD_ERR_INVALID; }
+    if ((uintptr_t)d_buf & 15u) { *err = "fqd_adopt_device: the buffer must be 16-byte aligned"; return FQD_ERR_INVALID; }
+    mt.adopted = true;
+    u8* base = (u8*)d_buf;
+    size_t off = 0;
+    while (off < n && !s->stats.err) {
+        u8* addr = base + off;
+        const u32 skip = (u32)((uintptr_t)addr & 15u);
+        const size_t remaining = n - off;
+        SeqSegment sg;
+        sg.owned = false; sg.skip = skip; sg.d = addr - skip;
+        sg.fill = sg.cap = std::min(s->seg_bytes, remaining) + skip;
+        sg.logical_base = off - skip;
+        mt.segs.push_back(sg);
+        int rc = seq_parse_segment(s, m, false, err);
+        if (rc) return rc;
+        const size_t consumed = mt.segs.back().fill;          // relative to sg.d; the view now ends at a record boundary
+        if (consumed <= skip) {                               // no complete record in this view
+            mt.segs.pop_back();
+            if (remaining > s->seg_bytes) { *err = "a single record does not fit into one device segment (raise max_chunk_bytes)"; return FQD_ERR_CAPACITY; }
+            // an incomplete last record is dropped silently (src/fastqview.cpp:114-115), but its first byte is still
+            // checked when the record before it is fetched (src/fastqview.cpp:91-92)
+            u8 b = 0;
+            SEQ_TRY(cudaMemcpy(&b, addr, 1, cudaMemcpyDeviceToHost));
+            const u8 lead = s->cfg.format == FQD_FORMAT_FASTQ ? '@' : '>';
+            if (b != lead && !s->stats.err) seq_set_error(s, FQD_ERR_BAD_START, b, mt.n_records, m);
+            break;
+        }
+        off += consumed - skip;
+    }
+    if (mt.segs.empty()) {            // nothing but an incomplete record: keep an empty view so that the mate is not "absent"
+        SeqSegment sg; sg.owned = false; sg.d = base; sg.fill = sg.cap = 0; mt.segs.push_back(sg);
+    }
+    return FQD_OK;
+}
+
 static int seq_append(SeqState* s, int m, const void* buf, size_t n, bool is_device, std::string* err) {
     if (m < 0 || (u32)m >= s->mates) { *err = "bad mate index"; return FQD_ERR_INVALID; }
     if (s->finished) { *err = "fqd_append after fqd_finish"; return FQD_ERR_INVALID; }
     SeqMate& mt = s->mate[m];
+    if (mt.adopted) { *err = "fqd_append after fqd_adopt_device"; return FQD_ERR_INVALID; }
     const u8* src = (const u8*)buf;
     while (n) {
         if (mt.segs.empty()) {
@@ -1041,6 +1089,7 @@ static int seq_parse_rest(SeqState* s, std::string* err) {
     for (u32 m = 0; m < s->mates; ++m) {
         SeqMate& mt = s->mate[m];
         if (mt.segs.empty()) { seq_set_error(s, FQD_ERR_EMPTY, 0, 0, m); continue; }
+        if (mt.adopted) continue;                 // fqd_adopt_device parsed everything in place
         // a segment may hold more records than one parse takes (chunk_cap): keep parsing its carried tail
         for (;;) {
             const u64 before = mt.n_records;

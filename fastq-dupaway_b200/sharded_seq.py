@@ -67,6 +67,11 @@ class GpuRangeOps:
             self.range.append_device(mate, recv.data_ptr(), int(recv.numel()))
             self.torch.cuda.synchronize(self.dev)
 
+    def receive_ptr(self, mate, dptr, nbytes):
+        """what arrived in a peer-exchange buffer is parsed in place (the buffer is not reused before the job ends)"""
+        if nbytes:
+            self.range.adopt_device(mate, dptr, nbytes)
+
     def scan(self):
         self.range.finish_scan()
         st = self.range.stats()
@@ -115,8 +120,9 @@ def _mark(name, t0):
     return t1
 
 
-def dedup_ranges(ops, dist, rank, world, n_samples=4096, tensor_device=None, via_cpu=False):
-    """Steps 1-7 above for what has been appended to ops' origin engine.  Returns (records this rank owns,
+def dedup_ranges(ops, dist, rank, world, n_samples=4096, tensor_device=None, via_cpu=False, peer=None):
+    """Steps 1-7 above for what has been appended to ops' origin engine.  peer: one PeerExchange per mate - the records
+    then travel over mapped peer memory and are parsed in place where they land; else torch.distributed moves them.  Returns (records this rank owns,
     records it writes, duplicates it removed) - `ops.output(mate)` then yields this rank's part of the output."""
     import torch
     dev = tensor_device if tensor_device is not None else getattr(ops, "dev", torch.device("cpu"))
@@ -149,6 +155,12 @@ def dedup_ranges(ops, dist, rank, world, n_samples=4096, tensor_device=None, via
     for m in range(mates):
         send = ops.gather(m, sum(nbytes[m]))
         t = _mark("gather records", t)
+        if peer is not None:          # mapped peer memory: the copy engines write straight into the owners' buffers
+            rptr, rsizes = peer[m].exchange(send.data_ptr(), nbytes[m])
+            t = _mark("records all-to-all", t)
+            ops.receive_ptr(m, rptr, sum(rsizes))
+            t = _mark("receive (append + parse of full segments)", t)
+            continue
         recv_sizes = [int(x) for x in c_in[1 + m].tolist()]
         if via_cpu:
             r_h = torch.empty(sum(recv_sizes), dtype=torch.uint8)

@@ -131,6 +131,11 @@ int fqd_reset(fqd_handle* h);
  */
 int fqd_append(fqd_handle* h, int mate, const char* buf, size_t n);
 int fqd_append_device(fqd_handle* h, int mate, const void* d_buf, size_t n);
+/* Zero-copy variant for input that is ALREADY in device memory as one buffer per mate (GPUDirect-style ingest, the
+ * receive buffer of the multi-GPU exchange): the engine parses the buffer in place (views of at most max_chunk_bytes,
+ * cut at record boundaries) and gathers the output from it.  One call per mate instead of fqd_append*; d_buf must be
+ * 16-byte aligned and stay valid and unchanged until fqd_reset / fqd_destroy. */
+int fqd_adopt_device(fqd_handle* h, int mate, const void* d_buf, size_t n);
 int fqd_finish(fqd_handle* h);
 typedef struct {
     uint64_t n_out;             /* records (pairs) written                                               */
@@ -231,6 +236,12 @@ int fqd_synth_fastq(int device, void* d_out, uint64_t first, uint64_t count, uin
 size_t fqd_synth_record_bytes(uint32_t read_len);
 
 /* Raw device memory helpers so that bindings need no CUDA runtime of their own. */
+/* Peer-memory exchange between the ranks of one box (one process per GPU): export a device allocation made with
+ * fqd_device_alloc as a 64-byte handle, map a peer's handle, and copy into mapped peer memory over NVLink. */
+int fqd_ipc_export(int device, void* d_ptr, void* handle64);
+int fqd_ipc_open(int device, const void* handle64, void** d_ptr);
+int fqd_ipc_close(int device, void* d_ptr);
+int fqd_peer_copy_async(int device, void* d_dst, const void* d_src, size_t bytes, void* cuda_stream);
 int fqd_device_alloc(int device, void** d_ptr, size_t bytes);
 int fqd_device_free(int device, void* d_ptr);
 int fqd_memcpy_d2h(int device, void* dst, const void* d_src, size_t bytes);

@@ -153,3 +153,35 @@ def test_byte_keys_on_plain_bases_match_code_keys(fqd, oracle):
         a, _, sa = fqd.dedup_whole(mode, buf, None, fqd.FORMAT_FASTQ, max_seq_len=70, byte_keys=0)
         b, _, sb = fqd.dedup_whole(mode, buf, None, fqd.FORMAT_FASTQ, max_seq_len=70, byte_keys=1)
         assert a == b and (sa.total, sa.dups) == (sb.total, sb.dups)
+
+
+@pytest.mark.parametrize("mode,dist,paired", [("tight", 2, False), ("loose", 2, True), ("tail-hamming", 2, True)])
+@pytest.mark.parametrize("seg", [1 << 14, 1 << 16, 1 << 22])
+def test_adopted_device_input(fqd, oracle, mode, dist, paired, seg):
+    """fqd_adopt_device: the input is parsed in place through views cut at record boundaries (unaligned view starts,
+    views smaller than the input, a trailing incomplete record) - same output as the copying path / the oracle."""
+    kw = dict(read_len=70, var_len=True, min_len=0, n_frac=0.05, prefix_frac=0.3, sub_frac=0.3, dup_frac=0.5)
+    if paired:
+        s1, s2 = synth.make_pair(3000, seed=101, **kw)
+        bufs = [synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2) + b"@incomplete\nACGT"]
+    else:
+        bufs = [synth.to_fastq(synth.make_reads(5000, seed=102, **kw))]
+    e1, e2, est = oracle.run_oracle(mode, oracle.FASTQ, bufs[0], bufs[1] if paired else None, dist=dist)
+    eng = fqd.Engine(mode, fqd.FORMAT_FASTQ, paired, False, dist, 70, 6000, seg, 0, 0)
+    dbufs = []
+    try:
+        for m, b in enumerate(bufs):
+            d = fqd.DeviceBuffer(len(b) + 64, 0)
+            d.upload(b)
+            dbufs.append(d)
+            eng.adopt_device(m, d.ptr, len(b))
+        eng.finish()
+        st = eng.stats()
+        assert st.err == 0 and (st.total, st.dups) == (est.total, est.dups)
+        assert eng.emit_all(0, 1 << 15) == e1
+        if paired:
+            assert eng.emit_all(1, 1 << 15) == e2
+    finally:
+        eng.close()
+        for d in dbufs:
+            d.free()
