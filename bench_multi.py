@@ -35,12 +35,16 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
     eng = fqd.Engine("fast", fqd.FORMAT_FASTQ, False, False, 2, b.READ_LEN, int(n_per_rank * 1.15) + (1 << 20),
                      chunk_reads * REC + 65536, chunk_reads + 1024, dev)
     ops = sharded.GpuShardOps(fqd, eng, world, dev, chunk_reads + 1024)
+    peer = None
+    if not os.environ.get("FQD_NO_PEER"):
+        px = importlib.import_module("fastq-dupaway_b200.peer")
+        peer = px.PeerExchange(fqd, dist, rank, world, dev, int((chunk_reads + 1024) * ops.row_bytes * 1.25) + (16 << 20))
 
     def step():
         eng.reset()
         dups = 0
         for c in range(n_chunks):
-            d, _ = sharded.exchange_chunk(ops, dist, world, raw.ptr + c * chunk_reads * REC, sizes[c] * REC)
+            d, _ = sharded.exchange_chunk(ops, dist, world, raw.ptr + c * chunk_reads * REC, sizes[c] * REC, peer=peer)
             dups += d
         return dups
 
@@ -93,12 +97,15 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
                              "avg_launch_ms": k1_ms, "kernel_share_of_step": prof.parse_ms / float(ms.item()),
                              "insert_share_of_step": prof.insert_ms / float(ms.item())},
                 "exchange": {"row_bytes": row_bytes, "alltoall_bytes_per_gpu_per_step": n_per_rank * (row_bytes + 1),
-                             "collectives_per_chunk": 3},
+                             "collectives_per_chunk": 3,
+                             "rows": "mapped peer memory (CUDA IPC + copy engines)" if peer is not None else "NCCL all_to_all_single"},
                 "duplicates_removed": int(tot[0].item()), "input_GBps": n_total * REC / (ms_per_step / 1000.0) / 1e9}
         print(json.dumps(line), flush=True)
     if rank == 0 and sharded.TRACE:
         print("[fqd trace] per-phase wall clock, ms over all steps:", json.dumps({k: round(v, 2) for k, v in sharded.TRACE.items()}), file=sys.stderr)
     eng.close()
+    if peer is not None:
+        peer.close()
     raw.free()
     dist.barrier()
     dist.destroy_process_group()

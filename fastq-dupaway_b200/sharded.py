@@ -46,6 +46,11 @@ class GpuShardOps:
         self.eng._check(rc)
         return self.flags[:n]
 
+    def insert_ptr(self, recv_ptr, n):
+        rc = self.lib.fqd_shard_insert(self.eng.h, C.c_void_p(recv_ptr), n, self.world, C.c_void_p(self.flags.data_ptr()))
+        self.eng._check(rc)
+        return self.flags[:n]
+
     def apply(self, flags_back):
         d = C.c_uint64(0)
         rc = self.lib.fqd_shard_apply(self.eng.h, C.c_void_p(flags_back.data_ptr()), C.byref(d))
@@ -69,7 +74,7 @@ def _mark(name, t0):
     return t1
 
 
-def exchange_chunk(ops, dist, world, raw_ptr, nbytes, via_cpu=False, raw2_ptr=None, nbytes2=0):
+def exchange_chunk(ops, dist, world, raw_ptr, nbytes, via_cpu=False, raw2_ptr=None, nbytes2=0, peer=None):
     """One chunk through pack -> all-to-all -> insert -> all-to-all -> apply.  Returns this rank's duplicate count."""
     import time
     import torch
@@ -78,6 +83,20 @@ def exchange_chunk(ops, dist, world, raw_ptr, nbytes, via_cpu=False, raw2_ptr=No
     t = _mark("pack (K1 + owner sort + row gather)", t)
     dev = send_rows.device
     row_bytes = int(send_rows.shape[1])
+    if peer is not None:
+        # rows over mapped peer memory (fastq-dupaway_b200/peer.py): the size matrix replaces the counts all-to-all
+        rptr, rsizes = peer.exchange(send_rows.data_ptr(), [c * row_bytes for c in counts])
+        recv_counts = [b // row_bytes for b in rsizes]
+        n_recv = sum(recv_counts)
+        t = _mark("rows all-to-all", t)
+        flags = ops.insert_ptr(rptr, n_recv)
+        t = _mark("insert (append + K2)", t)
+        back = torch.empty(sum(counts), dtype=torch.uint8, device=dev)
+        dist.all_to_all_single(back, flags, counts, recv_counts)
+        t = _mark("flags all-to-all", t)
+        r = ops.apply(back), sum(counts)
+        _mark("apply", t)
+        return r
     # how many rows will every peer send me?
     cdev = torch.device("cpu") if via_cpu else dev
     c_out = torch.tensor(counts, dtype=torch.int64, device=cdev)
