@@ -190,8 +190,10 @@ static int create_impl(const fqd_config* cfg, fqd_handle* h) {
     h->sm_count = prop.multiProcessorCount;
     CUDA_TRY(h, cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CUDA_TRY(h, pp_init_tables());
-    CUDA_TRY(h, cudaFuncSetAttribute(k_parse_pack<4>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
-    CUDA_TRY(h, cudaFuncSetAttribute(k_parse_pack<2>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_parse_pack<4, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_parse_pack<2, false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_parse_pack<4, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    CUDA_TRY(h, cudaFuncSetAttribute(k_parse_pack<2, true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
 
     const int mates = cfg->paired ? 2 : 1;
     if (cfg->byte_keys && (cfg->mode == FQD_MODE_FAST || cfg->unordered))
@@ -272,9 +274,7 @@ static int launch_parse(fqd_handle* h, int m, const u8* d_raw, size_t n, u8* d_d
     p.strict = 1; p.hash_salt = m * 4096u; p.bad_rec = nullptr; p.dup = (m == 0) ? h->d_dup : nullptr; p.byte_keys = 0; p.skip = 0;
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (h->profile) { pe0 = get_event(h); pe1 = get_event(h); cudaEventRecord(pe0, h->stream); }
-    const u32 grid = n_tiles;      // one tile per CTA, processed in ticket order
-    if (h->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<grid, PP_THREADS, 0, h->stream>>>(p);
-    else k_parse_pack<2><<<grid, PP_THREADS, 0, h->stream>>>(p);
+    pp_launch(h->cfg.format == FQD_FORMAT_FASTQ, p, h->stream);
     if (h->profile) { cudaEventRecord(pe1, h->stream); h->prof_parse.emplace_back(pe0, pe1); h->prof.parse_launches++; h->prof.parse_bytes += n; }
     h->launches++;
     return FQD_OK;
@@ -568,8 +568,7 @@ static int shard_pack_impl(fqd_handle* h, const void* d_raw, size_t n, const voi
         p.row_words = h->row_words; p.mate_off = m * h->W; p.W = h->W; p.hash = c.d_hash; p.seq_len = nullptr; p.word0 = nullptr;
         p.strict = 1; p.hash_salt = m * 4096u; p.dup = nullptr; p.bad_rec = nullptr; p.byte_keys = 0; p.skip = 0;
         if (n_tiles) {
-            if (h->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
-            else k_parse_pack<2><<<n_tiles, PP_THREADS, 0, h->stream>>>(p);
+            pp_launch(h->cfg.format == FQD_FORMAT_FASTQ, p, h->stream);
         }
         if (h->profile) { h->prof.parse_launches++; h->prof.parse_bytes += nb; }
     }

@@ -186,7 +186,7 @@ enum { RS_NONE = 0, RS_OK = 1, RS_BAD_START = 2, RS_LEN_MISMATCH = 3, RS_TOO_LON
 // e0..e3 (PP_NONE = not found before the end of the chunk).  Nothing here depends on the record's index, so it can
 // run before the look-back has delivered it.  Returns RS_* | first byte << 8;
 //   qoff = window-local offset of the sequence, qlen = bases | fast-path flag << 31   (RS_OK only)
-template <int LPR>
+template <int LPR, bool BYTES>
 __device__ __forceinline__ u32 classify_record(const ParseParams& p, const u8* win, u32 base, u32 start_l,
                                                u32 e0, u32 e1, u32 e2, u32 e3, u32& qoff, u32& qlen) {
     qoff = PP_NONE; qlen = 0;
@@ -197,7 +197,7 @@ __device__ __forceinline__ u32 classify_record(const ParseParams& p, const u8* w
     if (c0 != lead) return RS_BAD_START | (c0 << 8);
     if (LPR == 4 && (e1 - e0) != (e3 - e2)) return RS_LEN_MISMATCH;
     const u32 nb = e1 - e0 - 1u;
-    const u32 room = p.byte_keys ? p.W * 8u - 1u : p.W * BASES_PER_WORD;      // byte keys include the '\n'
+    const u32 room = BYTES ? p.W * 8u - 1u : p.W * BASES_PER_WORD;            // byte keys include the '\n'
     if (nb > room) return RS_TOO_LONG;
     qoff = e0 + 1u;
     // fast path: every word of the row can be fetched from the staged window
@@ -255,11 +255,12 @@ __device__ __forceinline__ u64 pack_word_bytes(const u8* win, const ParseParams&
     return word;
 }
 
+template <bool BYTES>
 __device__ __forceinline__ u64 pack_word(const u8* win, const ParseParams& p, u32 base, u32 off, u32 ql, u32 w, u32& bad) {
     const u32 nb = ql & 0x7FFFFFFFu;
     const u32 done = w * BASES_PER_WORD;
     bad = 0;
-    if (p.byte_keys) return pack_word_bytes(win, p, base, off, ql, w);
+    if (BYTES) return pack_word_bytes(win, p, base, off, ql, w);
     if (nb <= done) return 0ull;
     u32 nvalid = min(nb - done, (u32)BASES_PER_WORD);
     u32 first = done, shift = 0;
@@ -342,7 +343,10 @@ static inline cudaError_t pp_init_tables() {
     return cudaMemcpyToSymbol(c_hkeys, h, sizeof(h));
 }
 
-template <int LPR>   // lines per record: 4 = FASTQ, 2 = FASTA
+// LPR = lines per record: 4 = FASTQ, 2 = FASTA.  BYTES = raw-byte key rows (ParseParams::byte_keys; sequence-based
+// modes on arbitrary alphabets) - a template parameter so that the 3-bit instantiation every other path uses carries
+// none of its code or registers.
+template <int LPR, bool BYTES = false>
 __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const ParseParams p) {
     __shared__ __align__(128) u8 win[PP_WINDOW];
     __shared__ __align__(16) u64 mask64[PP_NW];
@@ -585,7 +589,7 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                             e[k] = from == PP_NONE ? PP_NONE : find_nl(mask64, max(from, PP_WINDOW), p.raw, base, p.n);
                         }
                     }
-                    status = classify_record<LPR>(p, win, base, start_l, e[0], e[1], LPR == 4 ? e[2] : e[1],
+                    status = classify_record<LPR, BYTES>(p, win, base, start_l, e[0], e[1], LPR == 4 ? e[2] : e[1],
                                                   LPR == 4 ? e[3] : e[1], qoff, qlen);
                 }
                 q_off[wtid] = qoff;
@@ -608,8 +612,8 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                     const u32 w = 2u * l4;
                     if (w < p.W) {
                         u32 bad_b;
-                        wa = pack_word(win, p, base, off, ql, w, bad);
-                        wb = pack_word(win, p, base, off, ql, w + 1u, bad_b);
+                        wa = pack_word<BYTES>(win, p, base, off, ql, w, bad);
+                        wb = pack_word<BYTES>(win, p, base, off, ql, w + 1u, bad_b);
                         if (!bad) bad = bad_b;
                         hsum = word_hash(wa, s_hkey[w]) + word_hash(wb, s_hkey[w + 1u]);
                     }
@@ -633,8 +637,8 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                     } else {
                         for (u32 w = 2u * l4; w < p.W; w += 2u * PP_GROUP) {
                             u32 bad_a, bad_b;
-                            const u64 xa = pack_word(win, p, base, off, ql, w, bad_a);
-                            const u64 xb = pack_word(win, p, base, off, ql, w + 1u, bad_b);
+                            const u64 xa = pack_word<BYTES>(win, p, base, off, ql, w, bad_a);
+                            const u64 xb = pack_word<BYTES>(win, p, base, off, ql, w + 1u, bad_b);
                             *reinterpret_cast<ulonglong2*>(row + w) = make_ulonglong2(xa, xb);
                             if (w == 0) w0 = xa;
                             if (!bad) bad = bad_a ? bad_a : bad_b;
@@ -690,7 +694,7 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                         e2 = e1 == PP_NONE ? PP_NONE : find_nl(mask64, e1 + 1u, p.raw, base, p.n);
                         e3 = e2 == PP_NONE ? PP_NONE : find_nl(mask64, e2 + 1u, p.raw, base, p.n);
                     }
-                    status = classify_record<LPR>(p, win, base, start_l, e0, e1, e2, e3, qoff, qlen);
+                    status = classify_record<LPR, BYTES>(p, win, base, start_l, e0, e1, e2, e3, qoff, qlen);
                 }
                 commit_record(p, slot_base, R, gstart, status);
                 q_off[o - rbase] = qoff;
@@ -708,8 +712,8 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                 u32 bad = 0;
                 for (u32 w = 2u * l4; w < p.W; w += 2u * PP_GROUP) {
                     u32 bad_a, bad_b;
-                    const u64 xa = pack_word(win, p, base, off, ql, w, bad_a);
-                    const u64 xb = pack_word(win, p, base, off, ql, w + 1u, bad_b);
+                    const u64 xa = pack_word<BYTES>(win, p, base, off, ql, w, bad_a);
+                    const u64 xb = pack_word<BYTES>(win, p, base, off, ql, w + 1u, bad_b);
                     *reinterpret_cast<ulonglong2*>(row + w) = make_ulonglong2(xa, xb);
                     if (w == 0) w0 = xa;
                     if (!bad) bad = bad_a ? bad_a : bad_b;
@@ -721,6 +725,18 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
             }
             __syncthreads();
         }
+    }
+}
+
+// one ticket (CTA) per tile
+static inline void pp_launch(bool fastq, const ParseParams& p, cudaStream_t stream) {
+    if (p.n_tiles == 0) return;
+    if (p.byte_keys) {
+        if (fastq) k_parse_pack<4, true><<<p.n_tiles, PP_THREADS, 0, stream>>>(p);
+        else k_parse_pack<2, true><<<p.n_tiles, PP_THREADS, 0, stream>>>(p);
+    } else {
+        if (fastq) k_parse_pack<4, false><<<p.n_tiles, PP_THREADS, 0, stream>>>(p);
+        else k_parse_pack<2, false><<<p.n_tiles, PP_THREADS, 0, stream>>>(p);
     }
 }
 

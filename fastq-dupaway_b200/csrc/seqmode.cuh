@@ -714,8 +714,7 @@ static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
     p.word0 = nullptr; p.dup = nullptr; p.strict = 0; p.hash_salt = m * 4096u; p.bad_rec = nullptr;
     p.byte_keys = s->cfg.byte_keys ? 1u : 0u; p.skip = sg.skip;
     if (s->cfg.unordered) { p.hash = mt.d_hash + mt.n_records; p.bad_rec = mt.d_bad + mt.n_records; }
-    if (s->cfg.format == FQD_FORMAT_FASTQ) k_parse_pack<4><<<n_tiles, PP_THREADS, 0, s->stream>>>(p);
-    else k_parse_pack<2><<<n_tiles, PP_THREADS, 0, s->stream>>>(p);
+    pp_launch(s->cfg.format == FQD_FORMAT_FASTQ, p, s->stream);
     if (s->cfg.unordered) {
         k_extract_tags<<<s->sm * 8, 128, 0, s->stream>>>(sg.d, s->d_rec_start, s->d_ctl, s->TW, mt.d_tags + mt.n_records * s->TW, s->d_ctl);
         s->launches++;
