@@ -185,3 +185,54 @@ def test_adopted_device_input(fqd, oracle, mode, dist, paired, seg):
         eng.close()
         for d in dbufs:
             d.free()
+
+
+def test_large_cross_mode_properties(fqd):
+    """Size-independent properties at 3 M pairs (the oracle would need minutes): on a stream whose duplicates are exact
+    copies of both mates, --compare-seq tight and --fast remove the same number of pairs (different representatives
+    and output order, same count); loose and tail-hamming (d = 2) can only remove more on the same data; tight is
+    idempotent (its own output holds no duplicates); the sorted output really is sorted."""
+    lib = fqd.load_library()
+    n, L = 3_000_000, 150
+    rb = lib.fqd_synth_record_bytes(L)
+    raw = [fqd.DeviceBuffer(n * rb + 4096) for _ in range(2)]
+    for m in range(2):
+        assert lib.fqd_synth_fastq(0, raw[m].ptr, 0, n, L, m + 1, 7, 300, 1, 0) == 0
+    fast = fqd.Engine("fast", fqd.FORMAT_FASTQ, True, False, 2, L, n + 16, n * rb + 4096, n + 16, 0)
+    res = fast.push_device(raw[0].ptr, n * rb, raw[1].ptr, n * rb)
+    fast_dups = n - res.n_survivors
+    fast.close()
+    assert 0.25 < fast_dups / n < 0.35
+    dups = {}
+    for mode in ("tight", "loose", "tail-hamming"):
+        eng = fqd.Engine(mode, fqd.FORMAT_FASTQ, True, False, 2, L, n + 16, 1 << 28, 0, 0)
+        for m in range(2):
+            eng.adopt_device(m, raw[m].ptr, n * rb)
+        eng.finish()
+        st = eng.stats()
+        assert st.err == 0 and st.total == n
+        dups[mode] = st.dups
+        if mode == "tight":
+            outs = [eng.emit_all(m, 1 << 26) for m in range(2)]
+        eng.close()
+    assert dups["tight"] == fast_dups
+    assert dups["loose"] >= dups["tight"] and dups["tail-hamming"] >= dups["tight"]
+    # the tight output: sorted by (R1 sequence, R2 sequence), no two equal neighbours; a second pass removes nothing
+    seq1 = np.frombuffer(outs[0], dtype=np.uint8).reshape(-1, rb)[:, 18:18 + L]
+    seq2 = np.frombuffer(outs[1], dtype=np.uint8).reshape(-1, rb)[:, 18:18 + L]
+    assert seq1.shape[0] == n - dups["tight"]
+    key = np.concatenate([seq1, seq2], axis=1)
+    a, b = key[:-1], key[1:]
+    neq = a != b
+    first = neq.argmax(axis=1)
+    assert neq.any(axis=1).all()                                   # no equal neighbours
+    rows = np.arange(len(first))
+    assert (a[rows, first] < b[rows, first]).all()                 # strictly increasing: byte order with N between G and T
+    eng = fqd.Engine("tight", fqd.FORMAT_FASTQ, True, False, 2, L, n + 16, 1 << 28, 0, 0)
+    eng.append(0, outs[0]); eng.append(1, outs[1])
+    eng.finish()
+    st = eng.stats()
+    assert st.err == 0 and st.dups == 0 and st.total == n - dups["tight"]
+    eng.close()
+    for d in raw:
+        d.free()
