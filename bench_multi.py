@@ -36,15 +36,29 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
                      chunk_reads * REC + 65536, chunk_reads + 1024, dev)
     ops = sharded.GpuShardOps(fqd, eng, world, dev, chunk_reads + 1024)
     peer = None
+    packers, peers2 = None, None
+    pipelined = not os.environ.get("FQD_NO_PEER") and not os.environ.get("FQD_NO_PIPELINE")
     if not os.environ.get("FQD_NO_PEER"):
         px = importlib.import_module("fastq-dupaway_b200.peer")
-        peer = px.PeerExchange(fqd, dist, rank, world, dev, int((chunk_reads + 1024) * ops.row_bytes * 1.25) + (16 << 20))
+        cap = int((chunk_reads + 1024) * ops.row_bytes * 1.25) + (16 << 20)
+        if pipelined:
+            # two pack-only engines on their own streams work one chunk ahead of the exchange; two receive buffers
+            peers2 = [px.PeerExchange(fqd, dist, rank, world, dev, cap) for _ in range(2)]
+            pengs = [fqd.Engine("fast", fqd.FORMAT_FASTQ, False, False, 2, b.READ_LEN, 1 << 16, chunk_reads * REC + 65536,
+                                chunk_reads + 1024, dev) for _ in range(2)]
+            packers = [sharded.GpuShardOps(fqd, e, world, dev, chunk_reads + 1024, own_stream=True) for e in pengs]
+            ops.pack(raw.ptr, 0)                      # sets the main engine up for fqd_shard_insert
+        else:
+            peer = px.PeerExchange(fqd, dist, rank, world, dev, cap)
+    chunks = [(raw.ptr + c * chunk_reads * REC, sizes[c] * REC) for c in range(n_chunks)]
 
     def step():
         eng.reset()
+        if pipelined:
+            return sharded.exchange_pipelined(packers, ops, dist, world, chunks, peers2)
         dups = 0
         for c in range(n_chunks):
-            d, _ = sharded.exchange_chunk(ops, dist, world, raw.ptr + c * chunk_reads * REC, sizes[c] * REC, peer=peer)
+            d, _ = sharded.exchange_chunk(ops, dist, world, chunks[c][0], chunks[c][1], peer=peer)
             dups += d
         return dups
 
@@ -56,7 +70,12 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
     if rank == 0:
         sampler.start()
     eng.profile_enable(True)
+    if pipelined:
+        for e in pengs:
+            e.profile_enable(True)
     _, l0 = eng.device_time_ms()
+    if pipelined:
+        l0 += sum(e.device_time_ms()[1] for e in pengs)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     torch.cuda.synchronize()
     dist.barrier()
@@ -72,7 +91,13 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
     tot = torch.tensor([dups, n_per_rank], dtype=torch.int64, device=f"cuda:{dev}")
     dist.all_reduce(tot, op=dist.ReduceOp.SUM)
     _, l1 = eng.device_time_ms()
+    if pipelined:
+        l1 += sum(e.device_time_ms()[1] for e in pengs)
     prof = eng.profile()
+    if pipelined:                                     # K1 runs on the pack engines, K2 on the main one
+        for e in pengs:
+            pp = e.profile()
+            prof.parse_ms += pp.parse_ms; prof.parse_launches += pp.parse_launches; prof.parse_bytes += pp.parse_bytes
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join()
@@ -98,7 +123,8 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
                              "insert_share_of_step": prof.insert_ms / float(ms.item())},
                 "exchange": {"row_bytes": row_bytes, "alltoall_bytes_per_gpu_per_step": n_per_rank * (row_bytes + 1),
                              "collectives_per_chunk": 3,
-                             "rows": "mapped peer memory (CUDA IPC + copy engines)" if peer is not None else "NCCL all_to_all_single"},
+                             "rows": ("mapped peer memory (CUDA IPC + copy engines), overlapped with the split + pack of the next chunk" if pipelined
+                                      else "mapped peer memory (CUDA IPC + copy engines)" if peer is not None else "NCCL all_to_all_single")},
                 "duplicates_removed": int(tot[0].item()), "input_GBps": n_total * REC / (ms_per_step / 1000.0) / 1e9}
         print(json.dumps(line), flush=True)
     if rank == 0 and sharded.TRACE:
@@ -106,6 +132,11 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
     eng.close()
     if peer is not None:
         peer.close()
+    if pipelined:
+        for e in pengs:
+            e.close()
+        for p_ in peers2:
+            p_.close()
     raw.free()
     dist.barrier()
     dist.destroy_process_group()

@@ -36,16 +36,16 @@ class PeerExchange:
         self.streams = [torch.cuda.Stream(device=tdev) for _ in range(world)]     # one per destination: the copies overlap
         dist.barrier()
 
-    def exchange(self, send_ptr, send_sizes):
-        """send_sizes[p] bytes (contiguous, in rank order, starting at send_ptr) go to rank p.
-        Returns (device pointer of this rank's receive buffer, [bytes received from every source])."""
+    def start(self, send_ptr, send_sizes):
+        """send_sizes[p] bytes (contiguous, in rank order, starting at send_ptr) go to rank p.  Returns after the copies
+        have been enqueued; the bytes received from every source are known already (finish() tells when they landed)."""
         torch, dist = self.torch, self.dist
         row = torch.tensor(send_sizes, dtype=torch.int64, device=self.tdev)
         mat = [torch.empty_like(row) for _ in range(self.world)]
         dist.all_gather(mat, row)                          # mat[src][dst]; doubles as the "buffers are free" barrier
         sizes = [[int(x) for x in m.tolist()] for m in mat]
         recv_sizes = [sizes[src][self.rank] for src in range(self.world)]
-        if sum(recv_sizes) > self.cap or any(sum(sizes[s][d] for s in range(self.world)) > self.cap for d in range(self.world)):
+        if any(sum(sizes[s][d] for s in range(self.world)) > self.cap for d in range(self.world)):
             raise MemoryError("peer exchange: a receive buffer is too small")
         torch.cuda.synchronize(self.tdev)                 # the send buffer is complete
         for k in range(self.world):
@@ -55,9 +55,18 @@ class PeerExchange:
             n = send_sizes[dst]
             assert self.lib.fqd_peer_copy_async(self.dev, C.c_void_p(self.peer[dst] + dst_off), C.c_void_p(send_ptr + src_off), n,
                                                 C.c_void_p(self.streams[k].cuda_stream)) == 0
-        torch.cuda.synchronize(self.tdev)
-        dist.barrier()                                     # every peer's writes into my buffer have landed
         return self.buf.ptr, recv_sizes
+
+    def finish(self):
+        for st in self.streams:
+            st.synchronize()
+        self.dist.barrier()                                # every peer's writes into my buffer have landed
+
+    def exchange(self, send_ptr, send_sizes):
+        """start + finish.  Returns (device pointer of this rank's receive buffer, [bytes received from every source])."""
+        r = self.start(send_ptr, send_sizes)
+        self.finish()
+        return r
 
     def close(self):
         for r, p in enumerate(self.peer):

@@ -17,7 +17,7 @@ import ctypes as C
 class GpuShardOps:
     """pack / insert / apply on one GPU through the C ABI; buffers are torch tensors on that GPU."""
 
-    def __init__(self, pkg, engine, world, device, max_rows):
+    def __init__(self, pkg, engine, world, device, max_rows, own_stream=False):
         import torch
         self.torch = torch
         self.pkg, self.eng, self.world = pkg, engine, world
@@ -26,7 +26,9 @@ class GpuShardOps:
         self.row_bytes = int(self.lib.fqd_shard_row_bytes(engine.h))
         self.send = torch.empty((max_rows, self.row_bytes), dtype=torch.uint8, device=self.dev)
         self.flags = torch.empty(2 * max_rows, dtype=torch.uint8, device=self.dev)
-        rc = self.lib.fqd_set_stream(engine.h, C.c_void_p(torch.cuda.current_stream(self.dev).cuda_stream))
+        # own_stream: a packer that works ahead of the exchange (exchange_pipelined) must not queue behind it
+        self.stream = torch.cuda.Stream(device=self.dev) if own_stream else torch.cuda.current_stream(self.dev)
+        rc = self.lib.fqd_set_stream(engine.h, C.c_void_p(self.stream.cuda_stream))
         assert rc == 0
 
     def pack(self, raw_ptr, nbytes, raw2_ptr=None, nbytes2=0):
@@ -131,3 +133,32 @@ def exchange_chunk(ops, dist, world, raw_ptr, nbytes, via_cpu=False, raw2_ptr=No
     r = ops.apply(back), sum(counts)
     _mark("apply", t)
     return r
+
+
+def exchange_pipelined(packers, main, dist, world, chunks, peers):
+    """All chunks of one job with the exchange of chunk c overlapping the split + pack of chunk c + 1.
+    packers: two GpuShardOps on pack-only engines with their own streams (they alternate); main: the GpuShardOps of the
+    engine that owns this rank's hash set; peers: two PeerExchange (alternating receive buffers); chunks: [(ptr, nbytes)].
+    The copy engines move chunk c's key rows into the owners' buffers while the SMs split chunk c + 1.  Returns dups."""
+    import torch
+    n = len(chunks)
+    if n == 0:
+        return 0
+    dev = main.dev
+    dups = 0
+    send, counts = packers[0].pack(*chunks[0])
+    for c in range(n):
+        pk, px = packers[c % 2], peers[c % 2]
+        rb = pk.row_bytes
+        rptr, rsizes = px.start(send.data_ptr(), [k * rb for k in counts])
+        cur_counts = counts
+        if c + 1 < n:
+            send, counts = packers[(c + 1) % 2].pack(*chunks[c + 1])      # K1 of the next chunk runs under the copies
+        px.finish()
+        recv_counts = [b // rb for b in rsizes]
+        flags = main.insert_ptr(rptr, sum(recv_counts))
+        back = torch.empty(sum(cur_counts), dtype=torch.uint8, device=dev)
+        dist.all_to_all_single(back, flags, cur_counts, recv_counts)
+        torch.cuda.current_stream(dev).synchronize()
+        dups += pk.apply(back)
+    return dups
