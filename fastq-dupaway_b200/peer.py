@@ -20,7 +20,9 @@ class PeerExchange:
         handle = C.create_string_buffer(64)
         assert self.lib.fqd_ipc_export(device, C.c_void_p(self.buf.ptr), handle) == 0
         tdev = torch.device("cuda", device)
-        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(tdev)
+        # control messages (handles, size matrix) travel on the device with NCCL, on the host with gloo (tests)
+        self.cdev = torch.device("cpu") if dist.get_backend() == "gloo" else tdev
+        mine = torch.frombuffer(bytearray(handle.raw), dtype=torch.uint8).to(self.cdev)
         allh = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(allh, mine)
         self.peer = []
@@ -40,7 +42,7 @@ class PeerExchange:
         """send_sizes[p] bytes (contiguous, in rank order, starting at send_ptr) go to rank p.  Returns after the copies
         have been enqueued; the bytes received from every source are known already (finish() tells when they landed)."""
         torch, dist = self.torch, self.dist
-        row = torch.tensor(send_sizes, dtype=torch.int64, device=self.tdev)
+        row = torch.tensor(send_sizes, dtype=torch.int64, device=self.cdev)
         mat = [torch.empty_like(row) for _ in range(self.world)]
         dist.all_gather(mat, row)                          # mat[src][dst]; doubles as the "buffers are free" barrier
         sizes = [[int(x) for x in m.tolist()] for m in mat]

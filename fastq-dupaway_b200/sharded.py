@@ -53,6 +53,12 @@ class GpuShardOps:
         self.eng._check(rc)
         return self.flags[:n]
 
+    def read_flags(self, n):
+        """duplicate flags of the chunk last applied on this engine (host copy)"""
+        out = C.create_string_buffer(int(n))
+        assert self.lib.fqd_shard_read_flags(self.eng.h, out, int(n)) == 0
+        return out.raw
+
     def apply(self, flags_back):
         d = C.c_uint64(0)
         rc = self.lib.fqd_shard_apply(self.eng.h, C.c_void_p(flags_back.data_ptr()), C.byref(d))
@@ -135,7 +141,7 @@ def exchange_chunk(ops, dist, world, raw_ptr, nbytes, via_cpu=False, raw2_ptr=No
     return r
 
 
-def exchange_pipelined(packers, main, dist, world, chunks, peers):
+def exchange_pipelined(packers, main, dist, world, chunks, peers, via_cpu=False, flags_out=None):
     """All chunks of one job with the exchange of chunk c overlapping the split + pack of chunk c + 1.
     packers: two GpuShardOps on pack-only engines with their own streams (they alternate); main: the GpuShardOps of the
     engine that owns this rank's hash set; peers: two PeerExchange (alternating receive buffers); chunks: [(ptr, nbytes)].
@@ -157,8 +163,15 @@ def exchange_pipelined(packers, main, dist, world, chunks, peers):
         px.finish()
         recv_counts = [b // rb for b in rsizes]
         flags = main.insert_ptr(rptr, sum(recv_counts))
-        back = torch.empty(sum(cur_counts), dtype=torch.uint8, device=dev)
-        dist.all_to_all_single(back, flags, cur_counts, recv_counts)
+        if via_cpu:                                   # gloo ranks sharing one GPU (tests)
+            b_h = torch.empty(sum(cur_counts), dtype=torch.uint8)
+            dist.all_to_all_single(b_h, flags.cpu(), cur_counts, recv_counts)
+            back = b_h.to(dev)
+        else:
+            back = torch.empty(sum(cur_counts), dtype=torch.uint8, device=dev)
+            dist.all_to_all_single(back, flags, cur_counts, recv_counts)
         torch.cuda.current_stream(dev).synchronize()
         dups += pk.apply(back)
+        if flags_out is not None:                     # per-record duplicate flags of this chunk, in input order
+            flags_out.append(pk.read_flags(sum(cur_counts)))
     return dups

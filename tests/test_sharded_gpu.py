@@ -105,3 +105,60 @@ def test_two_ranks_one_gpu_paired(tmp_path, oracle):
             lo = (c * world + r) * per_chunk
             got[lo: lo + per_chunk] = f[c * per_chunk: (c + 1) * per_chunk]
     assert np.array_equal(got, exp)
+
+
+def _worker_pipelined(rank, world, port, chunks, result_dir):
+    sys.path.insert(0, str(ROOT))
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fqd = importlib.import_module("fastq-dupaway_b200")
+    sharded = importlib.import_module("fastq-dupaway_b200.sharded")
+    peer = importlib.import_module("fastq-dupaway_b200.peer")
+    torch.cuda.set_device(0)
+    mine = chunks[rank]
+    maxb = max(len(c) for c in mine) + 4096
+    main_eng = fqd.Engine("fast", fqd.FORMAT_FASTQ, False, False, 2, 100, 200000, maxb, 50000, 0)
+    main = sharded.GpuShardOps(fqd, main_eng, world, 0, 50000)
+    pengs = [fqd.Engine("fast", fqd.FORMAT_FASTQ, False, False, 2, 100, 1024, maxb, 50000, 0) for _ in range(2)]
+    packers = [sharded.GpuShardOps(fqd, e, world, 0, 50000, own_stream=True) for e in pengs]
+    peers = [peer.PeerExchange(fqd, dist, rank, world, 0, 50000 * main.row_bytes) for _ in range(2)]
+    bufs = []
+    for c in mine:
+        b = fqd.DeviceBuffer(len(c) + 64, 0)
+        b.upload(c)
+        bufs.append(b)
+    main.pack(bufs[0].ptr, 0)                 # sets the main engine up for fqd_shard_insert
+    flags = []
+    dups = sharded.exchange_pipelined(packers, main, dist, world, [(b.ptr, len(c)) for b, c in zip(bufs, mine)], peers,
+                                      via_cpu=True, flags_out=flags)
+    got = np.concatenate([np.frombuffer(f, dtype=np.uint8) for f in flags])
+    assert int(got.sum()) == dups
+    np.save(Path(result_dir) / f"flags_{rank}.npy", got)
+    dist.barrier()
+    for p_ in peers:
+        p_.close()
+    for e in pengs + [main_eng]:
+        e.close()
+    dist.destroy_process_group()
+
+
+def test_two_ranks_one_gpu_pipelined_peer_memory(tmp_path, oracle):
+    """The pipelined exchange (pack-only engines one chunk ahead, key rows over mapped peer memory): per-record duplicate
+    flags against the oracle's decision on the global stream."""
+    world, n_chunks, per_chunk = 2, 4, 3000
+    seqs = synth.make_reads(world * n_chunks * per_chunk, seed=53, read_len=100, var_len=True, n_frac=0.02, dup_frac=0.4)
+    recs = [synth.to_fastq([s], ids=[b"@g.%d" % i]) for i, s in enumerate(seqs)]
+    chunks = [[b"".join(recs[(c * world + r) * per_chunk: (c * world + r + 1) * per_chunk]) for c in range(n_chunks)] for r in range(world)]
+    port = 29800 + (os.getpid() % 2000)
+    mp.spawn(_worker_pipelined, args=(world, port, chunks, str(tmp_path)), nprocs=world, join=True)
+    keep_idx, est = oracle.fast_se(b"".join(recs), oracle.FASTQ)
+    exp = np.ones(len(recs), dtype=np.uint8)
+    exp[keep_idx.astype(np.int64)] = 0
+    got = np.zeros(len(recs), dtype=np.uint8)
+    for r in range(world):
+        f = np.load(tmp_path / f"flags_{r}.npy")
+        for c in range(n_chunks):
+            lo = (c * world + r) * per_chunk
+            got[lo: lo + per_chunk] = f[c * per_chunk: (c + 1) * per_chunk]
+    assert np.array_equal(got, exp)
