@@ -18,7 +18,7 @@ pytestmark = pytest.mark.gpu
 ROOT = Path(__file__).resolve().parent.parent
 
 
-def _worker(rank, world, port, mode, dval, fmt_name, slices, result_dir):
+def _worker(rank, world, port, mode, dval, fmt_name, slices, result_dir, use_peer=False):
     sys.path.insert(0, str(ROOT))
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
@@ -39,7 +39,11 @@ def _worker(rank, world, port, mode, dval, fmt_name, slices, result_dir):
             d.free()
     n_local_expected = mine[0].count(b"\n") // (4 if fmt_name == "fastq" else 2)
     st0 = None
-    owned, kept, dups = sh.dedup_ranges(ops, dist, rank, world, n_samples=256, via_cpu=True)
+    peers = None
+    if use_peer:          # records over mapped peer memory, parsed in place where they land (fqd_adopt_device)
+        px = importlib.import_module("fastq-dupaway_b200.peer")
+        peers = [px.PeerExchange(fqd, dist, rank, world, 0, 1 << 20) for _ in mine]
+    owned, kept, dups = sh.dedup_ranges(ops, dist, rank, world, n_samples=256, via_cpu=True, peer=peers)
     st0 = ops.origin.stats()
     assert ops.origin.partition_sample(1)[1] == n_local_expected, (
         "origin parse", rank, ops.origin.partition_sample(1)[1], n_local_expected, st0.err, st0.err_record, st0.err_char, st0.err_mate,
@@ -49,17 +53,20 @@ def _worker(rank, world, port, mode, dval, fmt_name, slices, result_dir):
     (Path(result_dir) / f"cnt_{rank}.txt").write_text(f"{owned} {kept} {dups}")
     dist.barrier()
     ops.close()
+    if peers:
+        for p_ in peers:
+            p_.close()
     dist.destroy_process_group()
 
 
-def _run(tmp_path, oracle, mode, dval, fmt_name, b1, b2, world, cuts):
+def _run(tmp_path, oracle, mode, dval, fmt_name, b1, b2, world, cuts, use_peer=False):
     """cuts: record-aligned byte offsets that split the input into `world` contiguous slices"""
     bufs = [b1] if b2 is None else [b1, b2]
     slices = []
     for r in range(world):
         slices.append([b[c[r]: c[r + 1]] for b, c in zip(bufs, cuts)])
     port = 29900 + (os.getpid() % 2000)
-    mp.spawn(_worker, args=(world, port, mode, dval, fmt_name, slices, str(tmp_path)), nprocs=world, join=True)
+    mp.spawn(_worker, args=(world, port, mode, dval, fmt_name, slices, str(tmp_path), use_peer), nprocs=world, join=True)
     fmt = oracle.FASTQ if fmt_name == "fastq" else oracle.FASTA
     e1, e2, est = oracle.run_oracle(mode, fmt, b1, b2, dist=dval)
     got = [b"".join((tmp_path / f"out_{r}_{m}.bin").read_bytes() for r in range(world)) for m in range(len(bufs))]
@@ -109,3 +116,12 @@ def test_identical_reads_and_an_empty_range(tmp_path, oracle):
     recs = [synth.to_fastq([b"ACGTACGTACGTACGTACGTAAAA"], ids=[b"@x.%d" % i]) for i in range(500)]
     cnt = _run(tmp_path, oracle, "tail-hamming", 2, "fastq", b"".join(recs), None, 3, [_cuts(recs, 3)])
     assert sorted(c[0] for c in cnt) == [0, 0, 500]
+
+
+@pytest.mark.parametrize("mode,dval", [("loose", 2), ("tail-hamming", 2)])
+def test_three_ranks_paired_over_peer_memory(tmp_path, oracle, mode, dval):
+    """Same as above with the production exchange: CUDA IPC receive buffers, copy-engine writes, records parsed in place."""
+    s1, s2 = synth.make_pair(6000, seed=63, read_len=20, var_len=True, min_len=4, dup_frac=0.5, prefix_frac=0.3, sub_frac=0.3, alphabet=b"AC")
+    r1 = [synth.to_fastq([s], ids=[b"@p.%d 1" % i]) for i, s in enumerate(s1)]
+    r2 = [synth.to_fastq([s], ids=[b"@p.%d 2" % i]) for i, s in enumerate(s2)]
+    _run(tmp_path, oracle, mode, dval, "fastq", b"".join(r1), b"".join(r2), 3, [_cuts(r1, 3), _cuts(r2, 3)], use_peer=True)
