@@ -69,7 +69,7 @@ class ClockSampler(threading.Thread):
                     self.samples.append([t.strip() for t in out.split(",")])
             except Exception:
                 pass
-            self.stop_flag.wait(0.2)
+            self.stop_flag.wait(0.02)
 
     def summary(self):
         sm = sorted(int(float(s[1])) for s in self.samples if len(s) > 2 and s[1].replace(".", "").isdigit())

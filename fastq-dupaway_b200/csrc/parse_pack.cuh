@@ -7,14 +7,17 @@
 // One CTA handles one 16 KiB tile (+1 KiB halo) staged in shared memory by a 1-D bulk async copy (TMA);
 // tiles are taken in ticket order so that every predecessor of a tile is already running.
 //   1. newline bitmask of the window (SIMD-in-register byte compare, dp4a gathers the flags)
-//   2. block scan of per-thread newline counts -> local rank of every '\n'; positions compacted by rank into
-//      shared memory; decoupled look-back across tiles (128 predecessors per hop) -> global rank of the tile's
-//      first newline.  The rank modulo lines-per-record says which newline ends a record (the reference, too,
-//      simply counts 4 (2) newlines per record).
-//   3. one thread per record owned by the tile (its first byte lies in the tile): line ends = consecutive
-//      entries of the compacted positions; validation; queue (sequence offset, length)
-//   4. groups of 8 lanes pack one queued sequence each into 3-bit codes (20 bases per 64-bit word, see
-//      common.cuh), write the key row with coalesced 64-bit stores and reduce the multilinear key hash.
+//   2. block scan of per-thread newline counts -> local rank of every '\n'; the tile's count is published; positions
+//      are compacted by rank into shared memory
+//   3. warp 0: decoupled look-back across tiles (128 predecessors per hop) -> global rank P of the tile's first
+//      newline.  P modulo lines-per-record says which newline ends a record (the reference, too, simply counts 4 (2)
+//      newlines per record), P / lines-per-record is the index of the tile's first record.
+//   4. warps 1..7 do not wait for it: they guess P mod lines-per-record from the first bytes of the tile's lines, one
+//      thread per record owned by the tile (its first byte lies in the tile) derives its line ends from consecutive
+//      entries of the compacted positions and validates it, and groups of 4 lanes pack one sequence each into 3-bit
+//      codes (20 bases per 64-bit word, see common.cuh; or raw bytes, 8 per word: template parameter BYTES) in
+//      registers.  When P arrives the guess is verified (a wrong guess repeats the round) and everything is committed:
+//      record offsets, errors, 128-bit row stores, the multilinear key hash.
 #pragma once
 #include "common.cuh"
 

@@ -39,8 +39,8 @@ typedef enum {
     FQD_ERR_CAPACITY = 7,       /* record / key-store / table capacity exceeded                          */
     FQD_ERR_SEQ_TOO_LONG = 8,   /* sequence longer than fqd_config.max_seq_len                           */
     FQD_ERR_TAG_TOO_LONG = 10,  /* --unordered: an ID tag is longer than fqd_config.max_tag_len          */
-    FQD_ERR_UNSUPPORTED_BYTE = 9 /* sequence mode: a sequence byte outside {A,C,G,T,N}; the packed-key path does
-                                    not order arbitrary bytes yet (the reference accepts any byte there)   */
+    FQD_ERR_UNSUPPORTED_BYTE = 9 /* sequence mode with 3-bit rows: a sequence byte outside {A,C,G,T,N}; run the job again
+                                    with fqd_config.byte_keys = 1 (the reference orders any byte there)       */
 } fqd_status;
 
 typedef enum { FQD_FORMAT_FASTQ = 0, FQD_FORMAT_FASTA = 1 } fqd_format;      /* --format           src/main.cpp:111-120 */
