@@ -302,11 +302,19 @@ def e2e_run(args, fqd, lib, eng, raw, n_total, chunk_reads, dups_expected):
             eng.reset()
             surv = 0
             d2h = 0
-            for c in range(n_chunks):
+            def span(c):
                 first = c * chunk
-                cnt = min(chunk, n_e2e - first)
+                return first, min(chunk, n_e2e - first)
+            # fqd_push split in two: the H2D copy of chunk c+1 runs while chunk c is processed and its results come back
+            f0, c0 = span(0)
+            assert lib.fqd_push_prefetch(eng.h, C.c_void_p(host.value + f0 * REC_BYTES), c0 * REC_BYTES, None, 0) == 0
+            for c in range(n_chunks):
+                first, cnt = span(c)
+                if c + 1 < n_chunks:
+                    f1, c1 = span(c + 1)
+                    assert lib.fqd_push_prefetch(eng.h, C.c_void_p(host.value + f1 * REC_BYTES), c1 * REC_BYTES, None, 0) == 0
                 res = fqd.ChunkResult()
-                rc2 = lib.fqd_push(eng.h, C.c_void_p(host.value + first * REC_BYTES), cnt * REC_BYTES, None, 0, C.byref(res))
+                rc2 = lib.fqd_push_staged(eng.h, C.byref(res))
                 assert rc2 == 0 and res.n_records == cnt
                 surv += res.n_survivors
                 d2h += (cnt + 1) * 4 + cnt + 64
@@ -322,7 +330,8 @@ def e2e_run(args, fqd, lib, eng, raw, n_total, chunk_reads, dups_expected):
             assert n_e2e - surv == dups_expected
         return {"value": n_e2e / dt, "unit": UNIT, "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": d2h,
                 "reads_per_step": n_e2e, "ms_per_step": dt * 1000.0, "steps": steps,
-                "path": "fqd_push (pinned host FASTQ -> H2D -> kernels -> D2H of record offsets + duplicate flags), wall clock"}
+                "path": "fqd_push_prefetch / fqd_push_staged (pinned host FASTQ -> H2D of chunk c+1 overlapping kernels + D2H of record "
+                        "offsets + duplicate flags of chunk c), wall clock"}
     finally:
         lib.fqd_host_free(host)
 

@@ -95,6 +95,8 @@ def load_library():
     lib.fqd_host_alloc.argtypes = [C.POINTER(vp), sz]
     lib.fqd_host_free.argtypes = [vp]
     lib.fqd_push.argtypes = [vp, vp, sz, vp, sz, C.POINTER(ChunkResult)]
+    lib.fqd_push_prefetch.argtypes = [vp, vp, sz, vp, sz]
+    lib.fqd_push_staged.argtypes = [vp, C.POINTER(ChunkResult)]
     lib.fqd_push_device.argtypes = [vp, vp, sz, vp, sz, C.POINTER(ChunkResult)]
     lib.fqd_push_device_async.argtypes = [vp, vp, sz, vp, sz]
     lib.fqd_sync.argtypes = [vp]

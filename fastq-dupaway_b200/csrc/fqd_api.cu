@@ -57,6 +57,13 @@ struct fqd_handle {
     double device_ms = 0.0;
     u64 launches = 0;
     bool pending_async = false;
+    // fqd_push_prefetch / fqd_push_staged: the next chunk's host-to-device copy runs on its own stream into the
+    // alternate raw buffers while the current chunk is being processed
+    u8* d_raw_alt[2] = {nullptr, nullptr};
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t copy_done[2] = {nullptr, nullptr};
+    size_t staged_n[2][2] = {{0, 0}, {0, 0}};      // [slot][mate]
+    int pf_slot = 0, run_slot = 0, n_staged = 0;
     cudaEvent_t timer0 = nullptr, timer1 = nullptr;
     bool profile = false;
     fqd_profile_t prof;
@@ -172,6 +179,8 @@ extern "C" void fqd_destroy(fqd_handle* h) {
     cudaFree(h->d_keys); cudaFree(h->d_table); cudaFree(h->d_run); cudaFree(h->d_dup);
     if (h->h_run) cudaFreeHost(h->h_run);
     if (h->h_dup) cudaFreeHost(h->h_dup);
+    for (int k = 0; k < 2; ++k) { cudaFree(h->d_raw_alt[k]); if (h->copy_done[k]) cudaEventDestroy(h->copy_done[k]); }
+    if (h->copy_stream) cudaStreamDestroy(h->copy_stream);
     if (h->stream && h->own_stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -427,6 +436,49 @@ extern "C" int fqd_push(fqd_handle* h, const char* r1, size_t n1, const char* r2
     if (n1) CUDA_TRY(h, cudaMemcpyAsync(h->mate[0].d_raw, r1, n1, cudaMemcpyHostToDevice, h->stream));
     if (h->cfg.paired && n2) CUDA_TRY(h, cudaMemcpyAsync(h->mate[1].d_raw, r2, n2, cudaMemcpyHostToDevice, h->stream));
     int rc = enqueue_fast_chunk(h, h->mate[0].d_raw, n1, h->cfg.paired ? h->mate[1].d_raw : nullptr, h->cfg.paired ? n2 : 0);
+    if (rc) return rc;
+    return finish_fast_chunk(h, n1, n2, res);
+}
+
+// Same contract as fqd_push, split in two so that the copy of chunk c+1 overlaps the processing of chunk c:
+//   fqd_push_prefetch(c+1) ... fqd_push_staged(c) -> res(c).  At most two chunks are staged at any time; the host
+//   buffers must stay valid until the fqd_push_staged call that consumes them returns.
+extern "C" int fqd_push_prefetch(fqd_handle* h, const char* r1, size_t n1, const char* r2, size_t n2) {
+    if (!h) return FQD_ERR_INVALID;
+    if (h->cfg.mode != FQD_MODE_FAST || h->cfg.unordered) return fail(h, FQD_ERR_INVALID, "fqd_push* is for ordered --fast mode; use fqd_append/fqd_finish");
+    if (n1 > h->cfg.max_chunk_bytes || n2 > h->cfg.max_chunk_bytes) return fail(h, FQD_ERR_INVALID, "chunk larger than max_chunk_bytes");
+    if (h->n_staged >= 2) return fail(h, FQD_ERR_INVALID, "fqd_push_prefetch: two chunks are staged already");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const int mates = h->cfg.paired ? 2 : 1;
+    if (!h->copy_stream) {
+        CUDA_TRY(h, cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+        for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaEventCreateWithFlags(&h->copy_done[k], cudaEventDisableTiming));
+        for (int m = 0; m < mates; ++m) CUDA_TRY(h, cudaMalloc(&h->d_raw_alt[m], h->cfg.max_chunk_bytes + 4096));
+    }
+    const int s = h->pf_slot;
+    const char* src[2] = {r1, r2};
+    const size_t nn[2] = {n1, h->cfg.paired ? n2 : 0};
+    for (int m = 0; m < mates; ++m) {
+        u8* dst = s == 0 ? h->mate[m].d_raw : h->d_raw_alt[m];
+        if (nn[m]) CUDA_TRY(h, cudaMemcpyAsync(dst, src[m], nn[m], cudaMemcpyHostToDevice, h->copy_stream));
+        h->staged_n[s][m] = nn[m];
+    }
+    CUDA_TRY(h, cudaEventRecord(h->copy_done[s], h->copy_stream));
+    h->pf_slot ^= 1; h->n_staged++;
+    return FQD_OK;
+}
+extern "C" int fqd_push_staged(fqd_handle* h, fqd_chunk_result* res) {
+    if (!h) return FQD_ERR_INVALID;
+    if (h->n_staged == 0) return fail(h, FQD_ERR_INVALID, "fqd_push_staged without fqd_push_prefetch");
+    if (h->pending_async) { int rc = fqd_sync(h); if (rc) return rc; }
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const int s = h->run_slot;
+    CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->copy_done[s], 0));
+    const u8* d1 = s == 0 ? h->mate[0].d_raw : h->d_raw_alt[0];
+    const u8* d2 = h->cfg.paired ? (s == 0 ? h->mate[1].d_raw : h->d_raw_alt[1]) : nullptr;
+    const size_t n1 = h->staged_n[s][0], n2 = h->staged_n[s][1];
+    h->run_slot ^= 1; h->n_staged--;
+    int rc = enqueue_fast_chunk(h, d1, n1, d2, n2);
     if (rc) return rc;
     return finish_fast_chunk(h, n1, n2, res);
 }

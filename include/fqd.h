@@ -114,6 +114,12 @@ int fqd_host_free(void* p);
  * r2 / n2 are NULL / 0 for single-end.  res may be NULL (statistics only).
  */
 int fqd_push(fqd_handle* h, const char* r1, size_t n1, const char* r2, size_t n2, fqd_chunk_result* res);
+/* fqd_push in two halves, so that the host-to-device copy of chunk c+1 overlaps the processing of chunk c (the successor
+ * of BufferedInput's single buffer, src/bufferedinput.hpp:57-88, is a pair of device buffers): fqd_push_prefetch stages a
+ * chunk (copy on its own stream, returns at once; at most two staged), fqd_push_staged processes the oldest staged chunk
+ * and returns what fqd_push would have returned for it.  The host buffers must stay valid until that call returns. */
+int fqd_push_prefetch(fqd_handle* h, const char* r1, size_t n1, const char* r2, size_t n2);
+int fqd_push_staged(fqd_handle* h, fqd_chunk_result* res);
 int fqd_push_device(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2, fqd_chunk_result* res);
 /* Same as fqd_push_device but returns after enqueueing; nothing is copied to the host.  fqd_sync() waits and
  * folds the chunk counters into the statistics.  Used for device-resident throughput measurement. */

@@ -185,3 +185,35 @@ def test_device_generator_matches_cpu_twin(fqd):
         assert lib.fqd_synth_fastq(0, dbuf.ptr, first, n, L, 1, 1, 300, 20, 0) == 0
         assert dbuf.download(n * rb) == bench_synth.synth_fastq_cpu(first, n, L, 1, 1, 300, 20)
     dbuf.free()
+
+
+def test_prefetched_pushes_match_plain_pushes(fqd, oracle):
+    """fqd_push_prefetch / fqd_push_staged (copy of chunk c+1 under the processing of chunk c): same records, same flags
+    as the oracle; paired input; the chunks are cut at record boundaries."""
+    import ctypes as C
+    s1, s2 = synth.make_pair(9000, seed=77, read_len=90, var_len=True, n_frac=0.03, dup_frac=0.4)
+    r1 = [synth.to_fastq([s], ids=[b"@q.%d 1" % i]) for i, s in enumerate(s1)]
+    r2 = [synth.to_fastq([s], ids=[b"@q.%d 2" % i]) for i, s in enumerate(s2)]
+    per = 1500
+    chunks = [(b"".join(r1[i: i + per]), b"".join(r2[i: i + per])) for i in range(0, len(r1), per)]
+    maxb = max(max(len(a), len(b)) for a, b in chunks) + 4096
+    eng = fqd.Engine("fast", fqd.FORMAT_FASTQ, True, False, 2, 90, 20000, maxb, 4000, 0)
+    lib = eng.lib
+    try:
+        dup = []
+        assert lib.fqd_push_prefetch(eng.h, chunks[0][0], len(chunks[0][0]), chunks[0][1], len(chunks[0][1])) == 0
+        for c in range(len(chunks)):
+            if c + 1 < len(chunks):
+                a, b = chunks[c + 1]
+                assert lib.fqd_push_prefetch(eng.h, a, len(a), b, len(b)) == 0
+            res = fqd.ChunkResult()
+            assert lib.fqd_push_staged(eng.h, C.byref(res)) == 0
+            assert res.n_records == per
+            dup.append(np.ctypeslib.as_array(res.dup, shape=(per,)).copy())
+        keep_idx, est = oracle.fast_pe(b"".join(r1), b"".join(r2), oracle.FASTQ)
+        got = np.concatenate(dup)
+        assert np.array_equal(np.flatnonzero(got == 0).astype(np.uint64), keep_idx)
+        st = eng.stats()
+        assert (st.total, st.dups) == (est.total, est.dups)
+    finally:
+        eng.close()
