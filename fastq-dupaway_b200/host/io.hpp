@@ -13,6 +13,7 @@
 #include <deque>
 #include <filesystem>
 #include <iostream>
+#include <memory>
 #include <mutex>
 #include <stdexcept>
 #include <string>
@@ -20,30 +21,62 @@
 #include <vector>
 
 #include "../../include/fqd.h"
+#include "pargz.hpp"
 
 namespace fqdhost {
 
 inline bool has_gz_ext(const std::string& name) { return std::filesystem::path(name).extension() == ".gz"; }
 
+// Plain files are read with concurrent pread()s, ".gz" files are inflated member-parallel (pargz.hpp); pipes,
+// single-member archives and FQD_IO_THREADS=1 take the serial zlib path.
 class InputFile {
 public:
     explicit InputFile(const std::string& name) : m_name(name), m_gz(has_gz_ext(name)) {
-        m_f = std::fopen(name.c_str(), "rb");
-        if (!m_f) {
+        m_fd = ::open(name.c_str(), O_RDONLY);
+        if (m_fd < 0) {
             std::cerr << "Cannot open file " << name << std::endl;
             throw std::runtime_error("File does not exist or cannot be opened!");
         }
+        const bool parallel = io_threads() > 1;
         if (m_gz) {
+            if (parallel) {
+                m_map.reset(new MappedFile(m_fd));
+                if (m_map->ok()) { m_par.reset(new ParallelGzSource(m_map->data(), m_map->size())); return; }
+                m_map.reset();
+            }
+            m_f = fdopen(m_fd, "rb");
+            if (!m_f) throw std::runtime_error("File does not exist or cannot be opened!");
             std::memset(&m_z, 0, sizeof m_z);
             if (inflateInit2(&m_z, 15 + 16) != Z_OK) throw std::runtime_error("zlib: inflateInit2 failed");
+            m_zinit = true;
             m_in.resize(1 << 20);
+        } else {
+            struct stat sb;
+            m_regular = parallel && fstat(m_fd, &sb) == 0 && S_ISREG(sb.st_mode);
+            if (!m_regular) {
+                m_f = fdopen(m_fd, "rb");
+                if (!m_f) throw std::runtime_error("File does not exist or cannot be opened!");
+            }
         }
     }
-    ~InputFile() { if (m_gz) inflateEnd(&m_z); if (m_f) std::fclose(m_f); }
+    ~InputFile() {
+        if (m_zinit) inflateEnd(&m_z);
+        m_par.reset(); m_map.reset();
+        if (m_f) std::fclose(m_f); else if (m_fd >= 0) ::close(m_fd);
+    }
+    InputFile(const InputFile&) = delete;
+    InputFile& operator=(const InputFile&) = delete;
     // read up to n bytes; returns the number read (< n only at end of input)
     size_t read(char* dst, size_t n) {
+        if (m_par) {
+            size_t got = m_par->read(dst, n);
+            if (m_par->eof()) m_eof = true;
+            return got;
+        }
         if (!m_gz) {
-            size_t got = std::fread(dst, 1, n, m_f);
+            size_t got;
+            if (m_regular) { got = parallel_pread(m_fd, dst, n, m_off); m_off += got; }
+            else got = std::fread(dst, 1, n, m_f);
             if (got < n) m_eof = true;
             return got;
         }
@@ -66,12 +99,17 @@ public:
         return got;
     }
     bool eof() const { return m_eof; }
+    const ParallelGzSource* parallel_source() const { return m_par.get(); }
 private:
     std::string m_name;
-    bool m_gz, m_eof = false;
+    bool m_gz, m_eof = false, m_regular = false, m_zinit = false;
+    int m_fd = -1;
+    size_t m_off = 0;
     FILE* m_f = nullptr;
     z_stream m_z;
     std::vector<char> m_in;
+    std::unique_ptr<MappedFile> m_map;
+    std::unique_ptr<ParallelGzSource> m_par;
 };
 
 // One pinned block: [head room | data].  The consumer copies the (small) unconsumed tail of the previous
@@ -157,27 +195,32 @@ private:
     std::exception_ptr m_err;
 };
 
-// UniversalOutputFile (src/file_utils.cpp:83-92): plain or gzip by extension.
+// UniversalOutputFile (src/file_utils.cpp:83-92): plain or gzip by extension.  ".gz" output is deflated on the
+// worker pool as a multi-member archive (pargz.hpp); with FQD_IO_THREADS=1 by zlib's gzwrite.
 class OutputFile {
 public:
     explicit OutputFile(const std::string& name) : m_gz(has_gz_ext(name)) {
-        if (m_gz) {
+        if (m_gz && io_threads() <= 1) {
             m_g = gzopen(name.c_str(), "wb");
             if (m_g) gzbuffer(m_g, 1 << 20);
         } else {
             m_f = std::fopen(name.c_str(), "wb");
             if (m_f) std::setvbuf(m_f, nullptr, _IOFBF, 4 << 20);
+            if (m_f && m_gz) m_sink.reset(new ParallelGzSink(m_f));
         }
     }
     ~OutputFile() { close(); }
     void write(const char* p, size_t n) {
-        if (m_gz) {
-            while (m_g && n) { unsigned w = (unsigned)std::min<size_t>(n, 1u << 30); gzwrite(m_g, p, w); p += w; n -= w; }
+        if (m_g) {
+            while (n) { unsigned w = (unsigned)std::min<size_t>(n, 1u << 30); gzwrite(m_g, p, w); p += w; n -= w; }
+        } else if (m_sink) {
+            m_sink->write(p, n);
         } else if (m_f) {
             std::fwrite(p, 1, n, m_f);
         }
     }
     void close() {
+        if (m_sink) { m_sink->finish(); m_sink.reset(); }
         if (m_g) { gzclose(m_g); m_g = nullptr; }
         if (m_f) { std::fclose(m_f); m_f = nullptr; }
     }
@@ -185,6 +228,7 @@ private:
     bool m_gz;
     FILE* m_f = nullptr;
     gzFile m_g = nullptr;
+    std::unique_ptr<ParallelGzSink> m_sink;
 };
 
 // ClusterFile (src/file_utils.cpp:98-112): "<out>.clusters", head = ID line, member = "--" + ID line.

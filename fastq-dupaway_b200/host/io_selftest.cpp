@@ -1,0 +1,92 @@
+// io_selftest.cpp - CPU-only harness around io.hpp / pargz.hpp (no CUDA: the two pinned-memory entry points of
+// the C ABI are replaced by malloc here).  tests/test_host_io.py drives it:
+//   io_selftest cat  <file> [block_bytes]   file -> BlockReader ring -> stdout; "stats ..." line on stderr
+//   io_selftest put  <file>                 stdin -> OutputFile (plain or .gz by extension)
+//   io_selftest bench <file> [repeats]      InputFile::read into one buffer; prints uncompressed GB/s as JSON
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <iostream>
+#include <string>
+#include <vector>
+
+#include "io.hpp"
+
+extern "C" int fqd_host_alloc(void** p, size_t bytes) { *p = std::malloc(bytes); return *p ? FQD_OK : FQD_ERR_CUDA; }
+extern "C" int fqd_host_free(void* p) { std::free(p); return FQD_OK; }
+
+using namespace fqdhost;
+
+static int cmd_cat(const std::string& name, size_t block) {
+    // the ring, exactly as the drivers use it (dup_remover.cpp)
+    BlockReader reader(name, block);
+    size_t total = 0, blocks = 0;
+    while (Block* b = reader.next()) {
+        if (b->len && std::fwrite(b->data(), 1, b->len, stdout) != b->len) return 2;
+        total += b->len; ++blocks;
+        reader.release(b);
+    }
+    std::fflush(stdout);
+    std::fprintf(stderr, "stats bytes=%zu blocks=%zu\n", total, blocks);
+    return 0;
+}
+
+static int cmd_stat(const std::string& name) {
+    // InputFile alone: how the archive was decoded
+    InputFile f(name);
+    std::vector<char> buf(8u << 20);
+    size_t total = 0;
+    while (!f.eof()) total += f.read(buf.data(), buf.size());
+    const ParallelGzSource* ps = f.parallel_source();
+    std::printf("{\"bytes\": %zu, \"parallel\": %s, \"bgzf\": %s, \"tasks\": %zu, \"serial_members\": %zu, \"dropped\": %zu}\n",
+                total, ps ? "true" : "false", ps && ps->bgzf() ? "true" : "false", ps ? ps->parallel_tasks() : (size_t)0,
+                ps ? ps->serial_members() : (size_t)0, ps ? ps->dropped_tasks() : (size_t)0);
+    return 0;
+}
+
+static int cmd_put(const std::string& name) {
+    OutputFile out(name);
+    std::vector<char> buf(1u << 20);
+    size_t n;
+    // odd-sized writes on purpose: pieces must not depend on the caller's write sizes
+    size_t want = 777;
+    while ((n = std::fread(buf.data(), 1, std::min(want, buf.size()), stdin)) > 0) {
+        out.write(buf.data(), n);
+        want = want * 3 + 1;
+        if (want > buf.size()) want = 1000;
+    }
+    out.close();
+    return 0;
+}
+
+static int cmd_bench(const std::string& name, int repeats) {
+    std::vector<char> buf(64u << 20);
+    double best = 0; size_t bytes = 0;
+    for (int r = 0; r < repeats; ++r) {
+        auto t0 = std::chrono::steady_clock::now();
+        InputFile f(name);
+        size_t total = 0;
+        while (!f.eof()) total += f.read(buf.data(), buf.size());
+        double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        bytes = total;
+        best = std::max(best, (double)total / s / 1e9);
+    }
+    std::printf("{\"file\": \"%s\", \"bytes\": %zu, \"threads\": %d, \"GBps\": %.3f}\n", name.c_str(), bytes, io_threads(), best);
+    return 0;
+}
+
+int main(int argc, char** argv) {
+    if (argc < 3) { std::fprintf(stderr, "usage: io_selftest cat|stat|put|bench <file> [arg]\n"); return 64; }
+    const std::string cmd = argv[1], name = argv[2];
+    try {
+        if (cmd == "cat") return cmd_cat(name, argc > 3 ? (size_t)std::atoll(argv[3]) : (4u << 20));
+        if (cmd == "stat") return cmd_stat(name);
+        if (cmd == "put") return cmd_put(name);
+        if (cmd == "bench") return cmd_bench(name, argc > 3 ? std::atoi(argv[3]) : 3);
+    } catch (const std::exception& e) {
+        std::fprintf(stderr, "error: %s\n", e.what());
+        return 1;
+    }
+    return 64;
+}

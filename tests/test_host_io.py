@@ -1,0 +1,219 @@
+"""Host-side ingest / egress of the drop-in binary (fastq-dupaway_b200/host/io.hpp, pargz.hpp), on the CPU.
+
+The reference reads ".gz" through one Boost.Iostreams filter on the main thread (src/file_utils.cpp:59-66) and
+writes it the same way (:83-92); here members are inflated in parallel and the output is deflated in parallel.
+These tests check that whatever the archive looks like - one member, thousands, BGZF, header magic inside the
+compressed bytes, members larger than a task, padding, truncation, corruption - the bytes that reach the engine are
+exactly the decompressed file, against Python's gzip module as the independent decoder.
+"""
+import gzip
+import json
+import os
+import random
+import struct
+import subprocess
+import zlib
+from pathlib import Path
+
+import pytest
+
+HOST = Path(__file__).resolve().parent.parent / "fastq-dupaway_b200" / "host"
+EXE = HOST / "io_selftest"
+MAGIC = b"\x1f\x8b\x08\x00"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def build_selftest():
+    subprocess.run(["make", "-s", "-C", str(HOST), "io_selftest"], check=True)
+    assert EXE.exists()
+
+
+def run(args, threads=4, stdin=None, check=True):
+    env = dict(os.environ, FQD_IO_THREADS=str(threads))
+    p = subprocess.run([str(EXE)] + [str(a) for a in args], input=stdin, capture_output=True, env=env, timeout=300)
+    if check:
+        assert p.returncode == 0, p.stderr.decode()
+    return p
+
+
+def fastq_bytes(n, seed=0, read_len=100):
+    rng = random.Random(seed)
+    out = []
+    for i in range(n):
+        seq = "".join(rng.choice("ACGT") for _ in range(read_len))
+        out.append(f"@R.{i} 1\n{seq}\n+\n{'I' * read_len}\n")
+    return "".join(out).encode()
+
+
+def members(data, sizes, level=6):
+    """gzip members over consecutive slices of data"""
+    out, pos, i = [], 0, 0
+    while pos < len(data):
+        k = sizes[i % len(sizes)]
+        out.append(gzip.compress(data[pos:pos + k], compresslevel=level))
+        pos += k
+        i += 1
+    return b"".join(out)
+
+
+def bgzf(data, block=0xff00, eof_marker=True):
+    """BGZF as bgzip writes it: extra subfield BC = member size - 1"""
+    out = []
+    for pos in list(range(0, len(data), block)) + ([len(data)] if eof_marker else []):
+        piece = data[pos:pos + block]
+        c = zlib.compressobj(6, zlib.DEFLATED, -15)
+        body = c.compress(piece) + c.flush()
+        bsize = 12 + 6 + len(body) + 8
+        out.append(b"\x1f\x8b\x08\x04" + b"\0\0\0\0" + b"\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+                   + body + struct.pack("<II", zlib.crc32(piece), len(piece)))
+    return b"".join(out)
+
+
+def check_file(path, expect, threads=4, block=1 << 16):
+    got = run(["cat", path, block], threads=threads).stdout
+    assert got == expect
+    return json.loads(run(["stat", path], threads=threads).stdout)
+
+
+@pytest.mark.parametrize("threads", [1, 2, 8])
+def test_plain_file(tmp_path, threads):
+    data = fastq_bytes(40000, seed=1)          # ~9 MB: the concurrent pread path needs >= 8 MiB per block
+    f = tmp_path / "a.fastq"
+    f.write_bytes(data)
+    assert run(["cat", f, 1 << 16], threads=threads).stdout == data
+    assert run(["cat", f, 12 << 20], threads=threads).stdout == data
+
+
+def test_empty_inputs(tmp_path):
+    (tmp_path / "e.fastq").write_bytes(b"")
+    (tmp_path / "e.gz").write_bytes(b"")
+    (tmp_path / "m.gz").write_bytes(gzip.compress(b""))
+    for n in ("e.fastq", "e.gz", "m.gz"):
+        assert run(["cat", tmp_path / n]).stdout == b""
+    p = run(["cat", tmp_path / "missing.gz"], check=False)
+    assert p.returncode == 1 and b"Cannot open file" in p.stderr
+
+
+@pytest.mark.parametrize("threads", [1, 2, 8])
+def test_single_member(tmp_path, threads):
+    data = fastq_bytes(20000, seed=2)
+    f = tmp_path / "one.fq.gz"
+    f.write_bytes(gzip.compress(data))
+    st = check_file(f, data, threads)
+    assert st["bytes"] == len(data)
+
+
+@pytest.mark.parametrize("threads", [2, 8])
+@pytest.mark.parametrize("sizes", [[1000], [70000, 1, 333333], [3_000_000]])
+def test_multi_member(tmp_path, threads, sizes):
+    data = fastq_bytes(40000, seed=3)
+    f = tmp_path / "multi.fq.gz"
+    f.write_bytes(members(data, sizes))
+    st = check_file(f, data, threads)
+    assert st["parallel"] and st["tasks"] >= 1 and st["serial_members"] == 0
+
+
+def test_many_tasks_run_ahead(tmp_path):
+    # small span is not configurable from outside; 30 MB of poorly compressible data gives > 10 tasks of 2 MiB
+    rng = random.Random(5)
+    data = bytes(rng.getrandbits(8) for _ in range(1 << 16)) * 16
+    data = b"".join(data[i:] + data[:i] for i in range(0, 30))      # ~30 MB, rotated copies
+    blob = members(data, [200_000], level=1)
+    f = tmp_path / "many.gz"
+    f.write_bytes(blob)
+    st = check_file(f, data, 8, block=1 << 20)
+    assert st["tasks"] >= 2
+
+
+@pytest.mark.parametrize("threads", [2, 8])
+def test_bgzf(tmp_path, threads):
+    data = fastq_bytes(60000, seed=4)
+    f = tmp_path / "b.fq.gz"
+    f.write_bytes(bgzf(data))
+    st = check_file(f, data, threads)
+    assert st["parallel"] and st["bgzf"] and st["dropped"] == 0 and st["serial_members"] == 0
+    # BGZF followed by ordinary members: the hop list ends, the scan takes over
+    tail = fastq_bytes(3000, seed=5)
+    f.write_bytes(bgzf(data, eof_marker=False) + members(tail, [50000]))
+    check_file(f, data + tail, threads)
+
+
+@pytest.mark.parametrize("threads", [2, 8])
+def test_magic_inside_compressed_bytes(tmp_path, threads):
+    """Stored (level 0) members carry the payload verbatim, so the gzip magic inside the payload shows up in the
+    compressed stream: false member starts everywhere.  The output must still be exact."""
+    rng = random.Random(6)
+    payload = bytearray()
+    while len(payload) < 6_000_000:
+        payload += bytes(rng.getrandbits(8) for _ in range(rng.randrange(10, 3000)))
+        payload += MAGIC + bytes(rng.getrandbits(8) for _ in range(6))
+        if rng.random() < 0.2:   # a whole valid little member as payload: a false start that even inflates cleanly
+            payload += gzip.compress(b"decoy" * rng.randrange(1, 50))
+    data = bytes(payload)
+    for sizes in ([2_500_000], [100_000, 900_000], [len(data)]):
+        f = tmp_path / "decoy.gz"
+        f.write_bytes(members(data, sizes, level=0))
+        st = check_file(f, data, threads)
+        assert st["parallel"]
+    # one huge stored member with decoys followed by small real members
+    tail = fastq_bytes(5000, seed=7)
+    f.write_bytes(gzip.compress(data, compresslevel=0) + members(tail, [20000]))
+    check_file(f, data + tail, threads)
+
+
+def test_member_larger_than_a_task_goes_serial(tmp_path):
+    rng = random.Random(8)
+    big = bytes(rng.getrandbits(8) for _ in range(1 << 20)) * 40       # 40 MiB, compresses badly at level 1... stored
+    tail = fastq_bytes(5000, seed=9)
+    f = tmp_path / "big.gz"
+    f.write_bytes(gzip.compress(big, compresslevel=0) + members(tail, [100000]) + gzip.compress(big[:1 << 20], compresslevel=0))
+    st = check_file(f, big + tail + big[:1 << 20], 4, block=1 << 20)
+    assert st["serial_members"] >= 1 and st["tasks"] >= 1
+
+
+def test_padding_truncation_corruption(tmp_path):
+    data = fastq_bytes(20000, seed=10)
+    blob = members(data, [300000])
+    f = tmp_path / "x.gz"
+    # zero padding after the last member is ignored (as gzip(1) does)
+    f.write_bytes(blob + b"\0" * 1000)
+    check_file(f, data)
+    # garbage after the last member: error, like the serial zlib path
+    f.write_bytes(blob + b"garbage-garbage-garbage-garbage")
+    for t in (1, 4):
+        p = run(["cat", f], threads=t, check=False)
+        assert p.returncode == 1 and b"gzip error" in p.stderr
+    # cut in the middle of a member: the bytes before the cut are delivered, then end of input (both paths agree)
+    f.write_bytes(blob[:len(blob) // 2])
+    a = run(["cat", f], threads=1).stdout
+    b = run(["cat", f], threads=4).stdout
+    assert data.startswith(b) and len(b) > 0
+    assert data.startswith(a)
+    # a flipped bit in the middle: CRC / inflate error
+    bad = bytearray(blob)
+    bad[len(bad) // 2] ^= 0x10
+    f.write_bytes(bytes(bad))
+    p = run(["cat", f], threads=4, check=False)
+    assert p.returncode == 1 and b"gzip error" in p.stderr
+    # not gzip at all
+    f.write_bytes(b"@r\nACGT\n+\nIIII\n" * 10)
+    p = run(["cat", f], threads=4, check=False)
+    assert p.returncode == 1 and b"gzip error" in p.stderr
+
+
+@pytest.mark.parametrize("threads", [1, 2, 8])
+def test_gz_output(tmp_path, threads):
+    data = fastq_bytes(30000, seed=11)           # ~6.6 MB: several 1 MiB pieces
+    out = tmp_path / "o.fq.gz"
+    run(["put", out], threads=threads, stdin=data)
+    assert gzip.decompress(out.read_bytes()) == data
+    assert subprocess.run(["gzip", "-t", str(out)]).returncode == 0
+    # and back in through the parallel reader
+    check_file(out, data, threads)
+    # empty output is still a valid archive
+    run(["put", out], threads=threads, stdin=b"")
+    assert gzip.decompress(out.read_bytes()) == b""
+    # plain output
+    plain = tmp_path / "o.fq"
+    run(["put", plain], threads=threads, stdin=data)
+    assert plain.read_bytes() == data
