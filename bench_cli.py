@@ -1,0 +1,132 @@
+"""Files in, files out: the drop-in binary (fastq-dupaway_b200/host/fastq-dupaway) against the reference binary
+(oracle/_ref/fastq-dupaway, the unmodified sources compiled by oracle/Makefile) on the SAME input file, both started
+the way a user starts them.  This is the end-to-end number of the whole product - host ingest (plain / multi-member
+gzip / BGZF), pinned staging, H2D, kernels, D2H, output gather and file writes - next to bench.py's kernel-level lines.
+
+    python bench_cli.py [--reads 10000000] [--ref-reads 2000000] [--formats plain,gzmm,bgzf] [--mode fast|tight]
+
+The input is the synthetic stream of bench.py (device generator, 150 bp, 30 % duplicates) written to tmpfs.  The
+reference is timed on a prefix (--ref-reads; it is single-threaded, ~0.5 M reads/s) and on plain input only.  One JSON
+line per run; outputs are compared between the two binaries on the common prefix run (byte identity, --fast).
+Wall clock around the process (time.perf_counter), page cache warm, outputs on tmpfs.
+"""
+from __future__ import annotations
+
+import argparse
+import gzip
+import importlib
+import json
+import os
+import shutil
+import struct
+import subprocess
+import sys
+import tempfile
+import time
+import zlib
+from concurrent.futures import ThreadPoolExecutor
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+sys.path.insert(0, str(ROOT / "oracle"))
+EXE = ROOT / "fastq-dupaway_b200" / "host" / "fastq-dupaway"
+READ_LEN, SEED, DUP_PERMILLE, N_PERMILLE = 150, 1, 300, 0
+REC = 22 + 2 * READ_LEN
+
+
+def synth_file(path: Path, n_reads: int):
+    """device generator -> host -> file, 4 M reads at a time"""
+    pkg = importlib.import_module("fastq-dupaway_b200")
+    lib = pkg.load_library()
+    step = 4_000_000
+    buf = pkg.DeviceBuffer(step * REC)
+    with open(path, "wb") as f:
+        for first in range(0, n_reads, step):
+            cnt = min(step, n_reads - first)
+            rc = lib.fqd_synth_fastq(0, buf.ptr, first, cnt, READ_LEN, 1, SEED, DUP_PERMILLE, N_PERMILLE, 0)
+            assert rc == 0
+            f.write(buf.download(cnt * REC))
+    buf.free()
+
+
+def gz_members(src: Path, dst: Path, piece: int, bgzf: bool):
+    """multi-member gzip (16 MiB members) or BGZF (64 KiB members with the BC extra subfield), compressed in threads"""
+    data = src.read_bytes()
+
+    def one(pos):
+        part = data[pos:pos + piece]
+        if not bgzf:
+            return gzip.compress(part, compresslevel=1)
+        c = zlib.compressobj(1, zlib.DEFLATED, -15)
+        body = c.compress(part) + c.flush()
+        bsize = 12 + 6 + len(body) + 8
+        return (b"\x1f\x8b\x08\x04\0\0\0\0\x00\xff" + struct.pack("<H", 6) + b"BC" + struct.pack("<HH", 2, bsize - 1)
+                + body + struct.pack("<II", zlib.crc32(part), len(part)))
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 4)) as ex, open(dst, "wb") as f:
+        for blob in ex.map(one, range(0, len(data), piece)):
+            f.write(blob)
+
+
+def timed(cmd, cwd):
+    t0 = time.perf_counter()
+    res = subprocess.run([str(c) for c in cmd], cwd=cwd, capture_output=True, text=True)
+    dt = time.perf_counter() - t0
+    assert res.returncode == 0, res.stderr
+    return dt, res.stdout.strip()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--reads", type=int, default=10_000_000)
+    ap.add_argument("--ref-reads", type=int, default=2_000_000)
+    ap.add_argument("--formats", default="plain,gzmm,bgzf")
+    ap.add_argument("--mode", default="fast", choices=["fast", "tight"])
+    ap.add_argument("--repeats", type=int, default=2)
+    args = ap.parse_args()
+    oracle = importlib.import_module("oracle")
+    tmp = Path(tempfile.mkdtemp(prefix="fqd_cli_", dir="/dev/shm" if Path("/dev/shm").is_dir() else None))
+    mode_args = ["--fast"] if args.mode == "fast" else ["--compare-seq", "tight"]
+    try:
+        full = tmp / "in.fq"
+        synth_file(full, args.reads)
+        inputs = {"plain": full}
+        for fmt in args.formats.split(","):
+            if fmt == "gzmm":
+                inputs[fmt] = tmp / "in_mm.fq.gz"
+                gz_members(full, inputs[fmt], 16 << 20, False)
+            elif fmt == "bgzf":
+                inputs[fmt] = tmp / "in_bgzf.fq.gz"
+                gz_members(full, inputs[fmt], 0xff00, True)
+        for fmt in args.formats.split(","):
+            inp = inputs[fmt]
+            best = None
+            for _ in range(args.repeats):
+                dt, so = timed([EXE, "-i", inp, "-o", tmp / "out.fq", "-v", *mode_args], tmp)
+                best = dt if best is None else min(best, dt)
+            print(json.dumps({"impl": "ours", "binary": "fastq-dupaway_b200/host/fastq-dupaway", "mode": args.mode, "input": fmt,
+                              "reads": args.reads, "input_bytes": inp.stat().st_size, "seconds": round(best, 3),
+                              "reads_per_s": round(args.reads / best), "raw_GBps": round(args.reads * REC / best / 1e9, 3),
+                              "io_threads": os.environ.get("FQD_IO_THREADS", "auto"), "host_cores": os.cpu_count(), "stdout": so}), flush=True)
+        # common prefix: both binaries, outputs compared
+        n = min(args.ref_reads, args.reads)
+        pre = tmp / "pre.fq"
+        with open(full, "rb") as f, open(pre, "wb") as g:
+            g.write(f.read(n * REC))
+        dt_o, so_o = timed([EXE, "-i", pre, "-o", tmp / "o_ours.fq", "-v", *mode_args], tmp)
+        if oracle.ref_available():
+            ref_args = mode_args + ([] if args.mode == "fast" else ["-m", "10240"])
+            dt_r, so_r = timed([oracle.REF_BIN, "-i", pre, "-o", tmp / "o_ref.fq", "-v", *ref_args], tmp)
+            same = (tmp / "o_ours.fq").read_bytes() == (tmp / "o_ref.fq").read_bytes()
+            print(json.dumps({"impl": "reference", "binary": "oracle/_ref/fastq-dupaway", "mode": args.mode, "input": "plain", "reads": n,
+                              "seconds": round(dt_r, 3), "reads_per_s": round(n / dt_r), "cores": 1, "stdout": so_r,
+                              "ours_same_input_seconds": round(dt_o, 3), "outputs_byte_identical": same,
+                              "verbose_lines_identical": so_o == so_r}), flush=True)
+        else:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/fastq-dupaway not built"}), flush=True)
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -4,6 +4,9 @@
 #include <sys/stat.h>
 
 #include <algorithm>
+#include <condition_variable>
+#include <mutex>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <fstream>
@@ -65,6 +68,15 @@ struct Restart : std::exception { int what_code; explicit Restart(int c) : what_
     }
 }
 
+// FQD_BLOCK_BYTES: staging block size for tests (many small blocks exercise the tail carry and the recycling of
+// blocks behind the asynchronous writers on small inputs)
+size_t test_block_override(size_t block) {
+    const char* e = std::getenv("FQD_BLOCK_BYTES");
+    if (!e) return block;
+    long long v = std::atoll(e);
+    return v >= 4096 ? ((size_t)v & ~(size_t)4095) : block;
+}
+
 size_t file_size_or_zero(const std::string& name) {
     struct stat sb;
     return stat(name.c_str(), &sb) == 0 ? (size_t)sb.st_size : 0;
@@ -84,53 +96,6 @@ void sample_geometry(const char* p, size_t n, int lpr, size_t& max_seq, double& 
         cur = nl + 1;
     }
     if (recs) avg_rec = (double)last_rec_end / recs; else { avg_rec = 64; max_seq = std::max<size_t>(max_seq, n); }
-}
-
-struct MateStream {
-    std::unique_ptr<BlockReader> reader;
-    Block* cur = nullptr;      // block that holds [ptr, ptr+len)
-    Block* peeked = nullptr;   // next block, fetched early to look at its first byte
-    char* ptr = nullptr;
-    size_t len = 0;
-    bool no_more = false;      // reader exhausted
-    Block* fetch() {
-        if (peeked) { Block* b = peeked; peeked = nullptr; return b; }
-        if (no_more) return nullptr;
-        Block* b = reader->next();
-        if (!b) no_more = true;
-        return b;
-    }
-    // append the next block behind the unconsumed tail (tail is copied into the block's head room)
-    bool refill() {
-        Block* b = fetch();
-        if (!b) return false;
-        if (len > b->head) throw std::runtime_error("Not enough memory to read a single object!");
-        char* dst = b->data() - len;
-        if (len) memcpy(dst, ptr, len);
-        if (cur) reader->release(cur);
-        cur = b; ptr = dst; len += b->len;
-        return true;
-    }
-    // first byte that follows [ptr, ptr+len) in the file, or -1 at end of input
-    int peek_next_byte() {
-        if (!peeked) {
-            if (no_more) return -1;
-            peeked = reader->next();
-            if (!peeked) { no_more = true; return -1; }
-        }
-        return peeked->len ? (unsigned char)peeked->data()[0] : -1;
-    }
-};
-
-void write_survivors(OutputFile& out, const char* base, const uint32_t* rec_start, const uint8_t* dup, size_t n) {
-    size_t i = 0;
-    while (i < n) {
-        if (dup[i]) { ++i; continue; }
-        size_t j = i;
-        while (j + 1 < n && !dup[j + 1]) ++j;
-        out.write(base + rec_start[i], rec_start[j + 1] - rec_start[i]);
-        i = j + 1;
-    }
 }
 
 }  // namespace
@@ -155,6 +120,7 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
     // pinned staging: 3 blocks (head room + data) per input file inside the -m budget
     size_t block = (size_t)m_memlimit / (size_t)(mates * 3 * 2);
     block = std::min<size_t>(std::max<size_t>(block, 4u << 20), 256u << 20) & ~(size_t)4095;
+    block = test_block_override(block);
     double growth = 1.0;
     unsigned seq_growth = 0;
 
@@ -164,6 +130,18 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
         for (int m = 0; m < mates; ++m) outs.emplace_back(new OutputFile(out[m]));
         MateStream ms[2];
         for (int m = 0; m < mates; ++m) ms[m].reader.reset(new BlockReader(in[m], block));
+        // one writer thread per output: the survivors of chunk c are written while chunk c+1 is on the device; an
+        // input block goes back to its reader only after the writes that read from it (declared after `ms`, so the
+        // writers finish before the blocks are freed, whatever the way out of this scope)
+        std::vector<std::unique_ptr<AsyncWriter>> writers;
+        for (int m = 0; m < mates; ++m) {
+            writers.emplace_back(new AsyncWriter(*outs[m]));
+            AsyncWriter* w = writers[m].get();
+            BlockReader* r = ms[m].reader.get();
+            ms[m].release = [w, r](Block* b) { w->then([r, b] { r->release(b); }); };
+        }
+        auto close_outputs = [&] { for (auto& w : writers) w->drain(); for (auto& o : outs) o->close(); };
+        std::vector<Run> runs;
         for (int m = 0; m < mates; ++m)
             if (!ms[m].refill()) throw std::runtime_error("Not enough memory to read a single object!");   // empty file
         for (int m = 0; m < mates; ++m)       // the very first record is validated by set_file()'s refresh (src/bufferedinput.hpp:76-86)
@@ -228,15 +206,19 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
                 n -= 1;
                 chunk_dups -= last_dup;
             }
-            for (int m = 0; m < mates; ++m) write_survivors(*outs[m], ms[m].ptr, res.rec_start[m], res.dup, n);
+            for (int m = 0; m < mates; ++m) {
+                const size_t bytes = survivor_runs(res.rec_start[m], res.dup, n, runs);
+                writers[m]->write_runs(ms[m].ptr, std::move(runs), bytes);
+                runs = std::vector<Run>();
+            }
             total += n; dups += chunk_dups;
             if (tail_err_mate >= 0) {
                 st.err = FQD_ERR_BAD_START; st.err_char = tail_char;
-                for (auto& o : outs) o->close();
+                close_outputs();
                 throw_data_error(st, m_fasta);
             }
             if (st.err) {
-                for (auto& o : outs) o->close();
+                close_outputs();
                 const int em = st.err_mate;
                 size_t e = (size_t)(st.err_record - res.first_record);
                 const char* rec = nullptr; size_t rl = 0;
@@ -262,7 +244,7 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
             fqd_stats_t st; memset(&st, 0, sizeof st); st.err = FQD_ERR_EMPTY;
             throw_data_error(st, m_fasta);
         }
-        for (auto& o : outs) o->close();
+        close_outputs();
         if (m_verbose) {
             if (mates == 1) std::cout << total << " reads processed, out of which " << dups << " duplicates were removed.\n";
             else std::cout << total << " read pairs processed, out of which " << dups << " duplicates were removed.\n";
@@ -292,6 +274,7 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
     const int lpr = fasta ? 2 : 4;
     size_t block = (size_t)memlimit / (size_t)(mates * 3 * 2);
     block = std::min<size_t>(std::max<size_t>(block, 4u << 20), 256u << 20) & ~(size_t)4095;
+    block = test_block_override(block);
     double growth = 1.0;
     unsigned seq_growth = 0, tag_growth = 0;
     bool byte_keys = false;         // sequence-based modes order ANY byte (src/fastqview.cpp:56-67): raw-byte key rows
@@ -351,18 +334,31 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
 
         std::vector<std::unique_ptr<OutputFile>> outs;
         for (int m = 0; m < mates; ++m) outs.emplace_back(new OutputFile(out[m]));
+        // two pinned staging buffers: the device gathers + copies the next piece while a writer thread writes the last
         const size_t cap = 64u << 20;
-        void* stage = nullptr;
-        if (fqd_host_alloc(&stage, cap) != FQD_OK) throw std::runtime_error("pinned host allocation failed");
-        struct Free { void* p; ~Free() { fqd_host_free(p); } } guard{stage};
+        void* stage_buf[2] = {nullptr, nullptr};
+        for (auto& p : stage_buf)
+            if (fqd_host_alloc(&p, cap) != FQD_OK) throw std::runtime_error("pinned host allocation failed");
+        struct Free { void** p; ~Free() { fqd_host_free(p[0]); fqd_host_free(p[1]); } } guard{stage_buf};
+        void* stage = stage_buf[0];
         for (int m = 0; m < mates; ++m) {
+            std::mutex mu; std::condition_variable cv; bool busy[2] = {false, false};
+            AsyncWriter writer(*outs[m]);
+            int slot = 0;
             for (;;) {
+                { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&] { return !busy[slot]; }); }
                 size_t nb = 0; int done = 0;
-                rc = fqd_emit(eng.get(), m, stage, cap, &nb, &done);
-                if (rc) throw_engine_error(eng.get(), rc);
-                outs[m]->write((const char*)stage, nb);
+                rc = fqd_emit(eng.get(), m, stage_buf[slot], cap, &nb, &done);
+                if (rc) { writer.drain(); throw_engine_error(eng.get(), rc); }
+                if (nb) {
+                    { std::lock_guard<std::mutex> g(mu); busy[slot] = true; }
+                    writer.write_runs((const char*)stage_buf[slot], std::vector<Run>{Run{0, nb, 0}}, nb);
+                    writer.then([&mu, &cv, &busy, slot] { { std::lock_guard<std::mutex> g(mu); busy[slot] = false; } cv.notify_all(); });
+                    slot ^= 1;
+                }
                 if (done) break;
             }
+            writer.drain();
         }
         for (auto& o : outs) o->close();
         if (write_clusters) {

@@ -12,6 +12,7 @@
 #include <cstring>
 #include <deque>
 #include <filesystem>
+#include <functional>
 #include <iostream>
 #include <memory>
 #include <mutex>
@@ -195,41 +196,218 @@ private:
     std::exception_ptr m_err;
 };
 
+// The consumer's view of one input file: [ptr, ptr + len) is contiguous, unconsumed input.  refill() appends the
+// next block behind the unconsumed tail (the tail is copied into the block's head room - the successor of
+// BufferedInput::refresh's memmove, src/bufferedinput.hpp:66-74).  A block that is left behind goes back to its
+// reader through `release`, which the drivers route through the AsyncWriter that may still be reading from it.
+struct MateStream {
+    std::unique_ptr<BlockReader> reader;
+    std::function<void(Block*)> release;   // default: straight back to the reader
+    Block* cur = nullptr;      // block that holds [ptr, ptr+len)
+    Block* peeked = nullptr;   // next block, fetched early to look at its first byte
+    char* ptr = nullptr;
+    size_t len = 0;
+    bool no_more = false;      // reader exhausted
+    Block* fetch() {
+        if (peeked) { Block* b = peeked; peeked = nullptr; return b; }
+        if (no_more) return nullptr;
+        Block* b = reader->next();
+        if (!b) no_more = true;
+        return b;
+    }
+    bool refill() {
+        Block* b = fetch();
+        if (!b) return false;
+        if (len > b->head) throw std::runtime_error("Not enough memory to read a single object!");
+        char* dst = b->data() - len;
+        if (len) memcpy(dst, ptr, len);
+        if (cur) { if (release) release(cur); else reader->release(cur); }
+        cur = b; ptr = dst; len += b->len;
+        return true;
+    }
+    // first byte that follows [ptr, ptr+len) in the file, or -1 at end of input
+    int peek_next_byte() {
+        if (!peeked) {
+            if (no_more) return -1;
+            peeked = reader->next();
+            if (!peeked) { no_more = true; return -1; }
+        }
+        return peeked->len ? (unsigned char)peeked->data()[0] : -1;
+    }
+};
+
+// A stretch of bytes to write: `len` bytes at base + off, landing `out_off` bytes after the start of the job.
+struct Run { size_t off, len, out_off; };
+
 // UniversalOutputFile (src/file_utils.cpp:83-92): plain or gzip by extension.  ".gz" output is deflated on the
-// worker pool as a multi-member archive (pargz.hpp); with FQD_IO_THREADS=1 by zlib's gzwrite.
+// worker pool as a multi-member archive (pargz.hpp; with FQD_IO_THREADS=1 by zlib's gzwrite).  Plain output goes
+// through pwrite(): small writes are buffered, a list of runs (the survivors of a chunk) is gathered and written by
+// several workers at once, each at the file offset its bytes belong to.
 class OutputFile {
 public:
     explicit OutputFile(const std::string& name) : m_gz(has_gz_ext(name)) {
         if (m_gz && io_threads() <= 1) {
             m_g = gzopen(name.c_str(), "wb");
             if (m_g) gzbuffer(m_g, 1 << 20);
-        } else {
+        } else if (m_gz) {
             m_f = std::fopen(name.c_str(), "wb");
             if (m_f) std::setvbuf(m_f, nullptr, _IOFBF, 4 << 20);
-            if (m_f && m_gz) m_sink.reset(new ParallelGzSink(m_f));
+            if (m_f) m_sink.reset(new ParallelGzSink(m_f));
+        } else {
+            m_fd = ::open(name.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
+            m_wbuf.reserve(kBuf);
         }
     }
     ~OutputFile() { close(); }
+    OutputFile(const OutputFile&) = delete;
+    OutputFile& operator=(const OutputFile&) = delete;
     void write(const char* p, size_t n) {
         if (m_g) {
             while (n) { unsigned w = (unsigned)std::min<size_t>(n, 1u << 30); gzwrite(m_g, p, w); p += w; n -= w; }
         } else if (m_sink) {
             m_sink->write(p, n);
-        } else if (m_f) {
-            std::fwrite(p, 1, n, m_f);
+        } else if (m_fd >= 0) {
+            if (n >= kBuf) { flush(); pwrite_all(m_fd, p, n, m_off); m_off += n; return; }
+            if (m_wbuf.size() + n > kBuf) flush();
+            m_wbuf.insert(m_wbuf.end(), p, p + n);
         }
+    }
+    // runs must be sorted by out_off and dense: out_off[i+1] = out_off[i] + len[i], out_off[0] = 0
+    void write_runs(const char* base, const Run* runs, size_t n_runs, size_t total) {
+        if (m_fd < 0 || total < (8u << 20) || io_threads() <= 1) {
+            for (size_t i = 0; i < n_runs; ++i) write(base + runs[i].off, runs[i].len);
+            return;
+        }
+        flush();
+        const int parts = (int)std::min<size_t>(std::min(io_threads(), 16), total / (2u << 20));
+        const size_t per = (total + parts - 1) / parts;
+        struct Join { std::mutex mu; std::condition_variable cv; int left; };
+        Join join; join.left = parts;
+        const int fd = m_fd; const size_t file_off = m_off;
+        for (int k = 0; k < parts; ++k) {
+            const size_t lo = std::min(total, per * k), hi = std::min(total, per * (k + 1));
+            auto work = [=, &join] {
+                // first run that reaches beyond lo
+                size_t a = 0, b = n_runs;
+                while (a < b) { size_t m = (a + b) / 2; if (runs[m].out_off + runs[m].len <= lo) a = m + 1; else b = m; }
+                std::vector<char> buf;
+                size_t buf_at = lo, pos = lo;
+                for (size_t i = a; i < n_runs && pos < hi; ++i) {
+                    const size_t skip = pos - runs[i].out_off;
+                    const size_t k2 = std::min(runs[i].len - skip, hi - pos);
+                    const char* src = base + runs[i].off + skip;
+                    if (k2 >= (1u << 20)) {                     // long stretch: straight from the source
+                        if (!buf.empty()) { pwrite_all(fd, buf.data(), buf.size(), file_off + buf_at); buf.clear(); }
+                        pwrite_all(fd, src, k2, file_off + pos);
+                        buf_at = pos + k2;
+                    } else {
+                        if (buf.empty()) { buf.reserve(kBuf); buf_at = pos; }
+                        if (buf.size() + k2 > kBuf) { pwrite_all(fd, buf.data(), buf.size(), file_off + buf_at); buf_at += buf.size(); buf.clear(); }
+                        buf.insert(buf.end(), src, src + k2);
+                    }
+                    pos += k2;
+                }
+                if (!buf.empty()) pwrite_all(fd, buf.data(), buf.size(), file_off + buf_at);
+                { std::lock_guard<std::mutex> g(join.mu); --join.left; }
+                join.cv.notify_all();
+            };
+            if (k + 1 < parts) WorkerPool::shared().submit(work); else work();
+        }
+        { std::unique_lock<std::mutex> g(join.mu); join.cv.wait(g, [&] { return join.left == 0; }); }
+        m_off += total;
     }
     void close() {
         if (m_sink) { m_sink->finish(); m_sink.reset(); }
         if (m_g) { gzclose(m_g); m_g = nullptr; }
         if (m_f) { std::fclose(m_f); m_f = nullptr; }
+        if (m_fd >= 0) { flush(); ::close(m_fd); m_fd = -1; }
     }
 private:
+    static constexpr size_t kBuf = 4u << 20;
+    static void pwrite_all(int fd, const char* p, size_t n, size_t off) {
+        while (n) {
+            ssize_t w = ::pwrite(fd, p, n, (off_t)off);
+            if (w <= 0) return;                                  // a failed write is not reported (nor does the reference)
+            p += w; n -= (size_t)w; off += (size_t)w;
+        }
+    }
+    void flush() {
+        if (m_fd >= 0 && !m_wbuf.empty()) { pwrite_all(m_fd, m_wbuf.data(), m_wbuf.size(), m_off); m_off += m_wbuf.size(); m_wbuf.clear(); }
+    }
     bool m_gz;
     FILE* m_f = nullptr;
     gzFile m_g = nullptr;
+    int m_fd = -1;
+    size_t m_off = 0;
+    std::vector<char> m_wbuf;
     std::unique_ptr<ParallelGzSink> m_sink;
 };
+
+// Writes behind the caller's back, in order: one thread per output file executes the queued jobs (lists of runs
+// out of a pinned input block, or callbacks such as "hand this block back to its reader") first in, first out, so
+// the next chunk is pushed to the device while the survivors of the previous one are still being written.
+class AsyncWriter {
+public:
+    explicit AsyncWriter(OutputFile& out) : m_out(out) { m_thread = std::thread([this] { run(); }); }
+    ~AsyncWriter() {
+        { std::lock_guard<std::mutex> g(m_mu); m_stop = true; }
+        m_cv.notify_all();
+        if (m_thread.joinable()) m_thread.join();      // finishes what is queued first
+    }
+    void write_runs(const char* base, std::vector<Run>&& runs, size_t total) {
+        if (runs.empty()) return;
+        Job j; j.base = base; j.runs = std::move(runs); j.total = total;
+        push(std::move(j));
+    }
+    void then(std::function<void()> f) { Job j; j.fn = std::move(f); push(std::move(j)); }
+    void drain() {
+        std::unique_lock<std::mutex> g(m_mu);
+        m_cv.wait(g, [this] { return m_q.empty() && !m_busy; });
+    }
+private:
+    struct Job { const char* base = nullptr; std::vector<Run> runs; size_t total = 0; std::function<void()> fn; };
+    void push(Job&& j) {
+        { std::lock_guard<std::mutex> g(m_mu); m_q.push_back(std::move(j)); }
+        m_cv.notify_all();
+    }
+    void run() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> g(m_mu);
+                m_cv.wait(g, [this] { return m_stop || !m_q.empty(); });
+                if (m_q.empty()) return;
+                j = std::move(m_q.front()); m_q.pop_front();
+                m_busy = true;
+            }
+            if (j.fn) j.fn(); else m_out.write_runs(j.base, j.runs.data(), j.runs.size(), j.total);
+            { std::lock_guard<std::mutex> g(m_mu); m_busy = false; }
+            m_cv.notify_all();
+        }
+    }
+    OutputFile& m_out;
+    std::deque<Job> m_q;
+    std::mutex m_mu;
+    std::condition_variable m_cv;
+    std::thread m_thread;
+    bool m_stop = false, m_busy = false;
+};
+
+// Survivors of a chunk as runs of consecutive written records (rec_start has n + 1 entries).
+inline size_t survivor_runs(const uint32_t* rec_start, const uint8_t* dup, size_t n, std::vector<Run>& runs) {
+    runs.clear();
+    size_t total = 0, i = 0;
+    while (i < n) {
+        if (dup[i]) { ++i; continue; }
+        size_t j = i;
+        while (j + 1 < n && !dup[j + 1]) ++j;
+        const size_t len = rec_start[j + 1] - rec_start[i];
+        runs.push_back(Run{rec_start[i], len, total});
+        total += len;
+        i = j + 1;
+    }
+    return total;
+}
 
 // ClusterFile (src/file_utils.cpp:98-112): "<out>.clusters", head = ID line, member = "--" + ID line.
 class ClusterFile {

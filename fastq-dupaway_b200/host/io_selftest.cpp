@@ -3,6 +3,10 @@
 //   io_selftest cat  <file> [block_bytes]   file -> BlockReader ring -> stdout; "stats ..." line on stderr
 //   io_selftest put  <file>                 stdin -> OutputFile (plain or .gz by extension)
 //   io_selftest bench <file> [repeats]      InputFile::read into one buffer; prints uncompressed GB/s as JSON
+//   io_selftest filter <in> <out> [block]   the drivers' pipeline (dup_remover.cpp: BlockReader ring -> MateStream ->
+//                                           chunk -> survivor runs -> AsyncWriter -> OutputFile, blocks released
+//                                           behind the writes) with a stand-in for the engine's verdict: 4-line
+//                                           records, record i is dropped when i % 3 == 1; prints GB/s as JSON
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -76,6 +80,57 @@ static int cmd_bench(const std::string& name, int repeats) {
     return 0;
 }
 
+static int cmd_filter(const std::string& in, const std::string& out_name, size_t block) {
+    auto t0 = std::chrono::steady_clock::now();
+    OutputFile out(out_name);
+    MateStream ms;
+    ms.reader.reset(new BlockReader(in, block));
+    AsyncWriter writer(out);
+    {
+        AsyncWriter* w = &writer; BlockReader* r = ms.reader.get();
+        ms.release = [w, r](Block* b) { w->then([r, b] { r->release(b); }); };
+    }
+    std::vector<uint32_t> rec_start;
+    std::vector<uint8_t> dup;
+    std::vector<Run> runs;
+    size_t global = 0, in_bytes = 0;
+    for (;;) {
+        if (ms.len < block / 2) ms.refill();
+        rec_start.clear(); dup.clear();
+        rec_start.push_back(0);
+        const char* p = ms.ptr; const char* end = ms.ptr + ms.len;
+        // FQD_SELFTEST_FIXED=<bytes>: records of a fixed size (no newline search: measures the I/O pipeline alone)
+        static const size_t fixed = std::getenv("FQD_SELFTEST_FIXED") ? (size_t)std::atoll(std::getenv("FQD_SELFTEST_FIXED")) : 0;
+        for (; fixed;) {
+            if ((size_t)(end - p) < fixed) break;
+            p += fixed;
+            rec_start.push_back((uint32_t)(p - ms.ptr));
+            dup.push_back((global + dup.size()) % 3 == 1);
+        }
+        for (; !fixed;) {
+            const char* q = p; int lines = 0;
+            while (lines < 4 && q < end) { const char* nl = (const char*)memchr(q, '\n', end - q); if (!nl) break; q = nl + 1; ++lines; }
+            if (lines < 4) break;
+            p = q;
+            rec_start.push_back((uint32_t)(p - ms.ptr));
+            dup.push_back((global + dup.size()) % 3 == 1);
+        }
+        const size_t n = dup.size();
+        const size_t bytes = survivor_runs(rec_start.data(), dup.data(), n, runs);
+        writer.write_runs(ms.ptr, std::move(runs), bytes);
+        runs = std::vector<Run>();
+        global += n;
+        in_bytes += rec_start[n];
+        ms.ptr += rec_start[n]; ms.len -= rec_start[n];
+        if (n == 0 && !ms.refill()) break;
+    }
+    writer.drain();
+    out.close();
+    double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf("{\"records\": %zu, \"in_bytes\": %zu, \"threads\": %d, \"GBps\": %.3f}\n", global, in_bytes, io_threads(), (double)in_bytes / s / 1e9);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 3) { std::fprintf(stderr, "usage: io_selftest cat|stat|put|bench <file> [arg]\n"); return 64; }
     const std::string cmd = argv[1], name = argv[2];
@@ -83,6 +138,7 @@ int main(int argc, char** argv) {
         if (cmd == "cat") return cmd_cat(name, argc > 3 ? (size_t)std::atoll(argv[3]) : (4u << 20));
         if (cmd == "stat") return cmd_stat(name);
         if (cmd == "put") return cmd_put(name);
+        if (cmd == "filter" && argc > 3) return cmd_filter(name, argv[3], argc > 4 ? (size_t)std::atoll(argv[4]) : (4u << 20));
         if (cmd == "bench") return cmd_bench(name, argc > 3 ? std::atoi(argv[3]) : 3);
     } catch (const std::exception& e) {
         std::fprintf(stderr, "error: %s\n", e.what());

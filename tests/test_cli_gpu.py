@@ -13,8 +13,10 @@ EXE = ROOT / "fastq-dupaway_b200" / "host" / "fastq-dupaway"
 FIX = ROOT / "tests" / "golden" / "ref_fixtures"
 
 
-def run(*args, cwd=None):
-    return subprocess.run([str(EXE), *map(str, args)], capture_output=True, text=True, cwd=cwd)
+def run(*args, cwd=None, env=None):
+    import os
+    return subprocess.run([str(EXE), *map(str, args)], capture_output=True, text=True, cwd=cwd,
+                          env=dict(os.environ, **env) if env else None)
 
 
 def test_exe_available():
@@ -202,3 +204,24 @@ def test_arbitrary_bytes_through_files(tmp_path, oracle):
     exp, _, est = oracle.run_oracle("tail-hamming", oracle.FASTQ, buf)
     assert (tmp_path / "out.fq").read_bytes() == exp
     assert res.stdout == f"{est.total} reads processed, out of which {est.dups} duplicates were removed.\n"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("mode", ["fast", "tight"])
+def test_paired_multi_member_gzip_and_bgzf_inputs(tmp_path, oracle, mode):
+    """R1 as a multi-member archive, R2 as BGZF (both inflated member-parallel on the host, pargz.hpp), .gz outputs
+    (deflated in parallel, multi-member), many small blocks (FQD_BLOCK_BYTES) so that blocks are recycled behind the
+    asynchronous writers; byte parity of the decompressed outputs with the oracle."""
+    from test_host_io import bgzf, members
+    s1, s2 = synth.make_pair(120000, seed=77, read_len=100)
+    b1, b2 = synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2)
+    (tmp_path / "a.fq.gz").write_bytes(members(b1, [1_500_000, 20_000]))
+    (tmp_path / "b.fq.gz").write_bytes(bgzf(b2))
+    args = ["-i", tmp_path / "a.fq.gz", "-u", tmp_path / "b.fq.gz", "-o", tmp_path / "o1.fq.gz", "-p", tmp_path / "o2.fq.gz", "-v"]
+    args += ["--fast"] if mode == "fast" else ["--compare-seq", mode]
+    res = run(*args, env={"FQD_BLOCK_BYTES": str(1 << 20)})
+    assert res.returncode == 0, res.stderr
+    e1, e2, est = oracle.run_oracle(mode, oracle.FASTQ, b1, b2)
+    assert gzip.decompress((tmp_path / "o1.fq.gz").read_bytes()) == e1
+    assert gzip.decompress((tmp_path / "o2.fq.gz").read_bytes()) == e2
+    assert res.stdout == f"{est.total} read pairs processed, out of which {est.dups} duplicates were removed.\n"

@@ -217,3 +217,30 @@ def test_gz_output(tmp_path, threads):
     plain = tmp_path / "o.fq"
     run(["put", plain], threads=threads, stdin=data)
     assert plain.read_bytes() == data
+
+
+def every_third_dropped(data):
+    lines = data.split(b"\n")[:-1]
+    recs = [b"\n".join(lines[i:i + 4]) + b"\n" for i in range(0, len(lines), 4)]
+    return b"".join(r for i, r in enumerate(recs) if i % 3 != 1)
+
+
+@pytest.mark.parametrize("threads", [1, 2, 8])
+def test_driver_pipeline_with_stand_in_verdict(tmp_path, threads):
+    """BlockReader ring -> MateStream (tail carry) -> survivor runs -> AsyncWriter -> OutputFile, the way
+    dup_remover.cpp strings them together; blocks are recycled behind the asynchronous writes.  Tiny blocks make
+    every record straddle, a large block takes the concurrent pwrite path (>= 8 MiB of survivors per chunk)."""
+    data = fastq_bytes(80000, seed=12)           # 17.8 MB
+    expect = every_third_dropped(data)
+    src = tmp_path / "in.fq"
+    src.write_bytes(data)
+    gzsrc = tmp_path / "in.fq.gz"
+    gzsrc.write_bytes(members(data, [1_000_000]))
+    for block in (4096, 1 << 16, 32 << 20):
+        out = tmp_path / "out.fq"
+        st = json.loads(run(["filter", src, out, block], threads=threads).stdout)
+        assert st["records"] == 80000
+        assert out.read_bytes() == expect, block
+    outgz = tmp_path / "out.fq.gz"
+    run(["filter", gzsrc, outgz, 1 << 20], threads=threads)
+    assert gzip.decompress(outgz.read_bytes()) == expect
