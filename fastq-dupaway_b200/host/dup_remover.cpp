@@ -23,6 +23,28 @@ namespace {
 struct EngineDeleter { void operator()(fqd_handle* h) const { fqd_destroy(h); } };
 using EnginePtr = std::unique_ptr<fqd_handle, EngineDeleter>;
 
+// Everything a --fast run holds, in construction order (destroyed in reverse: engine, writers - which finish what
+// is queued -, readers and their pinned blocks, output files).
+struct OrderedJob {
+    std::vector<std::unique_ptr<OutputFile>> outs;
+    MateStream ms[2];
+    std::vector<std::unique_ptr<AsyncWriter>> writers;
+    EnginePtr eng;
+};
+
+// After a successful run the outputs are closed and nothing else needs an orderly end: unpinning gigabytes of
+// staging memory and freeing the device allocations one by one costs 0.2 - 2 s that process exit does for free
+// (main() leaves through _exit).  FQD_ORDERLY_EXIT=1 keeps the destructors (leak checkers).
+template <class T> void leave_to_the_os(std::unique_ptr<T>& job) {
+    static const bool orderly = std::getenv("FQD_ORDERLY_EXIT") != nullptr;
+    if (!orderly) (void)job.release();
+}
+
+struct WholeJob {
+    std::vector<std::unique_ptr<BlockReader>> readers;
+    EnginePtr eng;
+};
+
 struct Restart : std::exception { int what_code; explicit Restart(int c) : what_code(c) {} };
 
 [[noreturn]] void throw_engine_error(fqd_handle* h, int rc) {
@@ -119,21 +141,22 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
     const char lead = m_fasta ? '>' : '@';
     // pinned staging: 3 blocks (head room + data) per input file inside the -m budget
     size_t block = (size_t)m_memlimit / (size_t)(mates * 3 * 2);
-    block = std::min<size_t>(std::max<size_t>(block, 4u << 20), 256u << 20) & ~(size_t)4095;
+    block = std::min<size_t>(std::max<size_t>(block, 4u << 20), 64u << 20) & ~(size_t)4095;
     block = test_block_override(block);
     double growth = 1.0;
     unsigned seq_growth = 0;
 
     for (int attempt = 0; attempt < 8; ++attempt) {
         // outputs are created first, like the reference (an unreadable input leaves empty outputs behind)
-        std::vector<std::unique_ptr<OutputFile>> outs;
+        auto job = std::make_unique<OrderedJob>();
+        auto& outs = job->outs; auto& ms = job->ms; auto& writers = job->writers; auto& eng = job->eng;
         for (int m = 0; m < mates; ++m) outs.emplace_back(new OutputFile(out[m]));
-        MateStream ms[2];
+        trace("outputs created");
         for (int m = 0; m < mates; ++m) ms[m].reader.reset(new BlockReader(in[m], block));
+        trace("readers started (pinned blocks allocated)");
         // one writer thread per output: the survivors of chunk c are written while chunk c+1 is on the device; an
         // input block goes back to its reader only after the writes that read from it (declared after `ms`, so the
         // writers finish before the blocks are freed, whatever the way out of this scope)
-        std::vector<std::unique_ptr<AsyncWriter>> writers;
         for (int m = 0; m < mates; ++m) {
             writers.emplace_back(new AsyncWriter(*outs[m]));
             AsyncWriter* w = writers[m].get();
@@ -171,9 +194,11 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
         cfg.max_chunk_records = 0;
         cfg.max_tag_len = 0;
         fqd_handle* hraw = nullptr;
+        trace("first block read");
         int rc = fqd_create(&cfg, &hraw);
         if (rc) throw_engine_error(nullptr, rc);
-        EnginePtr eng(hraw);
+        eng.reset(hraw);
+        trace("engine created");
 
         bool restart = false;
         uint64_t total = 0, dups = 0;
@@ -239,16 +264,19 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
                 if (!progressed) break;      // a file is exhausted: stop at the shorter one (src/hash_dup_remover.hpp:228-230)
             }
         }
+        trace("last chunk processed");
         if (restart) continue;
         if (total == 0) {
             fqd_stats_t st; memset(&st, 0, sizeof st); st.err = FQD_ERR_EMPTY;
             throw_data_error(st, m_fasta);
         }
         close_outputs();
+        trace("outputs closed");
         if (m_verbose) {
             if (mates == 1) std::cout << total << " reads processed, out of which " << dups << " duplicates were removed.\n";
             else std::cout << total << " read pairs processed, out of which " << dups << " duplicates were removed.\n";
         }
+        leave_to_the_os(job);
         return;
     }
     throw std::runtime_error("input exceeds the device capacity of the fast-mode key store");
@@ -273,14 +301,15 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
                      const std::string* out, bool write_clusters, bool verbose, ssize_t memlimit, int device) {
     const int lpr = fasta ? 2 : 4;
     size_t block = (size_t)memlimit / (size_t)(mates * 3 * 2);
-    block = std::min<size_t>(std::max<size_t>(block, 4u << 20), 256u << 20) & ~(size_t)4095;
+    block = std::min<size_t>(std::max<size_t>(block, 4u << 20), 64u << 20) & ~(size_t)4095;
     block = test_block_override(block);
     double growth = 1.0;
     unsigned seq_growth = 0, tag_growth = 0;
     bool byte_keys = false;         // sequence-based modes order ANY byte (src/fastqview.cpp:56-67): raw-byte key rows
 
     for (int attempt = 0; attempt < 10; ++attempt) {
-        std::vector<std::unique_ptr<BlockReader>> readers;
+        auto job = std::make_unique<WholeJob>();
+        auto& readers = job->readers; auto& eng = job->eng;
         for (int m = 0; m < mates; ++m) readers.emplace_back(new BlockReader(in[m], block));
         // geometry of the first block of every file sizes the key rows and the record tables
         std::vector<Block*> first(mates, nullptr);
@@ -308,7 +337,7 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
         fqd_handle* hraw = nullptr;
         int rc = fqd_create(&cfg, &hraw);
         if (rc) throw_engine_error(nullptr, rc);
-        EnginePtr eng(hraw);
+        eng.reset(hraw);
 
         // ship every block to the device (the sort/join needs the whole input; nothing is kept on the host)
         for (int m = 0; m < mates; ++m) {
@@ -385,6 +414,7 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
                 std::cout << st.total << " read pairs processed, out of which " << st.dups << " duplicates were removed.\n";
             }
         }
+        leave_to_the_os(job);
         return;
     }
     throw std::runtime_error("input exceeds the device capacity");

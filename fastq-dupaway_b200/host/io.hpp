@@ -7,8 +7,10 @@
 #pragma once
 #include <zlib.h>
 
+#include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <filesystem>
@@ -25,6 +27,15 @@
 #include "pargz.hpp"
 
 namespace fqdhost {
+
+// FQD_TRACE=1: wall-clock checkpoints of the host pipeline on stderr (milliseconds since the first call)
+inline void trace(const char* what) {
+    static const bool on = std::getenv("FQD_TRACE") != nullptr;
+    if (!on) return;
+    static const auto t0 = std::chrono::steady_clock::now();
+    std::fprintf(stderr, "[host-trace] %9.1f ms  %s\n",
+                 std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(), what);
+}
 
 inline bool has_gz_ext(const std::string& name) { return std::filesystem::path(name).extension() == ".gz"; }
 

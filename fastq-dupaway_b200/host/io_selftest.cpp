@@ -43,9 +43,9 @@ static int cmd_stat(const std::string& name) {
     size_t total = 0;
     while (!f.eof()) total += f.read(buf.data(), buf.size());
     const ParallelGzSource* ps = f.parallel_source();
-    std::printf("{\"bytes\": %zu, \"parallel\": %s, \"bgzf\": %s, \"tasks\": %zu, \"serial_members\": %zu, \"dropped\": %zu}\n",
+    std::printf("{\"bytes\": %zu, \"parallel\": %s, \"bgzf\": %s, \"tasks\": %zu, \"serial_members\": %zu, \"dropped\": %zu, \"member_chunks\": %zu}\n",
                 total, ps ? "true" : "false", ps && ps->bgzf() ? "true" : "false", ps ? ps->parallel_tasks() : (size_t)0,
-                ps ? ps->serial_members() : (size_t)0, ps ? ps->dropped_tasks() : (size_t)0);
+                ps ? ps->serial_members() : (size_t)0, ps ? ps->dropped_tasks() : (size_t)0, ps ? ps->member_chunks() : (size_t)0);
     return 0;
 }
 
@@ -131,12 +131,43 @@ static int cmd_filter(const std::string& in, const std::string& out_name, size_t
     return 0;
 }
 
+// the block decoder of pinflate.hpp alone, one thread: the whole first member as ONE chunk, then the search
+static int cmd_rawinflate(const std::string& name) {
+    int fd = ::open(name.c_str(), O_RDONLY);
+    MappedFile mf(fd);
+    if (!mf.ok()) return 2;
+    ParallelMemberInflater probe(mf.data(), mf.size(), 0);     // parses the header
+    (void)probe;
+    pinfl::Chunk c;
+    size_t p = 10;                                             // plain header assumed (no name / extra)
+    if (mf.data()[3] & 8) { while (mf.data()[p]) ++p; ++p; }
+    c.from_bit = p * 8; c.stop_bit = mf.size() * 8; c.exact = true; c.known_window = true;
+    auto t0 = std::chrono::steady_clock::now();
+    pinfl::decode_chunk(mf.data(), mf.size(), c, (size_t)1 << 34);
+    double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf("{\"symbols\": %zu, \"failed\": %d, \"final\": %d, \"decode_GBps\": %.3f", c.sym.size(), (int)c.failed, (int)c.final_block, c.sym.size() / s / 1e9);
+    t0 = std::chrono::steady_clock::now();
+    size_t found = 0, tries = 0;
+    for (size_t b = mf.size() / 8; b < mf.size(); b += mf.size() / 8, ++tries)
+        found += pinfl::find_block(mf.data(), mf.size(), b * 8, (b + (1u << 20)) * 8) != pinfl::kNone;
+    s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf(", \"searches\": %zu, \"found\": %zu, \"ms_per_search\": %.3f", tries, found, 1e3 * s / std::max<size_t>(tries, 1));
+    pinfl::Piece pc; pc.sym.swap(c.sym);
+    t0 = std::chrono::steady_clock::now();
+    pinfl::resolve_piece(pc);
+    s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    std::printf(", \"resolve_GBps\": %.3f}\n", pc.bytes.size() / s / 1e9);
+    ::close(fd);
+    return 0;
+}
+
 int main(int argc, char** argv) {
     if (argc < 3) { std::fprintf(stderr, "usage: io_selftest cat|stat|put|bench <file> [arg]\n"); return 64; }
     const std::string cmd = argv[1], name = argv[2];
     try {
         if (cmd == "cat") return cmd_cat(name, argc > 3 ? (size_t)std::atoll(argv[3]) : (4u << 20));
         if (cmd == "stat") return cmd_stat(name);
+        if (cmd == "rawinflate") return cmd_rawinflate(name);
         if (cmd == "put") return cmd_put(name);
         if (cmd == "filter" && argc > 3) return cmd_filter(name, argv[3], argc > 4 ? (size_t)std::atoll(argv[4]) : (4u << 20));
         if (cmd == "bench") return cmd_bench(name, argc > 3 ? std::atoi(argv[3]) : 3);

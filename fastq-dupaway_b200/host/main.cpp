@@ -1,8 +1,13 @@
 // main.cpp - the drop-in `fastq-dupaway` binary: argument handling and dispatch as in the reference
 // (src/main.cpp:181-262), with the two drivers backed by the B200 engine (libfqd_cuda.so).
+#include <unistd.h>
+
+#include <cstdio>
+#include <cstdlib>
 #include <iostream>
 
 #include "dup_remover.hpp"
+#include "io.hpp"
 #include "options.hpp"
 
 using namespace fqdhost;
@@ -10,6 +15,7 @@ using namespace fqdhost;
 int main(int argc, char** argv) {
     Options opts;
     if (!parse_args(argc, argv, opts)) return 1;
+    trace("start");
     try {
         if (!opts.hash) {
             SeqDupRemover remover(opts.memLimit, opts.ctype, opts.hammdist, opts.fasta, opts.write_clusters, opts.verbose, opts.device);
@@ -28,5 +34,10 @@ int main(int argc, char** argv) {
         std::cerr << "Unknown error occured during fastq-dupaway execution!\n";
         return 1;
     }
+    trace("done");
+    // outputs are closed; the rest (CUDA context, pinned staging, worker threads) is left to process exit
+    std::cout.flush();
+    std::fflush(nullptr);
+    if (!std::getenv("FQD_ORDERLY_EXIT")) _exit(0);
     return 0;
 }

@@ -44,64 +44,10 @@
 #include <thread>
 #include <vector>
 
+#include "workers.hpp"
+#include "pinflate.hpp"
+
 namespace fqdhost {
-
-// Threads for inflate / deflate / pread: FQD_IO_THREADS, else the hardware's (at most 64).
-inline int io_threads() {
-    static const int n = [] {
-        const char* e = std::getenv("FQD_IO_THREADS");
-        int v = e ? std::atoi(e) : 0;
-        if (v <= 0) {
-            unsigned hc = std::thread::hardware_concurrency();
-            v = hc ? (int)std::min(hc, 64u) : 4;
-        }
-        return std::max(v, 1);
-    }();
-    return n;
-}
-
-// Fixed pool, FIFO with an express lane.  Tasks never wait for other tasks, so sharing one pool between all
-// readers and writers cannot deadlock.
-class WorkerPool {
-public:
-    explicit WorkerPool(int n) {
-        for (int i = 0; i < n; ++i) m_threads.emplace_back([this] { run(); });
-    }
-    ~WorkerPool() {
-        { std::lock_guard<std::mutex> g(m_mu); m_stop = true; }
-        m_cv.notify_all();
-        for (auto& t : m_threads) t.join();
-    }
-    void submit(std::function<void()> f, bool express = false) {
-        {
-            std::lock_guard<std::mutex> g(m_mu);
-            if (express) m_q.push_front(std::move(f)); else m_q.push_back(std::move(f));
-        }
-        m_cv.notify_one();
-    }
-    static WorkerPool& shared() {
-        static WorkerPool pool(io_threads());
-        return pool;
-    }
-private:
-    void run() {
-        for (;;) {
-            std::function<void()> f;
-            {
-                std::unique_lock<std::mutex> g(m_mu);
-                m_cv.wait(g, [this] { return m_stop || !m_q.empty(); });
-                if (m_q.empty()) return;          // stop requested and nothing left
-                f = std::move(m_q.front()); m_q.pop_front();
-            }
-            f();
-        }
-    }
-    std::vector<std::thread> m_threads;
-    std::deque<std::function<void()>> m_q;
-    std::mutex m_mu;
-    std::condition_variable m_cv;
-    bool m_stop = false;
-};
 
 // Read-only mapping of a regular file; ok() is false for pipes, empty files and mmap failures.
 class MappedFile {
@@ -229,12 +175,14 @@ class ParallelGzSource {
 public:
     // `span`: compressed bytes per task; `window`: tasks planned ahead of the consumer (0 = 2 x threads)
     ParallelGzSource(const unsigned char* data, size_t size, size_t span = 2u << 20, int window = 0)
-        : m_sh(std::make_shared<gzdetail::Shared>()), m_span(std::max<size_t>(span, 64)),
+        : m_sh(std::make_shared<gzdetail::Shared>()), m_span(std::max<size_t>(env_size("FQD_GZ_SPAN", span), 64)),
           m_window(window > 0 ? window : 2 * io_threads()) {
         m_sh->data = data; m_sh->size = size;
         m_sh->max_overrun = std::max<size_t>(16u << 20, 4 * m_span);
         m_sh->max_out = 512u << 20;
-        m_max_task = std::max<size_t>(32u << 20, 8 * m_span);
+        m_max_task = env_size("FQD_GZ_MAX_TASK", std::max<size_t>(8u << 20, 4 * m_span));
+        const char* e = std::getenv("FQD_PINFLATE");           // 0: members too large for a task are inflated serially
+        m_block_parallel = !(e && e[0] == '0');
         m_bgzf = gzdetail::bgzf_member_size(data, size, 0) != 0;
         m_hop = 0;
     }
@@ -247,6 +195,7 @@ public:
         for (auto& t : m_zombies) std::free(t->out);
         if (m_cur) std::free(m_cur->out);
         for (auto& b : m_spare) std::free(b.first);
+        m_member.reset();
         if (m_serial) inflateEnd(&m_z);
     }
     ParallelGzSource(const ParallelGzSource&) = delete;
@@ -258,6 +207,16 @@ public:
         size_t got = 0;
         while (got < n && !m_eof) {
             if (m_serial) { got += serial_read(dst + got, n - got); continue; }
+            if (m_member) {
+                got += m_member->read(dst + got, n - got);
+                if (m_member->done()) {
+                    m_pos = m_member->end_offset();
+                    m_member_chunks += m_member->chunks_accepted();
+                    ++m_serial_members;
+                    m_member.reset();
+                }
+                continue;
+            }
             if (m_cur) {
                 size_t k = std::min(n - got, m_cur->out_len - m_cur_off);
                 std::memcpy(dst + got, m_cur->out + m_cur_off, k);
@@ -299,7 +258,8 @@ public:
                 break;
             case TOO_BIG:
                 recycle(*t);
-                begin_serial();
+                if (m_block_parallel) m_member.reset(new ParallelMemberInflater(m_sh->data, m_sh->size, m_pos));
+                else begin_serial();
                 break;
             default:
                 recycle(*t);
@@ -311,7 +271,8 @@ public:
     bool eof() const { return m_eof; }
     // statistics for tests / the selftest's bench
     size_t parallel_tasks() const { return m_parallel_tasks; }
-    size_t serial_members() const { return m_serial_members; }
+    size_t serial_members() const { return m_serial_members; }     // members too large for a task (serial or pinflate)
+    size_t member_chunks() const { return m_member_chunks; }       // ... and the block-parallel chunks they were cut into
     size_t dropped_tasks() const { return m_dropped; }
     bool bgzf() const { return m_bgzf; }
 
@@ -442,7 +403,9 @@ private:
     TaskPtr m_cur;                    // accepted task being copied out
     size_t m_cur_off = 0;
     std::vector<std::pair<char*, size_t>> m_spare;
-    bool m_eof = false, m_serial = false;
+    bool m_eof = false, m_serial = false, m_block_parallel = true;
+    std::unique_ptr<ParallelMemberInflater> m_member;
+    size_t m_member_chunks = 0;
     z_stream m_z;
     size_t m_serial_pos = 0;
     size_t m_parallel_tasks = 0, m_serial_members = 0, m_dropped = 0;

@@ -1,0 +1,617 @@
+// pinflate.hpp - ONE gzip member inflated by many threads (the reference inflates on the main thread,
+// src/file_utils.cpp:59-66).  `gzip file.fastq` and pigz write a single member, so member-level parallelism
+// (pargz.hpp) finds nothing to split there; this does, inside the deflate stream:
+//   * the compressed range is cut at nominal byte boundaries into chunks; the task of a chunk searches, from its
+//     boundary on, the first bit position that parses as the header of a dynamic-Huffman block (complete code-length
+//     / literal / distance codes - random bits almost never pass), and decodes from there up to the first block
+//     boundary at or beyond the NEXT nominal boundary;
+//   * the 32 KiB of history before a chunk are unknown while it is decoded, so the decoder emits 16-bit symbols:
+//     a byte, or a MARKER "byte j of the window that precedes this chunk" (markers are copied by later matches like
+//     any other symbol);
+//   * the consumer walks the chunks in order.  A chunk is accepted only if it starts exactly at the bit where the
+//     accepted stream ended - the member's first block is a true start, so by induction every accepted chunk began at a
+//     true block boundary and its symbols, with the markers replaced from the now known window, are exactly the bytes
+//     zlib would have produced.  A chunk whose start was a false positive (or skipped a block the search does not
+//     recognise: stored, fixed, final) is dropped or bridged by a filler decode from the accepted position;
+//   * marker replacement + narrowing to bytes + CRC-32 of accepted chunks run on the pool again; the CRCs are combined in
+//     order and checked, with the length, against the member's trailer.
+// Own deflate decoder (zlib cannot emit markers): canonical Huffman with a 12-bit direct table and a bit-serial slow
+// path for longer codes.  Unit-tested on the CPU against Python's gzip (tests/test_host_io.py).
+#pragma once
+#include <zlib.h>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstdint>
+#include <cstdlib>
+#include <cstring>
+#include <deque>
+#include <memory>
+#include <mutex>
+#include <stdexcept>
+#include <vector>
+
+#include "workers.hpp"
+
+namespace fqdhost {
+
+namespace pinfl {
+
+constexpr unsigned kFastBits = 12;
+constexpr size_t kWindow = 32768;
+constexpr uint16_t kMarker = 0x8000;
+constexpr uint64_t kNone = ~0ull;
+
+// malloc'd array without value-initialisation (std::vector::resize would write every byte once more)
+template <class T> struct RawBuf {
+    T* p = nullptr; size_t n = 0, cap = 0;
+    RawBuf() = default;
+    RawBuf(const RawBuf&) = delete;
+    RawBuf& operator=(const RawBuf&) = delete;
+    ~RawBuf() { std::free(p); }
+    bool reserve(size_t want) {
+        if (want <= cap) return true;
+        T* q = (T*)std::realloc(p, want * sizeof(T));
+        if (!q) return false;
+        p = q; cap = want;
+        return true;
+    }
+    void swap(RawBuf& o) { std::swap(p, o.p); std::swap(n, o.n); std::swap(cap, o.cap); }
+    void release() { std::free(p); p = nullptr; n = cap = 0; }
+    size_t size() const { return n; }
+    T* data() { return p; }
+    const T* data() const { return p; }
+    T& operator[](size_t i) { return p[i]; }
+    const T& operator[](size_t i) const { return p[i]; }
+};
+
+struct BitReader {
+    const uint8_t* base; const uint8_t* p; const uint8_t* end;
+    uint64_t buf = 0; unsigned cnt = 0;
+    size_t past = 0;             // virtual zero bytes consumed beyond `end`
+    BitReader(const uint8_t* b, size_t size, uint64_t bitpos) : base(b), p(b + (bitpos >> 3)), end(b + size) {
+        if (p > end) p = end;
+        refill();
+        unsigned skip = (unsigned)(bitpos & 7);
+        buf >>= skip; cnt -= skip;
+    }
+    inline void refill() {
+        if (end - p >= 8) {
+            uint64_t v; std::memcpy(&v, p, 8);
+            buf |= v << cnt;
+            p += (63 - cnt) >> 3;
+            cnt |= 56;
+        } else {
+            while (cnt <= 56) {
+                if (p < end) buf |= (uint64_t)*p++ << cnt; else ++past;
+                cnt += 8;
+            }
+        }
+    }
+    inline uint32_t peek(unsigned n) const { return (uint32_t)(buf & ((1ull << n) - 1)); }
+    inline void drop(unsigned n) { buf >>= n; cnt -= n; }
+    inline uint32_t bits(unsigned n) { uint32_t v = peek(n); drop(n); return v; }
+    uint64_t bitpos() const { return (uint64_t)(p - base + past) * 8 - cnt; }
+    bool overrun() const { return bitpos() > (uint64_t)(end - base) * 8; }
+    void align() { drop(cnt & 7); }
+};
+
+struct Huff {
+    uint16_t fast[1u << kFastBits];     // (symbol << 4) | length, 0 = longer than kFastBits (or unused)
+    uint16_t count[16];
+    uint16_t symbol[288];
+    // returns the unused code space: 0 complete, > 0 incomplete, < 0 over-subscribed
+    int build(const uint8_t* lens, int n) {
+        std::memset(count, 0, sizeof count);
+        for (int i = 0; i < n; ++i) ++count[lens[i]];
+        int left = 1;
+        for (int l = 1; l <= 15; ++l) { left <<= 1; left -= count[l]; if (left < 0) return left; }
+        uint16_t offs[16]; offs[1] = 0;
+        for (int l = 1; l < 15; ++l) offs[l + 1] = (uint16_t)(offs[l] + count[l]);
+        for (int i = 0; i < n; ++i) if (lens[i]) symbol[offs[lens[i]]++] = (uint16_t)i;
+        std::memset(fast, 0, sizeof fast);
+        uint32_t code = 0; int idx = 0;
+        for (unsigned l = 1; l <= kFastBits; ++l) {
+            for (int k = 0; k < count[l]; ++k, ++idx, ++code) {
+                uint32_t r = 0;
+                for (unsigned b = 0; b < l; ++b) r |= ((code >> b) & 1u) << (l - 1 - b);
+                const uint16_t e = (uint16_t)((symbol[idx] << 4) | l);
+                for (uint32_t i = r; i < (1u << kFastBits); i += 1u << l) fast[i] = e;
+            }
+            code <<= 1;
+        }
+        return left;
+    }
+    // -1 on an invalid code
+    inline int decode(BitReader& br) const {
+        const uint16_t e = fast[br.peek(kFastBits)];
+        if (e) { br.drop(e & 15u); return e >> 4; }
+        int code = 0, first = 0, index = 0;
+        uint64_t b = br.buf;
+        for (int l = 1; l <= 15; ++l) {
+            code |= (int)(b & 1); b >>= 1;
+            const int c = count[l];
+            if (code - c < first) { br.drop((unsigned)l); return symbol[index + (code - first)]; }
+            index += c; first += c; first <<= 1; code <<= 1;
+        }
+        return -1;
+    }
+};
+
+static const uint16_t kLenBase[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
+static const uint8_t kLenExtra[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
+static const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145, 8193, 12289, 16385, 24577};
+static const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
+static const uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
+
+// Header of a dynamic block (after the 3 block-type bits).  strict = the search's acceptance test.
+inline bool read_dynamic_header(BitReader& br, Huff& lit, Huff& dist, bool strict) {
+    br.refill();
+    const unsigned hlit = br.bits(5) + 257, hdist = br.bits(5) + 1, hclen = br.bits(4) + 4;
+    if (hlit > 286 || hdist > 30) return false;
+    uint8_t cl[19] = {0};
+    for (unsigned i = 0; i < hclen; ++i) { if (br.cnt < 3) br.refill(); cl[kClOrder[i]] = (uint8_t)br.bits(3); }
+    unsigned kraft = 0;                                       // zlib, too, wants this code complete
+    for (int i = 0; i < 19; ++i) if (cl[i]) kraft += 128u >> cl[i];
+    if (kraft != 128u) return false;
+    Huff clh;
+    if (clh.build(cl, 19) != 0) return false;
+    uint8_t lens[286 + 30];
+    unsigned n = 0;
+    while (n < hlit + hdist) {
+        br.refill();
+        int s = clh.decode(br);
+        if (s < 0) return false;
+        if (s < 16) { lens[n++] = (uint8_t)s; continue; }
+        unsigned rep; uint8_t v = 0;
+        if (s == 16) { if (n == 0) return false; v = lens[n - 1]; rep = 3 + br.bits(2); }
+        else if (s == 17) rep = 3 + br.bits(3);
+        else rep = 11 + br.bits(7);
+        if (n + rep > hlit + hdist) return false;
+        while (rep--) lens[n++] = v;
+    }
+    if (lens[256] == 0) return false;                         // no end-of-block code
+    const int l_left = lit.build(lens, (int)hlit);
+    if (l_left < 0 || (l_left > 0 && (strict || hlit - lit.count[0] != 1))) return false;
+    const int d_left = dist.build(lens + hlit, (int)hdist);
+    if (d_left < 0) return false;
+    if (d_left > 0) {                                         // incomplete: only "at most one distance code" is legal
+        const unsigned used = hdist - dist.count[0];
+        if (used > 1) return false;
+    }
+    return !br.overrun();
+}
+
+inline void fixed_tables(Huff& lit, Huff& dist) {
+    uint8_t lens[288];
+    for (int i = 0; i < 144; ++i) lens[i] = 8;
+    for (int i = 144; i < 256; ++i) lens[i] = 9;
+    for (int i = 256; i < 280; ++i) lens[i] = 7;
+    for (int i = 280; i < 288; ++i) lens[i] = 8;
+    lit.build(lens, 288);
+    uint8_t d[30];
+    for (int i = 0; i < 30; ++i) d[i] = 5;
+    dist.build(d, 30);
+}
+
+// First bit position in [from, to) that passes as the start of a non-final dynamic block, or kNone.
+inline uint64_t find_block(const uint8_t* data, size_t size, uint64_t from, uint64_t to) {
+    auto tables = std::make_unique<std::pair<Huff, Huff>>();
+    const uint64_t total = (uint64_t)size * 8;
+    for (uint64_t b = from; b < to && b + 64 < total; ++b) {
+        // cheap gate on 13 bits: BFINAL = 0, BTYPE = 2, HLIT <= 29, HDIST <= 29
+        const size_t byte = (size_t)(b >> 3);
+        uint32_t v = 0;
+        std::memcpy(&v, data + byte, byte + 4 <= size ? 4 : size - byte);
+        v >>= (b & 7);
+        if ((v & 7u) != 4u) continue;
+        if (((v >> 3) & 31u) > 29u || ((v >> 8) & 31u) > 29u) continue;
+        BitReader br(data, size, b + 3);
+        if (!read_dynamic_header(br, tables->first, tables->second, true)) continue;
+        // a few symbols must decode to something legal
+        bool ok = true;
+        for (int i = 0; i < 64 && ok; ++i) {
+            br.refill();
+            int s = tables->first.decode(br);
+            if (s < 0 || s > 285) { ok = false; break; }
+            if (s == 256) break;
+            if (s > 256) {
+                br.drop(kLenExtra[s - 257]);
+                int d = tables->second.decode(br);
+                if (d < 0 || d > 29) { ok = false; break; }
+                br.refill();
+                br.drop(kDistExtra[d]);
+            }
+        }
+        if (ok && !br.overrun()) return b;
+    }
+    return kNone;
+}
+
+struct Chunk {
+    // plan
+    uint64_t from_bit = 0;      // exact start (exact = true) or where the search begins
+    uint64_t stop_bit = 0;      // decode up to the first block boundary at or beyond this bit
+    uint64_t search_end = 0;    // the search gives up here
+    bool exact = false;         // start is known to be a block start (first block of the member, fillers)
+    bool known_window = false;  // nothing precedes (first block of the member): a reference before the start is an error
+    // result
+    uint64_t start_bit = kNone; // where decoding began
+    uint64_t end_bit = 0;       // block boundary where it stopped
+    bool final_block = false, failed = false, truncated = false;
+    RawBuf<uint16_t> sym;
+    bool ready = false;
+};
+
+// Decode blocks from c.start_bit; symbols go to c.sym.
+inline void decode_chunk(const uint8_t* data, size_t size, Chunk& c, size_t max_symbols) {
+    if (c.exact) c.start_bit = c.from_bit;
+    else c.start_bit = find_block(data, size, c.from_bit, c.search_end);
+    if (c.start_bit == kNone) { c.failed = true; return; }
+    auto lit = std::make_unique<Huff>(); auto dist = std::make_unique<Huff>();
+    BitReader br(data, size, c.start_bit);
+    RawBuf<uint16_t>& out = c.sym;
+    if (!out.reserve(std::max<size_t>((size_t)((c.stop_bit > c.start_bit ? c.stop_bit - c.start_bit : 0) / 8) * 5 + (1u << 16), 1u << 16))) {
+        c.failed = true; return;
+    }
+    size_t n = 0;
+    const uint64_t total_bits = (uint64_t)size * 8;
+    for (;;) {
+        br.refill();
+        const unsigned bfinal = br.bits(1), btype = br.bits(2);
+        if (btype == 3) { c.failed = true; break; }
+        if (btype == 0) {
+            br.align(); br.refill();
+            const uint32_t len = br.bits(16), nlen = br.bits(16);
+            if ((len ^ nlen) != 0xFFFFu) { c.failed = true; break; }
+            if (br.bitpos() + (uint64_t)len * 8 > total_bits) { c.failed = c.truncated = true; }
+            uint64_t pos = br.bitpos() >> 3;
+            size_t take = c.truncated ? (size_t)(size - std::min<uint64_t>(size, pos)) : len;
+            if (n + take + 258 > out.cap && !out.reserve(std::max(out.cap * 2, n + take + 258))) { c.failed = true; c.truncated = false; break; }
+            for (size_t i = 0; i < take; ++i) out[n++] = data[pos + i];
+            if (c.truncated) break;
+            br = BitReader(data, size, (pos + len) * 8);
+        } else {
+            if (btype == 1) fixed_tables(*lit, *dist);
+            else if (!read_dynamic_header(br, *lit, *dist, false)) { c.failed = true; c.truncated = br.overrun(); break; }
+            bool bad = false;
+            for (;;) {
+                if (n + 258 > out.cap) {
+                    if (out.cap >= max_symbols || !out.reserve(out.cap * 2)) { bad = true; break; }
+                }
+                br.refill();
+                int s = lit->decode(br);
+                if (br.past && br.overrun()) { bad = true; break; }      // the symbol needs bits beyond the end of the file
+                if (s < 256) {
+                    if (s < 0) { bad = true; break; }
+                    out[n++] = (uint16_t)s;
+                    // a second literal from the same refill (the common case in text)
+                    const uint16_t e = lit->fast[br.peek(kFastBits)];
+                    if (e && (e >> 4) < 256 && !br.past) { br.drop(e & 15u); out[n++] = (uint16_t)(e >> 4); }
+                    continue;
+                }
+                if (s == 256) break;
+                if (s > 285) { bad = true; break; }
+                const unsigned len = kLenBase[s - 257] + br.bits(kLenExtra[s - 257]);
+                int d = dist->decode(br);
+                if (d < 0 || d > 29) { bad = true; break; }
+                br.refill();
+                const size_t dd = kDistBase[d] + br.bits(kDistExtra[d]);
+                if (br.past && br.overrun()) { bad = true; break; }
+                if (dd > n) {
+                    if (c.known_window || dd > kWindow) { bad = true; break; }
+                    // (part of) the source lies in the unknown window before this chunk
+                    for (unsigned i = 0; i < len; ++i, ++n)
+                        out[n] = dd > n ? (uint16_t)(kMarker | (kWindow - (dd - n))) : out[n - dd];
+                } else if (dd >= len) {
+                    std::memcpy(&out[n], &out[n - dd], len * sizeof(uint16_t));
+                    n += len;
+                } else {
+                    for (unsigned i = 0; i < len; ++i, ++n) out[n] = out[n - dd];
+                }
+            }
+            if (bad || br.overrun()) { c.failed = true; c.truncated = br.overrun(); break; }
+        }
+        c.end_bit = br.bitpos();
+        if (bfinal) { c.final_block = true; break; }
+        if (c.end_bit >= c.stop_bit) break;
+    }
+    if (c.failed && !c.truncated) n = 0;
+    out.n = n;
+}
+
+struct Piece {           // an accepted chunk on its way to bytes
+    RawBuf<uint16_t> sym;
+    std::vector<uint8_t> window;     // the 32 KiB before it (shorter at the start of the member)
+    RawBuf<char> bytes;
+    uint32_t crc = 0;
+    bool ready = false, bad = false; // bad: a marker points before the start of the member's output
+};
+
+inline void resolve_piece(Piece& pc) {
+    const size_t n = pc.sym.size();
+    if (!pc.bytes.reserve(std::max<size_t>(n, 1))) { pc.bad = true; return; }
+    pc.bytes.n = n;
+    const uint8_t* w = pc.window.data();
+    const size_t missing = kWindow - pc.window.size();   // markers index a full window; its first `missing` bytes do not exist
+    const uint16_t* s = pc.sym.data();
+    char* o = pc.bytes.data();
+    size_t i = 0;
+    while (i < n) {
+        // stretches without markers (everything, some 100 KB into a chunk of text) are narrowed 16 symbols at a time
+#if defined(__SSE2__)
+        while (i + 16 <= n) {
+            const __m128i a = _mm_loadu_si128((const __m128i*)(s + i)), b = _mm_loadu_si128((const __m128i*)(s + i + 8));
+            if (_mm_movemask_epi8(_mm_or_si128(a, b)) & 0xAAAA) break;           // bit 15 of some symbol: a marker
+            _mm_storeu_si128((__m128i*)(o + i), _mm_packus_epi16(a, b));
+            i += 16;
+        }
+#else
+        while (i + 16 <= n) {
+            uint16_t any = 0;
+            for (int k = 0; k < 16; ++k) any |= s[i + k];
+            if (any & kMarker) break;
+            for (int k = 0; k < 16; ++k) o[i + k] = (char)s[i + k];
+            i += 16;
+        }
+#endif
+        const size_t stop = std::min(n, i + 16);
+        for (; i < stop; ++i) {
+            const uint16_t v = s[i];
+            if (v < kMarker) { o[i] = (char)v; continue; }
+            const size_t j = v & 0x7FFFu;
+            if (j < missing) { pc.bad = true; o[i] = 0; } else o[i] = (char)w[j - missing];
+        }
+    }
+    pc.crc = (uint32_t)crc32_z(0L, (const Bytef*)o, n);
+}
+
+}  // namespace pinfl
+
+// size knobs for tests (small files must still be cut into many pieces)
+inline size_t env_size(const char* name, size_t dflt) {
+    const char* e = std::getenv(name);
+    long long v = e ? std::atoll(e) : 0;
+    return v > 0 ? (size_t)v : dflt;
+}
+
+class ParallelMemberInflater {
+public:
+    // data/size: the whole mapped file; member_start: offset of a gzip member header
+    ParallelMemberInflater(const unsigned char* data, size_t size, size_t member_start, size_t chunk_bytes = 1u << 20, int window = 0);
+    ~ParallelMemberInflater();
+    ParallelMemberInflater(const ParallelMemberInflater&) = delete;
+    ParallelMemberInflater& operator=(const ParallelMemberInflater&) = delete;
+    // up to n bytes of the member; 0 once it is complete (then done() is true)
+    size_t read(char* dst, size_t n);
+    bool done() const { return m_done; }
+    bool truncated() const { return m_truncated; }
+    size_t end_offset() const { return m_end_offset; }    // first byte after the member's trailer
+    size_t chunks_accepted() const { return m_accepted; }
+    size_t chunks_dropped() const { return m_dropped; }
+    size_t fillers() const { return m_fillers; }
+
+private:
+    struct Sync {
+        std::mutex mu; std::condition_variable cv; int inflight = 0;
+        // symbol / byte arrays go round (a fresh multi-megabyte malloc is an mmap + a page fault per 4 KiB)
+        std::vector<std::unique_ptr<pinfl::RawBuf<uint16_t>>> spare_sym;
+        std::vector<std::unique_ptr<pinfl::RawBuf<char>>> spare_bytes;
+        template <class T> static void take(std::vector<std::unique_ptr<pinfl::RawBuf<T>>>& from, pinfl::RawBuf<T>& into) {
+            if (!from.empty()) { into.swap(*from.back()); into.n = 0; from.pop_back(); }
+        }
+        template <class T> static void give(std::vector<std::unique_ptr<pinfl::RawBuf<T>>>& to, pinfl::RawBuf<T>& b, size_t keep) {
+            if (b.p && to.size() < keep) { to.emplace_back(new pinfl::RawBuf<T>()); to.back()->swap(b); }
+            b.release();
+        }
+    };
+    using ChunkPtr = std::shared_ptr<pinfl::Chunk>;
+    using PiecePtr = std::shared_ptr<pinfl::Piece>;
+    void launch(ChunkPtr c, bool express);
+    void top_up();
+    enum Step { ADVANCED, WINDOW_FULL, CHAIN_DONE };
+    Step advance_chain();        // look at the oldest planned chunk: accept / drop / bridge
+    void accept(ChunkPtr c);
+
+    const unsigned char* m_data; size_t m_size;
+    size_t m_chunk; int m_window;
+    std::shared_ptr<Sync> m_sync;
+    size_t m_deflate_start = 0;
+    size_t m_next_boundary = 0;          // nominal byte boundary of the next chunk to plan
+    std::deque<ChunkPtr> m_chunks;       // planned, in stream order
+    std::deque<PiecePtr> m_pieces;       // accepted, being resolved / copied out
+    size_t m_piece_off = 0;
+    uint64_t m_end_bit = 0;              // accepted stream ends here
+    std::vector<uint8_t> m_win;          // last <= 32 KiB of accepted output
+    uint32_t m_crc = 0; uint64_t m_len = 0;
+    bool m_chain_done = false, m_done = false, m_truncated = false, m_first = true;
+    size_t m_end_offset = 0;
+    size_t m_accepted = 0, m_dropped = 0, m_fillers = 0;
+};
+
+// ---- implementation -------------------------------------------------------------------------------------------
+inline ParallelMemberInflater::ParallelMemberInflater(const unsigned char* data, size_t size, size_t member_start,
+                                                      size_t chunk_bytes, int window)
+    : m_data(data), m_size(size), m_chunk(std::max<size_t>(env_size("FQD_PINFLATE_CHUNK", chunk_bytes), 1u << 12)),
+      m_window(window > 0 ? window : 2 * io_threads() + 2), m_sync(std::make_shared<Sync>()) {
+    // gzip header (RFC 1952): magic, CM = 8, FLG, MTIME(4), XFL, OS, then optional FEXTRA / FNAME / FCOMMENT / FHCRC
+    size_t p = member_start;
+    auto need = [&](size_t k) { if (p + k > size) throw std::runtime_error("gzip error"); };
+    need(10);
+    if (data[p] != 0x1f || data[p + 1] != 0x8b || data[p + 2] != 8) throw std::runtime_error("gzip error");
+    const unsigned flg = data[p + 3];
+    p += 10;
+    if (flg & 4) { need(2); size_t xlen = data[p] | (size_t)data[p + 1] << 8; p += 2; need(xlen); p += xlen; }
+    for (unsigned bit : {8u, 16u})
+        if (flg & bit) { while (p < size && data[p]) ++p; need(1); ++p; }
+    if (flg & 2) { need(2); p += 2; }
+    m_deflate_start = p;
+    m_end_bit = (uint64_t)p * 8;
+    m_next_boundary = p;
+}
+
+inline ParallelMemberInflater::~ParallelMemberInflater() {
+    std::unique_lock<std::mutex> g(m_sync->mu);
+    m_sync->cv.wait(g, [this] { return m_sync->inflight == 0; });
+}
+
+inline void ParallelMemberInflater::launch(ChunkPtr c, bool express) {
+    std::shared_ptr<Sync> sy = m_sync;
+    const unsigned char* data = m_data; const size_t size = m_size;
+    const size_t max_symbols = std::max<size_t>(m_chunk * 1100, 64u << 20);     // deflate expands at most ~1032 x
+    { std::lock_guard<std::mutex> g(sy->mu); ++sy->inflight; }
+    const size_t keep = (size_t)m_window;
+    WorkerPool::shared().submit([sy, c, data, size, max_symbols, keep] {
+        { std::lock_guard<std::mutex> g(sy->mu); Sync::take(sy->spare_sym, c->sym); }
+        pinfl::decode_chunk(data, size, *c, max_symbols);
+        { std::lock_guard<std::mutex> g(sy->mu); if (c->sym.n == 0) Sync::give(sy->spare_sym, c->sym, keep); c->ready = true; --sy->inflight; }
+        sy->cv.notify_all();
+    }, express);
+}
+
+inline void ParallelMemberInflater::top_up() {
+    while ((int)(m_chunks.size() + m_pieces.size()) < m_window && m_next_boundary < m_size) {
+        auto c = std::make_shared<pinfl::Chunk>();
+        const size_t next = std::min(m_size, m_next_boundary + m_chunk);
+        c->from_bit = (uint64_t)m_next_boundary * 8;
+        c->stop_bit = (uint64_t)next * 8;
+        c->search_end = c->stop_bit;
+        if (m_first) { c->exact = true; c->known_window = true; m_first = false; }
+        m_next_boundary = next;
+        m_chunks.push_back(c);
+        launch(c, false);
+    }
+}
+
+inline void ParallelMemberInflater::accept(ChunkPtr c) {
+    using namespace pinfl;
+    auto pc = std::make_shared<Piece>();
+    pc->window = m_win;
+    pc->sym.swap(c->sym);
+    // the window the next chunk will need: the last 32 KiB of (window + this chunk), markers replaced
+    const size_t n = pc->sym.size();
+    const size_t keep_old = n >= kWindow ? 0 : std::min(m_win.size(), kWindow - n);
+    std::vector<uint8_t> nw;
+    nw.reserve(kWindow);
+    nw.insert(nw.end(), m_win.end() - (ptrdiff_t)keep_old, m_win.end());
+    const size_t missing = kWindow - m_win.size();
+    for (size_t i = n - std::min(n, kWindow); i < n; ++i) {
+        const uint16_t v = pc->sym[i];
+        if (v < kMarker) nw.push_back((uint8_t)v);
+        else {
+            const size_t j = v & 0x7FFFu;
+            if (j < missing) throw std::runtime_error("gzip error");       // distance too far back
+            nw.push_back(m_win[j - missing]);
+        }
+    }
+    m_win.swap(nw);
+    m_end_bit = c->end_bit;
+    ++m_accepted;
+    m_pieces.push_back(pc);
+    std::shared_ptr<Sync> sy = m_sync;
+    { std::lock_guard<std::mutex> g(sy->mu); ++sy->inflight; }
+    const size_t keep = (size_t)m_window;
+    WorkerPool::shared().submit([sy, pc, keep] {
+        { std::lock_guard<std::mutex> g(sy->mu); Sync::take(sy->spare_bytes, pc->bytes); }
+        resolve_piece(*pc);
+        { std::lock_guard<std::mutex> g(sy->mu); Sync::give(sy->spare_sym, pc->sym, keep); pc->ready = true; --sy->inflight; }
+        sy->cv.notify_all();
+    }, true);
+}
+
+// One step of the chain: look at the oldest planned chunk, accept / drop / bridge.
+inline ParallelMemberInflater::Step ParallelMemberInflater::advance_chain() {
+    using namespace pinfl;
+    if (m_chain_done) return CHAIN_DONE;
+    top_up();
+    if (m_chunks.empty() && m_next_boundary < m_size) return WINDOW_FULL;   // accepted pieces wait to be read first
+    if (m_chunks.empty()) {
+        // the plan reached the end of the file without a final block: bridge from the accepted position
+        if (m_end_bit >= (uint64_t)m_size * 8) { m_chain_done = true; m_truncated = true; m_end_offset = m_size; return CHAIN_DONE; }
+        auto f = std::make_shared<Chunk>();
+        f->from_bit = m_end_bit; f->exact = true; f->known_window = m_accepted == 0;
+        f->stop_bit = (uint64_t)m_size * 8;
+        m_chunks.push_back(f); ++m_fillers;
+        launch(f, true);
+    }
+    ChunkPtr c = m_chunks.front();
+    {
+        std::unique_lock<std::mutex> g(m_sync->mu);
+        m_sync->cv.wait(g, [&] { return c->ready; });
+    }
+    const bool usable = !c->failed || c->truncated;
+    if (c->exact && c->start_bit == m_end_bit) {
+        if (!usable) throw std::runtime_error("gzip error");                 // a decode from a true block start failed
+    } else if (!usable || c->start_bit == kNone || c->start_bit < m_end_bit) {
+        m_chunks.pop_front(); ++m_dropped;                                   // false start, or nothing found: overtaken
+        return ADVANCED;
+    } else if (c->start_bit > m_end_bit) {
+        // a gap between the accepted stream and this chunk's start: decode it, up to that start
+        auto f = std::make_shared<Chunk>();
+        f->from_bit = m_end_bit; f->exact = true; f->known_window = m_accepted == 0;
+        f->stop_bit = c->start_bit;
+        m_chunks.push_front(f); ++m_fillers;
+        launch(f, true);
+        return ADVANCED;
+    }
+    // starts exactly where the accepted stream ends
+    m_chunks.pop_front();
+    accept(c);
+    if (c->truncated) { m_chain_done = true; m_truncated = true; m_end_offset = m_size; return CHAIN_DONE; }
+    if (c->final_block) {
+        m_chain_done = true;
+        const size_t trailer = (size_t)((m_end_bit + 7) >> 3);
+        if (trailer + 8 > m_size) { m_truncated = true; m_end_offset = m_size; }
+        else m_end_offset = trailer + 8;
+        return CHAIN_DONE;
+    }
+    return ADVANCED;
+}
+
+inline size_t ParallelMemberInflater::read(char* dst, size_t n) {
+    size_t got = 0;
+    while (got < n && !m_done) {
+        if (!m_pieces.empty()) {
+            PiecePtr pc = m_pieces.front();
+            // keep the chain moving while the head piece is being resolved
+            for (;;) {
+                { std::lock_guard<std::mutex> g(m_sync->mu); if (pc->ready) break; }
+                if (advance_chain() != ADVANCED) {
+                    std::unique_lock<std::mutex> g(m_sync->mu);
+                    m_sync->cv.wait(g, [&] { return pc->ready; });
+                    break;
+                }
+            }
+            if (pc->bad) throw std::runtime_error("gzip error");
+            if (m_piece_off == 0) {
+                m_crc = (uint32_t)crc32_combine(m_crc, pc->crc, (z_off_t)pc->bytes.size());
+                m_len += pc->bytes.size();
+            }
+            const size_t k = std::min(n - got, pc->bytes.size() - m_piece_off);
+            std::memcpy(dst + got, pc->bytes.data() + m_piece_off, k);
+            got += k; m_piece_off += k;
+            if (m_piece_off == pc->bytes.size()) {
+                { std::lock_guard<std::mutex> g(m_sync->mu); Sync::give(m_sync->spare_bytes, pc->bytes, (size_t)m_window); }
+                m_pieces.pop_front(); m_piece_off = 0;
+            }
+            continue;
+        }
+        if (m_chain_done) {
+            if (!m_truncated) {
+                const unsigned char* t = m_data + m_end_offset - 8;
+                const uint32_t crc = t[0] | (uint32_t)t[1] << 8 | (uint32_t)t[2] << 16 | (uint32_t)t[3] << 24;
+                const uint32_t isz = t[4] | (uint32_t)t[5] << 8 | (uint32_t)t[6] << 16 | (uint32_t)t[7] << 24;
+                if (crc != m_crc || isz != (uint32_t)m_len) throw std::runtime_error("gzip error");
+            }
+            m_done = true;
+            break;
+        }
+        advance_chain();
+    }
+    return got;
+}
+
+}  // namespace fqdhost

@@ -225,3 +225,18 @@ def test_paired_multi_member_gzip_and_bgzf_inputs(tmp_path, oracle, mode):
     assert gzip.decompress((tmp_path / "o1.fq.gz").read_bytes()) == e1
     assert gzip.decompress((tmp_path / "o2.fq.gz").read_bytes()) == e2
     assert res.stdout == f"{est.total} read pairs processed, out of which {est.dups} duplicates were removed.\n"
+
+
+@pytest.mark.gpu
+def test_single_member_gzip_inflated_block_parallel(tmp_path, oracle):
+    """`gzip reads.fq` writes ONE member; the host cuts its deflate stream into chunks and inflates them on all
+    threads (pinflate.hpp).  Small chunk sizes so that this small archive is cut into dozens of pieces."""
+    from test_host_io import SMALL, deflate_gz
+    seqs = synth.make_reads(80000, seed=78, read_len=100, var_len=True, n_frac=0.02, dup_frac=0.4)
+    buf = synth.to_fastq(seqs)
+    (tmp_path / "in.fq.gz").write_bytes(deflate_gz(buf, 6))
+    res = run("-i", tmp_path / "in.fq.gz", "-o", tmp_path / "out.fq", "--fast", "-v", env=dict(SMALL, FQD_BLOCK_BYTES=str(1 << 20)))
+    assert res.returncode == 0, res.stderr
+    exp, _, est = oracle.run_oracle("fast", oracle.FASTQ, buf)
+    assert (tmp_path / "out.fq").read_bytes() == exp
+    assert res.stdout == f"{est.total} reads processed, out of which {est.dups} duplicates were removed.\n"

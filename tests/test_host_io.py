@@ -28,8 +28,8 @@ def build_selftest():
     assert EXE.exists()
 
 
-def run(args, threads=4, stdin=None, check=True):
-    env = dict(os.environ, FQD_IO_THREADS=str(threads))
+def run(args, threads=4, stdin=None, check=True, env=None):
+    env = dict(os.environ, FQD_IO_THREADS=str(threads), **(env or {}))
     p = subprocess.run([str(EXE)] + [str(a) for a in args], input=stdin, capture_output=True, env=env, timeout=300)
     if check:
         assert p.returncode == 0, p.stderr.decode()
@@ -69,10 +69,10 @@ def bgzf(data, block=0xff00, eof_marker=True):
     return b"".join(out)
 
 
-def check_file(path, expect, threads=4, block=1 << 16):
-    got = run(["cat", path, block], threads=threads).stdout
+def check_file(path, expect, threads=4, block=1 << 16, env=None):
+    got = run(["cat", path, block], threads=threads, env=env).stdout
     assert got == expect
-    return json.loads(run(["stat", path], threads=threads).stdout)
+    return json.loads(run(["stat", path], threads=threads, env=env).stdout)
 
 
 @pytest.mark.parametrize("threads", [1, 2, 8])
@@ -244,3 +244,89 @@ def test_driver_pipeline_with_stand_in_verdict(tmp_path, threads):
     outgz = tmp_path / "out.fq.gz"
     run(["filter", gzsrc, outgz, 1 << 20], threads=threads)
     assert gzip.decompress(outgz.read_bytes()) == expect
+
+
+# ---- one member, many threads (pinflate.hpp) ---------------------------------------------------------------------
+# small files are cut into many pieces: 16 KiB chunks, every member above 64 KiB goes to the block-parallel decoder
+SMALL = {"FQD_PINFLATE_CHUNK": str(16 << 10), "FQD_GZ_MAX_TASK": str(64 << 10), "FQD_GZ_SPAN": str(32 << 10)}
+
+
+def deflate_gz(data, level=6, strategy=zlib.Z_DEFAULT_STRATEGY, mem=8):
+    c = zlib.compressobj(level, zlib.DEFLATED, 31, mem, strategy)
+    return c.compress(data) + c.flush()
+
+
+def payloads():
+    rng = random.Random(21)
+    text = fastq_bytes(30000, seed=20)                                   # 6.6 MB of FASTQ
+    noise = bytes(rng.getrandbits(8) for _ in range(1 << 20))            # incompressible: stored blocks
+    runs = b"".join(bytes([rng.randrange(4)]) * rng.randrange(1, 70000) for _ in range(200))   # long matches, distance 1
+    far = (noise[:30000] + b"x" * 2000) * 60                             # matches at distances close to 32 KiB
+    return {"text": text, "noise": noise, "runs": runs, "far": far, "mixed": text[:2_000_000] + noise + runs + far + text[2_000_000:]}
+
+
+@pytest.mark.parametrize("threads", [2, 8])
+@pytest.mark.parametrize("name", ["text", "noise", "runs", "far", "mixed"])
+def test_single_member_block_parallel(tmp_path, threads, name):
+    data = payloads()[name]
+    f = tmp_path / "one.gz"
+    for level, strategy in ((6, zlib.Z_DEFAULT_STRATEGY), (1, zlib.Z_DEFAULT_STRATEGY), (9, zlib.Z_DEFAULT_STRATEGY),
+                            (6, zlib.Z_FIXED), (6, zlib.Z_HUFFMAN_ONLY), (6, zlib.Z_RLE), (0, zlib.Z_DEFAULT_STRATEGY)):
+        f.write_bytes(deflate_gz(data, level, strategy))
+        st = check_file(f, data, threads, env=SMALL)
+        if f.stat().st_size > (64 << 10) + 100:        # smaller archives are one ordinary task
+            assert st["serial_members"] == 1 and st["member_chunks"] >= 1, (level, strategy, st)
+    # small blocks (memLevel 1): thousands of block boundaries
+    f.write_bytes(deflate_gz(data, 6, mem=1))
+    st = check_file(f, data, threads, env=SMALL)
+    assert st["member_chunks"] > 4 or name in ("runs", "noise", "far")
+
+
+def test_single_member_block_parallel_default_sizes(tmp_path):
+    """default sizes: 1 MiB chunks, members above 8 MiB of compressed data"""
+    data = fastq_bytes(30000, seed=22) * 8            # 53 MB, ~10 MB compressed at level 1
+    f = tmp_path / "big.fq.gz"
+    f.write_bytes(deflate_gz(data, 1))
+    assert f.stat().st_size > (8 << 20)
+    st = check_file(f, data, 8, block=4 << 20)
+    assert st["serial_members"] == 1 and st["member_chunks"] >= 4
+    # the same through the serial zlib path
+    assert run(["cat", f, 4 << 20], threads=8, env={"FQD_PINFLATE": "0"}).stdout == data
+
+
+def test_single_member_header_fields_and_neighbours(tmp_path):
+    import io
+    data = payloads()["text"]
+    buf = io.BytesIO()
+    with gzip.GzipFile(filename="reads_with_a_name.fastq", mode="wb", fileobj=buf, compresslevel=6, mtime=12345) as g:
+        g.write(data)
+    named = buf.getvalue()
+    assert named[3] & 8                                # FNAME present
+    extra = bytearray(deflate_gz(data))
+    extra[3] |= 4                                      # FEXTRA: splice a subfield in after the fixed header
+    extra = bytes(extra[:10]) + struct.pack("<H", 8) + b"ZZ" + struct.pack("<H", 4) + b"abcd" + bytes(extra[10:])
+    small = fastq_bytes(300, seed=23)
+    f = tmp_path / "n.gz"
+    for blob, expect in ((named, data), (extra, data),
+                         (members(small, [10000]) + named + members(small, [7000]) + extra, small + data + small + data)):
+        f.write_bytes(blob)
+        check_file(f, expect, 4, env=SMALL)
+
+
+def test_single_member_truncated_and_corrupt(tmp_path):
+    data = payloads()["text"]
+    blob = deflate_gz(data)
+    f = tmp_path / "t.gz"
+    f.write_bytes(blob[:len(blob) * 2 // 3])
+    a = run(["cat", f], threads=1).stdout                      # serial zlib
+    b = run(["cat", f], threads=4, env=SMALL).stdout           # block-parallel
+    assert a == b and data.startswith(b) and len(b) > len(data) // 2
+    # trailer cut off: all the data, no error (as the serial path)
+    f.write_bytes(blob[:-5])
+    assert run(["cat", f], threads=4, env=SMALL).stdout == data
+    for pos in (len(blob) // 3, len(blob) - 6, len(blob) - 2):    # body, CRC-32, ISIZE
+        bad = bytearray(blob)
+        bad[pos] ^= 0x04
+        f.write_bytes(bytes(bad))
+        p = run(["cat", f], threads=4, env=SMALL, check=False)
+        assert p.returncode == 1 and b"gzip error" in p.stderr, pos
