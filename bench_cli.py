@@ -1,9 +1,9 @@
 """Files in, files out: the drop-in binary (fastq-dupaway_b200/host/fastq-dupaway) against the reference binary
 (oracle/_ref/fastq-dupaway, the unmodified sources compiled by oracle/Makefile) on the SAME input file, both started
-the way a user starts them.  This is the end-to-end number of the whole product - host ingest (plain / multi-member
-gzip / BGZF), pinned staging, H2D, kernels, D2H, output gather and file writes - next to bench.py's kernel-level lines.
+the way a user starts them.  This is the end-to-end number of the whole product - host ingest (plain / single-member gzip /
+multi-member gzip / BGZF), pinned staging, H2D, kernels, D2H, output gather and file writes - next to bench.py's kernel-level lines.
 
-    python bench_cli.py [--reads 10000000] [--ref-reads 2000000] [--formats plain,gzmm,bgzf] [--mode fast|tight]
+    python bench_cli.py [--reads 10000000] [--ref-reads 2000000] [--formats plain,gz1,gzmm,bgzf] [--mode fast|tight]
 
 The input is the synthetic stream of bench.py (device generator, 150 bp, 30 % duplicates) written to tmpfs.  The
 reference is timed on a prefix (--ref-reads; it is single-threaded, ~0.5 M reads/s) and on plain input only.  One JSON
@@ -68,19 +68,49 @@ def gz_members(src: Path, dst: Path, piece: int, bgzf: bool):
             f.write(blob)
 
 
-def timed(cmd, cwd):
+def gz_single_member(src: Path, dst: Path, piece: int = 8 << 20):
+    """ONE gzip member, as `gzip` / pigz write it, built from pieces deflated in threads (each ends in a sync flush,
+    i.e. byte aligned and not final - pigz's construction, without its dictionary priming)"""
+    data = src.read_bytes()
+    starts = list(range(0, len(data), piece))
+
+    def one(pos):
+        c = zlib.compressobj(1, zlib.DEFLATED, -15)
+        body = c.compress(data[pos:pos + piece])
+        return body + (c.flush(zlib.Z_FINISH) if pos == starts[-1] else c.flush(zlib.Z_SYNC_FLUSH))
+    with ThreadPoolExecutor(max_workers=min(32, os.cpu_count() or 4)) as ex, open(dst, "wb") as f:
+        f.write(b"\x1f\x8b\x08\x00\0\0\0\0\x00\xff")
+        for blob in ex.map(one, starts):
+            f.write(blob)
+        f.write(struct.pack("<II", zlib.crc32(data), len(data) & 0xFFFFFFFF))
+
+
+def timed(cmd, cwd, trace=False):
+    env = dict(os.environ, FQD_TRACE="1") if trace else None
     t0 = time.perf_counter()
-    res = subprocess.run([str(c) for c in cmd], cwd=cwd, capture_output=True, text=True)
+    res = subprocess.run([str(c) for c in cmd], cwd=cwd, capture_output=True, text=True, env=env)
     dt = time.perf_counter() - t0
     assert res.returncode == 0, res.stderr
-    return dt, res.stdout.strip()
+    if not trace:
+        return dt, res.stdout.strip()
+    # [host-trace] <ms> ms  <label>: CUDA start-up (context, pinned staging, engine) vs the streaming part
+    marks = {}
+    for line in res.stderr.splitlines():
+        if line.startswith("[host-trace]"):
+            ms, label = line[len("[host-trace]"):].split("ms", 1)
+            marks[label.strip()] = float(ms)
+    phases = {}
+    if "engine created" in marks and "outputs closed" in marks:
+        phases = {"startup_s": round(marks["engine created"] / 1e3, 3),
+                  "stream_s": round((marks["outputs closed"] - marks["engine created"]) / 1e3, 3)}
+    return dt, res.stdout.strip(), phases
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reads", type=int, default=10_000_000)
     ap.add_argument("--ref-reads", type=int, default=2_000_000)
-    ap.add_argument("--formats", default="plain,gzmm,bgzf")
+    ap.add_argument("--formats", default="plain,gz1,gzmm,bgzf")
     ap.add_argument("--mode", default="fast", choices=["fast", "tight"])
     ap.add_argument("--repeats", type=int, default=2)
     args = ap.parse_args()
@@ -98,13 +128,20 @@ def main():
             elif fmt == "bgzf":
                 inputs[fmt] = tmp / "in_bgzf.fq.gz"
                 gz_members(full, inputs[fmt], 0xff00, True)
+            elif fmt == "gz1":
+                inputs[fmt] = tmp / "in_single.fq.gz"
+                gz_single_member(full, inputs[fmt])
         for fmt in args.formats.split(","):
             inp = inputs[fmt]
             best = None
+            phases = {}
             for _ in range(args.repeats):
-                dt, so = timed([EXE, "-i", inp, "-o", tmp / "out.fq", "-v", *mode_args], tmp)
-                best = dt if best is None else min(best, dt)
-            print(json.dumps({"impl": "ours", "binary": "fastq-dupaway_b200/host/fastq-dupaway", "mode": args.mode, "input": fmt,
+                dt, so, ph = timed([EXE, "-i", inp, "-o", tmp / "out.fq", "-v", *mode_args], tmp, trace=True)
+                if best is None or dt < best:
+                    best, phases = dt, ph
+            if phases.get("stream_s"):
+                phases["stream_reads_per_s"] = round(args.reads / phases["stream_s"])
+            print(json.dumps({"impl": "ours", **phases, "binary": "fastq-dupaway_b200/host/fastq-dupaway", "mode": args.mode, "input": fmt,
                               "reads": args.reads, "input_bytes": inp.stat().st_size, "seconds": round(best, 3),
                               "reads_per_s": round(args.reads / best), "raw_GBps": round(args.reads * REC / best / 1e9, 3),
                               "io_threads": os.environ.get("FQD_IO_THREADS", "auto"), "host_cores": os.cpu_count(), "stdout": so}), flush=True)
@@ -122,6 +159,15 @@ def main():
                               "seconds": round(dt_r, 3), "reads_per_s": round(n / dt_r), "cores": 1, "stdout": so_r,
                               "ours_same_input_seconds": round(dt_o, 3), "outputs_byte_identical": same,
                               "verbose_lines_identical": so_o == so_r}), flush=True)
+            if "gz1" in inputs:
+                # the reference on a single-member .gz of the same prefix (its gzip filter runs on the same one thread)
+                gz_single_member(pre, tmp / "pre.fq.gz")
+                dt_g, _ = timed([oracle.REF_BIN, "-i", tmp / "pre.fq.gz", "-o", tmp / "o_ref_gz.fq", "-v", *ref_args], tmp)
+                dt_og, _ = timed([EXE, "-i", tmp / "pre.fq.gz", "-o", tmp / "o_ours_gz.fq", "-v", *mode_args], tmp)
+                same = (tmp / "o_ours_gz.fq").read_bytes() == (tmp / "o_ref_gz.fq").read_bytes()
+                print(json.dumps({"impl": "reference", "binary": "oracle/_ref/fastq-dupaway", "mode": args.mode, "input": "gz1", "reads": n,
+                                  "seconds": round(dt_g, 3), "reads_per_s": round(n / dt_g), "cores": 1,
+                                  "ours_same_input_seconds": round(dt_og, 3), "outputs_byte_identical": same}), flush=True)
         else:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/fastq-dupaway not built"}), flush=True)
     finally:
