@@ -123,49 +123,47 @@ struct Shared {
     int inflight = 0;
 };
 
-// Inflate whole members from t.start until one ends at or beyond t.limit.
+// Inflate whole members from t.start until one ends at or beyond t.limit (pinflate.hpp's decoder in byte mode: the
+// window is known - nothing precedes a member -, CRC-32 and length are checked against each trailer).
 inline void inflate_task(Shared& sh, Task& t) {
+    using namespace pinfl;
     const unsigned char* d = sh.data;
-    z_stream z;
-    std::memset(&z, 0, sizeof z);
-    if (inflateInit2(&z, 15 + 16) != Z_OK) { t.status = FAILED; return; }
-    size_t in_pos = t.start;
+    RawBuf<uint8_t> out;                                  // borrows the task's (recycled) array
+    out.p = (uint8_t*)t.out; out.cap = t.out_cap; out.n = 0;
     const size_t in_stop = std::min(sh.size, t.limit + sh.max_overrun);   // give up beyond this without a member end
+    size_t pos = t.start;
     t.end = t.start;
     Status st = PENDING;
+    if (!out.reserve(std::max<size_t>((t.limit - t.start) * 4 + (64u << 10), 1u << 20))) st = FAILED;
     while (st == PENDING) {
         if (sh.cancel.load(std::memory_order_relaxed)) { st = FAILED; break; }
-        if (t.out_len == t.out_cap) {
-            size_t ncap = t.out_cap ? t.out_cap * 2 : std::max<size_t>((t.limit - t.start) * 4 + (64u << 10), 1u << 20);
-            if (t.out_cap >= sh.max_out) { st = TOO_BIG; break; }
-            char* np = (char*)std::realloc(t.out, ncap);
-            if (!np) { st = FAILED; break; }
-            t.out = np; t.out_cap = ncap;
+        const size_t hdr = gzip_header_len(d, sh.size, pos);
+        if (hdr == 0) { st = FAILED; break; }
+        if (hdr == kCutOff) { st = TRUNCATED; t.end = sh.size; break; }
+        const size_t member_out = out.n;
+        DecodeResult r;
+        decode_blocks<uint8_t>(d, in_stop, (uint64_t)(pos + hdr) * 8, kNone, true, sh.max_out, out, r);
+        const bool out_of_input = r.failed && r.truncated;
+        size_t trailer = (size_t)((r.end_bit + 7) >> 3);
+        if (out_of_input || (!r.failed && trailer + 8 > in_stop)) {
+            // the member runs beyond the task's allowance, or beyond the end of the file
+            st = in_stop == sh.size ? TRUNCATED : TOO_BIG;
+            if (st == TRUNCATED) t.end = sh.size;
+            break;
         }
-        z.next_in = (Bytef*)(d + in_pos);
-        z.avail_in = (uInt)std::min<size_t>(in_stop - in_pos, 1u << 30);
-        z.next_out = (Bytef*)t.out + t.out_len;
-        z.avail_out = (uInt)std::min<size_t>(t.out_cap - t.out_len, 1u << 30);
-        const uInt out_before = z.avail_out;
-        int rc = inflate(&z, Z_NO_FLUSH);
-        t.out_len += out_before - z.avail_out;
-        in_pos = (size_t)(z.next_in - d);
-        if (rc == Z_STREAM_END) {
-            t.end = in_pos;
-            if (in_pos >= t.limit || in_pos >= sh.size) { st = DONE; break; }
-            if (!looks_like_member(d, sh.size, in_pos)) { st = DONE; break; }   // padding or garbage: the consumer decides
-            inflateReset(&z);
-        } else if (rc == Z_OK || rc == Z_BUF_ERROR) {
-            if (in_pos >= in_stop && z.avail_out != 0) {
-                // input exhausted inside a member: end of file (truncated) or the task's allowance
-                st = in_stop == sh.size ? TRUNCATED : TOO_BIG;
-                if (st == TRUNCATED) t.end = sh.size;
-            }
-        } else {
-            st = FAILED;
-        }
+        if (r.failed) { st = r.too_big ? TOO_BIG : FAILED; break; }
+        const uint32_t crc = d[trailer] | (uint32_t)d[trailer + 1] << 8 | (uint32_t)d[trailer + 2] << 16 | (uint32_t)d[trailer + 3] << 24;
+        const uint32_t isz = d[trailer + 4] | (uint32_t)d[trailer + 5] << 8 | (uint32_t)d[trailer + 6] << 16 | (uint32_t)d[trailer + 7] << 24;
+        const size_t mlen = out.n - member_out;
+        if (isz != (uint32_t)mlen || crc != (uint32_t)crc32_z(0L, (const Bytef*)out.p + member_out, mlen)) { st = FAILED; break; }
+        if (out.n > sh.max_out) { st = TOO_BIG; break; }
+        pos = trailer + 8;
+        t.end = pos;
+        if (pos >= t.limit || pos >= sh.size) { st = DONE; break; }
+        if (!looks_like_member(d, sh.size, pos)) { st = DONE; break; }   // padding or garbage: the consumer decides
     }
-    inflateEnd(&z);
+    t.out = (char*)out.p; t.out_len = st == FAILED || st == TOO_BIG ? 0 : out.n; t.out_cap = out.cap;
+    out.p = nullptr; out.n = out.cap = 0;
     t.status = st;
 }
 

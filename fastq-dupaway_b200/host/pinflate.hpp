@@ -147,6 +147,93 @@ static const uint16_t kDistBase[30] = {1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 
 static const uint8_t kDistExtra[30] = {0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13};
 static const uint8_t kClOrder[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 
+// Pre-decoded table for the hot loop: one lookup gives the literal, or the base value and the number of extra bits
+// of a length / distance symbol.  Entry: bits 0-7 code bits to drop, 8-11 extra bits (or the width of a subtable),
+// 12-13 kind, 16-31 value (byte, base, subtable offset).  Codes longer than PB bits go through a subtable.
+enum : uint32_t { kKindBase = 0u << 12, kKindLiteral = 1u << 12, kKindSub = 2u << 12, kKindOther = 3u << 12, kKindMask = 3u << 12 };
+constexpr uint32_t kEntryEob = kKindOther | (0u << 16), kEntryInvalid = kKindOther | (1u << 16);
+
+template <unsigned PB> struct FastTable {
+    uint32_t t[(1u << PB) + 288 * 16];
+    void build(const Huff& h, bool litlen) {
+        for (uint32_t i = 0; i < (1u << PB); ++i) t[i] = kEntryInvalid;
+        auto entry = [litlen](unsigned sym, unsigned nbits) -> uint32_t {
+            if (litlen) {
+                if (sym < 256) return kKindLiteral | (sym << 16) | nbits;
+                if (sym == 256) return kEntryEob | nbits;
+                if (sym > 285) return kEntryInvalid | nbits;
+                return kKindBase | ((uint32_t)kLenBase[sym - 257] << 16) | ((uint32_t)kLenExtra[sym - 257] << 8) | nbits;
+            }
+            if (sym > 29) return kEntryInvalid | nbits;
+            return kKindBase | ((uint32_t)kDistBase[sym] << 16) | ((uint32_t)kDistExtra[sym] << 8) | nbits;
+        };
+        auto reversed = [](uint32_t code, unsigned l) { uint32_t r = 0; for (unsigned b = 0; b < l; ++b) r |= ((code >> b) & 1u) << (l - 1 - b); return r; };
+        // short codes straight into the primary table; the longest code behind every PB-bit prefix sizes its subtable
+        uint8_t maxlen[1u << PB];
+        bool any_long = false;
+        uint32_t code = 0; int idx = 0;
+        for (unsigned l = 1; l <= 15; ++l) {
+            for (int k = 0; k < h.count[l]; ++k, ++idx, ++code) {
+                const uint32_t r = reversed(code, l);
+                if (l <= PB) {
+                    const uint32_t e = entry(h.symbol[idx], l);
+                    for (uint32_t i = r; i < (1u << PB); i += 1u << l) t[i] = e;
+                } else {
+                    if (!any_long) { std::memset(maxlen, 0, sizeof maxlen); any_long = true; }
+                    uint8_t& m = maxlen[r & ((1u << PB) - 1)];
+                    if (l > m) m = (uint8_t)l;
+                }
+            }
+            code <<= 1;
+        }
+        if (litlen) {
+            // two literals in one entry where both codes fit into the PB index bits (short codes dominate in text):
+            // bit 8 = a second literal follows, value = first | second << 8
+            uint32_t single[1u << PB];
+            std::memcpy(single, t, sizeof single);
+            for (uint32_t i = 0; i < (1u << PB); ++i) {
+                const uint32_t e = single[i];
+                if ((e & kKindMask) != kKindLiteral) continue;
+                const unsigned l1 = e & 0xFFu;
+                if (l1 >= PB) continue;
+                const uint32_t e2 = single[i >> l1];
+                if ((e2 & kKindMask) != kKindLiteral || (e2 & 0xFFu) > PB - l1) continue;
+                t[i] = kKindLiteral | (1u << 8) | ((e >> 16) << 16) | ((e2 >> 16) << 24) | (l1 + (e2 & 0xFFu));
+            }
+        }
+        if (!any_long) return;
+        uint32_t next = 1u << PB;
+        for (uint32_t pfx = 0; pfx < (1u << PB); ++pfx) {
+            if (!maxlen[pfx]) continue;
+            const unsigned sb = maxlen[pfx] - PB;
+            t[pfx] = kKindSub | (next << 16) | (sb << 8) | PB;
+            for (uint32_t i = 0; i < (1u << sb); ++i) t[next + i] = kEntryInvalid;
+            next += 1u << sb;
+        }
+        code = 0; idx = 0;
+        for (unsigned l = 1; l <= 15; ++l) {
+            for (int k = 0; k < h.count[l]; ++k, ++idx, ++code) {
+                if (l <= PB) continue;
+                const uint32_t r = reversed(code, l);
+                const uint32_t sub = t[r & ((1u << PB) - 1)];
+                const uint32_t off = sub >> 16, sb = (sub >> 8) & 15u;
+                const uint32_t e = entry(h.symbol[idx], l - PB);
+                for (uint32_t i = r >> PB; i < (1u << sb); i += 1u << (l - PB)) t[off + i] = e;
+            }
+            code <<= 1;
+        }
+    }
+    inline uint32_t lookup(BitReader& br) const {       // consumes the code's bits
+        uint32_t e = t[br.buf & ((1u << PB) - 1)];
+        if ((e & kKindMask) == kKindSub) {
+            br.drop(PB);
+            e = t[(e >> 16) + (uint32_t)(br.buf & ((1u << ((e >> 8) & 15u)) - 1))];
+        }
+        br.drop(e & 0xFFu);
+        return e;
+    }
+};
+
 // Header of a dynamic block (after the 3 block-type bits).  strict = the search's acceptance test.
 inline bool read_dynamic_header(BitReader& br, Huff& lit, Huff& dist, bool strict) {
     br.refill();
@@ -246,51 +333,108 @@ struct Chunk {
     bool ready = false;
 };
 
-// Decode blocks from c.start_bit; symbols go to c.sym.
-inline void decode_chunk(const uint8_t* data, size_t size, Chunk& c, size_t max_symbols) {
-    if (c.exact) c.start_bit = c.from_bit;
-    else c.start_bit = find_block(data, size, c.from_bit, c.search_end);
-    if (c.start_bit == kNone) { c.failed = true; return; }
+struct DecodeResult {
+    uint64_t end_bit = 0;       // block boundary where decoding stopped
+    bool final_block = false, failed = false, truncated = false;
+    bool too_big = false;       // failed because max_symbols (or memory) was exhausted, not because of the data
+};
+
+// Decode deflate blocks from start_bit up to the first block boundary at or beyond stop_bit (or the final block),
+// APPENDING to out.  T = uint16_t: the window before the start may be unknown (known_window = false) and references
+// into it become markers; T = uint8_t: plain bytes, nothing may reach before out[base] (the start of this stream).
+template <class T>
+inline void decode_blocks(const uint8_t* data, size_t size, uint64_t start_bit, uint64_t stop_bit, bool known_window,
+                          size_t max_symbols, RawBuf<T>& out, DecodeResult& r) {
+    static_assert(sizeof(T) <= 2, "byte or 16-bit symbols");
+    constexpr bool kMarkers = sizeof(T) == 2;
+    constexpr unsigned kStep = 8 / sizeof(T);          // symbols per 8-byte copy step
     auto lit = std::make_unique<Huff>(); auto dist = std::make_unique<Huff>();
-    BitReader br(data, size, c.start_bit);
-    RawBuf<uint16_t>& out = c.sym;
-    if (!out.reserve(std::max<size_t>((size_t)((c.stop_bit > c.start_bit ? c.stop_bit - c.start_bit : 0) / 8) * 5 + (1u << 16), 1u << 16))) {
-        c.failed = true; return;
-    }
-    size_t n = 0;
+    auto flit = std::make_unique<FastTable<11>>(); auto fdist = std::make_unique<FastTable<8>>();
+    BitReader br(data, size, start_bit);
+    const size_t base = out.n;
+    size_t n = out.n;
+    const size_t guess = (size_t)((stop_bit > start_bit && stop_bit != kNone ? stop_bit - start_bit : 0) / 8) * 5 + (1u << 16);
+    if (!out.reserve(n + std::min(guess, std::max<size_t>(max_symbols, 1u << 16)))) { r.failed = true; return; }
     const uint64_t total_bits = (uint64_t)size * 8;
+    r.end_bit = start_bit;
     for (;;) {
         br.refill();
         const unsigned bfinal = br.bits(1), btype = br.bits(2);
-        if (btype == 3) { c.failed = true; break; }
+        if (btype == 3) { r.failed = true; break; }
         if (btype == 0) {
             br.align(); br.refill();
             const uint32_t len = br.bits(16), nlen = br.bits(16);
-            if ((len ^ nlen) != 0xFFFFu) { c.failed = true; break; }
-            if (br.bitpos() + (uint64_t)len * 8 > total_bits) { c.failed = c.truncated = true; }
+            if (br.overrun()) { r.failed = r.truncated = true; break; }
+            if ((len ^ nlen) != 0xFFFFu) { r.failed = true; break; }
+            if (br.bitpos() + (uint64_t)len * 8 > total_bits) { r.failed = r.truncated = true; }
             uint64_t pos = br.bitpos() >> 3;
-            size_t take = c.truncated ? (size_t)(size - std::min<uint64_t>(size, pos)) : len;
-            if (n + take + 258 > out.cap && !out.reserve(std::max(out.cap * 2, n + take + 258))) { c.failed = true; c.truncated = false; break; }
-            for (size_t i = 0; i < take; ++i) out[n++] = data[pos + i];
-            if (c.truncated) break;
+            size_t take = r.truncated ? (size_t)(size - std::min<uint64_t>(size, pos)) : len;
+            if (n + take + 320 > out.cap) {
+                if (n + take - base > max_symbols || !out.reserve(std::max(out.cap * 2, n + take + 320))) { r.failed = r.too_big = true; r.truncated = false; break; }
+            }
+            if (sizeof(T) == 1) std::memcpy(&out[n], data + pos, take);
+            else for (size_t i = 0; i < take; ++i) out[n + i] = (T)data[pos + i];
+            n += take;
+            if (r.truncated) break;
             br = BitReader(data, size, (pos + len) * 8);
         } else {
             if (btype == 1) fixed_tables(*lit, *dist);
-            else if (!read_dynamic_header(br, *lit, *dist, false)) { c.failed = true; c.truncated = br.overrun(); break; }
-            bool bad = false;
-            for (;;) {
-                if (n + 258 > out.cap) {
-                    if (out.cap >= max_symbols || !out.reserve(out.cap * 2)) { bad = true; break; }
+            else if (!read_dynamic_header(br, *lit, *dist, false)) { r.failed = true; r.truncated = br.overrun(); break; }
+            bool bad = false, eob = false;
+            flit->build(*lit, true); fdist->build(*dist, false);
+            // hot loop: at least 16 input bytes ahead, so the refill is one 8-byte load and no bit beyond the end of
+            // the input is ever consumed; one refill (>= 56 bits) covers a whole match (15 + 5 + 15 + 13) or 4 lookups
+            while (br.end - br.p >= 16) {
+                if (n + 320 > out.cap) {
+                    if (n - base >= max_symbols || !out.reserve(out.cap * 2)) { bad = r.too_big = true; break; }
+                }
+                br.refill();
+                uint32_t e = flit->lookup(br);
+                if ((e & kKindMask) == kKindLiteral) {
+                    // an entry holds one or two literals (the second slot is written either way: slack)
+                    out[n] = (T)((e >> 16) & 0xFFu); out[n + 1] = (T)(e >> 24); n += 1 + ((e >> 8) & 1u);
+                    for (int more = 0; more < 3; ++more) {          // 15 + 3 x 11 bits <= one refill
+                        e = flit->t[br.buf & 0x7FFu];
+                        if ((e & kKindMask) != kKindLiteral) break;
+                        br.drop(e & 0xFFu);
+                        out[n] = (T)((e >> 16) & 0xFFu); out[n + 1] = (T)(e >> 24); n += 1 + ((e >> 8) & 1u);
+                    }
+                    continue;
+                }
+                if ((e & kKindMask) != kKindBase) { if ((e & ~0xFFu) == kEntryEob) eob = true; else bad = true; break; }
+                const unsigned len = (e >> 16) + br.bits((e >> 8) & 15u);
+                const uint32_t d = fdist->lookup(br);
+                if ((d & kKindMask) != kKindBase) { bad = true; break; }
+                const size_t dd = (d >> 16) + br.bits((d >> 8) & 15u);
+                if (dd > n - base) {
+                    if (!kMarkers || known_window || dd > kWindow) { bad = true; break; }
+                    // (part of) the source lies in the unknown window before this chunk
+                    for (unsigned i = 0; i < len; ++i, ++n)
+                        out[n] = dd > n - base ? (T)(kMarker | (kWindow - (dd - (n - base)))) : out[n - dd];
+                } else if (dd >= kStep) {
+                    // 8 bytes per step; may write up to kStep - 1 symbols of slack beyond the match
+                    const T* src = &out[n - dd]; T* dst = &out[n];
+                    for (unsigned i = 0; i < len; i += kStep) std::memcpy(dst + i, src + i, 8);
+                    n += len;
+                } else if (dd == 1) {
+                    const T v = out[n - 1];
+                    for (unsigned i = 0; i < len; ++i) out[n + i] = v;
+                    n += len;
+                } else {
+                    for (unsigned i = 0; i < len; ++i, ++n) out[n] = out[n - dd];
+                }
+            }
+            // the last bytes of the input (and nothing else): symbol by symbol, with the end in view
+            for (; !bad && !eob;) {
+                if (n + 320 > out.cap) {
+                    if (n - base >= max_symbols || !out.reserve(out.cap * 2)) { bad = r.too_big = true; break; }
                 }
                 br.refill();
                 int s = lit->decode(br);
-                if (br.past && br.overrun()) { bad = true; break; }      // the symbol needs bits beyond the end of the file
+                if (br.past && br.overrun()) { bad = true; break; }      // the symbol needs bits beyond the end of the input
                 if (s < 256) {
                     if (s < 0) { bad = true; break; }
-                    out[n++] = (uint16_t)s;
-                    // a second literal from the same refill (the common case in text)
-                    const uint16_t e = lit->fast[br.peek(kFastBits)];
-                    if (e && (e >> 4) < 256 && !br.past) { br.drop(e & 15u); out[n++] = (uint16_t)(e >> 4); }
+                    out[n++] = (T)s;
                     continue;
                 }
                 if (s == 256) break;
@@ -301,26 +445,48 @@ inline void decode_chunk(const uint8_t* data, size_t size, Chunk& c, size_t max_
                 br.refill();
                 const size_t dd = kDistBase[d] + br.bits(kDistExtra[d]);
                 if (br.past && br.overrun()) { bad = true; break; }
-                if (dd > n) {
-                    if (c.known_window || dd > kWindow) { bad = true; break; }
-                    // (part of) the source lies in the unknown window before this chunk
+                if (dd > n - base) {
+                    if (!kMarkers || known_window || dd > kWindow) { bad = true; break; }
                     for (unsigned i = 0; i < len; ++i, ++n)
-                        out[n] = dd > n ? (uint16_t)(kMarker | (kWindow - (dd - n))) : out[n - dd];
-                } else if (dd >= len) {
-                    std::memcpy(&out[n], &out[n - dd], len * sizeof(uint16_t));
-                    n += len;
+                        out[n] = dd > n - base ? (T)(kMarker | (kWindow - (dd - (n - base)))) : out[n - dd];
                 } else {
                     for (unsigned i = 0; i < len; ++i, ++n) out[n] = out[n - dd];
                 }
             }
-            if (bad || br.overrun()) { c.failed = true; c.truncated = br.overrun(); break; }
+            if (bad || br.overrun()) { r.failed = true; r.truncated = br.overrun(); break; }
         }
-        c.end_bit = br.bitpos();
-        if (bfinal) { c.final_block = true; break; }
-        if (c.end_bit >= c.stop_bit) break;
+        r.end_bit = br.bitpos();
+        if (bfinal) { r.final_block = true; break; }
+        if (r.end_bit >= stop_bit) break;
     }
-    if (c.failed && !c.truncated) n = 0;
+    if (r.failed && !r.truncated) n = base;
     out.n = n;
+}
+
+// One chunk of a member: find its start (unless exact), decode to 16-bit symbols.
+inline void decode_chunk(const uint8_t* data, size_t size, Chunk& c, size_t max_symbols) {
+    if (c.exact) c.start_bit = c.from_bit;
+    else c.start_bit = find_block(data, size, c.from_bit, c.search_end);
+    if (c.start_bit == kNone) { c.failed = true; return; }
+    DecodeResult r;
+    c.sym.n = 0;
+    decode_blocks<uint16_t>(data, size, c.start_bit, c.stop_bit, c.known_window, max_symbols, c.sym, r);
+    c.end_bit = r.end_bit; c.final_block = r.final_block; c.failed = r.failed; c.truncated = r.truncated;
+}
+
+// Length of the gzip member header at p (RFC 1952); 0 if it is malformed, kCutOff if the file ends inside it.
+constexpr size_t kCutOff = ~(size_t)0;
+inline size_t gzip_header_len(const uint8_t* data, size_t size, size_t p) {
+    const size_t p0 = p;
+    if (p + 4 <= size && (data[p] != 0x1f || data[p + 1] != 0x8b || data[p + 2] != 8 || (data[p + 3] & 0xe0))) return 0;
+    if (p + 10 > size) return kCutOff;
+    const unsigned flg = data[p + 3];
+    p += 10;
+    if (flg & 4) { if (p + 2 > size) return kCutOff; size_t xlen = data[p] | (size_t)data[p + 1] << 8; p += 2 + xlen; if (p > size) return kCutOff; }
+    for (unsigned bit : {8u, 16u})
+        if (flg & bit) { while (p < size && data[p]) ++p; if (p >= size) return kCutOff; ++p; }
+    if (flg & 2) { p += 2; if (p > size) return kCutOff; }
+    return p - p0;
 }
 
 struct Piece {           // an accepted chunk on its way to bytes
@@ -437,17 +603,9 @@ inline ParallelMemberInflater::ParallelMemberInflater(const unsigned char* data,
                                                       size_t chunk_bytes, int window)
     : m_data(data), m_size(size), m_chunk(std::max<size_t>(env_size("FQD_PINFLATE_CHUNK", chunk_bytes), 1u << 12)),
       m_window(window > 0 ? window : 2 * io_threads() + 2), m_sync(std::make_shared<Sync>()) {
-    // gzip header (RFC 1952): magic, CM = 8, FLG, MTIME(4), XFL, OS, then optional FEXTRA / FNAME / FCOMMENT / FHCRC
-    size_t p = member_start;
-    auto need = [&](size_t k) { if (p + k > size) throw std::runtime_error("gzip error"); };
-    need(10);
-    if (data[p] != 0x1f || data[p + 1] != 0x8b || data[p + 2] != 8) throw std::runtime_error("gzip error");
-    const unsigned flg = data[p + 3];
-    p += 10;
-    if (flg & 4) { need(2); size_t xlen = data[p] | (size_t)data[p + 1] << 8; p += 2; need(xlen); p += xlen; }
-    for (unsigned bit : {8u, 16u})
-        if (flg & bit) { while (p < size && data[p]) ++p; need(1); ++p; }
-    if (flg & 2) { need(2); p += 2; }
+    const size_t hdr = pinfl::gzip_header_len(data, size, member_start);
+    if (!hdr || hdr == pinfl::kCutOff) throw std::runtime_error("gzip error");
+    const size_t p = member_start + hdr;
     m_deflate_start = p;
     m_end_bit = (uint64_t)p * 8;
     m_next_boundary = p;
