@@ -43,9 +43,9 @@ static int cmd_stat(const std::string& name) {
     size_t total = 0;
     while (!f.eof()) total += f.read(buf.data(), buf.size());
     const ParallelGzSource* ps = f.parallel_source();
-    std::printf("{\"bytes\": %zu, \"parallel\": %s, \"bgzf\": %s, \"tasks\": %zu, \"serial_members\": %zu, \"dropped\": %zu, \"member_chunks\": %zu}\n",
+    std::printf("{\"bytes\": %zu, \"parallel\": %s, \"bgzf\": %s, \"tasks\": %zu, \"serial_members\": %zu, \"dropped\": %zu, \"member_chunks\": %zu, \"symbol_bytes\": %zu, \"direct_bytes\": %zu}\n",
                 total, ps ? "true" : "false", ps && ps->bgzf() ? "true" : "false", ps ? ps->parallel_tasks() : (size_t)0,
-                ps ? ps->serial_members() : (size_t)0, ps ? ps->dropped_tasks() : (size_t)0, ps ? ps->member_chunks() : (size_t)0);
+                ps ? ps->serial_members() : (size_t)0, ps ? ps->dropped_tasks() : (size_t)0, ps ? ps->member_chunks() : (size_t)0, ps ? ps->symbol_bytes() : (size_t)0, ps ? ps->direct_bytes() : (size_t)0);
     return 0;
 }
 
@@ -148,7 +148,7 @@ static int cmd_rawinflate(const std::string& name) {
         if (c.sym.reserve(isize + (1u << 20))) std::memset(c.sym.data(), 0, c.sym.cap * sizeof(uint16_t));
     }
     auto t0 = std::chrono::steady_clock::now();
-    pinfl::decode_chunk(mf.data(), mf.size(), c, (size_t)1 << 34);
+    { pinfl::DecodeResult r; auto sc = std::make_unique<pinfl::DecodeScratch>(); pinfl::decode_blocks<uint16_t>(*sc, mf.data(), mf.size(), c.from_bit, c.stop_bit, true, (size_t)1 << 34, c.sym, r); c.failed = r.failed; c.final_block = r.final_block; }
     double s = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     std::printf("{\"symbols\": %zu, \"failed\": %d, \"final\": %d, \"decode_GBps\": %.3f", c.sym.size(), (int)c.failed, (int)c.final_block, c.sym.size() / s / 1e9);
     t0 = std::chrono::steady_clock::now();

@@ -134,6 +134,7 @@ inline void inflate_task(Shared& sh, Task& t) {
     size_t pos = t.start;
     t.end = t.start;
     Status st = PENDING;
+    auto sc = std::make_unique<DecodeScratch>();
     if (!out.reserve(std::max<size_t>((t.limit - t.start) * 4 + (64u << 10), 1u << 20))) st = FAILED;
     while (st == PENDING) {
         if (sh.cancel.load(std::memory_order_relaxed)) { st = FAILED; break; }
@@ -142,7 +143,7 @@ inline void inflate_task(Shared& sh, Task& t) {
         if (hdr == kCutOff) { st = TRUNCATED; t.end = sh.size; break; }
         const size_t member_out = out.n;
         DecodeResult r;
-        decode_blocks<uint8_t>(d, in_stop, (uint64_t)(pos + hdr) * 8, kNone, true, sh.max_out, out, r);
+        decode_blocks<uint8_t>(*sc, d, in_stop, (uint64_t)(pos + hdr) * 8, kNone, true, sh.max_out, out, r);
         const bool out_of_input = r.failed && r.truncated;
         size_t trailer = (size_t)((r.end_bit + 7) >> 3);
         if (out_of_input || (!r.failed && trailer + 8 > in_stop)) {
@@ -210,6 +211,7 @@ public:
                 if (m_member->done()) {
                     m_pos = m_member->end_offset();
                     m_member_chunks += m_member->chunks_accepted();
+                    m_symbol_bytes += m_member->symbol_bytes(); m_direct_bytes += m_member->direct_bytes();
                     ++m_serial_members;
                     m_member.reset();
                 }
@@ -270,6 +272,8 @@ public:
     // statistics for tests / the selftest's bench
     size_t parallel_tasks() const { return m_parallel_tasks; }
     size_t serial_members() const { return m_serial_members; }     // members too large for a task (serial or pinflate)
+    size_t symbol_bytes() const { return m_symbol_bytes; }
+    size_t direct_bytes() const { return m_direct_bytes; }
     size_t member_chunks() const { return m_member_chunks; }       // ... and the block-parallel chunks they were cut into
     size_t dropped_tasks() const { return m_dropped; }
     bool bgzf() const { return m_bgzf; }
@@ -403,7 +407,7 @@ private:
     std::vector<std::pair<char*, size_t>> m_spare;
     bool m_eof = false, m_serial = false, m_block_parallel = true;
     std::unique_ptr<ParallelMemberInflater> m_member;
-    size_t m_member_chunks = 0;
+    size_t m_member_chunks = 0, m_symbol_bytes = 0, m_direct_bytes = 0;
     z_stream m_z;
     size_t m_serial_pos = 0;
     size_t m_parallel_tasks = 0, m_serial_members = 0, m_dropped = 0;

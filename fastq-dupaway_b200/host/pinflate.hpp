@@ -329,7 +329,9 @@ struct Chunk {
     uint64_t start_bit = kNone; // where decoding began
     uint64_t end_bit = 0;       // block boundary where it stopped
     bool final_block = false, failed = false, truncated = false;
-    RawBuf<uint16_t> sym;
+    RawBuf<uint16_t> sym;       // symbols from the start of the chunk ...
+    RawBuf<uint8_t> tail;       // ... and, once 32 KiB in a row were free of markers, plain bytes for the rest:
+    size_t tail_skip = 0;       //     tail[0, tail_skip) is a copy of those 32 KiB (the decoder's window), not output
     bool ready = false;
 };
 
@@ -340,18 +342,25 @@ struct DecodeResult {
 };
 
 // Decode deflate blocks from start_bit up to the first block boundary at or beyond stop_bit (or the final block),
-// APPENDING to out.  T = uint16_t: the window before the start may be unknown (known_window = false) and references
+// APPENDING to out (out[base] is where this deflate stream, or chunk, began).  T = uint16_t: the window before the start may be unknown (known_window = false) and references
 // into it become markers; T = uint8_t: plain bytes, nothing may reach before out[base] (the start of this stream).
+struct DecodeScratch {          // the four tables of the block being decoded (~60 KB; one per task, not per call)
+    Huff lit, dist;
+    FastTable<11> flit;
+    FastTable<8> fdist;
+};
+
 template <class T>
-inline void decode_blocks(const uint8_t* data, size_t size, uint64_t start_bit, uint64_t stop_bit, bool known_window,
-                          size_t max_symbols, RawBuf<T>& out, DecodeResult& r) {
+inline void decode_blocks(DecodeScratch& sc, const uint8_t* data, size_t size, uint64_t start_bit, uint64_t stop_bit,
+                          bool known_window, size_t max_symbols, RawBuf<T>& out, DecodeResult& r, size_t base = ~(size_t)0) {
     static_assert(sizeof(T) <= 2, "byte or 16-bit symbols");
     constexpr bool kMarkers = sizeof(T) == 2;
     constexpr unsigned kStep = 8 / sizeof(T);          // symbols per 8-byte copy step
-    auto lit = std::make_unique<Huff>(); auto dist = std::make_unique<Huff>();
-    auto flit = std::make_unique<FastTable<11>>(); auto fdist = std::make_unique<FastTable<8>>();
+    Huff* lit = &sc.lit; Huff* dist = &sc.dist;
+    FastTable<11>* flit = &sc.flit; FastTable<8>* fdist = &sc.fdist;
     BitReader br(data, size, start_bit);
-    const size_t base = out.n;
+    if (base == ~(size_t)0) base = out.n;               // out[base] is the first symbol of this deflate stream / chunk
+    const size_t n0 = out.n;
     size_t n = out.n;
     const size_t guess = (size_t)((stop_bit > start_bit && stop_bit != kNone ? stop_bit - start_bit : 0) / 8) * 5 + (1u << 16);
     if (!out.reserve(n + std::min(guess, std::max<size_t>(max_symbols, 1u << 16)))) { r.failed = true; return; }
@@ -459,19 +468,51 @@ inline void decode_blocks(const uint8_t* data, size_t size, uint64_t start_bit, 
         if (bfinal) { r.final_block = true; break; }
         if (r.end_bit >= stop_bit) break;
     }
-    if (r.failed && !r.truncated) n = base;
+    if (r.failed && !r.truncated) n = n0;
     out.n = n;
 }
 
-// One chunk of a member: find its start (unless exact), decode to 16-bit symbols.
+inline bool marker_free(const uint16_t* s, size_t n) {
+    size_t i = 0;
+#if defined(__SSE2__)
+    __m128i acc = _mm_setzero_si128();
+    for (; i + 8 <= n; i += 8) acc = _mm_or_si128(acc, _mm_loadu_si128((const __m128i*)(s + i)));
+    if (_mm_movemask_epi8(acc) & 0xAAAA) return false;
+#endif
+    for (; i < n; ++i) if (s[i] & kMarker) return false;
+    return true;
+}
+
+// One chunk of a member: find its start (unless exact); 16-bit symbols while references into the unknown window are
+// still alive, block by block, and plain bytes (the faster decoder, no marker pass afterwards) from the first block
+// boundary at which the last 32 KiB hold no marker any more - in text that happens early.
 inline void decode_chunk(const uint8_t* data, size_t size, Chunk& c, size_t max_symbols) {
     if (c.exact) c.start_bit = c.from_bit;
     else c.start_bit = find_block(data, size, c.from_bit, c.search_end);
     if (c.start_bit == kNone) { c.failed = true; return; }
     DecodeResult r;
-    c.sym.n = 0;
-    decode_blocks<uint16_t>(data, size, c.start_bit, c.stop_bit, c.known_window, max_symbols, c.sym, r);
+    auto sc = std::make_unique<DecodeScratch>();
+    c.sym.n = 0; c.tail.n = 0; c.tail_skip = 0;
+    uint64_t pos = c.start_bit;
+    bool bytes_now = c.known_window;                   // nothing precedes the member's first block: bytes at once
+    while (!bytes_now) {
+        r = DecodeResult();
+        decode_blocks<uint16_t>(*sc, data, size, pos, pos + 1, false, max_symbols, c.sym, r, 0);     // one block
+        if (r.failed || r.final_block || r.end_bit >= c.stop_bit) break;
+        pos = r.end_bit;
+        if (c.sym.n >= kWindow && marker_free(c.sym.data() + c.sym.n - kWindow, kWindow)) {
+            if (!c.tail.reserve(kWindow + (size_t)((c.stop_bit > pos ? c.stop_bit - pos : 0) / 8) * 5 + (1u << 16))) break;
+            for (size_t i = 0; i < kWindow; ++i) c.tail[i] = (uint8_t)c.sym[c.sym.n - kWindow + i];
+            c.tail.n = c.tail_skip = kWindow;
+            bytes_now = true;
+        }
+    }
+    if (bytes_now) {
+        r = DecodeResult();
+        decode_blocks<uint8_t>(*sc, data, size, pos, c.stop_bit, true, max_symbols, c.tail, r, 0);
+    }
     c.end_bit = r.end_bit; c.final_block = r.final_block; c.failed = r.failed; c.truncated = r.truncated;
+    if (c.failed && !c.truncated) { c.sym.n = 0; c.tail.n = c.tail_skip = 0; }
 }
 
 // Length of the gzip member header at p (RFC 1952); 0 if it is malformed, kCutOff if the file ends inside it.
@@ -492,7 +533,10 @@ inline size_t gzip_header_len(const uint8_t* data, size_t size, size_t p) {
 struct Piece {           // an accepted chunk on its way to bytes
     RawBuf<uint16_t> sym;
     std::vector<uint8_t> window;     // the 32 KiB before it (shorter at the start of the member)
-    RawBuf<char> bytes;
+    RawBuf<uint8_t> bytes;           // sym with the markers replaced ...
+    RawBuf<uint8_t> tail;            // ... followed by tail[tail_skip, n): the part that was decoded as bytes
+    size_t tail_skip = 0;
+    size_t size() const { return bytes.n + (tail.n - tail_skip); }
     uint32_t crc = 0;
     bool ready = false, bad = false; // bad: a marker points before the start of the member's output
 };
@@ -504,7 +548,7 @@ inline void resolve_piece(Piece& pc) {
     const uint8_t* w = pc.window.data();
     const size_t missing = kWindow - pc.window.size();   // markers index a full window; its first `missing` bytes do not exist
     const uint16_t* s = pc.sym.data();
-    char* o = pc.bytes.data();
+    uint8_t* o = pc.bytes.data();
     size_t i = 0;
     while (i < n) {
         // stretches without markers (everything, some 100 KB into a chunk of text) are narrowed 16 symbols at a time
@@ -520,19 +564,21 @@ inline void resolve_piece(Piece& pc) {
             uint16_t any = 0;
             for (int k = 0; k < 16; ++k) any |= s[i + k];
             if (any & kMarker) break;
-            for (int k = 0; k < 16; ++k) o[i + k] = (char)s[i + k];
+            for (int k = 0; k < 16; ++k) o[i + k] = (uint8_t)s[i + k];
             i += 16;
         }
 #endif
         const size_t stop = std::min(n, i + 16);
         for (; i < stop; ++i) {
             const uint16_t v = s[i];
-            if (v < kMarker) { o[i] = (char)v; continue; }
+            if (v < kMarker) { o[i] = (uint8_t)v; continue; }
             const size_t j = v & 0x7FFFu;
-            if (j < missing) { pc.bad = true; o[i] = 0; } else o[i] = (char)w[j - missing];
+            if (j < missing) { pc.bad = true; o[i] = 0; } else o[i] = w[j - missing];
         }
     }
     pc.crc = (uint32_t)crc32_z(0L, (const Bytef*)o, n);
+    if (pc.tail.n > pc.tail_skip)        // (crc32_z with a null buffer would RESET the value)
+        pc.crc = (uint32_t)crc32_z(pc.crc, (const Bytef*)pc.tail.data() + pc.tail_skip, pc.tail.n - pc.tail_skip);
 }
 
 }  // namespace pinfl
@@ -559,13 +605,15 @@ public:
     size_t chunks_accepted() const { return m_accepted; }
     size_t chunks_dropped() const { return m_dropped; }
     size_t fillers() const { return m_fillers; }
+    size_t symbol_bytes() const { return m_sym_bytes; }      // decoded as 16-bit symbols (markers alive)
+    size_t direct_bytes() const { return m_direct_bytes; }   // decoded as bytes
 
 private:
     struct Sync {
         std::mutex mu; std::condition_variable cv; int inflight = 0;
         // symbol / byte arrays go round (a fresh multi-megabyte malloc is an mmap + a page fault per 4 KiB)
         std::vector<std::unique_ptr<pinfl::RawBuf<uint16_t>>> spare_sym;
-        std::vector<std::unique_ptr<pinfl::RawBuf<char>>> spare_bytes;
+        std::vector<std::unique_ptr<pinfl::RawBuf<uint8_t>>> spare_bytes;
         template <class T> static void take(std::vector<std::unique_ptr<pinfl::RawBuf<T>>>& from, pinfl::RawBuf<T>& into) {
             if (!from.empty()) { into.swap(*from.back()); into.n = 0; from.pop_back(); }
         }
@@ -595,7 +643,7 @@ private:
     uint32_t m_crc = 0; uint64_t m_len = 0;
     bool m_chain_done = false, m_done = false, m_truncated = false, m_first = true;
     size_t m_end_offset = 0;
-    size_t m_accepted = 0, m_dropped = 0, m_fillers = 0;
+    size_t m_accepted = 0, m_dropped = 0, m_fillers = 0, m_sym_bytes = 0, m_direct_bytes = 0;
 };
 
 // ---- implementation -------------------------------------------------------------------------------------------
@@ -623,9 +671,14 @@ inline void ParallelMemberInflater::launch(ChunkPtr c, bool express) {
     { std::lock_guard<std::mutex> g(sy->mu); ++sy->inflight; }
     const size_t keep = (size_t)m_window;
     WorkerPool::shared().submit([sy, c, data, size, max_symbols, keep] {
-        { std::lock_guard<std::mutex> g(sy->mu); Sync::take(sy->spare_sym, c->sym); }
+        { std::lock_guard<std::mutex> g(sy->mu); Sync::take(sy->spare_sym, c->sym); Sync::take(sy->spare_bytes, c->tail); }
         pinfl::decode_chunk(data, size, *c, max_symbols);
-        { std::lock_guard<std::mutex> g(sy->mu); if (c->sym.n == 0) Sync::give(sy->spare_sym, c->sym, keep); c->ready = true; --sy->inflight; }
+        {
+            std::lock_guard<std::mutex> g(sy->mu);
+            if (c->sym.n == 0) Sync::give(sy->spare_sym, c->sym, keep);
+            if (c->tail.n == 0) Sync::give(sy->spare_bytes, c->tail, 2 * keep);
+            c->ready = true; --sy->inflight;
+        }
         sy->cv.notify_all();
     }, express);
 }
@@ -649,21 +702,29 @@ inline void ParallelMemberInflater::accept(ChunkPtr c) {
     auto pc = std::make_shared<Piece>();
     pc->window = m_win;
     pc->sym.swap(c->sym);
-    // the window the next chunk will need: the last 32 KiB of (window + this chunk), markers replaced
-    const size_t n = pc->sym.size();
-    const size_t keep_old = n >= kWindow ? 0 : std::min(m_win.size(), kWindow - n);
+    pc->tail.swap(c->tail); pc->tail_skip = c->tail_skip;
+    // the window the next chunk will need: the last 32 KiB of (window + symbols, markers replaced + byte part)
+    const size_t n = pc->sym.size(), nt = pc->tail.n - pc->tail_skip;
+    m_sym_bytes += n; m_direct_bytes += nt;
     std::vector<uint8_t> nw;
     nw.reserve(kWindow);
-    nw.insert(nw.end(), m_win.end() - (ptrdiff_t)keep_old, m_win.end());
-    const size_t missing = kWindow - m_win.size();
-    for (size_t i = n - std::min(n, kWindow); i < n; ++i) {
-        const uint16_t v = pc->sym[i];
-        if (v < kMarker) nw.push_back((uint8_t)v);
-        else {
-            const size_t j = v & 0x7FFFu;
-            if (j < missing) throw std::runtime_error("gzip error");       // distance too far back
-            nw.push_back(m_win[j - missing]);
+    if (nt >= kWindow) {
+        nw.assign(pc->tail.data() + pc->tail.n - kWindow, pc->tail.data() + pc->tail.n);
+    } else {
+        const size_t from_sym = std::min(n, kWindow - nt);
+        const size_t keep_old = std::min(m_win.size(), kWindow - nt - from_sym);
+        nw.insert(nw.end(), m_win.end() - (ptrdiff_t)keep_old, m_win.end());
+        const size_t missing = kWindow - m_win.size();
+        for (size_t i = n - from_sym; i < n; ++i) {
+            const uint16_t v = pc->sym[i];
+            if (v < kMarker) nw.push_back((uint8_t)v);
+            else {
+                const size_t j = v & 0x7FFFu;
+                if (j < missing) throw std::runtime_error("gzip error");       // distance too far back
+                nw.push_back(m_win[j - missing]);
+            }
         }
+        nw.insert(nw.end(), pc->tail.data() + pc->tail_skip, pc->tail.data() + pc->tail.n);
     }
     m_win.swap(nw);
     m_end_bit = c->end_bit;
@@ -744,15 +805,26 @@ inline size_t ParallelMemberInflater::read(char* dst, size_t n) {
                 }
             }
             if (pc->bad) throw std::runtime_error("gzip error");
+            const size_t total = pc->size();
             if (m_piece_off == 0) {
-                m_crc = (uint32_t)crc32_combine(m_crc, pc->crc, (z_off_t)pc->bytes.size());
-                m_len += pc->bytes.size();
+                m_crc = (uint32_t)crc32_combine(m_crc, pc->crc, (z_off_t)total);
+                m_len += total;
             }
-            const size_t k = std::min(n - got, pc->bytes.size() - m_piece_off);
-            std::memcpy(dst + got, pc->bytes.data() + m_piece_off, k);
-            got += k; m_piece_off += k;
-            if (m_piece_off == pc->bytes.size()) {
-                { std::lock_guard<std::mutex> g(m_sync->mu); Sync::give(m_sync->spare_bytes, pc->bytes, (size_t)m_window); }
+            while (got < n && m_piece_off < total) {
+                // first the resolved symbols, then the part that was decoded as bytes
+                const bool in_tail = m_piece_off >= pc->bytes.n;
+                const uint8_t* src = in_tail ? pc->tail.data() + pc->tail_skip + (m_piece_off - pc->bytes.n) : pc->bytes.data() + m_piece_off;
+                const size_t avail = in_tail ? total - m_piece_off : pc->bytes.n - m_piece_off;
+                const size_t k = std::min(n - got, avail);
+                std::memcpy(dst + got, src, k);
+                got += k; m_piece_off += k;
+            }
+            if (m_piece_off == total) {
+                {
+                    std::lock_guard<std::mutex> g(m_sync->mu);
+                    Sync::give(m_sync->spare_bytes, pc->bytes, 2 * (size_t)m_window);
+                    Sync::give(m_sync->spare_bytes, pc->tail, 2 * (size_t)m_window);
+                }
                 m_pieces.pop_front(); m_piece_off = 0;
             }
             continue;

@@ -262,11 +262,15 @@ def payloads():
     noise = bytes(rng.getrandbits(8) for _ in range(1 << 20))            # incompressible: stored blocks
     runs = b"".join(bytes([rng.randrange(4)]) * rng.randrange(1, 70000) for _ in range(200))   # long matches, distance 1
     far = (noise[:30000] + b"x" * 2000) * 60                             # matches at distances close to 32 KiB
-    return {"text": text, "noise": noise, "runs": runs, "far": far, "mixed": text[:2_000_000] + noise + runs + far + text[2_000_000:]}
+    # lines of unique bytes + a constant: no long-lived references into the unknown window, so a chunk switches from
+    # 16-bit symbols to plain bytes early
+    unique = b"".join(bytes(rng.getrandbits(8) | 0x80 for _ in range(40)) + b"A" * 64 + b"\n" for _ in range(30000))
+    return {"text": text, "noise": noise, "runs": runs, "far": far, "unique": unique,
+            "mixed": text[:2_000_000] + noise + runs + far + text[2_000_000:]}
 
 
 @pytest.mark.parametrize("threads", [2, 8])
-@pytest.mark.parametrize("name", ["text", "noise", "runs", "far", "mixed"])
+@pytest.mark.parametrize("name", ["text", "noise", "runs", "far", "unique", "mixed"])
 def test_single_member_block_parallel(tmp_path, threads, name):
     data = payloads()[name]
     f = tmp_path / "one.gz"
@@ -280,6 +284,10 @@ def test_single_member_block_parallel(tmp_path, threads, name):
     f.write_bytes(deflate_gz(data, 6, mem=1))
     st = check_file(f, data, threads, env=SMALL)
     assert st["member_chunks"] > 4 or name in ("runs", "noise", "far")
+    if name == "unique":
+        f.write_bytes(deflate_gz(data, 6))
+        st = check_file(f, data, threads, env=dict(SMALL, FQD_PINFLATE_CHUNK=str(256 << 10)))
+        assert st["direct_bytes"] > 500_000                     # chunks went on in plain bytes after their first blocks
 
 
 def test_single_member_block_parallel_default_sizes(tmp_path):
