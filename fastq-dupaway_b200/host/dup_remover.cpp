@@ -104,6 +104,15 @@ size_t file_size_or_zero(const std::string& name) {
     return stat(name.c_str(), &sb) == 0 ? (size_t)sb.st_size : 0;
 }
 
+// How much larger than the file is its content?  Plain: 1.  ".gz": the ratio measured on what the reader has
+// inflated by now (the first block is there, i.e. tens of megabytes) plus 10 %, else a generous 8 (a wrong guess
+// costs device memory or a restart with doubled tables, never the result).
+double gz_expansion(const std::string& name, const BlockReader& reader) {
+    if (!has_gz_ext(name)) return 1.0;
+    const double h = reader.expansion_hint();
+    return h > 0 ? std::max(1.0, h * 1.1) : 8.0;
+}
+
 // Longest sequence line and mean record size of a sample (first bytes of the first block).
 void sample_geometry(const char* p, size_t n, int lpr, size_t& max_seq, double& avg_rec) {
     max_seq = 0; avg_rec = 0;
@@ -179,7 +188,7 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
             sample_geometry(ms[m].ptr, std::min<size_t>(ms[m].len, 8u << 20), lpr, ms_, ar);
             max_seq = std::max(max_seq, ms_);
             size_t fsz = file_size_or_zero(in[m]);
-            double expand = has_gz_ext(in[m]) ? 8.0 : 1.0;
+            double expand = gz_expansion(in[m], *ms[m].reader);
             uint64_t est = (uint64_t)((double)fsz * expand / std::max(ar, 8.0) * 1.02) + (1u << 16);
             est_records = m == 0 ? est : std::min(est_records, est);
             avg_rec = std::max(avg_rec, ar);
@@ -320,7 +329,7 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
             size_t ms_ = 0; double ar = 0;
             sample_geometry(first[m]->data(), std::min<size_t>(first[m]->len, 8u << 20), lpr, ms_, ar);
             max_seq = std::max(max_seq, ms_);
-            double expand = has_gz_ext(in[m]) ? 8.0 : 1.0;
+            double expand = gz_expansion(in[m], *readers[m]);
             uint64_t est = (uint64_t)((double)file_size_or_zero(in[m]) * expand / std::max(ar, 8.0) * 1.02) + (1u << 16);
             est_records = std::max(est_records, est);
         }

@@ -112,6 +112,7 @@ public:
     }
     bool eof() const { return m_eof; }
     const ParallelGzSource* parallel_source() const { return m_par.get(); }
+    double expansion_hint() const { return m_par ? m_par->expansion_hint() : 0.0; }
 private:
     std::string m_name;
     bool m_gz, m_eof = false, m_regular = false, m_zinit = false;
@@ -167,6 +168,8 @@ public:
         m_cv.notify_all();
     }
     size_t block_bytes() const { return m_block; }
+    // .gz input: measured uncompressed / compressed ratio of what has been inflated so far, 0 if unknown
+    double expansion_hint() const { return m_file.expansion_hint(); }
 private:
     void run() {
         try {

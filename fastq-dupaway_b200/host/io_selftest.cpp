@@ -43,9 +43,9 @@ static int cmd_stat(const std::string& name) {
     size_t total = 0;
     while (!f.eof()) total += f.read(buf.data(), buf.size());
     const ParallelGzSource* ps = f.parallel_source();
-    std::printf("{\"bytes\": %zu, \"parallel\": %s, \"bgzf\": %s, \"tasks\": %zu, \"serial_members\": %zu, \"dropped\": %zu, \"member_chunks\": %zu, \"symbol_bytes\": %zu, \"direct_bytes\": %zu}\n",
+    std::printf("{\"bytes\": %zu, \"parallel\": %s, \"bgzf\": %s, \"tasks\": %zu, \"serial_members\": %zu, \"dropped\": %zu, \"member_chunks\": %zu, \"symbol_bytes\": %zu, \"direct_bytes\": %zu, \"expansion\": %.4f}\n",
                 total, ps ? "true" : "false", ps && ps->bgzf() ? "true" : "false", ps ? ps->parallel_tasks() : (size_t)0,
-                ps ? ps->serial_members() : (size_t)0, ps ? ps->dropped_tasks() : (size_t)0, ps ? ps->member_chunks() : (size_t)0, ps ? ps->symbol_bytes() : (size_t)0, ps ? ps->direct_bytes() : (size_t)0);
+                ps ? ps->serial_members() : (size_t)0, ps ? ps->dropped_tasks() : (size_t)0, ps ? ps->member_chunks() : (size_t)0, ps ? ps->symbol_bytes() : (size_t)0, ps ? ps->direct_bytes() : (size_t)0, f.expansion_hint());
     return 0;
 }
 

@@ -208,11 +208,14 @@ public:
             if (m_serial) { got += serial_read(dst + got, n - got); continue; }
             if (m_member) {
                 got += m_member->read(dst + got, n - got);
+                m_hint_in.store(m_hint_in_base + m_member->accepted_compressed(), std::memory_order_relaxed);
+                m_hint_out.store(m_hint_out_base + m_member->accepted_output(), std::memory_order_relaxed);
                 if (m_member->done()) {
                     m_pos = m_member->end_offset();
                     m_member_chunks += m_member->chunks_accepted();
                     m_symbol_bytes += m_member->symbol_bytes(); m_direct_bytes += m_member->direct_bytes();
                     ++m_serial_members;
+                    m_hint_in_base = m_hint_in.load(std::memory_order_relaxed); m_hint_out_base = m_hint_out.load(std::memory_order_relaxed);
                     m_member.reset();
                 }
                 continue;
@@ -253,6 +256,8 @@ public:
             switch (t->status) {
             case DONE: case TRUNCATED:
                 ++m_parallel_tasks;
+                m_hint_in_base += t->end - t->start; m_hint_out_base += t->out_len;
+                m_hint_in.store(m_hint_in_base, std::memory_order_relaxed); m_hint_out.store(m_hint_out_base, std::memory_order_relaxed);
                 m_cur = t; m_cur_off = 0;
                 if (t->out_len == 0) { m_pos = t->end; recycle(*t); m_cur.reset(); }
                 break;
@@ -269,6 +274,12 @@ public:
         return got;
     }
     bool eof() const { return m_eof; }
+    // uncompressed / compressed bytes of what has been inflated so far (0 until 1 MiB of input is accounted for);
+    // may be read from another thread - the drivers size the device tables from it
+    double expansion_hint() const {
+        const size_t in = m_hint_in.load(std::memory_order_relaxed), out = m_hint_out.load(std::memory_order_relaxed);
+        return in >= (1u << 20) ? (double)out / (double)in : 0.0;
+    }
     // statistics for tests / the selftest's bench
     size_t parallel_tasks() const { return m_parallel_tasks; }
     size_t serial_members() const { return m_serial_members; }     // members too large for a task (serial or pinflate)
@@ -408,6 +419,8 @@ private:
     bool m_eof = false, m_serial = false, m_block_parallel = true;
     std::unique_ptr<ParallelMemberInflater> m_member;
     size_t m_member_chunks = 0, m_symbol_bytes = 0, m_direct_bytes = 0;
+    std::atomic<size_t> m_hint_in{0}, m_hint_out{0};
+    size_t m_hint_in_base = 0, m_hint_out_base = 0;
     z_stream m_z;
     size_t m_serial_pos = 0;
     size_t m_parallel_tasks = 0, m_serial_members = 0, m_dropped = 0;

@@ -605,6 +605,8 @@ public:
     size_t chunks_accepted() const { return m_accepted; }
     size_t chunks_dropped() const { return m_dropped; }
     size_t fillers() const { return m_fillers; }
+    size_t accepted_compressed() const { return (size_t)(m_end_bit >> 3) - m_deflate_start; }   // ... and what it inflated to:
+    size_t accepted_output() const { return m_sym_bytes + m_direct_bytes; }
     size_t symbol_bytes() const { return m_sym_bytes; }      // decoded as 16-bit symbols (markers alive)
     size_t direct_bytes() const { return m_direct_bytes; }   // decoded as bytes
 
