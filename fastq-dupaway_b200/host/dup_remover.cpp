@@ -376,7 +376,7 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
         const size_t cap = 64u << 20;
         void* stage_buf[2] = {nullptr, nullptr};
         for (auto& p : stage_buf)
-            if (fqd_host_alloc(&p, cap) != FQD_OK) throw std::runtime_error("pinned host allocation failed");
+            if (fqd_host_alloc(&p, cap) != FQD_OK) throw std::runtime_error("pinned host allocation failed (no usable CUDA device? this build has no CPU path)");
         struct Free { void** p; ~Free() { fqd_host_free(p[0]); fqd_host_free(p[1]); } } guard{stage_buf};
         void* stage = stage_buf[0];
         for (int m = 0; m < mates; ++m) {

@@ -141,7 +141,7 @@ public:
             Block* b = new Block();
             b->head = block_bytes; b->cap = block_bytes;
             void* p = nullptr;
-            if (fqd_host_alloc(&p, b->head + b->cap + 64) != FQD_OK) throw std::runtime_error("pinned host allocation failed");
+            if (fqd_host_alloc(&p, b->head + b->cap + 64) != FQD_OK) throw std::runtime_error("pinned host allocation failed (no usable CUDA device? this build has no CPU path)");
             b->base = (char*)p;
             m_all.push_back(b);
             m_free.push_back(b);
@@ -250,6 +250,16 @@ struct MateStream {
     }
 };
 
+// FQD_GZ_LEVEL = 1..9: deflate level of ".gz" outputs (default: zlib's default, as the reference's gzip filter)
+inline int gz_level() {
+    static const int level = [] {
+        const char* e = std::getenv("FQD_GZ_LEVEL");
+        const int v = e ? std::atoi(e) : 0;
+        return v >= 1 && v <= 9 ? v : Z_DEFAULT_COMPRESSION;
+    }();
+    return level;
+}
+
 // A stretch of bytes to write: `len` bytes at base + off, landing `out_off` bytes after the start of the job.
 struct Run { size_t off, len, out_off; };
 
@@ -261,12 +271,13 @@ class OutputFile {
 public:
     explicit OutputFile(const std::string& name) : m_gz(has_gz_ext(name)) {
         if (m_gz && io_threads() <= 1) {
-            m_g = gzopen(name.c_str(), "wb");
+            const std::string mode = gz_level() == Z_DEFAULT_COMPRESSION ? "wb" : "wb" + std::to_string(gz_level());
+            m_g = gzopen(name.c_str(), mode.c_str());
             if (m_g) gzbuffer(m_g, 1 << 20);
         } else if (m_gz) {
             m_f = std::fopen(name.c_str(), "wb");
             if (m_f) std::setvbuf(m_f, nullptr, _IOFBF, 4 << 20);
-            if (m_f) m_sink.reset(new ParallelGzSink(m_f));
+            if (m_f) m_sink.reset(new ParallelGzSink(m_f, 1u << 20, gz_level()));
         } else {
             m_fd = ::open(name.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
             m_wbuf.reserve(kBuf);

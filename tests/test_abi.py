@@ -33,3 +33,25 @@ def test_create_fails_loudly_without_gpu(fqd):
         assert e.code == 2      # FQD_ERR_CUDA - never a CPU fallback
     else:
         raise AssertionError("fqd_create succeeded without a CUDA device")
+
+
+def test_binary_fails_loudly_without_a_gpu(tmp_path):
+    """The drop-in binary has no CPU path either: without a CUDA device it stops with the reference's error banner
+    and exit status 1 instead of producing output some other way."""
+    import subprocess
+    from pathlib import Path
+    import pytest
+    import torch
+    ROOT = Path(__file__).resolve().parent.parent
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    exe = ROOT / "fastq-dupaway_b200" / "host" / "fastq-dupaway"
+    if not exe.exists():
+        pytest.skip("host binary not built")
+    inp = tmp_path / "in.fq"
+    inp.write_bytes(b"@r1\nACGT\n+\nIIII\n")
+    for extra in (["--fast"], []):
+        res = subprocess.run([str(exe), "-i", str(inp), "-o", str(tmp_path / "out.fq"), *extra], capture_output=True, text=True)
+        assert res.returncode == 1
+        assert res.stderr.startswith("An error occured during fastq-dupaway execution:")
+        assert "CUDA" in res.stderr

@@ -211,6 +211,10 @@ def test_gz_output(tmp_path, threads):
     assert subprocess.run(["gzip", "-t", str(out)]).returncode == 0
     # and back in through the parallel reader
     check_file(out, data, threads)
+    # FQD_GZ_LEVEL: faster, larger
+    size6 = out.stat().st_size
+    run(["put", out], threads=threads, stdin=data, env={"FQD_GZ_LEVEL": "1"})
+    assert gzip.decompress(out.read_bytes()) == data and out.stat().st_size > size6
     # empty output is still a valid archive
     run(["put", out], threads=threads, stdin=b"")
     assert gzip.decompress(out.read_bytes()) == b""
