@@ -175,7 +175,7 @@ public:
     // `span`: compressed bytes per task; `window`: tasks planned ahead of the consumer (0 = 2 x threads)
     ParallelGzSource(const unsigned char* data, size_t size, size_t span = 2u << 20, int window = 0)
         : m_sh(std::make_shared<gzdetail::Shared>()), m_span(std::max<size_t>(env_size("FQD_GZ_SPAN", span), 64)),
-          m_window(window > 0 ? window : 2 * io_threads()) {
+          m_window(window > 0 ? window : 2 * io_threads()), m_ahead(m_window) {
         m_sh->data = data; m_sh->size = size;
         m_sh->max_overrun = std::max<size_t>(16u << 20, 4 * m_span);
         m_sh->max_out = 512u << 20;
@@ -256,6 +256,7 @@ public:
             switch (t->status) {
             case DONE: case TRUNCATED:
                 ++m_parallel_tasks;
+                m_ahead.observed(t->out_cap);
                 m_hint_in_base += t->end - t->start; m_hint_out_base += t->out_len;
                 m_hint_in.store(m_hint_in_base, std::memory_order_relaxed); m_hint_out.store(m_hint_out_base, std::memory_order_relaxed);
                 m_cur = t; m_cur_off = 0;
@@ -337,7 +338,7 @@ private:
         }, express);
     }
     void top_up() {
-        while ((int)m_tasks.size() < m_window && m_plan_pos < m_sh->size) {
+        while ((int)m_tasks.size() < m_ahead.units() && m_plan_pos < m_sh->size) {
             size_t limit = plan_limit(m_plan_pos);
             launch(m_plan_pos, limit, false);
             m_plan_pos = limit;
@@ -407,6 +408,7 @@ private:
     std::shared_ptr<gzdetail::Shared> m_sh;
     size_t m_span, m_max_task = 0;
     int m_window;
+    RunAhead m_ahead;
     bool m_bgzf = false;
     size_t m_hop = 0;                 // BGZF: a true member start, advanced by header hops
     size_t m_pos = 0;                 // compressed offset up to which the output has been accepted

@@ -634,6 +634,7 @@ private:
 
     const unsigned char* m_data; size_t m_size;
     size_t m_chunk; int m_window;
+    RunAhead m_ahead;
     std::shared_ptr<Sync> m_sync;
     size_t m_deflate_start = 0;
     size_t m_next_boundary = 0;          // nominal byte boundary of the next chunk to plan
@@ -652,7 +653,7 @@ private:
 inline ParallelMemberInflater::ParallelMemberInflater(const unsigned char* data, size_t size, size_t member_start,
                                                       size_t chunk_bytes, int window)
     : m_data(data), m_size(size), m_chunk(std::max<size_t>(env_size("FQD_PINFLATE_CHUNK", chunk_bytes), 1u << 12)),
-      m_window(window > 0 ? window : 2 * io_threads() + 2), m_sync(std::make_shared<Sync>()) {
+      m_window(window > 0 ? window : 2 * io_threads() + 2), m_ahead(m_window), m_sync(std::make_shared<Sync>()) {
     const size_t hdr = pinfl::gzip_header_len(data, size, member_start);
     if (!hdr || hdr == pinfl::kCutOff) throw std::runtime_error("gzip error");
     const size_t p = member_start + hdr;
@@ -686,7 +687,7 @@ inline void ParallelMemberInflater::launch(ChunkPtr c, bool express) {
 }
 
 inline void ParallelMemberInflater::top_up() {
-    while ((int)(m_chunks.size() + m_pieces.size()) < m_window && m_next_boundary < m_size) {
+    while ((int)(m_chunks.size() + m_pieces.size()) < m_ahead.units() && m_next_boundary < m_size) {
         auto c = std::make_shared<pinfl::Chunk>();
         const size_t next = std::min(m_size, m_next_boundary + m_chunk);
         c->from_bit = (uint64_t)m_next_boundary * 8;
@@ -708,6 +709,7 @@ inline void ParallelMemberInflater::accept(ChunkPtr c) {
     // the window the next chunk will need: the last 32 KiB of (window + symbols, markers replaced + byte part)
     const size_t n = pc->sym.size(), nt = pc->tail.n - pc->tail_skip;
     m_sym_bytes += n; m_direct_bytes += nt;
+    m_ahead.observed(pc->sym.cap * sizeof(uint16_t) + pc->tail.cap + n);      // symbols + byte part + the resolved copy
     std::vector<uint8_t> nw;
     nw.reserve(kWindow);
     if (nt >= kWindow) {

@@ -25,6 +25,28 @@ inline int io_threads() {
     return n;
 }
 
+// How far a reader may run ahead of its consumer: `full` units (tasks, chunks) as long as their decoded size is
+// ordinary, fewer when the input expands enormously (a gigabyte of zeros is a megabyte of deflate), so that what is
+// in flight stays within FQD_IO_AHEAD_MB (default 2048) of memory.  Starts small until the first sizes are known.
+class RunAhead {
+public:
+    explicit RunAhead(int full) : m_full(std::max(full, 2)), m_now(std::min(m_full, 4)) {
+        const char* e = std::getenv("FQD_IO_AHEAD_MB");
+        const long long mb = e ? std::atoll(e) : 0;
+        m_budget = (size_t)(mb > 0 ? mb : 2048) << 20;
+    }
+    int units() const { return m_now; }
+    void observed(size_t bytes_in_memory) {           // one unit finished and occupied this much
+        m_avg = m_seen ? (m_avg * 7 + bytes_in_memory) / 8 : bytes_in_memory;
+        ++m_seen;
+        const size_t fit = m_budget / std::max<size_t>(m_avg, 1);
+        m_now = (int)std::min<size_t>((size_t)m_full, std::max<size_t>(fit, 2));
+    }
+private:
+    int m_full, m_now;
+    size_t m_budget = 0, m_avg = 0, m_seen = 0;
+};
+
 // Fixed pool, FIFO with an express lane.  Tasks never wait for other tasks, so sharing one pool between all
 // readers and writers cannot deadlock.
 class WorkerPool {

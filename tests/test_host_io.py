@@ -379,3 +379,23 @@ def test_damaged_archives_never_crash_and_agree_with_the_serial_path(tmp_path):
             assert serial.returncode == 0 and serial.stdout == p.stdout, it
             outcomes["ok"] += 1
     assert outcomes["error"] > 10
+
+
+def test_enormous_expansion_stays_within_the_run_ahead_budget(tmp_path):
+    """512 MiB of zeros are 0.5 MB of deflate: every 64 KiB chunk inflates to 64 MiB.  The reader must not keep
+    2 x threads of those in flight; FQD_IO_AHEAD_MB bounds it (peak RSS checked), and the bytes are still right."""
+    import resource
+    c = zlib.compressobj(6, zlib.DEFLATED, 31)
+    z = bytes(1 << 24)
+    blob = b"".join(c.compress(z) for _ in range(32)) + c.flush()
+    f = tmp_path / "zeros.gz"
+    f.write_bytes(blob)
+    env = {"FQD_PINFLATE_CHUNK": str(64 << 10), "FQD_GZ_MAX_TASK": str(64 << 10), "FQD_IO_AHEAD_MB": "64"}
+    before = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss
+    st = json.loads(run(["stat", f], threads=8, env=env).stdout)
+    peak_mb = resource.getrusage(resource.RUSAGE_CHILDREN).ru_maxrss // 1024
+    assert st["bytes"] == 32 << 24 and st["member_chunks"] >= 4
+    if peak_mb * 1024 > before:          # ru_maxrss is the maximum over all children so far
+        assert peak_mb < 1200, peak_mb   # 8 chunks in flight would hold more than 2 GB of symbols
+    p = run(["cat", f, 1 << 20], threads=8, env=env)
+    assert len(p.stdout) == 32 << 24 and p.stdout.count(0) == len(p.stdout)
