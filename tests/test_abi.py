@@ -55,3 +55,11 @@ def test_binary_fails_loudly_without_a_gpu(tmp_path):
         assert res.returncode == 1
         assert res.stderr.startswith("An error occured during fastq-dupaway execution:")
         assert "CUDA" in res.stderr
+
+
+def test_binding_loads_the_product_library_only(fqd):
+    """The ctypes binding opens fastq-dupaway_b200/csrc/libfqd_cuda.so by path - never the test double of
+    tests/fake_engine, whatever LD_LIBRARY_PATH says."""
+    from pathlib import Path
+    lib = fqd.load_library()
+    assert Path(lib._name).resolve() == (Path(fqd.__file__).resolve().parent / "csrc" / "libfqd_cuda.so")

@@ -1,0 +1,136 @@
+"""The drop-in binary's HOST logic on the CPU: the real `fastq-dupaway` executable, with a test double of the C ABI
+(tests/fake_engine/fake_fqd.cpp: newline counting + a std::unordered_set) preloaded in place of libfqd_cuda.so.
+
+What runs here is everything AROUND the engine - options, plain / gzip readers, rings of pinned blocks, tail carry,
+paired lock-step, restarts after wrong capacity / row-width estimates, asynchronous writers, gzip outputs, -v lines -
+checked byte for byte against the oracle.  The engine itself (and the error-order rules it implements) is tested on the
+GPU (tests/test_cli_gpu.py); the product has no CPU path: tests/test_abi.py checks that the binary fails without a GPU.
+"""
+import gzip
+import os
+import subprocess
+from pathlib import Path
+
+import pytest
+
+import synth
+from test_host_io import SMALL, bgzf, deflate_gz, members
+
+ROOT = Path(__file__).resolve().parent.parent
+EXE = ROOT / "fastq-dupaway_b200" / "host" / "fastq-dupaway"
+FAKE_SRC = ROOT / "tests" / "fake_engine" / "fake_fqd.cpp"
+FAKE_DIR = ROOT / "tests" / "fake_engine" / "_build"
+
+
+@pytest.fixture(scope="module", autouse=True)
+def fake_engine():
+    FAKE_DIR.mkdir(exist_ok=True)
+    subprocess.run(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-o", str(FAKE_DIR / "libfqd_cuda.so"), str(FAKE_SRC)], check=True)
+    # the host binary needs the real library only to LINK; build it if the tree is fresh
+    if not EXE.exists():
+        subprocess.run(["make", "-s", "-C", str(EXE.parent)], check=True)
+
+
+def run(*args, env=None):
+    e = dict(os.environ, LD_LIBRARY_PATH=str(FAKE_DIR), FQD_IO_THREADS="4")
+    e.update(env or {})
+    p = subprocess.run([str(EXE), *map(str, args)], capture_output=True, text=True, env=e, timeout=300)
+    assert "[fake_fqd] TEST DOUBLE" in p.stderr or p.returncode != 0 or "-h" in args
+    p.stderr = "".join(l + "\n" for l in p.stderr.splitlines() if not l.startswith("[fake_fqd]"))
+    return p
+
+
+@pytest.mark.parametrize("threads", ["1", "4"])
+@pytest.mark.parametrize("block", [4096, 1 << 16, None])
+def test_single_end_blocks_and_tail_carry(tmp_path, oracle, threads, block):
+    seqs = synth.make_reads(30000, seed=5, read_len=100, var_len=True, n_frac=0.02, dup_frac=0.4)
+    buf = synth.to_fastq(seqs)
+    (tmp_path / "in.fq").write_bytes(buf)
+    env = {"FQD_IO_THREADS": threads}
+    if block:
+        env["FQD_BLOCK_BYTES"] = str(block)
+    res = run("-i", tmp_path / "in.fq", "-o", tmp_path / "out.fq", "--fast", "-v", env=env)
+    assert res.returncode == 0, res.stderr
+    exp, _, est = oracle.run_oracle("fast", oracle.FASTQ, buf)
+    assert (tmp_path / "out.fq").read_bytes() == exp
+    assert res.stdout == f"{est.total} reads processed, out of which {est.dups} duplicates were removed.\n"
+
+
+def test_paired_gzip_inputs_and_outputs_files_of_different_length(tmp_path, oracle):
+    s1, s2 = synth.make_pair(40000, seed=6, read_len=80)
+    b1, b2 = synth.to_fastq(s1, mate=1), synth.to_fastq(s2[:35000], mate=2)       # R2 is shorter: stop there
+    (tmp_path / "a.fq.gz").write_bytes(members(b1, [400_000, 30_000]))
+    (tmp_path / "b.fq.gz").write_bytes(deflate_gz(b2, 6))                         # one member: block-parallel inflate
+    res = run("-i", tmp_path / "a.fq.gz", "-u", tmp_path / "b.fq.gz", "-o", tmp_path / "o1.fq.gz", "-p", tmp_path / "o2.fq.gz",
+              "--fast", "-v", env=dict(SMALL, FQD_BLOCK_BYTES=str(1 << 18)))
+    assert res.returncode == 0, res.stderr
+    e1, e2, est = oracle.run_oracle("fast", oracle.FASTQ, b1, b2)
+    assert gzip.decompress((tmp_path / "o1.fq.gz").read_bytes()) == e1
+    assert gzip.decompress((tmp_path / "o2.fq.gz").read_bytes()) == e2
+    assert res.stdout == f"{est.total} read pairs processed, out of which {est.dups} duplicates were removed.\n"
+
+
+def test_fasta_and_bgzf(tmp_path, oracle):
+    seqs = synth.make_reads(20000, seed=7, read_len=60, var_len=True, dup_frac=0.3)
+    buf = synth.to_fasta(seqs)
+    (tmp_path / "in.fa.gz").write_bytes(bgzf(buf))
+    res = run("-i", tmp_path / "in.fa.gz", "-o", tmp_path / "out.fa", "--format", "fasta", "--fast", "-v", env={"FQD_BLOCK_BYTES": str(1 << 16)})
+    assert res.returncode == 0, res.stderr
+    exp, _, est = oracle.run_oracle("fast", oracle.FASTA, buf)
+    assert (tmp_path / "out.fa").read_bytes() == exp
+
+
+def test_restart_when_the_capacity_estimate_was_too_small(tmp_path, oracle):
+    """The double pretends its key store is 4 x smaller than asked for: the run hits FQD_ERR_CAPACITY after survivors
+    have been written, starts over with doubled tables (twice), and the final output is still exact."""
+    seqs = synth.make_reads(150000, seed=8, read_len=50, dup_frac=0.2)
+    buf = synth.to_fastq(seqs)
+    (tmp_path / "in.fq").write_bytes(buf)
+    res = run("-i", tmp_path / "in.fq", "-o", tmp_path / "out.fq", "--fast", "-v",
+              env={"FAKE_FQD_SHRINK": "4", "FQD_BLOCK_BYTES": str(1 << 20), "FQD_TRACE": "1"})
+    assert res.returncode == 0, res.stderr
+    assert res.stderr.count("engine created") == 3            # two restarts
+    exp, _, est = oracle.run_oracle("fast", oracle.FASTQ, buf)
+    assert (tmp_path / "out.fq").read_bytes() == exp
+    assert res.stdout == f"{est.total} reads processed, out of which {est.dups} duplicates were removed.\n"
+
+
+def test_restart_when_a_later_read_is_longer_than_the_sampled_ones(tmp_path, oracle):
+    short = synth.make_reads(3000, seed=9, read_len=40, dup_frac=0.2)
+    long_ = synth.make_reads(3000, seed=10, read_len=130, dup_frac=0.2)
+    buf = synth.to_fastq(short + long_)
+    (tmp_path / "in.fq").write_bytes(buf)
+    res = run("-i", tmp_path / "in.fq", "-o", tmp_path / "out.fq", "--fast", "-v", env={"FQD_BLOCK_BYTES": str(1 << 14), "FQD_TRACE": "1"})
+    assert res.returncode == 0, res.stderr
+    assert res.stderr.count("engine created") >= 2            # started over with wider key rows
+    exp, _, est = oracle.run_oracle("fast", oracle.FASTQ, buf)
+    assert (tmp_path / "out.fq").read_bytes() == exp
+
+
+def test_errors_reach_the_user_with_the_reference_wording(tmp_path):
+    # empty input (src/bufferedinput.hpp:82-85)
+    (tmp_path / "e.fq").write_bytes(b"")
+    res = run("-i", tmp_path / "e.fq", "-o", tmp_path / "o.fq", "--fast")
+    assert res.returncode == 1 and res.stderr == "An error occured during fastq-dupaway execution:\nNot enough memory to read a single object!\n"
+    # missing input (src/file_utils.hpp:110-121); the output file has been created already, like the reference
+    res = run("-i", tmp_path / "nope.fq", "-o", tmp_path / "o2.fq", "--fast")
+    assert res.returncode == 1 and "Cannot open file" in res.stderr and (tmp_path / "o2.fq").exists()
+    # wrong first byte (src/fastqview.cpp:121-126)
+    (tmp_path / "x.fq").write_bytes(b">r\nACGT\n")
+    res = run("-i", tmp_path / "x.fq", "-o", tmp_path / "o3.fq", "--fast")
+    assert res.returncode == 1 and "Invalid record start character: >" in res.stderr
+    assert "Fastq record should start with @ symbol!" in res.stderr
+    # a base outside {A,C,G,T,N} in a later block (src/seq_utils.cpp:17-19): what came before is written
+    good = synth.to_fastq(synth.make_reads(2000, seed=11, read_len=50, dup_frac=0.0))
+    (tmp_path / "b.fq").write_bytes(good + b"@bad\nACGU\n+\nIIII\n" + good)
+    res = run("-i", tmp_path / "b.fq", "-o", tmp_path / "o4.fq", "--fast", env={"FQD_BLOCK_BYTES": str(1 << 14)})
+    assert res.returncode == 1
+    assert "Error: unknown character in DNA sequence: U" in res.stderr
+    assert "Supported sequence character set: {A, N, C, G, T}!" in res.stderr
+    assert (tmp_path / "o4.fq").read_bytes() == good
+    # corrupt gzip input
+    blob = bytearray(deflate_gz(good, 6))
+    blob[len(blob) // 2] ^= 0x20
+    (tmp_path / "c.fq.gz").write_bytes(bytes(blob))
+    res = run("-i", tmp_path / "c.fq.gz", "-o", tmp_path / "o5.fq", "--fast")
+    assert res.returncode == 1 and "gzip error" in res.stderr
