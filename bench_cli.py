@@ -35,16 +35,23 @@ READ_LEN, SEED, DUP_PERMILLE, N_PERMILLE = 150, 1, 300, 0
 REC = 22 + 2 * READ_LEN
 
 
-def synth_file(path: Path, n_reads: int):
-    """device generator -> host -> file, 4 M reads at a time"""
+def synth_file(path: Path, n_reads: int, mate: int = 1):
+    """device generator -> host -> file, 4 M reads at a time (FQD_BENCH_CLI_CPU_SYNTH=1: the numpy twin of the generator,
+    for trying this script where there is no GPU)"""
+    step = 4_000_000
+    if os.environ.get("FQD_BENCH_CLI_CPU_SYNTH"):
+        gen = importlib.import_module("bench_synth")
+        with open(path, "wb") as f:
+            for first in range(0, n_reads, step):
+                f.write(gen.synth_fastq_cpu(first, min(step, n_reads - first), READ_LEN, mate, SEED, DUP_PERMILLE, N_PERMILLE))
+        return
     pkg = importlib.import_module("fastq-dupaway_b200")
     lib = pkg.load_library()
-    step = 4_000_000
     buf = pkg.DeviceBuffer(step * REC)
     with open(path, "wb") as f:
         for first in range(0, n_reads, step):
             cnt = min(step, n_reads - first)
-            rc = lib.fqd_synth_fastq(0, buf.ptr, first, cnt, READ_LEN, 1, SEED, DUP_PERMILLE, N_PERMILLE, 0)
+            rc = lib.fqd_synth_fastq(0, buf.ptr, first, cnt, READ_LEN, mate, SEED, DUP_PERMILLE, N_PERMILLE, 0)
             assert rc == 0
             f.write(buf.download(cnt * REC))
     buf.free()
@@ -108,66 +115,91 @@ def timed(cmd, cwd, trace=False):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--reads", type=int, default=10_000_000)
+    ap.add_argument("--reads", type=int, default=10_000_000, help="reads (pairs with --paired)")
     ap.add_argument("--ref-reads", type=int, default=2_000_000)
     ap.add_argument("--formats", default="plain,gz1,gzmm,bgzf")
-    ap.add_argument("--mode", default="fast", choices=["fast", "tight"])
+    ap.add_argument("--mode", default="fast", choices=["fast", "tight", "loose", "tail-hamming"])
+    ap.add_argument("--paired", action="store_true", help="2 x 150 bp: -i/-u inputs, -o/-p outputs")
     ap.add_argument("--repeats", type=int, default=2)
     args = ap.parse_args()
     oracle = importlib.import_module("oracle")
     tmp = Path(tempfile.mkdtemp(prefix="fqd_cli_", dir="/dev/shm" if Path("/dev/shm").is_dir() else None))
-    mode_args = ["--fast"] if args.mode == "fast" else ["--compare-seq", "tight"]
+    mode_args = ["--fast"] if args.mode == "fast" else ["--compare-seq", args.mode]
+    mates = (1, 2) if args.paired else (1,)
+    unit = "pairs" if args.paired else "reads"
+
+    def io_args(ins, outs):
+        a = ["-i", ins[0], "-o", outs[0]]
+        if args.paired:
+            a += ["-u", ins[1], "-p", outs[1]]
+        return a
+
+    def make(fmt, src, dst):
+        if fmt == "gzmm":
+            gz_members(src, dst, 16 << 20, False)
+        elif fmt == "bgzf":
+            gz_members(src, dst, 0xff00, True)
+        elif fmt == "gz1":
+            gz_single_member(src, dst)
     try:
-        full = tmp / "in.fq"
-        synth_file(full, args.reads)
+        full = [tmp / f"in_{m}.fq" for m in mates]
+        for m, f in zip(mates, full):
+            synth_file(f, args.reads, m)
         inputs = {"plain": full}
         for fmt in args.formats.split(","):
-            if fmt == "gzmm":
-                inputs[fmt] = tmp / "in_mm.fq.gz"
-                gz_members(full, inputs[fmt], 16 << 20, False)
-            elif fmt == "bgzf":
-                inputs[fmt] = tmp / "in_bgzf.fq.gz"
-                gz_members(full, inputs[fmt], 0xff00, True)
-            elif fmt == "gz1":
-                inputs[fmt] = tmp / "in_single.fq.gz"
-                gz_single_member(full, inputs[fmt])
+            if fmt != "plain":
+                inputs[fmt] = [tmp / f"in_{fmt}_{m}.fq.gz" for m in mates]
+                for src, dst in zip(full, inputs[fmt]):
+                    make(fmt, src, dst)
+        outs = [tmp / f"out_{m}.fq" for m in mates]
         for fmt in args.formats.split(","):
-            inp = inputs[fmt]
             best = None
             phases = {}
             for _ in range(args.repeats):
-                dt, so, ph = timed([EXE, "-i", inp, "-o", tmp / "out.fq", "-v", *mode_args], tmp, trace=True)
+                dt, so, ph = timed([EXE, *io_args(inputs[fmt], outs), "-v", *mode_args], tmp, trace=True)
                 if best is None or dt < best:
                     best, phases = dt, ph
             if phases.get("stream_s"):
-                phases["stream_reads_per_s"] = round(args.reads / phases["stream_s"])
-            print(json.dumps({"impl": "ours", **phases, "binary": "fastq-dupaway_b200/host/fastq-dupaway", "mode": args.mode, "input": fmt,
-                              "reads": args.reads, "input_bytes": inp.stat().st_size, "seconds": round(best, 3),
-                              "reads_per_s": round(args.reads / best), "raw_GBps": round(args.reads * REC / best / 1e9, 3),
+                phases[f"stream_{unit}_per_s"] = round(args.reads / phases["stream_s"])
+            print(json.dumps({"impl": "ours", **phases, "binary": "fastq-dupaway_b200/host/fastq-dupaway", "mode": args.mode,
+                              "paired": args.paired, "input": fmt, unit: args.reads,
+                              "input_bytes": sum(f.stat().st_size for f in inputs[fmt]), "seconds": round(best, 3),
+                              f"{unit}_per_s": round(args.reads / best),
+                              "raw_GBps": round(args.reads * REC * len(mates) / best / 1e9, 3),
                               "io_threads": os.environ.get("FQD_IO_THREADS", "auto"), "host_cores": os.cpu_count(), "stdout": so}), flush=True)
-        # common prefix: both binaries, outputs compared
+        # common prefix: both binaries, outputs compared.  Sequence-based modes: the reference's choice inside a group of
+        # equal records depends on its unstable sort, so the comparison is with the stable-sort build of the
+        # same sources and the timing with the plain build.
         n = min(args.ref_reads, args.reads)
-        pre = tmp / "pre.fq"
-        with open(full, "rb") as f, open(pre, "wb") as g:
-            g.write(f.read(n * REC))
-        dt_o, so_o = timed([EXE, "-i", pre, "-o", tmp / "o_ours.fq", "-v", *mode_args], tmp)
+        pre = [tmp / f"pre_{m}.fq" for m in mates]
+        for src, dst in zip(full, pre):
+            with open(src, "rb") as f, open(dst, "wb") as g:
+                g.write(f.read(n * REC))
+        o_ours = [tmp / f"o_ours_{m}.fq" for m in mates]
+        o_ref = [tmp / f"o_ref_{m}.fq" for m in mates]
+        dt_o, so_o = timed([EXE, *io_args(pre, o_ours), "-v", *mode_args], tmp)
         if oracle.ref_available():
             ref_args = mode_args + ([] if args.mode == "fast" else ["-m", "10240"])
-            dt_r, so_r = timed([oracle.REF_BIN, "-i", pre, "-o", tmp / "o_ref.fq", "-v", *ref_args], tmp)
-            same = (tmp / "o_ours.fq").read_bytes() == (tmp / "o_ref.fq").read_bytes()
-            print(json.dumps({"impl": "reference", "binary": "oracle/_ref/fastq-dupaway", "mode": args.mode, "input": "plain", "reads": n,
-                              "seconds": round(dt_r, 3), "reads_per_s": round(n / dt_r), "cores": 1, "stdout": so_r,
-                              "ours_same_input_seconds": round(dt_o, 3), "outputs_byte_identical": same,
-                              "verbose_lines_identical": so_o == so_r}), flush=True)
+            dt_r, so_r = timed([oracle.REF_BIN, *io_args(pre, o_ref), "-v", *ref_args], tmp)
+            cmp_bin = "oracle/_ref/fastq-dupaway"
+            if args.mode != "fast" and oracle.ref_available(stable=True):
+                timed([oracle.REF_STABLE_BIN, *io_args(pre, o_ref), "-v", *ref_args], tmp)
+                cmp_bin = "oracle/_ref/fastq-dupaway-stable"
+            same = all(a.read_bytes() == b.read_bytes() for a, b in zip(o_ours, o_ref))
+            print(json.dumps({"impl": "reference", "binary": "oracle/_ref/fastq-dupaway", "mode": args.mode, "paired": args.paired,
+                              "input": "plain", unit: n, "seconds": round(dt_r, 3), f"{unit}_per_s": round(n / dt_r), "cores": 1,
+                              "stdout": so_r, "ours_same_input_seconds": round(dt_o, 3), "outputs_byte_identical": same,
+                              "outputs_compared_with": cmp_bin, "verbose_lines_identical": so_o == so_r}), flush=True)
             if "gz1" in inputs:
                 # the reference on a single-member .gz of the same prefix (its gzip filter runs on the same one thread)
-                gz_single_member(pre, tmp / "pre.fq.gz")
-                dt_g, _ = timed([oracle.REF_BIN, "-i", tmp / "pre.fq.gz", "-o", tmp / "o_ref_gz.fq", "-v", *ref_args], tmp)
-                dt_og, _ = timed([EXE, "-i", tmp / "pre.fq.gz", "-o", tmp / "o_ours_gz.fq", "-v", *mode_args], tmp)
-                same = (tmp / "o_ours_gz.fq").read_bytes() == (tmp / "o_ref_gz.fq").read_bytes()
-                print(json.dumps({"impl": "reference", "binary": "oracle/_ref/fastq-dupaway", "mode": args.mode, "input": "gz1", "reads": n,
-                                  "seconds": round(dt_g, 3), "reads_per_s": round(n / dt_g), "cores": 1,
-                                  "ours_same_input_seconds": round(dt_og, 3), "outputs_byte_identical": same}), flush=True)
+                pre_gz = [tmp / f"pre_{m}.fq.gz" for m in mates]
+                for src, dst in zip(pre, pre_gz):
+                    gz_single_member(src, dst)
+                dt_g, _ = timed([oracle.REF_BIN, *io_args(pre_gz, o_ref), "-v", *ref_args], tmp)
+                dt_og, _ = timed([EXE, *io_args(pre_gz, o_ours), "-v", *mode_args], tmp)
+                print(json.dumps({"impl": "reference", "binary": "oracle/_ref/fastq-dupaway", "mode": args.mode, "paired": args.paired,
+                                  "input": "gz1", unit: n, "seconds": round(dt_g, 3), f"{unit}_per_s": round(n / dt_g), "cores": 1,
+                                  "ours_same_input_seconds": round(dt_og, 3)}), flush=True)
         else:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/fastq-dupaway not built"}), flush=True)
     finally:
