@@ -16,7 +16,7 @@
 //   * a member too large for a task (single-member files, pigz output) is inflated serially, streaming, straight
 //     into the caller's buffer - today's behaviour - and the parallel plan resumes at the next member boundary.
 // Egress (ParallelGzSink): the output is cut into 1 MiB pieces, each deflated as a member of its own on a worker
-// and written in order (a valid multi-member gzip file; `zcat`, the reference and this reader all accept it).
+// and written in order (a valid multi-member gzip file, RFC 1952 section 2.2: `zcat`, Python and this reader read it as one stream).
 // The compressed bytes of the reference's .gz outputs are unpinned; the decompressed content is what
 // parity is about.
 //
