@@ -433,6 +433,12 @@ def dedup_fast(b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, chunk_bytes
             if tail_err is not None:
                 st.err, st.err_char, st.err_record = 4, tail_err[1], st.total
                 break
+            if st.err == 6 and st.err_record == 0:
+                # the reference writes the very first record (pair) BEFORE it keys it (src/hash_dup_remover.hpp:118-124,
+                # 216-228): a base outside {A,C,G,T,N} in record 0 still leaves record 0 in the output
+                for m in range(n_mates):
+                    span = _np(res.rec_start[m], 2, np.int64)
+                    outs[m].append(chunk[m][int(span[0]): int(span[1])])
             if st.err:
                 break
             if all(pos[m] >= len(bufs[m]) for m in range(n_mates)):

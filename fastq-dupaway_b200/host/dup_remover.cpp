@@ -174,6 +174,7 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
         }
         auto close_outputs = [&] { for (auto& w : writers) w->drain(); for (auto& o : outs) o->close(); };
         std::vector<Run> runs;
+        struct { bool valid = false; std::vector<char> bytes[2]; } held;      // last written pair of the previous chunk
         for (int m = 0; m < mates; ++m)
             if (!ms[m].refill()) throw std::runtime_error("Not enough memory to read a single object!");   // empty file
         for (int m = 0; m < mates; ++m)       // the very first record is validated by set_file()'s refresh (src/bufferedinput.hpp:76-86)
@@ -240,8 +241,31 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
                 n -= 1;
                 chunk_dups -= last_dup;
             }
+            // The lazy pre-parse reaches across chunks as well: the LAST pair of a chunk is written only once the
+            // record that follows it has parsed - which may need the next block (a sequence / quality length mismatch
+            // shows when the record is complete).  So that pair is held back (a copy of its bytes) and written in
+            // front of the next chunk's survivors, or dropped if that chunk opens with a malformed record.
+            const bool stops_here = st.err != 0 || tail_err_mate >= 0;
+            if (held.valid && (n > 0 || stops_here)) {
+                const bool next_is_malformed = (st.err == FQD_ERR_BAD_START || st.err == FQD_ERR_LEN_MISMATCH) &&
+                                               st.err_record == res.first_record;
+                if (!next_is_malformed)
+                    for (int m = 0; m < mates; ++m) writers[m]->write_owned(std::move(held.bytes[m]));
+                held.valid = false;
+            }
+            size_t n_now = n;
+            if (n > 0 && !stops_here) {
+                n_now = n - 1;
+                if (!res.dup[n - 1]) {
+                    held.valid = true;
+                    for (int m = 0; m < mates; ++m) {
+                        const char* b = ms[m].ptr + res.rec_start[m][n - 1];
+                        held.bytes[m].assign(b, (const char*)(ms[m].ptr + res.rec_start[m][n]));
+                    }
+                }
+            }
             for (int m = 0; m < mates; ++m) {
-                const size_t bytes = survivor_runs(res.rec_start[m], res.dup, n, runs);
+                const size_t bytes = survivor_runs(res.rec_start[m], res.dup, n_now, runs);
                 writers[m]->write_runs(ms[m].ptr, std::move(runs), bytes);
                 runs = std::vector<Run>();
             }
@@ -252,6 +276,14 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
                 throw_data_error(st, m_fasta);
             }
             if (st.err) {
+                if (st.err == FQD_ERR_BAD_BASE && st.err_record == 0) {
+                    // the reference writes the very first record (pair) BEFORE it keys it
+                    // (src/hash_dup_remover.hpp:118-124,216-228): a bad base there still leaves it in the output
+                    for (int m = 0; m < mates; ++m) {
+                        const char* b = ms[m].ptr + res.rec_start[m][0];
+                        writers[m]->write_owned(std::vector<char>(b, (const char*)(ms[m].ptr + res.rec_start[m][1])));
+                    }
+                }
                 close_outputs();
                 const int em = st.err_mate;
                 size_t e = (size_t)(st.err_record - res.first_record);
@@ -275,6 +307,8 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
         }
         trace("last chunk processed");
         if (restart) continue;
+        if (held.valid)
+            for (int m = 0; m < mates; ++m) writers[m]->write_owned(std::move(held.bytes[m]));
         if (total == 0) {
             fqd_stats_t st; memset(&st, 0, sizeof st); st.err = FQD_ERR_EMPTY;
             throw_data_error(st, m_fasta);

@@ -384,13 +384,19 @@ public:
         Job j; j.base = base; j.runs = std::move(runs); j.total = total;
         push(std::move(j));
     }
+    // bytes the job owns (a vector: its heap block does not move with the job)
+    void write_owned(std::vector<char>&& bytes) {
+        if (bytes.empty()) return;
+        Job j; j.owned = std::move(bytes);
+        push(std::move(j));
+    }
     void then(std::function<void()> f) { Job j; j.fn = std::move(f); push(std::move(j)); }
     void drain() {
         std::unique_lock<std::mutex> g(m_mu);
         m_cv.wait(g, [this] { return m_q.empty() && !m_busy; });
     }
 private:
-    struct Job { const char* base = nullptr; std::vector<Run> runs; size_t total = 0; std::function<void()> fn; };
+    struct Job { const char* base = nullptr; std::vector<Run> runs; size_t total = 0; std::function<void()> fn; std::vector<char> owned; };
     void push(Job&& j) {
         { std::lock_guard<std::mutex> g(m_mu); m_q.push_back(std::move(j)); }
         m_cv.notify_all();
@@ -405,7 +411,9 @@ private:
                 j = std::move(m_q.front()); m_q.pop_front();
                 m_busy = true;
             }
-            if (j.fn) j.fn(); else m_out.write_runs(j.base, j.runs.data(), j.runs.size(), j.total);
+            if (j.fn) j.fn();
+            else if (!j.owned.empty()) m_out.write(j.owned.data(), j.owned.size());
+            else m_out.write_runs(j.base, j.runs.data(), j.runs.size(), j.total);
             { std::lock_guard<std::mutex> g(m_mu); m_busy = false; }
             m_cv.notify_all();
         }

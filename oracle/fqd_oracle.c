@@ -257,12 +257,16 @@ int fqdo_fast_se(const char* buf, int64_t n, int format, uint64_t* out_idx, uint
     uint64_t idx = 0;
     int first = 1;
     /* first record is written and inserted unconditionally (:118-124); then the block loop (:126-144).
-     * With a single block the two are the same "fetch, test, write" step. */
+     * With a single block the two are the same "fetch, test, write" step - except that the first record is WRITTEN
+     * (:122) before it is keyed (:123), so a base outside {A,C,G,T,N} in record 0 leaves record 0 in the output. */
     while (first || !b.block_end) {
         first = 0;
         if (bi_next(&b, &r)) { st->err = b.err; st->err_char = b.err_char; st->err_record = b.n_parsed; break; }
         int64_t kw = build_key(&kb, 0, buf, &r, &bad);
-        if (kw == -1) { st->err = FQDO_ERR_BAD_BASE; st->err_char = bad; st->err_record = idx; break; }
+        if (kw == -1) {
+            if (idx == 0) out_idx[(*n_out)++] = 0;
+            st->err = FQDO_ERR_BAD_BASE; st->err_char = bad; st->err_record = idx; break;
+        }
         if (kw < 0) { st->err = FQDO_ERR_NOMEM; break; }
         st->total++;
         int ins = ks_insert(&ks, kb.w, (size_t)kw);
@@ -287,10 +291,11 @@ int fqdo_fast_pe(const char* buf1, int64_t n1, const char* buf2, int64_t n2, int
         first = 0;
         if (bi_next(&b1, &l)) { st->err = b1.err; st->err_char = b1.err_char; st->err_record = b1.n_parsed; break; }
         if (bi_next(&b2, &r)) { st->err = b2.err; st->err_char = b2.err_char; st->err_record = b2.n_parsed; break; }
+        /* the first pair is written to both files (:220-221) before it is keyed (:222-227) */
         int64_t k1 = build_key(&kb, 0, buf1, &l, &bad);
-        if (k1 == -1) { st->err = FQDO_ERR_BAD_BASE; st->err_char = bad; st->err_record = idx; break; }
+        if (k1 == -1) { if (idx == 0) out_idx[(*n_out)++] = 0; st->err = FQDO_ERR_BAD_BASE; st->err_char = bad; st->err_record = idx; break; }
         int64_t k2 = (k1 < 0) ? k1 : build_key(&kb, (size_t)k1, buf2, &r, &bad);
-        if (k2 == -1) { st->err = FQDO_ERR_BAD_BASE; st->err_char = bad; st->err_record = idx; break; }
+        if (k2 == -1) { if (idx == 0) out_idx[(*n_out)++] = 0; st->err = FQDO_ERR_BAD_BASE; st->err_char = bad; st->err_record = idx; break; }
         if (k1 < 0 || k2 < 0) { st->err = FQDO_ERR_NOMEM; break; }
         st->total++;
         int ins = ks_insert(&ks, kb.w, (size_t)(k1 + k2));

@@ -69,37 +69,64 @@ static std::string seq_of(const char* rec, const char* rec_end) {
     return std::string(l1, l1e);
 }
 
+// The engine's contract for data errors (include/fqd.h, csrc/fqd_api.cu::fold_chunk), restated: the first error in the
+// order in which the reference would meet it.  Fetching pair k pre-parses record k+1 of each mate (left first), so a
+// malformed record e (bad first byte, or FASTQ sequence / quality lengths differ) aborts before pair e-1 is processed;
+// a base outside {A,C,G,T,N} in pair j aborts while pair j is keyed (left mate first).
 int fqd_push(fqd_handle* h, const char* r1, size_t n1, const char* r2, size_t n2, fqd_chunk_result* res) {
     if (!h || h->cfg.mode != FQD_MODE_FAST || h->cfg.unordered) { if (h) h->err = "the fake knows ordered --fast only"; return FQD_ERR_INVALID; }
     if (n1 > h->cfg.max_chunk_bytes || n2 > h->cfg.max_chunk_bytes) { h->err = "chunk larger than max_chunk_bytes"; return FQD_ERR_INVALID; }
     const int mates = h->cfg.paired ? 2 : 1;
-    const int lpr = h->cfg.format == FQD_FORMAT_FASTA ? 2 : 4;
+    const bool fasta = h->cfg.format == FQD_FORMAT_FASTA;
+    const int lpr = fasta ? 2 : 4;
+    const char lead = fasta ? '>' : '@';
     const char* buf[2] = {r1, r2}; const size_t len[2] = {n1, n2};
     for (int m = 0; m < mates; ++m) split(buf[m], len[m], lpr, h->rec_start[m]);
     size_t pairs = h->rec_start[0].size() - 1;
     if (mates == 2) pairs = std::min(pairs, h->rec_start[1].size() - 1);
     for (int m = 0; m < mates; ++m) h->rec_start[m].resize(pairs + 1);
     h->dup.assign(pairs, 0);
-    size_t n_ok = pairs; uint64_t dups = 0;
-    for (size_t i = 0; i < pairs && !h->st.err; ++i) {
-        std::string key;
+    size_t n_ok = pairs;
+    const uint64_t first = h->n_records;
+    if (!h->st.err) {
+        bool have = false; long long best_t = 0; int code = 0, ch = 0, mate = 0; uint64_t rec = 0; size_t ok = 0;
+        auto consider = [&](long long t, int c, int chr, int m, uint64_t r, size_t nk) {
+            if (!have || t < best_t) { have = true; best_t = t; code = c; ch = chr; mate = m; rec = r; ok = nk; }
+        };
         for (int m = 0; m < mates; ++m) {
-            const std::string s = seq_of(buf[m] + h->rec_start[m][i], buf[m] + h->rec_start[m][i + 1]);
-            if (s.size() > h->cfg.max_seq_len) { h->st.err = FQD_ERR_SEQ_TOO_LONG; n_ok = 0; break; }
-            for (char c : s)
-                if (!std::strchr("ACGTN", c) || c == 0) { h->st.err = FQD_ERR_BAD_BASE; h->st.err_char = (unsigned char)c; h->st.err_record = h->n_records + i; h->st.err_mate = m; n_ok = i; break; }
-            if (h->st.err) break;
-            key += s; key += '\n';
+            for (size_t e = 0; e <= pairs; ++e) {            // record `pairs` is the (possibly incomplete) one that follows
+                const size_t off = h->rec_start[m][e];
+                if (off >= len[m]) break;
+                const long long t = e == 0 ? (first == 0 ? -8 + m : -4 + m) : (long long)(e - 1) * 4 + m;
+                if (buf[m][off] != lead) { consider(t, FQD_ERR_BAD_START, (unsigned char)buf[m][off], m, first + e, e == 0 ? 0 : e - 1); break; }
+                if (e == pairs) break;
+                const char* rb = buf[m] + off; const char* re = buf[m] + h->rec_start[m][e + 1];
+                const std::string s = seq_of(rb, re);
+                if (!fasta) {
+                    const char* l3 = rb; for (int k = 0; k < 3; ++k) l3 = (const char*)std::memchr(l3, '\n', re - l3) + 1;
+                    const size_t qlen = (size_t)(re - l3) - 1;
+                    if (qlen != s.size()) { consider(t, FQD_ERR_LEN_MISMATCH, 0, m, first + e, e == 0 ? 0 : e - 1); break; }
+                }
+                if (s.size() > h->cfg.max_seq_len) { consider(1ll << 60, FQD_ERR_SEQ_TOO_LONG, 0, m, 0, 0); break; }
+                size_t bad = s.find_first_not_of("ACGTN");
+                if (bad != std::string::npos) { consider((long long)e * 4 + 2 + m, FQD_ERR_BAD_BASE, (unsigned char)s[bad], m, first + e, e); break; }
+            }
         }
-        if (h->st.err) break;
-        if (h->n_records + i >= h->capacity) { h->st.err = FQD_ERR_CAPACITY; n_ok = i; break; }
+        if (have) { h->st.err = code; h->st.err_char = ch; h->st.err_mate = mate; h->st.err_record = rec; n_ok = ok; }
+    } else {
+        n_ok = 0;
+    }
+    uint64_t dups = 0;
+    for (size_t i = 0; i < n_ok; ++i) {
+        if (first + i >= h->capacity) { if (!h->st.err) h->st.err = FQD_ERR_CAPACITY; n_ok = i; break; }
+        std::string key;
+        for (int m = 0; m < mates; ++m) { key += seq_of(buf[m] + h->rec_start[m][i], buf[m] + h->rec_start[m][i + 1]); key += '\n'; }
         if (!h->seen.insert(key).second) { h->dup[i] = 1; ++dups; }
     }
-    if (h->st.err == FQD_ERR_BAD_BASE) { dups = 0; for (size_t i = 0; i < n_ok; ++i) dups += h->dup[i]; }
     h->st.total += n_ok; h->st.dups += dups;
     if (res) {
         std::memset(res, 0, sizeof *res);
-        res->n_records = n_ok; res->first_record = h->n_records; res->n_survivors = n_ok - dups;
+        res->n_records = n_ok; res->first_record = first; res->n_survivors = n_ok - dups;
         res->dup = h->dup.data();
         for (int m = 0; m < mates; ++m) { res->rec_start[m] = h->rec_start[m].data(); res->consumed[m] = len[m] ? h->rec_start[m][pairs] : 0; }
     }

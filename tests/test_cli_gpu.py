@@ -165,6 +165,8 @@ def test_error_messages_and_exit_codes(tmp_path):
     assert r.returncode == 1
     assert r.stderr == "Error: unknown character in DNA sequence: X\n" + banner + "Supported sequence character set: {A, N, C, G, T}!\n"
     assert (tmp_path / "e.out").read_bytes() == b"@a\nACGT\n+\nFFFF\n"
+    r = go(b"@a\nACXT\n+\nFFFF\n@b\nAAAA\n+\nFFFF\n")      # the reference writes record 0 before keying it
+    assert r.returncode == 1 and (tmp_path / "e.out").read_bytes() == b"@a\nACXT\n+\nFFFF\n"
     r = go(b"xa\nACGT\n+\nFFFF\n")
     assert r.returncode == 1 and r.stderr == "Invalid record start character: x\n" + banner + "Fastq record should start with @ symbol!\n"
     r = go(b"@a\nACGT\n+\nFFF\n")

@@ -134,3 +134,69 @@ def test_errors_reach_the_user_with_the_reference_wording(tmp_path):
     (tmp_path / "c.fq.gz").write_bytes(bytes(blob))
     res = run("-i", tmp_path / "c.fq.gz", "-o", tmp_path / "o5.fq", "--fast")
     assert res.returncode == 1 and "gzip error" in res.stderr
+
+
+def _records(n, seed, mate=1, read_len=100):
+    seqs = synth.make_reads(n, seed=seed, read_len=read_len, dup_frac=0.3)
+    buf = synth.to_fastq(seqs, mate=mate)
+    lines = buf.split(b"\n")[:-1]
+    return [b"\n".join(lines[i:i + 4]) + b"\n" for i in range(0, len(lines), 4)]
+
+
+def _damage(rec, kind):
+    l = rec.split(b"\n")
+    if kind == "start":
+        l[0] = b"X" + l[0][1:]
+    elif kind == "length":
+        l[3] = l[3][:-3]
+    elif kind == "base":
+        l[1] = l[1][:10] + b"U" + l[1][11:]
+    return b"\n".join(l)
+
+
+@pytest.mark.parametrize("kind", ["start", "length", "base"])
+def test_malformed_record_at_every_position_matches_the_reference_binary(tmp_path, oracle, kind):
+    """One malformed record, at every index of a 40-record file that spans ten 1 KiB..4 KiB blocks here and one block in
+    the reference: exit status, stderr and the bytes written before the stop must be the reference binary's.  This is
+    the lazy pre-parse rule (src/bufferedinput.hpp:90-103) carried across block boundaries by dup_remover.cpp - the tail
+    check, the peeked next block, the record dropped in front of a bad start."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/fastq-dupaway not built")
+    recs = _records(40, seed=30)
+    for pos in range(40):
+        data = b"".join(recs[:pos] + [_damage(recs[pos], kind)] + recs[pos + 1:])
+        inp = tmp_path / "in.fq"
+        inp.write_bytes(data)
+        ref = subprocess.run([str(oracle.REF_BIN), "-i", str(inp), "-o", str(tmp_path / "ref.fq"), "--fast", "-v"],
+                             capture_output=True, text=True, cwd=tmp_path)
+        for block in (4096, 1 << 20):
+            ours = run("-i", inp, "-o", tmp_path / "ours.fq", "--fast", "-v", env={"FQD_BLOCK_BYTES": str(block)})
+            assert ours.returncode == ref.returncode == 1, (pos, block)
+            assert ours.stderr == ref.stderr, (pos, block)
+            assert ours.stdout == ref.stdout
+            assert (tmp_path / "ours.fq").read_bytes() == (tmp_path / "ref.fq").read_bytes(), (pos, block)
+
+
+@pytest.mark.parametrize("kind", ["start", "length", "base"])
+@pytest.mark.parametrize("bad_mate", [0, 1])
+def test_malformed_record_in_paired_input_matches_the_reference_binary(tmp_path, oracle, kind, bad_mate):
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/fastq-dupaway not built")
+    r = [_records(24, seed=31, mate=1), _records(24, seed=32, mate=2, read_len=80)]
+    for pos in range(0, 24, 1):
+        files = []
+        for m in (0, 1):
+            recs = list(r[m])
+            if m == bad_mate:
+                recs[pos] = _damage(recs[pos], kind)
+            f = tmp_path / f"in{m}.fq"
+            f.write_bytes(b"".join(recs))
+            files.append(f)
+        ref = subprocess.run([str(oracle.REF_BIN), "-i", str(files[0]), "-u", str(files[1]), "-o", str(tmp_path / "r1.fq"),
+                              "-p", str(tmp_path / "r2.fq"), "--fast", "-v"], capture_output=True, text=True, cwd=tmp_path)
+        ours = run("-i", files[0], "-u", files[1], "-o", tmp_path / "o1.fq", "-p", tmp_path / "o2.fq", "--fast", "-v",
+                   env={"FQD_BLOCK_BYTES": "4096"})
+        assert ours.returncode == ref.returncode == 1, pos
+        assert ours.stderr == ref.stderr, pos
+        assert (tmp_path / "o1.fq").read_bytes() == (tmp_path / "r1.fq").read_bytes(), pos
+        assert (tmp_path / "o2.fq").read_bytes() == (tmp_path / "r2.fq").read_bytes(), pos

@@ -119,6 +119,18 @@ def test_error_paths(fqd, oracle):
     assert chr(st.err_char) == "X" and st.err_record == 1
 
 
+def test_bad_base_in_the_very_first_record(fqd, oracle):
+    """The reference writes record 0 (pair 0) before it keys it, so a base outside {A,C,G,T,N} there stops the run with
+    that record already in the output (pinned against the reference binary in tests/test_oracle.py)."""
+    se = b"@a\nACXT\n+\nFFFF\n@b\nAAAA\n+\nFFFF\n"
+    out, st = _check_se(fqd, oracle, se, fqd.FORMAT_FASTQ)
+    assert out == b"@a\nACXT\n+\nFFFF\n" and st.err == 6 and st.err_record == 0
+    good = b"@a\nACGT\n+\nFFFF\n@b\nAAAA\n+\nFFFF\n"
+    o1, o2, st = _check_pe(fqd, oracle, good, se, fqd.FORMAT_FASTQ)
+    assert o1 == b"@a\nACGT\n+\nFFFF\n" and o2 == b"@a\nACXT\n+\nFFFF\n"
+    _check_pe(fqd, oracle, se, good, fqd.FORMAT_FASTQ)
+
+
 def test_error_in_later_chunk(fqd, oracle):
     seqs = synth.make_reads(5000, seed=10, read_len=80)
     seqs[3777] = seqs[3777][:30] + b"Z" + seqs[3777][31:]

@@ -232,3 +232,39 @@ def test_ref_error_paths(oracle, tmp_path):
         out, _, st = oracle.run_oracle("fast", oracle.FASTQ, buf)
         assert (rc != 0) == (st.err != 0), (k, rc, st.err)
         assert out == r1, k
+
+
+def _sweep_records(n, seed, mate=1, read_len=60):
+    import synth
+    buf = synth.to_fastq(synth.make_reads(n, seed=seed, read_len=read_len, dup_frac=0.3), mate=mate)
+    lines = buf.split(b"\n")[:-1]
+    return [b"\n".join(lines[i:i + 4]) + b"\n" for i in range(0, len(lines), 4)]
+
+
+def _sweep_damage(rec, kind):
+    l = rec.split(b"\n")
+    if kind == "start":
+        l[0] = b"X" + l[0][1:]
+    elif kind == "length":
+        l[3] = l[3][:-3]
+    else:
+        l[1] = l[1][:10] + b"U" + l[1][11:]
+    return b"\n".join(l)
+
+
+@pytest.mark.parametrize("kind", ["start", "length", "base"])
+def test_ref_malformed_record_at_every_position(oracle, tmp_path, kind):
+    """One malformed record at every index, single- and paired-end (either mate): the oracle stops where the reference
+    binary stops and has written the same bytes - including record 0, which the reference writes BEFORE keying it
+    (src/hash_dup_remover.hpp:118-124,216-228), so a bad base there still leaves it in the output."""
+    _need_ref(oracle)
+    r1, r2 = _sweep_records(12, 50, 1), _sweep_records(12, 51, 2, read_len=45)
+    for pos in range(12):
+        bad1 = b"".join(r1[:pos] + [_sweep_damage(r1[pos], kind)] + r1[pos + 1:])
+        bad2 = b"".join(r2[:pos] + [_sweep_damage(r2[pos], kind)] + r2[pos + 1:])
+        good1, good2 = b"".join(r1), b"".join(r2)
+        for k, (b1, b2) in enumerate([(bad1, None), (bad1, good2), (good1, bad2)]):
+            rc, o1, o2, _, _ = oracle.run_ref(tmp_path / f"{pos}_{k}", "fast", oracle.FASTQ, b1, b2)
+            e1, e2, st = oracle.run_oracle("fast", oracle.FASTQ, b1, b2)
+            assert rc == 1 and st.err != 0, (pos, k)
+            assert e1 == o1 and (b2 is None or e2 == o2), (pos, k)
