@@ -200,3 +200,58 @@ def test_malformed_record_in_paired_input_matches_the_reference_binary(tmp_path,
         assert ours.stderr == ref.stderr, pos
         assert (tmp_path / "o1.fq").read_bytes() == (tmp_path / "r1.fq").read_bytes(), pos
         assert (tmp_path / "o2.fq").read_bytes() == (tmp_path / "r2.fq").read_bytes(), pos
+
+
+def test_input_cut_anywhere_in_the_last_record_matches_the_reference_binary(tmp_path, oracle):
+    """The file ends at every byte of its last record (and a little before it), single-end and in either mate of a
+    pair: the binary, the oracle and the reference binary agree on exit status, stderr, -v line and output bytes."""
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/fastq-dupaway not built")
+    r1, r2 = _records(12, seed=33), _records(12, seed=34, mate=2, read_len=70)
+    f1, f2 = b"".join(r1), b"".join(r2)
+    for cut in range(len(f1) - len(r1[-1]) - 2, len(f1) + 1, 3):
+        for paired in (False, True):
+            b1 = f1[:cut]
+            (tmp_path / "a.fq").write_bytes(b1)
+            (tmp_path / "b.fq").write_bytes(f2)
+            io_ref = ["-i", "a.fq", "-o", "r1.fq"] + (["-u", "b.fq", "-p", "r2.fq"] if paired else [])
+            io_our = ["-i", tmp_path / "a.fq", "-o", tmp_path / "o1.fq"] + (["-u", tmp_path / "b.fq", "-p", tmp_path / "o2.fq"] if paired else [])
+            ref = subprocess.run([str(oracle.REF_BIN), *io_ref, "--fast", "-v"], capture_output=True, text=True, cwd=tmp_path)
+            ours = run(*io_our, "--fast", "-v", env={"FQD_BLOCK_BYTES": "4096"})
+            assert (ours.returncode, ours.stdout, ours.stderr) == (ref.returncode, ref.stdout, ref.stderr), (cut, paired)
+            assert (tmp_path / "o1.fq").read_bytes() == (tmp_path / "r1.fq").read_bytes(), (cut, paired)
+            e1, e2, st = oracle.run_oracle("fast", oracle.FASTQ, b1, f2 if paired else None)
+            assert e1 == (tmp_path / "r1.fq").read_bytes() and (st.err != 0) == (ref.returncode != 0)
+            if paired:
+                assert (tmp_path / "o2.fq").read_bytes() == (tmp_path / "r2.fq").read_bytes() == e2, cut
+
+
+@pytest.mark.parametrize("kind", ["start", "base", "empty", "lower"])
+def test_malformed_fasta_record_at_every_position_matches_the_reference_binary(tmp_path, oracle, kind):
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/fastq-dupaway not built")
+    buf = synth.to_fasta(synth.make_reads(30, seed=40, read_len=90, dup_frac=0.3))
+    lines = buf.split(b"\n")[:-1]
+    recs = [b"\n".join(lines[i:i + 2]) + b"\n" for i in range(0, len(lines), 2)]
+
+    def damage(rec):
+        l = rec.split(b"\n")
+        if kind == "start":
+            l[0] = b"@" + l[0][1:]
+        elif kind == "base":
+            l[1] = l[1][:10] + b"U" + l[1][11:]
+        elif kind == "empty":
+            l[1] = b""
+        else:
+            l[1] = l[1].lower()
+        return b"\n".join(l)
+    for pos in range(30):
+        data = b"".join(recs[:pos] + [damage(recs[pos])] + recs[pos + 1:])
+        (tmp_path / "in.fa").write_bytes(data)
+        ref = subprocess.run([str(oracle.REF_BIN), "-i", "in.fa", "-o", "ref.fa", "--fast", "-v", "--format", "fasta"],
+                             capture_output=True, text=True, cwd=tmp_path)
+        ours = run("-i", tmp_path / "in.fa", "-o", tmp_path / "ours.fa", "--fast", "-v", "--format", "fasta", env={"FQD_BLOCK_BYTES": "4096"})
+        assert (ours.returncode, ours.stdout, ours.stderr) == (ref.returncode, ref.stdout, ref.stderr), pos
+        assert (tmp_path / "ours.fa").read_bytes() == (tmp_path / "ref.fa").read_bytes(), pos
+        e1, _, st = oracle.run_oracle("fast", oracle.FASTA, data)
+        assert e1 == (tmp_path / "ref.fa").read_bytes(), pos
