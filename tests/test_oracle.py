@@ -268,3 +268,25 @@ def test_ref_malformed_record_at_every_position(oracle, tmp_path, kind):
             e1, e2, st = oracle.run_oracle("fast", oracle.FASTQ, b1, b2)
             assert rc == 1 and st.err != 0, (pos, k)
             assert e1 == o1 and (b2 is None or e2 == o2), (pos, k)
+
+
+@pytest.mark.parametrize("mode,unordered", [("tight", False), ("loose", False), ("tail-hamming", False), ("fast", True)])
+def test_ref_malformed_record_in_whole_input_modes(oracle, tmp_path, mode, unordered):
+    """Sequence-based modes and --fast --unordered read (and sort) everything before they write anything: a malformed
+    record at any position, in either mate, ends the reference with exit status 1 and the outputs it has (or has not)
+    created by then; the oracle reports an error and the same bytes."""
+    _need_ref(oracle)
+    r1, r2 = _sweep_records(12, 50, 1), _sweep_records(12, 51, 2, read_len=45)
+    good1, good2 = b"".join(r1), b"".join(r2)
+    for kind in ("start", "length", "base"):
+        for pos in range(12):
+            bad1 = b"".join(r1[:pos] + [_sweep_damage(r1[pos], kind)] + r1[pos + 1:])
+            bad2 = b"".join(r2[:pos] + [_sweep_damage(r2[pos], kind)] + r2[pos + 1:])
+            cases = [(bad1, good2), (good1, bad2)] + ([] if unordered else [(bad1, None)])
+            for k, (b1, b2) in enumerate(cases):
+                rc, o1, o2, _, _ = oracle.run_ref(tmp_path / f"{kind}_{pos}_{k}", mode, oracle.FASTQ, b1, b2,
+                                                  stable=not unordered, unordered=unordered)
+                e1, e2, st = oracle.run_oracle(mode, oracle.FASTQ, b1, b2, unordered=unordered) if unordered \
+                    else oracle.run_oracle(mode, oracle.FASTQ, b1, b2)
+                assert (rc != 0) == (st.err != 0), (kind, pos, k)
+                assert e1 == (o1 or b"") and (b2 is None or (e2 or b"") == (o2 or b"")), (kind, pos, k)
