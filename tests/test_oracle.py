@@ -290,3 +290,33 @@ def test_ref_malformed_record_in_whole_input_modes(oracle, tmp_path, mode, unord
                     else oracle.run_oracle(mode, oracle.FASTQ, b1, b2)
                 assert (rc != 0) == (st.err != 0), (kind, pos, k)
                 assert e1 == (o1 or b"") and (b2 is None or (e2 or b"") == (o2 or b"")), (kind, pos, k)
+
+
+def test_ref_unordered_many_tiny_cases(oracle, tmp_path):
+    """300 random tiny --fast --unordered jobs against the reference binary: 0-8 records per file, tags drawn from a
+    handful of values (many duplicate tags, missing mates, an empty tag), ID lines with the dot in different places,
+    no dot, or no space - the cases where the end-of-stream rule of the two-pointer walk decides the output."""
+    import random
+    import shutil
+    _need_ref(oracle)
+    rng = random.Random(7)
+
+    def ident(tag, mate, style):
+        return [f"@R.{tag} {mate}", f"@R.{tag}", f"@{tag} x.{mate}", f"@R{tag}"][style].encode()
+
+    def fastq(items):
+        return b"".join(i + b"\n" + s + b"\n+\n" + b"I" * len(s) + b"\n" for i, s in items)
+    for it in range(300):
+        n1, n2 = rng.randrange(0, 9), rng.randrange(0, 9)
+        style = rng.choice([0, 0, 0, 1, 2, 3])
+        tags = [str(rng.randrange(0, 6)) if rng.random() < 0.7 else rng.choice(["10", "2a", "A", "", "05"]) for _ in range(n1 + n2)]
+        seqs = ["".join(rng.choice("ACGT") for _ in range(rng.choice([4, 4, 5]))).encode() for _ in range(4)]
+        b1 = fastq([(ident(tags[i], 1, style), rng.choice(seqs)) for i in range(n1)])
+        b2 = fastq([(ident(tags[n1 + i], 2, style), rng.choice(seqs)) for i in range(n2)])
+        shutil.rmtree(tmp_path / "w", ignore_errors=True)
+        rc, r1, r2, so, _ = oracle.run_ref(tmp_path / "w", "fast", oracle.FASTQ, b1, b2, unordered=True)
+        o1, o2, st = oracle.run_oracle("fast", oracle.FASTQ, b1, b2, unordered=True)
+        assert (rc != 0) == (st.err != 0), it
+        assert (o1 or b"") == (r1 or b"") and (o2 or b"") == (r2 or b""), it
+        if rc == 0:
+            assert _parse_counts(so)[:3] == [st.total, st.dups, st.unmatched], it
