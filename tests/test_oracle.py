@@ -320,3 +320,40 @@ def test_ref_unordered_many_tiny_cases(oracle, tmp_path):
         assert (o1 or b"") == (r1 or b"") and (o2 or b"") == (r2 or b""), it
         if rc == 0:
             assert _parse_counts(so)[:3] == [st.total, st.dups, st.unmatched], it
+
+
+def test_ref_stable_sequence_modes_many_tiny_cases(oracle, tmp_path):
+    """300 random tiny jobs per run through every --compare-seq mode (distance 0-3, single- and paired-end) against the
+    stable-sort build of the reference: 1-9 records of length 0-6 over {A,C,G,T,N}, made from three base sequences by
+    cutting prefixes and substituting single bases - dense in exactly the relations the comparators look at."""
+    import random
+    import shutil
+    _need_ref(oracle, stable=True)
+    rng = random.Random(11)
+
+    def fastq(seqs, mate):
+        return b"".join(b"@r%d %d\n" % (i, mate) + s + b"\n+\n" + b"I" * len(s) + b"\n" for i, s in enumerate(seqs))
+    for it in range(300):
+        k = rng.randrange(1, 10)
+        base = ["".join(rng.choice("ACGTN" if rng.random() < 0.9 else "AC") for _ in range(rng.choice([0, 1, 2, 3, 3, 4, 4, 5, 6]))).encode()
+                for _ in range(3)]
+
+        def pick():
+            s = rng.choice(base)
+            r = rng.random()
+            if r < 0.3 and s:
+                s = s[:rng.randrange(0, len(s) + 1)]
+            elif r < 0.5 and s:
+                j = rng.randrange(len(s))
+                s = s[:j] + bytes([rng.choice(b"ACGT")]) + s[j + 1:]
+            return s
+        s1 = [pick() for _ in range(k)]
+        paired = rng.random() < 0.5
+        s2 = [pick() for _ in range(k)] if paired else None
+        mode, dist = rng.choice(["tight", "loose", "tail-hamming"]), rng.choice([0, 1, 2, 3])
+        b1, b2 = fastq(s1, 1), (fastq(s2, 2) if paired else None)
+        shutil.rmtree(tmp_path / "w", ignore_errors=True)
+        rc, r1, r2, _, _ = oracle.run_ref(tmp_path / "w", mode, oracle.FASTQ, b1, b2, dist=dist, stable=True)
+        o1, o2, st = oracle.run_oracle(mode, oracle.FASTQ, b1, b2, dist=dist)
+        assert (rc != 0) == (st.err != 0), it
+        assert (o1 or b"") == (r1 or b"") and (not paired or (o2 or b"") == (r2 or b"")), (it, mode, dist)
