@@ -255,3 +255,32 @@ def test_malformed_fasta_record_at_every_position_matches_the_reference_binary(t
         assert (tmp_path / "ours.fa").read_bytes() == (tmp_path / "ref.fa").read_bytes(), pos
         e1, _, st = oracle.run_oracle("fast", oracle.FASTA, data)
         assert e1 == (tmp_path / "ref.fa").read_bytes(), pos
+
+
+def test_two_malformed_records_report_the_one_the_reference_meets_first(tmp_path, oracle):
+    """150 random jobs with TWO malformed records (any kinds, any positions, either mate, small or large blocks): which
+    error is reported, and what has been written by then, follows the reference's order of events - the pre-parse of
+    record k+1 of the left then the right mate comes before pair k is keyed (left mate first)."""
+    import random
+    if not oracle.ref_available():
+        pytest.skip("oracle/_ref/fastq-dupaway not built")
+    rng = random.Random(5)
+    r = [_records(24, seed=31, mate=1), _records(24, seed=32, mate=2, read_len=80)]
+    for it in range(150):
+        paired = rng.random() < 0.6
+        recs = [list(r[0]), list(r[1])]
+        for _ in range(2):
+            m, pos = rng.randrange(2 if paired else 1), rng.randrange(24)
+            recs[m][pos] = _damage(r[m][pos], rng.choice(["start", "length", "base"]))
+        (tmp_path / "a.fq").write_bytes(b"".join(recs[0]))
+        (tmp_path / "b.fq").write_bytes(b"".join(recs[1]))
+        for f in ("r1.fq", "r2.fq", "o1.fq", "o2.fq"):
+            (tmp_path / f).unlink(missing_ok=True)
+        io_ref = ["-i", "a.fq", "-o", "r1.fq"] + (["-u", "b.fq", "-p", "r2.fq"] if paired else [])
+        io_our = ["-i", tmp_path / "a.fq", "-o", tmp_path / "o1.fq"] + (["-u", tmp_path / "b.fq", "-p", tmp_path / "o2.fq"] if paired else [])
+        ref = subprocess.run([str(oracle.REF_BIN), *io_ref, "--fast", "-v"], capture_output=True, text=True, cwd=tmp_path)
+        ours = run(*io_our, "--fast", "-v", env={"FQD_BLOCK_BYTES": rng.choice(["4096", "1048576"])})
+        assert (ours.returncode, ours.stderr) == (ref.returncode, ref.stderr), it
+        assert (tmp_path / "o1.fq").read_bytes() == (tmp_path / "r1.fq").read_bytes(), it
+        if paired:
+            assert (tmp_path / "o2.fq").read_bytes() == (tmp_path / "r2.fq").read_bytes(), it
