@@ -390,6 +390,7 @@ def dedup_fast(b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, chunk_bytes
         n_mates = 2 if paired else 1
         first = True
         adj_total = adj_dups = 0
+        held = None
         st = eng.stats()
         while True:
             chunk = [bufs[m][pos[m]: pos[m] + chunk_bytes] for m in range(n_mates)]
@@ -426,9 +427,22 @@ def dedup_fast(b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, chunk_bytes
                 adj_total -= 1
                 adj_dups -= int(not keep[n - 1])
                 keep[n - 1] = False
+            starts = [_np(res.rec_start[m], n + 1, np.int64) if n else np.zeros(1, np.int64) for m in range(n_mates)]
+            # The lazy pre-parse reaches across chunks: the LAST pair of a chunk is written only once the record after it
+            # has parsed, which may need the next chunk (a sequence / quality length mismatch shows when the record is
+            # complete).  It is held back and written in front of the next chunk's survivors - or dropped if that chunk
+            # opens with a malformed record.
+            stops_here = st.err != 0 or tail_err is not None
+            if held is not None and (n > 0 or stops_here):
+                if not (st.err in (4, 5) and st.err_record == res.first_record):
+                    for m in range(n_mates):
+                        outs[m].append(held[m])
+                held = None
+            if n > 0 and not stops_here and keep[n - 1]:
+                held = [chunk[m][int(starts[m][n - 1]): int(starts[m][n])] for m in range(n_mates)]
+                keep[n - 1] = False
             for m in range(n_mates):
-                starts = _np(res.rec_start[m], n + 1, np.int64) if n else np.zeros(1, np.int64)
-                outs[m].append(_gather_spans(chunk[m], starts, keep))
+                outs[m].append(_gather_spans(chunk[m], starts[m], keep))
                 pos[m] += int(res.consumed[m]) if st.err == 0 else 0
             if tail_err is not None:
                 st.err, st.err_char, st.err_record = 4, tail_err[1], st.total
@@ -443,6 +457,9 @@ def dedup_fast(b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, chunk_bytes
                 break
             if all(pos[m] >= len(bufs[m]) for m in range(n_mates)):
                 break
+        if held is not None:
+            for m in range(n_mates):
+                outs[m].append(held[m])
         if st.err in (0, 4):
             st.total += adj_total
             st.dups += adj_dups
