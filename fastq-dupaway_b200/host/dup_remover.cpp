@@ -113,6 +113,29 @@ double gz_expansion(const std::string& name, const BlockReader& reader) {
     return h > 0 ? std::max(1.0, h * 1.1) : 8.0;
 }
 
+// Record `index` (0-based) of a file, read again from disk: the whole-input modes stream their input to the device and
+// keep nothing, but the reference's message for a sequence / quality length mismatch quotes both strings
+// (src/fastqview.cpp:128-138).  Error path only.
+std::string fetch_record(const std::string& name, uint64_t index, int lpr) {
+    InputFile f(name);
+    std::vector<char> buf(1u << 20);
+    std::string rec;
+    uint64_t lines_to_skip = index * (uint64_t)lpr;
+    int lines_wanted = lpr;
+    while (!f.eof() && lines_wanted > 0) {
+        const size_t n = f.read(buf.data(), buf.size());
+        const char* p = buf.data(); const char* end = p + n;
+        while (p < end && lines_wanted > 0) {
+            const char* nl = (const char*)memchr(p, '\n', end - p);
+            const char* stop = nl ? nl + 1 : end;
+            if (lines_to_skip == 0) rec.append(p, stop);
+            if (nl) { if (lines_to_skip) --lines_to_skip; else --lines_wanted; }
+            p = stop;
+        }
+    }
+    return rec;
+}
+
 // Longest sequence line and mean record size of a sample (first bytes of the first block).
 void sample_geometry(const char* p, size_t n, int lpr, size_t& max_seq, double& avg_rec) {
     max_seq = 0; avg_rec = 0;
@@ -402,6 +425,10 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
         if (st.err == FQD_ERR_UNSUPPORTED_BYTE && !byte_keys) { byte_keys = true; continue; }
         // parse errors surface while the inputs are being sorted, before any output file exists
         // (src/seq_dup_remover.hpp:44-50, src/hash_dup_remover.hpp:160-174)
+        if (st.err == FQD_ERR_LEN_MISMATCH) {
+            const std::string rec = fetch_record(in[st.err_mate == 1 && mates == 2 ? 1 : 0], st.err_record, lpr);
+            throw_data_error(st, fasta, rec.data(), rec.size());
+        }
         if (st.err && st.err != FQD_ERR_BAD_BASE) throw_data_error(st, fasta);
 
         std::vector<std::unique_ptr<OutputFile>> outs;

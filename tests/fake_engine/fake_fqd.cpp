@@ -1,11 +1,14 @@
 // fake_fqd.cpp - TEST DOUBLE of the C ABI (include/fqd.h) for CPU tests of the drop-in binary's HOST logic
 // (tests/test_cli_host_logic.py).  It is not a CPU path of the product: nothing outside tests/ builds, links or loads
-// it, it announces itself on stderr, and it implements only what the ordered --fast driver calls, in the plainest way
-// (newline counting + std::unordered_set of the sequence text).  The engine's real semantics - and everything about
+// it, it announces itself on stderr, and it implements what the drivers call in the plainest way: ordered --fast by
+// newline counting + a std::unordered_set of the sequence text, the whole-input modes (sequence-based, --fast
+// --unordered, cluster files) by handing the collected input to the oracle's C functions (oracle/fqd_oracle.c, linked
+// in - checker code serving a test, never the product).  The engine's real semantics - and everything about
 // speed - are tested on the GPU against the oracle; this file exists so that the code AROUND the engine (readers,
 // rings of blocks, tail carry, paired lock-step, restarts after capacity / row-width estimates, asynchronous writers,
 // gzip in and out, the -v lines) runs in the CPU test-suite through the very same binary.
 //   FAKE_FQD_SHRINK=k   pretend the key store holds cfg.max_records / k records (forces the restart path)
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -15,9 +18,25 @@
 
 #include "../../include/fqd.h"
 
+// the oracle's C interface (oracle/fqd_oracle.c)
+extern "C" {
+typedef struct { uint64_t total, dups, unmatched; int32_t err, err_char; uint64_t err_record; } fqdo_stats;
+int fqdo_seq(const char* buf1, int64_t n1, const char* buf2, int64_t n2, int format, int mode, uint32_t dist,
+             uint64_t* out_idx, uint64_t* n_out, uint64_t* order_out, uint64_t* head_out, fqdo_stats* st);
+int fqdo_fast_pe_unordered(const char* buf1, int64_t n1, const char* buf2, int64_t n2, int format,
+                           uint64_t* out_idx1, uint64_t* out_idx2, uint64_t* n_out, fqdo_stats* st);
+int fqdo_split(const char* buf, int64_t n, int format, int with_id, int64_t* table, uint64_t cap, uint64_t* cnt, fqdo_stats* st);
+}
+
 struct fqd_handle {
     fqd_config cfg;
     fqd_stats_t st;
+    // whole-input modes
+    std::string in[2];
+    bool finished = false;
+    std::string out[2], clusters[2];     // what fqd_emit / fqd_emit_clusters hand out, whole records / lines at a time
+    std::vector<size_t> out_cut[2], cl_cut[2];   // record / line boundaries inside them
+    size_t out_pos[2] = {0, 0}, cl_pos[2] = {0, 0};
     std::unordered_set<std::string> seen;
     std::vector<uint32_t> rec_start[2];
     std::vector<uint8_t> dup;
@@ -134,10 +153,107 @@ int fqd_push(fqd_handle* h, const char* r1, size_t n1, const char* r2, size_t n2
     return FQD_OK;
 }
 
-// whole-input modes: not in the fake
-int fqd_append(fqd_handle* h, int, const char*, size_t) { if (h) h->err = "the fake knows ordered --fast only"; return FQD_ERR_INVALID; }
-int fqd_finish(fqd_handle* h) { if (h) h->err = "the fake knows ordered --fast only"; return FQD_ERR_INVALID; }
-int fqd_emit(fqd_handle*, int, void*, size_t, size_t*, int*) { return FQD_ERR_INVALID; }
-int fqd_emit_clusters(fqd_handle*, int, void*, size_t, size_t*, int*) { return FQD_ERR_INVALID; }
+// ---- whole-input modes: collect, then let the oracle decide ---------------------------------------------------------
+int fqd_append(fqd_handle* h, int mate, const char* buf, size_t n) {
+    if (!h || mate < 0 || mate > 1 || h->finished) return FQD_ERR_INVALID;
+    if (h->cfg.mode == FQD_MODE_FAST && !h->cfg.unordered) { h->err = "fqd_append is for the whole-input modes"; return FQD_ERR_INVALID; }
+    h->in[mate].append(buf, n);
+    return FQD_OK;
+}
+
+static int map_err(int e) { static const int m[6] = {0, FQD_ERR_EMPTY, FQD_ERR_BAD_START, FQD_ERR_LEN_MISMATCH, FQD_ERR_BAD_BASE, FQD_ERR_CUDA}; return e >= 0 && e < 6 ? m[e] : FQD_ERR_CUDA; }
+
+int fqd_finish(fqd_handle* h) {
+    if (!h || h->finished) return FQD_ERR_INVALID;
+    h->finished = true;
+    const int mates = h->cfg.paired ? 2 : 1;
+    const int fmt = h->cfg.format;
+    const bool unordered = h->cfg.unordered != 0;
+    // record tables (as far as the input parses)
+    std::vector<int64_t> table[2]; uint64_t cnt[2] = {0, 0};
+    int parse_err_mate = -1; uint64_t parse_err_record = 0;      // the oracle's statistics do not say which file
+    for (int m = 0; m < mates; ++m) {
+        const uint64_t cap = (uint64_t)std::count(h->in[m].begin(), h->in[m].end(), '\n') / 2 + 2;
+        table[m].assign(cap * 7, 0);
+        fqdo_stats ps;
+        fqdo_split(h->in[m].data(), (int64_t)h->in[m].size(), fmt, unordered ? 1 : 0, table[m].data(), cap, &cnt[m], &ps);
+        if (ps.err && parse_err_mate < 0) { parse_err_mate = m; parse_err_record = ps.err_record; }
+    }
+    // the limits a real engine is created with: the host starts over with larger ones
+    for (int m = 0; m < mates; ++m) {
+        if (cnt[m] > h->capacity) { h->st.err = FQD_ERR_CAPACITY; return FQD_OK; }
+        for (uint64_t i = 0; i < cnt[m]; ++i) {
+            const int64_t* t = &table[m][7 * i];
+            if ((uint64_t)(t[2] - 1) > h->cfg.max_seq_len) { h->st.err = FQD_ERR_SEQ_TOO_LONG; return FQD_OK; }
+            if (unordered && (uint64_t)t[6] > (h->cfg.max_tag_len ? h->cfg.max_tag_len : 32u)) { h->st.err = FQD_ERR_TAG_TOO_LONG; return FQD_OK; }
+            if (!unordered && !h->cfg.byte_keys) {
+                const char* q = h->in[m].data() + t[0] + t[1];
+                for (int64_t k = 0; k + 1 < t[2]; ++k)
+                    if (!std::strchr("ACGTN", q[k]) || q[k] == 0) { h->st.err = FQD_ERR_UNSUPPORTED_BYTE; h->st.err_char = (unsigned char)q[k]; return FQD_OK; }
+            }
+        }
+    }
+    const uint64_t cap = std::max(cnt[0], cnt[1]) + 2;
+    std::vector<uint64_t> o1(cap), o2(cap), order(cap), head(cap);
+    uint64_t n_out = 0; fqdo_stats st;
+    if (unordered) {
+        fqdo_fast_pe_unordered(h->in[0].data(), (int64_t)h->in[0].size(), h->in[1].data(), (int64_t)h->in[1].size(), fmt,
+                               o1.data(), o2.data(), &n_out, &st);
+    } else {
+        fqdo_seq(h->in[0].data(), (int64_t)h->in[0].size(), mates == 2 ? h->in[1].data() : nullptr,
+                 mates == 2 ? (int64_t)h->in[1].size() : 0, fmt, h->cfg.mode, h->cfg.hamming_dist,
+                 o1.data(), &n_out, order.data(), head.data(), &st);
+        o2 = o1;
+    }
+    h->st.total = st.total; h->st.dups = st.dups; h->st.unmatched = st.unmatched;
+    h->st.err = map_err(st.err); h->st.err_char = st.err_char; h->st.err_record = st.err_record;
+    if ((h->st.err == FQD_ERR_BAD_START || h->st.err == FQD_ERR_LEN_MISMATCH) && parse_err_mate >= 0) {
+        h->st.err_mate = parse_err_mate; h->st.err_record = parse_err_record;      // index of the malformed record in its file
+    }
+    auto span = [&](int m, uint64_t i, size_t& off, size_t& len) {
+        const int64_t* t = &table[m][7 * i];
+        off = (size_t)t[0]; len = (size_t)(t[1] + t[2] + t[3] + t[4]);
+    };
+    for (int m = 0; m < mates; ++m) {
+        const std::vector<uint64_t>& idx = m == 0 ? o1 : o2;
+        h->out_cut[m].assign(1, 0);
+        for (uint64_t k = 0; k < n_out; ++k) {
+            size_t off, len; span(m, idx[k], off, len);
+            h->out[m].append(h->in[m], off, len);
+            h->out_cut[m].push_back(h->out[m].size());
+        }
+        h->cl_cut[m].assign(1, 0);
+        if (!unordered && !h->st.err) {
+            std::unordered_set<uint64_t> written(o1.begin(), o1.begin() + (ptrdiff_t)n_out);
+            for (uint64_t p = 0; p < st.total; ++p) {
+                const int64_t* t = &table[m][7 * order[p]];
+                if (!written.count(order[p])) h->clusters[m] += "--";
+                h->clusters[m].append(h->in[m], (size_t)t[0], (size_t)t[1]);
+                h->cl_cut[m].push_back(h->clusters[m].size());
+            }
+        }
+    }
+    return FQD_OK;
+}
+
+static int stream_out(const std::string& data, const std::vector<size_t>& cut, size_t& pos, void* dst, size_t cap, size_t* n_bytes, int* done) {
+    // whole units (records / lines), as many as fit
+    size_t a = pos, b = pos;
+    while (b + 1 < cut.size() && cut[b + 1] - cut[a] <= cap) ++b;
+    if (b == a && a + 1 < cut.size()) return FQD_ERR_INVALID;           // cap smaller than one unit
+    *n_bytes = cut.empty() ? 0 : cut[b] - cut[a];
+    if (*n_bytes) std::memcpy(dst, data.data() + cut[a], *n_bytes);
+    pos = b;
+    *done = b + 1 >= cut.size();
+    return FQD_OK;
+}
+int fqd_emit(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, int* done) {
+    if (!h || !h->finished || mate < 0 || mate > 1) return FQD_ERR_INVALID;
+    return stream_out(h->out[mate], h->out_cut[mate], h->out_pos[mate], dst, cap, n_bytes, done);
+}
+int fqd_emit_clusters(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, int* done) {
+    if (!h || !h->finished || mate < 0 || mate > 1) return FQD_ERR_INVALID;
+    return stream_out(h->clusters[mate], h->cl_cut[mate], h->cl_pos[mate], dst, cap, n_bytes, done);
+}
 
 }  // extern "C"

@@ -3,7 +3,7 @@ tail) on the CPU: the binding is pointed at the test double of the C ABI (tests/
 and its output compared with the oracle - well-formed input at many chunk sizes, and one malformed record at every
 position.  On the GPU the same Python code runs over the real library (tests/test_fast_gpu.py)."""
 import ctypes as C
-import subprocess
+import sys
 from pathlib import Path
 
 import pytest
@@ -11,16 +11,13 @@ import pytest
 import synth
 
 ROOT = Path(__file__).resolve().parent.parent
-FAKE_SRC = ROOT / "tests" / "fake_engine" / "fake_fqd.cpp"
-FAKE_DIR = ROOT / "tests" / "fake_engine" / "_build"
+sys.path.insert(0, str(ROOT / "tests" / "fake_engine"))
+from build import build_fake  # noqa: E402
 
 
 @pytest.fixture()
 def fake_binding(fqd, monkeypatch):
-    FAKE_DIR.mkdir(exist_ok=True)
-    so = FAKE_DIR / "libfqd_cuda.so"
-    subprocess.run(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-o", str(so), str(FAKE_SRC)], check=True)
-    lib = C.CDLL(str(so))
+    lib = C.CDLL(str(build_fake()))
     vp, sz = C.c_void_p, C.c_size_t
     lib.fqd_create.argtypes = [C.POINTER(fqd.Config), C.POINTER(vp)]
     lib.fqd_destroy.argtypes = [vp]

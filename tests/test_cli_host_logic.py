@@ -9,6 +9,7 @@ GPU (tests/test_cli_gpu.py); the product has no CPU path: tests/test_abi.py chec
 import gzip
 import os
 import subprocess
+import sys
 from pathlib import Path
 
 import pytest
@@ -18,14 +19,13 @@ from test_host_io import SMALL, bgzf, deflate_gz, members
 
 ROOT = Path(__file__).resolve().parent.parent
 EXE = ROOT / "fastq-dupaway_b200" / "host" / "fastq-dupaway"
-FAKE_SRC = ROOT / "tests" / "fake_engine" / "fake_fqd.cpp"
-FAKE_DIR = ROOT / "tests" / "fake_engine" / "_build"
+sys.path.insert(0, str(ROOT / "tests" / "fake_engine"))
+from build import BUILD as FAKE_DIR, build_fake  # noqa: E402
 
 
 @pytest.fixture(scope="module", autouse=True)
 def fake_engine():
-    FAKE_DIR.mkdir(exist_ok=True)
-    subprocess.run(["g++", "-std=c++17", "-O2", "-shared", "-fPIC", "-o", str(FAKE_DIR / "libfqd_cuda.so"), str(FAKE_SRC)], check=True)
+    build_fake()
     # the host binary needs the real library only to LINK; build it if the tree is fresh
     if not EXE.exists():
         subprocess.run(["make", "-s", "-C", str(EXE.parent)], check=True)
