@@ -152,3 +152,44 @@ def test_malformed_record_in_whole_input_modes_matches_the_reference_binary(tmp_
                     assert (work / mine).exists() == (work / theirs).exists(), where
                     if (work / mine).exists():
                         assert (work / mine).read_bytes() == (work / theirs).read_bytes(), where
+
+
+def test_odd_inputs_in_every_mode_match_the_reference_binaries(tmp_path, oracle):
+    """Files of different length, an empty mate, an empty file, one record, no final newline, a blank line at the end,
+    FASTA pairs - through tight, loose and --fast [--unordered]: exit status, stdout, stderr, which outputs exist and
+    their bytes are the reference binaries'."""
+    import shutil
+    if not oracle.ref_available(stable=True):
+        pytest.skip("oracle/_ref not built")
+    s1, s2 = synth.make_pair(60, seed=80, read_len=40, dup_frac=0.4)
+    cases = {
+        "pe_r2_shorter": (synth.to_fastq(s1, mate=1), synth.to_fastq(s2[:45], mate=2), "fastq"),
+        "pe_r1_shorter": (synth.to_fastq(s1[:45], mate=1), synth.to_fastq(s2, mate=2), "fastq"),
+        "pe_r2_empty": (synth.to_fastq(s1, mate=1), b"", "fastq"),
+        "se_empty": (b"", None, "fastq"),
+        "fasta_pe": (synth.to_fasta(s1, mate=1), synth.to_fasta(s2, mate=2), "fasta"),
+        "se_one_record": (synth.to_fastq(s1[:1]), None, "fastq"),
+        "se_no_final_newline": (synth.to_fastq(s1)[:-1], None, "fastq"),
+        "se_blank_line_end": (synth.to_fastq(s1) + b"\n", None, "fastq"),
+    }
+    for name, (b1, b2, fmt) in cases.items():
+        for flags in (["--compare-seq", "tight"], ["--compare-seq", "loose"], ["--fast"] + (["--unordered"] if b2 is not None else [])):
+            d = tmp_path / name
+            shutil.rmtree(d, ignore_errors=True)
+            d.mkdir()
+            (d / "a").write_bytes(b1)
+            io_r, io_o = ["-i", "a", "-o", "r1"], ["-i", d / "a", "-o", d / "o1"]
+            if b2 is not None:
+                (d / "b").write_bytes(b2)
+                io_r += ["-u", "b", "-p", "r2"]
+                io_o += ["-u", d / "b", "-p", d / "o2"]
+            common = ["-v", "--format", fmt, *flags]
+            ref_bin = oracle.REF_STABLE_BIN if flags[0] == "--compare-seq" else oracle.REF_BIN
+            ref = subprocess.run([str(ref_bin), *io_r, *common], capture_output=True, text=True, cwd=d)
+            ours = run(*io_o, *common, env={"FQD_BLOCK_BYTES": "4096"})
+            where = (name, flags)
+            assert (ours.returncode, ours.stdout, ours.stderr) == (ref.returncode, ref.stdout, ref.stderr), where
+            for mine, theirs in (("o1", "r1"), ("o2", "r2")):
+                assert (d / mine).exists() == (d / theirs).exists(), where
+                if (d / mine).exists():
+                    assert (d / mine).read_bytes() == (d / theirs).read_bytes(), where
