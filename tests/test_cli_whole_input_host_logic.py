@@ -193,3 +193,17 @@ def test_odd_inputs_in_every_mode_match_the_reference_binaries(tmp_path, oracle)
                 assert (d / mine).exists() == (d / theirs).exists(), where
                 if (d / mine).exists():
                     assert (d / mine).read_bytes() == (d / theirs).read_bytes(), where
+
+
+def test_the_references_own_test_suite_passes_against_the_binary(tmp_path):
+    """`pytest <reference>/test`, unchanged, from the directory of the drop-in binary (it looks for ./fastq-dupaway):
+    its 14 tests (help, fast SE/PE, every sequence-based mode, unordered) pass.  Only where the reference tree is
+    mounted; the same fixtures run against the real engine in tests/test_cli_gpu.py."""
+    ref_tests = Path("/root/reference/test")
+    if not ref_tests.is_dir():
+        pytest.skip("reference tree not present")
+    e = dict(os.environ, LD_LIBRARY_PATH=str(FAKE_DIR), FQD_IO_THREADS="4")
+    p = subprocess.run([sys.executable, "-m", "pytest", str(ref_tests), "-q", "-p", "no:cacheprovider"], capture_output=True, text=True,
+                       cwd=EXE.parent, env=e, timeout=600)
+    assert p.returncode == 0, p.stdout[-2000:]
+    assert " passed" in p.stdout and "failed" not in p.stdout
