@@ -307,11 +307,12 @@ public:
         const int parts = (int)std::min<size_t>(std::min(io_threads(), 16), total / (2u << 20));
         const size_t per = (total + parts - 1) / parts;
         struct Join { std::mutex mu; std::condition_variable cv; int left; };
-        Join join; join.left = parts;
+        auto join = std::make_shared<Join>();      // shared: a worker may still be inside notify when the waiter returns
+        join->left = parts;
         const int fd = m_fd; const size_t file_off = m_off;
         for (int k = 0; k < parts; ++k) {
             const size_t lo = std::min(total, per * k), hi = std::min(total, per * (k + 1));
-            auto work = [=, &join] {
+            auto work = [=] {
                 // first run that reaches beyond lo
                 size_t a = 0, b = n_runs;
                 while (a < b) { size_t m = (a + b) / 2; if (runs[m].out_off + runs[m].len <= lo) a = m + 1; else b = m; }
@@ -333,12 +334,12 @@ public:
                     pos += k2;
                 }
                 if (!buf.empty()) pwrite_all(fd, buf.data(), buf.size(), file_off + buf_at);
-                { std::lock_guard<std::mutex> g(join.mu); --join.left; }
-                join.cv.notify_all();
+                { std::lock_guard<std::mutex> g(join->mu); --join->left; }
+                join->cv.notify_all();
             };
             if (k + 1 < parts) WorkerPool::shared().submit(work); else work();
         }
-        { std::unique_lock<std::mutex> g(join.mu); join.cv.wait(g, [&] { return join.left == 0; }); }
+        { std::unique_lock<std::mutex> g(join->mu); join->cv.wait(g, [&] { return join->left == 0; }); }
         m_off += total;
     }
     void close() {
