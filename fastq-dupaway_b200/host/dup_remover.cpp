@@ -404,6 +404,7 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
         int rc = fqd_create(&cfg, &hraw);
         if (rc) throw_engine_error(nullptr, rc);
         eng.reset(hraw);
+        trace("engine created");
 
         // ship every block to the device (the sort/join needs the whole input; nothing is kept on the host)
         for (int m = 0; m < mates; ++m) {
@@ -415,8 +416,10 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
                 b = readers[m]->next();
             }
         }
+        trace("input on the device");
         rc = fqd_finish(eng.get());
         if (rc) throw_engine_error(eng.get(), rc);
+        trace("sorted / joined / scanned");
         fqd_stats_t st;
         fqd_stats(eng.get(), &st);
         if (st.err == FQD_ERR_SEQ_TOO_LONG) { ++seq_growth; continue; }
@@ -473,6 +476,7 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
                 }
             }
         }
+        trace("outputs closed");
         if (st.err == FQD_ERR_BAD_BASE) throw_data_error(st, fasta);     // --unordered: raised while pairs are keyed
         if (verbose) {
             if (unordered) {
