@@ -207,3 +207,44 @@ def test_the_references_own_test_suite_passes_against_the_binary(tmp_path):
                        cwd=EXE.parent, env=e, timeout=600)
     assert p.returncode == 0, p.stdout[-2000:]
     assert " passed" in p.stdout and "failed" not in p.stdout
+
+
+def test_unusual_files_in_every_mode_match_the_reference_binaries(tmp_path, oracle):
+    """CRLF line ends, multi-line FASTA, the wrong --format, tabs and '@' where they do not belong, empty sequence lines,
+    '+' lines that repeat the ID, binary garbage, a file of newlines - through --fast and every --compare-seq mode:
+    exit status, stdout, stderr, whether an output exists and its bytes are the reference binaries'."""
+    import shutil
+    if not oracle.ref_available(stable=True):
+        pytest.skip("oracle/_ref not built")
+    s1 = synth.make_reads(40, seed=90, read_len=30, dup_frac=0.4)
+    fq, fa = synth.to_fastq(s1), synth.to_fasta(s1)
+    cases = {
+        "crlf_fastq": (fq.replace(b"\n", b"\r\n"), "fastq"),
+        "crlf_fasta": (fa.replace(b"\n", b"\r\n"), "fasta"),
+        "multiline_fasta": (b"".join(b">r%d\n" % i + s[:15] + b"\n" + s[15:] + b"\n" for i, s in enumerate(s1)), "fasta"),
+        "fastq_as_fasta": (fq, "fasta"),
+        "fasta_as_fastq": (fa, "fastq"),
+        "tabs_in_seq": (fq.replace(b"A", b"\t", 3), "fastq"),
+        "empty_seq_lines": (b"@a\n\n+\n\n@b\n\n+\n\n@c\nA\n+\nI\n", "fastq"),
+        "plus_with_id": (b"".join(b"@r%d\n" % i + s + b"\n+r%d\n" % i + b"I" * len(s) + b"\n" for i, s in enumerate(s1)), "fastq"),
+        "binary_garbage": (bytes(range(256)) * 20, "fastq"),
+        "only_newlines": (b"\n" * 50, "fastq"),
+        "at_in_quality": (b"".join(b"@r%d\n" % i + s + b"\n+\n" + b"@" * len(s) + b"\n" for i, s in enumerate(s1)), "fastq"),
+    }
+    env = dict(os.environ, LD_LIBRARY_PATH=str(FAKE_DIR), FQD_IO_THREADS="4", FQD_BLOCK_BYTES="4096")
+    for name, (data, fmt) in cases.items():
+        for flags in (["--fast"], ["--compare-seq", "tight"], ["--compare-seq", "loose"], ["--compare-seq", "tail-hamming"]):
+            d = tmp_path / name
+            shutil.rmtree(d, ignore_errors=True)
+            d.mkdir()
+            (d / "a").write_bytes(data)
+            common = ["-v", "--format", fmt, *flags]
+            ref_bin = oracle.REF_STABLE_BIN if flags[0] == "--compare-seq" else oracle.REF_BIN
+            ref = subprocess.run([str(ref_bin), "-i", "a", "-o", "r1", *common], capture_output=True, cwd=d)
+            ours = subprocess.run([str(EXE), "-i", "a", "-o", "o1", *common], capture_output=True, cwd=d, env=env)
+            ours_err = b"".join(l for l in ours.stderr.splitlines(keepends=True) if not l.startswith(b"[fake_fqd]"))
+            where = (name, flags)
+            assert (ours.returncode, ours.stdout, ours_err) == (ref.returncode, ref.stdout, ref.stderr), where
+            assert (d / "o1").exists() == (d / "r1").exists(), where
+            if (d / "o1").exists():
+                assert (d / "o1").read_bytes() == (d / "r1").read_bytes(), where
