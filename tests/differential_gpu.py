@@ -1,0 +1,78 @@
+"""NOT collected by default (the file name does not match test_*.py): the CPU differential suites of
+test_cli_host_logic.py / test_cli_whole_input_host_logic.py once more, but with the REAL libfqd_cuda.so behind the
+binary - i.e. the engine itself against the reference binaries (oracle/_ref travels to the GPU box) on malformed records
+at every position, input cut anywhere in the last record, double faults, odd and unusual files, in every mode.
+
+    python -m pytest tests/differential_gpu.py -q          # on a GPU box
+
+Written at the end of round 1, when the GPU budget was spent: the host logic around the engine has passed all of this
+over the test double; whether the engine agrees in every one of these corners is the first thing to run in round 2.
+"""
+import importlib
+import os
+import subprocess
+
+import pytest
+
+import test_cli_host_logic as fast_suite
+import test_cli_whole_input_host_logic as whole_suite
+
+pytestmark = pytest.mark.gpu
+
+
+def _real_run(*args, env=None):
+    e = dict(os.environ, FQD_IO_THREADS="4")
+    e.pop("LD_LIBRARY_PATH", None)
+    e.update(env or {})
+    return subprocess.run([str(fast_suite.EXE), *map(str, args)], capture_output=True, text=True, env=e, timeout=600)
+
+
+@pytest.fixture(autouse=True)
+def real_engine(monkeypatch):
+    """Point both suites at the product library: their run() helpers stop preloading the test double."""
+    monkeypatch.setattr(fast_suite, "run", _real_run)
+    monkeypatch.setattr(whole_suite, "run", _real_run)
+    monkeypatch.setattr(whole_suite, "FAKE_DIR", "/nonexistent")      # the two tests that build their own environment
+
+
+@pytest.mark.parametrize("kind", ["start", "length", "base"])
+def test_fast_malformed_record_everywhere(tmp_path, oracle, kind):
+    fast_suite.test_malformed_record_at_every_position_matches_the_reference_binary(tmp_path, oracle, kind)
+
+
+@pytest.mark.parametrize("kind", ["start", "length", "base"])
+@pytest.mark.parametrize("bad_mate", [0, 1])
+def test_fast_malformed_record_paired(tmp_path, oracle, kind, bad_mate):
+    fast_suite.test_malformed_record_in_paired_input_matches_the_reference_binary(tmp_path, oracle, kind, bad_mate)
+
+
+def test_fast_input_cut_anywhere(tmp_path, oracle):
+    fast_suite.test_input_cut_anywhere_in_the_last_record_matches_the_reference_binary(tmp_path, oracle)
+
+
+def test_fast_double_faults(tmp_path, oracle):
+    fast_suite.test_two_malformed_records_report_the_one_the_reference_meets_first(tmp_path, oracle)
+
+
+@pytest.mark.parametrize("kind", ["start", "base", "empty", "lower"])
+def test_fast_malformed_fasta(tmp_path, oracle, kind):
+    fast_suite.test_malformed_fasta_record_at_every_position_matches_the_reference_binary(tmp_path, oracle, kind)
+
+
+@pytest.mark.parametrize("mode,dist", whole_suite.MODES)
+@pytest.mark.parametrize("paired", [False, True])
+def test_sequence_modes(tmp_path, oracle, mode, dist, paired):
+    whole_suite.test_sequence_modes_against_oracle_and_stable_reference(tmp_path, oracle, mode, dist, paired)
+
+
+@pytest.mark.parametrize("mode,unordered", [("tight", False), ("tail-hamming", False), ("fast", True)])
+def test_whole_input_malformed(tmp_path, oracle, mode, unordered):
+    whole_suite.test_malformed_record_in_whole_input_modes_matches_the_reference_binary(tmp_path, oracle, mode, unordered)
+
+
+def test_odd_inputs(tmp_path, oracle):
+    whole_suite.test_odd_inputs_in_every_mode_match_the_reference_binaries(tmp_path, oracle)
+
+
+def test_unusual_files(tmp_path, oracle):
+    whole_suite.test_unusual_files_in_every_mode_match_the_reference_binaries(tmp_path, oracle)
