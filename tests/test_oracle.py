@@ -357,3 +357,41 @@ def test_ref_stable_sequence_modes_many_tiny_cases(oracle, tmp_path):
         o1, o2, st = oracle.run_oracle(mode, oracle.FASTQ, b1, b2, dist=dist)
         assert (rc != 0) == (st.err != 0), it
         assert (o1 or b"") == (r1 or b"") and (not paired or (o2 or b"") == (r2 or b"")), (it, mode, dist)
+
+
+def test_ref_stable_cluster_files_many_tiny_cases(oracle, tmp_path):
+    """150 tiny random jobs with --write-clusters in every --compare-seq mode: the text of <out>.clusters (both files in
+    paired mode) equals what the stable-sort build of the reference writes."""
+    import random
+    import shutil
+    _need_ref(oracle, stable=True)
+    rng = random.Random(21)
+
+    def fastq(seqs, mate):
+        return b"".join(b"@r%d.%d %d\n" % (i, rng.randrange(9), mate) + s + b"\n+\n" + b"I" * len(s) + b"\n" for i, s in enumerate(seqs))
+    for it in range(150):
+        k = rng.randrange(1, 10)
+        base = ["".join(rng.choice("ACGTN") for _ in range(rng.choice([1, 2, 3, 4, 5, 6]))).encode() for _ in range(3)]
+
+        def pick():
+            s = rng.choice(base)
+            r = rng.random()
+            if r < 0.3:
+                s = s[:rng.randrange(1, len(s) + 1)]
+            elif r < 0.5:
+                j = rng.randrange(len(s))
+                s = s[:j] + bytes([rng.choice(b"ACGT")]) + s[j + 1:]
+            return s
+        s1 = [pick() for _ in range(k)]
+        paired = rng.random() < 0.5
+        s2 = [pick() for _ in range(k)] if paired else None
+        mode, dist = rng.choice(["tight", "loose", "tail-hamming"]), rng.choice([0, 1, 2])
+        b1, b2 = fastq(s1, 1), (fastq(s2, 2) if paired else None)
+        work = tmp_path / "w"
+        shutil.rmtree(work, ignore_errors=True)
+        rc, _, _, _, _ = oracle.run_ref(work, mode, oracle.FASTQ, b1, b2, dist=dist, stable=True, extra=["--write-clusters"])
+        cl, _ = oracle.cluster_text(mode, oracle.FASTQ, b1, b2, dist=dist)
+        assert rc == 0
+        assert (work / "out_1.fq.clusters").read_bytes() == cl[0], (it, mode, dist)
+        if paired:
+            assert (work / "out_2.fq.clusters").read_bytes() == cl[1], (it, mode, dist)
