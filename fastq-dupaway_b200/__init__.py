@@ -18,7 +18,9 @@ import numpy as np
 
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
-LIB_PATH = CSRC / "libfqd_cuda.so"
+import os as _os
+# FQD_LIB: an experiment build of the same library (csrc/Makefile `variants`); never a different implementation
+LIB_PATH = Path(_os.environ["FQD_LIB"]).resolve() if _os.environ.get("FQD_LIB") else CSRC / "libfqd_cuda.so"
 HEADER = HERE.parent / "include" / "fqd.h"
 
 FQD_ABI_VERSION = 1

@@ -28,9 +28,13 @@ struct ChunkCtl {
     u32 consumed;          // bytes covered by those records
     u64 err_parse;         // min over records of (record << 16 | code << 8 | char); ~0 = none
     u64 err_base;          // min over records of (record << 32 | pos << 8 | char);  ~0 = none
-    u32 too_long;          // a sequence exceeded the key row
-    u32 pad;
+    u32 too_long;          // bit mask (atomicOr): TL_SEQ a sequence exceeded the key row, TL_CAPACITY a record beyond the
+                           // key store / record tables, TL_TAG an ID tag longer than the tag rows
+    u32 pad;               // 1: byte outside {A,C,G,T,N} in a mode that accepts any byte; 2: byte below '\n' (byte keys)
+    u32 too_long_rec;      // smallest chunk-local index of a record with TL_SEQ (~0 = none)
+    u32 pad2;
 };
+enum { TL_SEQ = 1, TL_CAPACITY = 2, TL_TAG = 4 };
 
 // Persistent per-handle device state.
 struct RunState {
@@ -40,7 +44,13 @@ struct RunState {
     u32 capacity_exceeded; // key store or table overflow
     u32 chunk_pairs;       // pairs in the chunk being processed (min over mates)
     u32 chunk_dups;
-    u32 pad;
+    u32 chunk_wanted;      // capacity_exceeded: pairs the refused chunk holds
+    // first chunk that raised a data error, kept across chunks for callers that do not read every chunk's control
+    // block back (fqd_push_device_async): the mates' error words as K1 left them, and where the chunk began
+    u32 sticky_set, sticky_pairs;
+    u64 sticky_first;
+    u64 sticky_parse[2], sticky_base[2];
+    u32 sticky_too_long[2], sticky_too_long_rec[2];
 };
 
 constexpr u64 NO_ERR = ~0ull;
@@ -96,6 +106,11 @@ __device__ __forceinline__ void mbar_wait(u64* bar, u32 parity) {
 __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u32 bytes, u64* bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                  ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// HBM -> L2 only (no shared-memory destination): bytes a later CTA will stage
+__device__ __forceinline__ void bulk_prefetch_l2(const void* src_gmem, u32 bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src_gmem), "r"(bytes) : "memory");
 }
 
 __device__ __forceinline__ u64 ld_volatile_u64(const u64* p) {

@@ -79,6 +79,7 @@ struct fqd_handle {
     u64* d_recv_hash = nullptr;      // [cap_recv]
     u64 recv_cap = 0;
     u64 shard_last_n = 0;
+    u32 grows = 0;                   // times the key store / table were grown in place
 };
 
 #define CUDA_TRY(h, call)                                                                      \
@@ -150,6 +151,7 @@ extern "C" int fqd_peer_copy_async(int device, void* d_dst, const void* d_src, s
     return cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDefault, (cudaStream_t)cuda_stream) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
 }
 
+static void table_geometry(u64 capacity, u64* n_buckets, u32* shift);
 static u32 words_for(u32 max_seq_len, bool byte_keys = false) {
     u32 w = byte_keys ? (max_seq_len + 1 + 7) / 8 : (max_seq_len + BASES_PER_WORD - 1) / BASES_PER_WORD;
     if (w < 2) w = 2;
@@ -222,11 +224,9 @@ static int create_impl(const fqd_config* cfg, fqd_handle* h) {
         if (cfg->max_records == 0) return fail(h, FQD_ERR_INVALID, "max_records must be > 0");
         h->key_capacity = cfg->max_records;
         CUDA_TRY(h, cudaMalloc(&h->d_keys, h->key_capacity * h->row_words * sizeof(u64)));
-        u64 nb = 1024;
-        while (nb * 2 < h->key_capacity) nb <<= 1;        // 4*nb entries >= 2*capacity  (load factor <= 0.5)
+        u64 nb;
+        table_geometry(h->key_capacity, &nb, &h->bucket_shift);
         h->n_buckets = nb;
-        u32 lg = 0; while ((1ull << lg) < nb) ++lg;
-        h->bucket_shift = 64 - lg;
         CUDA_TRY(h, cudaMalloc(&h->d_table, nb * 4 * sizeof(u64)));
         CUDA_TRY(h, cudaMemsetAsync(h->d_table, 0xFF, nb * 4 * sizeof(u64), h->stream));
         for (int m = 0; m < mates; ++m) {
@@ -306,10 +306,10 @@ static int enqueue_fast_chunk(fqd_handle* h, const void* d_r1, size_t n1, const 
     k_chunk_begin<<<1, 1, 0, h->stream>>>(ip);
     cudaEvent_t ie0 = nullptr, ie1 = nullptr;
     if (h->profile) { ie0 = get_event(h); ie1 = get_event(h); cudaEventRecord(ie0, h->stream); }
-    k_insert<<<h->sm_count * 8, HS_THREADS, 0, h->stream>>>(ip);
+    insert_launch(ip, h->sm_count * 8, h->stream);
     if (h->profile) { cudaEventRecord(ie1, h->stream); h->prof_insert.emplace_back(ie0, ie1); h->prof.insert_launches++; }
     k_count_dups<<<h->sm_count * 2, HS_THREADS, 0, h->stream>>>(h->d_dup, h->d_run);
-    k_chunk_end<<<1, 1, 0, h->stream>>>(h->d_run);
+    k_chunk_end<<<1, 1, 0, h->stream>>>(h->d_run, h->mate[0].d_ctl, paired ? h->mate[1].d_ctl : nullptr);
     h->launches += 4;
     CUDA_TRY(h, cudaEventRecord(e1, h->stream));
     h->pending_events.emplace_back(e0, e1);
@@ -350,6 +350,7 @@ static int fold_chunk(fqd_handle* h, u64 first_record, u64* n_ok) {
     if (h->stats.err) { *n_ok = 0; return h->stats.err; }
     long long best_t = -1; int best_code = 0, best_char = 0, best_mate = 0; u64 best_rec = 0, best_ok = 0;
     bool have = false;
+    u64 first_too_long = ~0ull;      // chunk-local index of the first record whose sequence does not fit the key rows
     for (int m = 0; m < mates; ++m) {
         const ChunkCtl& c = *h->mate[m].h_ctl;
         if (c.err_parse != NO_ERR) {
@@ -372,7 +373,12 @@ static int fold_chunk(fqd_handle* h, u64 first_record, u64* n_ok) {
                 }
             }
         }
-        if (c.too_long == 1 && !have) { have = true; best_t = 1ll << 60; best_code = FQD_ERR_SEQ_TOO_LONG; best_ok = 0; }
+        if ((c.too_long & TL_SEQ) && c.too_long_rec < pairs) first_too_long = std::min<u64>(first_too_long, c.too_long_rec);
+    }
+    // A record that is too long for the key rows was not packed: flags at and after it are not valid.  The job must be run
+    // again with wider rows unless the reference would have stopped BEFORE that record anyway.
+    if (first_too_long != ~0ull && (!have || first_too_long <= best_rec - first_record)) {
+        have = true; best_code = FQD_ERR_SEQ_TOO_LONG; best_char = 0; best_rec = first_record + first_too_long; best_mate = 0; best_ok = 0;
     }
     if (h->h_run->capacity_exceeded && !have) { have = true; best_code = FQD_ERR_CAPACITY; best_ok = pairs; }
     if (have) {
@@ -382,13 +388,78 @@ static int fold_chunk(fqd_handle* h, u64 first_record, u64* n_ok) {
     return h->stats.err;
 }
 
-static int finish_fast_chunk(fqd_handle* h, size_t n1, size_t n2, fqd_chunk_result* res) {
+static int fold_fast_chunk(fqd_handle* h, size_t n1, size_t n2, fqd_chunk_result* res);
+
+static void table_geometry(u64 capacity, u64* n_buckets, u32* shift) {
+    u64 nb = 1024;
+    while (nb * 2 < capacity) nb <<= 1;        // 4*nb entries >= 2*capacity  (load factor <= 0.5)
+    u32 lg = 0; while ((1ull << lg) < nb) ++lg;
+    *n_buckets = nb; *shift = 64 - lg;
+}
+
+// In-place growth of the key store and the table (the reference's set simply rehashes, src/hash_dup_remover.hpp:113-114):
+// called when a chunk did not fit (k_chunk_begin refused it); the caller then runs the same chunk again.  Returns
+// FQD_ERR_CAPACITY when the device has no room for the larger store next to the old one.
+static int grow_fast(fqd_handle* h, u64 need) {
+    const u64 used = h->h_run->n_records;
+    u64 cap = std::max<u64>(h->key_capacity * 2, used + 2 * need);
+    const size_t row_bytes = (size_t)h->row_words * sizeof(u64);
+    u64 nb; u32 shift;
+    u64* keys = nullptr; u64* table = nullptr;
+    for (;; cap = used + need + (cap - used - need) / 2) {     // not enough memory for 2x: try less head room
+        table_geometry(cap, &nb, &shift);
+        const bool same_table = nb == h->n_buckets;
+        if (cudaMalloc(&keys, cap * row_bytes) == cudaSuccess && (same_table || cudaMalloc(&table, nb * 4 * sizeof(u64)) == cudaSuccess)) break;
+        cudaGetLastError();
+        if (keys) { cudaFree(keys); keys = nullptr; }
+        if (cap <= used + need + 1024) return fail(h, FQD_ERR_CAPACITY, "no device memory left to grow the key store");
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(keys, h->d_keys, used * row_bytes, cudaMemcpyDeviceToDevice, h->stream));
+    if (table) {
+        CUDA_TRY(h, cudaMemsetAsync(table, 0xFF, nb * 4 * sizeof(u64), h->stream));
+        RehashParams rp;
+        rp.old_table = h->d_table; rp.old_entries = h->n_buckets * 4; rp.table = table; rp.bucket_shift = shift; rp.bucket_mask = nb - 1;
+        rp.keys = keys; rp.row_words = h->row_words; rp.W = h->W; rp.mates = h->cfg.paired ? 2 : 1; rp.hash_mul = 1;
+        k_rehash<<<h->sm_count * 8, HS_THREADS, 0, h->stream>>>(rp);
+        h->launches++;
+    }
+    RunState* r = h->d_run;
+    CUDA_TRY(h, cudaMemsetAsync(&r->capacity_exceeded, 0, sizeof(u32), h->stream));
+    CUDA_TRY(h, cudaMemsetAsync(&r->sticky_set, 0, sizeof(u32), h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    cudaFree(h->d_keys); h->d_keys = keys; h->key_capacity = cap;
+    if (table) { cudaFree(h->d_table); h->d_table = table; h->n_buckets = nb; h->bucket_shift = shift; }
+    h->grows++;
+    CUDA_TRY(h, cudaGetLastError());
+    return FQD_OK;
+}
+
+static int read_back_chunk(fqd_handle* h) {
     const int mates = h->cfg.paired ? 2 : 1;
     for (int m = 0; m < mates; ++m)
         CUDA_TRY(h, cudaMemcpyAsync(h->mate[m].h_ctl, h->mate[m].d_ctl, sizeof(ChunkCtl), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaMemcpyAsync(h->h_run, h->d_run, sizeof(RunState), cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
-    drain_events(h);
+    return drain_events(h);
+}
+
+static int enqueue_fast_chunk(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2);
+
+// d_r1 / d_r2: where the chunk's bytes are on the device (needed to run it again after the set has grown)
+static int finish_fast_chunk(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2, fqd_chunk_result* res) {
+    int rc = read_back_chunk(h);
+    if (rc) return rc;
+    for (int attempt = 0; h->h_run->capacity_exceeded && attempt < 4; ++attempt) {
+        if (grow_fast(h, h->h_run->chunk_wanted) != FQD_OK) break;       // reported as FQD_ERR_CAPACITY below
+        rc = enqueue_fast_chunk(h, d_r1, n1, d_r2, n2);
+        if (!rc) rc = read_back_chunk(h);
+        if (rc) return rc;
+    }
+    return fold_fast_chunk(h, n1, n2, res);
+}
+
+static int fold_fast_chunk(fqd_handle* h, size_t n1, size_t n2, fqd_chunk_result* res) {
+    const int mates = h->cfg.paired ? 2 : 1;
     const u64 pairs = h->h_run->chunk_pairs;
     const u64 first_record = h->h_run->n_records - pairs;
     for (int m = 0; m < mates; ++m)
@@ -424,7 +495,7 @@ extern "C" int fqd_push_device(fqd_handle* h, const void* d_r1, size_t n1, const
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     int rc = enqueue_fast_chunk(h, d_r1, n1, h->cfg.paired ? d_r2 : nullptr, h->cfg.paired ? n2 : 0);
     if (rc) return rc;
-    return finish_fast_chunk(h, n1, n2, res);
+    return finish_fast_chunk(h, d_r1, n1, h->cfg.paired ? d_r2 : nullptr, h->cfg.paired ? n2 : 0, res);
 }
 
 extern "C" int fqd_push(fqd_handle* h, const char* r1, size_t n1, const char* r2, size_t n2, fqd_chunk_result* res) {
@@ -437,7 +508,7 @@ extern "C" int fqd_push(fqd_handle* h, const char* r1, size_t n1, const char* r2
     if (h->cfg.paired && n2) CUDA_TRY(h, cudaMemcpyAsync(h->mate[1].d_raw, r2, n2, cudaMemcpyHostToDevice, h->stream));
     int rc = enqueue_fast_chunk(h, h->mate[0].d_raw, n1, h->cfg.paired ? h->mate[1].d_raw : nullptr, h->cfg.paired ? n2 : 0);
     if (rc) return rc;
-    return finish_fast_chunk(h, n1, n2, res);
+    return finish_fast_chunk(h, h->mate[0].d_raw, n1, h->cfg.paired ? h->mate[1].d_raw : nullptr, h->cfg.paired ? n2 : 0, res);
 }
 
 // Same contract as fqd_push, split in two so that the copy of chunk c+1 overlaps the processing of chunk c:
@@ -480,7 +551,7 @@ extern "C" int fqd_push_staged(fqd_handle* h, fqd_chunk_result* res) {
     h->run_slot ^= 1; h->n_staged--;
     int rc = enqueue_fast_chunk(h, d1, n1, d2, n2);
     if (rc) return rc;
-    return finish_fast_chunk(h, n1, n2, res);
+    return finish_fast_chunk(h, d1, n1, d2, n2, res);
 }
 
 extern "C" int fqd_push_device_async(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2) {
@@ -502,12 +573,25 @@ extern "C" int fqd_sync(fqd_handle* h) {
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     drain_events(h);
     if (h->pending_async) {
-        // async pushes: totals come from the device counters; data errors are reported for the last chunk only
+        // async pushes: totals come from the device counters; the first chunk that raised a data error left its error
+        // words in the run state (k_chunk_end), whichever chunk it was
         h->pending_async = false;
         u64 n_ok;
         h->stats.total = h->h_run->n_records;
         h->stats.dups = h->h_run->n_dups;
-        fold_chunk(h, h->h_run->n_records - h->h_run->chunk_pairs, &n_ok);
+        if (h->h_run->sticky_set) {
+            const RunState& r = *h->h_run;
+            for (int m = 0; m < mates; ++m) {
+                ChunkCtl& c = *h->mate[m].h_ctl;
+                c.err_parse = r.sticky_parse[m]; c.err_base = r.sticky_base[m]; c.too_long = r.sticky_too_long[m]; c.too_long_rec = r.sticky_too_long_rec[m];
+            }
+            const u32 keep_pairs = h->h_run->chunk_pairs;
+            h->h_run->chunk_pairs = r.sticky_pairs;
+            fold_chunk(h, r.sticky_first, &n_ok);
+            h->h_run->chunk_pairs = keep_pairs;
+        } else {
+            fold_chunk(h, h->h_run->n_records - h->h_run->chunk_pairs, &n_ok);
+        }
     }
     return FQD_OK;
 }
@@ -677,9 +761,9 @@ extern "C" int fqd_shard_insert(fqd_handle* h, const void* d_recv, uint64_t n_re
     ip.ctl1 = nullptr; ip.ctl2 = nullptr; ip.run = h->d_run; ip.dup = (u8*)d_flags; ip.hash_mul = n_shards; ip.hash_final = 1;
     cudaEvent_t ie0 = nullptr, ie1 = nullptr;
     if (h->profile) { ie0 = get_event(h); ie1 = get_event(h); cudaEventRecord(ie0, h->stream); }
-    k_insert<<<g, HS_THREADS, 0, h->stream>>>(ip);
+    insert_launch(ip, g, h->stream);
     if (h->profile) { cudaEventRecord(ie1, h->stream); h->prof_insert.emplace_back(ie0, ie1); h->prof.insert_launches++; }
-    k_chunk_end<<<1, 1, 0, h->stream>>>(h->d_run);
+    k_chunk_end<<<1, 1, 0, h->stream>>>(h->d_run, nullptr, nullptr);
     h->launches += 4;
     CUDA_TRY(h, cudaGetLastError());
     return FQD_OK;
@@ -811,6 +895,15 @@ extern "C" int fqd_emission(fqd_handle* h, fqd_emission_t* out) {
     if (!h || !h->seq || !out) return fail(h, FQD_ERR_INVALID, "fqd_emission is for sequence / unordered modes");
     return seq_emission(h->seq, out, &h->err);
 }
+
+#ifdef FQD_K1_TIMELINE
+// experiment builds only (csrc/Makefile `variants`): per-phase clock64 stamps of every TL_STRIDE-th tile of the last K1 launch
+extern "C" int fqd_debug_k1_timeline(long long* dst, size_t n_values) {
+    const size_t n = std::min(n_values, (size_t)TL_CAP * TL_SLOTS);
+    if (cudaDeviceSynchronize() != cudaSuccess) return FQD_ERR_CUDA;
+    return cudaMemcpyFromSymbol(dst, g_k1_timeline, n * sizeof(long long)) == cudaSuccess ? FQD_OK : FQD_ERR_CUDA;
+}
+#endif
 
 // -----------------------------------------------------------------------------------------------------------
 extern "C" size_t fqd_synth_record_bytes(uint32_t read_len) { return 22u + 2u * (size_t)read_len; }

@@ -37,14 +37,25 @@ struct InsertParams {
     u32 hash_final;         // 1: hash1 already holds the finalised 64-bit hash (sharded path)
 };
 
+// RW = row width known at compile time (8: one 150 bp mate, 16: a 150 bp pair; 0: any, run-time loop).  With RW known
+// every 16-byte load of both rows is issued before the first compare: one DRAM round trip instead of RW / 2.
+template <int RW>
 __device__ __forceinline__ bool rows_equal(const u64* a, const u64* b, u32 words) {
     // rows are 16-byte aligned (row_words is even)
     const ulonglong2* pa = reinterpret_cast<const ulonglong2*>(a);
     const ulonglong2* pb = reinterpret_cast<const ulonglong2*>(b);
     u64 diff = 0;
-    for (u32 i = 0; i < words / 2; ++i) {
-        ulonglong2 x = pa[i], y = __ldcg(pb + i);
-        diff |= (x.x ^ y.x) | (x.y ^ y.y);
+    if (RW > 0) {
+        ulonglong2 x[RW / 2 > 0 ? RW / 2 : 1], y[RW / 2 > 0 ? RW / 2 : 1];
+#pragma unroll
+        for (int i = 0; i < RW / 2; ++i) { x[i] = __ldcg(pa + i); y[i] = __ldcg(pb + i); }
+#pragma unroll
+        for (int i = 0; i < RW / 2; ++i) diff |= (x[i].x ^ y[i].x) | (x[i].y ^ y[i].y);
+    } else {
+        for (u32 i = 0; i < words / 2; ++i) {
+            ulonglong2 x = pa[i], y = __ldcg(pb + i);
+            diff |= (x.x ^ y.x) | (x.y ^ y.y);
+        }
     }
     return diff == 0;
 }
@@ -54,13 +65,44 @@ __global__ void __launch_bounds__(HS_THREADS) k_chunk_begin(InsertParams p) {
     // shorter one (src/hash_dup_remover.hpp:228-230)
     u32 n = p.ctl1->n_records;
     if (p.ctl2) n = min(n, p.ctl2->n_records);
+    // A chunk that does not fit is not processed at all (nothing inserted, counters untouched): the host grows the key
+    // store and the table in place (grow_fast) and runs the same chunk again.
     u64 room = p.key_capacity - p.run->n_records;
-    if ((u64)n > room) { n = (u32)room; p.run->capacity_exceeded = 1; }
+    if ((u64)n > room) { p.run->chunk_wanted = n; n = 0; p.run->capacity_exceeded = 1; }
     p.run->chunk_pairs = n;
     p.run->chunk_dups = 0;
 }
 
-__global__ void __launch_bounds__(HS_THREADS) k_insert(const InsertParams p) {
+// Growth of the set (the reference's unordered_set rehashes as it fills, src/hash_dup_remover.hpp:113-114): every entry
+// of the old table is placed in the new, larger one.  The hash is recomputed from the key row (what K1 computed when
+// the record was packed); the entries are distinct keys, so there is nothing to compare.
+struct RehashParams {
+    const u64* old_table; u64 old_entries;
+    u64* table; u32 bucket_shift; u64 bucket_mask;
+    const u64* keys; u32 row_words; u32 W; u32 mates; u64 hash_mul;
+};
+__global__ void __launch_bounds__(HS_THREADS) k_rehash(const RehashParams p) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < p.old_entries; i += stride) {
+        const u64 e = p.old_table[i];
+        if (e == HS_EMPTY) continue;
+        const u64 slot = e & HS_SLOT_MASK;
+        const u64* row = p.keys + slot * p.row_words;
+        u64 hm[2] = {0, 0};
+        for (u32 m = 0; m < p.mates; ++m)
+            for (u32 w = 0; w < p.W; ++w) hm[m] += word_hash(row[m * p.W + w], pos_keys(m * 4096u + w));
+        u64 h = p.mates == 2 ? pair_hash(hm[0], hm[1]) : mix64(hm[0]);
+        h *= p.hash_mul;
+        const u64 mine = (((h >> 8) & 0xFFFFFFull) << 40) | slot;
+        u64 b = h >> p.bucket_shift;
+        for (bool done = false; !done; b = (b + 1) & p.bucket_mask)
+            for (int k = 0; k < 4 && !done; ++k)
+                if (p.table[b * 4 + k] == HS_EMPTY && atomicCAS(p.table + b * 4 + k, HS_EMPTY, mine) == HS_EMPTY) done = true;
+    }
+}
+
+template <int RW>
+__global__ void __launch_bounds__(HS_THREADS, 4) k_insert(const InsertParams p) {
     const u32 n = p.run->chunk_pairs;
     const u64 slot_base = p.run->n_records;
     const u32 stride = gridDim.x * blockDim.x;
@@ -89,7 +131,7 @@ __global__ void __launch_bounds__(HS_THREADS) k_insert(const InsertParams p) {
                 }
                 if ((cur >> 40) == tag) {
                     const u64 other = cur & HS_SLOT_MASK;
-                    if (rows_equal(myrow, p.keys + other * p.row_words, p.row_words)) {
+                    if (rows_equal<RW>(myrow, p.keys + other * p.row_words, p.row_words)) {
                         u64 old = atomicMin(bp + k, mine);
                         if (old < mine) p.dup[i] = 1;                          // an earlier record holds this key
                         else p.dup[(u32)((old & HS_SLOT_MASK) - slot_base)] = 1; // I displaced a later record
@@ -100,6 +142,12 @@ __global__ void __launch_bounds__(HS_THREADS) k_insert(const InsertParams p) {
             b = (b + 1) & p.bucket_mask;
         }
     }
+}
+
+static inline void insert_launch(const InsertParams& p, unsigned grid, cudaStream_t stream) {
+    if (p.row_words == 8) k_insert<8><<<grid, HS_THREADS, 0, stream>>>(p);
+    else if (p.row_words == 16) k_insert<16><<<grid, HS_THREADS, 0, stream>>>(p);
+    else k_insert<0><<<grid, HS_THREADS, 0, stream>>>(p);
 }
 
 // K3: count this chunk's duplicates and advance the run counters (single host-sync-free hand-over to the
@@ -126,7 +174,19 @@ __global__ void __launch_bounds__(HS_THREADS) k_count_dups(const u8* dup, RunSta
     if (threadIdx.x == 0 && s_cnt) atomicAdd(&run->chunk_dups, s_cnt);
 }
 
-__global__ void k_chunk_end(RunState* run) {
+__global__ void k_chunk_end(RunState* run, const ChunkCtl* ctl1, const ChunkCtl* ctl2) {
+    if (ctl1 && !run->sticky_set) {
+        const ChunkCtl* c[2] = {ctl1, ctl2 ? ctl2 : ctl1};
+        bool any = false;
+        for (int m = 0; m < (ctl2 ? 2 : 1); ++m) any |= c[m]->err_parse != NO_ERR || c[m]->err_base != NO_ERR || (c[m]->too_long & TL_SEQ);
+        if (any || run->capacity_exceeded) {
+            run->sticky_set = 1; run->sticky_pairs = run->capacity_exceeded ? run->chunk_wanted : run->chunk_pairs; run->sticky_first = run->n_records;
+            for (int m = 0; m < 2; ++m) {
+                run->sticky_parse[m] = c[m]->err_parse; run->sticky_base[m] = c[m]->err_base;
+                run->sticky_too_long[m] = c[m]->too_long; run->sticky_too_long_rec[m] = c[m]->too_long_rec;
+            }
+        }
+    }
     run->n_records += run->chunk_pairs;
     run->n_dups += run->chunk_dups;
     run->n_survivors += run->chunk_pairs - run->chunk_dups;

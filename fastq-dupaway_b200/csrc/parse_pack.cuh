@@ -220,8 +220,8 @@ __device__ __forceinline__ void commit_record(const ParseParams& p, u64 slot_bas
     if (rs == RS_BAD_START) atomicMin(&p.ctl->err_parse, ((u64)R << 16) | ((u64)PERR_BAD_START << 8) | (status >> 8));
     else if (rs == RS_LEN_MISMATCH) atomicMin(&p.ctl->err_parse, ((u64)R << 16) | ((u64)PERR_LEN_MISMATCH << 8));
     else if (rs == RS_OK || rs == RS_TOO_LONG) {
-        if (slot_base + R >= p.key_capacity) p.ctl->too_long = 2;
-        else if (rs == RS_TOO_LONG) p.ctl->too_long = 1;
+        if (slot_base + R >= p.key_capacity) atomicOr(&p.ctl->too_long, (u32)TL_CAPACITY);
+        else if (rs == RS_TOO_LONG) { atomicOr(&p.ctl->too_long, (u32)TL_SEQ); atomicMin(&p.ctl->too_long_rec, R); }
     }
 }
 
@@ -346,6 +346,26 @@ static inline cudaError_t pp_init_tables() {
     return cudaMemcpyToSymbol(c_hkeys, h, sizeof(h));
 }
 
+// ---- build-time experiments (profiles/r02_k1_variants.md): FQD_K1_TICKET=1 restores the atomic ticket of round 1,
+// FQD_K1_L2PF=<tiles> prefetches a later tile into L2 at CTA start, FQD_K1_TIMELINE records per-phase clocks.
+#ifndef FQD_K1_TICKET
+#define FQD_K1_TICKET 0
+#endif
+#ifndef FQD_K1_L2PF
+#define FQD_K1_L2PF 740      // tiles ahead = CTAs resident on 148 SMs (PP_MIN_CTAS each): what starts one CTA lifetime from now
+#endif
+#ifdef FQD_K1_TIMELINE
+constexpr u32 TL_STRIDE = 61, TL_SLOTS = 12, TL_CAP = 4096;
+__device__ long long g_k1_timeline[TL_CAP * TL_SLOTS];
+#define TL_STAMP(cond, k) do { if ((cond) && tile % TL_STRIDE == 0 && tile / TL_STRIDE < TL_CAP) g_k1_timeline[(tile / TL_STRIDE) * TL_SLOTS + (k)] = clock64(); } while (0)
+#define TL_ENTRY() const long long tl_t0 = clock64()
+#define TL_STAMP0(cond) do { if ((cond) && tile % TL_STRIDE == 0 && tile / TL_STRIDE < TL_CAP) g_k1_timeline[(tile / TL_STRIDE) * TL_SLOTS] = tl_t0; } while (0)
+#else
+#define TL_ENTRY() do { } while (0)
+#define TL_STAMP0(cond) do { } while (0)
+#define TL_STAMP(cond, k) do { } while (0)
+#endif
+
 // LPR = lines per record: 4 = FASTQ, 2 = FASTA.  BYTES = raw-byte key rows (ParseParams::byte_keys; sequence-based
 // modes on arbitrary alphabets) - a template parameter so that the 3-bit instantiation every other path uses carries
 // none of its code or registers.
@@ -358,18 +378,21 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     __shared__ u32 q_len[PP_QCAP];
     __shared__ uint2 s_hkey[PP_HKEYS];
     __shared__ u32 warp_sum[PP_THREADS / 32];
-    __shared__ u32 s_tile, s_P, s_halo, s_c;
-    __shared__ volatile u32 s_Pready;
+#if FQD_K1_TICKET
+    __shared__ u32 s_tile;
+#endif
+    __shared__ u32 s_P, s_halo;
     __shared__ __align__(8) u64 mbar;
 
     const u32 tid = threadIdx.x;
     const u32 lane = tid & 31u, warp = tid >> 5;
     const u64 slot_base = p.run->n_records;
+    TL_ENTRY();
 
+#if FQD_K1_TICKET
     if (tid == 0) {
         s_tile = atomicAdd(&p.ctl->ticket, 1u);      // tiles are processed in ticket order: every predecessor
         mbar_init(&mbar, 1);                         // of a tile is already resident (look-back cannot deadlock)
-        s_Pready = 0;
     }
     if (tid < PP_HKEYS) s_hkey[tid] = c_hkeys[((p.hash_salt >> 12) & 1u) * PP_HKEYS + tid];
     __syncthreads();
@@ -381,11 +404,38 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
         mbar_expect_tx(&mbar, bytes);
         bulk_g2s(win, p.raw + base, bytes, &mbar);
     }
+    mbar_wait(&mbar, 0);
+#else
+    // Tiles in block-index order: the hardware starts the CTAs of a 1-D grid in index order, so every predecessor of a
+    // tile is resident or done when the tile starts (the assumption every single-pass decoupled look-back scan makes) -
+    // no ticket atomic, and one barrier covers both the mbarrier set-up and the arrival of the tile's bytes.
+    const u32 tile = blockIdx.x;
+    const u32 base = tile * PP_TILE;
+    const u32 valid = min(PP_WINDOW, p.n - base);
+    if (warp == 0) {
+        if (lane == 0) {
+            mbar_init(&mbar, 1);
+            const u32 bytes = (valid + 15u) & ~15u;
+            mbar_expect_tx(&mbar, bytes);
+            bulk_g2s(win, p.raw + base, bytes, &mbar);
+#if FQD_K1_L2PF
+            // the tile a CTA will want about one CTA lifetime from now: HBM -> L2 while this one is being processed
+            const u64 pf = (u64)(tile + FQD_K1_L2PF) * PP_TILE;
+            if (pf + PP_TILE <= (u64)p.n) bulk_prefetch_l2(p.raw + pf, PP_TILE);
+#endif
+        }
+        __syncwarp();
+        mbar_wait(&mbar, 0);
+    }
+    if (tid < PP_HKEYS) s_hkey[tid] = c_hkeys[((p.hash_salt >> 12) & 1u) * PP_HKEYS + tid];
+    __syncthreads();
+#endif
+    TL_STAMP0(tid == 0);
+    TL_STAMP(tid == 0, 1);
     // constants the compiler must keep in registers (one LOP3 per use instead of two with immediates)
     u32 c_nl, c_7f;
     asm volatile("mov.u32 %0, 0x0A0A0A0A;" : "=r"(c_nl));
     asm volatile("mov.u32 %0, 0x7F7F7F7F;" : "=r"(c_7f));
-    mbar_wait(&mbar, 0);
 
     // ---- 1. newline bitmask of the window
     {
@@ -415,6 +465,7 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
         }
     }
     __syncthreads();
+    TL_STAMP(tid == 0, 2);
 
     // ---- 2. local ranks: block scan over the tile's mask words (+ the halo words, ranked after them)
     // PP_TILE/64 == PP_THREADS words cover the tile proper; newlines before the chunk's first byte are not ours
@@ -442,6 +493,7 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     }
     // publish this tile's aggregate as early as possible
     if (tid == 0) st_volatile_u64(p.tile_state + tile, ((tile == 0 ? 2ull : 1ull) << 32) | T);
+    TL_STAMP(tid == 0, 3);
     if (cnt) {
         // straight-line for the first two newlines of my 64 bytes (a FASTQ line pair "...\n+\n" at most), loop for more
         u64 m = my_mask;
@@ -462,8 +514,9 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
         }
     }
     bool compact;                                  // the compacted positions hold every newline of the window
-    if (warp == 0) {
-        // halo words (PP_HALO/64 <= 32): ranks continue after the tile's
+    if (warp == PP_THREADS / 32 - 1) {
+        // the last warp also ranks the halo words (PP_HALO/64 <= 32): their ranks continue after the tile's.  (Warp 0
+        // did this in round 1 - 1 400 cycles between publishing the tile's count and the first look-back load.)
         const u64 hm = lane < (PP_NW - PP_THREADS) ? mask64[PP_THREADS + lane] : 0ull;
         const u32 hc = (u32)__popcll(hm);
         u32 hi = hc;
@@ -482,12 +535,17 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
             if (r < PP_NLCAP) nlpos[r] = (u16)((PP_THREADS + lane) * 64u + b);
             ++r;
         }
-        compact = T + htot <= PP_NLCAP;
+    }
+    if (warp == 0) {
         __syncwarp();
         bar_arrive_c<BAR_POS, PP_THREADS>();
+        // newlines in the halo, for `compact` (s_halo belongs to the packers' side of BAR_POS)
+        const u32 htot = __reduce_add_sync(0xFFFFFFFFu, lane < (PP_NW - PP_THREADS) ? (u32)__popcll(mask64[PP_THREADS + lane]) : 0u);
+        compact = T + htot <= PP_NLCAP;
 
         // ---- decoupled look-back for the global rank of the tile's first newline; warps 1..7 do not wait for it
         u32 P = 0;
+        TL_STAMP(lane == 0, 9);
         if (tile != 0) {
             // window of 128 predecessors per hop (4 per lane): one L2 round trip must cover more tiles than
             // the chip starts in that time, otherwise the distance to the nearest published prefix grows
@@ -524,10 +582,9 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
             }
             if (lane == 0) st_volatile_u64(p.tile_state + tile, (2ull << 32) | (u64)(P + T));
         }
+        TL_STAMP(lane == 0, 10);
         if (lane == 0) {
             s_P = P;
-            __threadfence_block();
-            s_Pready = 1;
             if (tile == p.n_tiles - 1) {
                 u32 all = P + T;
                 p.ctl->n_newlines = all;
@@ -549,37 +606,34 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     const u32 Rrel_first = tile == 0 ? 0u : 1u;         // owned records, counted from floor(P / LPR)
 
     if (compact) {
-        // ================= normal tile: warps 1..7.  One thread per record: its line ends are consecutive entries
-        // of nlpos; everything but the record's index follows from c = P mod LPR.
+        // ================= normal tile: warps 1..7, PP_GROUP lanes per record.  A record's line ends are consecutive
+        // entries of nlpos; everything but the record's index follows from c = P mod LPR.  Every lane of a group
+        // derives the geometry of its record itself (identical work, broadcast loads): round 1 had one owner thread per
+        // record hand it over through shared memory, which kept five of the seven warps waiting at a barrier.
         const u32 wtid = tid - 32u;
         const u32 g = wtid / PP_GROUP;
-        // Only the warps that hold owner threads need c before the first barrier; the others read it afterwards.
-        // Without a usable guess the owners poll for the look-back result (BAR_P itself is always passed at the
-        // same point, after the pack stage, by every packer).
         u32 P = 0, c = 0;
         bool p_known = false;
-        const bool owner_warp = wtid < ((PP_PACKERS / PP_GROUP + 31u) & ~31u);
-        if (owner_warp && tile != 0) {
-            c = guess_phase<LPR>(win, nlpos, WN, valid, lane);
-            if (c == PP_NONE) {
-                while (!s_Pready) { }
-                c = s_P % LPR;
+        if (tile != 0) {
+            c = guess_phase<LPR>(win, nlpos, WN, valid, lane);      // same inputs in every warp -> same answer
+            if (c == PP_NONE) {                                      // no usable guess: all packers wait for the exact value
+                bar_sync_c<BAR_P, PP_THREADS>();
+                P = s_P; p_known = true; c = P % LPR;
             }
         }
-        if (wtid == 0) s_c = c;
+        TL_STAMP(wtid == 0, 4);
         u32 rbase = 0;
         for (;;) {
-            u32 Rrel_last = (c + T) / LPR;
-            u32 n_owned = Rrel_last >= Rrel_first ? Rrel_last - Rrel_first + 1u : 0u;
-            u32 n_round = rbase < n_owned ? min(PP_PACKERS / PP_GROUP, n_owned - rbase) : 0u;
-            // ---- owners: geometry + validation
-            u32 status = RS_NONE, gstart = 0;
-            if (wtid < n_round) {
-                const u32 Rrel = Rrel_first + rbase + wtid;
+            const u32 Rrel_last = (c + T) / LPR;
+            const u32 n_owned = Rrel_last >= Rrel_first ? Rrel_last - Rrel_first + 1u : 0u;
+            const u32 n_round = rbase < n_owned ? min(PP_PACKERS / PP_GROUP, n_owned - rbase) : 0u;
+            // ---- geometry + validation
+            u32 status = RS_NONE, gstart = 0, off = PP_NONE, ql = 0;
+            if (g < n_round) {
+                const u32 Rrel = Rrel_first + rbase + g;
                 const int j0 = (int)(LPR * Rrel) - 1 - (int)c;            // local rank of the newline before the record
                 const u32 start_l = j0 < 0 ? p.skip : (u32)nlpos[j0] + 1u;
                 gstart = base + start_l;
-                u32 qoff = PP_NONE, qlen = 0;
                 if (gstart < p.n) {
                     u32 e[4];
 #pragma unroll
@@ -593,43 +647,34 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                         }
                     }
                     status = classify_record<LPR, BYTES>(p, win, base, start_l, e[0], e[1], LPR == 4 ? e[2] : e[1],
-                                                  LPR == 4 ? e[3] : e[1], qoff, qlen);
+                                                  LPR == 4 ? e[3] : e[1], off, ql);
                 }
-                q_off[wtid] = qoff;
-                q_len[wtid] = qlen;
             }
-            bar_sync_c<BAR_WORK, PP_PACKERS>();
-            if (!p_known && !owner_warp) {
-                c = s_c;
-                Rrel_last = (c + T) / LPR;
-                n_owned = Rrel_last >= Rrel_first ? Rrel_last - Rrel_first + 1u : 0u;
-                n_round = rbase < n_owned ? min(PP_PACKERS / PP_GROUP, n_owned - rbase) : 0u;
-            }
+            TL_STAMP(wtid == 0 && rbase == 0, 5);
             // ---- pack (rows of up to 8 words: into registers, before the record index is known)
-            const bool active = g < n_round && q_off[g] != PP_NONE;
-            u32 off = 0, ql = 0, bad = 0;
+            const bool active = off != PP_NONE;
+            u32 bad = 0;
             u64 wa = 0, wb = 0, hsum = 0;
-            if (active) {
-                off = q_off[g]; ql = q_len[g];
-                if (p.W <= 8u) {
-                    const u32 w = 2u * l4;
-                    if (w < p.W) {
-                        u32 bad_b;
-                        wa = pack_word<BYTES>(win, p, base, off, ql, w, bad);
-                        wb = pack_word<BYTES>(win, p, base, off, ql, w + 1u, bad_b);
-                        if (!bad) bad = bad_b;
-                        hsum = word_hash(wa, s_hkey[w]) + word_hash(wb, s_hkey[w + 1u]);
-                    }
+            if (active && p.W <= 8u) {
+                const u32 w = 2u * l4;
+                if (w < p.W) {
+                    u32 bad_b;
+                    wa = pack_word<BYTES>(win, p, base, off, ql, w, bad);
+                    wb = pack_word<BYTES>(win, p, base, off, ql, w + 1u, bad_b);
+                    if (!bad) bad = bad_b;
+                    hsum = word_hash(wa, s_hkey[w]) + word_hash(wb, s_hkey[w + 1u]);
                 }
             }
+            TL_STAMP(wtid == 0 && rbase == 0, 6);
             if (!p_known) {
                 bar_sync_c<BAR_P, PP_THREADS>();
                 P = s_P; p_known = true;
                 if (P % LPR != c) { c = P % LPR; continue; }       // wrong guess: split this round again
             }
+            TL_STAMP(wtid == 0 && rbase == 0, 7);
             // ---- commit
             const u32 R0 = P / LPR + Rrel_first + rbase;
-            if (wtid < n_round) commit_record(p, slot_base, R0 + wtid, gstart, status);
+            if (g < n_round && l4 == 0) commit_record(p, slot_base, R0 + g, gstart, status);
             if (active) {
                 const u32 R = R0 + g;
                 if (R < p.cap && slot_base + R < p.key_capacity) {
@@ -654,8 +699,8 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                 }
             }
             rbase += PP_PACKERS / PP_GROUP;
+            TL_STAMP(wtid == 0, 8);
             if (rbase >= n_owned) break;
-            bar_sync_c<BAR_WORK, PP_PACKERS>();          // the queue is rewritten by the next round
         }
         return;
     }
@@ -747,7 +792,7 @@ __global__ void k_init_chunk(ChunkCtl* ctl, u64* tile_state, u32 n_tiles) {
     u32 i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i == 0) {
         ctl->ticket = 0; ctl->n_newlines = 0; ctl->n_records = 0; ctl->consumed = 0;
-        ctl->err_parse = NO_ERR; ctl->err_base = NO_ERR; ctl->too_long = 0; ctl->pad = 0;
+        ctl->err_parse = NO_ERR; ctl->err_base = NO_ERR; ctl->too_long = 0; ctl->pad = 0; ctl->too_long_rec = ~0u; ctl->pad2 = 0;
     }
     for (; i < n_tiles; i += gridDim.x * blockDim.x) tile_state[i] = 0;
 }

@@ -377,7 +377,7 @@ __global__ void k_extract_tags(const u8* raw, const u32* rec_start, const ChunkC
         u32 t1 = idlen;
         for (u32 i = t0; i < idlen; ++i) if (p[i] == ' ') { t1 = i; break; }
         const u32 tl = t1 > t0 ? t1 - t0 : 0u;
-        if (tl > TW * 8u) ctl_out->too_long = 3;
+        if (tl > TW * 8u) atomicOr(&ctl_out->too_long, (u32)TL_TAG);
         u64* out = tags + r * TW;
         for (u32 w = 0; w < TW; ++w) {
             u64 v = 0;
@@ -697,14 +697,53 @@ static void seq_set_error(SeqState* s, int code, int ch, u64 rec, int mate) {
     s->stats.err = code; s->stats.err_char = ch; s->stats.err_record = rec; s->stats.err_mate = mate;
 }
 
+// The record tables and the key rows are full: make them larger in place (the host sized them from the file size, which
+// a pipe does not have; the reference's vectors simply grow, src/external_sort.hpp:88-117).  A parse that stops at the
+// tables' end leaves the rest of its segment as the carried tail, so parsing just continues after this.
+template <class T>
+static cudaError_t seq_regrow(T** p, u64 old_count, u64 new_count, cudaStream_t st, int fill = -1) {
+    if (!*p) return cudaSuccess;
+    T* q = nullptr;
+    cudaError_t e = cudaMalloc(&q, new_count * sizeof(T));
+    if (e != cudaSuccess) return e;
+    e = cudaMemcpyAsync(q, *p, old_count * sizeof(T), cudaMemcpyDeviceToDevice, st);
+    if (e == cudaSuccess && fill >= 0) e = cudaMemsetAsync(q + old_count, fill, (new_count - old_count) * sizeof(T), st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess) { cudaFree(q); return e; }
+    cudaFree(*p);
+    *p = q;
+    return cudaSuccess;
+}
+static bool seq_grow(SeqState* s) {
+    const u64 old = s->capacity;
+    for (u64 cap = old * 2; cap > old + 1024; cap = old + (cap - old) / 2) {
+        // all or nothing per attempt: a failed allocation leaves the pointers that were not reached untouched, and the
+        // ones that were already moved are simply larger than they need to be
+        size_t free_b = 0, total_b = 0;
+        const size_t per_rec = s->row_words * 8 + s->mates * (8 + 4 + 4 + (s->cfg.unordered ? 8 + 4 + s->TW * 8 : 0));
+        if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess || (double)cap * per_rec * 1.02 > (double)free_b) continue;
+        bool ok = seq_regrow(&s->d_keys, old * s->row_words, cap * s->row_words, s->stream) == cudaSuccess;
+        for (u32 m = 0; ok && m < s->mates; ++m) {
+            SeqMate& mt = s->mate[m];
+            ok = seq_regrow(&mt.d_rec_off, old, cap, s->stream) == cudaSuccess && seq_regrow(&mt.d_rec_len, old, cap, s->stream) == cudaSuccess &&
+                 seq_regrow(&mt.d_seq_len, old, cap, s->stream) == cudaSuccess && seq_regrow(&mt.d_hash, old, cap, s->stream) == cudaSuccess &&
+                 seq_regrow(&mt.d_bad, old, cap, s->stream, 0xFF) == cudaSuccess && seq_regrow(&mt.d_tags, old * s->TW, cap * s->TW, s->stream) == cudaSuccess;
+        }
+        if (!ok) { cudaGetLastError(); return false; }
+        s->capacity = cap;
+        return true;
+    }
+    return false;
+}
+
 // Parse the current (last) segment of a mate; move its incomplete tail into a fresh segment unless `final`.
 static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
     SeqMate& mt = s->mate[m];
     SeqSegment& sg = mt.segs.back();
     if (sg.fill == 0) return FQD_OK;
     const u32 n_tiles = (u32)((sg.fill + PP_TILE - 1) / PP_TILE);
+    if (s->capacity == mt.n_records && !seq_grow(s)) { seq_set_error(s, FQD_ERR_CAPACITY, 0, mt.n_records, m); return FQD_OK; }
     const u64 room = s->capacity - mt.n_records;
-    if (room == 0) { seq_set_error(s, FQD_ERR_CAPACITY, 0, mt.n_records, m); return FQD_OK; }
     SEQ_TRY(cudaEventRecord(s->ev0, s->stream));
     k_init_chunk<<<std::max(1u, std::min(n_tiles / 256 + 1, 1024u)), 256, 0, s->stream>>>(s->d_ctl, s->d_tile_state, n_tiles);
     ParseParams p;
@@ -733,9 +772,9 @@ static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
         int code = (int)((c.err_parse >> 8) & 0xFF);
         seq_set_error(s, code == PERR_BAD_START ? FQD_ERR_BAD_START : FQD_ERR_LEN_MISMATCH, (int)(c.err_parse & 0xFF), first + (c.err_parse >> 16), m);
     }
-    if (c.too_long == 1) seq_set_error(s, FQD_ERR_SEQ_TOO_LONG, 0, first, m);
-    if (c.too_long == 2) seq_set_error(s, FQD_ERR_CAPACITY, 0, first, m);
-    if (c.too_long == 3) seq_set_error(s, FQD_ERR_TAG_TOO_LONG, 0, first, m);
+    if (c.too_long & TL_SEQ) seq_set_error(s, FQD_ERR_SEQ_TOO_LONG, 0, first, m);
+    // TL_CAPACITY: the parse stopped at the tables' end (p.cap); what it left is the carried tail, the next call grows
+    if (c.too_long & TL_TAG) seq_set_error(s, FQD_ERR_TAG_TOO_LONG, 0, first, m);
     if (c.pad == 2 && s->cfg.byte_keys) s->low_bytes = true;
     else if (c.pad && !s->cfg.unordered) seq_set_error(s, FQD_ERR_UNSUPPORTED_BYTE, 0, first, m);
     mt.n_records += c.n_records;
@@ -1215,7 +1254,7 @@ static int seq_finish_unordered(SeqState* s, std::string* err) {
     InsertParams ip;
     ip.table = table; ip.bucket_shift = 64 - lg; ip.bucket_mask = nb - 1; ip.keys = pair_rows; ip.row_words = 2 * W; ip.key_capacity = E;
     ip.hash1 = h1; ip.hash2 = h2; ip.ctl1 = nullptr; ip.ctl2 = nullptr; ip.run = run; ip.dup = dup; ip.hash_mul = 1; ip.hash_final = 0;
-    k_insert<<<s->sm * 8, HS_THREADS, 0, s->stream>>>(ip);
+    insert_launch(ip, s->sm * 8, s->stream);
     s->launches += 3;
     u64 hbad = 0;
     SEQ_TRY(cudaMemcpy(&hbad, first_bad, sizeof hbad, cudaMemcpyDeviceToHost));

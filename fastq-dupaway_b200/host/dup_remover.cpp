@@ -104,6 +104,26 @@ size_t file_size_or_zero(const std::string& name) {
     return stat(name.c_str(), &sb) == 0 ? (size_t)sb.st_size : 0;
 }
 
+// A pipe, a FIFO, /dev/stdin, `<(zcat x.gz)`: can be read once, has no size.
+bool rereadable(const std::string& name) {
+    struct stat sb;
+    return stat(name.c_str(), &sb) == 0 && S_ISREG(sb.st_mode);
+}
+
+// Restarting a job means reading the input again (wider key rows; tables the engine could not grow in place).
+void check_restart_possible(const std::string* in, int mates, const char* why) {
+    for (int m = 0; m < mates; ++m)
+        if (!rereadable(in[m]))
+            throw std::runtime_error(std::string("input ") + in[m] + " is not a regular file and cannot be read a second time (" + why +
+                                     "); write it to a file first");
+}
+
+void check_outputs(const std::vector<std::unique_ptr<OutputFile>>& outs, const std::string* names) {
+    for (size_t m = 0; m < outs.size(); ++m)
+        if (int e = outs[m]->error())
+            throw std::runtime_error("writing " + names[m] + " failed: " + std::strerror(e));
+}
+
 // How much larger than the file is its content?  Plain: 1.  ".gz": the ratio measured on what the reader has
 // inflated by now (the first block is there, i.e. tens of megabytes) plus 10 %, else a generous 8 (a wrong guess
 // costs device memory or a restart with doubled tables, never the result).
@@ -195,7 +215,7 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
             BlockReader* r = ms[m].reader.get();
             ms[m].release = [w, r](Block* b) { w->then([r, b] { r->release(b); }); };
         }
-        auto close_outputs = [&] { for (auto& w : writers) w->drain(); for (auto& o : outs) o->close(); };
+        auto close_outputs = [&] { for (auto& w : writers) w->drain(); for (auto& o : outs) o->close(); check_outputs(outs, out); };
         std::vector<Run> runs;
         struct { bool valid = false; std::vector<char> bytes[2]; } held;      // last written pair of the previous chunk
         for (int m = 0; m < mates; ++m)
@@ -244,8 +264,8 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
             if (rc) throw_engine_error(eng.get(), rc);
             fqd_stats_t st;
             fqd_stats(eng.get(), &st);
-            if (st.err == FQD_ERR_SEQ_TOO_LONG) { ++seq_growth; restart = true; break; }
-            if (st.err == FQD_ERR_CAPACITY) { growth *= 2.0; restart = true; break; }
+            if (st.err == FQD_ERR_SEQ_TOO_LONG) { check_restart_possible(in, mates, "a later sequence is longer than the key rows sized from the first block"); ++seq_growth; restart = true; break; }
+            if (st.err == FQD_ERR_CAPACITY) { check_restart_possible(in, mates, "the key store could not be grown in place"); growth *= 2.0; restart = true; break; }
             size_t n = (size_t)res.n_records;
             uint64_t chunk_dups = n - res.n_survivors;
             // A record that does not start with '@'/'>' aborts the run while the record BEFORE it is fetched
@@ -422,10 +442,10 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
         trace("sorted / joined / scanned");
         fqd_stats_t st;
         fqd_stats(eng.get(), &st);
-        if (st.err == FQD_ERR_SEQ_TOO_LONG) { ++seq_growth; continue; }
-        if (st.err == FQD_ERR_CAPACITY) { growth *= 2.0; continue; }
-        if (st.err == FQD_ERR_TAG_TOO_LONG) { ++tag_growth; continue; }
-        if (st.err == FQD_ERR_UNSUPPORTED_BYTE && !byte_keys) { byte_keys = true; continue; }
+        if (st.err == FQD_ERR_SEQ_TOO_LONG) { check_restart_possible(in, mates, "a later sequence is longer than the key rows sized from the first block"); ++seq_growth; continue; }
+        if (st.err == FQD_ERR_CAPACITY) { check_restart_possible(in, mates, "the record tables could not be grown in place"); growth *= 2.0; continue; }
+        if (st.err == FQD_ERR_TAG_TOO_LONG) { check_restart_possible(in, mates, "an ID tag is longer than the tag rows"); ++tag_growth; continue; }
+        if (st.err == FQD_ERR_UNSUPPORTED_BYTE && !byte_keys) { check_restart_possible(in, mates, "a sequence holds a byte outside {A,C,G,T,N}: raw-byte key rows are needed"); byte_keys = true; continue; }
         // parse errors surface while the inputs are being sorted, before any output file exists
         // (src/seq_dup_remover.hpp:44-50, src/hash_dup_remover.hpp:160-174)
         if (st.err == FQD_ERR_LEN_MISMATCH) {
@@ -463,6 +483,7 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
             writer.drain();
         }
         for (auto& o : outs) o->close();
+        check_outputs(outs, out);
         if (write_clusters) {
             // ClusterFile (src/file_utils.cpp:98-112): plain text <outfile>.clusters next to every output file
             for (int m = 0; m < mates; ++m) {

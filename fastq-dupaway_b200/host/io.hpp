@@ -5,7 +5,13 @@
 // of PINNED blocks (fqd_host_alloc) so that inflate / read() overlap the H2D copies and the kernels - the
 // successor of BufferedInput<T>'s single malloc'd block (src/bufferedinput.hpp:28-36,57-88).
 #pragma once
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
+
+#include <atomic>
+#include <cerrno>
 
 #include <chrono>
 #include <condition_variable>
@@ -281,6 +287,9 @@ public:
         } else {
             m_fd = ::open(name.c_str(), O_WRONLY | O_CREAT | O_TRUNC, 0666);
             m_wbuf.reserve(kBuf);
+            // /dev/stdout, a FIFO, `-o >(pigz > x.gz)`: no offsets there - every byte goes through write() in order
+            struct stat sb;
+            m_seekable = m_fd >= 0 && fstat(m_fd, &sb) == 0 && S_ISREG(sb.st_mode) && ::lseek(m_fd, 0, SEEK_CUR) != (off_t)-1;
         }
     }
     ~OutputFile() { close(); }
@@ -292,14 +301,14 @@ public:
         } else if (m_sink) {
             m_sink->write(p, n);
         } else if (m_fd >= 0) {
-            if (n >= kBuf) { flush(); pwrite_all(m_fd, p, n, m_off); m_off += n; return; }
+            if (n >= kBuf) { flush(); put_all(p, n, m_off); m_off += n; return; }
             if (m_wbuf.size() + n > kBuf) flush();
             m_wbuf.insert(m_wbuf.end(), p, p + n);
         }
     }
     // runs must be sorted by out_off and dense: out_off[i+1] = out_off[i] + len[i], out_off[0] = 0
     void write_runs(const char* base, const Run* runs, size_t n_runs, size_t total) {
-        if (m_fd < 0 || total < (8u << 20) || io_threads() <= 1) {
+        if (m_fd < 0 || !m_seekable || total < (8u << 20) || io_threads() <= 1) {
             for (size_t i = 0; i < n_runs; ++i) write(base + runs[i].off, runs[i].len);
             return;
         }
@@ -309,7 +318,8 @@ public:
         struct Join { std::mutex mu; std::condition_variable cv; int left; };
         auto join = std::make_shared<Join>();      // shared: a worker may still be inside notify when the waiter returns
         join->left = parts;
-        const int fd = m_fd; const size_t file_off = m_off;
+        const size_t file_off = m_off;
+        auto pwrite_all = [this](const char* q, size_t k, size_t at) { put_all(q, k, at); };
         for (int k = 0; k < parts; ++k) {
             const size_t lo = std::min(total, per * k), hi = std::min(total, per * (k + 1));
             auto work = [=] {
@@ -323,17 +333,17 @@ public:
                     const size_t k2 = std::min(runs[i].len - skip, hi - pos);
                     const char* src = base + runs[i].off + skip;
                     if (k2 >= (1u << 20)) {                     // long stretch: straight from the source
-                        if (!buf.empty()) { pwrite_all(fd, buf.data(), buf.size(), file_off + buf_at); buf.clear(); }
-                        pwrite_all(fd, src, k2, file_off + pos);
+                        if (!buf.empty()) { pwrite_all(buf.data(), buf.size(), file_off + buf_at); buf.clear(); }
+                        pwrite_all(src, k2, file_off + pos);
                         buf_at = pos + k2;
                     } else {
                         if (buf.empty()) { buf.reserve(kBuf); buf_at = pos; }
-                        if (buf.size() + k2 > kBuf) { pwrite_all(fd, buf.data(), buf.size(), file_off + buf_at); buf_at += buf.size(); buf.clear(); }
+                        if (buf.size() + k2 > kBuf) { pwrite_all(buf.data(), buf.size(), file_off + buf_at); buf_at += buf.size(); buf.clear(); }
                         buf.insert(buf.end(), src, src + k2);
                     }
                     pos += k2;
                 }
-                if (!buf.empty()) pwrite_all(fd, buf.data(), buf.size(), file_off + buf_at);
+                if (!buf.empty()) pwrite_all(buf.data(), buf.size(), file_off + buf_at);
                 { std::lock_guard<std::mutex> g(join->mu); --join->left; }
                 join->cv.notify_all();
             };
@@ -342,6 +352,8 @@ public:
         { std::unique_lock<std::mutex> g(join->mu); join->cv.wait(g, [&] { return join->left == 0; }); }
         m_off += total;
     }
+    // errno of the first failed write of a plain output (0 = none); the drivers turn it into a failed run after close()
+    int error() const { return m_err.load(); }
     void close() {
         if (m_sink) { m_sink->finish(); m_sink.reset(); }
         if (m_g) { gzclose(m_g); m_g = nullptr; }
@@ -350,17 +362,22 @@ public:
     }
 private:
     static constexpr size_t kBuf = 4u << 20;
-    static void pwrite_all(int fd, const char* p, size_t n, size_t off) {
+    // Regular files: pwrite at the offset the bytes belong to (several workers at once).  Anything else: write() in
+    // call order (write_runs takes its sequential path there).  The first failure is kept for error().
+    void put_all(const char* p, size_t n, size_t off) {
         while (n) {
-            ssize_t w = ::pwrite(fd, p, n, (off_t)off);
-            if (w <= 0) return;                                  // a failed write is not reported (nor does the reference)
+            const ssize_t w = m_seekable ? ::pwrite(m_fd, p, n, (off_t)off) : ::write(m_fd, p, n);
+            if (w < 0 && errno == EINTR) continue;
+            if (w <= 0) { int expected = 0; m_err.compare_exchange_strong(expected, w < 0 ? errno : EIO); return; }
             p += w; n -= (size_t)w; off += (size_t)w;
         }
     }
     void flush() {
-        if (m_fd >= 0 && !m_wbuf.empty()) { pwrite_all(m_fd, m_wbuf.data(), m_wbuf.size(), m_off); m_off += m_wbuf.size(); m_wbuf.clear(); }
+        if (m_fd >= 0 && !m_wbuf.empty()) { put_all(m_wbuf.data(), m_wbuf.size(), m_off); m_off += m_wbuf.size(); m_wbuf.clear(); }
     }
     bool m_gz;
+    bool m_seekable = false;
+    std::atomic<int> m_err{0};
     FILE* m_f = nullptr;
     gzFile m_g = nullptr;
     int m_fd = -1;

@@ -229,3 +229,43 @@ def test_prefetched_pushes_match_plain_pushes(fqd, oracle):
         assert (st.total, st.dups) == (est.total, est.dups)
     finally:
         eng.close()
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_key_store_grows_in_place(fqd, oracle, paired):
+    """max_records far below the input (what the host passes for a pipe, whose size it cannot know): the engine grows the
+    key store and rehashes the table between chunks instead of failing - several times in a row (round-1: restart)."""
+    if paired:
+        s1, s2 = synth.make_pair(30000, seed=41, read_len=100, dup_frac=0.3)
+        _check_pe(fqd, oracle, synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2), fqd.FORMAT_FASTQ, chunk_bytes=1 << 17, max_records=700)
+    else:
+        seqs = synth.make_reads(60000, seed=42, read_len=150, var_len=True, n_frac=0.02, dup_frac=0.4)
+        _check_se(fqd, oracle, synth.to_fastq(seqs), fqd.FORMAT_FASTQ, chunk_bytes=1 << 18, max_records=1000)
+
+
+def test_async_pushes_keep_the_first_error(fqd):
+    """fqd_push_device_async does not read anything back per chunk; a data error in ANY chunk must still be reported by
+    fqd_sync (round 1 looked at the last chunk only)."""
+    seqs = synth.make_reads(9000, seed=43, read_len=100)
+    seqs[1234] = seqs[1234][:50] + b"Z" + seqs[1234][51:]
+    buf = synth.to_fastq(seqs)
+    cut = [0]
+    for _ in range(2):                          # three chunks, cut at record boundaries
+        cut.append(buf.index(b"\n@SYN.", cut[-1] + len(buf) // 4) + 1)
+    cut.append(len(buf))
+    dbuf = fqd.DeviceBuffer(len(buf) + 4096)
+    eng = fqd.Engine("fast", fqd.FORMAT_FASTQ, max_seq_len=100, max_records=10000, max_chunk_bytes=len(buf) + 4096)
+    off = 0
+    parts = []
+    for a, b in zip(cut[:-1], cut[1:]):
+        o = (off + 15) & ~15
+        dbuf.upload(buf[a:b], o)
+        parts.append((o, b - a))
+        off = o + (b - a)
+    for o, n in parts:
+        eng.push_device_async(dbuf.ptr + o, n)
+    eng.sync()
+    st = eng.stats()
+    assert st.err == 6 and st.err_record == 1234 and st.err_char == ord("Z")
+    eng.close()
+    dbuf.free()

@@ -236,3 +236,20 @@ def test_large_cross_mode_properties(fqd):
     eng.close()
     for d in raw:
         d.free()
+
+
+@pytest.mark.parametrize("mode,dist,paired,unordered", [("tight", 2, False, False), ("tail-hamming", 2, True, False), ("fast", 2, True, True)])
+def test_record_tables_grow_in_place(fqd, oracle, mode, dist, paired, unordered):
+    """max_records far below the input (a pipe has no size): the record tables and key rows grow while the input streams in."""
+    kw = dict(read_len=50, var_len=True, min_len=5, n_frac=0.02, prefix_frac=0.2, sub_frac=0.2, dup_frac=0.4)
+    if paired:
+        s1, s2 = synth.make_pair(7000, seed=51, **kw)
+        b1, b2 = synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2)
+    else:
+        b1, b2 = synth.to_fastq(synth.make_reads(9000, seed=52, **kw)), None
+    if unordered:
+        o1, o2, st = fqd.dedup_whole("fast", b1, b2, fqd.FORMAT_FASTQ, unordered=True, max_seq_len=50, seg_bytes=1 << 16, max_records=300)
+        e1, e2, est = oracle.run_oracle("fast", oracle.FASTQ, b1, b2, unordered=True)
+        assert (o1, o2) == (e1, e2) and (st.total, st.dups, st.unmatched) == (est.total, est.dups, est.unmatched)
+    else:
+        _check(fqd, oracle, mode, b1, b2, fqd.FORMAT_FASTQ, dist=dist, max_seq_len=50, seg_bytes=1 << 16, max_records=300)
