@@ -1,13 +1,17 @@
 #!/usr/bin/env python
-"""bench.py - throughput of the --fast deduplication hot path on B200 (contract in the build prompt).
+"""bench.py - throughput of the deduplication hot paths on B200 (contract in the build prompt).
 
   python bench.py --gpus N --steps K --warmup W            our arm (CUDA through the C ABI)
   python bench.py --impl reference --gpus N --steps K ...   the reference's own CPU implementation (oracle/_ref)
 
-A "step" is one whole job: the hash set is emptied, then every read of the workload goes through
-parse+pack -> insert -> count, with the raw FASTQ already resident in HBM (`value`), or pushed from pinned host
-memory through fqd_push with the per-chunk results copied back (`e2e`).  Workload = BASELINE.json configs[1]:
-synthetic 100 M x 150 bp single-end FASTQ, 30 % exact duplicates (32.2 GB, far larger than the 126 MB L2).
+Headline (`value`, `e2e`, `roofline`, `cpu_baseline`): BASELINE.json configs[1] - synthetic 100 M x 150 bp single-end
+FASTQ, 30 % exact duplicates (32.2 GB, far larger than the 126 MB L2), `--fast`.  A "step" is one whole job: the hash set
+is emptied, then every read goes through parse+pack -> insert -> duplicate count -> survivor index list, with the raw
+FASTQ already resident in HBM (`value`), or pushed from pinned host memory through fqd_push_* with the per-chunk
+results copied back (`e2e`).  In the same run the first 3 M reads go through the unmodified reference binary
+(`cpu_baseline`) and our output on them must be byte-identical (`parity`).
+`modes`: the metric's own shape, 2 x 150 bp paired-end, through `--fast`, every `--compare-seq` mode and `--fast
+--unordered` (bench_modes.py) - each with its own value / roofline / e2e / cpu_baseline / parity.
 """
 from __future__ import annotations
 
@@ -138,39 +142,90 @@ def reference_arm(args):
                 "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
                 "config": workload_config(args, n_step),
                 "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": kind, "sample": sample},
+                "sample_reads_per_step": n_step, "host_cores": os.cpu_count(),
                 "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                "gpu_launches": 0}
+                "gpu_launches": 0, "modes": reference_modes(oracle, tmp) if kind == "reference" and not os.environ.get("FQD_BENCH_SKIP_MODES") else None}
         print(json.dumps(line), flush=True)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
 
-def workload_config(args, n_reads):
+def reference_modes(oracle, tmp):
+    """The reference binary on the metric's own shape (2 x 150 bp paired-end), one run per mode on a 1 M-pair prefix of the
+    CPU twin of the generator (exact duplicates; the loose / tail-hamming variants of the stream exist on the device
+    only - bench.py's own arm times the reference on those, next to its parity check)."""
+    gen = importlib.import_module("bench_synth")
+    n = int(os.environ.get("FQD_REF_MODE_PAIRS", 1_000_000))
+    (tmp / "m1.fq").write_bytes(gen.synth_fastq_cpu(0, n, READ_LEN, 1, 2, DUP_PERMILLE, N_PERMILLE))
+    (tmp / "m2.fq").write_bytes(gen.synth_fastq_cpu(0, n, READ_LEN, 2, 2, DUP_PERMILLE, N_PERMILLE))
+    out = {}
+    for mode, flags in (("fast_pe", ["--fast"]), ("tight", ["--compare-seq", "tight"]), ("loose", ["--compare-seq", "loose"]),
+                        ("tail-hamming", ["--compare-seq", "tail-hamming", "--distance", "2"]), ("unordered", ["--fast", "--unordered"])):
+        t0 = time.perf_counter()
+        r = subprocess.run([str(oracle.REF_BIN), "-i", "m1.fq", "-u", "m2.fq", "-o", "mo1.fq", "-p", "mo2.fq", "-m", "10240", *flags], cwd=tmp, capture_output=True)
+        dt = time.perf_counter() - t0
+        out[mode] = {"value": n / dt if r.returncode == 0 else None, "unit": "pairs/s", "cores": 1, "kind": "reference",
+                     "sample": f"first {n} pairs (exact duplicates), plain FASTQ on tmpfs, {' '.join(flags)} -m 10240, one run, wall clock"}
+    return out
+
+
+def workload_config(args, n_reads=None):
+    """Identical in both arms.  The reference arm cannot take the whole workload inside a bounded run (0.5 M reads/s: 200 s
+    per 100 M-read step), so it times the first reads of the SAME stream and reports a rate; how many is in its
+    `cpu_baseline.sample` / `sample_reads_per_step`."""
+    n_workload = int(os.environ.get("FQD_BENCH_READS", 100_000_000))
     return {"workload": "BASELINE configs[1]: synthetic 100Mx150bp single-end FASTQ, 30% exact duplicates, --fast",
-            "reads_per_step": int(n_reads), "read_len": READ_LEN, "record_bytes": REC_BYTES, "dup_fraction": DUP_PERMILLE / 1000,
-            "input": "larger than L2 (no flush needed)", "seed": SEED}
+            "reads_per_step": n_workload, "read_len": READ_LEN, "record_bytes": REC_BYTES, "dup_fraction": DUP_PERMILLE / 1000,
+            "input": "larger than L2 (no flush needed)", "seed": SEED,
+            "reference_arm": "a prefix of the same stream per step (bounded run; reads/s is a rate - the smaller set favours the reference's unordered_set)"}
 
 
 # ---------------------------------------------------------------------------------------------------------
-def cpu_baseline(n_sample=3_000_000):
+def cpu_baseline_and_parity(fqd, lib, dev, n_sample=3_000_000):
+    """First n_sample reads of the workload (downloaded from the device generator): the unmodified reference binary on one
+    core, wall clock (`cpu_baseline`), and this engine's output on the same bytes, which must be identical (`parity`)."""
+    import numpy as np
     sys.path.insert(0, str(ROOT / "oracle"))
     oracle = importlib.import_module("oracle")
-    gen = importlib.import_module("bench_synth")
     kind = "reference" if oracle.ref_available() else "port"
     tmp = Path(tempfile.mkdtemp(prefix="fqd_cpu_", dir="/dev/shm" if Path("/dev/shm").is_dir() else None))
     try:
-        buf = gen.synth_fastq_cpu(0, n_sample, READ_LEN, 1, SEED, DUP_PERMILLE, N_PERMILLE)
+        nbytes = n_sample * REC_BYTES
+        dbuf = fqd.DeviceBuffer(nbytes + 65536, dev)
+        for first in range(0, n_sample, 1_000_000):
+            cnt = min(1_000_000, n_sample - first)
+            assert lib.fqd_synth_fastq(dev, dbuf.ptr + first * REC_BYTES, first, cnt, READ_LEN, 1, SEED, DUP_PERMILLE, N_PERMILLE, 0) == 0
+        buf = dbuf.download(nbytes)
+        eng = fqd.Engine("fast", fqd.FORMAT_FASTQ, False, False, 2, READ_LEN, n_sample + 1024, nbytes + 65536, n_sample + 1024, dev)
+        eng.keep_survivors(True)
+        res = eng.push_device(dbuf.ptr, nbytes)
+        assert res.n_records == n_sample
+        idx, _, _ = eng.survivors()
+        st = eng.stats()
+        eng.close()
+        dbuf.free()
+        ours = np.frombuffer(buf, dtype=np.uint8).reshape(n_sample, REC_BYTES)[idx.astype(np.int64)].tobytes()
         inp = tmp / "in.fq"
         inp.write_bytes(buf)
         t0 = time.perf_counter()
         if kind == "reference":
-            res = subprocess.run([str(oracle.REF_BIN), "-i", str(inp), "-o", str(tmp / "out.fq"), "--fast"], cwd=tmp, capture_output=True)
-            assert res.returncode == 0, res.stderr.decode()
+            r = subprocess.run([str(oracle.REF_BIN), "-i", str(inp), "-o", str(tmp / "out.fq"), "--fast", "-v"], cwd=tmp, capture_output=True)
+            assert r.returncode == 0, r.stderr.decode()
+            dt = time.perf_counter() - t0
+            exp, exp_line = (tmp / "out.fq").read_bytes(), r.stdout.decode()
         else:
-            oracle.fast_se(buf, oracle.FASTQ)
-        dt = time.perf_counter() - t0
-        return {"value": n_sample / dt, "unit": UNIT, "cores": 1, "kind": kind,
-                "sample": f"first {n_sample} reads of the same synthetic stream ({n_sample * REC_BYTES / 1e9:.2f} GB plain FASTQ on tmpfs), --fast, one run, wall clock"}
+            eidx, est = oracle.fast_se(buf, oracle.FASTQ)
+            dt = time.perf_counter() - t0
+            exp = np.frombuffer(buf, dtype=np.uint8).reshape(n_sample, REC_BYTES)[eidx.astype(np.int64)].tobytes()
+            exp_line = f"{est.total} reads processed, out of which {est.dups} duplicates were removed.\n"
+        line = f"{st.total} reads processed, out of which {st.dups} duplicates were removed.\n"
+        parity = {"checked": True, "records": n_sample, "against": "oracle/_ref/fastq-dupaway (unmodified reference sources)" if kind == "reference" else "oracle port",
+                  "bytes_identical": ours == exp, "summary_line_identical": line == exp_line, "output_bytes": len(ours)}
+        parity["ok"] = parity["bytes_identical"] and parity["summary_line_identical"]
+        assert parity["ok"], parity
+        cpu = {"value": n_sample / dt, "unit": UNIT, "cores": 1, "kind": kind,
+               "sample": f"first {n_sample} reads of the same synthetic stream ({nbytes / 1e9:.2f} GB plain FASTQ on tmpfs), --fast, one run, wall clock"}
+        return cpu, parity
     finally:
         shutil.rmtree(tmp, ignore_errors=True)
 
@@ -204,6 +259,7 @@ def our_arm(args):
         assert rc == 0
     eng = fqd.Engine("fast", fqd.FORMAT_FASTQ, False, False, 2, READ_LEN, n_total + 1024, chunk_reads * REC_BYTES + 65536,
                      chunk_reads + 1024, dev)
+    eng.keep_survivors(True)         # device time = first kernel start -> survivor list ready
 
     def step_device():
         eng.reset()
@@ -235,6 +291,8 @@ def our_arm(args):
     sampler.join()
     st = eng.stats()
     assert st.err == 0 and st.total == n_total and st.dups == dups
+    _, n_surv, _ = eng.survivors(fetch=False)
+    assert n_surv == n_total - dups, (n_surv, n_total, dups)
     ms_per_step = ms_total / args.steps
     value = n_total / (ms_per_step / 1000.0)
 
@@ -247,7 +305,10 @@ def our_arm(args):
                 "alg_bytes_per_read": K1_BYTES_PER_READ, "reads_per_launch": reads_per_launch, "avg_launch_ms": k1_ms,
                 "kernel_share_of_step": prof.parse_ms / ms_total if ms_total else None,
                 "insert_share_of_step": prof.insert_ms / ms_total if ms_total else None,
-                "whole_path_input_GBps": n_total * REC_BYTES / (ms_per_step / 1000.0) / 1e9}
+                "whole_path_input_GBps": n_total * REC_BYTES / (ms_per_step / 1000.0) / 1e9,
+                "whole_path": {"alg_bytes_per_read": 454, "alg_bytes_source": "SURVEY.md 8d (fast SE)", "this_build_bytes_per_read": 488 + 6,
+                               "achieved": n_total * 454 / (ms_per_step / 1000.0) / 1e9, "frac": n_total * 454 / (ms_per_step / 1000.0) / 1e9 / peak,
+                               "timed": "parse+pack, insert, duplicate count, survivor index list of every chunk of a job"}}
     tr = ROOT / "profiles" / "traffic.json"
     if tr.exists():
         try:
@@ -268,12 +329,18 @@ def our_arm(args):
     eng.close()
     raw.free()
 
-    cpu = None if os.environ.get("FQD_BENCH_SKIP_CPU") else cpu_baseline()
+    cpu, parity = (None, {"checked": False, "why": "FQD_BENCH_SKIP_CPU"}) if os.environ.get("FQD_BENCH_SKIP_CPU") else cpu_baseline_and_parity(fqd, lib, dev)
+    modes = None
+    if not os.environ.get("FQD_BENCH_SKIP_MODES"):
+        bm = importlib.import_module("bench_modes")
+        want = [m for m in os.environ.get("FQD_BENCH_MODES", "").split(",") if m] or None
+        modes = bm.run_modes(fqd, lib, args, dev, (peak, peak_kind), want)
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": workload_config(args, n_total), "clocks": sampler.summary(),
-            "e2e": e2e, "gpu_launches": int((l1 - l0)), "roofline": roofline, "cpu_baseline": cpu,
-            "duplicates_removed": int(dups), "input_GBps": n_total * REC_BYTES / (ms_per_step / 1000.0) / 1e9}
+            "e2e": e2e, "gpu_launches": int((l1 - l0)), "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
+            "duplicates_removed": int(dups), "survivors_listed": int(n_surv), "input_GBps": n_total * REC_BYTES / (ms_per_step / 1000.0) / 1e9,
+            "modes": modes}
     print(json.dumps(line), flush=True)
 
 

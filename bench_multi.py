@@ -1,142 +1,207 @@
-"""bench.py's N > 1 path: --fast deduplication of ONE global read stream sharded by hash range over N GPUs.
+"""bench.py's N > 1 path: deduplication of ONE global read stream sharded over the N GPUs of one box, one process per GPU.
+
+Headline (`value`): `--fast` on single-end reads, hash-range sharding (fastq-dupaway_b200/sharded2.py, csrc/shard2.cuh).
 Weak scaling: every rank contributes FQD_BENCH_READS reads (default 100 M x 150 bp = 32.2 GB in its HBM); the global
-stream is N times that, and duplicates reference ANY earlier read of the global stream, so the all-to-all is real."""
+stream is N times that and duplicates reference ANY earlier read of the global stream, so the exchange is real.  Timed on
+the device (CUDA events over both streams of every rank), max over ranks.  Outside the timed region rank 0 pushes the
+same global stream through ONE single-GPU engine and the duplicate counts must agree (`verify`).
+`modes`: the metric's own shape (2 x 150 bp paired-end) - `--fast` through the same sharded path, and every
+`--compare-seq` mode through key-range sharding (fastq-dupaway_b200/sharded_seq.py, bench_seq.py)."""
 from __future__ import annotations
 
 import importlib
 import json
 import os
 import sys
+import time
 from pathlib import Path
 
 ROOT = Path(__file__).resolve().parent
 
 
-def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
+def _sharded_fast(args, fqd, lib, sharded2, dist, gloo, rank, dev, world, n_per_rank, paired, seed, steps, warmup, b):
+    """One sharded --fast workload; returns (ms_per_step max over ranks, duplicates of the global stream, profile, launches, engine bits)."""
     import torch
-    b = importlib.import_module("bench")
-    sharded = importlib.import_module("fastq-dupaway_b200.sharded")
-    lib = fqd.load_library()
-    dev = local_rank
-    torch.cuda.set_device(dev)
     REC = b.REC_BYTES
-    chunk_reads = int(os.environ.get("FQD_BENCH_CHUNK_READS", 10_000_000))     # < 4 GiB per chunk (u32 offsets); fewer, larger chunks amortise the per-chunk collectives
+    chunk_reads = int(os.environ.get("FQD_BENCH_CHUNK_READS", 10_000_000 if not paired else 5_000_000))
     n_chunks = (n_per_rank + chunk_reads - 1) // chunk_reads
-    raw = fqd.DeviceBuffer(n_per_rank * REC + 65536, dev)
-    # chunk c of rank r = global reads [(c*world + r) * chunk_reads, ...): chunks are fed in global input order
+    mates = 2 if paired else 1
+    raw = [fqd.DeviceBuffer(n_per_rank * REC + 65536, dev) for _ in range(mates)]
+    # chunk c of rank r = global records [(c*world + r) * chunk_reads, ...): chunks are dealt round-robin in global input order
     sizes = []
     for c in range(n_chunks):
         cnt = min(chunk_reads, n_per_rank - c * chunk_reads)
         first_global = (c * world + rank) * chunk_reads
-        rc = lib.fqd_synth_fastq(dev, raw.ptr + c * chunk_reads * REC, first_global, cnt, b.READ_LEN, 1, b.SEED, b.DUP_PERMILLE, b.N_PERMILLE, 0)
-        assert rc == 0
+        for m in range(mates):
+            assert lib.fqd_synth_fastq(dev, raw[m].ptr + c * chunk_reads * REC, first_global, cnt, b.READ_LEN, m + 1, seed, b.DUP_PERMILLE, b.N_PERMILLE, 0) == 0
         sizes.append(cnt)
-    # every rank owns 1/world of the key space: ~n_per_rank rows arrive here (+ imbalance margin)
-    eng = fqd.Engine("fast", fqd.FORMAT_FASTQ, False, False, 2, b.READ_LEN, int(n_per_rank * 1.15) + (1 << 20),
+    region = sharded2.region_rows_for(chunk_reads, world)
+    region = (region + 15) // 16 * 16
+    eng = fqd.Engine("fast", fqd.FORMAT_FASTQ, paired, False, 2, b.READ_LEN, n_chunks * world * region + 1024,
                      chunk_reads * REC + 65536, chunk_reads + 1024, dev)
-    ops = sharded.GpuShardOps(fqd, eng, world, dev, chunk_reads + 1024)
-    peer = None
-    packers, peers2 = None, None
-    pipelined = not os.environ.get("FQD_NO_PEER") and not os.environ.get("FQD_NO_PIPELINE")
-    if not os.environ.get("FQD_NO_PEER"):
-        px = importlib.import_module("fastq-dupaway_b200.peer")
-        cap = int((chunk_reads + 1024) * ops.row_bytes * 1.25) + (16 << 20)
-        if pipelined:
-            # two pack-only engines on their own streams work one chunk ahead of the exchange; two receive buffers
-            peers2 = [px.PeerExchange(fqd, dist, rank, world, dev, cap) for _ in range(2)]
-            pengs = [fqd.Engine("fast", fqd.FORMAT_FASTQ, False, False, 2, b.READ_LEN, 1 << 16, chunk_reads * REC + 65536,
-                                chunk_reads + 1024, dev) for _ in range(2)]
-            packers = [sharded.GpuShardOps(fqd, e, world, dev, chunk_reads + 1024, own_stream=True) for e in pengs]
-            ops.pack(raw.ptr, 0)                      # sets the main engine up for fqd_shard_insert
-        else:
-            peer = px.PeerExchange(fqd, dist, rank, world, dev, cap)
-    chunks = [(raw.ptr + c * chunk_reads * REC, sizes[c] * REC) for c in range(n_chunks)]
+    ops = sharded2.GpuShard2Ops(fqd, eng, world, rank, region)
+    sharded2.connect(ops, dist, rank, world)
+    chunks = [tuple(x for m in range(mates) for x in (raw[m].ptr + c * chunk_reads * REC, sizes[c] * REC)) for c in range(n_chunks)]
+
+    def barrier():
+        dist.barrier(group=gloo)
 
     def step():
-        eng.reset()
-        if pipelined:
-            return sharded.exchange_pipelined(packers, ops, dist, world, chunks, peers2)
-        dups = 0
-        for c in range(n_chunks):
-            d, _ = sharded.exchange_chunk(ops, dist, world, chunks[c][0], chunks[c][1], peer=peer)
-            dups += d
-        return dups
+        barrier()
+        ops.reset()
+        barrier()
+        return sharded2.run_job(ops, barrier, chunks)
 
-    for _ in range(max(3, args.warmup)):
-        dups = step()
-    torch.cuda.synchronize()
-    dist.barrier()
+    for _ in range(warmup):
+        total, dups = step()
+    assert total == n_per_rank
+    barrier()
+    eng.profile_enable(True)
+    _, l0 = eng.device_time_ms()
+    ops.timer_start()
+    for _ in range(steps):
+        total2, dups2 = step()
+    ms_local = ops.timer_stop()
+    barrier()
+    assert (total2, dups2) == (total, dups)
+    ms = torch.tensor([ms_local], dtype=torch.float64, device=f"cuda:{dev}")
+    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    tot = torch.tensor([dups, total], dtype=torch.int64, device=f"cuda:{dev}")
+    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+    _, l1 = eng.device_time_ms()
+    prof = eng.profile()
+    eng.profile_enable(False)
+    res = {"ms_per_step": float(ms.item()) / steps, "dups": int(tot[0].item()), "total": int(tot[1].item()), "prof": prof, "launches": int(l1 - l0),
+           "chunk_reads": chunk_reads, "region_rows": region, "row_bytes": 64 * mates + 8, "ms_total": float(ms.item())}
+    barrier()
+    eng.close()
+    for r in raw:
+        r.free()
+    barrier()
+    return res
+
+
+def _single_gpu_duplicates(fqd, lib, dev, world, n_per_rank, chunk_reads, paired, seed, b):
+    """The same global stream through ONE engine on this GPU (generated chunk by chunk into a scratch buffer)."""
+    REC = b.REC_BYTES
+    mates = 2 if paired else 1
+    n_total = world * n_per_rank
+    scratch = [fqd.DeviceBuffer(chunk_reads * REC + 65536, dev) for _ in range(mates)]
+    eng = fqd.Engine("fast", fqd.FORMAT_FASTQ, paired, False, 2, b.READ_LEN, n_total + 1024, chunk_reads * REC + 65536, chunk_reads + 1024, dev)
+    n_chunks_rank = (n_per_rank + chunk_reads - 1) // chunk_reads
+    for c in range(n_chunks_rank):
+        cnt = min(chunk_reads, n_per_rank - c * chunk_reads)
+        for r in range(world):                               # global input order: chunk c of rank 0, 1, ...
+            first_global = (c * world + r) * chunk_reads
+            for m in range(mates):
+                assert lib.fqd_synth_fastq(dev, scratch[m].ptr, first_global, cnt, b.READ_LEN, m + 1, seed, b.DUP_PERMILLE, b.N_PERMILLE, 0) == 0
+            res = eng.push_device(scratch[0].ptr, cnt * REC, scratch[1].ptr if paired else None, cnt * REC if paired else 0)
+            assert res.n_records == cnt
+    st = eng.stats()
+    assert st.err == 0 and st.total == n_total, (st.err, st.total)
+    eng.close()
+    for s_ in scratch:
+        s_.free()
+    return int(st.dups)
+
+
+def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
+    import torch
+    b = importlib.import_module("bench")
+    sharded2 = importlib.import_module("fastq-dupaway_b200.sharded2")
+    lib = fqd.load_library()
+    dev = local_rank
+    torch.cuda.set_device(dev)
+    gloo = dist.new_group(backend="gloo")                 # host barriers (pure CPU: nothing is launched on the GPUs for them)
+    REC = b.REC_BYTES
     sampler = b.ClockSampler(dev)
     if rank == 0:
         sampler.start()
-    eng.profile_enable(True)
-    if pipelined:
-        for e in pengs:
-            e.profile_enable(True)
-    _, l0 = eng.device_time_ms()
-    if pipelined:
-        l0 += sum(e.device_time_ms()[1] for e in pengs)
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    dist.barrier()
-    e0.record()
-    for _ in range(args.steps):
-        d2 = step()
-    e1.record()
-    torch.cuda.synchronize()
-    dist.barrier()
-    assert d2 == dups
-    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{dev}")
-    dist.all_reduce(ms, op=dist.ReduceOp.MAX)
-    tot = torch.tensor([dups, n_per_rank], dtype=torch.int64, device=f"cuda:{dev}")
-    dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-    _, l1 = eng.device_time_ms()
-    if pipelined:
-        l1 += sum(e.device_time_ms()[1] for e in pengs)
-    prof = eng.profile()
-    if pipelined:                                     # K1 runs on the pack engines, K2 on the main one
-        for e in pengs:
-            pp = e.profile()
-            prof.parse_ms += pp.parse_ms; prof.parse_launches += pp.parse_launches; prof.parse_bytes += pp.parse_bytes
+    r = _sharded_fast(args, fqd, lib, sharded2, dist, gloo, rank, dev, world, n_per_rank, False, b.SEED, args.steps, max(3, args.warmup), b)
     if rank == 0:
         sampler.stop_flag.set()
         sampler.join()
-        ms_per_step = float(ms.item()) / args.steps
-        n_total = int(tot[1].item())
+    verify = None
+    if not os.environ.get("FQD_BENCH_SKIP_VERIFY"):
+        if rank == 0:
+            try:
+                single = _single_gpu_duplicates(fqd, lib, dev, world, n_per_rank, r["chunk_reads"], False, b.SEED, b)
+                verify = {"single_gpu_duplicates": single, "sharded_duplicates": r["dups"], "equal": single == r["dups"],
+                          "how": "rank 0 pushed the same global stream (chunks in global input order) through one single-GPU engine, outside the timed region"}
+            except Exception as ex:
+                verify = {"equal": None, "error": repr(ex)}
+        dist.barrier(group=gloo)
+        if rank == 0 and verify.get("equal") is False:
+            raise AssertionError(f"sharded duplicate count differs from the single-GPU run: {verify}")
+
+    modes = None
+    if not os.environ.get("FQD_BENCH_SKIP_MODES"):
+        modes = {}
+        n_pairs = int(os.environ.get("FQD_BENCH_PAIRS_PER_GPU", 25_000_000))        # configs[2]: 200 M pairs at N = 8
+        msteps = max(1, min(args.steps, int(os.environ.get("FQD_BENCH_MODE_STEPS", 2))))
+        peak, peak_kind = b.measured_peak_gbs()
+        t0 = time.perf_counter()
+        pe = _sharded_fast(args, fqd, lib, sharded2, dist, gloo, rank, dev, world, n_pairs, True, 2, msteps, 1, b)
+        pv = None
+        if rank == 0 and not os.environ.get("FQD_BENCH_SKIP_VERIFY"):
+            try:
+                single = _single_gpu_duplicates(fqd, lib, dev, world, n_pairs, pe["chunk_reads"], True, 2, b)
+                pv = {"single_gpu_duplicates": single, "sharded_duplicates": pe["dups"], "equal": single == pe["dups"]}
+            except Exception as ex:
+                pv = {"equal": None, "error": repr(ex)}
+        dist.barrier(group=gloo)
+        if rank == 0:
+            assert pv is None or pv.get("equal") is not False, pv
+            ach = pe["total"] * 860 / (pe["ms_per_step"] / 1e3) / 1e9
+            modes["fast_pe"] = {"value": pe["total"] / (pe["ms_per_step"] / 1e3), "unit": "pairs/s", "reads_per_s": 2 * pe["total"] / (pe["ms_per_step"] / 1e3),
+                                "ms_per_step": pe["ms_per_step"], "steps": msteps, "pairs_per_gpu": n_pairs, "pairs_total": pe["total"],
+                                "duplicates_removed": pe["dups"], "verify": pv, "gpu_launches": pe["launches"],
+                                "roofline": {"bound": "hbm", "kernel": "whole path", "achieved": ach, "peak": peak * world, "peak_kind": peak_kind, "unit": "GB/s",
+                                             "frac": ach / (peak * world), "alg_bytes_per_pair": 860, "alg_bytes_source": "SURVEY.md 8d"},
+                                "parallelism": f"hash-range x{world}", "leg_wall_s": round(time.perf_counter() - t0, 1)}
+        bs = importlib.import_module("bench_seq")
+        for mode in ("tight", "loose", "tail-hamming"):
+            t0 = time.perf_counter()
+            try:
+                line = bs.run_mode_multi(fqd, lib, mode, int(os.environ.get("FQD_BENCH_SEQ_PAIRS_PER_GPU", 20_000_000)), msteps, emit=False)
+            except Exception as ex:
+                line = {"value": None, "unit": "pairs/s", "error": repr(ex)}
+            if rank == 0:
+                if line.get("value"):
+                    ach = line["pairs_total"] * 1068 / (line["ms_per_step"] / 1e3) / 1e9
+                    line["roofline"] = {"bound": "hbm", "kernel": "whole path", "achieved": ach, "peak": peak * world, "peak_kind": peak_kind, "unit": "GB/s",
+                                        "frac": ach / (peak * world), "alg_bytes_per_pair": 1068, "alg_bytes_source": "SURVEY.md 8d"}
+                line["leg_wall_s"] = round(time.perf_counter() - t0, 1)
+                modes[mode] = line
+        modes["unordered"] = {"value": None, "unit": "pairs/s", "note": "--fast --unordered runs on one GPU (bench.py --gpus 1); across GPUs it is not built"}
+
+    if rank == 0:
+        prof = r["prof"]
+        ms_per_step = r["ms_per_step"]
+        n_total = r["total"]
         value = n_total / (ms_per_step / 1000.0)
         peak, peak_kind = b.measured_peak_gbs()
         k1_ms = prof.parse_ms / max(1, prof.parse_launches)
         rpl = (prof.parse_bytes / max(1, prof.parse_launches)) / REC
         achieved = rpl * b.K1_BYTES_PER_READ / (k1_ms / 1000.0) / 1e9 if k1_ms > 0 else 0.0
-        row_bytes = ops.row_bytes
         line = {"metric": b.METRIC, "value": value, "unit": b.UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
-                "data": "synthetic", "config": dict(b.workload_config(args, n_total), parallelism=f"hash-range x{world}",
-                                                     reads_per_gpu=n_per_rank, chunk_reads=chunk_reads),
+                "data": "synthetic", "config": dict(b.workload_config(args), parallelism=f"hash-range x{world}",
+                                                     reads_per_gpu=n_per_rank, chunk_reads=r["chunk_reads"]),
                 "clocks": sampler.summary(),
                 "e2e": {"value": None, "unit": b.UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
                         "note": "end-to-end (host buffers) is measured at N=1; the N>1 arm measures the sharded device path"},
-                "gpu_launches": int(l1 - l0),
+                "gpu_launches": r["launches"],
                 "roofline": {"bound": "hbm", "kernel": "k_parse_pack<4>", "achieved": achieved, "peak": peak, "peak_kind": peak_kind,
                              "unit": "GB/s", "frac": achieved / peak, "traffic": None, "alg_bytes_per_read": b.K1_BYTES_PER_READ,
-                             "avg_launch_ms": k1_ms, "kernel_share_of_step": prof.parse_ms / float(ms.item()),
-                             "insert_share_of_step": prof.insert_ms / float(ms.item())},
-                "exchange": {"row_bytes": row_bytes, "alltoall_bytes_per_gpu_per_step": n_per_rank * (row_bytes + 1),
-                             "collectives_per_chunk": 3,
-                             "rows": ("mapped peer memory (CUDA IPC + copy engines), overlapped with the split + pack of the next chunk" if pipelined
-                                      else "mapped peer memory (CUDA IPC + copy engines)" if peer is not None else "NCCL all_to_all_single")},
-                "duplicates_removed": int(tot[0].item()), "input_GBps": n_total * REC / (ms_per_step / 1000.0) / 1e9}
+                             "avg_launch_ms": k1_ms, "kernel_share_of_step": prof.parse_ms / r["ms_total"],
+                             "insert_share_of_step": prof.insert_ms / r["ms_total"],
+                             "note": "rank 0's K1 launches, timed while the other stream of the same GPU inserts the previous chunk"},
+                "exchange": {"row_bytes": r["row_bytes"], "bytes_over_nvlink_per_gpu_per_step": int(n_per_rank * (r["row_bytes"] + 1) * (world - 1) / world),
+                             "region_rows": r["region_rows"], "host_barriers_per_chunk": 1,
+                             "rows": "written by the scatter kernel straight into the owners' key-store regions over mapped peer memory (CUDA IPC, NVLink stores "
+                                     "from the SMs); flags written back the same way; ordering by interprocess CUDA events"},
+                "verify": verify, "duplicates_removed": r["dups"], "input_GBps": n_total * REC / (ms_per_step / 1000.0) / 1e9, "modes": modes}
         print(json.dumps(line), flush=True)
-    if rank == 0 and sharded.TRACE:
-        print("[fqd trace] per-phase wall clock, ms over all steps:", json.dumps({k: round(v, 2) for k, v in sharded.TRACE.items()}), file=sys.stderr)
-    eng.close()
-    if peer is not None:
-        peer.close()
-    if pipelined:
-        for e in pengs:
-            e.close()
-        for p_ in peers2:
-            p_.close()
-    raw.free()
-    dist.barrier()
+    dist.barrier(group=gloo)
     dist.destroy_process_group()

@@ -96,7 +96,7 @@ def run_mode(fqd, lib, mode, n_pairs, steps, dev=0):
     return line
 
 
-def run_mode_multi(fqd, lib, mode, n_pairs_per_rank, steps):
+def run_mode_multi(fqd, lib, mode, n_pairs_per_rank, steps, emit=True):
     """N > 1 (under torchrun): weak scaling, every rank contributes n_pairs_per_rank pairs of ONE global stream
     (rank r holds pairs [r * n, (r + 1) * n)); key-range sharding through fastq-dupaway_b200/sharded_seq.py."""
     import torch
@@ -147,6 +147,7 @@ def run_mode_multi(fqd, lib, mode, n_pairs_per_rank, steps):
     tot = torch.tensor(list(res), dtype=torch.int64, device=f"cuda:{dev}")
     own = [torch.zeros_like(tot) for _ in range(world)]
     dist.all_gather(own, tot)
+    line = {}
     if rank == 0:
         ms = sum(times) / len(times)
         total = world * n
@@ -162,7 +163,8 @@ def run_mode_multi(fqd, lib, mode, n_pairs_per_rank, steps):
                 "imbalance": max(owned) / (sum(owned) / world), "input_GBps": total * 2 * REC / (ms / 1e3) / 1e9,
                 "alltoall_bytes_per_gpu": n * 2 * REC,
                 "exchange": "mapped peer memory (CUDA IPC + copy engines)" if peer is not None else "NCCL all_to_all_single"}
-        print(json.dumps(line), flush=True)
+        if emit:
+            print(json.dumps(line), flush=True)
         if sh.TRACE:
             print("[fqd trace] ms over all steps:", json.dumps({k: round(v, 1) for k, v in sh.TRACE.items()}), file=sys.stderr)
             sh.TRACE.clear()
@@ -172,6 +174,7 @@ def run_mode_multi(fqd, lib, mode, n_pairs_per_rank, steps):
             px_.close()
     for s_ in raw:
         s_.free()
+    return line
 
 
 def cpu_reference(mode, n_pairs):

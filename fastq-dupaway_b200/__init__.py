@@ -103,6 +103,8 @@ def load_library():
     lib.fqd_push_device_async.argtypes = [vp, vp, sz, vp, sz]
     lib.fqd_sync.argtypes = [vp]
     lib.fqd_reset.argtypes = [vp]
+    lib.fqd_keep_survivors.argtypes = [vp, C.c_int]
+    lib.fqd_survivors.argtypes = [vp, u64, vp, u64, C.POINTER(u64), C.POINTER(vp)]
     lib.fqd_timer_start.argtypes = [vp]
     lib.fqd_timer_stop.argtypes = [vp, C.POINTER(C.c_double)]
     lib.fqd_profile_enable.argtypes = [vp, C.c_int]
@@ -243,6 +245,20 @@ class Engine:
 
     def reset(self):
         self._check(self.lib.fqd_reset(self.h))
+
+    def keep_survivors(self, on=True):
+        self._check(self.lib.fqd_keep_survivors(self.h, int(on)))
+
+    def survivors(self, fetch=True):
+        """-> (numpy uint64 array of the written records' global indices | None, count, device pointer of the list)"""
+        n, dp = C.c_uint64(0), C.c_void_p()
+        self._check(self.lib.fqd_survivors(self.h, 0, None, 0, C.byref(n), C.byref(dp)))
+        arr = None
+        if fetch:
+            arr = np.empty(int(n.value), dtype=np.uint64)
+            if n.value:
+                self._check(self.lib.fqd_survivors(self.h, 0, arr.ctypes.data_as(C.c_void_p), int(n.value), None, None))
+        return arr, int(n.value), dp.value
 
     def timer_start(self):
         self._check(self.lib.fqd_timer_start(self.h))

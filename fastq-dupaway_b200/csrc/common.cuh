@@ -22,7 +22,7 @@ constexpr int BASES_PER_WORD = 20;
 
 // Per-chunk control block written by the kernels, read back by the host (or by later kernels).
 struct ChunkCtl {
-    u32 ticket;            // dynamic tile ordering for the decoupled look-back
+    u32 ticket;            // unused since round 2 (tiles are taken in block-index order)
     u32 n_newlines;        // total '\n' in the chunk (written by the last tile)
     u32 n_records;         // complete records parsed (<= capacity)
     u32 consumed;          // bytes covered by those records

@@ -16,6 +16,7 @@
 #include "parse_pack.cuh"
 #include "seqmode.cuh"
 #include "shard.cuh"
+#include "shard2.cuh"
 #include "synth.cuh"
 
 using namespace fqd;
@@ -31,6 +32,28 @@ struct MateChunk {
     u32* h_rec_start = nullptr;   // pinned
     ChunkCtl* h_ctl = nullptr;    // pinned
     u32 n_tiles_cap = 0;
+};
+
+struct Shard2State {
+    u32 N = 0, me = 0, region_rows = 0, n_blocks_cap = 0;
+    u32 *d_block_cnt = nullptr, *d_block_base = nullptr, *d_dest[2] = {nullptr, nullptr}, *d_totals = nullptr;
+    u64 *d_final_hash = nullptr, *d_stage_keys = nullptr;
+    RunState *d_stage_run = nullptr, *d_run2 = nullptr, *h_run2 = nullptr;
+    u64* d_hash_regions = nullptr;      // [2][N * region_rows]   written by my peers (and me)
+    u32* d_counts = nullptr;            // [2][S2_MAX]            rows per source, written by my peers
+    u8* d_flags = nullptr;              // [N * region_rows]      what k_insert2 decides
+    u8* d_flags_in = nullptr;           // [2][N * region_rows]   flags of MY records, written by their owners
+    unsigned long long* d_ndups = nullptr;
+    u32* h_totals = nullptr;
+    u32* d_chunk_n = nullptr;           // [2] records of the chunk packed with this parity
+    cudaStream_t s_pack = nullptr, s_ins = nullptr;
+    cudaEvent_t ev_scatter[2] = {nullptr, nullptr}, ev_flags[2] = {nullptr, nullptr};
+    u64* peer_keys[S2_MAX] = {}; u64* peer_hash[S2_MAX] = {}; u32* peer_counts[S2_MAX] = {}; u8* peer_flags_in[S2_MAX] = {};
+    cudaEvent_t peer_scatter[S2_MAX][2] = {}, peer_flags[S2_MAX][2] = {};
+    bool imported[S2_MAX] = {};
+    u64 chunks_packed = 0, chunks_inserted = 0, chunks_applied = 0;
+    u32 last_n = 0;
+    cudaEvent_t t_ins = nullptr;
 };
 
 struct fqd_handle {
@@ -80,6 +103,9 @@ struct fqd_handle {
     u64 recv_cap = 0;
     u64 shard_last_n = 0;
     u32 grows = 0;                   // times the key store / table were grown in place
+    struct Shard2State* s2 = nullptr; // multi-GPU --fast mode, round 2 (shard2.cuh)
+    u64* d_surv = nullptr;           // fqd_keep_survivors: global indices of the written records, ascending
+    u32* d_surv_cnt = nullptr;       // survivors per SV_BLOCK records of the current chunk
 };
 
 #define CUDA_TRY(h, call)                                                                      \
@@ -158,10 +184,13 @@ static u32 words_for(u32 max_seq_len, bool byte_keys = false) {
     return (w + 1u) & ~1u;      // even, so rows are 16-byte aligned
 }
 
+static void shard2_free(fqd_handle* h);
+
 extern "C" void fqd_destroy(fqd_handle* h) {
     if (!h) return;
     cudaSetDevice(h->cfg.device);
     if (h->stream) cudaStreamSynchronize(h->stream);
+    shard2_free(h);
     if (h->seq) seq_destroy(h->seq);
     if (h->shard_ctx) {
         seq_free_results(h->shard_ctx); delete h->shard_ctx;
@@ -178,7 +207,7 @@ extern "C" void fqd_destroy(fqd_handle* h) {
         if (c.h_rec_start) cudaFreeHost(c.h_rec_start);
         if (c.h_ctl) cudaFreeHost(c.h_ctl);
     }
-    cudaFree(h->d_keys); cudaFree(h->d_table); cudaFree(h->d_run); cudaFree(h->d_dup);
+    cudaFree(h->d_keys); cudaFree(h->d_table); cudaFree(h->d_run); cudaFree(h->d_dup); cudaFree(h->d_surv); cudaFree(h->d_surv_cnt);
     if (h->h_run) cudaFreeHost(h->h_run);
     if (h->h_dup) cudaFreeHost(h->h_dup);
     for (int k = 0; k < 2; ++k) { cudaFree(h->d_raw_alt[k]); if (h->copy_done[k]) cudaEventDestroy(h->copy_done[k]); }
@@ -284,6 +313,7 @@ static int launch_parse(fqd_handle* h, int m, const u8* d_raw, size_t n, u8* d_d
     cudaEvent_t pe0 = nullptr, pe1 = nullptr;
     if (h->profile) { pe0 = get_event(h); pe1 = get_event(h); cudaEventRecord(pe0, h->stream); }
     pp_launch(h->cfg.format == FQD_FORMAT_FASTQ, p, h->stream);
+    h->launches += 2;                 // + the two head kernels of pp_launch
     if (h->profile) { cudaEventRecord(pe1, h->stream); h->prof_parse.emplace_back(pe0, pe1); h->prof.parse_launches++; h->prof.parse_bytes += n; }
     h->launches++;
     return FQD_OK;
@@ -309,6 +339,12 @@ static int enqueue_fast_chunk(fqd_handle* h, const void* d_r1, size_t n1, const 
     insert_launch(ip, h->sm_count * 8, h->stream);
     if (h->profile) { cudaEventRecord(ie1, h->stream); h->prof_insert.emplace_back(ie0, ie1); h->prof.insert_launches++; }
     k_count_dups<<<h->sm_count * 2, HS_THREADS, 0, h->stream>>>(h->d_dup, h->d_run);
+    if (h->d_surv) {
+        const unsigned sb = (h->cap + SV_BLOCK - 1) / SV_BLOCK;
+        k_surv_count<<<sb, HS_THREADS, 0, h->stream>>>(h->d_dup, h->d_run, h->d_surv_cnt);
+        k_surv_write<<<sb, HS_THREADS, 0, h->stream>>>(h->d_dup, h->d_run, h->d_surv_cnt, h->d_surv, h->key_capacity);
+        h->launches += 2;
+    }
     k_chunk_end<<<1, 1, 0, h->stream>>>(h->d_run, h->mate[0].d_ctl, paired ? h->mate[1].d_ctl : nullptr);
     h->launches += 4;
     CUDA_TRY(h, cudaEventRecord(e1, h->stream));
@@ -427,6 +463,12 @@ static int grow_fast(fqd_handle* h, u64 need) {
     CUDA_TRY(h, cudaMemsetAsync(&r->capacity_exceeded, 0, sizeof(u32), h->stream));
     CUDA_TRY(h, cudaMemsetAsync(&r->sticky_set, 0, sizeof(u32), h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (h->d_surv) {
+        u64* sv = nullptr;
+        if (cudaMalloc(&sv, cap * sizeof(u64)) != cudaSuccess) { cudaGetLastError(); cudaFree(keys); cudaFree(table); return fail(h, FQD_ERR_CAPACITY, "no device memory left to grow the survivor list"); }
+        CUDA_TRY(h, cudaMemcpy(sv, h->d_surv, h->h_run->n_survivors * sizeof(u64), cudaMemcpyDeviceToDevice));
+        cudaFree(h->d_surv); h->d_surv = sv;
+    }
     cudaFree(h->d_keys); h->d_keys = keys; h->key_capacity = cap;
     if (table) { cudaFree(h->d_table); h->d_table = table; h->n_buckets = nb; h->bucket_shift = shift; }
     h->grows++;
@@ -630,6 +672,36 @@ extern "C" int fqd_profile_get(fqd_handle* h, fqd_profile_t* out) {
     return FQD_OK;
 }
 
+extern "C" int fqd_keep_survivors(fqd_handle* h, int on) {
+    if (!h) return FQD_ERR_INVALID;
+    if (h->cfg.mode != FQD_MODE_FAST || h->cfg.unordered) return fail(h, FQD_ERR_INVALID, "fqd_keep_survivors is for ordered --fast mode (fqd_emission lists the written records of the other modes)");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    if (on && !h->d_surv) {
+        if (h->stats.total || h->pending_async) return fail(h, FQD_ERR_INVALID, "fqd_keep_survivors: enable it before the first chunk (or after fqd_reset)");
+        CUDA_TRY(h, cudaMalloc(&h->d_surv, h->key_capacity * sizeof(u64)));
+        CUDA_TRY(h, cudaMalloc(&h->d_surv_cnt, ((size_t)h->cap / SV_BLOCK + 2) * sizeof(u32)));
+    } else if (!on && h->d_surv) {
+        cudaFree(h->d_surv); cudaFree(h->d_surv_cnt); h->d_surv = nullptr; h->d_surv_cnt = nullptr;
+    }
+    return FQD_OK;
+}
+extern "C" int fqd_survivors(fqd_handle* h, uint64_t first, uint64_t* dst, uint64_t cap, uint64_t* n_total, const uint64_t** d_list) {
+    if (!h || !h->d_surv) return fail(h, FQD_ERR_INVALID, "fqd_survivors: call fqd_keep_survivors(h, 1) before the first chunk");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (h->pending_async) { int rc = fqd_sync(h); if (rc) return rc; }
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_run, h->d_run, sizeof(RunState), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    const u64 n = h->h_run->n_survivors;
+    if (n_total) *n_total = n;
+    if (d_list) *d_list = (const uint64_t*)h->d_surv;
+    if (dst && first < n) {
+        const u64 k = std::min<u64>(cap, n - first);
+        CUDA_TRY(h, cudaMemcpy(dst, h->d_surv + first, k * sizeof(u64), cudaMemcpyDeviceToHost));
+    }
+    return FQD_OK;
+}
+
 extern "C" int fqd_reset(fqd_handle* h) {
     if (!h) return FQD_ERR_INVALID;
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
@@ -705,6 +777,7 @@ static int shard_pack_impl(fqd_handle* h, const void* d_raw, size_t n, const voi
         p.strict = 1; p.hash_salt = m * 4096u; p.dup = nullptr; p.bad_rec = nullptr; p.byte_keys = 0; p.skip = 0;
         if (n_tiles) {
             pp_launch(h->cfg.format == FQD_FORMAT_FASTQ, p, h->stream);
+            h->launches += 2;
         }
         if (h->profile) { h->prof.parse_launches++; h->prof.parse_bytes += nb; }
     }
@@ -795,6 +868,337 @@ extern "C" int fqd_shard_read_flags(fqd_handle* h, void* dst, size_t n) {
     CUDA_TRY(h, cudaSetDevice(h->cfg.device));
     CUDA_TRY(h, cudaMemcpyAsync(dst, h->d_dup, n, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return FQD_OK;
+}
+
+
+// -----------------------------------------------------------------------------------------------------------
+// multi-GPU --fast mode, round 2 (shard2.cuh): regions in the owners' key stores, rows written over peer memory by the
+// scatter kernel, ordering by interprocess events.  Call sequence per rank (host barriers of the caller marked |):
+//   fqd_shard2_init; fqd_shard2_export -> all-gather -> fqd_shard2_import for every rank |
+//   pack(0) | for every chunk c: [pack(c+1)] insert(c) | apply(c)        ... fqd_shard2_finish
+// Every call only enqueues; a barrier makes sure that an event has been RECORDED (enqueued) by its owner before a peer
+// enqueues the wait for it (cudaStreamWaitEvent waits for the most recent record at the time of the call).
+struct Shard2Blob { cudaIpcMemHandle_t keys, hash, counts, flags_in; cudaIpcEventHandle_t scatter[2], flags[2]; };
+
+static void shard2_free(fqd_handle* h) {
+    Shard2State* s = h->s2;
+    if (!s) return;
+    cudaSetDevice(h->cfg.device);
+    if (s->s_pack) cudaStreamSynchronize(s->s_pack);
+    if (s->s_ins) cudaStreamSynchronize(s->s_ins);
+    for (u32 r = 0; r < s->N; ++r) {
+        if (r == s->me || !s->imported[r]) continue;
+        cudaIpcCloseMemHandle(s->peer_keys[r]); cudaIpcCloseMemHandle(s->peer_hash[r]); cudaIpcCloseMemHandle(s->peer_counts[r]); cudaIpcCloseMemHandle(s->peer_flags_in[r]);
+        for (int k = 0; k < 2; ++k) { cudaEventDestroy(s->peer_scatter[r][k]); cudaEventDestroy(s->peer_flags[r][k]); }
+    }
+    cudaFree(s->d_block_cnt); cudaFree(s->d_block_base); cudaFree(s->d_dest[0]); cudaFree(s->d_dest[1]); cudaFree(s->d_totals);
+    cudaFree(s->d_final_hash); cudaFree(s->d_stage_keys); cudaFree(s->d_stage_run); cudaFree(s->d_run2); cudaFree(s->d_hash_regions);
+    cudaFree(s->d_counts); cudaFree(s->d_flags); cudaFree(s->d_flags_in); cudaFree(s->d_ndups); cudaFree(s->d_chunk_n);
+    if (s->h_run2) cudaFreeHost(s->h_run2);
+    if (s->h_totals) cudaFreeHost(s->h_totals);
+    for (int k = 0; k < 2; ++k) { if (s->ev_scatter[k]) cudaEventDestroy(s->ev_scatter[k]); if (s->ev_flags[k]) cudaEventDestroy(s->ev_flags[k]); }
+    if (s->t_ins) cudaEventDestroy(s->t_ins);
+    if (s->s_pack) cudaStreamDestroy(s->s_pack);
+    if (s->s_ins) cudaStreamDestroy(s->s_ins);
+    delete s; h->s2 = nullptr;
+}
+
+extern "C" size_t fqd_shard2_blob_bytes(void) { return sizeof(Shard2Blob); }
+
+extern "C" int fqd_shard2_init(fqd_handle* h, uint32_t n_shards, uint32_t me, uint32_t region_rows) {
+    if (!h || n_shards == 0 || n_shards > S2_MAX || me >= n_shards || region_rows == 0) return FQD_ERR_INVALID;
+    if (h->cfg.mode != FQD_MODE_FAST || h->cfg.unordered) return fail(h, FQD_ERR_INVALID, "sharded path: ordered --fast only");
+    if (h->s2) return fail(h, FQD_ERR_INVALID, "fqd_shard2_init: already initialised");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    region_rows = (region_rows + 15u) & ~15u;
+    if (region_rows >= (1u << 27)) return fail(h, FQD_ERR_INVALID, "fqd_shard2_init: region_rows must be below 2^27");
+    Shard2State* s = new Shard2State();
+    h->s2 = s;
+    s->N = n_shards; s->me = me; s->region_rows = region_rows;
+    s->n_blocks_cap = (h->cap + S2_BLOCK - 1) / S2_BLOCK;
+    const size_t reg = (size_t)n_shards * region_rows;
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&s->s_pack, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaStreamCreateWithFlags(&s->s_ins, cudaStreamNonBlocking));
+    CUDA_TRY(h, cudaMalloc(&s->d_block_cnt, (size_t)s->n_blocks_cap * S2_MAX * sizeof(u32)));
+    CUDA_TRY(h, cudaMalloc(&s->d_block_base, (size_t)s->n_blocks_cap * S2_MAX * sizeof(u32)));
+    for (int k = 0; k < 2; ++k) CUDA_TRY(h, cudaMalloc(&s->d_dest[k], (size_t)h->cap * sizeof(u32)));
+    CUDA_TRY(h, cudaMalloc(&s->d_totals, (S2_MAX + 1) * sizeof(u32)));
+    CUDA_TRY(h, cudaMemset(s->d_totals, 0, (S2_MAX + 1) * sizeof(u32)));
+    CUDA_TRY(h, cudaMalloc(&s->d_final_hash, (size_t)h->cap * sizeof(u64)));
+    CUDA_TRY(h, cudaMalloc(&s->d_stage_keys, (size_t)h->cap * h->row_words * sizeof(u64)));
+    CUDA_TRY(h, cudaMalloc(&s->d_stage_run, sizeof(RunState)));
+    CUDA_TRY(h, cudaMemset(s->d_stage_run, 0, sizeof(RunState)));
+    CUDA_TRY(h, cudaMalloc(&s->d_run2, sizeof(RunState)));
+    CUDA_TRY(h, cudaMemset(s->d_run2, 0, sizeof(RunState)));
+    CUDA_TRY(h, cudaHostAlloc(&s->h_run2, sizeof(RunState), cudaHostAllocDefault));
+    CUDA_TRY(h, cudaHostAlloc(&s->h_totals, (S2_MAX + 1) * sizeof(u32), cudaHostAllocDefault));
+    CUDA_TRY(h, cudaMalloc(&s->d_hash_regions, 2 * reg * sizeof(u64)));
+    CUDA_TRY(h, cudaMalloc(&s->d_counts, 2 * S2_MAX * sizeof(u32)));
+    CUDA_TRY(h, cudaMemset(s->d_counts, 0, 2 * S2_MAX * sizeof(u32)));
+    CUDA_TRY(h, cudaMalloc(&s->d_flags, reg));
+    CUDA_TRY(h, cudaMalloc(&s->d_flags_in, 2 * reg));
+    CUDA_TRY(h, cudaMalloc(&s->d_chunk_n, 2 * sizeof(u32)));
+    CUDA_TRY(h, cudaMalloc(&s->d_ndups, sizeof(unsigned long long)));
+    CUDA_TRY(h, cudaMemset(s->d_ndups, 0, sizeof(unsigned long long)));
+    for (int k = 0; k < 2; ++k) {
+        CUDA_TRY(h, cudaEventCreateWithFlags(&s->ev_scatter[k], cudaEventDisableTiming | cudaEventInterprocess));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&s->ev_flags[k], cudaEventDisableTiming | cudaEventInterprocess));
+    }
+    s->peer_keys[me] = h->d_keys; s->peer_hash[me] = s->d_hash_regions; s->peer_counts[me] = s->d_counts; s->peer_flags_in[me] = s->d_flags_in;
+    for (int k = 0; k < 2; ++k) { s->peer_scatter[me][k] = s->ev_scatter[k]; s->peer_flags[me][k] = s->ev_flags[k]; }
+    s->imported[me] = true;
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    return FQD_OK;
+}
+
+extern "C" int fqd_shard2_export(fqd_handle* h, void* blob) {
+    if (!h || !h->s2 || !blob) return FQD_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    Shard2State* s = h->s2;
+    Shard2Blob b;
+    memset(&b, 0, sizeof b);
+    CUDA_TRY(h, cudaIpcGetMemHandle(&b.keys, h->d_keys));
+    CUDA_TRY(h, cudaIpcGetMemHandle(&b.hash, s->d_hash_regions));
+    CUDA_TRY(h, cudaIpcGetMemHandle(&b.counts, s->d_counts));
+    CUDA_TRY(h, cudaIpcGetMemHandle(&b.flags_in, s->d_flags_in));
+    for (int k = 0; k < 2; ++k) {
+        CUDA_TRY(h, cudaIpcGetEventHandle(&b.scatter[k], s->ev_scatter[k]));
+        CUDA_TRY(h, cudaIpcGetEventHandle(&b.flags[k], s->ev_flags[k]));
+    }
+    memcpy(blob, &b, sizeof b);
+    return FQD_OK;
+}
+
+extern "C" int fqd_shard2_import(fqd_handle* h, uint32_t rank, const void* blob) {
+    if (!h || !h->s2 || !blob || rank >= h->s2->N) return FQD_ERR_INVALID;
+    Shard2State* s = h->s2;
+    if (rank == s->me) return FQD_OK;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    Shard2Blob b;
+    memcpy(&b, blob, sizeof b);
+    CUDA_TRY(h, cudaIpcOpenMemHandle((void**)&s->peer_keys[rank], b.keys, cudaIpcMemLazyEnablePeerAccess));
+    CUDA_TRY(h, cudaIpcOpenMemHandle((void**)&s->peer_hash[rank], b.hash, cudaIpcMemLazyEnablePeerAccess));
+    CUDA_TRY(h, cudaIpcOpenMemHandle((void**)&s->peer_counts[rank], b.counts, cudaIpcMemLazyEnablePeerAccess));
+    CUDA_TRY(h, cudaIpcOpenMemHandle((void**)&s->peer_flags_in[rank], b.flags_in, cudaIpcMemLazyEnablePeerAccess));
+    for (int k = 0; k < 2; ++k) {
+        CUDA_TRY(h, cudaIpcOpenEventHandle(&s->peer_scatter[rank][k], b.scatter[k]));
+        CUDA_TRY(h, cudaIpcOpenEventHandle(&s->peer_flags[rank][k], b.flags[k]));
+    }
+    s->imported[rank] = true;
+    return FQD_OK;
+}
+
+__global__ void k_shard2_chunk_end(RunState* run, const ChunkCtl* ctl1, const ChunkCtl* ctl2, u32* n_out) {
+    u32 n = ctl1->n_records;
+    if (ctl2) n = min(n, ctl2->n_records);
+    *n_out = n;
+    run->chunk_pairs = n; run->chunk_dups = 0;
+    if (!run->sticky_set) {
+        const ChunkCtl* c[2] = {ctl1, ctl2 ? ctl2 : ctl1};
+        bool any = false;
+        for (int m = 0; m < (ctl2 ? 2 : 1); ++m) any |= c[m]->err_parse != NO_ERR || c[m]->err_base != NO_ERR || (c[m]->too_long & TL_SEQ);
+        if (any) {
+            run->sticky_set = 1; run->sticky_pairs = n; run->sticky_first = run->n_records;
+            for (int m = 0; m < 2; ++m) {
+                run->sticky_parse[m] = c[m]->err_parse; run->sticky_base[m] = c[m]->err_base;
+                run->sticky_too_long[m] = c[m]->too_long; run->sticky_too_long_rec[m] = c[m]->too_long_rec;
+            }
+        }
+    }
+    run->n_records += n;
+}
+
+// split + pack chunk number `chunk` of THIS rank's input and scatter its rows to their owners.  Chunks are numbered
+// alike on every rank; chunk c of rank r holds the records that follow chunk c of rank r - 1 in the global input.
+extern "C" int fqd_shard2_pack(fqd_handle* h, uint64_t chunk, const void* d_r1, size_t n1, const void* d_r2, size_t n2) {
+    if (!h || !h->s2) return FQD_ERR_INVALID;
+    Shard2State* s = h->s2;
+    const int mates = h->cfg.paired ? 2 : 1;
+    if ((mates == 2) != (d_r2 != nullptr)) return fail(h, FQD_ERR_INVALID, "paired handle needs both chunks, single-end handle one");
+    if (n1 > h->cfg.max_chunk_bytes || n2 > h->cfg.max_chunk_bytes) return fail(h, FQD_ERR_INVALID, "chunk larger than max_chunk_bytes");
+    if (chunk != s->chunks_packed) return fail(h, FQD_ERR_INVALID, "fqd_shard2_pack: chunks must be packed in order");
+    for (u32 r = 0; r < s->N; ++r) if (!s->imported[r]) return fail(h, FQD_ERR_INVALID, "fqd_shard2_pack: a peer has not been imported");
+    if ((chunk + 1) * s->N * (u64)s->region_rows > h->key_capacity) return fail(h, FQD_ERR_CAPACITY, "fqd_shard2_pack: the key store has no region left for this chunk");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const int par = (int)(chunk & 1);
+    cudaStream_t st = s->s_pack;
+    // the regions of this parity are free once every owner has sent back the flags of chunk - 2
+    if (chunk >= 2) for (u32 r = 0; r < s->N; ++r) CUDA_TRY(h, cudaStreamWaitEvent(st, s->peer_flags[r][par], 0));
+    cudaEvent_t pe0 = nullptr, pe1 = nullptr;
+    if (h->profile) { pe0 = get_event(h); pe1 = get_event(h); cudaEventRecord(pe0, st); }
+    for (int m = 0; m < mates; ++m) {
+        MateChunk& c = h->mate[m];
+        const u8* raw = (const u8*)(m ? d_r2 : d_r1);
+        const size_t nb = m ? n2 : n1;
+        const u32 n_tiles = (u32)((nb + PP_TILE - 1) / PP_TILE);
+        k_init_chunk<<<std::max(1u, std::min(n_tiles / 256 + 1, 1024u)), 256, 0, st>>>(c.d_ctl, c.d_tile_state, n_tiles);
+        ParseParams p;
+        p.raw = raw; p.n = (u32)nb; p.n_tiles = n_tiles; p.tile_state = c.d_tile_state; p.ctl = c.d_ctl; p.run = s->d_stage_run;
+        p.rec_start = c.d_rec_start; p.cap = h->cap; p.keys = s->d_stage_keys; p.key_capacity = h->cap;
+        p.row_words = h->row_words; p.mate_off = m * h->W; p.W = h->W; p.hash = c.d_hash; p.seq_len = nullptr; p.word0 = nullptr;
+        p.strict = 1; p.hash_salt = m * 4096u; p.dup = nullptr; p.bad_rec = nullptr; p.byte_keys = 0; p.skip = 0;
+        if (n_tiles) { pp_launch(h->cfg.format == FQD_FORMAT_FASTQ, p, st); h->launches += 2; }
+        if (h->profile) { h->prof.parse_launches++; h->prof.parse_bytes += nb; }
+        h->launches += 2;
+    }
+    if (h->profile) { cudaEventRecord(pe1, st); h->prof_parse.emplace_back(pe0, pe1); }
+    Shard2Src sp;
+    memset(&sp, 0, sizeof sp);
+    sp.stage_keys = s->d_stage_keys; sp.row_words = h->row_words; sp.hash1 = h->mate[0].d_hash; sp.hash2 = mates == 2 ? h->mate[1].d_hash : nullptr;
+    sp.ctl1 = h->mate[0].d_ctl; sp.ctl2 = mates == 2 ? h->mate[1].d_ctl : nullptr; sp.n_shards = s->N; sp.me = s->me;
+    sp.region_rows = s->region_rows; sp.chunk = chunk; sp.block_cnt = s->d_block_cnt; sp.block_base = s->d_block_base;
+    sp.dest = s->d_dest[par]; sp.final_hash = s->d_final_hash; sp.totals = s->d_totals;
+    const size_t reg = (size_t)s->N * s->region_rows;
+    for (u32 r = 0; r < s->N; ++r) {
+        sp.peer_keys[r] = s->peer_keys[r]; sp.peer_hash[r] = s->peer_hash[r] + (size_t)par * reg; sp.peer_counts[r] = s->peer_counts[r] + (size_t)par * S2_MAX;
+    }
+    k_shard_count2<<<s->n_blocks_cap, 256, 0, st>>>(sp);
+    k_shard_bases2<<<1, 256, 0, st>>>(sp, s->n_blocks_cap);
+    k_shard_scatter2<<<s->n_blocks_cap, 256, 0, st>>>(sp);
+    k_shard2_chunk_end<<<1, 1, 0, st>>>(s->d_run2, sp.ctl1, sp.ctl2, s->d_chunk_n + par);
+    h->launches += 4;
+    CUDA_TRY(h, cudaEventRecord(s->ev_scatter[par], st));
+    s->chunks_packed++;
+    CUDA_TRY(h, cudaGetLastError());
+    return FQD_OK;
+}
+
+// owner side of chunk `chunk`: every source's rows are in my key store once their scatter events have fired
+extern "C" int fqd_shard2_insert(fqd_handle* h, uint64_t chunk) {
+    if (!h || !h->s2) return FQD_ERR_INVALID;
+    Shard2State* s = h->s2;
+    if (chunk != s->chunks_inserted) return fail(h, FQD_ERR_INVALID, "fqd_shard2_insert: chunks must be inserted in order");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const int par = (int)(chunk & 1);
+    cudaStream_t st = s->s_ins;
+    for (u32 r = 0; r < s->N; ++r) CUDA_TRY(h, cudaStreamWaitEvent(st, s->peer_scatter[r][par], 0));
+    const size_t reg = (size_t)s->N * s->region_rows;
+    CUDA_TRY(h, cudaMemsetAsync(s->d_flags, 0, reg, st));
+    Insert2Params ip;
+    ip.table = h->d_table; ip.bucket_shift = h->bucket_shift; ip.bucket_mask = h->n_buckets - 1; ip.keys = h->d_keys; ip.row_words = h->row_words;
+    ip.hash = s->d_hash_regions + (size_t)par * reg; ip.counts = s->d_counts + (size_t)par * S2_MAX; ip.n_shards = s->N; ip.region_rows = s->region_rows;
+    ip.chunk = chunk; ip.flags = s->d_flags; ip.run = s->d_run2;
+    cudaEvent_t ie0 = nullptr, ie1 = nullptr;
+    if (h->profile) { ie0 = get_event(h); ie1 = get_event(h); cudaEventRecord(ie0, st); }
+    const unsigned g = (unsigned)h->sm_count * 8;
+    if (h->row_words == 8) k_insert2<8><<<g, HS_THREADS, 0, st>>>(ip);
+    else if (h->row_words == 16) k_insert2<16><<<g, HS_THREADS, 0, st>>>(ip);
+    else k_insert2<0><<<g, HS_THREADS, 0, st>>>(ip);
+    if (h->profile) { cudaEventRecord(ie1, st); h->prof_insert.emplace_back(ie0, ie1); h->prof.insert_launches++; }
+    FlagsBack2 fb;
+    memset(&fb, 0, sizeof fb);
+    fb.flags = s->d_flags; fb.counts = ip.counts; fb.n_shards = s->N; fb.region_rows = s->region_rows; fb.me = s->me;
+    for (u32 r = 0; r < s->N; ++r) fb.peer_flags[r] = s->peer_flags_in[r] + (size_t)par * reg;
+    k_shard_flags_send2<<<h->sm_count, 256, 0, st>>>(fb);
+    h->launches += 3;
+    CUDA_TRY(h, cudaEventRecord(s->ev_flags[par], st));
+    s->chunks_inserted++;
+    CUDA_TRY(h, cudaGetLastError());
+    return FQD_OK;
+}
+
+// source side again: the owners' flags for my records of chunk `chunk` -> h->d_dup (record order) + duplicate count
+extern "C" int fqd_shard2_apply(fqd_handle* h, uint64_t chunk) {
+    if (!h || !h->s2) return FQD_ERR_INVALID;
+    Shard2State* s = h->s2;
+    if (chunk != s->chunks_applied || chunk >= s->chunks_packed) return fail(h, FQD_ERR_INVALID, "fqd_shard2_apply: chunks must be applied in order, after their pack");
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    const int par = (int)(chunk & 1);
+    cudaStream_t st = s->s_pack;             // after this chunk's pack, before the pack that reuses its parity
+    for (u32 r = 0; r < s->N; ++r) CUDA_TRY(h, cudaStreamWaitEvent(st, s->peer_flags[r][par], 0));
+    const size_t reg = (size_t)s->N * s->region_rows;
+    // (the control blocks already belong to the next chunk's pack: the record count of this one was put aside)
+    k_shard_flags2<<<h->sm_count * 4, 256, 0, st>>>(s->d_flags_in + (size_t)par * reg, s->d_dest[par], s->d_chunk_n + par, s->region_rows, h->d_dup, s->d_ndups);
+    h->launches += 1;
+    s->chunks_applied++;
+    CUDA_TRY(h, cudaGetLastError());
+    return FQD_OK;
+}
+
+// waits for everything enqueued on this rank; totals of THIS rank's records; data errors / region overflow -> fqd_stats
+extern "C" int fqd_shard2_finish(fqd_handle* h, uint64_t* n_records, uint64_t* n_dups) {
+    if (!h || !h->s2) return FQD_ERR_INVALID;
+    Shard2State* s = h->s2;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(s->s_pack));
+    CUDA_TRY(h, cudaStreamSynchronize(s->s_ins));
+    unsigned long long nd = 0;
+    CUDA_TRY(h, cudaMemcpy(&nd, s->d_ndups, sizeof nd, cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(s->h_run2, s->d_run2, sizeof(RunState), cudaMemcpyDeviceToHost));
+    CUDA_TRY(h, cudaMemcpy(s->h_totals, s->d_totals, (S2_MAX + 1) * sizeof(u32), cudaMemcpyDeviceToHost));
+    drain_events(h);
+    h->stats.total = s->h_run2->n_records;
+    h->stats.dups = nd;
+    if (s->h_totals[S2_MAX]) { h->stats.err = FQD_ERR_CAPACITY; h->err = "a (chunk, source) region of an owner's key store overflowed: raise region_rows"; }
+    if (s->h_run2->sticky_set && !h->stats.err) {
+        const RunState& r = *s->h_run2;
+        const int mates = h->cfg.paired ? 2 : 1;
+        for (int m = 0; m < mates; ++m) {
+            ChunkCtl& c = *h->mate[m].h_ctl;
+            memset(&c, 0, sizeof c);
+            c.err_parse = r.sticky_parse[m]; c.err_base = r.sticky_base[m]; c.too_long = r.sticky_too_long[m]; c.too_long_rec = r.sticky_too_long_rec[m];
+        }
+        h->h_run->chunk_pairs = r.sticky_pairs; h->h_run->capacity_exceeded = 0;
+        u64 n_ok;
+        fold_chunk(h, r.sticky_first, &n_ok);
+    }
+    if (n_records) *n_records = h->stats.total;
+    if (n_dups) *n_dups = nd;
+    return FQD_OK;
+}
+
+// start a new job on the same handles (every rank, between two barriers): empty set, counters cleared
+extern "C" int fqd_shard2_reset(fqd_handle* h) {
+    if (!h || !h->s2) return FQD_ERR_INVALID;
+    Shard2State* s = h->s2;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(s->s_pack));
+    CUDA_TRY(h, cudaStreamSynchronize(s->s_ins));
+    CUDA_TRY(h, cudaMemsetAsync(h->d_table, 0xFF, h->n_buckets * 4 * sizeof(u64), s->s_ins));
+    CUDA_TRY(h, cudaMemsetAsync(s->d_run2, 0, sizeof(RunState), s->s_ins));
+    CUDA_TRY(h, cudaMemsetAsync(s->d_ndups, 0, sizeof(unsigned long long), s->s_ins));
+    CUDA_TRY(h, cudaMemsetAsync(s->d_totals, 0, (S2_MAX + 1) * sizeof(u32), s->s_ins));
+    CUDA_TRY(h, cudaStreamSynchronize(s->s_ins));
+    s->chunks_packed = s->chunks_inserted = s->chunks_applied = 0;
+    memset(&h->stats, 0, sizeof h->stats);
+    return FQD_OK;
+}
+
+// Stopwatch over BOTH streams of this rank: start records an event on the (idle) pack stream, stop records one at the end
+// of each stream, waits, and returns the longer interval - first kernel start to last kernel end on this GPU.
+extern "C" int fqd_shard2_timer_start(fqd_handle* h) {
+    if (!h || !h->s2) return FQD_ERR_INVALID;
+    Shard2State* s = h->s2;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    if (!h->timer0) { CUDA_TRY(h, cudaEventCreate(&h->timer0)); CUDA_TRY(h, cudaEventCreate(&h->timer1)); }
+    if (!s->t_ins) CUDA_TRY(h, cudaEventCreate(&s->t_ins));
+    CUDA_TRY(h, cudaStreamSynchronize(s->s_ins));
+    CUDA_TRY(h, cudaStreamSynchronize(s->s_pack));
+    CUDA_TRY(h, cudaEventRecord(h->timer0, s->s_pack));
+    return FQD_OK;
+}
+extern "C" int fqd_shard2_timer_stop(fqd_handle* h, double* ms) {
+    if (!h || !h->s2 || !h->timer0 || !h->s2->t_ins) return FQD_ERR_INVALID;
+    Shard2State* s = h->s2;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaEventRecord(h->timer1, s->s_pack));
+    CUDA_TRY(h, cudaEventRecord(s->t_ins, s->s_ins));
+    CUDA_TRY(h, cudaEventSynchronize(h->timer1));
+    CUDA_TRY(h, cudaEventSynchronize(s->t_ins));
+    float a = 0.f, b = 0.f;
+    CUDA_TRY(h, cudaEventElapsedTime(&a, h->timer0, h->timer1));
+    CUDA_TRY(h, cudaEventElapsedTime(&b, h->timer0, s->t_ins));
+    if (ms) *ms = std::max(a, b);
+    return FQD_OK;
+}
+
+// duplicate flags (record order) of the chunk last applied on this rank
+extern "C" int fqd_shard2_read_flags(fqd_handle* h, void* dst, size_t n) {
+    if (!h || !h->s2) return FQD_ERR_INVALID;
+    CUDA_TRY(h, cudaSetDevice(h->cfg.device));
+    CUDA_TRY(h, cudaStreamSynchronize(h->s2->s_pack));
+    CUDA_TRY(h, cudaMemcpy(dst, h->d_dup, n, cudaMemcpyDeviceToHost));
     return FQD_OK;
 }
 

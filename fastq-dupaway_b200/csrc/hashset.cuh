@@ -174,6 +174,72 @@ __global__ void __launch_bounds__(HS_THREADS) k_count_dups(const u8* dup, RunSta
     if (threadIdx.x == 0 && s_cnt) atomicAdd(&run->chunk_dups, s_cnt);
 }
 
+// Survivor list (fqd_keep_survivors): the global input indices of the records that are WRITTEN, ascending, appended chunk
+// by chunk - what the reference's `output << record` loop amounts to (src/hash_dup_remover.hpp:136-138,240-244).  Two
+// passes over the chunk's flag bytes: survivors per block of SV_BLOCK records, then every block sums the counts before it
+// (a few hundred values) and writes its indices at their ranks.
+constexpr u32 SV_BLOCK = 8192;
+__global__ void __launch_bounds__(HS_THREADS) k_surv_count(const u8* __restrict__ dup, const RunState* run, u32* __restrict__ block_cnt) {
+    __shared__ u32 s_cnt;
+    if (threadIdx.x == 0) s_cnt = 0;
+    __syncthreads();
+    const u32 n = run->chunk_pairs;
+    const u32 lo = blockIdx.x * SV_BLOCK, hi = min(n, lo + SV_BLOCK);
+    u32 c = 0;
+    for (u32 i = lo + threadIdx.x * 16u; i < hi; i += HS_THREADS * 16u) {
+        if (i + 16u <= hi) {
+            const uint4 v = *reinterpret_cast<const uint4*>(dup + i);
+            c += 16u - (__popc(v.x) + __popc(v.y) + __popc(v.z) + __popc(v.w));       // flags are 0/1 bytes
+        } else {
+            for (u32 j = i; j < hi; ++j) c += dup[j] ? 0u : 1u;
+        }
+    }
+    c = __reduce_add_sync(0xFFFFFFFFu, c);
+    if ((threadIdx.x & 31) == 0 && c) atomicAdd(&s_cnt, c);
+    __syncthreads();
+    if (threadIdx.x == 0) block_cnt[blockIdx.x] = s_cnt;
+}
+__global__ void __launch_bounds__(HS_THREADS) k_surv_write(const u8* __restrict__ dup, const RunState* run, const u32* __restrict__ block_cnt,
+                                                           u64* __restrict__ out, u64 out_cap) {
+    __shared__ u32 s_warp[HS_THREADS / 32];
+    __shared__ u32 s_before;
+    const u32 n = run->chunk_pairs;
+    const u32 lo = blockIdx.x * SV_BLOCK, hi = min(n, lo + SV_BLOCK);
+    if (lo >= n) return;
+    // survivors of this chunk before my block
+    u32 b = 0;
+    for (u32 j = threadIdx.x; j < blockIdx.x; j += HS_THREADS) b += block_cnt[j];
+    b = __reduce_add_sync(0xFFFFFFFFu, b);
+    if (threadIdx.x == 0) s_before = 0;
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0 && b) atomicAdd(&s_before, b);
+    // my SV_BLOCK / HS_THREADS consecutive records
+    constexpr u32 PER = SV_BLOCK / HS_THREADS;
+    const u32 first = lo + threadIdx.x * PER;
+    u32 keep = 0, c = 0;
+#pragma unroll 8
+    for (u32 k = 0; k < PER; ++k)
+        if (first + k < hi && !dup[first + k]) { keep |= 1u << k; ++c; }
+    u32 incl = c;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const u32 x = __shfl_up_sync(0xFFFFFFFFu, incl, d);
+        if ((threadIdx.x & 31) >= (u32)d) incl += x;
+    }
+    if ((threadIdx.x & 31) == 31) s_warp[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    u32 wbase = 0;
+    for (u32 w = 0; w < (threadIdx.x >> 5); ++w) wbase += s_warp[w];
+    u64 at = run->n_survivors + s_before + wbase + incl - c;
+    const u64 slot0 = run->n_records + first;
+    while (keep) {
+        const u32 k = (u32)__ffs((int)keep) - 1u;
+        keep &= keep - 1u;
+        if (at < out_cap) out[at] = slot0 + k;
+        ++at;
+    }
+}
+
 __global__ void k_chunk_end(RunState* run, const ChunkCtl* ctl1, const ChunkCtl* ctl2) {
     if (ctl1 && !run->sticky_set) {
         const ChunkCtl* c[2] = {ctl1, ctl2 ? ctl2 : ctl1};

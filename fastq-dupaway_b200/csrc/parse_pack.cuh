@@ -4,20 +4,18 @@
 // src/fastaview.cpp:75-93: 4 or 2 newline searches, '@'/'>' check, len(seq)==len(qual)) and
 // SeqUtils::seq2hash (src/seq_utils.cpp:35-49) for a whole chunk of raw bytes resident in HBM.
 //
-// One CTA handles one 16 KiB tile (+1 KiB halo) staged in shared memory by a 1-D bulk async copy (TMA);
-// tiles are taken in ticket order so that every predecessor of a tile is already running.
+// One CTA handles one 16 KiB tile (+1 KiB halo) staged in shared memory by a 1-D bulk async copy (TMA); tiles are
+// taken in block-index order.
+//   0. while the tile's bytes are in flight the CTA counts the newlines of the tile PP_LEAD ahead ("scout") and publishes
+//      the count; later warp 0 resolves that tile's prefix (decoupled look-back, 128 predecessors per hop) - so P, the
+//      number of newlines before the CTA's own tile, was resolved two CTA lifetimes before the CTA started
 //   1. newline bitmask of the window (SIMD-in-register byte compare, dp4a gathers the flags)
-//   2. block scan of per-thread newline counts -> local rank of every '\n'; the tile's count is published; positions
-//      are compacted by rank into shared memory
-//   3. warp 0: decoupled look-back across tiles (128 predecessors per hop) -> global rank P of the tile's first
-//      newline.  P modulo lines-per-record says which newline ends a record (the reference, too, simply counts 4 (2)
-//      newlines per record), P / lines-per-record is the index of the tile's first record.
-//   4. warps 1..7 do not wait for it: they guess P mod lines-per-record from the first bytes of the tile's lines, one
-//      thread per record owned by the tile (its first byte lies in the tile) derives its line ends from consecutive
-//      entries of the compacted positions and validates it, and groups of 4 lanes pack one sequence each into 3-bit
-//      codes (20 bases per 64-bit word, see common.cuh; or raw bytes, 8 per word: template parameter BYTES) in
-//      registers.  When P arrives the guess is verified (a wrong guess repeats the round) and everything is committed:
-//      record offsets, errors, 128-bit row stores, the multilinear key hash.
+//   2. block scan of per-thread newline counts -> local rank of every '\n'; positions compacted by rank into shared memory
+//   3. P modulo lines-per-record says which newline ends a record (the reference, too, simply counts 4 (2) newlines per
+//      record), P / lines-per-record is the index of the tile's first record.  Groups of 4 lanes take one record each
+//      (its first byte lies in the tile): line ends = consecutive entries of the compacted positions, validation, then
+//      the sequence is packed into 3-bit codes (20 bases per 64-bit word, see common.cuh; or raw bytes, 8 per word:
+//      template parameter BYTES) and committed: record offset, errors, 128-bit row stores, the multilinear key hash.
 #pragma once
 #include "common.cuh"
 
@@ -175,12 +173,10 @@ __device__ __forceinline__ u32 find_nl(const u64* mask64, u32 pos, const u8* raw
     return PP_NONE;
 }
 
-// ---- named barriers: warp 0 resolves the tile's newline rank (decoupled look-back) while warps 1..7 already split
-// and pack the records; BAR_POS = compacted newline positions complete, BAR_P = look-back result available,
-// BAR_WORK = warps 1..7 only
+// ---- named barrier: warps 1..7 leave their scout counts (arrive), warp 0 collects them (sync) when its look-back is done
 template <int ID, int N> __device__ __forceinline__ void bar_sync_c() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
 template <int ID, int N> __device__ __forceinline__ void bar_arrive_c() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
-enum { BAR_POS = 1, BAR_P = 2, BAR_WORK = 3 };
+enum { BAR_SCOUT = 1 };
 constexpr u32 PP_PACKERS = PP_THREADS - 32;        // threads of warps 1..7
 constexpr u32 PP_GROUP = 4;                        // lanes that pack one record (two key words each per 8 words)
 enum { RS_NONE = 0, RS_OK = 1, RS_BAD_START = 2, RS_LEN_MISMATCH = 3, RS_TOO_LONG = 4 };
@@ -287,39 +283,6 @@ __device__ __forceinline__ u64 pack_word(const u8* win, const ParseParams& p, u3
     return (po.word << shift) & 0x0FFFFFFFFFFFFFFFull;
 }
 
-// Which newline of the tile ends a record?  c = (rank of the tile's first newline) mod LPR decides it.  The exact
-// value comes from the look-back; this is a guess from the first bytes of up to 32 lines ('@' ... '+' for FASTQ,
-// '>' for FASTA) that lets the packers start before the look-back returns.  It is verified against the exact
-// value before anything is written; an ambiguous window returns PP_NONE (no speculation).
-template <int LPR>
-__device__ __forceinline__ u32 guess_phase(const u8* win, const u16* nlpos, u32 WN, u32 valid, u32 lane) {
-    bool ok = lane < WN;
-    u32 ch = 0;
-    if (ok) {
-        const u32 st = (u32)nlpos[lane] + 1u;
-        ok = st < valid;
-        if (ok) ch = win[st];
-    }
-    const u32 V = __ballot_sync(0xFFFFFFFFu, ok);
-    const u32 A = __ballot_sync(0xFFFFFFFFu, ok && ch == (LPR == 4 ? '@' : '>'));
-    const u32 B = __ballot_sync(0xFFFFFFFFu, ok && ch == '+');
-    u32 found = PP_NONE, n_ok = 0;
-#pragma unroll
-    for (u32 c = 0; c < (u32)LPR; ++c) {
-        bool good;
-        if (LPR == 4) {
-            const u32 m0 = 0x11111111u << (3u - c);                 // lines that must start a record
-            const u32 m2 = 0x11111111u << ((5u - c) & 3u);          // lines that must be the '+' line
-            good = (V & m0) != 0 && (V & m0 & ~A) == 0 && (V & m2 & ~B) == 0;
-        } else {
-            const u32 m0 = c == 0 ? 0xAAAAAAAAu : 0x55555555u;
-            good = (V & m0) != 0 && (V & m0 & ~A) == 0 && (V & ~m0 & A) == 0;
-        }
-        if (good) { found = c; ++n_ok; }
-    }
-    return n_ok == 1 ? found : PP_NONE;
-}
-
 // Per-record results of a pack group: PP_GROUP lanes reduce the key hash; lane 0 writes the per-record tables.
 __device__ __forceinline__ void commit_group(const ParseParams& p, u32 R, u32 nb, u32 l4, u32 gmask, u64 hsum, u64 w0, u32 bad) {
     hsum += __shfl_xor_sync(gmask, hsum, 1);
@@ -346,14 +309,12 @@ static inline cudaError_t pp_init_tables() {
     return cudaMemcpyToSymbol(c_hkeys, h, sizeof(h));
 }
 
-// ---- build-time experiments (profiles/r02_k1_variants.md): FQD_K1_TICKET=1 restores the atomic ticket of round 1,
-// FQD_K1_L2PF=<tiles> prefetches a later tile into L2 at CTA start, FQD_K1_TIMELINE records per-phase clocks.
-#ifndef FQD_K1_TICKET
-#define FQD_K1_TICKET 0
+// ---- build-time experiments (profiles/r02_k1_summary.md): FQD_K1_LEAD=<tiles> scout distance, FQD_K1_TIMELINE records
+// per-phase clocks of every TL_STRIDE-th tile.
+#ifndef FQD_K1_LEAD
+#define FQD_K1_LEAD 1480     // = 2 x the CTAs resident on 148 SMs (PP_MIN_CTAS each): the tile that starts about two CTA lifetimes from now
 #endif
-#ifndef FQD_K1_L2PF
-#define FQD_K1_L2PF 740      // tiles ahead = CTAs resident on 148 SMs (PP_MIN_CTAS each): what starts one CTA lifetime from now
-#endif
+constexpr u32 PP_LEAD = FQD_K1_LEAD;
 #ifdef FQD_K1_TIMELINE
 constexpr u32 TL_STRIDE = 61, TL_SLOTS = 12, TL_CAP = 4096;
 __device__ long long g_k1_timeline[TL_CAP * TL_SLOTS];
@@ -361,14 +322,68 @@ __device__ long long g_k1_timeline[TL_CAP * TL_SLOTS];
 #define TL_ENTRY() const long long tl_t0 = clock64()
 #define TL_STAMP0(cond) do { if ((cond) && tile % TL_STRIDE == 0 && tile / TL_STRIDE < TL_CAP) g_k1_timeline[(tile / TL_STRIDE) * TL_SLOTS] = tl_t0; } while (0)
 #else
+#define TL_STAMP(cond, k) do { } while (0)
 #define TL_ENTRY() do { } while (0)
 #define TL_STAMP0(cond) do { } while (0)
-#define TL_STAMP(cond, k) do { } while (0)
 #endif
+
+// Decoupled look-back (one warp): exclusive prefix of tile > 0 over the published per-tile newline counts.
+// tile_state[t] = flag << 32 | value; flag 1: value = count of tile t, flag 2: value = count of tiles 0..t.
+// 128 predecessors per hop (4 per lane): one L2 round trip must cover more tiles than the chip starts in that time.
+__device__ __forceinline__ u32 pp_lookback(const u64* tile_state, u32 tile, u32 lane) {
+    u32 P = 0;
+    int look = (int)tile - 1;
+    for (;;) {
+        u64 s4[4];
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+            int idx = look - (int)lane - 32 * r4;
+            s4[r4] = (2ull << 32);
+            if (idx >= 0) s4[r4] = ld_volatile_u64(tile_state + idx);
+        }
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+            int idx = look - (int)lane - 32 * r4;
+            while ((s4[r4] >> 32) == 0) s4[r4] = ld_volatile_u64(tile_state + idx);
+        }
+        bool found = false;
+#pragma unroll
+        for (int r4 = 0; r4 < 4; ++r4) {
+            if (!found) {
+                u32 is_prefix = __ballot_sync(0xFFFFFFFFu, (s4[r4] >> 32) == 2);
+                u32 val = (u32)s4[r4];
+                if (is_prefix) {
+                    u32 first = (u32)__ffs((int)is_prefix) - 1u;     // closest predecessor holding a prefix
+                    if (lane > first) val = 0;
+                    found = true;
+                }
+                P += __reduce_add_sync(0xFFFFFFFFu, val);
+            }
+        }
+        if (found) return P;
+        look -= 128;
+    }
+}
 
 // LPR = lines per record: 4 = FASTQ, 2 = FASTA.  BYTES = raw-byte key rows (ParseParams::byte_keys; sequence-based
 // modes on arbitrary alphabets) - a template parameter so that the 3-bit instantiation every other path uses carries
 // none of its code or registers.
+//
+// One CTA per tile, tiles in block-index order (the hardware starts the CTAs of a 1-D grid in index order, so every
+// predecessor of a tile is resident or done when the tile starts - the assumption every single-pass look-back scan makes).
+// The one thing a tile needs from its predecessors is P, the number of newlines before it.  Round 1 published a tile's
+// count after its own scan and hid the look-back behind a guess of P mod LPR; the packers still waited 3 500 cycles (of
+// a 14 600-cycle CTA life) for the slowest of ~400 neighbours, and the look-back itself never takes less than ~4 000
+// cycles (three L2 round trips: the nearest resolved prefix is as far away as the look-back is long).  So nobody waits
+// for it any more - every CTA works for a tile PP_LEAD ahead of its own (about two CTA lifetimes):
+//   * while its own tile is on its way through the TMA, all 8 warps count the newlines of that later tile ("scout":
+//     plain 16-byte loads, which also pull the tile into L2) and publish the count;
+//   * after the barriers of its own tile, warp 0 resolves that later tile's prefix by decoupled look-back and
+//     publishes it, while warps 1..7 split and pack the CTA's own tile.
+// A tile therefore finds its own prefix resolved long before it starts (one load), splits with the exact P - no guess, no
+// second round, no wait - and every spin in this kernel is on something published by a CTA that started earlier (the
+// first PP_LEAD tiles are resolved by k_scout_head / k_scan_head before the kernel starts): deadlock-free whatever the
+// number of resident CTAs.
 template <int LPR, bool BYTES = false>
 __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const ParseParams p) {
     __shared__ __align__(128) u8 win[PP_WINDOW];
@@ -378,9 +393,6 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     __shared__ u32 q_len[PP_QCAP];
     __shared__ uint2 s_hkey[PP_HKEYS];
     __shared__ u32 warp_sum[PP_THREADS / 32];
-#if FQD_K1_TICKET
-    __shared__ u32 s_tile;
-#endif
     __shared__ u32 s_P, s_halo;
     __shared__ __align__(8) u64 mbar;
 
@@ -388,54 +400,59 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     const u32 lane = tid & 31u, warp = tid >> 5;
     const u64 slot_base = p.run->n_records;
     TL_ENTRY();
-
-#if FQD_K1_TICKET
-    if (tid == 0) {
-        s_tile = atomicAdd(&p.ctl->ticket, 1u);      // tiles are processed in ticket order: every predecessor
-        mbar_init(&mbar, 1);                         // of a tile is already resident (look-back cannot deadlock)
-    }
-    if (tid < PP_HKEYS) s_hkey[tid] = c_hkeys[((p.hash_salt >> 12) & 1u) * PP_HKEYS + tid];
-    __syncthreads();
-    const u32 tile = s_tile;
-    const u32 base = tile * PP_TILE;
-    const u32 valid = min(PP_WINDOW, p.n - base);
-    if (tid == 0) {
-        const u32 bytes = (valid + 15u) & ~15u;
-        mbar_expect_tx(&mbar, bytes);
-        bulk_g2s(win, p.raw + base, bytes, &mbar);
-    }
-    mbar_wait(&mbar, 0);
-#else
-    // Tiles in block-index order: the hardware starts the CTAs of a 1-D grid in index order, so every predecessor of a
-    // tile is resident or done when the tile starts (the assumption every single-pass decoupled look-back scan makes) -
-    // no ticket atomic, and one barrier covers both the mbarrier set-up and the arrival of the tile's bytes.
     const u32 tile = blockIdx.x;
     const u32 base = tile * PP_TILE;
     const u32 valid = min(PP_WINDOW, p.n - base);
-    if (warp == 0) {
-        if (lane == 0) {
-            mbar_init(&mbar, 1);
-            const u32 bytes = (valid + 15u) & ~15u;
-            mbar_expect_tx(&mbar, bytes);
-            bulk_g2s(win, p.raw + base, bytes, &mbar);
-#if FQD_K1_L2PF
-            // the tile a CTA will want about one CTA lifetime from now: HBM -> L2 while this one is being processed
-            const u64 pf = (u64)(tile + FQD_K1_L2PF) * PP_TILE;
-            if (pf + PP_TILE <= (u64)p.n) bulk_prefetch_l2(p.raw + pf, PP_TILE);
-#endif
-        }
-        __syncwarp();
-        mbar_wait(&mbar, 0);
-    }
-    if (tid < PP_HKEYS) s_hkey[tid] = c_hkeys[((p.hash_salt >> 12) & 1u) * PP_HKEYS + tid];
-    __syncthreads();
-#endif
-    TL_STAMP0(tid == 0);
-    TL_STAMP(tid == 0, 1);
+    const u32 stile = tile + PP_LEAD;                   // the tile I count for its future CTA
+    const bool scouting = stile < p.n_tiles;
     // constants the compiler must keep in registers (one LOP3 per use instead of two with immediates)
     u32 c_nl, c_7f;
     asm volatile("mov.u32 %0, 0x0A0A0A0A;" : "=r"(c_nl));
     asm volatile("mov.u32 %0, 0x7F7F7F7F;" : "=r"(c_7f));
+
+    // ---- 0. own tile: one bulk async copy (TMA); scout tile: 64 bytes per thread, loads in flight next to it
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        const u32 bytes = (valid + 15u) & ~15u;
+        mbar_expect_tx(&mbar, bytes);
+        bulk_g2s(win, p.raw + base, bytes, &mbar);
+    }
+    uint4 sv[4];
+    const u64 sbase = (u64)stile * PP_TILE + tid * 64u;          // 64-bit: a chunk may end within 4 GiB of 2^32
+    if (scouting) {
+        const uint4* sp = reinterpret_cast<const uint4*>(p.raw + sbase);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            sv[k] = make_uint4(0u, 0u, 0u, 0u);
+            if (sbase + 16u * k < (u64)p.n) sv[k] = __ldcg(sp + k);      // like the bulk copy, the last unit may reach past n
+        }
+    }
+    if (tid < PP_HKEYS) s_hkey[tid] = c_hkeys[((p.hash_salt >> 12) & 1u) * PP_HKEYS + tid];
+    u32 T_scout = 0;                                    // warp 0: newlines of the scout tile
+    if (scouting) {
+        u32 cnt = 0;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            u32 m = nl_mask16(sv[k], c_nl, c_7f);
+            const u64 o = sbase + 16u * k;
+            if (o + 16u > (u64)p.n) m = o < (u64)p.n ? (m & ((1u << (u32)((u64)p.n - o)) - 1u)) : 0u;
+            cnt += __popc(m);
+        }
+        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+        if (lane == 0) warp_sum[warp] = cnt;
+        if (warp == 0) {
+            bar_sync_c<BAR_SCOUT, PP_THREADS>();
+#pragma unroll
+            for (int w = 0; w < PP_THREADS / 32; ++w) T_scout += warp_sum[w];
+            if (lane == 0) st_volatile_u64(p.tile_state + stile, (1ull << 32) | (u64)T_scout);
+        } else {
+            bar_arrive_c<BAR_SCOUT, PP_THREADS>();
+        }
+    }
+    if (warp == 0) { __syncwarp(); mbar_wait(&mbar, 0); }
+    __syncthreads();                                    // the window is staged; s_P (scouted tiles), s_hkey visible
+    TL_STAMP0(tid == 0);
+    TL_STAMP(tid == 0, 1);
 
     // ---- 1. newline bitmask of the window
     {
@@ -491,9 +508,20 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
         T = __shfl_sync(0xFFFFFFFFu, wi, PP_THREADS / 32 - 1);
         lex = __shfl_sync(0xFFFFFFFFu, wi - ws, warp) + (incl - cnt);
     }
-    // publish this tile's aggregate as early as possible
-    if (tid == 0) st_volatile_u64(p.tile_state + tile, ((tile == 0 ? 2ull : 1ull) << 32) | T);
     TL_STAMP(tid == 0, 3);
+    if (tid == 0) {
+        // resolved two CTA lifetimes ago by the CTA that scouted this tile (the first PP_LEAD tiles: by pp_scout_head,
+        // before this kernel started): inclusive prefix = P + T
+        u64 own = ld_volatile_u64(p.tile_state + tile);
+        while ((own >> 32) != 2) own = ld_volatile_u64(p.tile_state + tile);
+        const u32 all = (u32)own;
+        s_P = all - T;
+        if (tile == p.n_tiles - 1) {
+            p.ctl->n_newlines = all;
+            const u32 nrec = all / LPR;
+            p.ctl->n_records = nrec < p.cap ? nrec : p.cap;
+        }
+    }
     if (cnt) {
         // straight-line for the first two newlines of my 64 bytes (a FASTQ line pair "...\n+\n" at most), loop for more
         u64 m = my_mask;
@@ -513,10 +541,8 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
             }
         }
     }
-    bool compact;                                  // the compacted positions hold every newline of the window
     if (warp == PP_THREADS / 32 - 1) {
-        // the last warp also ranks the halo words (PP_HALO/64 <= 32): their ranks continue after the tile's.  (Warp 0
-        // did this in round 1 - 1 400 cycles between publishing the tile's count and the first look-back load.)
+        // the last warp also ranks the halo words (PP_HALO/64 <= 32): their ranks continue after the tile's
         const u64 hm = lane < (PP_NW - PP_THREADS) ? mask64[PP_THREADS + lane] : 0ull;
         const u32 hc = (u32)__popcll(hm);
         u32 hi = hc;
@@ -536,97 +562,36 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
             ++r;
         }
     }
-    if (warp == 0) {
-        __syncwarp();
-        bar_arrive_c<BAR_POS, PP_THREADS>();
-        // newlines in the halo, for `compact` (s_halo belongs to the packers' side of BAR_POS)
-        const u32 htot = __reduce_add_sync(0xFFFFFFFFu, lane < (PP_NW - PP_THREADS) ? (u32)__popcll(mask64[PP_THREADS + lane]) : 0u);
-        compact = T + htot <= PP_NLCAP;
-
-        // ---- decoupled look-back for the global rank of the tile's first newline; warps 1..7 do not wait for it
-        u32 P = 0;
-        TL_STAMP(lane == 0, 9);
-        if (tile != 0) {
-            // window of 128 predecessors per hop (4 per lane): one L2 round trip must cover more tiles than
-            // the chip starts in that time, otherwise the distance to the nearest published prefix grows
-            int look = (int)tile - 1;
-            for (;;) {
-                u64 s4[4];
-#pragma unroll
-                for (int r4 = 0; r4 < 4; ++r4) {
-                    int idx = look - (int)lane - 32 * r4;
-                    s4[r4] = (2ull << 32);
-                    if (idx >= 0) s4[r4] = ld_volatile_u64(p.tile_state + idx);
-                }
-#pragma unroll
-                for (int r4 = 0; r4 < 4; ++r4) {
-                    int idx = look - (int)lane - 32 * r4;
-                    while ((s4[r4] >> 32) == 0) s4[r4] = ld_volatile_u64(p.tile_state + idx);
-                }
-                bool found = false;
-#pragma unroll
-                for (int r4 = 0; r4 < 4; ++r4) {
-                    if (!found) {
-                        u32 is_prefix = __ballot_sync(0xFFFFFFFFu, (s4[r4] >> 32) == 2);
-                        u32 val = (u32)s4[r4];
-                        if (is_prefix) {
-                            u32 first = (u32)__ffs((int)is_prefix) - 1u;     // closest predecessor holding a prefix
-                            if (lane > first) val = 0;
-                            found = true;
-                        }
-                        P += __reduce_add_sync(0xFFFFFFFFu, val);
-                    }
-                }
-                if (found) break;
-                look -= 128;
-            }
-            if (lane == 0) st_volatile_u64(p.tile_state + tile, (2ull << 32) | (u64)(P + T));
-        }
-        TL_STAMP(lane == 0, 10);
-        if (lane == 0) {
-            s_P = P;
-            if (tile == p.n_tiles - 1) {
-                u32 all = P + T;
-                p.ctl->n_newlines = all;
-                u32 nrec = all / LPR;
-                p.ctl->n_records = nrec < p.cap ? nrec : p.cap;
-            }
-        }
-        __syncwarp();
-        if (compact) { bar_arrive_c<BAR_P, PP_THREADS>(); return; }
-        bar_sync_c<BAR_P, PP_THREADS>();                // very dense tile: warp 0 helps to split and pack it
-    } else {
-        bar_sync_c<BAR_POS, PP_THREADS>();
-        compact = T + s_halo <= PP_NLCAP;
-        if (!compact) bar_sync_c<BAR_P, PP_THREADS>();  // very dense tile: everybody waits for the look-back
-    }
+    __syncthreads();                                    // newline positions complete; s_P, s_halo visible
+    TL_STAMP(tid == 0, 4);
     const u32 WN = T + s_halo;                          // newlines in the whole window
+    const bool compact = WN <= PP_NLCAP;                // the compacted positions hold every newline of the window
+    const u32 P = s_P;
+    if (warp == 0) {
+        // warp 0 works for the future: the prefix of the scout tile, resolved while warps 1..7 split and pack this one
+        if (scouting) {
+            TL_STAMP(lane == 0, 9);
+            const u32 Pu = pp_lookback(p.tile_state, stile, lane);
+            if (lane == 0) st_volatile_u64(p.tile_state + stile, (2ull << 32) | (u64)(Pu + T_scout));
+            TL_STAMP(lane == 0, 10);
+        }
+        if (compact) return;
+    }
     const u32 l4 = tid & (PP_GROUP - 1u);
     const u32 gmask = 0xFu << (lane & 28u);
-    const u32 Rrel_first = tile == 0 ? 0u : 1u;         // owned records, counted from floor(P / LPR)
 
     if (compact) {
-        // ================= normal tile: warps 1..7, PP_GROUP lanes per record.  A record's line ends are consecutive
-        // entries of nlpos; everything but the record's index follows from c = P mod LPR.  Every lane of a group
-        // derives the geometry of its record itself (identical work, broadcast loads): round 1 had one owner thread per
-        // record hand it over through shared memory, which kept five of the seven warps waiting at a barrier.
-        const u32 wtid = tid - 32u;
-        const u32 g = wtid / PP_GROUP;
-        u32 P = 0, c = 0;
-        bool p_known = false;
-        if (tile != 0) {
-            c = guess_phase<LPR>(win, nlpos, WN, valid, lane);      // same inputs in every warp -> same answer
-            if (c == PP_NONE) {                                      // no usable guess: all packers wait for the exact value
-                bar_sync_c<BAR_P, PP_THREADS>();
-                P = s_P; p_known = true; c = P % LPR;
-            }
-        }
-        TL_STAMP(wtid == 0, 4);
-        u32 rbase = 0;
-        for (;;) {
-            const u32 Rrel_last = (c + T) / LPR;
-            const u32 n_owned = Rrel_last >= Rrel_first ? Rrel_last - Rrel_first + 1u : 0u;
-            const u32 n_round = rbase < n_owned ? min(PP_PACKERS / PP_GROUP, n_owned - rbase) : 0u;
+        // ================= normal tile: PP_GROUP lanes per record, 64 records per round.  A record's line ends are
+        // consecutive entries of nlpos; c = P mod LPR says which newline ends a record (the reference, too, simply counts
+        // 4 (2) newlines per record).  Every lane of a group derives the geometry of its record itself (identical work,
+        // broadcast loads) - no hand-over through shared memory, no barrier.
+        const u32 g = (tid - 32u) / PP_GROUP;
+        const u32 c = P % LPR;
+        const u32 Rrel_first = tile == 0 ? 0u : 1u;     // owned records, counted from floor(P / LPR)
+        const u32 Rrel_last = (c + T) / LPR;
+        const u32 n_owned = Rrel_last >= Rrel_first ? Rrel_last - Rrel_first + 1u : 0u;
+        for (u32 rbase = 0; rbase < n_owned; rbase += PP_PACKERS / PP_GROUP) {
+            const u32 n_round = min((u32)(PP_PACKERS / PP_GROUP), n_owned - rbase);
             // ---- geometry + validation
             u32 status = RS_NONE, gstart = 0, off = PP_NONE, ql = 0;
             if (g < n_round) {
@@ -650,57 +615,42 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                                                   LPR == 4 ? e[3] : e[1], off, ql);
                 }
             }
-            TL_STAMP(wtid == 0 && rbase == 0, 5);
-            // ---- pack (rows of up to 8 words: into registers, before the record index is known)
-            const bool active = off != PP_NONE;
-            u32 bad = 0;
-            u64 wa = 0, wb = 0, hsum = 0;
-            if (active && p.W <= 8u) {
-                const u32 w = 2u * l4;
-                if (w < p.W) {
-                    u32 bad_b;
-                    wa = pack_word<BYTES>(win, p, base, off, ql, w, bad);
-                    wb = pack_word<BYTES>(win, p, base, off, ql, w + 1u, bad_b);
-                    if (!bad) bad = bad_b;
-                    hsum = word_hash(wa, s_hkey[w]) + word_hash(wb, s_hkey[w + 1u]);
-                }
-            }
-            TL_STAMP(wtid == 0 && rbase == 0, 6);
-            if (!p_known) {
-                bar_sync_c<BAR_P, PP_THREADS>();
-                P = s_P; p_known = true;
-                if (P % LPR != c) { c = P % LPR; continue; }       // wrong guess: split this round again
-            }
-            TL_STAMP(wtid == 0 && rbase == 0, 7);
-            // ---- commit
-            const u32 R0 = P / LPR + Rrel_first + rbase;
-            if (g < n_round && l4 == 0) commit_record(p, slot_base, R0 + g, gstart, status);
-            if (active) {
-                const u32 R = R0 + g;
-                if (R < p.cap && slot_base + R < p.key_capacity) {
-                    u64* row = p.keys + (slot_base + R) * p.row_words + p.mate_off;
-                    u64 w0 = wa;
-                    if (p.W <= 8u) {
-                        if (2u * l4 < p.W) *reinterpret_cast<ulonglong2*>(row + 2u * l4) = make_ulonglong2(wa, wb);
-                    } else {
-                        for (u32 w = 2u * l4; w < p.W; w += 2u * PP_GROUP) {
-                            u32 bad_a, bad_b;
-                            const u64 xa = pack_word<BYTES>(win, p, base, off, ql, w, bad_a);
-                            const u64 xb = pack_word<BYTES>(win, p, base, off, ql, w + 1u, bad_b);
-                            *reinterpret_cast<ulonglong2*>(row + w) = make_ulonglong2(xa, xb);
-                            if (w == 0) w0 = xa;
-                            if (!bad) bad = bad_a ? bad_a : bad_b;
-                            const uint2 ka = w < PP_HKEYS ? s_hkey[w] : pos_keys(p.hash_salt + w);
-                            const uint2 kb = w + 1u < PP_HKEYS ? s_hkey[w + 1u] : pos_keys(p.hash_salt + w + 1u);
-                            hsum += word_hash(xa, ka) + word_hash(xb, kb);
-                        }
+            TL_STAMP(tid == 32 && rbase == 0, 5);
+            const u32 R = P / LPR + Rrel_first + rbase + g;
+            if (g < n_round && l4 == 0) commit_record(p, slot_base, R, gstart, status);
+            // ---- pack + commit
+            if (off != PP_NONE && R < p.cap && slot_base + R < p.key_capacity) {
+                u64* row = p.keys + (slot_base + R) * p.row_words + p.mate_off;
+                u32 bad = 0;
+                u64 hsum = 0, w0 = 0;
+                if (p.W <= 8u) {
+                    const u32 w = 2u * l4;
+                    if (w < p.W) {
+                        u32 bad_b;
+                        const u64 wa = pack_word<BYTES>(win, p, base, off, ql, w, bad);
+                        const u64 wb = pack_word<BYTES>(win, p, base, off, ql, w + 1u, bad_b);
+                        if (!bad) bad = bad_b;
+                        hsum = word_hash(wa, s_hkey[w]) + word_hash(wb, s_hkey[w + 1u]);
+                        *reinterpret_cast<ulonglong2*>(row + w) = make_ulonglong2(wa, wb);
+                        w0 = wa;
                     }
-                    commit_group(p, R, ql & 0x7FFFFFFFu, l4, gmask, hsum, w0, bad);
+                } else {
+                    for (u32 w = 2u * l4; w < p.W; w += 2u * PP_GROUP) {
+                        u32 bad_a, bad_b;
+                        const u64 xa = pack_word<BYTES>(win, p, base, off, ql, w, bad_a);
+                        const u64 xb = pack_word<BYTES>(win, p, base, off, ql, w + 1u, bad_b);
+                        *reinterpret_cast<ulonglong2*>(row + w) = make_ulonglong2(xa, xb);
+                        if (w == 0) w0 = xa;
+                        if (!bad) bad = bad_a ? bad_a : bad_b;
+                        const uint2 ka = w < PP_HKEYS ? s_hkey[w] : pos_keys(p.hash_salt + w);
+                        const uint2 kb = w + 1u < PP_HKEYS ? s_hkey[w + 1u] : pos_keys(p.hash_salt + w + 1u);
+                        hsum += word_hash(xa, ka) + word_hash(xb, kb);
+                    }
                 }
+                TL_STAMP(tid == 32 && rbase == 0, 6);
+                commit_group(p, R, ql & 0x7FFFFFFFu, l4, gmask, hsum, w0, bad);
             }
-            rbase += PP_PACKERS / PP_GROUP;
-            TL_STAMP(wtid == 0, 8);
-            if (rbase >= n_owned) break;
+            TL_STAMP(tid == 32, 8);
         }
         return;
     }
@@ -708,7 +658,6 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     // ================= very dense tile (tiny records; all 8 warps, after the look-back): every thread walks its
     // own newline bits
     {
-        const u32 P = s_P;
         u32 R_first = (P + LPR) / LPR;
         const u32 R_last = (P + T) / LPR;
         if (tile == 0) R_first = 0;
@@ -776,9 +725,63 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     }
 }
 
-// one ticket (CTA) per tile
+// The first PP_LEAD tiles of a chunk have no CTA ahead of them to count their newlines: a small kernel does it before K1
+// starts (PP_LEAD x 16 KiB = 24 MB, a few microseconds), a second one turns the counts into resolved prefixes.  After
+// that every tile of the chunk finds its prefix published by somebody who started EARLIER - which is what makes the
+// spin-waits of K1 deadlock-free whatever the number of resident CTAs.
+__global__ void __launch_bounds__(PP_THREADS) k_scout_head(const ParseParams p) {
+    __shared__ u32 warp_sum[PP_THREADS / 32];
+    const u32 tile = blockIdx.x, tid = threadIdx.x;
+    u32 c_nl, c_7f;
+    asm volatile("mov.u32 %0, 0x0A0A0A0A;" : "=r"(c_nl));
+    asm volatile("mov.u32 %0, 0x7F7F7F7F;" : "=r"(c_7f));
+    const u64 sbase = (u64)tile * PP_TILE + tid * 64u;
+    const uint4* sp = reinterpret_cast<const uint4*>(p.raw + sbase);
+    u32 cnt = 0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+        const u64 o = sbase + 16u * k;
+        if (o >= (u64)p.n) continue;
+        u32 m = nl_mask16(__ldcg(sp + k), c_nl, c_7f);
+        if (o + 16u > (u64)p.n) m &= (1u << (u32)((u64)p.n - o)) - 1u;
+        if (o < (u64)p.skip) m &= o + 16u <= (u64)p.skip ? 0u : ~0u << (u32)((u64)p.skip - o);      // newlines before the chunk proper are not ours
+        cnt += __popc(m);
+    }
+    cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
+    if ((tid & 31u) == 0) warp_sum[tid >> 5] = cnt;
+    __syncthreads();
+    if (tid == 0) {
+        u32 tot = 0;
+#pragma unroll
+        for (int w = 0; w < PP_THREADS / 32; ++w) tot += warp_sum[w];
+        p.tile_state[tile] = (1ull << 32) | (u64)tot;
+    }
+}
+__global__ void __launch_bounds__(1024) k_scan_head(u64* tile_state, u32 n_head) {
+    __shared__ u32 s_part[1024];
+    // thread t owns entries [t * per, (t + 1) * per)
+    const u32 per = (n_head + 1023u) / 1024u;
+    const u32 lo = min(n_head, threadIdx.x * per), hi = min(n_head, lo + per);
+    u32 sum = 0;
+    for (u32 i = lo; i < hi; ++i) sum += (u32)tile_state[i];
+    s_part[threadIdx.x] = sum;
+    __syncthreads();
+    for (u32 d = 1; d < 1024; d <<= 1) {          // inclusive scan of the partial sums
+        const u32 v = threadIdx.x >= d ? s_part[threadIdx.x - d] : 0u;
+        __syncthreads();
+        s_part[threadIdx.x] += v;
+        __syncthreads();
+    }
+    u32 run = s_part[threadIdx.x] - sum;
+    for (u32 i = lo; i < hi; ++i) { run += (u32)tile_state[i]; tile_state[i] = (2ull << 32) | (u64)run; }
+}
+
+// one CTA per tile
 static inline void pp_launch(bool fastq, const ParseParams& p, cudaStream_t stream) {
     if (p.n_tiles == 0) return;
+    const u32 n_head = p.n_tiles < PP_LEAD ? p.n_tiles : PP_LEAD;
+    k_scout_head<<<n_head, PP_THREADS, 0, stream>>>(p);
+    k_scan_head<<<1, 1024, 0, stream>>>(p.tile_state, n_head);
     if (p.byte_keys) {
         if (fastq) k_parse_pack<4, true><<<p.n_tiles, PP_THREADS, 0, stream>>>(p);
         else k_parse_pack<2, true><<<p.n_tiles, PP_THREADS, 0, stream>>>(p);

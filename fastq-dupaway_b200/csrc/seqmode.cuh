@@ -161,24 +161,75 @@ __global__ void k_ham_breaks(const ScanParams p) {
         p.brk[i] = b;
     }
 }
-__global__ void k_ham_segments(const ScanParams p) {
+// One thread per segment walks the first HAM_SHORT records of its segment (segments are cluster-sized on ordinary
+// libraries); a segment that is longer - an amplicon, a low-complexity repeat, a heavily duplicated library: it can be
+// most of the input - is handed, with the head reached so far, to k_ham_long, where a whole block tests 256 candidates
+// against the current head at a time.  (Round 1 walked every segment to its end in one thread: a million-member
+// Hamming chain was a million dependent DRAM round trips on one lane.)
+constexpr u32 HAM_SHORT = 48;
+struct HamLong { u64 next; u32 head; u32 pad; };
+__device__ __forceinline__ bool ham_dup(const ScanParams& p, u32 c, const u64* q) {
+    const u64* a = p.rows + (u64)c * p.stride;
+    // lengths are equal inside a segment (a length change is a break)
+    bool dup = hamming_words(a, q, p.W, p.bits) <= p.dist;
+    if (dup && p.mates == 2) dup = hamming_words(a + p.W, q + p.W, p.W, p.bits) <= p.dist;
+    return dup;
+}
+__global__ void k_ham_segments(const ScanParams p, HamLong* longs, u32* n_long) {
     u64 step = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < p.n; i += step) {
         if (!p.brk[i]) continue;
         p.keep[i] = 1;
         u32 head = p.perm[i];
         u64 j = i + 1;
-        for (; j < p.n && !p.brk[j]; ++j) {
+        const u64 stop = min(p.n, i + 1 + HAM_SHORT);
+        for (; j < stop && !p.brk[j]; ++j) {
             const u32 c = p.perm[j];
-            const u64* a = p.rows + (u64)c * p.stride;
-            const u64* q = p.rows + (u64)head * p.stride;
-            // lengths are equal inside a segment (a length change is a break)
-            bool dup = hamming_words(a, q, p.W, p.bits) <= p.dist;
-            if (dup && p.mates == 2) dup = hamming_words(a + p.W, q + p.W, p.W, p.bits) <= p.dist;
+            const bool dup = ham_dup(p, c, p.rows + (u64)head * p.stride);
             p.keep[j] = dup ? 0u : 1u;
             if (!dup) head = c;
         }
-        if (j == p.n && p.tail_head) *p.tail_head = head;      // cluster head at the end of this key range
+        if (j == p.n) { if (p.tail_head) *p.tail_head = head; }      // cluster head at the end of this key range
+        else if (j == stop && !p.brk[j]) {                            // the segment goes on: a block takes over
+            const u32 k = atomicAdd(n_long, 1u);
+            longs[k].next = j; longs[k].head = head;
+        }
+    }
+}
+// The greedy scan of one long segment, 256 candidates per step: everything before the first candidate that is NOT a
+// duplicate of the current head is one (keep = 0); that candidate becomes the head (keep = 1) and the scan goes on
+// behind it.  Same result as the sequential loop of src/seq_dup_remover.hpp:78-101 with src/comparator.cpp:76-91.
+__global__ void __launch_bounds__(256) k_ham_long(const ScanParams p, const HamLong* longs, const u32* n_long) {
+    __shared__ u32 s_first;              // offset in the batch of the first non-duplicate / break (256 = none)
+    __shared__ u32 s_is_break;
+    const u32 t = threadIdx.x;
+    for (u32 e = blockIdx.x; e < *n_long; e += gridDim.x) {
+        u64 j = longs[e].next;
+        u32 head = longs[e].head;
+        for (;;) {
+            if (t == 0) { s_first = 256u; s_is_break = 0; }
+            __syncthreads();
+            const u64 idx = j + t;
+            u32 what = 0;                // 1 = break (or end of the stream), 2 = not a duplicate of the head
+            u32 c = 0;
+            if (idx >= p.n || p.brk[idx]) what = 1;
+            else { c = p.perm[idx]; if (!ham_dup(p, c, p.rows + (u64)head * p.stride)) what = 2; }
+            if (what) atomicMin(&s_first, t);
+            __syncthreads();
+            const u32 first = s_first;
+            if (t < first) p.keep[idx] = 0;                      // duplicates of the head
+            if (t == first && what == 1) s_is_break = 1;
+            if (t == first && what == 2) p.keep[idx] = 1;
+            __syncthreads();
+            if (first == 256u) { j += 256; continue; }
+            if (s_is_break) {
+                if (j + first >= p.n && t == 0 && p.tail_head) *p.tail_head = head;
+                break;
+            }
+            head = p.perm[j + first];                            // every thread reads the new head itself
+            j += first + 1;
+        }
+        __syncthreads();
     }
 }
 
@@ -754,6 +805,7 @@ static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
     p.byte_keys = s->cfg.byte_keys ? 1u : 0u; p.skip = sg.skip;
     if (s->cfg.unordered) { p.hash = mt.d_hash + mt.n_records; p.bad_rec = mt.d_bad + mt.n_records; }
     pp_launch(s->cfg.format == FQD_FORMAT_FASTQ, p, s->stream);
+    s->launches += 2;               // the two head kernels of pp_launch
     if (s->cfg.unordered) {
         k_extract_tags<<<s->sm * 8, 128, 0, s->stream>>>(sg.d, s->d_rec_start, s->d_ctl, s->TW, mt.d_tags + mt.n_records * s->TW, s->d_ctl);
         s->launches++;
@@ -1048,9 +1100,13 @@ static int seq_scan_stage(SeqState* s, std::string* err) {
     else if (s->cfg.mode == FQD_MODE_SEQ_LOOSE && s->low_bytes) k_scan_loose_literal<<<1, 1, 0, s->stream>>>(sp);
     else if (s->cfg.mode == FQD_MODE_SEQ_LOOSE) k_scan_loose<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
     else {
+        HamLong* d_long = nullptr; u32* d_nlong = nullptr;
+        if ((rc = seq_dalloc(s, &d_long, n / HAM_SHORT + 2, err)) || (rc = seq_dalloc(s, &d_nlong, 1, err))) return rc;
+        SEQ_TRY(cudaMemsetAsync(d_nlong, 0, sizeof(u32), s->stream));
         k_ham_breaks<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
-        k_ham_segments<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
-        s->launches++;
+        k_ham_segments<<<seq_grid(s, n), 256, 0, s->stream>>>(sp, d_long, d_nlong);
+        k_ham_long<<<s->sm * 4, 256, 0, s->stream>>>(sp, d_long, d_nlong);
+        s->launches += 2;
     }
     s->launches++;
     s->scanned = true;

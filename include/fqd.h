@@ -36,7 +36,7 @@ typedef enum {
     FQD_ERR_BAD_START = 4,      /* record does not start with '@' / '>'          src/fastqview.cpp:121-126   */
     FQD_ERR_LEN_MISMATCH = 5,   /* FASTQ: len(seq) != len(qual)                  src/fastqview.cpp:117       */
     FQD_ERR_BAD_BASE = 6,       /* fast mode: byte outside {A,C,G,T,N}           src/seq_utils.cpp:17-19     */
-    FQD_ERR_CAPACITY = 7,       /* record / key-store / table capacity exceeded                          */
+    FQD_ERR_CAPACITY = 7,       /* key store / tables full and no device memory left to grow them in place */
     FQD_ERR_SEQ_TOO_LONG = 8,   /* sequence longer than fqd_config.max_seq_len                           */
     FQD_ERR_TAG_TOO_LONG = 10,  /* --unordered: an ID tag is longer than fqd_config.max_tag_len          */
     FQD_ERR_UNSUPPORTED_BYTE = 9 /* sequence mode with 3-bit rows: a sequence byte outside {A,C,G,T,N}; run the job again
@@ -122,9 +122,21 @@ int fqd_push_prefetch(fqd_handle* h, const char* r1, size_t n1, const char* r2, 
 int fqd_push_staged(fqd_handle* h, fqd_chunk_result* res);
 int fqd_push_device(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2, fqd_chunk_result* res);
 /* Same as fqd_push_device but returns after enqueueing; nothing is copied to the host.  fqd_sync() waits and
- * folds the chunk counters into the statistics.  Used for device-resident throughput measurement. */
+ * folds the chunk counters into the statistics; the first chunk that raised a data error is remembered on the device,
+ * whichever chunk it was, and reported then (fqd_stats).  A chunk that does not fit the key store is refused as a whole
+ * (FQD_ERR_CAPACITY at fqd_sync; the synchronous pushes grow the key store and the table in place instead and run the
+ * chunk again).  Used for device-resident throughput measurement. */
 int fqd_push_device_async(fqd_handle* h, const void* d_r1, size_t n1, const void* d_r2, size_t n2);
 int fqd_sync(fqd_handle* h);
+/* Survivor list of a whole ordered --fast run, kept on the device: the global input indices (record 0 = first record pushed)
+ * of the records that are WRITTEN, ascending - what the reference's write loop produces one record at a time
+ * (src/hash_dup_remover.hpp:136-138,240-244).  fqd_keep_survivors(h, 1) before the first chunk (or right after fqd_reset)
+ * makes every chunk append its survivors (8 bytes each, capacity = fqd_config.max_records, grown with the key store);
+ * fqd_survivors waits for the chunks enqueued so far, reports the count, copies entries [first, first + cap) to dst (may be
+ * NULL) and hands out the device pointer of the list (may be NULL).  For callers that keep the input on the device or
+ * fetch the written records themselves; the streaming host path gets per-chunk flags from fqd_push instead. */
+int fqd_keep_survivors(fqd_handle* h, int on);
+int fqd_survivors(fqd_handle* h, uint64_t first, uint64_t* dst, uint64_t cap, uint64_t* n_total, const uint64_t** d_list);
 /* Forget every key seen so far (empty set, counters and sticky error cleared): start a new job on the same handle. */
 int fqd_reset(fqd_handle* h);
 
@@ -212,6 +224,42 @@ int fqd_shard_insert(fqd_handle* h, const void* d_recv, uint64_t n_recv, uint32_
 int fqd_shard_apply(fqd_handle* h, const void* d_flags_back, uint64_t* chunk_dups);
 /* duplicate flags (one byte per record, record order) of the chunk last given to fqd_shard_apply, copied to the host */
 int fqd_shard_read_flags(fqd_handle* h, void* dst, size_t n);
+
+/*
+ * Multi-GPU --fast mode, round 2: the same hash-range ownership without a host round trip or a staging copy per chunk.
+ * The key store of an owner is a sequence of fixed REGIONS, one per (chunk, source rank), region_rows rows each, so a source
+ * knows the slot of every row it sends before anything is exchanged: slot = (chunk * n_shards + source) * region_rows +
+ * position among the source's rows for that owner - still global input order (chunks dealt round-robin in input order, sources
+ * in rank order), which is what makes "smallest slot wins" keep the record the reference keeps (src/hash_dup_remover.hpp:
+ * 133-139).  fqd_config.max_records of every handle must cover n_chunks * n_shards * region_rows.
+ *   fqd_shard2_init      allocates the per-chunk regions (hashes, counts, flags; double-buffered by chunk parity) and the
+ *                        interprocess events of this rank;
+ *   fqd_shard2_export    fqd_shard2_blob_bytes() bytes (CUDA IPC handles of the key store, the regions and the events); the
+ *                        ranks all-gather them and fqd_shard2_import every peer's;
+ *   fqd_shard2_pack      split + pack chunk number `chunk` of THIS rank's input, partition its rows stably by owner, write
+ *                        every row straight into its owner's key store over mapped peer memory (NVLink), record "scattered";
+ *   fqd_shard2_insert    owner side: waits (on the device) for every source's "scattered" of that chunk, inserts region by
+ *                        region, writes one flag byte per row into the SOURCE's flag regions, records "flags sent";
+ *   fqd_shard2_apply     source side: waits (on the device) for every owner's "flags sent", stores the flags against this rank's
+ *                        records (fqd_shard2_read_flags) and counts the duplicates;
+ *   fqd_shard2_finish    waits for this rank's streams; totals of this rank's records; data errors / a region overflow are
+ *                        reported through fqd_stats.
+ * Every call but finish only enqueues.  The caller's loop is  pack(0) | for c: [pack(c+1)] insert(c) | apply(c)  with a host
+ * barrier at every "|": it makes sure an event has been RECORDED by its owner before a peer enqueues the wait for it.
+ * Chunks must be numbered alike on every rank (a rank whose slice is shorter passes empty chunks).
+ */
+size_t fqd_shard2_blob_bytes(void);
+int fqd_shard2_init(fqd_handle* h, uint32_t n_shards, uint32_t me, uint32_t region_rows);
+int fqd_shard2_export(fqd_handle* h, void* blob);
+int fqd_shard2_import(fqd_handle* h, uint32_t rank, const void* blob);
+int fqd_shard2_pack(fqd_handle* h, uint64_t chunk, const void* d_r1, size_t n1, const void* d_r2, size_t n2);
+int fqd_shard2_insert(fqd_handle* h, uint64_t chunk);
+int fqd_shard2_apply(fqd_handle* h, uint64_t chunk);
+int fqd_shard2_finish(fqd_handle* h, uint64_t* n_records, uint64_t* n_dups);
+int fqd_shard2_reset(fqd_handle* h);
+int fqd_shard2_read_flags(fqd_handle* h, void* dst, size_t n);
+int fqd_shard2_timer_start(fqd_handle* h);
+int fqd_shard2_timer_stop(fqd_handle* h, double* ms);
 
 /* Statistics / sticky data error (feeds the -v lines and the reference's error messages). */
 int fqd_stats(fqd_handle* h, fqd_stats_t* out);

@@ -59,7 +59,9 @@ int fqd_create(const fqd_config* cfg, fqd_handle** out) {
     std::memset(&h->st, 0, sizeof h->st);
     const char* e = std::getenv("FAKE_FQD_SHRINK");
     const long long k = e ? std::atoll(e) : 1;
-    h->capacity = cfg->max_records / (uint64_t)(k > 0 ? k : 1);
+    // like the real engine since round 2, the double grows its tables as it fills (max_records is a first size, not a
+    // limit); FAKE_FQD_SHRINK makes it refuse instead, which is what the real engine does when the device is full
+    h->capacity = e ? cfg->max_records / (uint64_t)(k > 0 ? k : 1) : ~0ull;
     *out = h;
     return FQD_OK;
 }

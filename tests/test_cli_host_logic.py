@@ -23,7 +23,19 @@ sys.path.insert(0, str(ROOT / "tests" / "fake_engine"))
 from build import BUILD as FAKE_DIR, build_fake  # noqa: E402
 
 
+# Every position by default.  tests/test_differential_gpu.py thins the sweeps (each run of the real binary pays ~1 s of
+# CUDA start-up): first, last and every SWEEP_STRIDE-th position; FQD_DIFF_FULL=1 restores every position there.
+SWEEP_STRIDE = 1
+
+
+def _sweep(n):
+    if SWEEP_STRIDE > 1:            # thinned (GPU box): one position early, one in the last block
+        return [1, n - 2]
+    return list(range(n))
+
+
 @pytest.fixture(scope="module", autouse=True)
+
 def fake_engine():
     build_fake()
     # the host binary needs the real library only to LINK; build it if the tree is fresh
@@ -163,13 +175,13 @@ def test_malformed_record_at_every_position_matches_the_reference_binary(tmp_pat
     if not oracle.ref_available():
         pytest.skip("oracle/_ref/fastq-dupaway not built")
     recs = _records(40, seed=30)
-    for pos in range(40):
+    for pos in _sweep(40):
         data = b"".join(recs[:pos] + [_damage(recs[pos], kind)] + recs[pos + 1:])
         inp = tmp_path / "in.fq"
         inp.write_bytes(data)
         ref = subprocess.run([str(oracle.REF_BIN), "-i", str(inp), "-o", str(tmp_path / "ref.fq"), "--fast", "-v"],
                              capture_output=True, text=True, cwd=tmp_path)
-        for block in (4096, 1 << 20):
+        for block in ((4096, 1 << 20) if SWEEP_STRIDE == 1 else (4096,)):
             ours = run("-i", inp, "-o", tmp_path / "ours.fq", "--fast", "-v", env={"FQD_BLOCK_BYTES": str(block)})
             assert ours.returncode == ref.returncode == 1, (pos, block)
             assert ours.stderr == ref.stderr, (pos, block)
@@ -183,7 +195,7 @@ def test_malformed_record_in_paired_input_matches_the_reference_binary(tmp_path,
     if not oracle.ref_available():
         pytest.skip("oracle/_ref/fastq-dupaway not built")
     r = [_records(24, seed=31, mate=1), _records(24, seed=32, mate=2, read_len=80)]
-    for pos in range(0, 24, 1):
+    for pos in _sweep(24):
         files = []
         for m in (0, 1):
             recs = list(r[m])
@@ -209,7 +221,7 @@ def test_input_cut_anywhere_in_the_last_record_matches_the_reference_binary(tmp_
         pytest.skip("oracle/_ref/fastq-dupaway not built")
     r1, r2 = _records(12, seed=33), _records(12, seed=34, mate=2, read_len=70)
     f1, f2 = b"".join(r1), b"".join(r2)
-    for cut in range(len(f1) - len(r1[-1]) - 2, len(f1) + 1, 3):
+    for cut in range(len(f1) - len(r1[-1]) - 2, len(f1) + 1, 3 if SWEEP_STRIDE == 1 else 61):
         for paired in (False, True):
             b1 = f1[:cut]
             (tmp_path / "a.fq").write_bytes(b1)
@@ -245,7 +257,7 @@ def test_malformed_fasta_record_at_every_position_matches_the_reference_binary(t
         else:
             l[1] = l[1].lower()
         return b"\n".join(l)
-    for pos in range(30):
+    for pos in _sweep(30):
         data = b"".join(recs[:pos] + [damage(recs[pos])] + recs[pos + 1:])
         (tmp_path / "in.fa").write_bytes(data)
         ref = subprocess.run([str(oracle.REF_BIN), "-i", "in.fa", "-o", "ref.fa", "--fast", "-v", "--format", "fasta"],
@@ -266,7 +278,7 @@ def test_two_malformed_records_report_the_one_the_reference_meets_first(tmp_path
         pytest.skip("oracle/_ref/fastq-dupaway not built")
     rng = random.Random(5)
     r = [_records(24, seed=31, mate=1), _records(24, seed=32, mate=2, read_len=80)]
-    for it in range(150):
+    for it in range(150 if SWEEP_STRIDE == 1 else 6):
         paired = rng.random() < 0.6
         recs = [list(r[0]), list(r[1])]
         for _ in range(2):
@@ -284,3 +296,73 @@ def test_two_malformed_records_report_the_one_the_reference_meets_first(tmp_path
         assert (tmp_path / "o1.fq").read_bytes() == (tmp_path / "r1.fq").read_bytes(), it
         if paired:
             assert (tmp_path / "o2.fq").read_bytes() == (tmp_path / "r2.fq").read_bytes(), it
+
+
+def _run_with_fifo_output(tmp_path, args, fifo_names):
+    """Runs the binary with some outputs being FIFOs; returns (CompletedProcess, {name: bytes read from the FIFO})."""
+    import threading
+    got = {}
+    def drain(name):
+        with open(tmp_path / name, "rb") as f:
+            got[name] = f.read()
+    for n in fifo_names:
+        os.mkfifo(tmp_path / n)
+    th = [threading.Thread(target=drain, args=(n,)) for n in fifo_names]
+    for t in th:
+        t.start()
+    p = run(*args)
+    for t in th:
+        t.join(timeout=60)
+    return p, got
+
+
+@pytest.mark.parametrize("paired", [False, True])
+def test_non_seekable_outputs(tmp_path, oracle, paired):
+    """-o /dev/stdout, -o <FIFO> (`-o >(pigz > x.gz)`): plain outputs are written with pwrite() at offsets on regular files
+    only; anything else gets every byte through write() in order (round 1 wrote nothing and exited 0)."""
+    s1, s2 = synth.make_pair(30000, seed=61, read_len=100, dup_frac=0.3)
+    b1, b2 = synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2)
+    (tmp_path / "a.fq").write_bytes(b1)
+    (tmp_path / "b.fq").write_bytes(b2)
+    if paired:
+        e1, e2, _ = oracle.run_oracle("fast", oracle.FASTQ, b1, b2)
+        p, got = _run_with_fifo_output(tmp_path, ["-i", tmp_path / "a.fq", "-u", tmp_path / "b.fq", "-o", tmp_path / "o1.fifo", "-p", tmp_path / "o2.fifo", "--fast"],
+                                       ["o1.fifo", "o2.fifo"])
+        assert p.returncode == 0, p.stderr
+        assert got["o1.fifo"] == e1 and got["o2.fifo"] == e2
+    else:
+        e1, _, _ = oracle.run_oracle("fast", oracle.FASTQ, b1)
+        p, got = _run_with_fifo_output(tmp_path, ["-i", tmp_path / "a.fq", "-o", tmp_path / "o.fifo", "--fast"], ["o.fifo"])
+        assert p.returncode == 0, p.stderr
+        assert got["o.fifo"] == e1
+        # /dev/stdout of a process whose stdout is a pipe
+        e = dict(os.environ, LD_LIBRARY_PATH=str(FAKE_DIR))
+        q = subprocess.run([str(EXE), "-i", str(tmp_path / "a.fq"), "-o", "/dev/stdout", "--fast"], capture_output=True, env=e, timeout=120)
+        assert q.returncode == 0 and q.stdout == e1
+
+
+def test_failed_writes_fail_the_run(tmp_path):
+    """A write error on a plain output (here: /dev/full) ends the run with the error banner and exit status 1."""
+    (tmp_path / "a.fq").write_bytes(synth.to_fastq(synth.make_reads(2000, seed=62, read_len=80)))
+    p = run("-i", tmp_path / "a.fq", "-o", "/dev/full", "--fast")
+    assert p.returncode == 1 and "writing /dev/full failed" in p.stderr
+
+
+def test_fifo_input_larger_than_the_first_table_size(tmp_path, oracle):
+    """A FIFO has no size: the tables start at 65 536 records and must grow while the input streams in (round 1 tried to
+    restart, which cannot work on a pipe: it hung / failed with 'Not enough memory to read a single object!')."""
+    import threading
+    seqs = synth.make_reads(120000, seed=63, read_len=60, dup_frac=0.3)
+    buf = synth.to_fastq(seqs)
+    exp, _, est = oracle.run_oracle("fast", oracle.FASTQ, buf)
+    os.mkfifo(tmp_path / "in.fifo")
+    def feed():
+        with open(tmp_path / "in.fifo", "wb") as f:
+            f.write(buf)
+    t = threading.Thread(target=feed)
+    t.start()
+    p = run("-i", tmp_path / "in.fifo", "-o", tmp_path / "o.fq", "--fast", "-v")
+    t.join(timeout=60)
+    assert p.returncode == 0, p.stderr
+    assert (tmp_path / "o.fq").read_bytes() == exp
+    assert p.stdout == f"{est.total} reads processed, out of which {est.dups} duplicates were removed.\n"

@@ -1,12 +1,9 @@
-"""NOT collected by default (the file name does not match test_*.py): the CPU differential suites of
-test_cli_host_logic.py / test_cli_whole_input_host_logic.py once more, but with the REAL libfqd_cuda.so behind the
-binary - i.e. the engine itself against the reference binaries (oracle/_ref travels to the GPU box) on malformed records
-at every position, input cut anywhere in the last record, double faults, odd and unusual files, in every mode.
-
-    python -m pytest tests/differential_gpu.py -q          # on a GPU box
-
-Written at the end of round 1, when the GPU budget was spent: the host logic around the engine has passed all of this
-over the test double; whether the engine agrees in every one of these corners is the first thing to run in round 2.
+"""The CPU differential suites of test_cli_host_logic.py / test_cli_whole_input_host_logic.py once more, but with the REAL
+libfqd_cuda.so behind the binary - i.e. the engine itself against the reference binaries (oracle/_ref travels to the GPU
+box) on malformed records swept over the file, input cut inside the last record, double faults, odd and unusual files,
+in every mode.  Every run of the real binary pays 1 - 3 s of CUDA start-up, so under `-m gpu` the sweeps visit two
+positions each (one early, one in the last block) and fewer flag sets - ~80 runs; the CPU suites over the test double
+visit every position, and FQD_DIFF_FULL=1 restores all ~800 runs here as well (over 30 min on a B200 box).
 """
 import importlib
 import os
@@ -33,6 +30,9 @@ def real_engine(monkeypatch):
     monkeypatch.setattr(fast_suite, "run", _real_run)
     monkeypatch.setattr(whole_suite, "run", _real_run)
     monkeypatch.setattr(whole_suite, "FAKE_DIR", "/nonexistent")      # the two tests that build their own environment
+    if not os.environ.get("FQD_DIFF_FULL"):
+        monkeypatch.setattr(fast_suite, "SWEEP_STRIDE", 7)
+        monkeypatch.setattr(whole_suite, "THIN", True)
 
 
 @pytest.mark.parametrize("kind", ["start", "length", "base"])

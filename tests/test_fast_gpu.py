@@ -269,3 +269,37 @@ def test_async_pushes_keep_the_first_error(fqd):
     assert st.err == 6 and st.err_record == 1234 and st.err_char == ord("Z")
     eng.close()
     dbuf.free()
+
+
+@pytest.mark.parametrize("grow", [False, True])
+def test_survivor_list_on_the_device(fqd, oracle, grow):
+    """fqd_keep_survivors: the ascending list of written records over a whole multi-chunk job equals the oracle's output
+    index list - with the chunks pushed asynchronously (nothing read back per chunk), and across an in-place growth."""
+    lib = fqd.load_library()
+    n, L, chunk = 50000, 150, 12000
+    rb = lib.fqd_synth_record_bytes(L)
+    dbuf = fqd.DeviceBuffer(n * rb + 4096)
+    assert lib.fqd_synth_fastq(0, dbuf.ptr, 0, n, L, 1, 7, 300, 1, 0) == 0
+    exp_idx, est = oracle.fast_se(dbuf.download(n * rb), oracle.FASTQ)
+    eng = fqd.Engine("fast", fqd.FORMAT_FASTQ, max_seq_len=L, max_records=(5000 if grow else n + 16), max_chunk_bytes=chunk * rb + 4096)
+    eng.keep_survivors(True)
+    for first in range(0, n, chunk):
+        cnt = min(chunk, n - first)
+        if grow:
+            eng.push_device(dbuf.ptr + first * rb, cnt * rb)
+        else:
+            eng.push_device_async(dbuf.ptr + first * rb, cnt * rb)
+    eng.sync()
+    got, cnt, dptr = eng.survivors()
+    st = eng.stats()
+    assert st.err == 0 and (st.total, st.dups) == (est.total, est.dups)
+    assert cnt == est.total - est.dups and dptr
+    assert np.array_equal(got, exp_idx)
+    # a second job on the same handle starts a new list
+    eng.reset()
+    eng.push_device_async(dbuf.ptr, chunk * rb)
+    eng.sync()
+    got2, _, _ = eng.survivors()
+    assert np.array_equal(got2, exp_idx[exp_idx < chunk])
+    eng.close()
+    dbuf.free()

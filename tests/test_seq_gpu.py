@@ -253,3 +253,28 @@ def test_record_tables_grow_in_place(fqd, oracle, mode, dist, paired, unordered)
         assert (o1, o2) == (e1, e2) and (st.total, st.dups, st.unmatched) == (est.total, est.dups, est.unmatched)
     else:
         _check(fqd, oracle, mode, b1, b2, fqd.FORMAT_FASTQ, dist=dist, max_seq_len=50, seg_bytes=1 << 16, max_records=300)
+
+
+@pytest.mark.parametrize("paired", [False, True])
+@pytest.mark.parametrize("dist", [0, 1, 2])
+def test_long_hamming_chains(fqd, oracle, paired, dist):
+    """Amplicon-like input: thousands of reads within a few substitutions of each other form ONE segment of the
+    tail-hamming scan (no definite break inside); the block-cooperative continuation of the greedy scan (k_ham_long) must
+    keep exactly the heads the reference's sequential loop keeps."""
+    rng = np.random.default_rng(91 + dist)
+    base = [bytes(rng.choice(list(b"ACGT"), size=60).astype(np.uint8)) for _ in range(3)]
+
+    def mutate(s, k):
+        s = bytearray(s)
+        for _ in range(k):
+            s[int(rng.integers(40, 60))] = int(rng.choice(list(b"ACGT")))
+        return bytes(s)
+    seqs = [mutate(base[int(rng.integers(0, 3))], int(rng.integers(0, 3))) for _ in range(6000)]
+    seqs += [bytes(rng.choice(list(b"ACGT"), size=60).astype(np.uint8)) for _ in range(500)]
+    rng.shuffle(seqs)
+    b1 = synth.to_fastq(seqs, mate=1)
+    b2 = None
+    if paired:
+        seqs2 = [mutate(base[int(rng.integers(0, 3))], int(rng.integers(0, 2))) for _ in range(len(seqs))]
+        b2 = synth.to_fastq(seqs2, mate=2)
+    _check(fqd, oracle, "tail-hamming", b1, b2, fqd.FORMAT_FASTQ, dist=dist, max_seq_len=60, seg_bytes=1 << 20)
