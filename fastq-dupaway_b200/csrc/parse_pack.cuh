@@ -173,10 +173,8 @@ __device__ __forceinline__ u32 find_nl(const u64* mask64, u32 pos, const u8* raw
     return PP_NONE;
 }
 
-// ---- named barrier: warps 1..7 leave their scout counts (arrive), warp 0 collects them (sync) when its look-back is done
 template <int ID, int N> __device__ __forceinline__ void bar_sync_c() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
 template <int ID, int N> __device__ __forceinline__ void bar_arrive_c() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(N) : "memory"); }
-enum { BAR_SCOUT = 1 };
 constexpr u32 PP_PACKERS = PP_THREADS - 32;        // threads of warps 1..7
 constexpr u32 PP_GROUP = 4;                        // lanes that pack one record (two key words each per 8 words)
 enum { RS_NONE = 0, RS_OK = 1, RS_BAD_START = 2, RS_LEN_MISMATCH = 3, RS_TOO_LONG = 4 };
@@ -314,7 +312,11 @@ static inline cudaError_t pp_init_tables() {
 #ifndef FQD_K1_LEAD
 #define FQD_K1_LEAD 1480     // = 2 x the CTAs resident on 148 SMs (PP_MIN_CTAS each): the tile that starts about two CTA lifetimes from now
 #endif
-constexpr u32 PP_LEAD = FQD_K1_LEAD;
+constexpr u32 PP_LEAD = FQD_K1_LEAD;        // the tile whose newlines this CTA counts
+constexpr u32 PP_PLEAD = PP_LEAD / 2;       // the tile whose prefix this CTA resolves: every count it needs is a CTA lifetime old
+#ifndef FQD_K1_OWNERS
+#define FQD_K1_OWNERS 0
+#endif
 #ifdef FQD_K1_TIMELINE
 constexpr u32 TL_STRIDE = 61, TL_SLOTS = 12, TL_CAP = 4096;
 __device__ long long g_k1_timeline[TL_CAP * TL_SLOTS];
@@ -392,7 +394,7 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
     __shared__ u32 q_off[PP_QCAP];
     __shared__ u32 q_len[PP_QCAP];
     __shared__ uint2 s_hkey[PP_HKEYS];
-    __shared__ u32 warp_sum[PP_THREADS / 32];
+    __shared__ u32 warp_sum[PP_THREADS / 32], s_scout[PP_THREADS / 32];
     __shared__ u32 s_P, s_halo;
     __shared__ __align__(8) u64 mbar;
 
@@ -417,38 +419,24 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
         mbar_expect_tx(&mbar, bytes);
         bulk_g2s(win, p.raw + base, bytes, &mbar);
     }
+    // scout loads: 16 bytes per thread and step, consecutive threads on consecutive units (any assignment will do, only
+    // the COUNT matters).  They are not looked at before this CTA's own mask and scan are done: a cold-DRAM latency
+    // that nobody waits for.
     uint4 sv[4];
-    const u64 sbase = (u64)stile * PP_TILE + tid * 64u;          // 64-bit: a chunk may end within 4 GiB of 2^32
-    if (scouting) {
-        const uint4* sp = reinterpret_cast<const uint4*>(p.raw + sbase);
+    const u64 sbase = (u64)stile * PP_TILE + tid * 16u;          // 64-bit: a chunk may end within 4 GiB of 2^32
+    const bool scout_full = (u64)(stile + 1u) * PP_TILE <= (u64)p.n;      // every tile but the chunk's last one
+    if (scout_full) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) sv[k] = __ldcg(reinterpret_cast<const uint4*>(p.raw + sbase) + k * PP_THREADS);
+    } else if (scouting) {
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
+            const u64 o = sbase + (u64)k * (PP_THREADS * 16u);
             sv[k] = make_uint4(0u, 0u, 0u, 0u);
-            if (sbase + 16u * k < (u64)p.n) sv[k] = __ldcg(sp + k);      // like the bulk copy, the last unit may reach past n
+            if (o < (u64)p.n) sv[k] = __ldcg(reinterpret_cast<const uint4*>(p.raw + o));      // like the bulk copy, the last unit may reach past n
         }
     }
     if (tid < PP_HKEYS) s_hkey[tid] = c_hkeys[((p.hash_salt >> 12) & 1u) * PP_HKEYS + tid];
-    u32 T_scout = 0;                                    // warp 0: newlines of the scout tile
-    if (scouting) {
-        u32 cnt = 0;
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            u32 m = nl_mask16(sv[k], c_nl, c_7f);
-            const u64 o = sbase + 16u * k;
-            if (o + 16u > (u64)p.n) m = o < (u64)p.n ? (m & ((1u << (u32)((u64)p.n - o)) - 1u)) : 0u;
-            cnt += __popc(m);
-        }
-        cnt = __reduce_add_sync(0xFFFFFFFFu, cnt);
-        if (lane == 0) warp_sum[warp] = cnt;
-        if (warp == 0) {
-            bar_sync_c<BAR_SCOUT, PP_THREADS>();
-#pragma unroll
-            for (int w = 0; w < PP_THREADS / 32; ++w) T_scout += warp_sum[w];
-            if (lane == 0) st_volatile_u64(p.tile_state + stile, (1ull << 32) | (u64)T_scout);
-        } else {
-            bar_arrive_c<BAR_SCOUT, PP_THREADS>();
-        }
-    }
     if (warp == 0) { __syncwarp(); mbar_wait(&mbar, 0); }
     __syncthreads();                                    // the window is staged; s_P (scouted tiles), s_hkey visible
     TL_STAMP0(tid == 0);
@@ -562,17 +550,54 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
             ++r;
         }
     }
-    __syncthreads();                                    // newline positions complete; s_P, s_halo visible
+    if (scouting) {
+        u32 c2 = 0;
+        if (scout_full) {
+            // only the COUNT matters: the 0x80 flags of a word add up to 128 x (newlines in the word) in one dp4a
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                c2 = __dp4a(nl_flags(sv[k].x, c_nl, c_7f), 0x01010101u, c2);
+                c2 = __dp4a(nl_flags(sv[k].y, c_nl, c_7f), 0x01010101u, c2);
+                c2 = __dp4a(nl_flags(sv[k].z, c_nl, c_7f), 0x01010101u, c2);
+                c2 = __dp4a(nl_flags(sv[k].w, c_nl, c_7f), 0x01010101u, c2);
+            }
+            c2 >>= 7;
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                u32 m = nl_mask16(sv[k], c_nl, c_7f);
+                const u64 o = sbase + (u64)k * (PP_THREADS * 16u);
+                if (o + 16u > (u64)p.n) m = o < (u64)p.n ? (m & ((1u << (u32)((u64)p.n - o)) - 1u)) : 0u;
+                c2 += __popc(m);
+            }
+        }
+        c2 = __reduce_add_sync(0xFFFFFFFFu, c2);
+        if (lane == 0) s_scout[warp] = c2;
+    }
+    __syncthreads();                                    // newline positions complete; s_P, s_halo, s_scout visible
     TL_STAMP(tid == 0, 4);
     const u32 WN = T + s_halo;                          // newlines in the whole window
     const bool compact = WN <= PP_NLCAP;                // the compacted positions hold every newline of the window
     const u32 P = s_P;
     if (warp == 0) {
-        // warp 0 works for the future: the prefix of the scout tile, resolved while warps 1..7 split and pack this one
+        // warp 0 works for the future while warps 1..7 split and pack this tile: it publishes the count of the scout
+        // tile (PP_LEAD ahead) and resolves the prefix of the tile PP_PLEAD ahead.  Not the same tile: the counts just
+        // before the scout tile are being published right now by this CTA's neighbours, and a look-back over them would
+        // wait for the slowest of 128 CTAs (11 500 cycles, measured); the counts before the nearer tile are a CTA
+        // lifetime old, so this look-back never spins and finds a resolved prefix within one or two hops.
         if (scouting) {
+            u32 T_scout = 0;
+#pragma unroll
+            for (int w = 0; w < PP_THREADS / 32; ++w) T_scout += s_scout[w];
+            if (lane == 0) st_volatile_u64(p.tile_state + stile, (1ull << 32) | (u64)T_scout);
+        }
+        const u32 ptile = tile + PP_PLEAD;
+        if (ptile >= PP_LEAD && ptile < p.n_tiles) {          // (the first PP_LEAD tiles were resolved by k_scan_head)
             TL_STAMP(lane == 0, 9);
-            const u32 Pu = pp_lookback(p.tile_state, stile, lane);
-            if (lane == 0) st_volatile_u64(p.tile_state + stile, (2ull << 32) | (u64)(Pu + T_scout));
+            const u32 Pu = pp_lookback(p.tile_state, ptile, lane);
+            u64 own = ld_volatile_u64(p.tile_state + ptile);
+            while ((own >> 32) == 0) own = ld_volatile_u64(p.tile_state + ptile);
+            if (lane == 0) st_volatile_u64(p.tile_state + ptile, (2ull << 32) | (u64)(Pu + (u32)own));
             TL_STAMP(lane == 0, 10);
         }
         if (compact) return;
@@ -594,8 +619,16 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
             const u32 n_round = min((u32)(PP_PACKERS / PP_GROUP), n_owned - rbase);
             // ---- geometry + validation
             u32 status = RS_NONE, gstart = 0, off = PP_NONE, ql = 0;
+#if FQD_K1_OWNERS
+            // one owner thread per record (the first n_round packer threads) hands the geometry over through shared memory
+            const u32 wtid = tid - 32u;
+            if (rbase) bar_sync_c<1, PP_PACKERS>();                       // the queue of the round before has been read
+            if (wtid < n_round) {
+                const u32 Rrel = Rrel_first + rbase + wtid;
+#else
             if (g < n_round) {
                 const u32 Rrel = Rrel_first + rbase + g;
+#endif
                 const int j0 = (int)(LPR * Rrel) - 1 - (int)c;            // local rank of the newline before the record
                 const u32 start_l = j0 < 0 ? p.skip : (u32)nlpos[j0] + 1u;
                 gstart = base + start_l;
@@ -614,10 +647,21 @@ __global__ void __launch_bounds__(PP_THREADS, PP_MIN_CTAS) k_parse_pack(const Pa
                     status = classify_record<LPR, BYTES>(p, win, base, start_l, e[0], e[1], LPR == 4 ? e[2] : e[1],
                                                   LPR == 4 ? e[3] : e[1], off, ql);
                 }
+#if FQD_K1_OWNERS
+                commit_record(p, slot_base, P / LPR + Rrel, gstart, status);
+                q_off[wtid] = off; q_len[wtid] = ql;
+            }
+            bar_sync_c<1, PP_PACKERS>();
+            off = PP_NONE; ql = 0;
+            if (g < n_round) { off = q_off[g]; ql = q_len[g]; }
+            TL_STAMP(tid == 32 && rbase == 0, 5);
+            const u32 R = P / LPR + Rrel_first + rbase + g;
+#else
             }
             TL_STAMP(tid == 32 && rbase == 0, 5);
             const u32 R = P / LPR + Rrel_first + rbase + g;
             if (g < n_round && l4 == 0) commit_record(p, slot_base, R, gstart, status);
+#endif
             // ---- pack + commit
             if (off != PP_NONE && R < p.cap && slot_base + R < p.key_capacity) {
                 u64* row = p.keys + (slot_base + R) * p.row_words + p.mate_off;

@@ -767,7 +767,8 @@ static cudaError_t seq_regrow(T** p, u64 old_count, u64 new_count, cudaStream_t 
 }
 static bool seq_grow(SeqState* s) {
     const u64 old = s->capacity;
-    for (u64 cap = old * 2; cap > old + 1024; cap = old + (cap - old) / 2) {
+    for (u64 add = std::max<u64>(old, 4096); add >= 1024; add /= 2) {      // double; with less head room when memory is short
+        const u64 cap = old + add;
         // all or nothing per attempt: a failed allocation leaves the pointers that were not reached untouched, and the
         // ones that were already moved are simply larger than they need to be
         size_t free_b = 0, total_b = 0;
@@ -909,6 +910,7 @@ static int seq_append(SeqState* s, int m, const void* buf, size_t n, bool is_dev
     if (mt.adopted) { *err = "fqd_append after fqd_adopt_device"; return FQD_ERR_INVALID; }
     const u8* src = (const u8*)buf;
     while (n) {
+        if (s->stats.err) return FQD_OK;        // a data error is sticky: what follows it is never looked at
         if (mt.segs.empty()) {
             SeqSegment sg; sg.cap = s->seg_bytes;
             SEQ_TRY(cudaMallocAsync(&sg.d, sg.cap + 4096, s->stream));
