@@ -43,8 +43,7 @@ def _sharded_fast(args, fqd, lib, sharded2, dist, gloo, rank, dev, world, n_per_
     sharded2.connect(ops, dist, rank, world)
     chunks = [tuple(x for m in range(mates) for x in (raw[m].ptr + c * chunk_reads * REC, sizes[c] * REC)) for c in range(n_chunks)]
 
-    def barrier():
-        dist.barrier(group=gloo)
+    barrier = gloo          # a callable: the shared-memory host barrier
 
     def step():
         barrier()
@@ -112,7 +111,7 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
     lib = fqd.load_library()
     dev = local_rank
     torch.cuda.set_device(dev)
-    gloo = dist.new_group(backend="gloo")                 # host barriers (pure CPU: nothing is launched on the GPUs for them)
+    gloo = sharded2.HostBarrier(fqd, dist, rank, world)   # host barriers: shared memory + two atomics, nothing is launched on the GPUs for them
     REC = b.REC_BYTES
     sampler = b.ClockSampler(dev)
     if rank == 0:
@@ -130,7 +129,7 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
                           "how": "rank 0 pushed the same global stream (chunks in global input order) through one single-GPU engine, outside the timed region"}
             except Exception as ex:
                 verify = {"equal": None, "error": repr(ex)}
-        dist.barrier(group=gloo)
+        gloo()
         if rank == 0 and verify.get("equal") is False:
             raise AssertionError(f"sharded duplicate count differs from the single-GPU run: {verify}")
 
@@ -149,7 +148,7 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
                 pv = {"single_gpu_duplicates": single, "sharded_duplicates": pe["dups"], "equal": single == pe["dups"]}
             except Exception as ex:
                 pv = {"equal": None, "error": repr(ex)}
-        dist.barrier(group=gloo)
+        gloo()
         if rank == 0:
             assert pv is None or pv.get("equal") is not False, pv
             ach = pe["total"] * 860 / (pe["ms_per_step"] / 1e3) / 1e9
@@ -196,6 +195,7 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
                              "unit": "GB/s", "frac": achieved / peak, "traffic": None, "alg_bytes_per_read": b.K1_BYTES_PER_READ,
                              "avg_launch_ms": k1_ms, "kernel_share_of_step": prof.parse_ms / r["ms_total"],
                              "insert_share_of_step": prof.insert_ms / r["ms_total"],
+                             "scatter_share_of_step": prof.scatter_ms / r["ms_total"],
                              "note": "rank 0's K1 launches, timed while the other stream of the same GPU inserts the previous chunk"},
                 "exchange": {"row_bytes": r["row_bytes"], "bytes_over_nvlink_per_gpu_per_step": int(n_per_rank * (r["row_bytes"] + 1) * (world - 1) / world),
                              "region_rows": r["region_rows"], "host_barriers_per_chunk": 1,
@@ -203,5 +203,6 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
                                      "from the SMs); flags written back the same way; ordering by interprocess CUDA events"},
                 "verify": verify, "duplicates_removed": r["dups"], "input_GBps": n_total * REC / (ms_per_step / 1000.0) / 1e9, "modes": modes}
         print(json.dumps(line), flush=True)
-    dist.barrier(group=gloo)
+    gloo()
+    gloo.close()
     dist.destroy_process_group()

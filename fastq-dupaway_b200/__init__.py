@@ -63,7 +63,8 @@ class Emission(C.Structure):
 
 class Profile(C.Structure):
     _fields_ = [("parse_ms", C.c_double), ("parse_launches", C.c_uint64), ("parse_bytes", C.c_uint64),
-                ("parse_records", C.c_uint64), ("insert_ms", C.c_double), ("insert_launches", C.c_uint64)]
+                ("parse_records", C.c_uint64), ("insert_ms", C.c_double), ("insert_launches", C.c_uint64),
+                ("scatter_ms", C.c_double), ("scatter_launches", C.c_uint64)]
 
 
 _lib = None

@@ -9,9 +9,12 @@
 //     round-robin in input order, sources in rank order, positions in record order) - K2's "smallest slot wins" rule
 //     keeps exactly the record the reference keeps (src/hash_dup_remover.hpp:133-139);
 //   * k_shard_count2 / k_shard_bases2 / k_shard_scatter2 partition a chunk's rows stably by owner in one pass over the
-//     rows (per-block counts -> exclusive bases -> ranks by warp match) and the scatter writes every row STRAIGHT INTO ITS
-//     OWNER'S KEY STORE over mapped peer memory (NVLink / NVSwitch, 16-byte stores from the SMs), its hash into the
-//     owner's per-chunk hash regions, and the per-source count into the owner's header;
+//     rows (per-block counts -> exclusive bases -> ranks by warp match) into a staging area that is laid out like the
+//     owners' regions; the COPY ENGINES then move every owner's part STRAIGHT INTO THAT OWNER'S KEY STORE and hash
+//     regions over mapped peer memory (fixed-size copies of region_rows rows: no size has to cross the host), while the
+//     SMs already split the next chunk.  (The first version of this file scattered with 16-byte stores from the SMs:
+//     6.3 GB per GPU and job over NVLink on the pack stream, K1 of the next chunk behind it - 0.69 of linear at 8 GPUs.)
+//     The per-source counts go into the owner's header with plain peer stores;
 //   * the owner inserts region by region (k_insert2: the same probe as K2), and writes one flag byte per row back into
 //     the SOURCE's flag regions, again over peer memory; k_shard_flags2 puts them at the source's records.
 // Ordering between ranks is carried by interprocess CUDA events (fqd_shard2_* in fqd_api.cu); the host only enqueues.
@@ -37,9 +40,9 @@ struct Shard2Src {
     u32* dest;                          // [cap] owner << 27 | position, for the way back
     u64* final_hash;                    // [cap]
     u32* totals;                        // [S2_MAX + 1]: rows per owner of this chunk, [S2_MAX] = overflow flag
+    u64* stage_rows;                    // [n_shards * region_rows * row_words] rows grouped by owner (this chunk parity)
+    u64* stage_hash;                    // [n_shards * region_rows]
     // per owner (mapped peer memory; [me] = my own)
-    u64* peer_keys[S2_MAX];             // key store
-    u64* peer_hash[S2_MAX];             // hash regions of chunk parity: [n_shards * region_rows]
     u32* peer_counts[S2_MAX];           // header of chunk parity: [n_shards]
 };
 
@@ -145,13 +148,12 @@ __global__ void __launch_bounds__(256) k_shard_scatter2(const Shard2Src p) {
             const u32 d = (o << 27) | pos;
             s_pos[i - lo] = d;
             p.dest[i] = d;
-            if (pos < p.region_rows) p.peer_hash[o][(u64)p.me * p.region_rows + pos] = p.final_hash[i];
+            if (pos < p.region_rows) p.stage_hash[(u64)o * p.region_rows + pos] = p.final_hash[i];
         }
     }
     __syncthreads();
-    // rows: 16 bytes per thread, the lanes of a row next to each other (64-byte pieces over NVLink)
+    // rows: 16 bytes per thread, the lanes of a row next to each other
     const u32 q = p.row_words / 2;                                     // 16-byte pieces per row
-    const u64 region0 = (p.chunk * p.n_shards + p.me) * (u64)p.region_rows;
     const u32 pieces = (hi - lo) * q;
     for (u32 t = threadIdx.x; t < pieces; t += 256) {
         const u32 r = t / q, w = t % q;
@@ -159,7 +161,7 @@ __global__ void __launch_bounds__(256) k_shard_scatter2(const Shard2Src p) {
         const u32 o = d >> 27, pos = d & 0x7FFFFFFu;
         if (pos >= p.region_rows) continue;
         const ulonglong2 v = *reinterpret_cast<const ulonglong2*>(p.stage_keys + (u64)(lo + r) * p.row_words + 2u * w);
-        *reinterpret_cast<ulonglong2*>(p.peer_keys[o] + (region0 + pos) * p.row_words + 2u * w) = v;
+        *reinterpret_cast<ulonglong2*>(p.stage_rows + ((u64)o * p.region_rows + pos) * p.row_words + 2u * w) = v;
     }
 }
 

@@ -7,6 +7,7 @@
 #include <condition_variable>
 #include <mutex>
 #include <cstdlib>
+#include <cmath>
 #include <cstring>
 #include <iostream>
 #include <fstream>
@@ -188,7 +189,26 @@ void HashDupRemover::filterPE(const std::string& infile1, const std::string& inf
     else run_ordered(in, out, 2);
 }
 
+// FQD_DEVICES="0,1,2,3" (CUDA ordinals; the same ordinal may be listed twice - two shards on one GPU, for tests)
+static std::vector<int> devices_from_env() {
+    std::vector<int> d;
+    const char* e = std::getenv("FQD_DEVICES");
+    if (!e) return d;
+    for (const char* p = e; *p;) {
+        char* end = nullptr;
+        const long v = std::strtol(p, &end, 10);
+        if (end == p) break;
+        d.push_back((int)v);
+        p = *end == ',' ? end + 1 : end;
+    }
+    return d;
+}
+
 void HashDupRemover::run_ordered(const std::string* in, const std::string* out, int mates) {
+    {
+        const std::vector<int> devs = devices_from_env();
+        if (devs.size() > 1) { run_ordered_multi(in, out, mates, devs); return; }
+    }
     const int lpr = m_fasta ? 2 : 4;
     const char lead = m_fasta ? '>' : '@';
     // pinned staging: 3 blocks (head room + data) per input file inside the -m budget
@@ -366,6 +386,203 @@ void HashDupRemover::run_ordered(const std::string* in, const std::string* out, 
         return;
     }
     throw std::runtime_error("input exceeds the device capacity of the fast-mode key store");
+}
+
+
+// -------------------------------------------------------------------------------------------------------------
+// --fast over several GPUs of the box (FQD_DEVICES): the chunks of the input are dealt round-robin to one engine per
+// GPU, every engine owns one hash range of the key space (csrc/shard2.cuh: rows travel over NVLink into the owner's
+// key store, flags come back the same way), and the survivors are written in input order exactly as in run_ordered.
+// What this buys is CAPACITY - the key set of an input that one GPU cannot hold (BASELINE configs[4]: 1 G pairs = 128 GB
+// of key rows + table) is spread over N x 180 GB; the files themselves are read and written by the same host threads
+// at the same speed.  One host thread enqueues everything in program order, so the engines need no barrier.
+void HashDupRemover::run_ordered_multi(const std::string* in, const std::string* out, int mates, const std::vector<int>& devices) {
+    const int lpr = m_fasta ? 2 : 4;
+    const char lead = m_fasta ? '>' : '@';
+    const uint32_t N = (uint32_t)devices.size();
+    size_t block = (size_t)m_memlimit / (size_t)(mates * (N + 3) * 2);
+    block = std::min<size_t>(std::max<size_t>(block, 4u << 20), 64u << 20) & ~(size_t)4095;
+    block = test_block_override(block);
+    double growth = 1.0;
+    unsigned seq_growth = 0;
+
+    for (int attempt = 0; attempt < 8; ++attempt) {
+        std::vector<std::unique_ptr<OutputFile>> outs;
+        MateStream ms[2];
+        std::vector<std::unique_ptr<AsyncWriter>> writers;
+        std::vector<EnginePtr> eng;
+        for (int m = 0; m < mates; ++m) outs.emplace_back(new OutputFile(out[m]));
+        for (int m = 0; m < mates; ++m) ms[m].reader.reset(new BlockReader(in[m], block, (int)N + 3));
+        // blocks go back to their reader only behind the writes of the round that still reads from them
+        std::vector<Block*> deferred[2];
+        for (int m = 0; m < mates; ++m) {
+            writers.emplace_back(new AsyncWriter(*outs[m]));
+            std::vector<Block*>* d = &deferred[m];
+            ms[m].release = [d](Block* b) { d->push_back(b); };
+        }
+        auto flush_deferred = [&] {
+            for (int m = 0; m < mates; ++m) {
+                AsyncWriter* w = writers[m].get(); BlockReader* r = ms[m].reader.get();
+                for (Block* b : deferred[m]) w->then([r, b] { r->release(b); });
+                deferred[m].clear();
+            }
+        };
+        auto close_outputs = [&] { for (auto& w : writers) w->drain(); for (auto& o : outs) o->close(); check_outputs(outs, out); };
+        for (int m = 0; m < mates; ++m)
+            if (!ms[m].refill()) throw std::runtime_error("Not enough memory to read a single object!");
+        for (int m = 0; m < mates; ++m)
+            if (ms[m].len && ms[m].ptr[0] != lead) {
+                fqd_stats_t st; memset(&st, 0, sizeof st); st.err = FQD_ERR_BAD_START; st.err_char = (unsigned char)ms[m].ptr[0];
+                throw_data_error(st, m_fasta);
+            }
+        size_t max_seq = 0; double avg_rec = 1e9; uint64_t est_records = 0;
+        for (int m = 0; m < mates; ++m) {
+            size_t ms_ = 0; double ar = 0;
+            sample_geometry(ms[m].ptr, std::min<size_t>(ms[m].len, 8u << 20), lpr, ms_, ar);
+            max_seq = std::max(max_seq, ms_);
+            double expand = gz_expansion(in[m], *ms[m].reader);
+            uint64_t est = (uint64_t)((double)file_size_or_zero(in[m]) * expand / std::max(ar, 8.0) * 1.02) + (1u << 16);
+            est_records = m == 0 ? est : std::min(est_records, est);
+            avg_rec = std::min(avg_rec, std::max(ar, 8.0));
+        }
+        // a chunk is at most 2 blocks of the mate with the shortest records; an owner gets 1/N of it from every source
+        const uint64_t chunk_records = (uint64_t)((double)(2 * block + 4096) / avg_rec * 1.1 * growth) + 1024;
+        uint64_t region = chunk_records / N + (uint64_t)(8.0 * std::sqrt((double)chunk_records / N)) + chunk_records / (N * 32) + 1024;
+        region = (region + 15) / 16 * 16;
+        const uint64_t n_chunks_est = (uint64_t)((double)est_records * growth / std::max<double>(1.0, (double)block / avg_rec)) / N + 4;   // rounds
+        fqd_config cfg;
+        memset(&cfg, 0, sizeof cfg);
+        cfg.abi_version = FQD_ABI_VERSION; cfg.mode = FQD_MODE_FAST;
+        cfg.format = m_fasta ? FQD_FORMAT_FASTA : FQD_FORMAT_FASTQ; cfg.paired = mates == 2;
+        cfg.max_seq_len = (uint32_t)((std::max<size_t>(max_seq, 20) + 19) / 20 * 20) << seq_growth;
+        cfg.max_records = n_chunks_est * N * region + 1024;       // rounds x (one region per source)
+        cfg.max_chunk_bytes = 2 * block + 4096;
+        cfg.max_chunk_records = chunk_records;
+        for (uint32_t r = 0; r < N; ++r) {
+            cfg.device = devices[r];
+            fqd_handle* hraw = nullptr;
+            int rc = fqd_create(&cfg, &hraw);
+            if (rc) throw_engine_error(nullptr, rc);
+            eng.emplace_back(hraw);
+            rc = fqd_shard2_init(hraw, N, r, (uint32_t)region);
+            if (rc) throw_engine_error(hraw, rc);
+        }
+        for (uint32_t a = 0; a < N; ++a)
+            for (uint32_t b = 0; b < N; ++b)
+                if (a != b) { int rc = fqd_shard2_link(eng[a].get(), b, eng[b].get()); if (rc) throw_engine_error(eng[a].get(), rc); }
+        trace("engines created and linked");
+
+        struct InFlight { const char* ptr[2]; size_t len[2]; uint64_t n; uint64_t consumed[2]; int next_byte[2]; bool pushed; };
+        std::vector<InFlight> fl(N);
+        std::vector<Run> runs;
+        struct { bool valid = false; std::vector<char> bytes[2]; } held;
+        bool restart = false, input_done = false;
+        uint64_t total = 0, dups = 0, first_record = 0;
+        for (uint64_t round = 0; !input_done && !restart; ++round) {
+            // ---- deal one chunk to every engine, in input order (an engine without input gets an empty chunk)
+            uint32_t n_pushed = 0;
+            for (uint32_t r = 0; r < N; ++r) {
+                InFlight& f = fl[r];
+                f.pushed = false; f.n = 0;
+                if (!input_done) {
+                    for (int m = 0; m < mates; ++m)
+                        if (ms[m].len < block / 2) ms[m].refill();
+                }
+                for (int m = 0; m < 2; ++m) { f.ptr[m] = m < mates ? ms[m].ptr : nullptr; f.len[m] = (m < mates && !input_done) ? ms[m].len : 0; f.consumed[m] = 0; f.next_byte[m] = -1; }
+                int rc = fqd_shard2_push_host(eng[r].get(), round, f.ptr[0], f.len[0], mates == 2 ? f.ptr[1] : nullptr, mates == 2 ? f.len[1] : 0, &f.n, f.consumed);
+                if (rc == FQD_ERR_CAPACITY) { check_restart_possible(in, mates, "the key stores could not hold another round of chunks"); growth *= 2.0; restart = true; break; }
+                if (rc) throw_engine_error(eng[r].get(), rc);
+                f.pushed = true; ++n_pushed;
+                if (input_done) continue;
+                for (int m = 0; m < mates; ++m)
+                    f.next_byte[m] = f.consumed[m] < f.len[m] ? (unsigned char)f.ptr[m][f.consumed[m]] : ms[m].peek_next_byte();
+                for (int m = 0; m < mates; ++m) { ms[m].ptr += f.consumed[m]; ms[m].len -= f.consumed[m]; }
+                if (f.n == 0) {
+                    // nothing complete in what we have: read more, or stop at the end of a file
+                    bool progressed = false;
+                    for (int m = 0; m < mates; ++m) {
+                        size_t cnt = 0; const char* c = ms[m].ptr; const char* e2 = c + ms[m].len;
+                        while (cnt < (size_t)lpr && c < e2) { const char* nl = (const char*)memchr(c, '\n', e2 - c); if (!nl) break; ++cnt; c = nl + 1; }
+                        if (cnt != (size_t)lpr) progressed |= ms[m].refill();
+                    }
+                    if (!progressed) input_done = true;      // a file is exhausted: stop at the shorter one
+                }
+            }
+            if (restart) break;
+            for (uint32_t r = 0; r < N; ++r) { int rc = fqd_shard2_insert(eng[r].get(), round); if (rc) throw_engine_error(eng[r].get(), rc); }
+            for (uint32_t r = 0; r < N; ++r) { int rc = fqd_shard2_apply(eng[r].get(), round); if (rc) throw_engine_error(eng[r].get(), rc); }
+            // ---- the round's results, in input order: the same rules as run_ordered
+            for (uint32_t r = 0; r < N && !restart; ++r) {
+                InFlight& f = fl[r];
+                fqd_chunk_result res;
+                int rc = fqd_shard2_result(eng[r].get(), first_record, f.len[0], f.len[1], &res);
+                if (rc) throw_engine_error(eng[r].get(), rc);
+                fqd_stats_t st;
+                fqd_stats(eng[r].get(), &st);
+                if (st.err == FQD_ERR_SEQ_TOO_LONG) { check_restart_possible(in, mates, "a later sequence is longer than the key rows sized from the first block"); ++seq_growth; restart = true; break; }
+                if (st.err == FQD_ERR_CAPACITY) { check_restart_possible(in, mates, "a key-store region overflowed"); growth *= 2.0; restart = true; break; }
+                size_t n = (size_t)res.n_records;
+                uint64_t chunk_dups = n - res.n_survivors;
+                int tail_err_mate = -1, tail_char = 0;
+                if (st.err == 0 && n > 0)
+                    for (int m = 0; m < mates && tail_err_mate < 0; ++m)
+                        if (f.next_byte[m] >= 0 && f.next_byte[m] != lead) { tail_err_mate = m; tail_char = f.next_byte[m]; }
+                if (tail_err_mate >= 0) { const uint8_t last_dup = res.dup[n - 1]; n -= 1; chunk_dups -= last_dup; }
+                const bool stops_here = st.err != 0 || tail_err_mate >= 0;
+                if (held.valid && (n > 0 || stops_here)) {
+                    const bool next_is_malformed = (st.err == FQD_ERR_BAD_START || st.err == FQD_ERR_LEN_MISMATCH) && st.err_record == res.first_record;
+                    if (!next_is_malformed)
+                        for (int m = 0; m < mates; ++m) writers[m]->write_owned(std::move(held.bytes[m]));
+                    held.valid = false;
+                }
+                size_t n_now = n;
+                if (n > 0 && !stops_here) {
+                    n_now = n - 1;
+                    if (!res.dup[n - 1]) {
+                        held.valid = true;
+                        for (int m = 0; m < mates; ++m) held.bytes[m].assign(f.ptr[m] + res.rec_start[m][n - 1], f.ptr[m] + res.rec_start[m][n]);
+                    }
+                }
+                for (int m = 0; m < mates; ++m) {
+                    const size_t bytes = survivor_runs(res.rec_start[m], res.dup, n_now, runs);
+                    writers[m]->write_runs(f.ptr[m], std::move(runs), bytes);
+                    runs = std::vector<Run>();
+                }
+                total += n; dups += chunk_dups; first_record += res.n_records;
+                if (tail_err_mate >= 0) {
+                    st.err = FQD_ERR_BAD_START; st.err_char = tail_char;
+                    close_outputs();
+                    throw_data_error(st, m_fasta);
+                }
+                if (st.err) {
+                    if (st.err == FQD_ERR_BAD_BASE && st.err_record == 0)
+                        for (int m = 0; m < mates; ++m) writers[m]->write_owned(std::vector<char>(f.ptr[m] + res.rec_start[m][0], f.ptr[m] + res.rec_start[m][1]));
+                    close_outputs();
+                    const int em = st.err_mate;
+                    const size_t e = (size_t)(st.err_record - res.first_record);
+                    const char* rec = nullptr; size_t rl = 0;
+                    if (st.err == FQD_ERR_LEN_MISMATCH) { rec = f.ptr[em] + res.rec_start[em][e]; rl = f.len[em] - res.rec_start[em][e]; }
+                    throw_data_error(st, m_fasta, rec, rl);
+                }
+            }
+            flush_deferred();
+        }
+        if (restart) { for (auto& w : writers) w->drain(); continue; }
+        if (held.valid)
+            for (int m = 0; m < mates; ++m) writers[m]->write_owned(std::move(held.bytes[m]));
+        if (total == 0) {
+            fqd_stats_t st; memset(&st, 0, sizeof st); st.err = FQD_ERR_EMPTY;
+            throw_data_error(st, m_fasta);
+        }
+        flush_deferred();
+        close_outputs();
+        if (m_verbose) {
+            if (mates == 1) std::cout << total << " reads processed, out of which " << dups << " duplicates were removed.\n";
+            else std::cout << total << " read pairs processed, out of which " << dups << " duplicates were removed.\n";
+        }
+        return;
+    }
+    throw std::runtime_error("input exceeds the device capacity of the fast-mode key stores");
 }
 
 // -------------------------------------------------------------------------------------------------------------

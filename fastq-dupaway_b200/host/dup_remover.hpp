@@ -8,6 +8,7 @@
 #pragma once
 #include <sys/types.h>
 #include <string>
+#include <vector>
 
 #include "options.hpp"
 
@@ -22,6 +23,8 @@ public:
                   const std::string& outfile1, const std::string& outfile2, bool unordered);
 private:
     void run_ordered(const std::string* in, const std::string* out, int mates);
+    // FQD_DEVICES=0,1,...: the duplicate set is sharded by hash range over several GPUs (one process, one thread)
+    void run_ordered_multi(const std::string* in, const std::string* out, int mates, const std::vector<int>& devices);
     ssize_t m_memlimit;
     bool m_fasta, m_verbose;
     int m_device;

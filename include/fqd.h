@@ -236,15 +236,16 @@ int fqd_shard_read_flags(fqd_handle* h, void* dst, size_t n);
  *                        interprocess events of this rank;
  *   fqd_shard2_export    fqd_shard2_blob_bytes() bytes (CUDA IPC handles of the key store, the regions and the events); the
  *                        ranks all-gather them and fqd_shard2_import every peer's;
- *   fqd_shard2_pack      split + pack chunk number `chunk` of THIS rank's input, partition its rows stably by owner, write
- *                        every row straight into its owner's key store over mapped peer memory (NVLink), record "scattered";
+ *   fqd_shard2_pack      split + pack chunk number `chunk` of THIS rank's input, partition its rows stably by owner into a
+ *                        staging area, let the copy engines move every owner's part straight into that owner's key store
+ *                        over mapped peer memory (NVLink; fixed-size copies, nothing crosses the host), record "scattered";
  *   fqd_shard2_insert    owner side: waits (on the device) for every source's "scattered" of that chunk, inserts region by
  *                        region, writes one flag byte per row into the SOURCE's flag regions, records "flags sent";
  *   fqd_shard2_apply     source side: waits (on the device) for every owner's "flags sent", stores the flags against this rank's
  *                        records (fqd_shard2_read_flags) and counts the duplicates;
  *   fqd_shard2_finish    waits for this rank's streams; totals of this rank's records; data errors / a region overflow are
  *                        reported through fqd_stats.
- * Every call but finish only enqueues.  The caller's loop is  pack(0) | for c: [pack(c+1)] insert(c) | apply(c)  with a host
+ * Every call but finish only enqueues.  The caller's loop is  pack(0) pack(1) | for c: insert(c) | apply(c) [pack(c+2)]  with a host
  * barrier at every "|": it makes sure an event has been RECORDED by its owner before a peer enqueues the wait for it.
  * Chunks must be numbered alike on every rank (a rank whose slice is shorter passes empty chunks).
  */
@@ -258,8 +259,23 @@ int fqd_shard2_apply(fqd_handle* h, uint64_t chunk);
 int fqd_shard2_finish(fqd_handle* h, uint64_t* n_records, uint64_t* n_dups);
 int fqd_shard2_reset(fqd_handle* h);
 int fqd_shard2_read_flags(fqd_handle* h, void* dst, size_t n);
+/* The same protocol inside ONE process that drives several GPUs (the drop-in binary): fqd_shard2_link instead of export /
+ * import (peer access between the devices of one process, ordinary events), no barriers (one thread enqueues in order).
+ * fqd_shard2_push_host = pack for a chunk in pinned host memory; it waits until the chunk is split and reports the records
+ * (pairs) it holds and where the incomplete tail of each mate begins.  fqd_shard2_result, after insert(chunk) on EVERY handle
+ * and apply(chunk) on this one, returns what fqd_push would have returned for the chunk. */
+int fqd_shard2_link(fqd_handle* h, uint32_t rank, fqd_handle* peer);
+int fqd_shard2_push_host(fqd_handle* h, uint64_t chunk, const char* r1, size_t n1, const char* r2, size_t n2,
+                         uint64_t* n_records, uint64_t* consumed);
+int fqd_shard2_result(fqd_handle* h, uint64_t first_record, size_t n1, size_t n2, fqd_chunk_result* res);
 int fqd_shard2_timer_start(fqd_handle* h);
 int fqd_shard2_timer_stop(fqd_handle* h, double* ms);
+
+/* Host barrier between the rank processes of one box (POSIX shared memory, a few microseconds): the "|" of the loop above.
+ * Every rank opens the same name (unique per job), rank 0 unlinks it at close. */
+int fqd_hostbar_open(const char* name, uint32_t n_ranks, void** out);
+int fqd_hostbar_wait(void* bar);
+int fqd_hostbar_close(void* bar, const char* unlink_name);
 
 /* Statistics / sticky data error (feeds the -v lines and the reference's error messages). */
 int fqd_stats(fqd_handle* h, fqd_stats_t* out);
@@ -275,6 +291,7 @@ int fqd_timer_stop(fqd_handle* h, double* ms);
 typedef struct {
     double   parse_ms;   uint64_t parse_launches;   uint64_t parse_bytes;    uint64_t parse_records;
     double   insert_ms;  uint64_t insert_launches;
+    double   scatter_ms; uint64_t scatter_launches;   /* multi-GPU --fast: partition by owner + scatter over peer memory */
 } fqd_profile_t;
 int fqd_profile_enable(fqd_handle* h, int on);
 int fqd_profile_get(fqd_handle* h, fqd_profile_t* out);

@@ -131,3 +131,29 @@ def test_region_rows_margin():
     for chunk, world in ((10_000_000, 8), (10_000_000, 2), (1000, 3)):
         r = sharded2.region_rows_for(chunk, world)
         assert r > chunk / world and r < 1.2 * chunk / world + 8192
+
+
+def _bar_worker(rank, world, port, shared):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import importlib
+    fqd = importlib.import_module("fastq-dupaway_b200")
+    sharded2 = importlib.import_module("fastq-dupaway_b200.sharded2")
+    bar = sharded2.HostBarrier(fqd, dist, rank, world)
+    cnt = np.lib.format.open_memmap(Path(shared) / "cnt.npy", mode="r+")
+    for it in range(300):
+        cnt[rank] = it + 1
+        bar()
+        assert all(int(cnt[r]) >= it + 1 for r in range(world)), (it, list(cnt))      # nobody passes before everybody arrived
+        bar()
+    bar.close()
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_shared_memory_host_barrier(tmp_path):
+    world = 3
+    np.lib.format.open_memmap(tmp_path / "cnt.npy", mode="w+", dtype=np.int64, shape=(world,)).flush()
+    port = 29500 + (os.getpid() * 11 + 5) % 2000
+    mp.spawn(_bar_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
