@@ -56,6 +56,9 @@ struct Shard2State {
     u64* d_stage_hash[2] = {nullptr, nullptr};
     cudaStream_t s_pack = nullptr, s_ins = nullptr, s_copy = nullptr;
     cudaEvent_t ev_scatter[2] = {nullptr, nullptr}, ev_flags[2] = {nullptr, nullptr}, ev_staged[2] = {nullptr, nullptr};
+    // the same two, as plain events, for peers of the SAME process (waiting on an interprocess-capable event of another
+    // device from inside its own process crashes driver 580.159 in cuStreamWaitEvent)
+    cudaEvent_t lv_scatter[2] = {nullptr, nullptr}, lv_flags[2] = {nullptr, nullptr};
     u64* peer_keys[S2_MAX] = {}; u64* peer_hash[S2_MAX] = {}; u32* peer_counts[S2_MAX] = {}; u8* peer_flags_in[S2_MAX] = {};
     cudaEvent_t peer_scatter[S2_MAX][2] = {}, peer_flags[S2_MAX][2] = {};
     bool imported[S2_MAX] = {}, linked[S2_MAX] = {};      // linked: a handle of this process (nothing to close)
@@ -914,7 +917,7 @@ static void shard2_free(fqd_handle* h) {
     cudaFree(s->d_counts); cudaFree(s->d_flags); cudaFree(s->d_flags_in); cudaFree(s->d_ndups); cudaFree(s->d_chunk_n);
     if (s->h_run2) cudaFreeHost(s->h_run2);
     if (s->h_totals) cudaFreeHost(s->h_totals);
-    for (int k = 0; k < 2; ++k) { if (s->ev_scatter[k]) cudaEventDestroy(s->ev_scatter[k]); if (s->ev_flags[k]) cudaEventDestroy(s->ev_flags[k]); }
+    for (int k = 0; k < 2; ++k) { if (s->ev_scatter[k]) cudaEventDestroy(s->ev_scatter[k]); if (s->ev_flags[k]) cudaEventDestroy(s->ev_flags[k]); if (s->lv_scatter[k]) cudaEventDestroy(s->lv_scatter[k]); if (s->lv_flags[k]) cudaEventDestroy(s->lv_flags[k]); }
     if (s->t_ins) cudaEventDestroy(s->t_ins);
     if (s->s_pack) cudaStreamDestroy(s->s_pack);
     if (s->s_ins) cudaStreamDestroy(s->s_ins);
@@ -967,6 +970,8 @@ extern "C" int fqd_shard2_init(fqd_handle* h, uint32_t n_shards, uint32_t me, ui
     for (int k = 0; k < 2; ++k) {
         CUDA_TRY(h, cudaEventCreateWithFlags(&s->ev_scatter[k], cudaEventDisableTiming | cudaEventInterprocess));
         CUDA_TRY(h, cudaEventCreateWithFlags(&s->ev_flags[k], cudaEventDisableTiming | cudaEventInterprocess));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&s->lv_scatter[k], cudaEventDisableTiming));
+        CUDA_TRY(h, cudaEventCreateWithFlags(&s->lv_flags[k], cudaEventDisableTiming));
     }
     s->peer_keys[me] = h->d_keys; s->peer_hash[me] = s->d_hash_regions; s->peer_counts[me] = s->d_counts; s->peer_flags_in[me] = s->d_flags_in;
     for (int k = 0; k < 2; ++k) { s->peer_scatter[me][k] = s->ev_scatter[k]; s->peer_flags[me][k] = s->ev_flags[k]; }
@@ -1101,6 +1106,7 @@ extern "C" int fqd_shard2_pack(fqd_handle* h, uint64_t chunk, const void* d_r1, 
                                     (size_t)s->region_rows * sizeof(u64), cudaMemcpyDefault, s->s_copy));
     }
     CUDA_TRY(h, cudaEventRecord(s->ev_scatter[par], s->s_copy));
+    CUDA_TRY(h, cudaEventRecord(s->lv_scatter[par], s->s_copy));
     s->chunks_packed++;
     CUDA_TRY(h, cudaGetLastError());
     return FQD_OK;
@@ -1135,6 +1141,7 @@ extern "C" int fqd_shard2_insert(fqd_handle* h, uint64_t chunk) {
     k_shard_flags_send2<<<h->sm_count, 256, 0, st>>>(fb);
     h->launches += 3;
     CUDA_TRY(h, cudaEventRecord(s->ev_flags[par], st));
+    CUDA_TRY(h, cudaEventRecord(s->lv_flags[par], st));
     s->chunks_inserted++;
     CUDA_TRY(h, cudaGetLastError());
     return FQD_OK;
@@ -1229,7 +1236,7 @@ extern "C" int fqd_shard2_link(fqd_handle* h, uint32_t rank, fqd_handle* peer) {
     }
     Shard2State* q = peer->s2;
     s->peer_keys[rank] = peer->d_keys; s->peer_hash[rank] = q->d_hash_regions; s->peer_counts[rank] = q->d_counts; s->peer_flags_in[rank] = q->d_flags_in;
-    for (int k = 0; k < 2; ++k) { s->peer_scatter[rank][k] = q->ev_scatter[k]; s->peer_flags[rank][k] = q->ev_flags[k]; }
+    for (int k = 0; k < 2; ++k) { s->peer_scatter[rank][k] = q->lv_scatter[k]; s->peer_flags[rank][k] = q->lv_flags[k]; }
     s->imported[rank] = true; s->linked[rank] = true;
     return FQD_OK;
 }

@@ -1,5 +1,7 @@
 // main.cpp - the drop-in `fastq-dupaway` binary: argument handling and dispatch as in the reference
 // (src/main.cpp:181-262), with the two drivers backed by the B200 engine (libfqd_cuda.so).
+#include <execinfo.h>
+#include <signal.h>
 #include <unistd.h>
 
 #include <cstdio>
@@ -12,7 +14,18 @@
 
 using namespace fqdhost;
 
+// FQD_BACKTRACE=1: raw return addresses on a crash (resolve with addr2line against the binary / libfqd_cuda.so)
+static void crash_handler(int sig) {
+    void* frames[48];
+    const int n = backtrace(frames, 48);
+    const char msg[] = "fastq-dupaway: fatal signal, backtrace:\n";
+    (void)!write(2, msg, sizeof msg - 1);
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
 int main(int argc, char** argv) {
+    if (std::getenv("FQD_BACKTRACE")) { signal(SIGSEGV, crash_handler); signal(SIGBUS, crash_handler); signal(SIGABRT, crash_handler); }
     Options opts;
     if (!parse_args(argc, argv, opts)) return 1;
     trace("start");

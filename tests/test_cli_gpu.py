@@ -242,3 +242,57 @@ def test_single_member_gzip_inflated_block_parallel(tmp_path, oracle):
     exp, _, est = oracle.run_oracle("fast", oracle.FASTQ, buf)
     assert (tmp_path / "out.fq").read_bytes() == exp
     assert res.stdout == f"{est.total} reads processed, out of which {est.dups} duplicates were removed.\n"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("devices,block", [("0,0", 1 << 16), ("0,0,0", 1 << 18), ("0,0", None)])
+@pytest.mark.parametrize("paired", [False, True])
+def test_fast_sharded_over_several_engines(tmp_path, oracle, devices, block, paired):
+    """FQD_DEVICES: the duplicate set of `--fast` is sharded by hash range over several engines of ONE process (here: on the
+    same GPU - the protocol is the same, rows travel through the copy engines into the owner's key store); chunks are dealt
+    round-robin, survivors are written in input order: outputs and -v line identical to the oracle's."""
+    s1, s2 = synth.make_pair(60000, seed=95, read_len=100, var_len=True, n_frac=0.02, dup_frac=0.4)
+    s2 = s2[:-7]
+    b1, b2 = synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2)
+    (tmp_path / "a.fq").write_bytes(b1)
+    (tmp_path / "b.fq").write_bytes(b2)
+    env = {"FQD_DEVICES": devices}
+    if block:
+        env["FQD_BLOCK_BYTES"] = str(block)
+    if paired:
+        res = run("-i", tmp_path / "a.fq", "-u", tmp_path / "b.fq", "-o", tmp_path / "o1.fq", "-p", tmp_path / "o2.fq", "--fast", "-v", env=env)
+        e1, e2, est = oracle.run_oracle("fast", oracle.FASTQ, b1, b2)
+        assert res.returncode == 0, res.stderr
+        assert (tmp_path / "o1.fq").read_bytes() == e1 and (tmp_path / "o2.fq").read_bytes() == e2
+        assert res.stdout == f"{est.total} read pairs processed, out of which {est.dups} duplicates were removed.\n"
+    else:
+        res = run("-i", tmp_path / "a.fq", "-o", tmp_path / "o1.fq", "--fast", "-v", env=env)
+        e1, _, est = oracle.run_oracle("fast", oracle.FASTQ, b1)
+        assert res.returncode == 0, res.stderr
+        assert (tmp_path / "o1.fq").read_bytes() == e1
+        assert res.stdout == f"{est.total} reads processed, out of which {est.dups} duplicates were removed.\n"
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["base", "start", "length"])
+def test_fast_sharded_error_paths_match_the_single_engine_binary(tmp_path, kind):
+    """A malformed record in the middle of the input: the sharded driver stops where the single-engine driver stops (same exit
+    status, stderr, output bytes) - both follow the reference's order of events (tests/test_differential_gpu.py pins the latter)."""
+    seqs = synth.make_reads(9000, seed=96, read_len=80, dup_frac=0.3)
+    recs = [synth.to_fastq([s], ids=[b"@r.%d" % i]) for i, s in enumerate(seqs)]
+    bad = 5432
+    r = recs[bad].split(b"\n")
+    if kind == "base":
+        r[1] = r[1][:10] + b"Z" + r[1][11:]
+    elif kind == "start":
+        r[0] = b"x" + r[0][1:]
+    else:
+        r[3] = r[3][:-3]
+    recs[bad] = b"\n".join(r)
+    (tmp_path / "a.fq").write_bytes(b"".join(recs))
+    outs = []
+    for tag, env in (("one", {"FQD_BLOCK_BYTES": str(1 << 16)}), ("many", {"FQD_BLOCK_BYTES": str(1 << 16), "FQD_DEVICES": "0,0,0"})):
+        res = run("-i", tmp_path / "a.fq", "-o", tmp_path / f"{tag}.fq", "--fast", "-v", env=env)
+        outs.append((res.returncode, res.stdout, res.stderr, (tmp_path / f"{tag}.fq").read_bytes()))
+    assert outs[0][0] == 1
+    assert outs[0] == outs[1]
