@@ -119,6 +119,95 @@ __global__ void k_scan_loose(const ScanParams p) {
         p.keep[i] = k;
     }
 }
+// ---- warp-cooperative adjacent scan (tight, loose, the Hamming breaks).  The thread-per-record kernels above read two
+// rows per record at random (its own and its predecessor's: 2 x 128 bytes per pair, 12.8 GB at 50 M pairs).  Here a warp
+// walks a run of consecutive sorted positions; a row is 16 bytes in each of Q = row_words / 2 neighbouring lanes, loaded
+// ONCE, and the predecessor's 16 bytes come from the lane group before (shuffle) - or, for the first row of a step, from
+// the registers that kept the last row of the step before.
+constexpr u32 COOP_RUN = 512;           // sorted positions per warp
+template <int MODE>                     // 1 tight, 2 loose, 3 hamming breaks
+__global__ void __launch_bounds__(256) k_scan_coop(const ScanParams p, u32 Q) {
+    const u32 lane = threadIdx.x & 31u;
+    const u64 warp_id = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const u64 lo = warp_id * COOP_RUN;
+    if (lo >= p.n) return;
+    const u64 hi = min(p.n, lo + COOP_RUN);
+    const u32 rows_per_step = 32u / Q;
+    const u32 piece = lane % Q, grp = lane / Q;
+    const u32 Qm = p.W / 2u;                                   // pieces per mate
+    const u32 mate = piece / Qm;                               // which mate this lane's 16 bytes belong to
+    const u32 sym_per_word = p.bits == 8u ? 8u : (u32)BASES_PER_WORD;
+    const u32 first_sym = (piece % Qm) * 2u * sym_per_word;    // first symbol of the mate covered by this piece
+    u32* out = MODE == 3 ? p.brk : p.keep;
+    // the row (and lengths) before position lo, held like "the last row of the previous step"
+    ulonglong2 carry = make_ulonglong2(0ull, 0ull);
+    u32 carry_len = 0;
+    if (lo > 0) {
+        const u32 h = p.perm[lo - 1];
+        carry = *reinterpret_cast<const ulonglong2*>(p.rows + (u64)h * p.stride + 2u * piece);
+        if (MODE != 1) carry_len = mate ? p.len1[h] : p.len0[h];
+    }
+    for (u64 base = lo; base < hi; base += rows_per_step) {
+        const u64 i = base + grp;
+        const bool in = i < hi;
+        ulonglong2 v = make_ulonglong2(0ull, 0ull);
+        u32 len = 0;
+        if (in) {
+            const u32 c = p.perm[i];
+            v = *reinterpret_cast<const ulonglong2*>(p.rows + (u64)c * p.stride + 2u * piece);
+            if (MODE != 1) len = mate ? p.len1[c] : p.len0[c];
+        }
+        // predecessor's piece: the lane group before, or the carry for the first row of the step
+        ulonglong2 pv;
+        pv.x = __shfl_up_sync(0xFFFFFFFFu, v.x, Q);
+        pv.y = __shfl_up_sync(0xFFFFFFFFu, v.y, Q);
+        u32 plen = __shfl_up_sync(0xFFFFFFFFu, len, Q);
+        if (grp == 0) { pv = carry; plen = carry_len; }
+        // next step's carry: the last row of this step (lanes 32 - Q + piece)
+        carry.x = __shfl_sync(0xFFFFFFFFu, v.x, 32u - Q + piece);
+        carry.y = __shfl_sync(0xFFFFFFFFu, v.y, 32u - Q + piece);
+        carry_len = __shfl_sync(0xFFFFFFFFu, len, 32u - Q + piece);
+        bool bad;                                               // this piece says "not a duplicate of the predecessor"
+        if (MODE == 1) {
+            bad = ((v.x ^ pv.x) | (v.y ^ pv.y)) != 0ull;
+        } else if (MODE == 2) {
+            // the predecessor's mate is a prefix of mine over min(len) symbols (src/comparator.cpp:60-63)
+            const u32 nb = min(len, plen);
+            u64 dx = v.x ^ pv.x, dy = v.y ^ pv.y;
+            const u32 s0 = first_sym, s1 = first_sym + sym_per_word;
+            if (nb <= s0) dx = 0; else if (nb < s0 + sym_per_word) dx &= ~0ull << (p.bits * (sym_per_word - (nb - s0)));
+            if (nb <= s1) dy = 0; else if (nb < s1 + sym_per_word) dy &= ~0ull << (p.bits * (sym_per_word - (nb - s1)));
+            bad = (dx | dy) != 0ull;
+        } else {
+            u64 x = v.x ^ pv.x, y = v.y ^ pv.y;
+            if (p.bits == 8u) {
+                x |= x >> 4; x |= x >> 2; x |= x >> 1; x &= 0x0101010101010101ull;
+                y |= y >> 4; y |= y >> 2; y |= y >> 1; y &= 0x0101010101010101ull;
+            } else {
+                x = (x | (x >> 1) | (x >> 2)) & 0x0249249249249249ull;
+                y = (y | (y >> 1) | (y >> 2)) & 0x0249249249249249ull;
+            }
+            u32 d = (u32)__popcll(x) + (u32)__popcll(y);
+            for (u32 o = 1; o < Qm; o <<= 1) d += __shfl_xor_sync(0xFFFFFFFFu, d, o);      // distance of the whole mate
+            bad = d > 2u * p.dist || len != plen;
+        }
+        const u32 votes = __ballot_sync(0xFFFFFFFFu, bad);
+        // paired loose: lengths of the second mate, from the first lane that holds it (every lane takes part in the shuffle)
+        const u32 src2 = p.mates == 2 ? grp * Q + Qm : lane;
+        const u32 lc2 = __shfl_sync(0xFFFFFFFFu, len, src2), lh2 = __shfl_sync(0xFFFFFFFFu, plen, src2);
+        if (in && piece == 0) {
+            const u32 gmask = (Q == 32u ? 0xFFFFFFFFu : ((1u << Q) - 1u)) << (grp * Q);
+            bool brk = (votes & gmask) != 0u;
+            if (MODE == 2 && !brk && p.mates == 2) {
+                // the overlap must be same-sided (src/comparator.cpp:65-74)
+                const u32 lc1 = len, lh1 = plen;
+                brk = !(((lh1 <= lc1) && (lh2 <= lc2)) || ((lh1 > lc1) && (lh2 > lc2)));
+            }
+            out[i] = (i == 0 || brk) ? 1u : 0u;
+        }
+    }
+}
+
 // The literal loop of SeqDupRemover::impl_filterSE/PE with the LooseComparator (src/seq_dup_remover.hpp:78-101,173-208,
 // src/comparator.cpp:60-74), one thread.  Only used when a sequence holds a byte below the line feed: such a byte sorts
 // an extension BEFORE its prefix, and the head of a cluster is then no longer the previous record.
@@ -995,12 +1084,15 @@ static int device_scan(SeqState* s, SortScratch& sc, const u32* in, u32* out, u6
 static int radix_sort(SeqState* s, SortScratch& sc, u64 n, u32 bit_lo, u32 bit_hi, bool has_b, std::string* err) {
     if (n < 2) return FQD_OK;
     const u32 nblocks = (u32)((n + RS_TILE - 1) / RS_TILE);
+    // the scatter reorders a tile in shared memory: more than the 48 KB a kernel gets without asking
+    SEQ_TRY(cudaFuncSetAttribute(k_radix_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true)));
+    SEQ_TRY(cudaFuncSetAttribute(k_radix_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false)));
     for (u32 shift = bit_lo; shift < bit_hi; shift += 8) {
         k_radix_hist<<<nblocks, RS_THREADS, 0, s->stream>>>(sc.keyA, n, shift, sc.hist, nblocks);
         int rc = device_scan(s, sc, sc.hist, sc.hist_scan, 256ull * nblocks, nullptr, err);
         if (rc) return rc;
-        if (has_b) k_radix_scatter<true><<<nblocks, RS_THREADS, 0, s->stream>>>(sc.keyA, sc.aA, sc.bA, sc.keyB, sc.aB, sc.bB, n, shift, sc.hist_scan, nblocks);
-        else k_radix_scatter<false><<<nblocks, RS_THREADS, 0, s->stream>>>(sc.keyA, sc.aA, nullptr, sc.keyB, sc.aB, nullptr, n, shift, sc.hist_scan, nblocks);
+        if (has_b) k_radix_scatter<true><<<nblocks, RS_THREADS, rs_smem_bytes(true), s->stream>>>(sc.keyA, sc.aA, sc.bA, sc.keyB, sc.aB, sc.bB, n, shift, sc.hist_scan, nblocks);
+        else k_radix_scatter<false><<<nblocks, RS_THREADS, rs_smem_bytes(false), s->stream>>>(sc.keyA, sc.aA, nullptr, sc.keyB, sc.aB, nullptr, n, shift, sc.hist_scan, nblocks);
         s->launches += 2;
         std::swap(sc.keyA, sc.keyB); std::swap(sc.aA, sc.aB);
         if (has_b) std::swap(sc.bA, sc.bB);
@@ -1098,14 +1190,21 @@ static int seq_scan_stage(SeqState* s, std::string* err) {
     SEQ_TRY(cudaMemsetAsync(s->d_bound_prev, 0, boundary_words(s->row_words) * sizeof(u64), s->stream));
     if (s->cfg.mode == FQD_MODE_SEQ_HAMMING && (rc = seq_dalloc(s, &s->d_brk, n, err))) return rc;
     const ScanParams sp = seq_scan_params(s);
-    if (s->cfg.mode == FQD_MODE_SEQ_TIGHT) k_scan_tight<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
+    // rows of 2^k 16-byte pieces (150 bp: 4 per mate): the warp-cooperative scan, every row loaded once
+    const u32 Q = s->row_words / 2u, Qm = s->W / 2u;
+    const bool coop = Q >= 1 && Q <= 32 && (Q & (Q - 1)) == 0 && Qm >= 1 && (Qm & (Qm - 1)) == 0 && !getenv("FQD_SCAN_PER_THREAD");
+    const unsigned coop_blocks = (unsigned)(((n + COOP_RUN - 1) / COOP_RUN + 7) / 8);
+    if (s->cfg.mode == FQD_MODE_SEQ_TIGHT && coop) k_scan_coop<1><<<coop_blocks, 256, 0, s->stream>>>(sp, Q);
+    else if (s->cfg.mode == FQD_MODE_SEQ_TIGHT) k_scan_tight<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
     else if (s->cfg.mode == FQD_MODE_SEQ_LOOSE && s->low_bytes) k_scan_loose_literal<<<1, 1, 0, s->stream>>>(sp);
+    else if (s->cfg.mode == FQD_MODE_SEQ_LOOSE && coop) k_scan_coop<2><<<coop_blocks, 256, 0, s->stream>>>(sp, Q);
     else if (s->cfg.mode == FQD_MODE_SEQ_LOOSE) k_scan_loose<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
     else {
         HamLong* d_long = nullptr; u32* d_nlong = nullptr;
         if ((rc = seq_dalloc(s, &d_long, n / HAM_SHORT + 2, err)) || (rc = seq_dalloc(s, &d_nlong, 1, err))) return rc;
         SEQ_TRY(cudaMemsetAsync(d_nlong, 0, sizeof(u32), s->stream));
-        k_ham_breaks<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
+        if (coop) k_scan_coop<3><<<coop_blocks, 256, 0, s->stream>>>(sp, Q);
+        else k_ham_breaks<<<seq_grid(s, n), 256, 0, s->stream>>>(sp);
         k_ham_segments<<<seq_grid(s, n), 256, 0, s->stream>>>(sp, d_long, d_nlong);
         k_ham_long<<<s->sm * 4, 256, 0, s->stream>>>(sp, d_long, d_nlong);
         s->launches += 2;

@@ -258,4 +258,13 @@ int fqd_emit_clusters(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_
     return stream_out(h->clusters[mate], h->cl_cut[mate], h->cl_pos[mate], dst, cap, n_bytes, done);
 }
 
+
+// Several engines behind one binary (FQD_DEVICES) need real devices: the double refuses, loudly.
+static int no_shards(fqd_handle* h) { if (h) h->err = "[fake_fqd] the test double has no sharded path"; return FQD_ERR_INVALID; }
+int fqd_shard2_init(fqd_handle* h, uint32_t, uint32_t, uint32_t) { return no_shards(h); }
+int fqd_shard2_link(fqd_handle* h, uint32_t, fqd_handle*) { return no_shards(h); }
+int fqd_shard2_push_host(fqd_handle* h, uint64_t, const char*, size_t, const char*, size_t, uint64_t*, uint64_t*) { return no_shards(h); }
+int fqd_shard2_insert(fqd_handle* h, uint64_t) { return no_shards(h); }
+int fqd_shard2_apply(fqd_handle* h, uint64_t) { return no_shards(h); }
+int fqd_shard2_result(fqd_handle* h, uint64_t, size_t, size_t, fqd_chunk_result*) { return no_shards(h); }
 }  // extern "C"
