@@ -1,6 +1,6 @@
 #!/bin/bash
 cd "$(dirname "$0")/.."
-timeout 400 python -m pytest tests/test_seq_gpu.py tests/test_unordered_gpu.py tests/test_sharded_gpu.py -x -q -m gpu --timeout 100 2>&1 | tail -3
+timeout 400 python -m pytest tests/test_seq_gpu.py tests/test_sharded_seq_gpu.py -x -q -m gpu --timeout 100 2>&1 | tail -3
 for m in tight loose tail-hamming unordered; do
   timeout 200 python bench_seq.py --mode $m --pairs 50000000 --steps 2 2>&1 | python -c "
 import json,sys
