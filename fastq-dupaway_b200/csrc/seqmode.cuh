@@ -1087,7 +1087,22 @@ static int radix_sort(SeqState* s, SortScratch& sc, u64 n, u32 bit_lo, u32 bit_h
     // the scatter reorders a tile in shared memory: more than the 48 KB a kernel gets without asking
     SEQ_TRY(cudaFuncSetAttribute(k_radix_scatter<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(true)));
     SEQ_TRY(cudaFuncSetAttribute(k_radix_scatter<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)rs_smem_bytes(false)));
+    // digits that are the same in every key need no pass (sc.d_total doubles as the two-word result)
+    u64 varying = ~0ull;
+    if (n >= (1u << 16)) {
+        u64 h_oa[2] = {0ull, ~0ull};
+        u64* d_oa = nullptr;
+        SEQ_TRY(cudaMallocAsync((void**)&d_oa, 2 * sizeof(u64), s->stream));
+        SEQ_TRY(cudaMemcpyAsync(d_oa, h_oa, sizeof h_oa, cudaMemcpyHostToDevice, s->stream));
+        k_key_or_and<<<s->sm * 4, 256, 0, s->stream>>>(sc.keyA, n, d_oa);
+        SEQ_TRY(cudaMemcpyAsync(h_oa, d_oa, sizeof h_oa, cudaMemcpyDeviceToHost, s->stream));
+        SEQ_TRY(cudaStreamSynchronize(s->stream));
+        SEQ_TRY(cudaFreeAsync(d_oa, s->stream));
+        varying = h_oa[0] ^ h_oa[1];
+        s->launches++;
+    }
     for (u32 shift = bit_lo; shift < bit_hi; shift += 8) {
+        if (((varying >> shift) & 0xFFull) == 0) continue;
         k_radix_hist<<<nblocks, RS_THREADS, 0, s->stream>>>(sc.keyA, n, shift, sc.hist, nblocks);
         int rc = device_scan(s, sc, sc.hist, sc.hist_scan, 256ull * nblocks, nullptr, err);
         if (rc) return rc;
@@ -1137,6 +1152,10 @@ static int sort_rows(SeqState* s, const u64* rows, u32 stride, u32 w_begin, u32 
         s->launches += 2;
         if (w + 1 >= n_words) break;      // every word used: remaining ties are identical rows, already in index order
         k_mark_unresolved<<<seq_grid(s, n_act), 256, 0, s->stream>>>(rows + w_begin, stride, w + 1, n_words, sc.aA, gid, n_act, gdiff);
+        if (!getenv("FQD_SORT_NO_SMALL_GROUPS")) {
+            k_sort_small_groups<<<seq_grid(s, n_act), 256, 0, s->stream>>>(rows + w_begin, stride, w + 1, n_words, head, gid, gsize, gdiff, sc.aA, pos_in, n_act, perm);
+            s->launches++;
+        }
         k_active_flags<<<seq_grid(s, n_act), 256, 0, s->stream>>>(gid, gsize, gdiff, n_act, flag);
         u64 n_next = 0;
         if ((rc = device_scan(s, sc, flag, excl, n_act, &n_next, err))) return rc;

@@ -111,6 +111,17 @@ __global__ void __launch_bounds__(RS_THREADS) k_radix_hist(const u64* __restrict
     hist[(u64)tid * nblocks + blockIdx.x] = h[tid];      // bin-major: a plain exclusive scan yields global bases
 }
 
+// Which bits differ between any two keys?  out[0] |= keys, out[1] &= keys: a digit whose bits are the same in every key
+// (the leading zeros of a counter in an ID tag, the padding of a short last word) needs no pass.
+__global__ void __launch_bounds__(256) k_key_or_and(const u64* __restrict__ keys, u64 n, u64* out) {
+    u64 o = 0, a = ~0ull;
+    const u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) { const u64 k = keys[i]; o |= k; a &= k; }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) { o |= __shfl_xor_sync(0xFFFFFFFFu, o, d); a &= __shfl_xor_sync(0xFFFFFFFFu, a, d); }
+    if ((threadIdx.x & 31u) == 0) { atomicOr(out, o); atomicAnd(out + 1, a); }
+}
+
 // Scatter of one pass.  Round 1 wrote every item straight to its global position: 32 lanes, up to 32 different bins,
 // 8- and 4-byte writes all over the output - the sort ran at a quarter of the bandwidth its traffic needs (10.5 ms for
 // 8 passes over 50 M (key, index) pairs).  Now a tile's 4096 items are first put in digit order in SHARED memory
@@ -246,6 +257,44 @@ __global__ void k_mark_unresolved(const u64* __restrict__ rows, u32 stride, u32 
         u64 diff = 0;
         for (u32 w = w_next; w < n_words; ++w) diff |= a[w] ^ b[w];
         if (diff) gdiff[gid[i]] = 1u;
+    }
+}
+// Small unresolved groups (a duplicate with a substitution near its end, a truncated copy next to its original: members
+// that share their first word and differ somewhere later) are put in order right here, one thread per group, by an
+// insertion sort on the remaining words - instead of one more round of gather + two radix sorts PER WORD until the
+// differing word is reached (a difference in the last 10 bases of a 150 bp read took 7 rounds: 19 - 23 ms at 50 M
+// pairs).  Stable: members arrive in index order and only strictly greater predecessors are shifted.
+constexpr u32 SMALL_GROUP = 16;
+__global__ void k_sort_small_groups(const u64* __restrict__ rows, u32 stride, u32 w_next, u32 n_words, const u32* __restrict__ head,
+                                    const u32* __restrict__ gid, const u32* __restrict__ gsize, u32* __restrict__ gdiff,
+                                    const u32* __restrict__ idx, const u32* __restrict__ pos_in, u64 n, u32* __restrict__ perm) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        if (!head[i]) continue;
+        const u32 g = gid[i];
+        const u32 m = gsize[g];
+        if (m < 2u || m > SMALL_GROUP || !gdiff[g]) continue;
+        u32 v[SMALL_GROUP];
+        for (u32 k = 0; k < m; ++k) v[k] = idx[i + k];
+        for (u32 k = 1; k < m; ++k) {
+            const u32 cur = v[k];
+            const u64* a = rows + (u64)cur * stride;
+            u32 j = k;
+            while (j > 0) {
+                const u64* b = rows + (u64)v[j - 1] * stride;
+                bool greater = false;                       // is the predecessor strictly greater than cur?
+                for (u32 w = w_next; w < n_words; ++w) {
+                    const u64 x = b[w], y = a[w];
+                    if (x != y) { greater = x > y; break; }
+                }
+                if (!greater) break;
+                v[j] = v[j - 1];
+                --j;
+            }
+            v[j] = cur;
+        }
+        for (u32 k = 0; k < m; ++k) perm[pos_in ? pos_in[i + k] : (u32)(i + k)] = v[k];
+        gdiff[g] = 0;                                       // resolved: not part of the next round
     }
 }
 __global__ void k_active_flags(const u32* __restrict__ gid, const u32* __restrict__ gsize, const u32* __restrict__ gdiff, u64 n, u32* __restrict__ flag) {
