@@ -32,6 +32,9 @@ STATUS = {0: "FQD_OK", 1: "FQD_ERR_INVALID", 2: "FQD_ERR_CUDA", 3: "FQD_ERR_EMPT
           5: "FQD_ERR_LEN_MISMATCH", 6: "FQD_ERR_BAD_BASE", 7: "FQD_ERR_CAPACITY", 8: "FQD_ERR_SEQ_TOO_LONG", 9: "FQD_ERR_UNSUPPORTED_BYTE", 10: "FQD_ERR_TAG_TOO_LONG"}
 
 
+NONE64 = 0xFFFFFFFFFFFFFFFF
+
+
 class FqdError(RuntimeError):
     def __init__(self, code, msg=""):
         super().__init__(f"{STATUS.get(code, code)}: {msg}")
@@ -123,6 +126,14 @@ def load_library():
     lib.fqd_partition_sample.argtypes = [vp, C.c_uint32, C.POINTER(u64), C.POINTER(u64)]
     lib.fqd_partition_plan.argtypes = [vp, C.POINTER(u64), C.c_uint32, C.POINTER(u64), C.POINTER(u64)]
     lib.fqd_partition_gather.argtypes = [vp, C.c_int, vp]
+    lib.fqd_unordered_prepare.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    lib.fqd_unordered_enter.argtypes = [vp, C.c_int, u64, C.POINTER(u64)]
+    lib.fqd_unordered_join.argtypes = [vp, u64, u64, u64, u64, C.POINTER(u64)]
+    lib.fqd_unordered_row_bytes.argtypes = [vp]
+    lib.fqd_unordered_row_bytes.restype = sz
+    lib.fqd_unordered_rows.argtypes = [vp, u64, C.c_uint32, vp, C.POINTER(u64)]
+    lib.fqd_unordered_insert.argtypes = [vp, vp, u64, C.c_uint32, vp]
+    lib.fqd_unordered_apply.argtypes = [vp, vp, u64, C.c_int]
     lib.fqd_emission.argtypes = [vp, C.POINTER(Emission)]
     lib.fqd_emit.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(C.c_int)]
     lib.fqd_emit_clusters.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(C.c_int)]
@@ -327,6 +338,35 @@ class Engine:
 
     def partition_gather(self, mate: int, dptr: int):
         self._check(self.lib.fqd_partition_gather(self.h, mate, C.c_void_p(dptr)))
+
+    # -- --unordered by stages (tag ranges across GPUs, sharded_unordered.py)
+    def unordered_prepare(self):
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.fqd_unordered_prepare(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def unordered_enter(self, side: int, i: int) -> int:
+        pos = C.c_uint64(0)
+        self._check(self.lib.fqd_unordered_enter(self.h, side, i, C.byref(pos)))
+        return int(pos.value)
+
+    def unordered_join(self, limit_i: int, limit_j: int, final_i: int, final_j: int):
+        """-> (pairs emitted, unmatched here, emission index of the first bad pair or None, last comparison matched here)"""
+        out = (C.c_uint64 * 4)()
+        self._check(self.lib.fqd_unordered_join(self.h, limit_i, limit_j, final_i, final_j, out))
+        bad = int(out[2])
+        return int(out[0]), int(out[1]), (None if bad == NONE64 else bad), bool(out[3])
+
+    def unordered_rows(self, limit: int, n_shards: int, dptr: int):
+        counts = (C.c_uint64 * n_shards)()
+        self._check(self.lib.fqd_unordered_rows(self.h, limit, n_shards, C.c_void_p(dptr), counts))
+        return [int(c) for c in counts]
+
+    def unordered_insert(self, recv_ptr: int, n_recv: int, n_shards: int, flags_ptr: int):
+        self._check(self.lib.fqd_unordered_insert(self.h, C.c_void_p(recv_ptr), n_recv, n_shards, C.c_void_p(flags_ptr)))
+
+    def unordered_apply(self, flags_ptr: int, limit: int, report_bad: bool):
+        self._check(self.lib.fqd_unordered_apply(self.h, C.c_void_p(flags_ptr), limit, int(report_bad)))
 
     def emission(self) -> Emission:
         em = Emission()

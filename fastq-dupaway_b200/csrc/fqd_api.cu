@@ -1470,6 +1470,42 @@ extern "C" int fqd_partition_gather(fqd_handle* h, int mate, void* d_out) {
     cudaSetDevice(h->cfg.device);
     return seq_partition_gather(h->seq, mate, d_out, &h->err);
 }
+static bool un_handle(fqd_handle* h) { return h && h->seq && h->cfg.unordered; }
+extern "C" int fqd_unordered_prepare(fqd_handle* h, uint64_t* n_left, uint64_t* n_right) {
+    if (!un_handle(h) || !n_left || !n_right) return fail(h, FQD_ERR_INVALID, "fqd_unordered_prepare is for --unordered handles");
+    cudaSetDevice(h->cfg.device);
+    int rc = seq_unordered_prepare(h->seq, (u64*)n_left, (u64*)n_right, &h->err);
+    seq_stats(h->seq, &h->stats);
+    return rc;
+}
+extern "C" int fqd_unordered_enter(fqd_handle* h, int side, uint64_t i, uint64_t* pos) {
+    if (!un_handle(h) || !pos || side < 0 || side > 1) return fail(h, FQD_ERR_INVALID, "fqd_unordered_enter: bad arguments");
+    cudaSetDevice(h->cfg.device);
+    return seq_unordered_enter(h->seq, side, i, (u64*)pos, &h->err);
+}
+extern "C" int fqd_unordered_join(fqd_handle* h, uint64_t limit_i, uint64_t limit_j, uint64_t final_i, uint64_t final_j, uint64_t out[4]) {
+    if (!un_handle(h) || !out) return fail(h, FQD_ERR_INVALID, "fqd_unordered_join is for --unordered handles");
+    cudaSetDevice(h->cfg.device);
+    return seq_unordered_join(h->seq, limit_i, limit_j, final_i, final_j, (u64*)out, &h->err);
+}
+extern "C" size_t fqd_unordered_row_bytes(fqd_handle* h) { return un_handle(h) ? ((size_t)2 * h->seq->W + 1) * sizeof(u64) : 0; }
+extern "C" int fqd_unordered_rows(fqd_handle* h, uint64_t limit, uint32_t n_shards, void* d_send, uint64_t* counts) {
+    if (!un_handle(h) || !counts || (!d_send && limit)) return fail(h, FQD_ERR_INVALID, "fqd_unordered_rows: bad arguments");
+    cudaSetDevice(h->cfg.device);
+    return seq_unordered_rows(h->seq, limit, n_shards, d_send, (u64*)counts, &h->err);
+}
+extern "C" int fqd_unordered_insert(fqd_handle* h, const void* d_recv, uint64_t n_recv, uint32_t n_shards, void* d_flags) {
+    if (!un_handle(h) || (n_recv && (!d_recv || !d_flags)) || n_shards == 0) return fail(h, FQD_ERR_INVALID, "fqd_unordered_insert: bad arguments");
+    cudaSetDevice(h->cfg.device);
+    return seq_unordered_insert(h->seq, d_recv, n_recv, n_shards, d_flags, &h->err);
+}
+extern "C" int fqd_unordered_apply(fqd_handle* h, const void* d_flags_back, uint64_t limit, int report_bad) {
+    if (!un_handle(h)) return fail(h, FQD_ERR_INVALID, "fqd_unordered_apply is for --unordered handles");
+    cudaSetDevice(h->cfg.device);
+    int rc = seq_unordered_apply(h->seq, d_flags_back, limit, report_bad, &h->err);
+    seq_stats(h->seq, &h->stats);
+    return rc;
+}
 extern "C" int fqd_emit(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, int* done) {
     if (!h || !h->seq || !dst || !n_bytes || !done) return fail(h, FQD_ERR_INVALID, "fqd_emit is for sequence / unordered modes");
     cudaSetDevice(h->cfg.device);

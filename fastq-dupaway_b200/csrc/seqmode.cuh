@@ -7,6 +7,7 @@
 // sortlib.cuh sorts record indices by packed key rows (stable on the input index), and the scans below decide
 // which records are written.  Nothing spills to disk; nothing is computed on the host.
 #pragma once
+#include "shard.cuh"
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -385,11 +386,11 @@ __global__ void k_tail_state(const ScanParams p, const u64* prev, int hamming, u
 }
 
 // ---- repartition of the input records by key range (multi-GPU sequence mode)
-// owner of record i = number of splitters <= (word 0, word 1) of its row
-__global__ void k_range_owner(const u64* rows, u32 stride, u64 n, const u64* splitters, u32 n_split, u64* owner_key, u32* idx) {
+// owner of record i = number of splitters <= (word 0, word 1) of its row (word 1 = 0 for rows of a single word)
+__global__ void k_range_owner(const u64* rows, u32 stride, u32 nw, u64 n, const u64* splitters, u32 n_split, u64* owner_key, u32* idx) {
     u64 step = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-        const u64 w0 = rows[i * stride], w1 = rows[i * stride + 1];
+        const u64 w0 = rows[i * stride], w1 = nw > 1 ? rows[i * stride + 1] : 0ull;
         u32 lo = 0, hi = n_split;            // first splitter > key
         while (lo < hi) {
             const u32 mid = (lo + hi) >> 1;
@@ -415,11 +416,11 @@ __global__ void k_pick_u64(const u64* src, const u64* pos, u32 n, u64 total_pos,
     const u32 t = threadIdx.x;
     if (t < n) out[t] = pos[t] >= total_pos ? total : src[pos[t]];
 }
-__global__ void k_sample_rows(const u64* rows, u32 stride, u64 n, u32 n_samples, u64* out) {
+__global__ void k_sample_rows(const u64* rows, u32 stride, u32 nw, u64 n, u32 n_samples, u64* out) {
     const u32 j = blockIdx.x * blockDim.x + threadIdx.x;
     if (j >= n_samples) return;
     const u64 i = (u64)(((unsigned __int128)j * n) / n_samples);
-    out[2 * j] = rows[i * stride]; out[2 * j + 1] = rows[i * stride + 1];
+    out[2 * j] = rows[i * stride]; out[2 * j + 1] = nw > 1 ? rows[i * stride + 1] : 0ull;
 }
 // ---- record gathers.  A warp takes 32 records at a time: every lane fetches the geometry of ONE record (coalesced
 // table reads, the segment search in parallel), then the warp copies the 32 records one after the other with the
@@ -594,6 +595,21 @@ __global__ void k_join_stop(const JoinParams p, JoinStop* out) {
         s.final_equal = cmp_rows(p.tagsL + (u64)p.permL[s.is] * p.TW, p.tagsR + (u64)p.permR[s.js] * p.TW, p.TW) == 0 ? 1u : 0u;
     *out = s;
 }
+// Tag ranges across GPUs: the driver knows where the job's walk stops and hands every range its part of that state
+// (limits clamped to the range, is / js = ~0 when the stop state's record lives in another range); equal tags always
+// share a range, so the last comparison can only succeed where both of its records are.
+__global__ void k_join_final(const JoinParams p, JoinStop* st) {
+    JoinStop s = *st;
+    s.final_equal = 0;
+    if (s.is < p.n && s.js < p.m)
+        s.final_equal = cmp_rows(p.tagsL + (u64)p.permL[s.is] * p.TW, p.tagsR + (u64)p.permR[s.js] * p.TW, p.TW) == 0 ? 1u : 0u;
+    *st = s;
+}
+// position in the other list when the walk first stands on element i of this one (side 0: this = L)
+__global__ void k_join_enter(const JoinParams p, int side, u32 i, u32* out) {
+    *out = side == 0 ? join_enter(p.tagsL, p.permL, p.n, p.tagsR, p.permR, p.m, p.TW, i)
+                     : join_enter(p.tagsR, p.permR, p.m, p.tagsL, p.permL, p.n, p.TW, i);
+}
 __global__ void k_join_flags(const JoinParams p, const JoinStop* st, u32* emit, u32* unL, u32* unR) {
     const JoinStop s = *st;
     u64 step = (u64)gridDim.x * blockDim.x;
@@ -633,6 +649,29 @@ __global__ void k_build_pairs(const JoinParams p, const JoinStop* st, const u32*
         else if (br != 0xFFFFFFFFu) atomicMin(first_bad, ((u64)e << 8) | (br & 0xFFu));
     }
 }
+// pairs of one tag range -> the GPUs that own their hash range (same rule and row layout as shard.cuh)
+__global__ void k_un_owner(const u64* __restrict__ h1, const u64* __restrict__ h2, u64 n, u32 n_shards, u64* __restrict__ owner_key, u32* __restrict__ idx) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
+        owner_key[i] = __umul64hi(pair_hash(h1[i], h2[i]), (u64)n_shards);
+        idx[i] = (u32)i;
+    }
+}
+__global__ void k_un_gather(const u64* __restrict__ pair_rows, u32 row_words, const u64* __restrict__ h1, const u64* __restrict__ h2,
+                            const u32* __restrict__ sorted_idx, u64 n, u64* __restrict__ send) {
+    const u32 rw = row_words + 1;
+    u64 step = (u64)gridDim.x * blockDim.x;
+    const u64 total = n * rw;
+    for (u64 t = (u64)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += step) {
+        const u64 r = t / rw; const u32 w = (u32)(t % rw);
+        const u32 src = sorted_idx[r];
+        send[t] = w < row_words ? pair_rows[(u64)src * row_words + w] : pair_hash(h1[src], h2[src]);
+    }
+}
+__global__ void k_un_flags_back(const u8* __restrict__ flags_sorted, const u32* __restrict__ sorted_idx, u64 n, u8* __restrict__ dup) {
+    u64 step = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) dup[sorted_idx[i]] = flags_sorted[i];
+}
 __global__ void k_keep_from_dup(const u8* dup, u64 n, u64 limit, u32* keep) {
     u64 step = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) keep[i] = (i < limit && !dup[i]) ? 1u : 0u;
@@ -666,6 +705,29 @@ struct SeqMate {
     u32* d_bad = nullptr;         // unordered: first byte outside {A,C,G,T,N} per record (~0 = none)
     u64* d_tags = nullptr;        // unordered: TW words per record
     bool finished = false;
+};
+
+struct SortScratch {
+    u64 *keyA = nullptr, *keyB = nullptr;
+    u32 *aA = nullptr, *aB = nullptr, *bA = nullptr, *bB = nullptr;
+    u32 *hist = nullptr, *hist_scan = nullptr;
+    u64* scan_state = nullptr; u32* ticket = nullptr; u64* d_total = nullptr;
+    u64 n_cap = 0; u64 hist_cap = 0; u64 state_cap = 0;
+};
+
+// --unordered by stages: fqd_finish runs them back to back on one GPU; across GPUs (tag ranges, sharded_unordered.py) the
+// driver runs them one by one and supplies, between them, what only the whole job knows: where the walk stops, where
+// this range's pairs stand in the job's emission order, and which of them another range has seen first.
+struct UnJoin {
+    int stage = 0;              // 1 tags sorted + partners known, 2 emission order + pair keys built, 3 finished
+    u32 *permL = nullptr, *permR = nullptr, *matchL = nullptr, *matchR = nullptr, *emit = nullptr, *unL = nullptr, *unR = nullptr, *excl = nullptr;
+    JoinStop* d_stop = nullptr;
+    SortScratch sc;             // scan fields only
+    u64 E = 0, unmatched = 0, hbad = ~0ull; u32 final_equal = 0;
+    u64 *pair_rows = nullptr, *h1 = nullptr, *h2 = nullptr, *first_bad = nullptr;
+    u32 *idxL = nullptr, *idxR = nullptr, *keep = nullptr;
+    u8* dup = nullptr;
+    u32* send_idx = nullptr; u64 n_send = 0;      // rows handed to the owners of their hash range, in sending order
 };
 
 struct SeqState {
@@ -705,6 +767,8 @@ struct SeqState {
     // repartition by key range
     u32* d_part_perm = nullptr; u64* d_part_starts = nullptr; u64* d_part_off[2] = {nullptr, nullptr};
     u32 part_G = 0; u64 part_n = 0;
+    u32* d_part_perm1 = nullptr; u64 part_n1 = 0;      // --unordered: the second file is partitioned by its own tags
+    UnJoin un;
     u32* d_cl_len[2] = {nullptr, nullptr};     // --write-clusters: line length per sorted position
     u64 cl_cursor[2] = {0, 0};
     bool low_bytes = false;          // byte keys: a sequence holds a byte below '\n' (see k_scan_loose_literal)
@@ -812,6 +876,8 @@ static int seq_reset(SeqState* s, std::string* err) {
     s->d_cl_len[0] = s->d_cl_len[1] = nullptr; s->cl_cursor[0] = s->cl_cursor[1] = 0;
     s->d_perm = s->d_keep = s->d_brk = s->d_tail_head = nullptr; s->d_bound_prev = s->d_bound_out = nullptr;
     s->d_part_perm = nullptr; s->d_part_starts = nullptr; s->d_part_off[0] = s->d_part_off[1] = nullptr; s->part_G = 0; s->part_n = 0;
+    s->d_part_perm1 = nullptr; s->part_n1 = 0;
+    s->un = UnJoin();
     s->emit_cursor[0] = s->emit_cursor[1] = 0;
     for (int m = 0; m < 2; ++m) { s->d_o_off[m] = nullptr; s->d_o_len[m] = nullptr; s->d_seg_base[m] = nullptr; s->d_seg_ptr[m] = nullptr; }
     s->d_stage = nullptr; s->stage_cap = 0; s->d_dst = nullptr; s->dst_cap = 0; s->em_scan_state = nullptr;
@@ -1023,14 +1089,6 @@ static int seq_append(SeqState* s, int m, const void* buf, size_t n, bool is_dev
 
 // ---------------------------------------------------------------------------------------------------------
 // sort driver
-struct SortScratch {
-    u64 *keyA = nullptr, *keyB = nullptr;
-    u32 *aA = nullptr, *aB = nullptr, *bA = nullptr, *bB = nullptr;
-    u32 *hist = nullptr, *hist_scan = nullptr;
-    u64* scan_state = nullptr; u32* ticket = nullptr; u64* d_total = nullptr;
-    u64 n_cap = 0; u64 hist_cap = 0; u64 state_cap = 0;
-};
-
 template <class T>
 static int seq_dalloc(SeqState* s, T** p, size_t count, std::string* err) {
     void* q = nullptr;
@@ -1127,6 +1185,9 @@ static int sort_rows(SeqState* s, const u64* rows, u32 stride, u32 w_begin, u32 
     if ((rc = seq_dalloc(s, &head, n, err)) || (rc = seq_dalloc(s, &excl, n, err)) || (rc = seq_dalloc(s, &gid, n, err)) ||
         (rc = seq_dalloc(s, &gsize, n, err)) || (rc = seq_dalloc(s, &gdiff, n, err)) || (rc = seq_dalloc(s, &flag, n, err)) ||
         (rc = seq_dalloc(s, &posA, n, err)) || (rc = seq_dalloc(s, &posB, n, err))) return rc;
+    MidGroup* mid = nullptr; MidCtl* n_mid = nullptr;
+    if ((rc = seq_dalloc(s, &mid, MID_LIST_CAP, err)) || (rc = seq_dalloc(s, &n_mid, 1, err))) return rc;
+    const bool fine = getenv("FQD_TRACE_SORT") != nullptr;
     const u32 hi_bit = (word_bits + 7) / 8 * 8;
     tr.mark(s->stream, "  sort: scratch alloc");
 
@@ -1151,15 +1212,22 @@ static int sort_rows(SeqState* s, const u64* rows, u32 stride, u32 w_begin, u32 
         k_group_ids<<<seq_grid(s, n_act), 256, 0, s->stream>>>(head, excl, n_act, gid, gsize);
         s->launches += 2;
         if (w + 1 >= n_words) break;      // every word used: remaining ties are identical rows, already in index order
+        if (fine) tr.mark(s->stream, "    round: heads, groups");
         k_mark_unresolved<<<seq_grid(s, n_act), 256, 0, s->stream>>>(rows + w_begin, stride, w + 1, n_words, sc.aA, gid, n_act, gdiff);
+        if (fine) tr.mark(s->stream, "    round: mark unresolved");
         if (!getenv("FQD_SORT_NO_SMALL_GROUPS")) {
-            k_sort_small_groups<<<seq_grid(s, n_act), 256, 0, s->stream>>>(rows + w_begin, stride, w + 1, n_words, head, gid, gsize, gdiff, sc.aA, pos_in, n_act, perm);
-            s->launches++;
+            SEQ_TRY(cudaMemsetAsync(n_mid, 0, sizeof(MidCtl), s->stream));
+            k_sort_small_groups<<<seq_grid(s, n_act), 256, 0, s->stream>>>(rows + w_begin, stride, w + 1, n_words, head, gid, gsize, gdiff, sc.aA, pos_in, n_act, perm, mid, n_mid);
+            if (fine) tr.mark(s->stream, "    round: small groups");
+            k_sort_mid_groups<<<s->sm * 4, 256, 0, s->stream>>>(rows + w_begin, stride, w + 1, n_words, gid, gdiff, sc.aA, pos_in, perm, mid, n_mid);
+            s->launches += 2;
         }
+        if (fine) tr.mark(s->stream, "    round: mid groups");
         k_active_flags<<<seq_grid(s, n_act), 256, 0, s->stream>>>(gid, gsize, gdiff, n_act, flag);
         u64 n_next = 0;
         if ((rc = device_scan(s, sc, flag, excl, n_act, &n_next, err))) return rc;
         s->launches += 2;
+        if (fine) tr.mark(s->stream, "    round: active scan");
         if (n_next == 0) break;
         // compact the unresolved items (position in perm, record index, group id), keeping their order
         k_compact_active<<<seq_grid(s, n_act), 256, 0, s->stream>>>(flag, excl, pos_in, sc.aA, gid, n_act, posB, sc.aB, sc.bB);
@@ -1178,6 +1246,7 @@ static int sort_rows(SeqState* s, const u64* rows, u32 stride, u32 w_begin, u32 
         k_gather_word<<<seq_grid(s, n_act), 256, 0, s->stream>>>(rows + w_begin, stride, w + 1, sc.aA, n_act, sc.keyA);
         s->launches += 3;
         seg_in = sc.bA;
+        if (fine) tr.mark(s->stream, "    round: sort of the unresolved");
     }
     tr.mark(s->stream, "  sort: refine rounds");
     SEQ_TRY(cudaGetLastError());
@@ -1296,13 +1365,13 @@ static int seq_emit_stage(SeqState* s, std::string* err) {
 static int seq_finish_unordered(SeqState* s, std::string* err);
 
 // everything appended so far is parsed; s->n = records (pairs) that take part
-static int seq_parse_rest(SeqState* s, std::string* err) {
+static int seq_parse_rest(SeqState* s, std::string* err, bool allow_empty = false) {
     if (s->parsed) return FQD_OK;
     s->parsed = true;
     SeqTrace tr;
     for (u32 m = 0; m < s->mates; ++m) {
         SeqMate& mt = s->mate[m];
-        if (mt.segs.empty()) { seq_set_error(s, FQD_ERR_EMPTY, 0, 0, m); continue; }
+        if (mt.segs.empty()) { if (!allow_empty) seq_set_error(s, FQD_ERR_EMPTY, 0, 0, m); continue; }
         if (mt.adopted) continue;                 // fqd_adopt_device parsed everything in place
         // a segment may hold more records than one parse takes (chunk_cap): keep parsing its carried tail
         for (;;) {
@@ -1318,7 +1387,10 @@ static int seq_parse_rest(SeqState* s, std::string* err) {
     if (s->stats.err) return FQD_OK;            // data error: reported through fqd_stats, like the fast mode
     u64 n = s->mate[0].n_records;
     if (s->mates == 2 && !s->cfg.unordered) n = std::min(n, s->mate[1].n_records);      // stops at the shorter file
-    if (n == 0 || (s->mates == 2 && s->mate[1].n_records == 0)) { seq_set_error(s, FQD_ERR_EMPTY, 0, 0, 0); return FQD_OK; }
+    if (n == 0 || (s->mates == 2 && s->mate[1].n_records == 0)) {
+        if (!allow_empty) seq_set_error(s, FQD_ERR_EMPTY, 0, 0, 0);
+        if (!allow_empty || !s->cfg.unordered) return FQD_OK;
+    }
     s->n = n;
     return FQD_OK;
 }
@@ -1370,89 +1442,263 @@ static int seq_finish(SeqState* s, std::string* err) {
     return FQD_OK;
 }
 
-static int seq_finish_unordered(SeqState* s, std::string* err) {
-    const u64 n = s->mate[0].n_records, m = s->mate[1].n_records;
-    int rc;
-    u32 *permL, *permR;
-    if ((rc = seq_dalloc(s, &permL, n, err)) || (rc = seq_dalloc(s, &permR, m, err))) return rc;
-    // ExternalSorter<*ViewWithId> on each file (src/hash_dup_remover.hpp:163-173), stable on the input index
-    if ((rc = sort_rows(s, s->mate[0].d_tags, s->TW, 0, s->TW, 64, n, permL, err))) return rc;
-    if ((rc = sort_rows(s, s->mate[1].d_tags, s->TW, 0, s->TW, 64, m, permR, err))) return rc;
-
-    const u64 big = std::max(n, m);
-    u32 *matchL, *matchR, *emit, *unL, *unR, *excl;
-    JoinStop* d_stop;
-    if ((rc = seq_dalloc(s, &matchL, n, err)) || (rc = seq_dalloc(s, &matchR, m, err)) || (rc = seq_dalloc(s, &emit, n, err)) ||
-        (rc = seq_dalloc(s, &unL, n, err)) || (rc = seq_dalloc(s, &unR, m, err)) || (rc = seq_dalloc(s, &excl, big, err)) ||
-        (rc = seq_dalloc(s, &d_stop, 1, err))) return rc;
-    SEQ_TRY(cudaMemsetAsync(matchR, 0xFF, m * sizeof(u32), s->stream));
+static JoinParams un_join_params(SeqState* s) {
+    UnJoin& u = s->un;
     JoinParams jp;
-    jp.tagsL = s->mate[0].d_tags; jp.permL = permL; jp.n = (u32)n; jp.tagsR = s->mate[1].d_tags; jp.permR = permR; jp.m = (u32)m;
-    jp.TW = s->TW; jp.matchL = matchL; jp.matchR = matchR;
-    k_join_match<<<seq_grid(s, n), 256, 0, s->stream>>>(jp);
-    k_join_stop<<<1, 1, 0, s->stream>>>(jp, d_stop);
-    k_join_flags<<<seq_grid(s, big), 256, 0, s->stream>>>(jp, d_stop, emit, unL, unR);
-    s->launches += 3;
-    SortScratch sc;
-    if ((rc = seq_dalloc(s, &sc.scan_state, (big + SCAN_TILE - 1) / SCAN_TILE + 16, err)) || (rc = seq_dalloc(s, &sc.ticket, 4, err)) ||
-        (rc = seq_dalloc(s, &sc.d_total, 2, err))) return rc;
-    u64 uL = 0, uR = 0, E = 0;
-    if ((rc = device_scan(s, sc, unL, excl, n, &uL, err))) return rc;
-    if ((rc = device_scan(s, sc, unR, excl, m, &uR, err))) return rc;
-    if ((rc = device_scan(s, sc, emit, excl, n, &E, err))) return rc;
-    JoinStop hs;
-    SEQ_TRY(cudaMemcpy(&hs, d_stop, sizeof hs, cudaMemcpyDeviceToHost));
-    s->stats.unmatched = uL + uR + (hs.final_equal ? 0 : 1);
-    s->stats.total = E;
-    s->n = E;
-    s->n_out = 0;
-    if (E == 0) { s->stats.dups = 0; return FQD_OK; }
+    jp.tagsL = s->mate[0].d_tags; jp.permL = u.permL; jp.n = (u32)s->mate[0].n_records;
+    jp.tagsR = s->mate[1].d_tags; jp.permR = u.permR; jp.m = (u32)s->mate[1].n_records;
+    jp.TW = s->TW; jp.matchL = u.matchL; jp.matchR = u.matchR;
+    return jp;
+}
 
-    // exact first-occurrence set over the pair keys, in emission order (src/hash_dup_remover.hpp:291-306)
-    const u32 W = s->W;
-    u64 *pair_rows, *h1, *h2, *first_bad, *table;
-    u32 *idxL, *idxR, *keep;
-    u8* dup;
-    RunState* run;
-    u64 nb = 1024;
-    while (nb * 2 < E) nb <<= 1;
-    u32 lg = 0; while ((1ull << lg) < nb) ++lg;
-    if ((rc = seq_dalloc(s, &pair_rows, E * 2 * W, err)) || (rc = seq_dalloc(s, &h1, E, err)) || (rc = seq_dalloc(s, &h2, E, err)) ||
-        (rc = seq_dalloc(s, &first_bad, 1, err)) || (rc = seq_dalloc(s, &table, nb * 4, err)) || (rc = seq_dalloc(s, &idxL, E, err)) ||
-        (rc = seq_dalloc(s, &idxR, E, err)) || (rc = seq_dalloc(s, &keep, E, err)) || (rc = seq_dalloc(s, &dup, E + 64, err)) ||
-        (rc = seq_dalloc(s, &run, 1, err))) return rc;
-    SEQ_TRY(cudaMemsetAsync(first_bad, 0xFF, sizeof(u64), s->stream));
-    SEQ_TRY(cudaMemsetAsync(table, 0xFF, nb * 4 * sizeof(u64), s->stream));
-    SEQ_TRY(cudaMemsetAsync(dup, 0, E + 64, s->stream));
-    k_build_pairs<<<seq_grid(s, n), 256, 0, s->stream>>>(jp, d_stop, emit, excl, s->d_keys, s->row_words, W, s->mate[0].d_hash, s->mate[1].d_hash,
-                                                         s->mate[0].d_bad, s->mate[1].d_bad, pair_rows, h1, h2, idxL, idxR, first_bad);
-    k_set_chunk_pairs<<<1, 1, 0, s->stream>>>(run, (u32)E);
-    InsertParams ip;
-    ip.table = table; ip.bucket_shift = 64 - lg; ip.bucket_mask = nb - 1; ip.keys = pair_rows; ip.row_words = 2 * W; ip.key_capacity = E;
-    ip.hash1 = h1; ip.hash2 = h2; ip.ctl1 = nullptr; ip.ctl2 = nullptr; ip.run = run; ip.dup = dup; ip.hash_mul = 1; ip.hash_final = 0;
-    insert_launch(ip, s->sm * 8, s->stream);
-    s->launches += 3;
-    u64 hbad = 0;
-    SEQ_TRY(cudaMemcpy(&hbad, first_bad, sizeof hbad, cudaMemcpyDeviceToHost));
-    u64 limit = E;
-    if (hbad != ~0ull) {      // a matched pair holds a byte outside {A,C,G,T,N}: the run aborts when it is keyed
-        limit = hbad >> 8;
-        seq_set_error(s, FQD_ERR_BAD_BASE, (int)(hbad & 0xFF), limit, 0);
+// stage 1: ExternalSorter<*ViewWithId> on each file (src/hash_dup_remover.hpp:163-173), stable on the input index, and
+// the partner of every record (k-th record of a tag in L with the k-th of the same tag in R)
+static int un_prepare(SeqState* s, std::string* err) {
+    UnJoin& u = s->un;
+    const u64 n = s->mate[0].n_records, m = s->mate[1].n_records;
+    const u64 big = std::max(n, m);
+    int rc;
+    if ((rc = seq_dalloc(s, &u.permL, n, err)) || (rc = seq_dalloc(s, &u.permR, m, err))) return rc;
+    if (n && (rc = sort_rows(s, s->mate[0].d_tags, s->TW, 0, s->TW, 64, n, u.permL, err))) return rc;
+    if (m && (rc = sort_rows(s, s->mate[1].d_tags, s->TW, 0, s->TW, 64, m, u.permR, err))) return rc;
+    if ((rc = seq_dalloc(s, &u.matchL, n, err)) || (rc = seq_dalloc(s, &u.matchR, m, err)) || (rc = seq_dalloc(s, &u.emit, n, err)) ||
+        (rc = seq_dalloc(s, &u.unL, n, err)) || (rc = seq_dalloc(s, &u.unR, m, err)) || (rc = seq_dalloc(s, &u.excl, big, err)) ||
+        (rc = seq_dalloc(s, &u.d_stop, 1, err))) return rc;
+    if ((rc = seq_dalloc(s, &u.sc.scan_state, (big + SCAN_TILE - 1) / SCAN_TILE + 16, err)) || (rc = seq_dalloc(s, &u.sc.ticket, 4, err)) ||
+        (rc = seq_dalloc(s, &u.sc.d_total, 2, err))) return rc;
+    if (n) SEQ_TRY(cudaMemsetAsync(u.matchL, 0xFF, n * sizeof(u32), s->stream));
+    if (m) SEQ_TRY(cudaMemsetAsync(u.matchR, 0xFF, m * sizeof(u32), s->stream));
+    if (n && m) {
+        k_join_match<<<seq_grid(s, n), 256, 0, s->stream>>>(un_join_params(s));
+        s->launches++;
     }
-    k_keep_from_dup<<<seq_grid(s, E), 256, 0, s->stream>>>(dup, E, limit, keep);
+    SEQ_TRY(cudaGetLastError());
+    u.stage = 1;
+    return FQD_OK;
+}
+
+// stage 2: which pairs the walk emits (given == nullptr: both whole files are here, the stop state is computed; else
+// it is this range's share of the job's stop state), their order, their keys
+static int un_join(SeqState* s, const JoinStop* given, std::string* err) {
+    UnJoin& u = s->un;
+    const u64 n = s->mate[0].n_records, m = s->mate[1].n_records;
+    const u64 big = std::max(n, m);
+    const JoinParams jp = un_join_params(s);
+    int rc;
+    if (!given) k_join_stop<<<1, 1, 0, s->stream>>>(jp, u.d_stop);
+    else {
+        SEQ_TRY(cudaMemcpyAsync(u.d_stop, given, sizeof(JoinStop), cudaMemcpyHostToDevice, s->stream));
+        k_join_final<<<1, 1, 0, s->stream>>>(jp, u.d_stop);
+    }
+    if (big) k_join_flags<<<seq_grid(s, big), 256, 0, s->stream>>>(jp, u.d_stop, u.emit, u.unL, u.unR);
+    s->launches += 2;
+    u64 uL = 0, uR = 0, E = 0;
+    if ((rc = device_scan(s, u.sc, u.unL, u.excl, n, &uL, err))) return rc;
+    if ((rc = device_scan(s, u.sc, u.unR, u.excl, m, &uR, err))) return rc;
+    if ((rc = device_scan(s, u.sc, u.emit, u.excl, n, &E, err))) return rc;
+    JoinStop hs;
+    SEQ_TRY(cudaMemcpyAsync(&hs, u.d_stop, sizeof hs, cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    u.final_equal = hs.final_equal;
+    u.unmatched = uL + uR;
+    u.E = E;
+    u.hbad = ~0ull;
+    u.stage = 2;
+    if (E == 0) return FQD_OK;
+    const u32 W = s->W;
+    if ((rc = seq_dalloc(s, &u.pair_rows, E * 2 * W, err)) || (rc = seq_dalloc(s, &u.h1, E, err)) || (rc = seq_dalloc(s, &u.h2, E, err)) ||
+        (rc = seq_dalloc(s, &u.first_bad, 1, err)) || (rc = seq_dalloc(s, &u.idxL, E, err)) || (rc = seq_dalloc(s, &u.idxR, E, err)) ||
+        (rc = seq_dalloc(s, &u.keep, E, err)) || (rc = seq_dalloc(s, &u.dup, E + 64, err))) return rc;
+    SEQ_TRY(cudaMemsetAsync(u.first_bad, 0xFF, sizeof(u64), s->stream));
+    SEQ_TRY(cudaMemsetAsync(u.dup, 0, E + 64, s->stream));
+    k_build_pairs<<<seq_grid(s, n), 256, 0, s->stream>>>(jp, u.d_stop, u.emit, u.excl, s->d_keys, s->row_words, W, s->mate[0].d_hash, s->mate[1].d_hash,
+                                                         s->mate[0].d_bad, s->mate[1].d_bad, u.pair_rows, u.h1, u.h2, u.idxL, u.idxR, u.first_bad);
+    s->launches++;
+    SEQ_TRY(cudaMemcpyAsync(&u.hbad, u.first_bad, sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    return FQD_OK;
+}
+
+// exact first-occurrence set over `n_rows` pair keys (src/hash_dup_remover.hpp:291-306): the row with the smallest
+// position among equal keys stays, the others get their flag set
+static int un_insert_rows(SeqState* s, const u64* rows, const u64* h1, const u64* h2, u64 n_rows, u64 hash_mul, u8* flags, std::string* err) {
+    u64* table; RunState* run;
+    u64 nb = 1024;
+    while (nb * 2 < n_rows) nb <<= 1;
+    u32 lg = 0; while ((1ull << lg) < nb) ++lg;
+    int rc;
+    if ((rc = seq_dalloc(s, &table, nb * 4, err)) || (rc = seq_dalloc(s, &run, 1, err))) return rc;
+    SEQ_TRY(cudaMemsetAsync(table, 0xFF, nb * 4 * sizeof(u64), s->stream));
+    k_set_chunk_pairs<<<1, 1, 0, s->stream>>>(run, (u32)n_rows);
+    InsertParams ip;
+    ip.table = table; ip.bucket_shift = 64 - lg; ip.bucket_mask = nb - 1; ip.keys = rows; ip.row_words = 2 * s->W; ip.key_capacity = n_rows;
+    ip.hash1 = h1; ip.hash2 = h2; ip.ctl1 = nullptr; ip.ctl2 = nullptr; ip.run = run; ip.dup = flags; ip.hash_mul = hash_mul; ip.hash_final = h2 ? 0 : 1;
+    insert_launch(ip, s->sm * 8, s->stream);
+    s->launches += 2;
+    SEQ_TRY(cudaGetLastError());
+    return FQD_OK;
+}
+
+// stage 3: survivors = emitted pairs before `limit` whose flag is clear; their records, in emission order
+static int un_finish(SeqState* s, u64 limit, bool report_bad, std::string* err) {
+    UnJoin& u = s->un;
+    const u64 E = u.E;
+    int rc;
+    u.stage = 3;
+    s->n = E; s->n_out = 0;
+    s->stats.total = limit; s->stats.dups = 0;
+    if (report_bad) seq_set_error(s, FQD_ERR_BAD_BASE, (int)(u.hbad & 0xFF), limit, 0);
+    if (E == 0) return FQD_OK;
+    k_keep_from_dup<<<seq_grid(s, E), 256, 0, s->stream>>>(u.dup, E, limit, u.keep);
     u64 n_out = 0;
-    if ((rc = device_scan(s, sc, keep, excl, E, &n_out, err))) return rc;
+    if ((rc = device_scan(s, u.sc, u.keep, u.excl, E, &n_out, err))) return rc;
     s->n_out = n_out;
-    s->stats.total = limit;
     s->stats.dups = limit - n_out;
     u64* o_off[2]; u32* o_len[2];
     for (u32 k = 0; k < 2; ++k)
         if ((rc = seq_dalloc(s, &o_off[k], n_out, err)) || (rc = seq_dalloc(s, &o_len[k], n_out, err))) return rc;
-    k_emit_pairs<<<seq_grid(s, E), 256, 0, s->stream>>>(keep, excl, E, idxL, idxR, s->mate[0].d_rec_off, s->mate[0].d_rec_len,
+    k_emit_pairs<<<seq_grid(s, E), 256, 0, s->stream>>>(u.keep, u.excl, E, u.idxL, u.idxR, s->mate[0].d_rec_off, s->mate[0].d_rec_len,
                                                         s->mate[1].d_rec_off, s->mate[1].d_rec_len, o_off[0], o_len[0], o_off[1], o_len[1]);
     s->launches += 2;
     for (u32 k = 0; k < 2; ++k) { s->d_o_off[k] = o_off[k]; s->d_o_len[k] = o_len[k]; }
     SEQ_TRY(cudaStreamSynchronize(s->stream));
+    return FQD_OK;
+}
+
+static int seq_finish_unordered(SeqState* s, std::string* err) {
+    UnJoin& u = s->un;
+    int rc;
+    if ((rc = un_prepare(s, err)) || (rc = un_join(s, nullptr, err))) return rc;
+    s->stats.unmatched = u.unmatched + (u.final_equal ? 0 : 1);
+    s->stats.total = u.E;
+    s->n = u.E;
+    s->n_out = 0;
+    if (u.E == 0) { s->stats.dups = 0; u.stage = 3; return FQD_OK; }
+    if ((rc = un_insert_rows(s, u.pair_rows, u.h1, u.h2, u.E, 1, u.dup, err))) return rc;
+    // a matched pair holds a byte outside {A,C,G,T,N}: the run aborts when it is keyed
+    const bool bad = u.hbad != ~0ull;
+    return un_finish(s, bad ? (u.hbad >> 8) : u.E, bad, err);
+}
+
+// ---- --unordered across GPUs: the stages one by one (fastq-dupaway_b200/sharded_unordered.py holds the protocol).
+// This engine holds the records of both files whose tags fall into ONE tag range; ranges in rank order = tag order.
+static int seq_unordered_prepare(SeqState* s, u64* n_left, u64* n_right, std::string* err) {
+    if (!s->cfg.unordered) { *err = "fqd_unordered_prepare is for --unordered handles"; return FQD_ERR_INVALID; }
+    if (s->finished || s->un.stage) { *err = "fqd_unordered_prepare called twice"; return FQD_ERR_INVALID; }
+    int rc = seq_parse_rest(s, err, true);          // a range may well be empty on one side or on both
+    if (rc) return rc;
+    *n_left = s->mate[0].n_records; *n_right = s->mate[1].n_records;
+    if (s->stats.err) return FQD_OK;
+    SEQ_TRY(cudaEventRecord(s->ev0, s->stream));
+    if ((rc = un_prepare(s, err))) return rc;
+    SEQ_TRY(cudaEventRecord(s->ev1, s->stream));
+    SEQ_TRY(cudaEventSynchronize(s->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, s->ev0, s->ev1); s->ms += ms;
+    return FQD_OK;
+}
+static int seq_unordered_enter(SeqState* s, int side, u64 i, u64* pos, std::string* err) {
+    if (s->un.stage < 1) { *err = "fqd_unordered_enter before fqd_unordered_prepare"; return FQD_ERR_INVALID; }
+    const u64 na = s->mate[side ? 1 : 0].n_records;
+    if (i > na) { *err = "fqd_unordered_enter: position outside the list"; return FQD_ERR_INVALID; }
+    u32* d_out; u32 h = 0;
+    int rc;
+    if ((rc = seq_dalloc(s, &d_out, 1, err))) return rc;
+    k_join_enter<<<1, 1, 0, s->stream>>>(un_join_params(s), side, (u32)i, d_out);
+    s->launches++;
+    SEQ_TRY(cudaMemcpyAsync(&h, d_out, sizeof h, cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    *pos = h;
+    return FQD_OK;
+}
+// out: pairs emitted here, unmatched records here (the job adds one when its last comparison fails), emission index of
+// the first pair holding a byte outside {A,C,G,T,N} (~0 = none), 1 when the job's last comparison happened here and matched
+static int seq_unordered_join(SeqState* s, u64 limit_i, u64 limit_j, u64 final_i, u64 final_j, u64* out, std::string* err) {
+    if (s->un.stage != 1) { *err = "fqd_unordered_join needs fqd_unordered_prepare first (once)"; return FQD_ERR_INVALID; }
+    JoinStop g;
+    g.limit_i = (u32)std::min<u64>(limit_i, s->mate[0].n_records); g.limit_j = (u32)std::min<u64>(limit_j, s->mate[1].n_records);
+    g.is = final_i < s->mate[0].n_records ? (u32)final_i : 0xFFFFFFFFu;
+    g.js = final_j < s->mate[1].n_records ? (u32)final_j : 0xFFFFFFFFu;
+    g.final_equal = 0; g.use_a = 0;
+    SEQ_TRY(cudaEventRecord(s->ev0, s->stream));
+    int rc = un_join(s, &g, err);
+    if (rc) return rc;
+    SEQ_TRY(cudaEventRecord(s->ev1, s->stream));
+    SEQ_TRY(cudaEventSynchronize(s->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, s->ev0, s->ev1); s->ms += ms;
+    out[0] = s->un.E; out[1] = s->un.unmatched; out[2] = s->un.hbad == ~0ull ? ~0ull : (s->un.hbad >> 8); out[3] = s->un.final_equal;
+    return FQD_OK;
+}
+// rows [pair key 2W words][hash] of the pairs before `limit`, grouped by the owner of their hash range, emission order
+// kept inside a group; counts[n_shards]
+static int seq_unordered_rows(SeqState* s, u64 limit, u32 n_shards, void* d_send, u64* counts, std::string* err) {
+    UnJoin& u = s->un;
+    if (u.stage != 2) { *err = "fqd_unordered_rows needs fqd_unordered_join first"; return FQD_ERR_INVALID; }
+    if (n_shards == 0 || n_shards > 64) { *err = "bad number of hash ranges"; return FQD_ERR_INVALID; }
+    limit = std::min(limit, u.E);
+    for (u32 o = 0; o < n_shards; ++o) counts[o] = 0;
+    u.n_send = limit;
+    if (limit == 0) return FQD_OK;
+    int rc;
+    SortScratch sc;
+    u64* d_starts;
+    if ((rc = sort_scratch_alloc(s, sc, limit, err)) || (rc = seq_dalloc(s, &d_starts, n_shards + 1, err)) ||
+        (rc = seq_dalloc(s, &u.send_idx, limit, err))) return rc;
+    SEQ_TRY(cudaEventRecord(s->ev0, s->stream));
+    k_un_owner<<<seq_grid(s, limit), 256, 0, s->stream>>>(u.h1, u.h2, limit, n_shards, sc.keyA, sc.aA);
+    if ((rc = radix_sort(s, sc, limit, 0, 8, false, err))) return rc;
+    k_range_starts<<<1, 128, 0, s->stream>>>(sc.keyA, limit, n_shards, d_starts);
+    SEQ_TRY(cudaMemcpyAsync(u.send_idx, sc.aA, limit * sizeof(u32), cudaMemcpyDeviceToDevice, s->stream));
+    k_un_gather<<<seq_grid(s, limit * (2 * s->W + 1)), 256, 0, s->stream>>>(u.pair_rows, 2 * s->W, u.h1, u.h2, u.send_idx, limit, (u64*)d_send);
+    s->launches += 3;
+    std::vector<u64> h_starts(n_shards + 1);
+    SEQ_TRY(cudaMemcpyAsync(h_starts.data(), d_starts, (n_shards + 1) * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaEventRecord(s->ev1, s->stream));
+    SEQ_TRY(cudaEventSynchronize(s->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, s->ev0, s->ev1); s->ms += ms;
+    for (u32 o = 0; o < n_shards; ++o) counts[o] = h_starts[o + 1] - h_starts[o];
+    SEQ_TRY(cudaGetLastError());
+    return FQD_OK;
+}
+// owner side: the rows every range sent here, in rank order (= the job's emission order); d_flags[i] = 1 when an
+// earlier row holds the same key
+static int seq_unordered_insert(SeqState* s, const void* d_recv, u64 n_recv, u32 n_shards, void* d_flags, std::string* err) {
+    if (!s->cfg.unordered) { *err = "fqd_unordered_insert is for --unordered handles"; return FQD_ERR_INVALID; }
+    if (n_recv == 0) return FQD_OK;
+    if (n_recv > 0xFFFFFFF0ull) { *err = "too many rows for one hash range"; return FQD_ERR_CAPACITY; }
+    const u32 RW = 2 * s->W;
+    u64 *keys, *hash; RunState* run;
+    int rc;
+    if ((rc = seq_dalloc(s, &keys, n_recv * RW, err)) || (rc = seq_dalloc(s, &hash, n_recv, err)) || (rc = seq_dalloc(s, &run, 1, err))) return rc;
+    SEQ_TRY(cudaEventRecord(s->ev0, s->stream));
+    SEQ_TRY(cudaMemsetAsync(d_flags, 0, n_recv, s->stream));
+    SEQ_TRY(cudaMemsetAsync(run, 0, sizeof(RunState), s->stream));
+    k_shard_append<<<seq_grid(s, n_recv * (RW + 1)), 256, 0, s->stream>>>((const u64*)d_recv, (u32)n_recv, RW, keys, run, n_recv, hash);
+    s->launches++;
+    if ((rc = un_insert_rows(s, keys, hash, nullptr, n_recv, n_shards, (u8*)d_flags, err))) return rc;
+    SEQ_TRY(cudaEventRecord(s->ev1, s->stream));
+    SEQ_TRY(cudaEventSynchronize(s->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, s->ev0, s->ev1); s->ms += ms;
+    return FQD_OK;
+}
+// flags of the rows this range sent (in sending order) -> survivors and emission lists.  unmatched: the JOB's figure is
+// kept by the driver; this handle reports its own share.
+static int seq_unordered_apply(SeqState* s, const void* d_flags_back, u64 limit, int report_bad, std::string* err) {
+    UnJoin& u = s->un;
+    if (u.stage != 2) { *err = "fqd_unordered_apply needs fqd_unordered_join first"; return FQD_ERR_INVALID; }
+    if (s->finished) { *err = "fqd_finish called twice"; return FQD_ERR_INVALID; }
+    s->finished = true;
+    limit = std::min(limit, u.E);
+    SEQ_TRY(cudaEventRecord(s->ev0, s->stream));
+    if (u.n_send) {
+        k_un_flags_back<<<seq_grid(s, u.n_send), 256, 0, s->stream>>>((const u8*)d_flags_back, u.send_idx, u.n_send, u.dup);
+        s->launches++;
+    }
+    s->stats.unmatched = u.unmatched;
+    int rc = un_finish(s, limit, report_bad != 0, err);
+    if (rc) return rc;
+    SEQ_TRY(cudaEventRecord(s->ev1, s->stream));
+    SEQ_TRY(cudaEventSynchronize(s->ev1));
+    float ms = 0; cudaEventElapsedTime(&ms, s->ev0, s->ev1); s->ms += ms;
     return FQD_OK;
 }
 
@@ -1548,75 +1794,111 @@ static int seq_upload_segtab(SeqState* s, int m, std::string* err) {
 // with the ordinary single-GPU engine.  Rows with equal leading words share an owner, so exact duplicates never
 // straddle two ranks; prefix and Hamming neighbours can, which the boundary state above takes care of.
 static int seq_partition_sample(SeqState* s, u32 n_samples, u64* out, u64* n_records, std::string* err) {
-    int rc = seq_parse_rest(s, err);
+    const bool un = s->cfg.unordered != 0;
+    int rc = seq_parse_rest(s, err, un);
     if (rc) return rc;
+    for (u32 i = 0; i < 2 * n_samples; ++i) out[i] = ~0ull;
+    if (un) {
+        // --unordered: the two files are partitioned independently, each by its own ID tags; half of the samples each
+        *n_records = s->stats.err ? 0 : s->mate[0].n_records + s->mate[1].n_records;
+        if (s->stats.err || n_samples < 2) return FQD_OK;
+        const u32 half = n_samples / 2;
+        u64* d_out;
+        if ((rc = seq_dalloc(s, &d_out, 2ull * n_samples, err))) return rc;
+        SEQ_TRY(cudaMemsetAsync(d_out, 0xFF, 2ull * n_samples * sizeof(u64), s->stream));
+        for (u32 m = 0; m < 2; ++m) {
+            if (!s->mate[m].n_records) continue;
+            k_sample_rows<<<(half + 255) / 256, 256, 0, s->stream>>>(s->mate[m].d_tags, s->TW, s->TW, s->mate[m].n_records, half, d_out + 2ull * m * half);
+            s->launches++;
+        }
+        SEQ_TRY(cudaMemcpyAsync(out, d_out, 2ull * n_samples * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+        SEQ_TRY(cudaStreamSynchronize(s->stream));
+        return FQD_OK;
+    }
     *n_records = s->stats.err ? 0 : s->n;
     if (s->stats.err == FQD_ERR_EMPTY) { s->stats.err = 0; s->n = 0; }      // an empty slice is fine here
-    if (s->stats.err || s->n == 0 || n_samples == 0) { for (u32 i = 0; i < 2 * n_samples; ++i) out[i] = ~0ull; return FQD_OK; }
+    if (s->stats.err || s->n == 0 || n_samples == 0) return FQD_OK;
     u64* d_out;
     if ((rc = seq_dalloc(s, &d_out, 2ull * n_samples, err))) return rc;
-    k_sample_rows<<<(n_samples + 255) / 256, 256, 0, s->stream>>>(s->d_keys, s->row_words, s->n, n_samples, d_out);
+    k_sample_rows<<<(n_samples + 255) / 256, 256, 0, s->stream>>>(s->d_keys, s->row_words, s->row_words, s->n, n_samples, d_out);
     s->launches++;
     SEQ_TRY(cudaMemcpyAsync(out, d_out, 2ull * n_samples * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
     SEQ_TRY(cudaStreamSynchronize(s->stream));
     return FQD_OK;
 }
 
-// splitters: (G-1) x 2 words, ascending.  counts[G]: records per owner; bytes[mates * G]: raw bytes per mate and owner
-static int seq_partition_plan(SeqState* s, const u64* splitters, u32 G, u64* counts, u64* bytes, std::string* err) {
-    if (!s->parsed) { *err = "fqd_partition_plan before fqd_partition_sample"; return FQD_ERR_INVALID; }
-    if (G == 0 || G > 64) { *err = "bad number of key ranges"; return FQD_ERR_INVALID; }
-    const u64 n = s->n;
-    s->part_G = G; s->part_n = n;
-    for (u32 o = 0; o < G; ++o) { counts[o] = 0; for (u32 m = 0; m < s->mates; ++m) bytes[m * G + o] = 0; }
+// One partition: records [0, n) with key rows `rows` go to the owner of their (word 0, word 1); perm = the records
+// grouped by owner (input order kept), counts[G] += records per owner, and for the mates [m0, m1) that travel with this
+// partition the byte offset of every record in the owner-grouped stream + bytes[m * G + o].
+static int partition_one(SeqState* s, const u64* rows, u32 stride, u32 nw, u64 n, const u64* d_split, u32 G, u32 m0, u32 m1,
+                         u32** perm_out, u64* counts, u64* bytes, std::string* err) {
     if (n == 0) return FQD_OK;
     int rc;
     SortScratch sc;
-    if ((rc = sort_scratch_alloc(s, sc, n, err))) return rc;
-    u64* d_split;
-    if ((rc = seq_dalloc(s, &d_split, 2ull * std::max(G, 2u), err)) || (rc = seq_dalloc(s, &s->d_part_starts, G + 1, err)) ||
-        (rc = seq_dalloc(s, &s->d_part_perm, n, err))) return rc;
-    if (G > 1) SEQ_TRY(cudaMemcpyAsync(d_split, splitters, 2ull * (G - 1) * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
-    k_range_owner<<<seq_grid(s, n), 256, 0, s->stream>>>(s->d_keys, s->row_words, n, d_split, G - 1, sc.keyA, sc.aA);
+    u64* d_starts;
+    if ((rc = sort_scratch_alloc(s, sc, n, err)) || (rc = seq_dalloc(s, &d_starts, G + 1, err)) || (rc = seq_dalloc(s, perm_out, n, err))) return rc;
+    k_range_owner<<<seq_grid(s, n), 256, 0, s->stream>>>(rows, stride, nw, n, d_split, G - 1, sc.keyA, sc.aA);
     if ((rc = radix_sort(s, sc, n, 0, 8, false, err))) return rc;
-    k_range_starts<<<1, 128, 0, s->stream>>>(sc.keyA, n, G, s->d_part_starts);
-    SEQ_TRY(cudaMemcpyAsync(s->d_part_perm, sc.aA, n * sizeof(u32), cudaMemcpyDeviceToDevice, s->stream));
+    k_range_starts<<<1, 128, 0, s->stream>>>(sc.keyA, n, G, d_starts);
+    SEQ_TRY(cudaMemcpyAsync(*perm_out, sc.aA, n * sizeof(u32), cudaMemcpyDeviceToDevice, s->stream));
     s->launches += 2;
     std::vector<u64> h_starts(G + 1), h_pick(G + 1);
-    SEQ_TRY(cudaMemcpyAsync(h_starts.data(), s->d_part_starts, (G + 1) * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
-    // byte offset of every record in the owner-grouped stream of each mate
+    SEQ_TRY(cudaMemcpyAsync(h_starts.data(), d_starts, (G + 1) * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
     u32* lens;
     u64* d_pick;
     if ((rc = seq_dalloc(s, &lens, n, err)) || (rc = seq_dalloc(s, &d_pick, G + 1, err))) return rc;
-    for (u32 m = 0; m < s->mates; ++m) {
+    for (u32 m = m0; m < m1; ++m) {
         if ((rc = seq_dalloc(s, &s->d_part_off[m], n + 1, err))) return rc;
-        k_gather_u32<<<seq_grid(s, n), 256, 0, s->stream>>>(s->mate[m].d_rec_len, s->d_part_perm, n, lens);
+        k_gather_u32<<<seq_grid(s, n), 256, 0, s->stream>>>(s->mate[m].d_rec_len, *perm_out, n, lens);
         const u64 tiles = (n + SCAN_TILE - 1) / SCAN_TILE;
         SEQ_TRY(cudaMemsetAsync(sc.scan_state, 0, tiles * sizeof(u64), s->stream));
         SEQ_TRY(cudaMemsetAsync(sc.ticket, 0, sizeof(u32), s->stream));
         k_scan_exclusive_t<u64><<<(unsigned)tiles, SCAN_THREADS, 0, s->stream>>>(lens, s->d_part_off[m], n, sc.scan_state, sc.ticket, sc.d_total);
         SEQ_TRY(cudaMemcpyAsync(s->d_part_off[m] + n, sc.d_total, sizeof(u64), cudaMemcpyDeviceToDevice, s->stream));
-        k_pick_u64<<<1, 128, 0, s->stream>>>(s->d_part_off[m], s->d_part_starts, G + 1, n + 1, 0, d_pick);
+        k_pick_u64<<<1, 128, 0, s->stream>>>(s->d_part_off[m], d_starts, G + 1, n + 1, 0, d_pick);
         s->launches += 3;
         SEQ_TRY(cudaMemcpyAsync(h_pick.data(), d_pick, (G + 1) * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
         SEQ_TRY(cudaStreamSynchronize(s->stream));
         for (u32 o = 0; o < G; ++o) bytes[m * G + o] = h_pick[o + 1] - h_pick[o];
     }
-    for (u32 o = 0; o < G; ++o) counts[o] = h_starts[o + 1] - h_starts[o];
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    for (u32 o = 0; o < G; ++o) counts[o] += h_starts[o + 1] - h_starts[o];
     SEQ_TRY(cudaGetLastError());
     return FQD_OK;
 }
 
+// splitters: (G-1) x 2 words, ascending.  counts[G]: records per owner (--unordered: of both files together);
+// bytes[mates * G]: raw bytes per mate and owner
+static int seq_partition_plan(SeqState* s, const u64* splitters, u32 G, u64* counts, u64* bytes, std::string* err) {
+    if (!s->parsed) { *err = "fqd_partition_plan before fqd_partition_sample"; return FQD_ERR_INVALID; }
+    if (G == 0 || G > 64) { *err = "bad number of key ranges"; return FQD_ERR_INVALID; }
+    const bool un = s->cfg.unordered != 0;
+    s->part_G = G;
+    s->part_n = un ? s->mate[0].n_records : s->n;
+    s->part_n1 = un ? s->mate[1].n_records : 0;
+    for (u32 o = 0; o < G; ++o) { counts[o] = 0; for (u32 m = 0; m < s->mates; ++m) bytes[m * G + o] = 0; }
+    if (s->part_n + s->part_n1 == 0) return FQD_OK;
+    int rc;
+    u64* d_split;
+    if ((rc = seq_dalloc(s, &d_split, 2ull * std::max(G, 2u), err))) return rc;
+    if (G > 1) SEQ_TRY(cudaMemcpyAsync(d_split, splitters, 2ull * (G - 1) * sizeof(u64), cudaMemcpyHostToDevice, s->stream));
+    if (!un) return partition_one(s, s->d_keys, s->row_words, s->row_words, s->part_n, d_split, G, 0, s->mates, &s->d_part_perm, counts, bytes, err);
+    if ((rc = partition_one(s, s->mate[0].d_tags, s->TW, s->TW, s->part_n, d_split, G, 0, 1, &s->d_part_perm, counts, bytes, err))) return rc;
+    return partition_one(s, s->mate[1].d_tags, s->TW, s->TW, s->part_n1, d_split, G, 1, 2, &s->d_part_perm1, counts, bytes, err);
+}
+
 // the records of one mate, grouped by owner (input order inside a group), written back to back into d_out
 static int seq_partition_gather(SeqState* s, int m, void* d_out, std::string* err) {
-    if (!s->d_part_perm && s->part_n) { *err = "fqd_partition_gather before fqd_partition_plan"; return FQD_ERR_INVALID; }
     if (m < 0 || (u32)m >= s->mates) { *err = "bad mate index"; return FQD_ERR_INVALID; }
-    if (s->part_n == 0) return FQD_OK;
+    const bool second = s->cfg.unordered && m == 1;
+    const u32* perm = second ? s->d_part_perm1 : s->d_part_perm;
+    const u64 n = second ? s->part_n1 : s->part_n;
+    if (!perm && n) { *err = "fqd_partition_gather before fqd_partition_plan"; return FQD_ERR_INVALID; }
+    if (n == 0) return FQD_OK;
     int rc = seq_upload_segtab(s, m, err);
     if (rc) return rc;
-    k_gather_records_perm<<<seq_grid(s, s->part_n), 256, 0, s->stream>>>(s->mate[m].d_rec_off, s->mate[m].d_rec_len, s->d_part_perm,
-                                                                             s->d_part_off[m], s->part_n, s->d_seg_base[m], s->d_seg_ptr[m],
-                                                                             s->n_segs[m], (u8*)d_out);
+    k_gather_records_perm<<<seq_grid(s, n), 256, 0, s->stream>>>(s->mate[m].d_rec_off, s->mate[m].d_rec_len, perm, s->d_part_off[m], n,
+                                                                 s->d_seg_base[m], s->d_seg_ptr[m], s->n_segs[m], (u8*)d_out);
     s->launches++;
     SEQ_TRY(cudaGetLastError());
     return FQD_OK;

@@ -265,14 +265,26 @@ __global__ void k_mark_unresolved(const u64* __restrict__ rows, u32 stride, u32 
 // differing word is reached (a difference in the last 10 bases of a 150 bp read took 7 rounds: 19 - 23 ms at 50 M
 // pairs).  Stable: members arrive in index order and only strictly greater predecessors are shifted.
 constexpr u32 SMALL_GROUP = 16;
+constexpr u32 MID_GROUP = 1024;         // up to here a block ranks the group's members against each other (k_sort_mid_groups)
+constexpr u32 MID_LIST_CAP = 1u << 16;
+constexpr u64 MID_WORK_CAP = 1ull << 27;   // row comparisons; beyond it (or beyond the list) the groups go to the next round instead
+struct MidGroup { u32 first; u32 size; };
+struct MidCtl { u32 n; u32 pad; u64 work; };
 __global__ void k_sort_small_groups(const u64* __restrict__ rows, u32 stride, u32 w_next, u32 n_words, const u32* __restrict__ head,
                                     const u32* __restrict__ gid, const u32* __restrict__ gsize, u32* __restrict__ gdiff,
-                                    const u32* __restrict__ idx, const u32* __restrict__ pos_in, u64 n, u32* __restrict__ perm) {
+                                    const u32* __restrict__ idx, const u32* __restrict__ pos_in, u64 n, u32* __restrict__ perm,
+                                    MidGroup* __restrict__ mid, MidCtl* __restrict__ mc) {
     u64 step = (u64)gridDim.x * blockDim.x;
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
         if (!head[i]) continue;
         const u32 g = gid[i];
         const u32 m = gsize[g];
+        if (m > SMALL_GROUP && m <= MID_GROUP && gdiff[g]) {          // a block will take it
+            const u32 k = atomicAdd(&mc->n, 1u);
+            atomicAdd((unsigned long long*)&mc->work, (unsigned long long)m * m);
+            if (k < MID_LIST_CAP) { mid[k].first = (u32)i; mid[k].size = m; }
+            continue;
+        }
         if (m < 2u || m > SMALL_GROUP || !gdiff[g]) continue;
         u32 v[SMALL_GROUP];
         for (u32 k = 0; k < m; ++k) v[k] = idx[i + k];
@@ -295,6 +307,41 @@ __global__ void k_sort_small_groups(const u64* __restrict__ rows, u32 stride, u3
         }
         for (u32 k = 0; k < m; ++k) perm[pos_in ? pos_in[i + k] : (u32)(i + k)] = v[k];
         gdiff[g] = 0;                                       // resolved: not part of the next round
+    }
+}
+// Groups of 17 .. 1024 members (a popular read with a few variants): one block per group, every thread ranks one member
+// against all the others - rank = members that are smaller, or equal and earlier (stable) - and writes it to its place.
+// A handful of such groups used to drag the whole sort through one round per remaining word (15 for a pair of 150 bp
+// reads) with ~1 ms of fixed cost each.  All or nothing: when the input has very many of them (read names that share
+// their first 8 bytes in groups of a hundred) the next radix round is the cheaper tool and the kernel leaves them alone.
+__global__ void __launch_bounds__(256) k_sort_mid_groups(const u64* __restrict__ rows, u32 stride, u32 w_next, u32 n_words,
+                                                         const u32* __restrict__ gid, u32* __restrict__ gdiff, const u32* __restrict__ idx,
+                                                         const u32* __restrict__ pos_in, u32* __restrict__ perm,
+                                                         const MidGroup* __restrict__ mid, const MidCtl* __restrict__ mc) {
+    __shared__ u32 v[MID_GROUP];
+    if (mc->n > MID_LIST_CAP || mc->work > MID_WORK_CAP) return;      // many such groups: a radix round is cheaper
+    const u32 n_groups = mc->n;
+    for (u32 e = blockIdx.x; e < n_groups; e += gridDim.x) {
+        const u32 first = mid[e].first, m = mid[e].size;
+        for (u32 t = threadIdx.x; t < m; t += blockDim.x) v[t] = idx[first + t];
+        __syncthreads();
+        for (u32 t = threadIdx.x; t < m; t += blockDim.x) {
+            const u64* a = rows + (u64)v[t] * stride;
+            u32 rank = 0;
+            for (u32 j = 0; j < m; ++j) {
+                if (j == t) continue;
+                const u64* b = rows + (u64)v[j] * stride;
+                int c = 0;                                   // sign of (b - a) on the remaining words
+                for (u32 w = w_next; w < n_words; ++w) {
+                    const u64 x = b[w], y = a[w];
+                    if (x != y) { c = x < y ? -1 : 1; break; }
+                }
+                if (c < 0 || (c == 0 && j < t)) ++rank;
+            }
+            perm[pos_in ? pos_in[first + rank] : first + rank] = v[t];
+        }
+        if (threadIdx.x == 0) gdiff[gid[first]] = 0;         // resolved: not part of the next round
+        __syncthreads();
     }
 }
 __global__ void k_active_flags(const u32* __restrict__ gid, const u32* __restrict__ gsize, const u32* __restrict__ gdiff, u64 n, u32* __restrict__ flag) {

@@ -201,6 +201,46 @@ int fqd_boundary_fix(fqd_handle* h, const void* prev_state);
 int fqd_finish_emit(fqd_handle* h);
 
 /*
+ * Multi-GPU --fast --unordered (one process per GPU; the reference's counterpart is the single-threaded
+ * src/hash_dup_remover.hpp:150-192,257-347).  Both files are range-partitioned by ID TAG with shared splitters, so the
+ * ranges in rank order are the job's tag order and equal tags always meet in one range.  On an --unordered handle
+ *   fqd_partition_sample / _plan / _gather   work per file: samples come half from each file's tags, every file is
+ *                          partitioned by its own tags (counts[o] = records of both files, bytes[mate * n_ranges + o]);
+ *   the receiver appends what it got to a second --unordered handle, then runs the stages of fqd_finish one by one:
+ *   fqd_unordered_prepare  parse + sort both tag lists + partner of every record; returns the two list lengths.  An
+ *                          empty list is fine here.
+ *   -- all-gather of the lengths: every rank now knows where each range starts in the job's sorted lists L and R --
+ *   fqd_unordered_enter    (side 0) position in this range's R list when the walk first stands on element i of its L
+ *                          list, i.e. after element i - 1 has been consumed (side 1: the roles swapped).  The walk of
+ *                          src/hash_dup_remover.hpp:279-315 stops when either side has fetched its LAST record, so the
+ *                          range holding L[n-2] and the range holding R[m-2] answer this once each and the job's stop
+ *                          state (is, js) follows: (n-1, ja) if ja < m-1, else (ia, m-1).
+ *   fqd_unordered_join     limit_i / limit_j: the stop state clamped to this range's lists; final_i / final_j: its
+ *                          local position when the stop state's record lives here, else UINT64_MAX.  Emits the matched
+ *                          pairs before the limits, plus the stop state when both of its records are here and their
+ *                          tags are equal.  out[0] pairs emitted, out[1] unmatched records counted here, out[2] emission
+ *                          index of the first pair holding a byte outside {A,C,G,T,N} or UINT64_MAX, out[3] 1 when the
+ *                          job's last comparison happened here and matched.
+ *   -- all-gather of out[]: emission offsets, the job's abort point (first bad pair), unmatched total (+1 when the
+ *      last comparison matched nowhere) --
+ *   fqd_unordered_rows     rows (fqd_unordered_row_bytes() each: pair key + hash) of this range's pairs before `limit`,
+ *                          grouped by the GPU that owns their hash range, emission order kept; counts[k] rows for k
+ *   -- all-to-all of the rows: what arrives is in rank order = the job's emission order --
+ *   fqd_unordered_insert   on the owner: d_flags[i] = 1 when an earlier row holds the same pair key
+ *   -- all-to-all of the flags back --
+ *   fqd_unordered_apply    survivors + emission lists of this range; fqd_emit / fqd_emission work as after fqd_finish.
+ *                          report_bad: this range holds the pair the job aborts on (FQD_ERR_BAD_BASE in fqd_stats).
+ * The job's output is the concatenation of the ranges' outputs in rank order.
+ */
+int fqd_unordered_prepare(fqd_handle* h, uint64_t* n_left, uint64_t* n_right);
+int fqd_unordered_enter(fqd_handle* h, int side, uint64_t i, uint64_t* pos);
+int fqd_unordered_join(fqd_handle* h, uint64_t limit_i, uint64_t limit_j, uint64_t final_i, uint64_t final_j, uint64_t out[4]);
+size_t fqd_unordered_row_bytes(fqd_handle* h);
+int fqd_unordered_rows(fqd_handle* h, uint64_t limit, uint32_t n_shards, void* d_send, uint64_t* counts);
+int fqd_unordered_insert(fqd_handle* h, const void* d_recv, uint64_t n_recv, uint32_t n_shards, void* d_flags);
+int fqd_unordered_apply(fqd_handle* h, const void* d_flags_back, uint64_t limit, int report_bad);
+
+/*
  * Multi-GPU --fast mode (one handle per GPU / process).  The all-to-all exchanges themselves are
  * done by the caller (torch.distributed / NCCL) on the stream given to fqd_set_stream, between these calls:
  *   fqd_shard_pack     split + pack one chunk of THIS rank's input and group the packed keys by owning shard;

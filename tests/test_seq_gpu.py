@@ -79,6 +79,28 @@ def test_long_shared_prefixes_need_many_sort_rounds(fqd, oracle):
         _check(fqd, oracle, mode, synth.to_fastq(seqs), None, fqd.FORMAT_FASTQ, dist=dist, max_seq_len=120)
 
 
+@pytest.mark.parametrize("paired", [False, True])
+def test_groups_of_every_size_behind_one_key_word(fqd, oracle, paired):
+    """Groups of 2 .. 3000 reads share the first key word (21 bases) and differ - or not - further on: the sort hands
+    groups up to 16 to one thread, up to 1024 to one block (rank among the members, ties by input order) and keeps only
+    the larger ones for the next round; the order must stay the stable order of the reference's sort."""
+    rng = np.random.default_rng(38)
+    seqs = []
+    for size in (2, 3, 15, 16, 17, 18, 40, 100, 255, 256, 257, 700, 1023, 1024, 1025, 3000):
+        prefix = bytes(rng.choice(list(b"ACGT"), size=30).astype(np.uint8))
+        variants = [bytes(rng.choice(list(b"ACGT"), size=int(rng.integers(0, 60))).astype(np.uint8)) for _ in range(max(2, size // 3))]
+        seqs += [prefix + variants[int(k)] for k in rng.integers(0, len(variants), size=size)]
+    seqs += synth.make_reads(3000, seed=39, read_len=90, dup_frac=0.2)
+    order = rng.permutation(len(seqs))
+    seqs = [seqs[int(k)] for k in order]
+    b1, b2 = synth.to_fastq(seqs, mate=1), None
+    if paired:
+        mates = [seqs[int(k)][:int(rng.integers(20, 90))] for k in rng.integers(0, len(seqs), size=len(seqs))]
+        b2 = synth.to_fastq(mates, mate=2)
+    for mode, dist in (("tight", 2), ("loose", 2), ("tail-hamming", 2)):
+        _check(fqd, oracle, mode, b1, b2, fqd.FORMAT_FASTQ, dist=dist, max_seq_len=90, seg_bytes=1 << 20)
+
+
 def test_150bp_with_exact_duplicates(fqd, oracle):
     seqs = synth.make_reads(20000, seed=35, read_len=150, dup_frac=0.3)
     st = _check(fqd, oracle, "tight", synth.to_fastq(seqs), None, fqd.FORMAT_FASTQ, max_seq_len=150, seg_bytes=1 << 20)
