@@ -172,7 +172,27 @@ def run(args, fqd, dist, rank, local_rank, world, n_per_rank):
                                         "frac": ach / (peak * world), "alg_bytes_per_pair": 1068, "alg_bytes_source": "SURVEY.md 8d"}
                 line["leg_wall_s"] = round(time.perf_counter() - t0, 1)
                 modes[mode] = line
-        modes["unordered"] = {"value": None, "unit": "pairs/s", "note": "--fast --unordered runs on one GPU (bench.py --gpus 1); across GPUs it is not built"}
+        t0 = time.perf_counter()
+        try:
+            # the pairs of the fast_pe leg (same generator, seed and count) with file 2 in another order: same duplicates
+            line = bs.run_unordered_multi(fqd, lib, n_pairs, msteps, seed=2, emit=False)
+        except Exception as ex:
+            line = {"value": None, "unit": "pairs/s", "error": repr(ex)}
+        if rank == 0:
+            if line.get("value"):
+                ach = line["pairs_total"] * 1156 / (line["ms_per_step"] / 1e3) / 1e9
+                line["roofline"] = {"bound": "hbm", "kernel": "whole path", "achieved": ach, "peak": peak * world, "peak_kind": peak_kind, "unit": "GB/s",
+                                    "frac": ach / (peak * world), "alg_bytes_per_pair": 1156, "alg_bytes_source": "bench_modes.py (SURVEY.md 8d + tag rows)"}
+                uv = {"pairs_total": line["pairs_total"], "expected_pairs": world * n_pairs, "unmatched": line["unmatched"],
+                      "duplicates_removed": line["duplicates_removed"], "fast_pe_duplicates_same_pairs": pe["dups"],
+                      "how": "same pairs as the fast_pe leg (whose duplicate count is checked against one single-GPU engine); every pair must be "
+                             "matched, none skipped, and the same number removed"}
+                uv["equal"] = (line["err"] == 0 and uv["pairs_total"] == uv["expected_pairs"] and uv["unmatched"] == 0
+                               and uv["duplicates_removed"] == pe["dups"])
+                line["verify"] = uv
+                assert uv["equal"], uv
+            line["leg_wall_s"] = round(time.perf_counter() - t0, 1)
+            modes["unordered"] = line
 
     if rank == 0:
         prof = r["prof"]

@@ -177,6 +177,77 @@ def run_mode_multi(fqd, lib, mode, n_pairs_per_rank, steps, emit=True):
     return line
 
 
+def run_unordered_multi(fqd, lib, n_pairs_per_rank, steps, seed=SEED, emit=True):
+    """N > 1 (under torchrun): --fast --unordered over tag ranges (fastq-dupaway_b200/sharded_unordered.py), weak scaling.
+    ONE global job of world * n pairs, dealt to the ranks chunk by chunk round-robin: file 1 in input order, file 2 with
+    its chunks in reverse order, so every rank holds records of every tag range in both files (a true all-to-all) and
+    no rank holds the mates of its own file-1 records."""
+    import torch
+    import torch.distributed as dist
+    rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
+    sh = importlib.import_module("fastq-dupaway_b200.sharded_unordered")
+    dev = local
+    n = n_pairs_per_rank
+    chunk_pairs = 1_250_000
+    n_chunks = (n + chunk_pairs - 1) // chunk_pairs
+    assert n % chunk_pairs == 0, "pairs per GPU must be a multiple of 1.25 M"
+    total_chunks = n_chunks * world
+    raw = [fqd.DeviceBuffer(n * REC + 65536, dev) for _ in range(2)]
+    for c in range(n_chunks):
+        g1 = c * world + rank                       # global chunk of file 1
+        g2 = total_chunks - 1 - g1                  # file 2: the chunks arrive in reverse order
+        for m, g in ((0, g1), (1, g2)):
+            assert lib.fqd_synth_fastq(dev, raw[m].ptr + c * chunk_pairs * REC, g * chunk_pairs, chunk_pairs, READ_LEN, m + 1, seed,
+                                       DUP_PERMILLE, N_PERMILLE, 0) == 0
+    ops = sh.GpuTagRangeOps(fqd, fqd.FORMAT_FASTQ, READ_LEN, n + 1024, int(n * 1.3) + (1 << 20), dev, seg_bytes=1 << 30, max_tag_len=16)
+    times = []
+    res = None
+    for it in range(steps + 1):
+        if it:
+            ops.reset()
+        torch.cuda.synchronize(dev)
+        dist.barrier()
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for m in range(2):
+            ops.adopt(m, raw[m].ptr, n * REC)       # parse + pack + tags of this rank's slices, in place
+        res = sh.dedup_tag_ranges(ops, dist, rank, world, n_samples=8192)
+        e1.record()
+        torch.cuda.synchronize(dev)
+        ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=f"cuda:{dev}")
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        if it:
+            times.append(float(ms.item()))
+    own = torch.tensor([res.local_pairs, res.local_kept], dtype=torch.int64, device=f"cuda:{dev}")
+    allown = [torch.zeros_like(own) for _ in range(world)]
+    dist.all_gather(allown, own)
+    line = {}
+    if rank == 0:
+        ms = sum(times) / len(times)
+        total = world * n
+        owned = [int(t[0].item()) for t in allown]
+        line = {"metric": "dedup read pairs/sec", "mode": "unordered", "value": total / (ms / 1e3), "unit": "pairs/s",
+                "reads_per_s": 2 * total / (ms / 1e3), "n_gpus": world, "steps": steps, "ms_per_step": ms, "scaling": "weak",
+                "config": {"workload": f"synthetic {total} x 2x150bp paired-end FASTQ, 30% duplicates, --fast --unordered "
+                                       "(file 2 chunk-reversed; chunks of 1.25 M pairs dealt round-robin to the ranks)",
+                           "pairs_per_gpu": n, "parallelism": f"tag-range x{world} (join) + hash-range x{world} (pair set)", "record_bytes": REC,
+                           "seed": seed,
+                           "timed": "adopt (parse + pack + tags of the slices in place) + sample + splitters + plan + gather + all-to-all of the raw "
+                                    "records of both files + parse + tag sorts + join + stop state + all-to-all of the pair keys + pair set + "
+                                    "flags back + emission lists (slices resident in HBM)"},
+                "err": res.err, "pairs_total": res.total, "duplicates_removed": res.dups, "unmatched": res.unmatched,
+                "pairs_out": res.total - res.dups, "pairs_per_rank": owned, "imbalance": max(owned) / max(1.0, sum(owned) / world),
+                "input_GBps": total * 2 * REC / (ms / 1e3) / 1e9,
+                "alltoall_bytes_per_gpu": n * 2 * REC + n * ops.row_bytes, "exchange": "NCCL all_to_all_single"}
+        if emit:
+            print(json.dumps(line), flush=True)
+    ops.close()
+    for s_ in raw:
+        s_.free()
+    return line
+
+
 def cpu_reference(mode, n_pairs):
     """The unmodified reference (oracle/_ref) on the same synthetic stream, one core, tmpfs."""
     sys.path.insert(0, str(ROOT / "oracle"))

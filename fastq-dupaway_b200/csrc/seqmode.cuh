@@ -1185,7 +1185,7 @@ static int sort_rows(SeqState* s, const u64* rows, u32 stride, u32 w_begin, u32 
     if ((rc = seq_dalloc(s, &head, n, err)) || (rc = seq_dalloc(s, &excl, n, err)) || (rc = seq_dalloc(s, &gid, n, err)) ||
         (rc = seq_dalloc(s, &gsize, n, err)) || (rc = seq_dalloc(s, &gdiff, n, err)) || (rc = seq_dalloc(s, &flag, n, err)) ||
         (rc = seq_dalloc(s, &posA, n, err)) || (rc = seq_dalloc(s, &posB, n, err))) return rc;
-    MidGroup* mid = nullptr; MidCtl* n_mid = nullptr;
+    MidUnit* mid = nullptr; MidCtl* n_mid = nullptr;
     if ((rc = seq_dalloc(s, &mid, MID_LIST_CAP, err)) || (rc = seq_dalloc(s, &n_mid, 1, err))) return rc;
     const bool fine = getenv("FQD_TRACE_SORT") != nullptr;
     const u32 hi_bit = (word_bits + 7) / 8 * 8;
@@ -1217,10 +1217,13 @@ static int sort_rows(SeqState* s, const u64* rows, u32 stride, u32 w_begin, u32 
         if (fine) tr.mark(s->stream, "    round: mark unresolved");
         if (!getenv("FQD_SORT_NO_SMALL_GROUPS")) {
             SEQ_TRY(cudaMemsetAsync(n_mid, 0, sizeof(MidCtl), s->stream));
-            k_sort_small_groups<<<seq_grid(s, n_act), 256, 0, s->stream>>>(rows + w_begin, stride, w + 1, n_words, head, gid, gsize, gdiff, sc.aA, pos_in, n_act, perm, mid, n_mid);
+            // `flag` is free until k_active_flags: it holds the list of small groups (at most n_act / 2 of them)
+            k_collect_groups<<<seq_grid(s, n_act), 256, 0, s->stream>>>(head, gid, gsize, gdiff, n_act, flag, mid, n_mid);
+            if (fine) tr.mark(s->stream, "    round: collect groups");
+            k_sort_small_groups<<<seq_grid(s, n_act / 2 + 1), 256, 0, s->stream>>>(rows + w_begin, stride, w + 1, n_words, gid, gsize, gdiff, sc.aA, pos_in, perm, flag, n_mid);
             if (fine) tr.mark(s->stream, "    round: small groups");
-            k_sort_mid_groups<<<s->sm * 4, 256, 0, s->stream>>>(rows + w_begin, stride, w + 1, n_words, gid, gdiff, sc.aA, pos_in, perm, mid, n_mid);
-            s->launches += 2;
+            k_sort_mid_groups<<<s->sm * 8, 256, 0, s->stream>>>(rows + w_begin, stride, w + 1, n_words, gid, gdiff, sc.aA, pos_in, perm, mid, n_mid);
+            s->launches += 3;
         }
         if (fine) tr.mark(s->stream, "    round: mid groups");
         k_active_flags<<<seq_grid(s, n_act), 256, 0, s->stream>>>(gid, gsize, gdiff, n_act, flag);

@@ -265,27 +265,53 @@ __global__ void k_mark_unresolved(const u64* __restrict__ rows, u32 stride, u32 
 // differing word is reached (a difference in the last 10 bases of a 150 bp read took 7 rounds: 19 - 23 ms at 50 M
 // pairs).  Stable: members arrive in index order and only strictly greater predecessors are shifted.
 constexpr u32 SMALL_GROUP = 16;
-constexpr u32 MID_GROUP = 1024;         // up to here a block ranks the group's members against each other (k_sort_mid_groups)
+constexpr u32 MID_GROUP = 1024;         // up to here blocks rank the group's members against each other (k_sort_mid_groups)
+constexpr u32 MID_CHUNK = 64;           // members one block ranks at a time: a large group is spread over several blocks
 constexpr u32 MID_LIST_CAP = 1u << 16;
 constexpr u64 MID_WORK_CAP = 1ull << 27;   // row comparisons; beyond it (or beyond the list) the groups go to the next round instead
-struct MidGroup { u32 first; u32 size; };
-struct MidCtl { u32 n; u32 pad; u64 work; };
-__global__ void k_sort_small_groups(const u64* __restrict__ rows, u32 stride, u32 w_next, u32 n_words, const u32* __restrict__ head,
-                                    const u32* __restrict__ gid, const u32* __restrict__ gsize, u32* __restrict__ gdiff,
-                                    const u32* __restrict__ idx, const u32* __restrict__ pos_in, u64 n, u32* __restrict__ perm,
-                                    MidGroup* __restrict__ mid, MidCtl* __restrict__ mc) {
-    u64 step = (u64)gridDim.x * blockDim.x;
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += step) {
-        if (!head[i]) continue;
+struct MidUnit { u32 first; u32 size; u32 chunk; };
+struct MidCtl { u32 n_units; u32 n_small; u64 work; };
+// The unresolved groups of this round, by size: heads of the small ones go to a dense list (so that the threads sorting
+// them sit side by side - one group per thread on scattered lanes was bound by the latency of a single lane per warp:
+// 2.5 ms for 1.5 M groups), the middle-sized ones become (group, chunk of 64 members) units.
+__global__ void __launch_bounds__(256) k_collect_groups(const u32* __restrict__ head, const u32* __restrict__ gid, const u32* __restrict__ gsize,
+                                                        const u32* __restrict__ gdiff, u64 n, u32* __restrict__ small_list,
+                                                        MidUnit* __restrict__ units, MidCtl* __restrict__ mc) {
+    const u64 step = (u64)gridDim.x * blockDim.x;
+    const u32 lane = threadIdx.x & 31u;
+    for (u64 b = (u64)blockIdx.x * blockDim.x; b < n; b += step) {
+        const u64 i = b + threadIdx.x;
+        u32 m = 0;
+        if (i < n && head[i]) {
+            const u32 g = gid[i];
+            if (gdiff[g]) m = gsize[g];
+        }
+        const bool small = m >= 2u && m <= SMALL_GROUP;
+        const u32 ballot = __ballot_sync(0xFFFFFFFFu, small);
+        if (ballot) {
+            u32 base = 0;
+            if (lane == 0) base = atomicAdd(&mc->n_small, (u32)__popc(ballot));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (small) small_list[base + __popc(ballot & ((1u << lane) - 1u))] = (u32)i;
+        }
+        if (m > SMALL_GROUP && m <= MID_GROUP) {
+            const u32 chunks = (m + MID_CHUNK - 1) / MID_CHUNK;
+            const u32 k = atomicAdd(&mc->n_units, chunks);
+            atomicAdd((unsigned long long*)&mc->work, (unsigned long long)m * m);
+            for (u32 c = 0; c < chunks && k + c < MID_LIST_CAP; ++c) { units[k + c].first = (u32)i; units[k + c].size = m; units[k + c].chunk = c; }
+        }
+    }
+}
+__global__ void __launch_bounds__(256) k_sort_small_groups(const u64* __restrict__ rows, u32 stride, u32 w_next, u32 n_words,
+                                                           const u32* __restrict__ gid, const u32* __restrict__ gsize, u32* __restrict__ gdiff,
+                                                           const u32* __restrict__ idx, const u32* __restrict__ pos_in, u32* __restrict__ perm,
+                                                           const u32* __restrict__ small_list, const MidCtl* __restrict__ mc) {
+    const u32 n_list = mc->n_small;
+    const u32 step = gridDim.x * blockDim.x;
+    for (u32 e = blockIdx.x * blockDim.x + threadIdx.x; e < n_list; e += step) {
+        const u32 i = small_list[e];
         const u32 g = gid[i];
         const u32 m = gsize[g];
-        if (m > SMALL_GROUP && m <= MID_GROUP && gdiff[g]) {          // a block will take it
-            const u32 k = atomicAdd(&mc->n, 1u);
-            atomicAdd((unsigned long long*)&mc->work, (unsigned long long)m * m);
-            if (k < MID_LIST_CAP) { mid[k].first = (u32)i; mid[k].size = m; }
-            continue;
-        }
-        if (m < 2u || m > SMALL_GROUP || !gdiff[g]) continue;
         u32 v[SMALL_GROUP];
         for (u32 k = 0; k < m; ++k) v[k] = idx[i + k];
         for (u32 k = 1; k < m; ++k) {
@@ -305,30 +331,33 @@ __global__ void k_sort_small_groups(const u64* __restrict__ rows, u32 stride, u3
             }
             v[j] = cur;
         }
-        for (u32 k = 0; k < m; ++k) perm[pos_in ? pos_in[i + k] : (u32)(i + k)] = v[k];
+        for (u32 k = 0; k < m; ++k) perm[pos_in ? pos_in[i + k] : i + k] = v[k];
         gdiff[g] = 0;                                       // resolved: not part of the next round
     }
 }
-// Groups of 17 .. 1024 members (a popular read with a few variants): one block per group, every thread ranks one member
-// against all the others - rank = members that are smaller, or equal and earlier (stable) - and writes it to its place.
+// Groups of 17 .. 1024 members (a popular read with a few variants): every member's rank = members that are smaller, or
+// equal and earlier (stable); a block takes 64 members, four threads each (a quarter of the comparisons per thread).
 // A handful of such groups used to drag the whole sort through one round per remaining word (15 for a pair of 150 bp
 // reads) with ~1 ms of fixed cost each.  All or nothing: when the input has very many of them (read names that share
 // their first 8 bytes in groups of a hundred) the next radix round is the cheaper tool and the kernel leaves them alone.
 __global__ void __launch_bounds__(256) k_sort_mid_groups(const u64* __restrict__ rows, u32 stride, u32 w_next, u32 n_words,
                                                          const u32* __restrict__ gid, u32* __restrict__ gdiff, const u32* __restrict__ idx,
                                                          const u32* __restrict__ pos_in, u32* __restrict__ perm,
-                                                         const MidGroup* __restrict__ mid, const MidCtl* __restrict__ mc) {
+                                                         const MidUnit* __restrict__ units, const MidCtl* __restrict__ mc) {
     __shared__ u32 v[MID_GROUP];
-    if (mc->n > MID_LIST_CAP || mc->work > MID_WORK_CAP) return;      // many such groups: a radix round is cheaper
-    const u32 n_groups = mc->n;
-    for (u32 e = blockIdx.x; e < n_groups; e += gridDim.x) {
-        const u32 first = mid[e].first, m = mid[e].size;
+    if (mc->n_units > MID_LIST_CAP || mc->work > MID_WORK_CAP) return;      // many such groups: a radix round is cheaper
+    const u32 n_units = mc->n_units;
+    const u32 part = threadIdx.x & 3u;
+    for (u32 e = blockIdx.x; e < n_units; e += gridDim.x) {
+        const u32 first = units[e].first, m = units[e].size;
+        __syncthreads();
         for (u32 t = threadIdx.x; t < m; t += blockDim.x) v[t] = idx[first + t];
         __syncthreads();
-        for (u32 t = threadIdx.x; t < m; t += blockDim.x) {
+        const u32 t = units[e].chunk * MID_CHUNK + (threadIdx.x >> 2);
+        u32 rank = 0;
+        if (t < m) {
             const u64* a = rows + (u64)v[t] * stride;
-            u32 rank = 0;
-            for (u32 j = 0; j < m; ++j) {
+            for (u32 j = part; j < m; j += 4u) {
                 if (j == t) continue;
                 const u64* b = rows + (u64)v[j] * stride;
                 int c = 0;                                   // sign of (b - a) on the remaining words
@@ -338,10 +367,11 @@ __global__ void __launch_bounds__(256) k_sort_mid_groups(const u64* __restrict__
                 }
                 if (c < 0 || (c == 0 && j < t)) ++rank;
             }
-            perm[pos_in ? pos_in[first + rank] : first + rank] = v[t];
         }
-        if (threadIdx.x == 0) gdiff[gid[first]] = 0;         // resolved: not part of the next round
-        __syncthreads();
+        rank += __shfl_xor_sync(0xFFFFFFFFu, rank, 1);
+        rank += __shfl_xor_sync(0xFFFFFFFFu, rank, 2);
+        if (t < m && part == 0) perm[pos_in ? pos_in[first + rank] : first + rank] = v[t];
+        if (threadIdx.x == 0 && units[e].chunk == 0) gdiff[gid[first]] = 0;         // resolved: not part of the next round
     }
 }
 __global__ void k_active_flags(const u32* __restrict__ gid, const u32* __restrict__ gsize, const u32* __restrict__ gdiff, u64 n, u32* __restrict__ flag) {

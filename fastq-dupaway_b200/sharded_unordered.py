@@ -60,6 +60,10 @@ class GpuTagRangeOps:
     def append(self, mate, dptr, nbytes):
         self.origin.append_device(mate, dptr, nbytes)
 
+    def adopt(self, mate, dptr, nbytes):
+        """this rank's whole slice of one file, device-resident and 16-byte aligned: parsed in place, not copied"""
+        self.origin.adopt_device(mate, dptr, nbytes)
+
     def sample(self, n_samples):
         smp, n = self.origin.partition_sample(n_samples)
         return smp, n, int(self.origin.stats().err)
@@ -75,10 +79,11 @@ class GpuTagRangeOps:
 
     # -- range side
     def receive(self, mate, recv):
+        """what the all-to-all delivered is parsed in place (the tensor stays alive until reset)"""
         self.torch.cuda.synchronize(self.dev)
         if recv.numel():
-            self.range.append_device(mate, recv.data_ptr(), int(recv.numel()))
-            self.torch.cuda.synchronize(self.dev)
+            self._keep.append(recv)
+            self.range.adopt_device(mate, recv.data_ptr(), int(recv.numel()))
 
     def prepare(self):
         nl, nr = self.range.unordered_prepare()
@@ -117,9 +122,10 @@ class GpuTagRangeOps:
         return self.origin.device_time_ms()[0] + self.range.device_time_ms()[0]
 
     def reset(self):
-        self._keep.clear()
         self.origin.reset()
         self.range.reset()
+        self.torch.cuda.synchronize(self.dev)
+        self._keep.clear()
 
     def close(self):
         self.origin.close()
