@@ -275,3 +275,10 @@ def test_one_file_empty(tmp_path, oracle):
     cases = [(2, [(b">X.1\nACGT\n", b""), (b"", b""), (b">X.2\nACGT\n", b"")], 4)]
     got = run_cases(tmp_path, cases, 3)
     assert got[0][0].err == 3
+
+
+def test_one_rank_is_the_whole_job(tmp_path, oracle):
+    cases, wholes = tiny_cases(60, seed=13, world=1)
+    got = run_cases(tmp_path, cases, 1)
+    for whole, g in zip(wholes, got):
+        check_against_oracle(oracle, oracle.FASTA, whole, g)

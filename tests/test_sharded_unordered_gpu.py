@@ -87,3 +87,33 @@ def test_two_ranks_tags_that_differ_behind_the_splitter_words(tmp_path, oracle):
     cases = [(2, [(sl[0][r], sl[1][r]) for r in range(2)], 32)]
     got = proto.run_cases(tmp_path, cases, 2, worker=_worker, port_base=33900)
     proto.check_against_oracle(oracle, oracle.FASTA, (b"".join(recs[0]), b"".join(recs[1])), got[0])
+
+
+def test_one_rank_is_the_whole_job(tmp_path, oracle):
+    cases, wholes = proto.tiny_cases(60, seed=13, world=1)
+    got = proto.run_cases(tmp_path, cases, 1, worker=_worker, port_base=33900)
+    for whole, g in zip(wholes, got):
+        proto.check_against_oracle(oracle, oracle.FASTA, whole, g)
+
+
+def test_stage_calls_out_of_order_are_refused(fqd):
+    eng = fqd.Engine("fast", fqd.FORMAT_FASTA, True, True, 2, 64, 1000, 1 << 18, 0, 0)
+    with pytest.raises(fqd.FqdError):
+        eng.unordered_join(0, 0, 0, 0)              # before fqd_unordered_prepare
+    with pytest.raises(fqd.FqdError):
+        eng.unordered_enter(0, 0)
+    eng.append(0, b">X.1\nACGT\n>X.2\nACGT\n")
+    eng.append(1, b">X.2\nACGT\n")
+    assert eng.unordered_prepare() == (2, 1)
+    with pytest.raises(fqd.FqdError):
+        eng.unordered_prepare()                     # twice
+    with pytest.raises(fqd.FqdError):
+        eng.unordered_enter(0, 3)                   # outside the list
+    assert eng.unordered_enter(0, 2) == 1 and eng.unordered_enter(1, 1) == 2
+    with pytest.raises(fqd.FqdError):
+        eng.unordered_apply(0, 0, False)            # before fqd_unordered_join
+    eng.close()
+    plain = fqd.Engine("tight", fqd.FORMAT_FASTA, False, False, 2, 64, 1000, 1 << 18, 0, 0)
+    with pytest.raises(fqd.FqdError):
+        plain.unordered_prepare()
+    plain.close()
