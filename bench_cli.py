@@ -102,14 +102,28 @@ def timed(cmd, cwd, trace=False):
         return dt, res.stdout.strip()
     # [host-trace] <ms> ms  <label>: CUDA start-up (context, pinned staging, engine) vs the streaming part
     marks = {}
+    extra = {}
     for line in res.stderr.splitlines():
-        if line.startswith("[host-trace]"):
+        if line.startswith("[host-trace] device memory high-water mark"):
+            extra["device_GiB_high_water"] = float(line.split("mark", 1)[1].split("GiB", 1)[0])
+        elif line.startswith("[host-trace]"):
             ms, label = line[len("[host-trace]"):].split("ms", 1)
-            marks[label.strip()] = float(ms)
+            label = label.strip()
+            marks[label] = float(ms)
+            for short in ("engine created", "outputs closed", "input on the device", "sorted / joined / scanned"):      # "... (raw input not kept on the device)"
+                if label.startswith(short):
+                    marks[short] = float(ms)
+            if "raw input not kept" in label:
+                extra["raw_input"] = "discarded after the parse (host gathers the output)"
     phases = {}
     if "engine created" in marks and "outputs closed" in marks:
         phases = {"startup_s": round(marks["engine created"] / 1e3, 3),
                   "stream_s": round((marks["outputs closed"] - marks["engine created"]) / 1e3, 3)}
+        if "input on the device" in marks and "sorted / joined / scanned" in marks:
+            phases["ingest_s"] = round((marks["input on the device"] - marks["engine created"]) / 1e3, 3)
+            phases["sort_scan_s"] = round((marks["sorted / joined / scanned"] - marks["input on the device"]) / 1e3, 3)
+            phases["output_s"] = round((marks["outputs closed"] - marks["sorted / joined / scanned"]) / 1e3, 3)
+    phases.update(extra)
     return dt, res.stdout.strip(), phases
 
 
@@ -121,6 +135,7 @@ def main():
     ap.add_argument("--mode", default="fast", choices=["fast", "tight", "loose", "tail-hamming"])
     ap.add_argument("--paired", action="store_true", help="2 x 150 bp: -i/-u inputs, -o/-p outputs")
     ap.add_argument("--repeats", type=int, default=2)
+    ap.add_argument("--no-reference", action="store_true", help="skip the common-prefix runs of both binaries")
     args = ap.parse_args()
     oracle = importlib.import_module("oracle")
     tmp = Path(tempfile.mkdtemp(prefix="fqd_cli_", dir="/dev/shm" if Path("/dev/shm").is_dir() else None))
@@ -161,6 +176,8 @@ def main():
                     best, phases = dt, ph
             if phases.get("stream_s"):
                 phases[f"stream_{unit}_per_s"] = round(args.reads / phases["stream_s"])
+            if os.environ.get("FQD_WHOLE_INPUT"):
+                phases["FQD_WHOLE_INPUT"] = os.environ["FQD_WHOLE_INPUT"]
             print(json.dumps({"impl": "ours", **phases, "binary": "fastq-dupaway_b200/host/fastq-dupaway", "mode": args.mode,
                               "paired": args.paired, "input": fmt, unit: args.reads,
                               "input_bytes": sum(f.stat().st_size for f in inputs[fmt]), "seconds": round(best, 3),
@@ -170,6 +187,8 @@ def main():
         # common prefix: both binaries, outputs compared.  Sequence-based modes: the reference's choice inside a group of
         # equal records depends on its unstable sort, so the comparison is with the stable-sort build of the
         # same sources and the timing with the plain build.
+        if args.no_reference:
+            return
         n = min(args.ref_reads, args.reads)
         pre = [tmp / f"pre_{m}.fq" for m in mates]
         for src, dst in zip(full, pre):

@@ -137,6 +137,11 @@ def load_library():
     lib.fqd_emission.argtypes = [vp, C.POINTER(Emission)]
     lib.fqd_emit.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(C.c_int)]
     lib.fqd_emit_clusters.argtypes = [vp, C.c_int, vp, sz, C.POINTER(sz), C.POINTER(C.c_int)]
+    lib.fqd_discard_input.argtypes = [vp, C.c_int]
+    lib.fqd_emission_count.argtypes = [vp, C.POINTER(u64), C.POINTER(u64)]
+    lib.fqd_emission_read.argtypes = [vp, C.c_int, u64, u64, vp, vp]
+    lib.fqd_cluster_read.argtypes = [vp, C.c_int, u64, u64, vp, vp, vp]
+    lib.fqd_device_memory.argtypes = [C.c_int, C.POINTER(sz), C.POINTER(sz)]
     lib.fqd_stats.argtypes = [vp, C.POINTER(Stats)]
     lib.fqd_set_stream.argtypes = [vp, vp]
     lib.fqd_shard_row_bytes.argtypes = [vp]
@@ -397,6 +402,34 @@ class Engine:
                 break
         return b"".join(out)
 
+    # -- whole-input modes without the raw input in device memory (inputs larger than HBM)
+    def discard_input(self, on: bool = True):
+        """Free every input segment as soon as it is parsed; the caller fetches the written records itself."""
+        self._check(self.lib.fqd_discard_input(self.h, int(on)))
+
+    def emission_count(self):
+        """(records written, sorted positions available to cluster_read)."""
+        a, b = C.c_uint64(0), C.c_uint64(0)
+        self._check(self.lib.fqd_emission_count(self.h, C.byref(a), C.byref(b)))
+        return int(a.value), int(b.value)
+
+    def emission_read(self, mate: int, first: int, count: int):
+        """(offsets uint64[count], lengths uint32[count]) of the written records [first, first + count) of `mate`."""
+        import numpy as np
+        off = np.empty(count, dtype=np.uint64)
+        ln = np.empty(count, dtype=np.uint32)
+        self._check(self.lib.fqd_emission_read(self.h, mate, first, count, off.ctypes.data, ln.ctypes.data))
+        return off, ln
+
+    def cluster_read(self, mate: int, first: int, count: int):
+        """Sorted positions [first, first + count): (offsets, lengths, head flags) of the records standing there."""
+        import numpy as np
+        off = np.empty(count, dtype=np.uint64)
+        ln = np.empty(count, dtype=np.uint32)
+        head = np.empty(count, dtype=np.uint8)
+        self._check(self.lib.fqd_cluster_read(self.h, mate, first, count, off.ctypes.data, ln.ctypes.data, head.ctypes.data))
+        return off, ln, head
+
     def stats(self) -> Stats:
         st = Stats()
         self._check(self.lib.fqd_stats(self.h, C.byref(st)))
@@ -529,13 +562,17 @@ def dedup_fast(b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, chunk_bytes
 
 def dedup_whole(mode: str, b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ, dist=2, unordered=False,
                 max_seq_len=150, append_bytes=1 << 22, seg_bytes=1 << 24, max_records=None, device=0, max_tag_len=0,
-                device_gather=True, emit_cap=1 << 16, byte_keys=0):
-    """Sequence-based modes and --fast --unordered: whole input on the device, emission order out."""
+                device_gather=True, emit_cap=1 << 16, byte_keys=0, discard=False, window=997):
+    """Sequence-based modes and --fast --unordered: whole input on the device, emission order out.
+    discard=True: the raw input does not stay on the device (fqd_discard_input, inputs larger than HBM); the written
+    records are fetched here from the emission list read window by window (fqd_emission_read)."""
     paired = b2 is not None
     if max_records is None:
         max_records = max(1024, max(b1.count(b"\n"), b2.count(b"\n") if paired else 0) // 2 + 16)
     eng = Engine(mode, fmt, paired, unordered, dist, max_seq_len, max_records, seg_bytes, 0, device, max_tag_len, byte_keys)
     try:
+        if discard:
+            eng.discard_input(True)
         for m, b in enumerate([b1, b2] if paired else [b1]):
             for o in range(0, len(b), append_bytes):
                 eng.append(m, b[o: o + append_bytes])
@@ -551,6 +588,15 @@ def dedup_whole(mode: str, b1: bytes, b2: bytes | None = None, fmt=FORMAT_FASTQ,
             ln = _np(em.len[m], n, np.int64)
             mv = memoryview(b)
             outs.append(b"".join(mv[int(o): int(o + l)] for o, l in zip(off, ln)))
+            if discard:            # the windowed reader must hand out the same list
+                if eng.emission_count()[0] != n:
+                    raise AssertionError("fqd_emission_count differs from fqd_emission")
+                for k in range(0, n, window):
+                    c = min(window, n - k)
+                    o2, l2 = eng.emission_read(m, k, c)
+                    if not (np.array_equal(o2.astype(np.int64), off[k: k + c]) and np.array_equal(l2.astype(np.int64), ln[k: k + c])):
+                        raise AssertionError("fqd_emission_read differs from fqd_emission")
+                continue
             if device_gather:      # the device-side gather must produce the same bytes
                 got = eng.emit_all(m, emit_cap)
                 if got != outs[-1]:

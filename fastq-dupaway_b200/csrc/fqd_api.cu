@@ -1516,6 +1516,38 @@ extern "C" int fqd_emit_clusters(fqd_handle* h, int mate, void* dst, size_t cap,
     cudaSetDevice(h->cfg.device);
     return seq_emit_clusters(h->seq, mate, dst, cap, n_bytes, done, &h->err);
 }
+extern "C" int fqd_discard_input(fqd_handle* h, int on) {
+    if (!h || !h->seq) return fail(h, FQD_ERR_INVALID, "fqd_discard_input is for sequence / unordered modes");
+    for (u32 m = 0; m < h->seq->mates; ++m)
+        if (!h->seq->mate[m].segs.empty()) return fail(h, FQD_ERR_INVALID, "fqd_discard_input after the first fqd_append");
+    h->seq->discard = on != 0;
+    return FQD_OK;
+}
+extern "C" int fqd_emission_count(fqd_handle* h, uint64_t* n_written, uint64_t* n_sorted) {
+    if (!h || !h->seq) return fail(h, FQD_ERR_INVALID, "fqd_emission_count is for sequence / unordered modes");
+    if (!h->seq->finished) return fail(h, FQD_ERR_INVALID, "fqd_emission_count before fqd_finish");
+    const SeqState* s = h->seq;
+    if (n_written) *n_written = s->n_out;
+    if (n_sorted) *n_sorted = (s->cfg.unordered || s->cfg.mode == FQD_MODE_FAST || s->stats.err || !s->d_perm || !s->d_keep) ? 0 : s->n;
+    return FQD_OK;
+}
+extern "C" int fqd_emission_read(fqd_handle* h, int mate, uint64_t first, uint64_t count, uint64_t* off, uint32_t* len) {
+    if (!h || !h->seq || (count && (!off || !len))) return fail(h, FQD_ERR_INVALID, "fqd_emission_read: bad arguments");
+    cudaSetDevice(h->cfg.device);
+    return seq_emission_read(h->seq, mate, first, count, (u64*)off, len, &h->err);
+}
+extern "C" int fqd_cluster_read(fqd_handle* h, int mate, uint64_t first, uint64_t count, uint64_t* off, uint32_t* len, uint8_t* head) {
+    if (!h || !h->seq || (count && (!off || !len || !head))) return fail(h, FQD_ERR_INVALID, "fqd_cluster_read: bad arguments");
+    cudaSetDevice(h->cfg.device);
+    return seq_cluster_read(h->seq, mate, first, count, (u64*)off, len, head, &h->err);
+}
+extern "C" int fqd_device_memory(int device, size_t* free_bytes, size_t* total_bytes) {
+    size_t f = 0, t = 0;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMemGetInfo(&f, &t) != cudaSuccess) { cudaGetLastError(); return FQD_ERR_CUDA; }
+    if (free_bytes) *free_bytes = f;
+    if (total_bytes) *total_bytes = t;
+    return FQD_OK;
+}
 extern "C" int fqd_emission(fqd_handle* h, fqd_emission_t* out) {
     if (!h || !h->seq || !out) return fail(h, FQD_ERR_INVALID, "fqd_emission is for sequence / unordered modes");
     return seq_emission(h->seq, out, &h->err);

@@ -772,6 +772,8 @@ struct SeqState {
     u32* d_cl_len[2] = {nullptr, nullptr};     // --write-clusters: line length per sorted position
     u64 cl_cursor[2] = {0, 0};
     bool low_bytes = false;          // byte keys: a sequence holds a byte below '\n' (see k_scan_loose_literal)
+    bool discard = false;            // fqd_discard_input: a segment's raw bytes are freed as soon as it is split and packed
+    u64* d_clr_off = nullptr; u32* d_clr_len = nullptr; u8* d_clr_head = nullptr; u64 clr_cap = 0;    // fqd_cluster_read window
     bool lists_on_host = false;      // h_off / h_len filled (only fqd_emission needs them)
     u32* h_lenwin = nullptr;         // pinned window of record lengths for fqd_emit's batch cuts
     std::vector<void*> scratch;      // freed at destroy / reset
@@ -849,7 +851,7 @@ static void seq_free_results(SeqState* s) {
 static void seq_destroy(SeqState* s) {
     if (!s) return;
     seq_free_results(s);
-    for (int m = 0; m < 2; ++m) for (auto& sg : s->mate[m].segs) if (sg.owned) cudaFreeAsync(sg.d, s->stream);
+    for (int m = 0; m < 2; ++m) for (auto& sg : s->mate[m].segs) if (sg.owned && sg.d) cudaFreeAsync(sg.d, s->stream);
     seq_pool_trim(s);
     if (s->h_lenwin) cudaFreeHost(s->h_lenwin);
     for (int m = 0; m < 2; ++m) {
@@ -865,7 +867,7 @@ static void seq_destroy(SeqState* s) {
 static int seq_reset(SeqState* s, std::string* err) {
     seq_free_results(s);
     for (u32 m = 0; m < s->mates; ++m) {
-        for (auto& sg : s->mate[m].segs) if (sg.owned) cudaFreeAsync(sg.d, s->stream);
+        for (auto& sg : s->mate[m].segs) if (sg.owned && sg.d) cudaFreeAsync(sg.d, s->stream);
         s->mate[m].segs.clear(); s->mate[m].adopted = false;
         s->mate[m].n_records = 0; s->mate[m].finished = false;
         SEQ_TRY(cudaMemsetAsync(s->mate[m].d_run, 0, sizeof(RunState), s->stream));
@@ -881,6 +883,7 @@ static int seq_reset(SeqState* s, std::string* err) {
     s->emit_cursor[0] = s->emit_cursor[1] = 0;
     for (int m = 0; m < 2; ++m) { s->d_o_off[m] = nullptr; s->d_o_len[m] = nullptr; s->d_seg_base[m] = nullptr; s->d_seg_ptr[m] = nullptr; }
     s->d_stage = nullptr; s->stage_cap = 0; s->d_dst = nullptr; s->dst_cap = 0; s->em_scan_state = nullptr;
+    s->d_clr_off = nullptr; s->d_clr_len = nullptr; s->d_clr_head = nullptr; s->clr_cap = 0;
     memset(&s->stats, 0, sizeof s->stats);
     return FQD_OK;
 }
@@ -947,7 +950,7 @@ static bool seq_grow(SeqState* s) {
 static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
     SeqMate& mt = s->mate[m];
     SeqSegment& sg = mt.segs.back();
-    if (sg.fill == 0) return FQD_OK;
+    if (sg.fill == 0 || !sg.d) return FQD_OK;
     const u32 n_tiles = (u32)((sg.fill + PP_TILE - 1) / PP_TILE);
     if (s->capacity == mt.n_records && !seq_grow(s)) { seq_set_error(s, FQD_ERR_CAPACITY, 0, mt.n_records, m); return FQD_OK; }
     const u64 room = s->capacity - mt.n_records;
@@ -1001,6 +1004,10 @@ static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
         if (tail) SEQ_TRY(cudaMemcpyAsync(nx.d, sg.d + consumed, tail, cudaMemcpyDeviceToDevice, s->stream));
         nx.fill = tail;
         mt.segs.back().fill = consumed;
+        if (s->discard) {               // stream-ordered: after the parse kernels and the copy of the tail
+            SEQ_TRY(cudaFreeAsync(mt.segs.back().d, s->stream));
+            mt.segs.back().d = nullptr;
+        }
         mt.segs.push_back(nx);
     } else {
         if (tail) {
@@ -1012,6 +1019,10 @@ static int seq_parse_segment(SeqState* s, int m, bool final, std::string* err) {
             if (b != lead) seq_set_error(s, FQD_ERR_BAD_START, b, mt.n_records, m);
         }
         mt.segs.back().fill = consumed;
+        if (s->discard && sg.owned && sg.d) {
+            SEQ_TRY(cudaFreeAsync(mt.segs.back().d, s->stream));
+            mt.segs.back().d = nullptr;
+        }
     }
     return FQD_OK;
 }
@@ -1777,6 +1788,7 @@ __global__ void k_gather_clusters(const u32* perm, const u32* keep, const u64* r
 
 // per mate: where every input segment lives (logical base -> device pointer), for the record gathers
 static int seq_upload_segtab(SeqState* s, int m, std::string* err) {
+    if (s->discard) { *err = "the raw input was discarded (fqd_discard_input): fetch the records with fqd_emission_read / fqd_cluster_read"; return FQD_ERR_INVALID; }
     if (s->d_seg_base[m]) return FQD_OK;
     SeqMate& mt = s->mate[m];
     std::vector<u64> base; std::vector<u8*> ptr;
@@ -2004,6 +2016,54 @@ static int seq_emission(SeqState* s, fqd_emission_t* out, std::string* err) {
     for (u32 m = 0; m < s->mates; ++m) { out->off[m] = (const uint64_t*)s->h_off[m].data(); out->len[m] = s->h_len[m].data(); }
     return FQD_OK;
 }
+// A window of one mate's emission list, straight into the caller's memory (fqd_emission_read).
+static int seq_emission_read(SeqState* s, int m, u64 first, u64 count, u64* off, u32* len, std::string* err) {
+    if (!s->finished) { *err = "fqd_emission_read before fqd_finish"; return FQD_ERR_INVALID; }
+    if (m < 0 || (u32)m >= s->mates) { *err = "bad mate index"; return FQD_ERR_INVALID; }
+    if (first > s->n_out || count > s->n_out - first) { *err = "fqd_emission_read: window beyond the emission list"; return FQD_ERR_INVALID; }
+    if (count == 0) return FQD_OK;
+    if (!s->d_o_off[m] || !s->d_o_len[m]) { *err = "fqd_emission_read: no emission list"; return FQD_ERR_INVALID; }
+    SEQ_TRY(cudaMemcpyAsync(off, s->d_o_off[m] + first, count * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaMemcpyAsync(len, s->d_o_len[m] + first, count * sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    return FQD_OK;
+}
+
+// --write-clusters without the raw input: who stands at the sorted positions [first, first + count) and is it written?
+__global__ void k_cluster_index(const u32* __restrict__ perm, const u32* __restrict__ keep, const u64* __restrict__ rec_off,
+                                const u32* __restrict__ rec_len, u64 first, u64 count, u64* __restrict__ out_off, u32* __restrict__ out_len,
+                                u8* __restrict__ out_head) {
+    for (u64 r = (u64)blockIdx.x * blockDim.x + threadIdx.x; r < count; r += (u64)gridDim.x * blockDim.x) {
+        const u32 g = perm[first + r];
+        out_off[r] = rec_off[g];
+        out_len[r] = rec_len[g];
+        out_head[r] = keep[first + r] ? 1 : 0;
+    }
+}
+static int seq_cluster_read(SeqState* s, int m, u64 first, u64 count, u64* off, u32* len, u8* head, std::string* err) {
+    if (!s->finished) { *err = "fqd_cluster_read before fqd_finish"; return FQD_ERR_INVALID; }
+    if (s->cfg.unordered || s->cfg.mode == FQD_MODE_FAST) { *err = "cluster files exist in sequence-based modes only"; return FQD_ERR_INVALID; }
+    if (m < 0 || (u32)m >= s->mates) { *err = "bad mate index"; return FQD_ERR_INVALID; }
+    const u64 n = s->stats.err ? 0 : s->n;
+    if (first > n || count > n - first) { *err = "fqd_cluster_read: window beyond the records processed"; return FQD_ERR_INVALID; }
+    if (count == 0) return FQD_OK;
+    if (!s->d_perm || !s->d_keep) { *err = "fqd_cluster_read: no sorted order"; return FQD_ERR_INVALID; }
+    int rc;
+    if (s->clr_cap < count) {
+        if ((rc = seq_dalloc(s, &s->d_clr_off, count, err)) || (rc = seq_dalloc(s, &s->d_clr_len, count, err)) ||
+            (rc = seq_dalloc(s, &s->d_clr_head, count, err))) return rc;
+        s->clr_cap = count;
+    }
+    k_cluster_index<<<seq_grid(s, count), 256, 0, s->stream>>>(s->d_perm, s->d_keep, s->mate[m].d_rec_off, s->mate[m].d_rec_len, first, count,
+                                                              s->d_clr_off, s->d_clr_len, s->d_clr_head);
+    s->launches++;
+    SEQ_TRY(cudaMemcpyAsync(off, s->d_clr_off, count * sizeof(u64), cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaMemcpyAsync(len, s->d_clr_len, count * sizeof(u32), cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaMemcpyAsync(head, s->d_clr_head, count, cudaMemcpyDeviceToHost, s->stream));
+    SEQ_TRY(cudaStreamSynchronize(s->stream));
+    return FQD_OK;
+}
+
 static void seq_stats(SeqState* s, fqd_stats_t* st) { *st = s->stats; }
 static double seq_device_ms(SeqState* s) { return s->ms; }
 static u64 seq_launches(SeqState* s) { return s->launches; }

@@ -17,6 +17,7 @@
 
 #include "../../include/fqd.h"
 #include "io.hpp"
+#include "replay.hpp"
 
 namespace fqdhost {
 namespace {
@@ -43,6 +44,7 @@ template <class T> void leave_to_the_os(std::unique_ptr<T>& job) {
 
 struct WholeJob {
     std::vector<std::unique_ptr<BlockReader>> readers;
+    std::vector<std::unique_ptr<InputReplay>> replay;      // discarded-input path only
     EnginePtr eng;
 };
 
@@ -171,6 +173,92 @@ void sample_geometry(const char* p, size_t n, int lpr, size_t& max_seq, double& 
         cur = nl + 1;
     }
     if (recs) avg_rec = (double)last_rec_end / recs; else { avg_rec = 64; max_seq = std::max<size_t>(max_seq, n); }
+}
+
+// the -v lines of the whole-input modes (src/seq_dup_remover.hpp:107-108,216-217; src/hash_dup_remover.hpp:344-346)
+void print_whole_summary(const fqd_stats_t& st, bool unordered, int mates, bool verbose) {
+    if (!verbose) return;
+    if (unordered) {
+        std::cout << st.total << " valid read pairs processed, out of which " << st.dups << " duplicates were removed.\n";
+        std::cout << st.unmatched << " Non-matching entries from both files were skipped.\n";
+    } else if (mates == 1) {
+        std::cout << st.total << " reads processed, out of which " << st.dups << " duplicates were removed.\n";
+    } else {
+        std::cout << st.total << " read pairs processed, out of which " << st.dups << " duplicates were removed.\n";
+    }
+}
+
+// FQD_WHOLE_INPUT=resident | discard: where the raw bytes of a whole-input job live while it is sorted (default: decided
+// from the input size and the device's free memory, see run_whole_input)
+int whole_input_policy() {
+    const char* e = std::getenv("FQD_WHOLE_INPUT");
+    if (!e) return 0;
+    if (!std::strcmp(e, "resident")) return 1;
+    if (!std::strcmp(e, "discard")) return 2;
+    return 0;
+}
+
+// Device bytes one record (pair) occupies without its raw text: key row(s), (offset, length, sequence length) per
+// mate, tags / hashes of --unordered, and the sort's ping-pong keys and index lists.
+size_t resident_bytes_per_record(const fqd_config& cfg, int mates) {
+    const size_t row = cfg.byte_keys ? ((size_t)cfg.max_seq_len + 1 + 7) / 8 * 8 : (((size_t)cfg.max_seq_len * 3 + 63) / 64 + 1) * 8;
+    size_t b = (size_t)mates * (row + 16) + 64;
+    if (cfg.unordered) b += (size_t)mates * (((cfg.max_tag_len ? cfg.max_tag_len : 32) + 7) / 8 * 8 + 12) + 2 * row + 16;
+    return b;
+}
+
+// The written records of one mate, fetched from the host's copy of the input in emission order: the lists come from
+// the device window by window, a window's records are gathered and written by the output file's workers (write_runs:
+// several at once, each at the file offset its bytes belong to) while the next window's lists arrive.
+void gather_from_replay(fqd_handle* eng, int m, uint64_t n_written, const InputReplay& src, OutputFile& out) {
+    constexpr uint64_t WIN = 1u << 20;
+    std::vector<uint64_t> off((size_t)std::min<uint64_t>(WIN, std::max<uint64_t>(n_written, 1)));
+    std::vector<uint32_t> len(off.size());
+    std::mutex mu; std::condition_variable cv; int in_flight = 0;
+    AsyncWriter writer(out);
+    for (uint64_t k = 0; k < n_written; k += WIN) {
+        const uint64_t c = std::min(WIN, n_written - k);
+        int rc = fqd_emission_read(eng, m, k, c, off.data(), len.data());
+        if (rc) { writer.drain(); throw_engine_error(eng, rc); }
+        std::vector<Run> runs;
+        runs.reserve((size_t)c);
+        size_t total = 0;
+        for (uint64_t i = 0; i < c; ++i) {
+            if (off[i] > src.size() || len[i] > src.size() - off[i]) { writer.drain(); throw std::runtime_error("the engine returned a record outside the input"); }
+            if (!runs.empty() && runs.back().off + runs.back().len == off[i]) runs.back().len += len[i];      // neighbours in the input too
+            else runs.push_back(Run{(size_t)off[i], len[i], total});
+            total += len[i];
+        }
+        { std::unique_lock<std::mutex> g(mu); cv.wait(g, [&] { return in_flight < 3; }); ++in_flight; }      // ~24 MB of runs each
+        writer.write_runs(src.data(), std::move(runs), total);
+        writer.then([&mu, &cv, &in_flight] { { std::lock_guard<std::mutex> g(mu); --in_flight; } cv.notify_all(); });
+    }
+    writer.drain();
+}
+
+// <out>.clusters from the host's copy of the input (src/seq_dup_remover.hpp:60-62,75-76,89-101; src/file_utils.cpp:98-112):
+// one line per record in sorted order, the ID line of a written record, "--" + the ID line of a removed one.
+void clusters_from_replay(fqd_handle* eng, int m, uint64_t n_sorted, const InputReplay& src, const std::string& out_name) {
+    std::ofstream cf(out_name + ".clusters", std::ios::binary);
+    constexpr uint64_t WIN = 1u << 20;
+    std::vector<uint64_t> off((size_t)std::min<uint64_t>(WIN, std::max<uint64_t>(n_sorted, 1)));
+    std::vector<uint32_t> len(off.size());
+    std::vector<uint8_t> head(off.size());
+    std::string text;
+    for (uint64_t k = 0; k < n_sorted; k += WIN) {
+        const uint64_t c = std::min(WIN, n_sorted - k);
+        int rc = fqd_cluster_read(eng, m, k, c, off.data(), len.data(), head.data());
+        if (rc) throw_engine_error(eng, rc);
+        text.clear();
+        for (uint64_t i = 0; i < c; ++i) {
+            if (off[i] > src.size() || len[i] > src.size() - off[i]) throw std::runtime_error("the engine returned a record outside the input");
+            const char* p = src.data() + off[i];
+            const char* nl = (const char*)memchr(p, '\n', len[i]);
+            if (!head[i]) text += "--";
+            text.append(p, nl ? (size_t)(nl - p) + 1 : (size_t)len[i]);
+        }
+        cf.write(text.data(), (std::streamsize)text.size());
+    }
 }
 
 }  // namespace
@@ -609,14 +697,20 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
     double growth = 1.0;
     unsigned seq_growth = 0, tag_growth = 0;
     bool byte_keys = false;         // sequence-based modes order ANY byte (src/fastqview.cpp:56-67): raw-byte key rows
+    // Where the raw bytes live while the job sorts: on the device (it gathers the output itself), or - inputs larger than
+    // device memory - nowhere on the device: only key rows + record tables stay, the host fetches the written records
+    // from its own copy of the input (replay.hpp).  The reference's counterpart is the external sort's disk chunks.
+    const int policy = whole_input_policy();
+    bool discard = policy == 2;
 
     for (int attempt = 0; attempt < 10; ++attempt) {
         auto job = std::make_unique<WholeJob>();
-        auto& readers = job->readers; auto& eng = job->eng;
+        auto& readers = job->readers; auto& eng = job->eng; auto& replay = job->replay;
         for (int m = 0; m < mates; ++m) readers.emplace_back(new BlockReader(in[m], block));
         // geometry of the first block of every file sizes the key rows and the record tables
         std::vector<Block*> first(mates, nullptr);
         size_t max_seq = 0; uint64_t est_records = 0;
+        double raw_bytes = 0; bool sizes_known = true;
         for (int m = 0; m < mates; ++m) {
             first[m] = readers[m]->next();
             if (!first[m] || first[m]->len == 0) throw std::runtime_error("Not enough memory to read a single object!");
@@ -626,6 +720,8 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
             double expand = gz_expansion(in[m], *readers[m]);
             uint64_t est = (uint64_t)((double)file_size_or_zero(in[m]) * expand / std::max(ar, 8.0) * 1.02) + (1u << 16);
             est_records = std::max(est_records, est);
+            raw_bytes += (double)file_size_or_zero(in[m]) * expand;
+            if (!rereadable(in[m])) sizes_known = false;
         }
         fqd_config cfg;
         memset(&cfg, 0, sizeof cfg);
@@ -637,26 +733,57 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
         cfg.max_chunk_bytes = 1ull << 30;              // device segments of 1 GiB
         cfg.max_tag_len = 32u << tag_growth;
         cfg.byte_keys = byte_keys ? 1u : 0u;
+        if (policy == 0 && !discard && sizes_known) {
+            // resident needs the raw bytes + what discard needs anyway + staging for the output gather
+            size_t free_b = 0;
+            if (fqd_device_memory(device, &free_b, nullptr) == FQD_OK) {
+                const double need = raw_bytes * 1.03 + (double)cfg.max_records * (double)resident_bytes_per_record(cfg, mates) + 3.0 * (double)(1ull << 30);
+                if (need > 0.92 * (double)free_b) discard = true;
+            }
+        }
         fqd_handle* hraw = nullptr;
         int rc = fqd_create(&cfg, &hraw);
         if (rc) throw_engine_error(nullptr, rc);
         eng.reset(hraw);
-        trace("engine created");
+        if (discard) {
+            rc = fqd_discard_input(eng.get(), 1);
+            if (rc) throw_engine_error(eng.get(), rc);
+            for (int m = 0; m < mates; ++m)
+                replay.emplace_back(new InputReplay(in[m], rereadable(in[m]) && !has_gz_ext(in[m]), spool_dir_for(out[m])));
+        }
+        trace(discard ? "engine created (raw input not kept on the device)" : "engine created");
 
         // ship every block to the device (the sort/join needs the whole input; nothing is kept on the host)
-        for (int m = 0; m < mates; ++m) {
+        bool out_of_device_memory = false;
+        for (int m = 0; m < mates && !out_of_device_memory; ++m) {
             Block* b = first[m];
             while (b) {
                 rc = fqd_append(eng.get(), m, b->data(), b->len);
+                if (rc == FQD_ERR_CUDA && !discard && policy == 0 && std::strstr(fqd_last_error(eng.get()), "out of memory")) { out_of_device_memory = true; break; }
                 if (rc) throw_engine_error(eng.get(), rc);
+                if (discard) replay[m]->add(b->data(), b->len);
                 readers[m]->release(b);
                 b = readers[m]->next();
             }
         }
+        if (out_of_device_memory) {       // the size estimate was too kind (a .gz that expands more than its head suggested)
+            check_restart_possible(in, mates, "the input does not fit into device memory");
+            discard = true;
+            continue;
+        }
         trace("input on the device");
         rc = fqd_finish(eng.get());
+        if (rc == FQD_ERR_CUDA && !discard && policy == 0 && std::strstr(fqd_last_error(eng.get()), "out of memory") && rereadable(in[0]) && (mates == 1 || rereadable(in[1]))) {
+            discard = true;
+            continue;
+        }
         if (rc) throw_engine_error(eng.get(), rc);
         trace("sorted / joined / scanned");
+        if (std::getenv("FQD_TRACE")) {      // the pool keeps what it ever held: this is the job's high-water mark
+            size_t free_b = 0, total_b = 0;
+            if (fqd_device_memory(device, &free_b, &total_b) == FQD_OK)
+                std::fprintf(stderr, "[host-trace] device memory high-water mark %.2f GiB of %.2f GiB\n", (double)(total_b - free_b) / (1ull << 30), (double)total_b / (1ull << 30));
+        }
         fqd_stats_t st;
         fqd_stats(eng.get(), &st);
         if (st.err == FQD_ERR_SEQ_TOO_LONG) { check_restart_possible(in, mates, "a later sequence is longer than the key rows sized from the first block"); ++seq_growth; continue; }
@@ -673,6 +800,25 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
 
         std::vector<std::unique_ptr<OutputFile>> outs;
         for (int m = 0; m < mates; ++m) outs.emplace_back(new OutputFile(out[m]));
+        if (discard) {
+            uint64_t n_written = 0, n_sorted = 0;
+            rc = fqd_emission_count(eng.get(), &n_written, &n_sorted);
+            if (rc) throw_engine_error(eng.get(), rc);
+            for (int m = 0; m < mates; ++m) {
+                replay[m]->seal();
+                replay[m]->prefault(io_threads());
+                gather_from_replay(eng.get(), m, n_written, *replay[m], *outs[m]);
+            }
+            for (auto& o : outs) o->close();
+            check_outputs(outs, out);
+            if (write_clusters)
+                for (int m = 0; m < mates; ++m) clusters_from_replay(eng.get(), m, n_sorted, *replay[m], out[m]);
+            trace("outputs closed (gathered on the host)");
+            if (st.err == FQD_ERR_BAD_BASE) throw_data_error(st, fasta);
+            print_whole_summary(st, unordered, mates, verbose);
+            leave_to_the_os(job);
+            return;
+        }
         // two pinned staging buffers: the device gathers + copies the next piece while a writer thread writes the last
         const size_t cap = 64u << 20;
         void* stage_buf[2] = {nullptr, nullptr};
@@ -716,16 +862,7 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
         }
         trace("outputs closed");
         if (st.err == FQD_ERR_BAD_BASE) throw_data_error(st, fasta);     // --unordered: raised while pairs are keyed
-        if (verbose) {
-            if (unordered) {
-                std::cout << st.total << " valid read pairs processed, out of which " << st.dups << " duplicates were removed.\n";
-                std::cout << st.unmatched << " Non-matching entries from both files were skipped.\n";
-            } else if (mates == 1) {
-                std::cout << st.total << " reads processed, out of which " << st.dups << " duplicates were removed.\n";
-            } else {
-                std::cout << st.total << " read pairs processed, out of which " << st.dups << " duplicates were removed.\n";
-            }
-        }
+        print_whole_summary(st, unordered, mates, verbose);
         leave_to_the_os(job);
         return;
     }

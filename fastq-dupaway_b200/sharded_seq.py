@@ -22,6 +22,8 @@ import numpy as np
 
 def choose_splitters(samples: np.ndarray, world: int) -> np.ndarray:
     """samples: uint64 [k, 2] (all-ones rows = no data) -> [world - 1, 2] ascending splitters (quantiles)."""
+    if world <= 1:
+        return np.zeros((0, 2), dtype=np.uint64)
     s = samples[~((samples[:, 0] == np.uint64(0xFFFFFFFFFFFFFFFF)) & (samples[:, 1] == np.uint64(0xFFFFFFFFFFFFFFFF)))]
     if len(s) == 0:
         return np.full((world - 1, 2), 0xFFFFFFFFFFFFFFFF, dtype=np.uint64)

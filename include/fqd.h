@@ -172,6 +172,31 @@ int fqd_emit(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, in
  * per input record in sorted order, the ID line of a written record (cluster head) or "--" + the ID line of a removed
  * one (src/seq_dup_remover.hpp:60-62,75-76,89-101,142-146,165-169,187-208; src/file_utils.cpp:98-112). */
 int fqd_emit_clusters(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, int* done);
+/*
+ * Whole-input modes on inputs LARGER THAN DEVICE MEMORY (the successor of the reference's bounded-memory external sort:
+ * chunks of 2/3 memlimit sorted and written to disk, then a k-way merge, src/external_sort.hpp:88-207,
+ * src/paired_external_sort.hpp:112-257).  Sorting, the comparator scans and the tag join only ever look at the packed key
+ * rows and the per-record tables, so the raw bytes need not stay: after fqd_discard_input(h, 1) (before the first
+ * fqd_append; it survives fqd_reset) every input segment is freed as soon as it has been split and packed.  What stays
+ * resident per record is its key row (3 bits per base) + 16 bytes of (offset, lengths) per mate - about a quarter of
+ * the record - and the caller, which still has the input (a file it can map, or a spool it wrote while reading a pipe
+ * or a .gz), fetches the written records itself:
+ *   fqd_emission_read   entries [first, first + count) of one mate's emission list (emission order, as fqd_emission):
+ *                       byte offset in the concatenated input and byte length of every WRITTEN record;
+ *   fqd_cluster_read    --write-clusters: for the sorted positions [first, first + count) (count <= records processed)
+ *                       offset and length of the record standing there and head[i] = 1 when it is written (cluster head;
+ *                       its ID line goes to <out>.clusters as it is, a removed record's with "--" in front).
+ * Both work on any finished whole-input handle; fqd_emit / fqd_emit_clusters / fqd_partition_gather need the raw bytes
+ * and fail with FQD_ERR_INVALID after fqd_discard_input.
+ */
+int fqd_discard_input(fqd_handle* h, int on);
+/* n_written: length of the emission lists; n_sorted: sorted positions fqd_cluster_read can be asked for (0 outside the
+ * sequence-based modes or after a data error).  Either pointer may be NULL. */
+int fqd_emission_count(fqd_handle* h, uint64_t* n_written, uint64_t* n_sorted);
+int fqd_emission_read(fqd_handle* h, int mate, uint64_t first, uint64_t count, uint64_t* off, uint32_t* len);
+int fqd_cluster_read(fqd_handle* h, int mate, uint64_t first, uint64_t count, uint64_t* off, uint32_t* len, uint8_t* head);
+/* Free and total memory of a device in bytes (cudaMemGetInfo): how the host decides whether an input can stay resident. */
+int fqd_device_memory(int device, size_t* free_bytes, size_t* total_bytes);
 
 /*
  * Multi-GPU sequence-based mode (one process per GPU, SURVEY.md 8e: sampled splitters + all-to-all).  The reference has

@@ -8,6 +8,9 @@
 // rings of blocks, tail carry, paired lock-step, restarts after capacity / row-width estimates, asynchronous writers,
 // gzip in and out, the -v lines) runs in the CPU test-suite through the very same binary.
 //   FAKE_FQD_SHRINK=k   pretend the key store holds cfg.max_records / k records (forces the restart path)
+//   FAKE_FQD_REQUIRE_DISCARD=1   fqd_emit refuses: the test expects the host to take the discarded-input path
+//   FAKE_FQD_DEVICE_BYTES=n   what fqd_device_memory reports as free (default 1 TiB): makes the host choose between the
+//                       resident and the discarded-input path of the whole-input modes
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
@@ -37,6 +40,11 @@ struct fqd_handle {
     std::string out[2], clusters[2];     // what fqd_emit / fqd_emit_clusters hand out, whole records / lines at a time
     std::vector<size_t> out_cut[2], cl_cut[2];   // record / line boundaries inside them
     size_t out_pos[2] = {0, 0}, cl_pos[2] = {0, 0};
+    bool discard = false;                        // fqd_discard_input: fqd_emit* refuse, the lists below are what the host gets
+    std::vector<uint64_t> em_off[2], cl_off[2];
+    std::vector<uint32_t> em_len[2], cl_len[2];
+    std::vector<uint8_t> cl_head[2];
+    size_t appended = 0;
     std::unordered_set<std::string> seen;
     std::vector<uint32_t> rec_start[2];
     std::vector<uint8_t> dup;
@@ -160,6 +168,7 @@ int fqd_append(fqd_handle* h, int mate, const char* buf, size_t n) {
     if (!h || mate < 0 || mate > 1 || h->finished) return FQD_ERR_INVALID;
     if (h->cfg.mode == FQD_MODE_FAST && !h->cfg.unordered) { h->err = "fqd_append is for the whole-input modes"; return FQD_ERR_INVALID; }
     h->in[mate].append(buf, n);
+    h->appended += n;
     return FQD_OK;
 }
 
@@ -223,6 +232,7 @@ int fqd_finish(fqd_handle* h) {
             size_t off, len; span(m, idx[k], off, len);
             h->out[m].append(h->in[m], off, len);
             h->out_cut[m].push_back(h->out[m].size());
+            h->em_off[m].push_back(off); h->em_len[m].push_back((uint32_t)len);
         }
         h->cl_cut[m].assign(1, 0);
         if (!unordered && !h->st.err) {
@@ -232,6 +242,8 @@ int fqd_finish(fqd_handle* h) {
                 if (!written.count(order[p])) h->clusters[m] += "--";
                 h->clusters[m].append(h->in[m], (size_t)t[0], (size_t)t[1]);
                 h->cl_cut[m].push_back(h->clusters[m].size());
+                h->cl_off[m].push_back((uint64_t)t[0]); h->cl_len[m].push_back((uint32_t)(t[1] + t[2] + t[3] + t[4]));
+                h->cl_head[m].push_back(written.count(order[p]) ? 1 : 0);
             }
         }
     }
@@ -251,13 +263,49 @@ static int stream_out(const std::string& data, const std::vector<size_t>& cut, s
 }
 int fqd_emit(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, int* done) {
     if (!h || !h->finished || mate < 0 || mate > 1) return FQD_ERR_INVALID;
+    if (h->discard) { h->err = "[fake_fqd] fqd_emit after fqd_discard_input"; return FQD_ERR_INVALID; }
+    if (std::getenv("FAKE_FQD_REQUIRE_DISCARD")) { h->err = "[fake_fqd] the test expected the discarded-input path"; return FQD_ERR_INVALID; }
     return stream_out(h->out[mate], h->out_cut[mate], h->out_pos[mate], dst, cap, n_bytes, done);
 }
 int fqd_emit_clusters(fqd_handle* h, int mate, void* dst, size_t cap, size_t* n_bytes, int* done) {
     if (!h || !h->finished || mate < 0 || mate > 1) return FQD_ERR_INVALID;
+    if (h->discard) { h->err = "[fake_fqd] fqd_emit_clusters after fqd_discard_input"; return FQD_ERR_INVALID; }
     return stream_out(h->clusters[mate], h->cl_cut[mate], h->cl_pos[mate], dst, cap, n_bytes, done);
 }
 
+// ---- the discarded-input path (include/fqd.h): lists instead of bytes -------------------------------------------------
+int fqd_discard_input(fqd_handle* h, int on) {
+    if (!h || h->appended) { if (h) h->err = "fqd_discard_input after the first fqd_append"; return FQD_ERR_INVALID; }
+    h->discard = on != 0;
+    return FQD_OK;
+}
+int fqd_emission_count(fqd_handle* h, uint64_t* n_written, uint64_t* n_sorted) {
+    if (!h || !h->finished) return FQD_ERR_INVALID;
+    if (n_written) *n_written = h->em_off[0].size();
+    if (n_sorted) *n_sorted = h->cl_off[0].size();
+    return FQD_OK;
+}
+int fqd_emission_read(fqd_handle* h, int mate, uint64_t first, uint64_t count, uint64_t* off, uint32_t* len) {
+    if (!h || !h->finished || mate < 0 || mate > 1) return FQD_ERR_INVALID;
+    const uint64_t n = h->em_off[mate].size();
+    if (first > n || count > n - first) { h->err = "fqd_emission_read: window beyond the emission list"; return FQD_ERR_INVALID; }
+    for (uint64_t i = 0; i < count; ++i) { off[i] = h->em_off[mate][first + i]; len[i] = h->em_len[mate][first + i]; }
+    return FQD_OK;
+}
+int fqd_cluster_read(fqd_handle* h, int mate, uint64_t first, uint64_t count, uint64_t* off, uint32_t* len, uint8_t* head) {
+    if (!h || !h->finished || mate < 0 || mate > 1) return FQD_ERR_INVALID;
+    const uint64_t n = h->cl_off[mate].size();
+    if (first > n || count > n - first) { h->err = "fqd_cluster_read: window beyond the records processed"; return FQD_ERR_INVALID; }
+    for (uint64_t i = 0; i < count; ++i) { off[i] = h->cl_off[mate][first + i]; len[i] = h->cl_len[mate][first + i]; head[i] = h->cl_head[mate][first + i]; }
+    return FQD_OK;
+}
+int fqd_device_memory(int, size_t* free_bytes, size_t* total_bytes) {
+    const char* e = std::getenv("FAKE_FQD_DEVICE_BYTES");
+    const size_t v = e ? (size_t)std::atoll(e) : (size_t)1 << 40;
+    if (free_bytes) *free_bytes = v;
+    if (total_bytes) *total_bytes = v;
+    return FQD_OK;
+}
 
 // Several engines behind one binary (FQD_DEVICES) need real devices: the double refuses, loudly.
 static int no_shards(fqd_handle* h) { if (h) h->err = "[fake_fqd] the test double has no sharded path"; return FQD_ERR_INVALID; }

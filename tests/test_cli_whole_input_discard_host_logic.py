@@ -1,0 +1,145 @@
+"""The whole-input host suite once more with FQD_WHOLE_INPUT=discard: the device (here: the test double) keeps no raw
+bytes, the binary maps a plain input or spools a .gz / a pipe into an unlinked temporary file, reads the (offset, length)
+emission lists window by window and gathers the written records - and the cluster files - itself (host/replay.hpp,
+dup_remover.cpp::gather_from_replay).  FAKE_FQD_REQUIRE_DISCARD makes the double refuse fqd_emit, so a run that silently
+took the resident path fails.  Then the cases of its own: the automatic choice by device memory, spool directory
+problems, outputs that are pipes or .gz."""
+import gzip
+import os
+import subprocess
+import threading
+
+import pytest
+
+import synth
+import test_cli_whole_input_host_logic as whole_suite
+from test_cli_whole_input_host_logic import run, fake_engine  # noqa: F401  (module fixture builds the double + the binary)
+from test_host_io import deflate_gz
+
+
+@pytest.fixture(autouse=True)
+def discarded_input(monkeypatch):
+    monkeypatch.setenv("FQD_WHOLE_INPUT", "discard")
+    monkeypatch.setenv("FAKE_FQD_REQUIRE_DISCARD", "1")
+
+
+@pytest.mark.parametrize("mode,dist", whole_suite.MODES)
+@pytest.mark.parametrize("paired", [False, True])
+def test_sequence_modes(tmp_path, oracle, mode, dist, paired):
+    # mate 1 is a multi-member .gz (spooled), mate 2 a plain file (mapped); .gz and plain outputs; cluster files
+    whole_suite.test_sequence_modes_against_oracle_and_stable_reference(tmp_path, oracle, mode, dist, paired)
+
+
+def test_unordered_with_restart(tmp_path, oracle):
+    whole_suite.test_unordered_with_long_tags_restarts_and_matches_the_reference(tmp_path, oracle)
+
+
+@pytest.mark.parametrize("mode", ["tight", "loose", "tail-hamming"])
+def test_byte_key_restart(tmp_path, oracle, mode):
+    whole_suite.test_arbitrary_sequence_bytes_restart_with_byte_keys(tmp_path, oracle, mode)
+
+
+def test_capacity_and_row_width_restarts(tmp_path, oracle):
+    whole_suite.test_restarts_on_capacity_and_row_width(tmp_path, oracle)
+
+
+@pytest.mark.parametrize("mode,unordered", [("tight", False), ("tail-hamming", False), ("fast", True)])
+def test_malformed_records(tmp_path, oracle, mode, unordered):
+    whole_suite.test_malformed_record_in_whole_input_modes_matches_the_reference_binary(tmp_path, oracle, mode, unordered)
+
+
+def test_odd_inputs(tmp_path, oracle):
+    whole_suite.test_odd_inputs_in_every_mode_match_the_reference_binaries(tmp_path, oracle)
+
+
+def test_unusual_files(tmp_path, oracle):
+    whole_suite.test_unusual_files_in_every_mode_match_the_reference_binaries(tmp_path, oracle)
+
+
+def test_fifo_in_fifo_out(tmp_path, oracle):
+    whole_suite.test_fifo_input_and_fifo_output_in_a_sequence_mode(tmp_path, oracle)
+
+
+# ---- cases of this path's own --------------------------------------------------------------------------------------
+def _job(tmp_path, n=20000, seed=5):
+    s1, s2 = synth.make_pair(n, seed=seed, read_len=50, var_len=True, prefix_frac=0.2, sub_frac=0.2, dup_frac=0.4)
+    b1, b2 = synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2)
+    (tmp_path / "a.fq").write_bytes(b1)
+    (tmp_path / "b.fq").write_bytes(b2)
+    return b1, b2
+
+
+def test_choice_follows_device_memory(tmp_path, oracle, monkeypatch):
+    """Without FQD_WHOLE_INPUT the host compares the input's size with the device's free memory: a device with room keeps
+    the raw bytes (fqd_emit gathers), a small one makes the host gather; both give the oracle's bytes."""
+    monkeypatch.delenv("FQD_WHOLE_INPUT")
+    monkeypatch.delenv("FAKE_FQD_REQUIRE_DISCARD")
+    b1, b2 = _job(tmp_path)
+    e1, e2, est = oracle.run_oracle("loose", oracle.FASTQ, b1, b2)
+    io = ["-i", tmp_path / "a.fq", "-u", tmp_path / "b.fq", "-o", tmp_path / "o1.fq", "-p", tmp_path / "o2.fq", "--compare-seq", "loose", "-v"]
+    roomy = run(*io, env={"FQD_TRACE": "1"})
+    assert roomy.returncode == 0, roomy.stderr
+    assert "raw input not kept" not in roomy.stderr
+    assert (tmp_path / "o1.fq").read_bytes() == e1 and (tmp_path / "o2.fq").read_bytes() == e2
+    os.remove(tmp_path / "o1.fq"), os.remove(tmp_path / "o2.fq")
+    tight = run(*io, env={"FQD_TRACE": "1", "FAKE_FQD_DEVICE_BYTES": str(2 << 30), "FAKE_FQD_REQUIRE_DISCARD": "1"})
+    assert tight.returncode == 0, tight.stderr
+    assert "raw input not kept" in tight.stderr and "gathered on the host" in tight.stderr
+    assert (tmp_path / "o1.fq").read_bytes() == e1 and (tmp_path / "o2.fq").read_bytes() == e2
+    assert tight.stdout == roomy.stdout == f"{est.total} read pairs processed, out of which {est.dups} duplicates were removed.\n"
+    # the resident path can be forced as well
+    forced = run(*io, env={"FQD_TRACE": "1", "FAKE_FQD_DEVICE_BYTES": str(2 << 30), "FQD_WHOLE_INPUT": "resident"})
+    assert forced.returncode == 0 and "raw input not kept" not in forced.stderr
+
+
+def test_spool_goes_where_it_is_told_and_leaves_nothing_behind(tmp_path, oracle):
+    b1, _ = _job(tmp_path, n=8000)
+    (tmp_path / "a.fq.gz").write_bytes(deflate_gz(b1, 6))
+    spool = tmp_path / "spool"
+    spool.mkdir()
+    out = tmp_path / "out"
+    out.mkdir()
+    res = run("-i", tmp_path / "a.fq.gz", "-o", out / "o.fq", "--compare-seq", "tight", env={"FQD_SPOOL_DIR": str(spool)})
+    assert res.returncode == 0, res.stderr
+    e1, _, _ = oracle.run_oracle("tight", oracle.FASTQ, b1)
+    assert (out / "o.fq").read_bytes() == e1
+    assert list(spool.iterdir()) == [] and [p.name for p in out.iterdir()] == ["o.fq"]
+    # default: next to the output file; unlinked at once
+    res = run("-i", tmp_path / "a.fq.gz", "-o", out / "o2.fq", "--compare-seq", "tight")
+    assert res.returncode == 0 and sorted(p.name for p in out.iterdir()) == ["o.fq", "o2.fq"]
+    # a spool directory that does not exist is an error with advice, not a crash
+    res = run("-i", tmp_path / "a.fq.gz", "-o", out / "o3.fq", "--compare-seq", "tight", env={"FQD_SPOOL_DIR": str(tmp_path / "missing")})
+    assert res.returncode != 0 and "input spool" in res.stderr and "FQD_SPOOL_DIR" in res.stderr
+
+
+def test_gz_and_pipe_outputs(tmp_path, oracle):
+    b1, b2 = _job(tmp_path, n=12000, seed=6)
+    e1, e2, _ = oracle.run_oracle("tail-hamming", oracle.FASTQ, b1, b2, dist=2)
+    os.mkfifo(tmp_path / "out.fifo")
+    got = {}
+
+    def drain():
+        with open(tmp_path / "out.fifo", "rb") as f:
+            got["out"] = f.read()
+    t = threading.Thread(target=drain)
+    t.start()
+    res = run("-i", tmp_path / "a.fq", "-u", tmp_path / "b.fq", "-o", tmp_path / "o1.fq.gz", "-p", tmp_path / "out.fifo",
+              "--compare-seq", "tail-hamming", "--distance", 2)
+    t.join(timeout=60)
+    assert res.returncode == 0, res.stderr
+    assert gzip.decompress((tmp_path / "o1.fq.gz").read_bytes()) == e1
+    assert got["out"] == e2
+
+
+def test_large_windows(tmp_path, oracle):
+    """More written records than one list window (2^20): several windows in flight behind the asynchronous writer."""
+    seqs = synth.make_reads(1_300_000, seed=8, read_len=24, dup_frac=0.1)
+    buf = synth.to_fasta(seqs)
+    (tmp_path / "a.fa").write_bytes(buf)
+    res = run("-i", tmp_path / "a.fa", "-o", tmp_path / "o.fa", "--format", "fasta", "--compare-seq", "tight", "-v", "--write-clusters")
+    assert res.returncode == 0, res.stderr
+    e1, _, est = oracle.run_oracle("tight", oracle.FASTA, buf)
+    assert est.total - est.dups > (1 << 20)
+    assert (tmp_path / "o.fa").read_bytes() == e1
+    cl, _ = oracle.cluster_text("tight", oracle.FASTA, buf)
+    assert (tmp_path / "o.fa.clusters").read_bytes() == cl[0]

@@ -76,3 +76,32 @@ def test_odd_inputs(tmp_path, oracle):
 
 def test_unusual_files(tmp_path, oracle):
     whole_suite.test_unusual_files_in_every_mode_match_the_reference_binaries(tmp_path, oracle)
+
+
+# ---- the same jobs with nothing but key rows resident (FQD_WHOLE_INPUT=discard: inputs larger than device memory) ----
+def _discard_run(*args, env=None):
+    res = _real_run(*args, env=dict(env or {}, FQD_WHOLE_INPUT="discard", FQD_TRACE="1"))
+    if res.returncode == 0:
+        assert "raw input not kept on the device" in res.stderr and "gathered on the host" in res.stderr
+    res.stderr = "".join(l + "\n" for l in res.stderr.splitlines() if not l.startswith(("[host-trace]", "[fqd trace]")))
+    return res
+
+
+@pytest.mark.parametrize("mode,dist", whole_suite.MODES)
+@pytest.mark.parametrize("paired", [False, True])
+def test_sequence_modes_discarded_input(tmp_path, oracle, monkeypatch, mode, dist, paired):
+    """.gz input spooled, plain input mapped, output records and cluster files gathered on the host from the engine's
+    (offset, length) lists: bytes equal to the oracle and to the stable-sort reference binary."""
+    monkeypatch.setattr(whole_suite, "run", _discard_run)
+    whole_suite.test_sequence_modes_against_oracle_and_stable_reference(tmp_path, oracle, mode, dist, paired)
+
+
+def test_unordered_discarded_input(tmp_path, oracle, monkeypatch):
+    monkeypatch.setattr(whole_suite, "run", _discard_run)
+    whole_suite.test_unordered_with_long_tags_restarts_and_matches_the_reference(tmp_path, oracle)
+
+
+@pytest.mark.parametrize("mode,unordered", [("tight", False), ("fast", True)])
+def test_whole_input_malformed_discarded_input(tmp_path, oracle, monkeypatch, mode, unordered):
+    monkeypatch.setattr(whole_suite, "run", _discard_run)
+    whole_suite.test_malformed_record_in_whole_input_modes_matches_the_reference_binary(tmp_path, oracle, mode, unordered)

@@ -300,3 +300,83 @@ def test_long_hamming_chains(fqd, oracle, paired, dist):
         seqs2 = [mutate(base[int(rng.integers(0, 3))], int(rng.integers(0, 2))) for _ in range(len(seqs))]
         b2 = synth.to_fastq(seqs2, mate=2)
     _check(fqd, oracle, "tail-hamming", b1, b2, fqd.FORMAT_FASTQ, dist=dist, max_seq_len=60, seg_bytes=1 << 20)
+
+
+# ---- inputs larger than device memory: the raw bytes are freed as they are parsed (fqd_discard_input) ----------------
+@pytest.mark.parametrize("mode,dist", MODES)
+@pytest.mark.parametrize("paired", [False, True])
+def test_discarded_input_matches_oracle(fqd, oracle, mode, dist, paired):
+    """Same jobs as above with nothing but key rows and record tables resident: many small segments (each freed after its
+    parse, tails carried), records fetched on the host from the windowed emission list."""
+    kw = dict(read_len=60, var_len=True, min_len=0, n_frac=0.05, prefix_frac=0.3, sub_frac=0.3, dup_frac=0.5)
+    if paired:
+        s1, s2 = synth.make_pair(5000, seed=91, **kw)
+        b1, b2 = synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2)
+    else:
+        b1, b2 = synth.to_fastq(synth.make_reads(7000, seed=92, **kw)), None
+    _check(fqd, oracle, mode, b1, b2, fqd.FORMAT_FASTQ, dist=dist, max_seq_len=60, seg_bytes=1 << 16, append_bytes=37_000,
+           discard=True, window=613)
+
+
+def test_discarded_input_error_paths_and_refusals(fqd, oracle):
+    for buf in (b"", b"@a\nACGT\n+\nFFF\n", b"@a\nACGT\n+\nFFFF\nxb\nACGT\n+\nFFFF\n", b"@a\nACGT\n+\nFFFF\n@b\nAC"):
+        _check(fqd, oracle, "tight", buf, None, fqd.FORMAT_FASTQ, discard=True)
+    eng = fqd.Engine("tight", fqd.FORMAT_FASTQ, False, False, 2, 40, 100, 1 << 16, 0, 0)
+    try:
+        eng.discard_input(True)
+        eng.append(0, b"@a\nACGT\n+\nFFFF\n@b\nACGT\n+\nFFFF\n@c\nTTTT\n+\nFFFF\n")
+        with pytest.raises(fqd.FqdError):
+            eng.discard_input(False)                  # not after the first append
+        eng.finish()
+        st = eng.stats()
+        assert (st.err, st.total, st.dups) == (0, 3, 1)
+        with pytest.raises(fqd.FqdError):
+            eng.emit_all(0)                           # the device has no bytes to gather from
+        with pytest.raises(fqd.FqdError):
+            eng.emit_clusters_all(0)
+        with pytest.raises(fqd.FqdError):
+            eng.emission_read(0, 1, 2)                # beyond the two written records
+        off, ln = eng.emission_read(0, 0, 2)
+        assert off.tolist() == [0, 30] and ln.tolist() == [15, 15]
+        off, ln, head = eng.cluster_read(0, 0, 3)
+        assert off.tolist() == [0, 15, 30] and ln.tolist() == [15, 15, 15] and head.tolist() == [1, 0, 1]
+        eng.reset()                                   # the setting survives a reset
+        eng.append(0, b"@a\nACGT\n+\nFFFF\n")
+        eng.finish()
+        with pytest.raises(fqd.FqdError):
+            eng.emit_all(0)
+    finally:
+        eng.close()
+
+
+@pytest.mark.parametrize("mode,dist", [("tight", 2), ("loose", 2), ("tail-hamming", 2)])
+@pytest.mark.parametrize("paired", [False, True])
+def test_cluster_files_from_discarded_input(fqd, oracle, mode, dist, paired):
+    """--write-clusters when the device kept no raw bytes: the text rebuilt on the host from fqd_cluster_read windows
+    must be the oracle's cluster text."""
+    kw = dict(read_len=40, var_len=True, min_len=0, n_frac=0.05, prefix_frac=0.3, sub_frac=0.3, dup_frac=0.5)
+    if paired:
+        s1, s2 = synth.make_pair(3000, seed=73, **kw)
+        bufs = [synth.to_fastq(s1, mate=1), synth.to_fastq(s2, mate=2)]
+    else:
+        bufs = [synth.to_fastq(synth.make_reads(4000, seed=74, **kw), id_fmt="@SYN.{i} some description {mate}")]
+    texts, est = oracle.cluster_text(mode, oracle.FASTQ, bufs[0], bufs[1] if paired else None, dist=dist)
+    eng = fqd.Engine(mode, fqd.FORMAT_FASTQ, paired, False, dist, 40, 5000, 1 << 16, 0, 0)
+    try:
+        eng.discard_input(True)
+        for m, b in enumerate(bufs):
+            for o in range(0, len(b), 70_000):
+                eng.append(m, b[o: o + 70_000])
+        eng.finish()
+        st = eng.stats()
+        assert st.err == 0 and (st.total, st.dups) == (est.total, est.dups)
+        for m, b in enumerate(bufs):
+            text = []
+            for k in range(0, st.total, 777):
+                off, ln, head = eng.cluster_read(m, k, min(777, st.total - k))
+                for o, l, hd in zip(off.tolist(), ln.tolist(), head.tolist()):
+                    line = b[o: b.index(b"\n", o, o + l) + 1]
+                    text.append(line if hd else b"--" + line)
+            assert b"".join(text) == texts[m]
+    finally:
+        eng.close()

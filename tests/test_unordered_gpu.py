@@ -116,3 +116,10 @@ def test_long_tags_report_their_limit(fqd):
     assert st.err == 10
     o1, o2, st = fqd.dedup_whole("fast", b, b, fqd.FORMAT_FASTQ, unordered=True, max_tag_len=64)
     assert st.err == 0 and o1 == b and o2 == b
+
+
+@pytest.mark.parametrize("seed", [5, 6])
+def test_discarded_input(fqd, oracle, seed):
+    """--fast --unordered with nothing but tags, key rows and record tables resident (fqd_discard_input)."""
+    b1, b2 = _make(3000, seed)
+    _check(fqd, oracle, b1, b2, fqd.FORMAT_FASTQ, max_seq_len=40, seg_bytes=1 << 16, append_bytes=45_000, discard=True, window=211)
