@@ -335,13 +335,60 @@ def our_arm(args):
         bm = importlib.import_module("bench_modes")
         want = [m for m in os.environ.get("FQD_BENCH_MODES", "").split(",") if m] or None
         modes = bm.run_modes(fqd, lib, args, dev, (peak, peak_kind), want)
+    files = None
+    if not os.environ.get("FQD_BENCH_SKIP_FILES"):
+        try:
+            files = files_in_files_out()
+        except Exception as ex:   # report, never hide
+            files = {"error": repr(ex)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8",
             "data": "synthetic", "config": workload_config(args, n_total), "clocks": sampler.summary(),
             "e2e": e2e, "gpu_launches": int((l1 - l0)), "roofline": roofline, "cpu_baseline": cpu, "parity": parity,
             "duplicates_removed": int(dups), "survivors_listed": int(n_surv), "input_GBps": n_total * REC_BYTES / (ms_per_step / 1000.0) / 1e9,
-            "modes": modes}
+            "modes": modes, "files": files}
     print(json.dumps(line), flush=True)
+
+
+def files_in_files_out():
+    """What a user of the drop-in binary sees: fastq-dupaway_b200/host/fastq-dupaway started as a process on FILES (tmpfs),
+    wall clock around it - CUDA start-up, host ingest, H2D, kernels, output gather and file writes included.  Bounded
+    samples of the same synthetic stream: FQD_BENCH_FILE_READS single-end reads through --fast (default 20 M) and
+    FQD_BENCH_FILE_PAIRS pairs through --compare-seq tight (default 10 M).  The reference's rate on files is `cpu_baseline`."""
+    bc = importlib.import_module("bench_cli")
+    shm = Path("/dev/shm")
+    n_se = int(os.environ.get("FQD_BENCH_FILE_READS", 20_000_000))
+    n_pe = int(os.environ.get("FQD_BENCH_FILE_PAIRS", 10_000_000))
+    need = max(n_se, 2 * n_pe) * REC_BYTES * 2
+    if not shm.is_dir() or shutil.disk_usage(shm).free < need * 1.5:
+        return {"error": "not enough room on /dev/shm for the sample files"}
+    if not bc.EXE.exists():
+        subprocess.run(["make", "-s", "-C", str(bc.EXE.parent)], check=True)
+    tmp = Path(tempfile.mkdtemp(prefix="fqd_files_", dir=shm))
+    out = {}
+    try:
+        a, b = tmp / "in_1.fq", tmp / "in_2.fq"
+        bc.synth_file(a, n_se, 1)
+        best = None
+        for _ in range(2):
+            dt, so, ph = bc.timed([bc.EXE, "-i", a, "-o", tmp / "out_1.fq", "--fast", "-v"], tmp, trace=True)
+            if best is None or dt < best[0]:
+                best = (dt, so, ph)
+        out["fast_se"] = {"value": n_se / best[0], "unit": "reads/s", "reads": n_se, "seconds": best[0], **best[2],
+                          "input_bytes": a.stat().st_size, "output_bytes": (tmp / "out_1.fq").stat().st_size, "stdout": best[1]}
+        (tmp / "out_1.fq").unlink()
+        if n_pe:
+            if n_pe != n_se:
+                bc.synth_file(a, n_pe, 1)
+            bc.synth_file(b, n_pe, 2)
+            dt, so, ph = bc.timed([bc.EXE, "-i", a, "-u", b, "-o", tmp / "out_1.fq", "-p", tmp / "out_2.fq", "--compare-seq", "tight", "-v"], tmp, trace=True)
+            out["tight_pe"] = {"value": n_pe / dt, "unit": "pairs/s", "pairs": n_pe, "seconds": dt, **ph, "input_bytes": a.stat().st_size + b.stat().st_size,
+                               "output_bytes": (tmp / "out_1.fq").stat().st_size + (tmp / "out_2.fq").stat().st_size, "stdout": so}
+        out["how"] = "plain FASTQ on tmpfs in, plain FASTQ on tmpfs out, one process per job, wall clock (time.perf_counter) around it; fast_se: best of 2"
+        out["host_cores"] = os.cpu_count()
+        return out
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
 
 
 def e2e_run(args, fqd, lib, eng, raw, n_total, chunk_reads, dups_expected):

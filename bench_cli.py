@@ -35,26 +35,41 @@ READ_LEN, SEED, DUP_PERMILLE, N_PERMILLE = 150, 1, 300, 0
 REC = 22 + 2 * READ_LEN
 
 
-def synth_file(path: Path, n_reads: int, mate: int = 1):
-    """device generator -> host -> file, 4 M reads at a time (FQD_BENCH_CLI_CPU_SYNTH=1: the numpy twin of the generator,
-    for trying this script where there is no GPU)"""
-    step = 4_000_000
+def synth_file(path: Path, n_reads: int, mate: int = 1, workers: int = 4):
+    """device generator -> host -> file; `workers` threads take every k-th stretch of 2 M reads and pwrite it where it
+    belongs (the generator is counter-based, tmpfs page allocation is the slow part and runs in parallel this way).
+    FQD_BENCH_CLI_CPU_SYNTH=1: the numpy twin of the generator, for trying this script where there is no GPU."""
     if os.environ.get("FQD_BENCH_CLI_CPU_SYNTH"):
         gen = importlib.import_module("bench_synth")
+        step = 4_000_000
         with open(path, "wb") as f:
             for first in range(0, n_reads, step):
                 f.write(gen.synth_fastq_cpu(first, min(step, n_reads - first), READ_LEN, mate, SEED, DUP_PERMILLE, N_PERMILLE))
         return
+    import ctypes as C
     pkg = importlib.import_module("fastq-dupaway_b200")
     lib = pkg.load_library()
-    buf = pkg.DeviceBuffer(step * REC)
-    with open(path, "wb") as f:
-        for first in range(0, n_reads, step):
+    step = 2_000_000
+    workers = max(1, min(workers, (n_reads + step - 1) // step))
+    fd = os.open(path, os.O_WRONLY | os.O_CREAT | os.O_TRUNC, 0o644)
+
+    def work(k):
+        buf = pkg.DeviceBuffer(step * REC)
+        host = C.create_string_buffer(step * REC)
+        view = memoryview(host)
+        for first in range(k * step, n_reads, step * workers):
             cnt = min(step, n_reads - first)
-            rc = lib.fqd_synth_fastq(0, buf.ptr, first, cnt, READ_LEN, mate, SEED, DUP_PERMILLE, N_PERMILLE, 0)
-            assert rc == 0
-            f.write(buf.download(cnt * REC))
-    buf.free()
+            assert lib.fqd_synth_fastq(0, buf.ptr, first, cnt, READ_LEN, mate, SEED, DUP_PERMILLE, N_PERMILLE, 0) == 0
+            assert lib.fqd_memcpy_d2h(0, host, C.c_void_p(buf.ptr), cnt * REC) == 0
+            done = 0
+            while done < cnt * REC:
+                done += os.pwrite(fd, view[done: cnt * REC], first * REC + done)
+        buf.free()
+    try:
+        with ThreadPoolExecutor(max_workers=workers) as ex:
+            list(ex.map(work, range(workers)))
+    finally:
+        os.close(fd)
 
 
 def gz_members(src: Path, dst: Path, piece: int, bgzf: bool):

@@ -83,6 +83,8 @@ def main():
     ap.add_argument("--ref-pairs", type=int, default=1_000_000)
     ap.add_argument("--big-pairs", type=int, default=-1, help="-1: from MemAvailable (at most 200 M); 0: skip")
     ap.add_argument("--mode", default="tight")
+    ap.add_argument("--big-out", default="tmpfs", choices=["tmpfs", "null"],
+                    help="null: the large job writes to /dev/null (input alone fills the box's RAM); records are still gathered")
     args = ap.parse_args()
     oracle = importlib.import_module("oracle")
     tmp = Path(tempfile.mkdtemp(prefix="fqd_discard_", dir="/dev/shm"))
@@ -142,15 +144,17 @@ def main():
                 except OSError:
                     pass
             shm = shutil.disk_usage("/dev/shm").free
-            big = min(200_000_000, int(min(avail * 0.75, shm * 0.9) / (2 * REC * 1.7)) // 1_000_000 * 1_000_000)
+            per_pair = 2 * REC * (1.0 if args.big_out == "null" else 1.7)
+            big = min(200_000_000, int(min(avail * (0.8 if args.big_out == "null" else 0.75), shm * 0.9) / per_pair) // 1_000_000 * 1_000_000)
             print(json.dumps({"what": "box", "MemAvailable_GiB": round(avail / 2**30, 1), "dev_shm_free_GiB": round(shm / 2**30, 1), "big_pairs": big,
                               "cores": os.cpu_count()}), flush=True)
         if big > 0:
             ins, gen_s = make_inputs(tmp, big, "big")
-            outs = [tmp / f"bigout_{m}.fq" for m in (1, 2)]
+            outs = [tmp / f"bigout_{m}.fq" for m in (1, 2)] if args.big_out == "tmpfs" else [Path("/dev/null"), Path("/dev/zero")]
             dt, so, ph, hw, disc = run(ins, outs, args.mode, None)
             print(json.dumps({"what": "large job, policy chosen by the binary", "mode": args.mode, "pairs": big, "input_bytes": sum(f.stat().st_size for f in ins),
-                              "output_bytes": sum(f.stat().st_size for f in outs), "discarded_input_path": disc, "seconds": round(dt, 2),
+                              "outputs": "tmpfs" if args.big_out == "tmpfs" else "/dev/null, /dev/zero (gathered, not kept: the input alone fills this box's RAM)",
+                              "output_bytes": sum(f.stat().st_size for f in outs) if args.big_out == "tmpfs" else None, "discarded_input_path": disc, "seconds": round(dt, 2),
                               "pairs_per_s": round(big / dt), **ph, "device_GiB_high_water": hw, "stdout": so, "generate_s": round(gen_s, 1)}), flush=True)
     finally:
         shutil.rmtree(tmp, ignore_errors=True)

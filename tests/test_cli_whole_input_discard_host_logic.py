@@ -75,8 +75,9 @@ def test_choice_follows_device_memory(tmp_path, oracle, monkeypatch):
     monkeypatch.delenv("FQD_WHOLE_INPUT")
     monkeypatch.delenv("FAKE_FQD_REQUIRE_DISCARD")
     b1, b2 = _job(tmp_path)
+    (tmp_path / "a.fq.gz").write_bytes(deflate_gz(b1, 6))       # a .gz would have to be spooled: it stays on a device with room
     e1, e2, est = oracle.run_oracle("loose", oracle.FASTQ, b1, b2)
-    io = ["-i", tmp_path / "a.fq", "-u", tmp_path / "b.fq", "-o", tmp_path / "o1.fq", "-p", tmp_path / "o2.fq", "--compare-seq", "loose", "-v"]
+    io = ["-i", tmp_path / "a.fq.gz", "-u", tmp_path / "b.fq", "-o", tmp_path / "o1.fq", "-p", tmp_path / "o2.fq", "--compare-seq", "loose", "-v"]
     roomy = run(*io, env={"FQD_TRACE": "1"})
     assert roomy.returncode == 0, roomy.stderr
     assert "raw input not kept" not in roomy.stderr
@@ -90,6 +91,11 @@ def test_choice_follows_device_memory(tmp_path, oracle, monkeypatch):
     # the resident path can be forced as well
     forced = run(*io, env={"FQD_TRACE": "1", "FAKE_FQD_DEVICE_BYTES": str(2 << 30), "FQD_WHOLE_INPUT": "resident"})
     assert forced.returncode == 0 and "raw input not kept" not in forced.stderr
+    # plain files that fit the page cache are mapped and gathered on the host even when the device has room
+    io_plain = ["-i", tmp_path / "a.fq", "-u", tmp_path / "b.fq", "-o", tmp_path / "p1.fq", "-p", tmp_path / "p2.fq", "--compare-seq", "loose", "-v"]
+    plain = run(*io_plain, env={"FQD_TRACE": "1", "FAKE_FQD_REQUIRE_DISCARD": "1"})
+    assert plain.returncode == 0, plain.stderr
+    assert "raw input not kept" in plain.stderr and (tmp_path / "p1.fq").read_bytes() == e1 and (tmp_path / "p2.fq").read_bytes() == e2
 
 
 def test_spool_goes_where_it_is_told_and_leaves_nothing_behind(tmp_path, oracle):
