@@ -45,7 +45,7 @@ template <class T> void leave_to_the_os(std::unique_ptr<T>& job) {
 
 struct WholeJob {
     std::vector<std::unique_ptr<BlockReader>> readers;
-    std::vector<std::unique_ptr<InputReplay>> replay;      // discarded-input path only
+    std::vector<std::shared_ptr<InputReplay>> replay;      // discarded-input path only
     EnginePtr eng;
 };
 
@@ -703,6 +703,18 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
     // from its own copy of the input (replay.hpp).  The reference's counterpart is the external sort's disk chunks.
     const int policy = whole_input_policy();
     bool discard = policy == 2;
+    // A pipe can be read once, but its complete spool can be read again: `in` is what the user named, `eff` what this
+    // attempt reads (the original, or /proc/self/fd/<spool> after the first pass), `kept` holds the spools alive.
+    const std::vector<std::string> original(in, in + mates);
+    std::vector<std::string> eff(original);
+    std::vector<std::shared_ptr<InputReplay>> kept(mates);
+    in = eff.data();
+    auto can_restart = [&](const char* why) {
+        for (int m = 0; m < mates; ++m)
+            if (!rereadable(eff[m]))
+                throw std::runtime_error(std::string("input ") + original[m] + " is not a regular file and cannot be read a second time (" + why +
+                                         "); write it to a file first");
+    };
 
     for (int attempt = 0; attempt < 10; ++attempt) {
         auto job = std::make_unique<WholeJob>();
@@ -734,6 +746,9 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
         cfg.max_chunk_bytes = 1ull << 30;              // device segments of 1 GiB
         cfg.max_tag_len = 32u << tag_growth;
         cfg.byte_keys = byte_keys ? 1u : 0u;
+        // a pipe has no size to decide by and cannot be read twice: spool it (the reference writes its whole input to the
+        // temporary directory as sorted chunks, src/external_sort.hpp:104-113) - any size works, and so do restarts
+        if (policy == 0 && !sizes_known) discard = true;
         if (policy == 0 && !discard && sizes_known) {
             // resident needs the raw bytes + what discard needs anyway + staging for the output gather
             size_t free_b = 0;
@@ -775,10 +790,13 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
             }
         }
         if (out_of_device_memory) {       // the size estimate was too kind (a .gz that expands more than its head suggested)
-            check_restart_possible(in, mates, "the input does not fit into device memory");
+            can_restart("the input does not fit into device memory");
             discard = true;
             continue;
         }
+        if (discard)                       // every byte of a pipe is in its spool now: later attempts and error messages read that
+            for (int m = 0; m < mates; ++m)
+                if (replay[m]->spooling() && !rereadable(eff[m])) { kept[m] = replay[m]; eff[m] = kept[m]->proc_path(); }
         trace("input on the device");
         rc = fqd_finish(eng.get());
         if (rc == FQD_ERR_CUDA && !discard && policy == 0 && std::strstr(fqd_last_error(eng.get()), "out of memory") && rereadable(in[0]) && (mates == 1 || rereadable(in[1]))) {
@@ -794,10 +812,10 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
         }
         fqd_stats_t st;
         fqd_stats(eng.get(), &st);
-        if (st.err == FQD_ERR_SEQ_TOO_LONG) { check_restart_possible(in, mates, "a later sequence is longer than the key rows sized from the first block"); ++seq_growth; continue; }
-        if (st.err == FQD_ERR_CAPACITY) { check_restart_possible(in, mates, "the record tables could not be grown in place"); growth *= 2.0; continue; }
-        if (st.err == FQD_ERR_TAG_TOO_LONG) { check_restart_possible(in, mates, "an ID tag is longer than the tag rows"); ++tag_growth; continue; }
-        if (st.err == FQD_ERR_UNSUPPORTED_BYTE && !byte_keys) { check_restart_possible(in, mates, "a sequence holds a byte outside {A,C,G,T,N}: raw-byte key rows are needed"); byte_keys = true; continue; }
+        if (st.err == FQD_ERR_SEQ_TOO_LONG) { can_restart("a later sequence is longer than the key rows sized from the first block"); ++seq_growth; continue; }
+        if (st.err == FQD_ERR_CAPACITY) { can_restart("the record tables could not be grown in place"); growth *= 2.0; continue; }
+        if (st.err == FQD_ERR_TAG_TOO_LONG) { can_restart("an ID tag is longer than the tag rows"); ++tag_growth; continue; }
+        if (st.err == FQD_ERR_UNSUPPORTED_BYTE && !byte_keys) { can_restart("a sequence holds a byte outside {A,C,G,T,N}: raw-byte key rows are needed"); byte_keys = true; continue; }
         // parse errors surface while the inputs are being sorted, before any output file exists
         // (src/seq_dup_remover.hpp:44-50, src/hash_dup_remover.hpp:160-174)
         if (st.err == FQD_ERR_LEN_MISMATCH) {

@@ -95,6 +95,9 @@ public:
     }
     const char* data() const { return m_p; }
     size_t size() const { return m_n; }
+    // A name under which the (unlinked) spool can be opened again while this object lives: a job that has to start over
+    // - wider key rows, byte keys, longer tags - reads a pipe's bytes from here the second time.
+    std::string proc_path() const { return "/proc/self/fd/" + std::to_string(m_fd); }
 
 private:
     int m_fd = -1;

@@ -40,11 +40,12 @@ jobs = [["-i", plain, "-o", tmp + "/c.fq", "--fast"], ["-i", plain, "-o", tmp + 
         ["-i", single, "-u", bg, "-o", tmp + "/c1.fq", "-p", tmp + "/c2.fq", "--compare-seq", "loose"]]
 for job in jobs:
     for block in ("262144", "33554432"):
-        env = dict(os.environ, LD_LIBRARY_PATH=os.path.abspath("tests/fake_engine/_build"), FQD_IO_THREADS="6", FQD_BLOCK_BYTES=block,
-                   FQD_ORDERLY_EXIT="1", **small)
-        r = subprocess.run(["/tmp/fqd_cli_tsan", *job], capture_output=True, env=env)
-        assert r.returncode == 0, r.stderr[-500:]
-        reports += r.stderr.count(b"WARNING: ThreadSanitizer")
+        for policy in ("resident", "discard"):      # whole-input modes: device gather / host gather from the mapped file or the spool
+            env = dict(os.environ, LD_LIBRARY_PATH=os.path.abspath("tests/fake_engine/_build"), FQD_IO_THREADS="6", FQD_BLOCK_BYTES=block,
+                       FQD_ORDERLY_EXIT="1", FQD_WHOLE_INPUT=policy, **small)
+            r = subprocess.run(["/tmp/fqd_cli_tsan", *job], capture_output=True, env=env)
+            assert r.returncode == 0, r.stderr[-500:]
+            reports += r.stderr.count(b"WARNING: ThreadSanitizer")
 print("ThreadSanitizer reports:", reports)
 rng = random.Random(99)
 P = payloads()

@@ -149,3 +149,57 @@ def test_large_windows(tmp_path, oracle):
     assert (tmp_path / "o.fa").read_bytes() == e1
     cl, _ = oracle.cluster_text("tight", oracle.FASTA, buf)
     assert (tmp_path / "o.fa.clusters").read_bytes() == cl[0]
+
+
+def _feed(path, data):
+    def go():
+        with open(path, "wb") as f:
+            f.write(data)
+    t = threading.Thread(target=go)
+    t.start()
+    return t
+
+
+@pytest.mark.parametrize("mode", ["tight", "tail-hamming"])
+def test_pipe_input_survives_a_restart(tmp_path, oracle, monkeypatch, mode):
+    """A FIFO cannot be read twice, its spool can: lower-case bases force the byte-key restart, a late long sequence the
+    wider rows - both read the pipe's bytes from /proc/self/fd/<spool> the second time.  No FQD_WHOLE_INPUT: a pipe is
+    spooled by default."""
+    import random
+    monkeypatch.delenv("FQD_WHOLE_INPUT")
+    rng = random.Random(11)
+    seqs = [bytes(rng.choice(b"ACGTNacgt") for _ in range(rng.choice([20, 25]))) for _ in range(60)]
+    reads = [rng.choice(seqs) for _ in range(3000)] + [bytes(rng.choice(b"ACGT") for _ in range(130))] * 3
+    buf = synth.to_fastq(reads)
+    os.mkfifo(tmp_path / "in.fifo")
+    t = _feed(tmp_path / "in.fifo", buf)
+    res = run("-i", tmp_path / "in.fifo", "-o", tmp_path / "o.fq", "--compare-seq", mode, "-v", "--write-clusters",
+              env={"FQD_BLOCK_BYTES": str(1 << 14), "FQD_TRACE": "1"})
+    t.join(timeout=60)
+    assert res.returncode == 0, res.stderr
+    assert res.stderr.count("raw input not kept") >= 2          # at least one restart happened, on the spool
+    e1, _, est = oracle.run_oracle(mode, oracle.FASTQ, buf)
+    assert (tmp_path / "o.fq").read_bytes() == e1
+    cl, _ = oracle.cluster_text(mode, oracle.FASTQ, buf)
+    assert (tmp_path / "o.fq.clusters").read_bytes() == cl[0]
+    assert res.stdout == f"{est.total} reads processed, out of which {est.dups} duplicates were removed.\n"
+    assert sorted(p.name for p in tmp_path.iterdir()) == ["in.fifo", "o.fq", "o.fq.clusters"]      # the spool left nothing behind
+
+
+def test_pipe_input_length_mismatch_quotes_the_record(tmp_path, oracle, monkeypatch):
+    """The reference's message for len(seq) != len(qual) quotes both strings; with a pipe the record is fetched from the spool."""
+    if not oracle.ref_available(stable=True):
+        pytest.skip("oracle/_ref not built")
+    monkeypatch.delenv("FQD_WHOLE_INPUT")
+    from test_cli_host_logic import _damage, _records
+    recs = _records(40, seed=12, mate=1)
+    recs[23] = _damage(recs[23], "length")
+    buf = b"".join(recs)
+    (tmp_path / "a.fq").write_bytes(buf)
+    ref = subprocess.run([str(oracle.REF_STABLE_BIN), "-i", "a.fq", "-o", "r.fq", "--compare-seq", "tight", "-v"], capture_output=True, text=True, cwd=tmp_path)
+    os.mkfifo(tmp_path / "in.fifo")
+    t = _feed(tmp_path / "in.fifo", buf)
+    res = run("-i", tmp_path / "in.fifo", "-o", tmp_path / "o.fq", "--compare-seq", "tight", "-v", env={"FQD_BLOCK_BYTES": "4096"})
+    t.join(timeout=60)
+    assert (res.returncode, res.stdout, res.stderr) == (ref.returncode, ref.stdout, ref.stderr)
+    assert (tmp_path / "o.fq").exists() == (tmp_path / "r.fq").exists()
