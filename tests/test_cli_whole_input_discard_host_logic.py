@@ -203,3 +203,73 @@ def test_pipe_input_length_mismatch_quotes_the_record(tmp_path, oracle, monkeypa
     t.join(timeout=60)
     assert (res.returncode, res.stdout, res.stderr) == (ref.returncode, ref.stdout, ref.stderr)
     assert (tmp_path / "o.fq").exists() == (tmp_path / "r.fq").exists()
+
+
+def test_many_tiny_jobs_match_the_reference_binary(tmp_path, oracle):
+    """200 random tiny jobs through the binary on the discarded-input path - every --compare-seq mode and --fast --unordered,
+    single- and paired-end, FASTQ and FASTA, inputs plain (mapped) or .gz (spooled) by turns, cluster files - against the
+    reference binaries: exit status, -v line, output bytes, <out>.clusters.  Records of length 0-6 built from three base
+    sequences by cutting prefixes and substituting bases: dense in the relations the comparators look at, and in ties."""
+    import random
+    import shutil
+    if not oracle.ref_available(stable=True):
+        pytest.skip("oracle/_ref not built")
+    rng = random.Random(23)
+
+    def text(seqs, mate, fasta, tags=None):
+        ids = tags if tags is not None else [b"r%d" % i for i in range(len(seqs))]
+        if fasta:
+            return b"".join(b">RUN." + t + b" %d\n" % mate + s + b"\n" for t, s in zip(ids, seqs))
+        return b"".join(b"@RUN." + t + b" %d\n" % mate + s + b"\n+\n" + b"I" * len(s) + b"\n" for t, s in zip(ids, seqs))
+    for it in range(200):
+        k = rng.randrange(1, 10)
+        base = ["".join(rng.choice("ACGTN") for _ in range(rng.choice([0, 1, 2, 3, 3, 4, 4, 5, 6]))).encode() for _ in range(3)]
+
+        def pick():
+            s = rng.choice(base)
+            r = rng.random()
+            if r < 0.3 and s:
+                s = s[:rng.randrange(0, len(s) + 1)]
+            elif r < 0.5 and s:
+                j = rng.randrange(len(s))
+                s = s[:j] + bytes([rng.choice(b"ACGT")]) + s[j + 1:]
+            return s
+        unordered = rng.random() < 0.25
+        paired = unordered or rng.random() < 0.5
+        fasta = rng.random() < 0.3
+        s1 = [pick() for _ in range(k)]
+        s2 = [pick() for _ in range(k)] if paired else None
+        t1 = t2 = None
+        if unordered:                    # tags from a small pool, both files sorted differently, some without a partner
+            t1 = [b"%02d" % rng.randrange(12) for _ in range(k)]
+            t2 = [b"%02d" % rng.randrange(12) for _ in range(k)]
+        d = tmp_path / "w"
+        shutil.rmtree(d, ignore_errors=True)
+        d.mkdir()
+        b1 = text(s1, 1, fasta, t1)
+        b2 = text(s2, 2, fasta, t2) if paired else None
+        gz = [rng.random() < 0.4, rng.random() < 0.4]
+        names = ["a.gz" if gz[0] else "a", "b.gz" if gz[1] else "b"]
+        (d / "a").write_bytes(b1)
+        (d / names[0]).write_bytes(gzip.compress(b1) if gz[0] else b1)
+        if paired:
+            (d / "b").write_bytes(b2)
+            (d / names[1]).write_bytes(gzip.compress(b2) if gz[1] else b2)
+        if unordered:
+            flags, ref_bin, clusters = ["--fast", "--unordered"], oracle.REF_BIN, False
+        else:
+            mode = rng.choice(["tight", "loose", "tail-hamming"])
+            clusters = rng.random() < 0.5
+            flags = ["--compare-seq", mode, "--distance", str(rng.choice([0, 1, 2, 3]))] + (["--write-clusters"] if clusters else [])
+            ref_bin = oracle.REF_STABLE_BIN
+        common = ["-v", "--format", "fasta" if fasta else "fastq", *flags]
+        io_r = ["-i", "a", "-o", "r1"] + (["-u", "b", "-p", "r2"] if paired else [])
+        io_o = ["-i", d / names[0], "-o", d / "o1"] + (["-u", d / names[1], "-p", d / "o2"] if paired else [])
+        ref = subprocess.run([str(ref_bin), *io_r, *common], capture_output=True, text=True, cwd=d)
+        ours = run(*io_o, *common, env={"FQD_BLOCK_BYTES": "4096"})
+        where = (it, flags, paired, fasta, gz)
+        assert (ours.returncode, ours.stdout, ours.stderr) == (ref.returncode, ref.stdout, ref.stderr), where
+        for mine, theirs in (("o1", "r1"), ("o2", "r2"), ("o1.clusters", "r1.clusters"), ("o2.clusters", "r2.clusters")):
+            assert (d / mine).exists() == (d / theirs).exists(), (where, mine)
+            if (d / mine).exists():
+                assert (d / mine).read_bytes() == (d / theirs).read_bytes(), (where, mine)
