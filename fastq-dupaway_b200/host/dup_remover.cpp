@@ -779,14 +779,35 @@ void run_whole_input(int mode, bool fasta, bool unordered, unsigned dist, int ma
         // ship every block to the device (the sort/join needs the whole input; nothing is kept on the host)
         bool out_of_device_memory = false;
         for (int m = 0; m < mates && !out_of_device_memory; ++m) {
+            // a spooled input is written behind the caller's back, like an output: the block goes to the device, then to the
+            // spool's ordered writer (several workers pwrite it), and returns to its reader when that is done
+            std::unique_ptr<OutputFile> spool_file;
+            std::unique_ptr<AsyncWriter> spool;
+            if (discard && replay[m]->spooling()) {
+                spool_file.reset(new OutputFile(replay[m]->proc_path()));
+                spool.reset(new AsyncWriter(*spool_file));
+            }
             Block* b = first[m];
             while (b) {
                 rc = fqd_append(eng.get(), m, b->data(), b->len);
                 if (rc == FQD_ERR_CUDA && !discard && policy == 0 && std::strstr(fqd_last_error(eng.get()), "out of memory")) { out_of_device_memory = true; break; }
                 if (rc) throw_engine_error(eng.get(), rc);
-                if (discard) replay[m]->add(b->data(), b->len);
-                readers[m]->release(b);
+                if (spool) {
+                    BlockReader* rd = readers[m].get();
+                    spool->write_runs(b->data(), std::vector<Run>{Run{0, b->len, 0}}, b->len);
+                    spool->then([rd, b] { rd->release(b); });
+                } else {
+                    readers[m]->release(b);
+                }
                 b = readers[m]->next();
+            }
+            if (spool) {
+                spool->drain();
+                spool.reset();
+                spool_file->close();
+                if (int e = spool_file->error())
+                    throw std::runtime_error(std::string("writing the input spool failed: ") + std::strerror(e) +
+                                             " (set FQD_SPOOL_DIR to a directory with room for the uncompressed input)");
             }
         }
         if (out_of_device_memory) {       // the size estimate was too kind (a .gz that expands more than its head suggested)

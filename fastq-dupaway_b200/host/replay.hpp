@@ -4,8 +4,9 @@
 // external sort - sorted chunks of 2/3 memlimit written to `<tmp>/chunks/<k>.tmp` and merged from disk
 // (src/external_sort.hpp:88-117,120-207; src/file_utils.cpp:116-130 creates and removes the temporary directory).
 // Here: a plain regular file is simply mapped (nothing is written); anything that can be read only once or is not the
-// bytes themselves (a pipe, a FIFO, a ".gz") is SPOOLED - every inflated block is appended to an unlinked temporary
-// file while it streams to the device - and that file is mapped afterwards.  Host memory stays what -m allows: the
+// bytes themselves (a pipe, a FIFO, a ".gz") is SPOOLED - every inflated block is written to an unlinked temporary
+// file (by an ordered asynchronous writer, several workers per block) while it streams to the device - and that file
+// is mapped afterwards.  Host memory stays what -m allows: the
 // mappings are page cache, which the kernel drops under pressure.
 #pragma once
 #include <fcntl.h>
@@ -51,24 +52,12 @@ public:
     InputReplay& operator=(const InputReplay&) = delete;
 
     bool spooling() const { return m_spooling; }
-    // spooling only: the next stretch of (inflated) input, in input order
-    void add(const char* p, size_t n) {
-        if (!m_spooling) return;
-        while (n) {
-            const ssize_t w = ::write(m_fd, p, n);
-            if (w < 0 && errno == EINTR) continue;
-            if (w <= 0) throw std::runtime_error(std::string("writing the input spool failed: ") + std::strerror(w < 0 ? errno : EIO) + " (set FQD_SPOOL_DIR to a directory with room for the uncompressed input)");
-            p += w; n -= (size_t)w; m_n += (size_t)w;
-        }
-    }
-    // the input is complete: map it
+    // the input is complete (and, when spooling, written through proc_path() by the driver's ordered writer): map it
     void seal() {
         if (m_p) return;
-        if (!m_spooling) {
-            struct stat sb;
-            if (fstat(m_fd, &sb) != 0) throw std::runtime_error("fstat failed on the input");
-            m_n = (size_t)sb.st_size;
-        }
+        struct stat sb;
+        if (fstat(m_fd, &sb) != 0) throw std::runtime_error("fstat failed on the input");
+        m_n = (size_t)sb.st_size;
         if (m_n == 0) return;
         void* p = ::mmap(nullptr, m_n, PROT_READ, MAP_SHARED, m_fd, 0);
         if (p == MAP_FAILED) throw std::runtime_error(std::string("cannot map the input for the output gather: ") + std::strerror(errno));
