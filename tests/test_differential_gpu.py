@@ -105,3 +105,15 @@ def test_unordered_discarded_input(tmp_path, oracle, monkeypatch):
 def test_whole_input_malformed_discarded_input(tmp_path, oracle, monkeypatch, mode, unordered):
     monkeypatch.setattr(whole_suite, "run", _discard_run)
     whole_suite.test_malformed_record_in_whole_input_modes_matches_the_reference_binary(tmp_path, oracle, mode, unordered)
+
+
+# ---- pipes: no size, read once - spooled by default, the spool is what a restart reads ----------------------------------
+def test_fifo_in_and_out_of_a_sequence_mode(tmp_path, oracle):
+    whole_suite.test_fifo_input_and_fifo_output_in_a_sequence_mode(tmp_path, oracle)
+
+
+def test_pipe_input_is_spooled_and_survives_a_restart(tmp_path, oracle, monkeypatch):
+    import test_cli_whole_input_discard_host_logic as discard_suite
+    monkeypatch.setattr(discard_suite, "run", _real_run)
+    monkeypatch.setenv("FQD_WHOLE_INPUT", "unset-by-the-test")
+    discard_suite.test_pipe_input_survives_a_restart(tmp_path, oracle, monkeypatch, "tail-hamming")
