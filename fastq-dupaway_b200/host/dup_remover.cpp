@@ -208,11 +208,18 @@ size_t resident_bytes_per_record(const fqd_config& cfg, int mates) {
     return b;
 }
 
+// FQD_LIST_WINDOW: records per list window (test knob: small jobs then cross many windows)
+uint64_t list_window() {
+    const char* e = std::getenv("FQD_LIST_WINDOW");
+    const long long v = e ? std::atoll(e) : 0;
+    return v > 0 ? (uint64_t)v : (uint64_t)1 << 20;
+}
+
 // The written records of one mate, fetched from the host's copy of the input in emission order: the lists come from
 // the device window by window, a window's records are gathered and written by the output file's workers (write_runs:
 // several at once, each at the file offset its bytes belong to) while the next window's lists arrive.
 void gather_from_replay(fqd_handle* eng, int m, uint64_t n_written, const InputReplay& src, OutputFile& out) {
-    constexpr uint64_t WIN = 1u << 20;
+    const uint64_t WIN = list_window();
     std::vector<uint64_t> off((size_t)std::min<uint64_t>(WIN, std::max<uint64_t>(n_written, 1)));
     std::vector<uint32_t> len(off.size());
     std::mutex mu; std::condition_variable cv; int in_flight = 0;
@@ -241,7 +248,7 @@ void gather_from_replay(fqd_handle* eng, int m, uint64_t n_written, const InputR
 // one line per record in sorted order, the ID line of a written record, "--" + the ID line of a removed one.
 void clusters_from_replay(fqd_handle* eng, int m, uint64_t n_sorted, const InputReplay& src, const std::string& out_name) {
     std::ofstream cf(out_name + ".clusters", std::ios::binary);
-    constexpr uint64_t WIN = 1u << 20;
+    const uint64_t WIN = list_window();
     std::vector<uint64_t> off((size_t)std::min<uint64_t>(WIN, std::max<uint64_t>(n_sorted, 1)));
     std::vector<uint32_t> len(off.size());
     std::vector<uint8_t> head(off.size());

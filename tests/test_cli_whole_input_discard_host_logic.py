@@ -137,15 +137,17 @@ def test_gz_and_pipe_outputs(tmp_path, oracle):
     assert got["out"] == e2
 
 
-def test_large_windows(tmp_path, oracle):
-    """More written records than one list window (2^20): several windows in flight behind the asynchronous writer."""
-    seqs = synth.make_reads(1_300_000, seed=8, read_len=24, dup_frac=0.1)
+def test_many_list_windows(tmp_path, oracle):
+    """More written records than one list window (FQD_LIST_WINDOW shrinks the 2^20 of production): dozens of windows, three
+    in flight behind the asynchronous writer, records and cluster lines gathered window by window."""
+    seqs = synth.make_reads(40_000, seed=8, read_len=24, dup_frac=0.1)
     buf = synth.to_fasta(seqs)
     (tmp_path / "a.fa").write_bytes(buf)
-    res = run("-i", tmp_path / "a.fa", "-o", tmp_path / "o.fa", "--format", "fasta", "--compare-seq", "tight", "-v", "--write-clusters")
+    res = run("-i", tmp_path / "a.fa", "-o", tmp_path / "o.fa", "--format", "fasta", "--compare-seq", "tight", "-v", "--write-clusters",
+              env={"FQD_LIST_WINDOW": "777"})
     assert res.returncode == 0, res.stderr
     e1, _, est = oracle.run_oracle("tight", oracle.FASTA, buf)
-    assert est.total - est.dups > (1 << 20)
+    assert est.total - est.dups > 30 * 777
     assert (tmp_path / "o.fa").read_bytes() == e1
     cl, _ = oracle.cluster_text("tight", oracle.FASTA, buf)
     assert (tmp_path / "o.fa.clusters").read_bytes() == cl[0]
